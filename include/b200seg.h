@@ -1,0 +1,123 @@
+/* b200seg.h -- C ABI of the B200-native segmentation hot path (libb200seg.so).
+ *
+ * Drop-in boundary for ONE path of taintpro98/rnd-semantic-segmentation: the DeepLabV2 ASPP
+ * classifier head, align-corners upsample fused with (hard / soft-label) cross-entropy, and the
+ * eval argmax + confusion-matrix.  The reference is pure Python/PyTorch and has no FFI of its own;
+ * each entry point below names the reference call (file:line under the reference root) whose
+ * arithmetic it replaces, and INTEGRATION.md shows the ctypes stubs a maintainer binds them with.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every data pointer is a DEVICE pointer unless the name ends in
+ *    "_host"; tensors are contiguous, fp32 NCHW / int64 NHW exactly as the reference passes them;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *    enqueued asynchronously on it, no hidden synchronisation, no hidden allocation: scratch is
+ *    caller-provided and sized by the *_bytes() queries;
+ *  - return value 0 = success; non-zero = error, message via b200seg_last_error() (thread-local);
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef B200SEG_H_
+#define B200SEG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SEG_ABI_VERSION 1
+#if defined(__GNUC__)
+#define B200SEG_API __attribute__((visibility("default")))
+#else
+#define B200SEG_API
+#endif
+
+B200SEG_API int b200seg_abi_version(void);
+B200SEG_API const char* b200seg_last_error(void);
+/* number of SMs of the current device (148 on B200); <0 on error */
+B200SEG_API int b200seg_device_sms(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  eval: upsample -> argmax(softmax) -> confusion matrix
+ *   replaces  F.interpolate(align_corners=True) + F.softmax   core/utils/utility.py:185-186
+ *             output.max(1)[1]                                 core/testers/aspp_tester.py:63
+ *             confusion_matrix(cfg, pd, gt)                    core/utils/utility.py:347-359
+ *   logits [N,C,h,w] f32; labels [N,H,W] i64 (may be NULL if cm is NULL);
+ *   cm: i64, ACCUMULATED into; frame n adds into cm + n*cm_frame_stride (0 => one shared [C,C]);
+ *   pred: optional i64 [N,H,W] argmax labels (bit-exact with the reference on CUDA);
+ *   fma_mode: 0 = default (matches ATen's compiled expression); 1..3 = diagnostic variants.
+ * ------------------------------------------------------------------------------------------- */
+B200SEG_API int b200seg_upsample_argmax_confusion(const float* logits, int N, int C, int h, int w, const int64_t* labels, int H,
+                                      int W, int ignore_index, int64_t* cm, int64_t cm_frame_stride, int64_t* pred,
+                                      int fma_mode, void* stream);
+
+/* confusion matrix from a materialised prediction map (API-compat form of utility.py:347-359);
+ * mutate_pd != 0 also writes pd[i] = ignore_index where gt[i] == ignore_index, as
+ * intersectionAndUnionGPU does to its `output` argument (utility.py:154). */
+B200SEG_API int b200seg_confusion_from_pred(int64_t* pd, const int64_t* gt, int64_t n, int C, int ignore_index, int mutate_pd,
+                                int64_t* cm, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  upsample + softmax cross-entropy (ignore_index) forward, gradient w.r.t. low-res logits
+ *   replaces  F.interpolate(...)                         core/models/classifiers/aspp/classifier.py:30-31
+ *             .div(temperature)                          core/combos/aspp_fada.py:93-94
+ *             CrossEntropyLoss(ignore_index=255)(o, y)   core/trainers/aspp_trainer.py:61,91
+ *             loss.backward()                            core/trainers/aspp_trainer.py:92
+ *   loss_out2: float[2] = { mean loss over valid pixels (NaN if none), number of valid pixels }.
+ *   forward with need_grad != 0 leaves per-tile partial gradients in `workspace`; backward turns
+ *   them into grad_logits [N,C,h,w] scaled by grad_out[0] (device scalar, NULL => 1).
+ * ------------------------------------------------------------------------------------------- */
+B200SEG_API int64_t b200seg_upsample_ce_workspace_bytes(int N, int C, int h, int w, int H, int W);
+B200SEG_API int b200seg_upsample_ce_forward(const float* logits, int N, int C, int h, int w, const int64_t* labels, int H, int W,
+                                int ignore_index, float inv_temperature, int need_grad, void* workspace,
+                                int64_t workspace_bytes, float* loss_out2, void* stream);
+B200SEG_API int b200seg_upsample_ce_backward(const void* workspace, int N, int C, int h, int w, int H, int W,
+                                 float inv_temperature, const float* loss_out2, const float* grad_out,
+                                 float* grad_logits, void* stream);
+
+/* materialising align-corners bilinear upsample and its adjoint ([NC,h,w] <-> [NC,H,W], f32)
+ *   replaces  F.interpolate(..., mode='bilinear', align_corners=True)   classifier.py:31, discriminator.py:49 */
+B200SEG_API int b200seg_upsample_bilinear_forward(const float* in, float* out, int NC, int h, int w, int H, int W, int fma_mode,
+                                      void* stream);
+B200SEG_API int b200seg_upsample_bilinear_backward(const float* grad_out, float* grad_in, int NC, int h, int w, int H, int W,
+                                       void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3  soft-label cross-entropy on materialised [N,K,H,W] f32 operands
+ *   replaces  soft_label_cross_entropy(pred, soft_label, pixel_weights)   core/utils/utility.py:172-177
+ *   weights: optional [N,H,W] f32 (NULL => none).  loss_out: float[1].
+ * ------------------------------------------------------------------------------------------- */
+B200SEG_API int64_t b200seg_soft_ce_workspace_bytes(void);
+B200SEG_API int b200seg_soft_ce_forward(const float* pred, const float* soft, const float* weights, int N, int K, int H, int W,
+                            void* workspace, int64_t workspace_bytes, float* loss_out, void* stream);
+B200SEG_API int b200seg_soft_ce_backward(const float* pred, const float* soft, const float* weights, const float* grad_out, int N,
+                             int K, int H, int W, float* grad_pred, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  fused multi-dilation ASPP head (tcgen05 tap-packed GEMMs)
+ *   replaces  ASPP_Classifier_V2.forward (size=None part)   core/models/classifiers/aspp/classifier.py:26-29
+ *   R dilation branches (padding == dilation), weights R x [C,Cin,3,3] f32, biases R x [C] f32.
+ *   NJ = b200seg_aspp_packed_rows(C, R): rows of the packed weight matrix ((8R+1)*C rounded to 128).
+ *   Packed operands are bf16:  Wp [NJ,Cin], WpT [Cin,NJ], Xp [N*h*w, Cin].
+ *   `weights`/`biases`/`grad_w`/`grad_b` are HOST arrays of R device pointers.
+ * ------------------------------------------------------------------------------------------- */
+B200SEG_API int b200seg_aspp_packed_rows(int C, int R);
+B200SEG_API int b200seg_aspp_pack_weights(const float* const* weights, const float* const* biases, int R, int C, int Cin, void* Wp,
+                              void* WpT, float* bias_sum, void* stream);
+B200SEG_API int b200seg_aspp_pack_features(const float* x_nchw, int N, int Cin, int h, int w, void* Xp, void* stream);
+B200SEG_API int64_t b200seg_aspp_forward_scratch_bytes(int N, int C, int h, int w, int R);
+B200SEG_API int b200seg_aspp_forward(const void* Xp, const void* Wp, const float* bias_sum, const int* rates_host, int R, int N,
+                         int Cin, int C, int h, int w, void* scratch, float* logits, void* stream);
+B200SEG_API int64_t b200seg_aspp_backward_scratch_bytes(int N, int Cin, int C, int h, int w, int R, int splits);
+/* grad_x (f32 NCHW, may be NULL), grad_w[r] / grad_b[r] (may be NULL) are overwritten, not accumulated */
+B200SEG_API int b200seg_aspp_backward(const float* grad_logits, const void* Xp, const void* WpT, const int* rates_host, int R, int N,
+                          int Cin, int C, int h, int w, void* scratch, int64_t scratch_bytes, int splits, float* grad_x,
+                          float* const* grad_w, float* const* grad_b, void* stream);
+
+/* on-device self-test of the tcgen05 GEMM core against a CUDA-core reference (synchronous) */
+B200SEG_API int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b_mn_major, int splits, int col_hw, double* max_err,
+                          double* max_ref);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SEG_H_ */

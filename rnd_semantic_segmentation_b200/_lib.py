@@ -1,0 +1,364 @@
+"""ctypes binding of libb200seg.so (C ABI declared in include/b200seg.h).
+
+PyTorch is used for device memory and streams only: every wrapper below takes
+CUDA tensors, checks dtype / contiguity / device, and hands raw device pointers
+plus the current CUDA stream to the C entry point.  There is no CPU fallback:
+a missing library or a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libb200seg.so")
+_lib = None
+
+c_int, c_i64, c_f32, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+# name -> (restype, argtypes); must list every symbol include/b200seg.h declares
+SIGNATURES = {
+    "b200seg_abi_version": (c_int, []),
+    "b200seg_last_error": (ctypes.c_char_p, []),
+    "b200seg_device_sms": (c_int, []),
+    "b200seg_upsample_argmax_confusion": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp, c_i64,
+                                                  c_vp, c_int, c_vp]),
+    "b200seg_confusion_from_pred": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp]),
+    "b200seg_upsample_ce_workspace_bytes": (c_i64, [c_int] * 6),
+    "b200seg_upsample_ce_forward": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_f32, c_int, c_vp,
+                                            c_i64, c_vp, c_vp]),
+    "b200seg_upsample_ce_backward": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp, c_vp]),
+    "b200seg_upsample_bilinear_forward": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "b200seg_upsample_bilinear_backward": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "b200seg_soft_ce_workspace_bytes": (c_i64, []),
+    "b200seg_soft_ce_forward": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_vp]),
+    "b200seg_soft_ce_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "b200seg_aspp_packed_rows": (c_int, [c_int, c_int]),
+    "b200seg_aspp_pack_weights": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "b200seg_aspp_pack_features": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "b200seg_aspp_forward_scratch_bytes": (c_i64, [c_int] * 5),
+    "b200seg_aspp_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "b200seg_aspp_backward_scratch_bytes": (c_i64, [c_int] * 7),
+    "b200seg_aspp_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64, c_int,
+                                      c_vp, c_vp, c_vp, c_vp]),
+    "b200seg_gemm_selftest": (c_int, [c_int] * 7 + [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+}
+
+
+class B200SegError(RuntimeError):
+    pass
+
+
+def load(build_if_missing: bool = False) -> ctypes.CDLL:
+    """Load the shared library (once).  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if build_if_missing:
+            from ._build_ext import build
+            build()
+        else:
+            raise B200SegError(
+                f"{LIB_PATH} not found: build it with `python -m rnd_semantic_segmentation_b200._build_ext` "
+                "(or __graft_entry__.build()).  There is no CPU / PyTorch fallback for this path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    if lib.b200seg_abi_version() != 1:
+        raise B200SegError("libb200seg.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise B200SegError(load().b200seg_last_error().decode("utf-8", "replace"))
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise B200SegError(f"{name}: expected a CUDA tensor (b200seg has no CPU fallback), got device {t.device}")
+    if t.dtype != dtype:
+        raise B200SegError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise B200SegError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def device_sms() -> int:
+    return load().b200seg_device_sms()
+
+
+# --------------------------------------------------------------------------------------------
+# K4
+# --------------------------------------------------------------------------------------------
+def upsample_argmax_confusion(logits_lr: torch.Tensor, labels: Optional[torch.Tensor], size, num_classes: Optional[int] = None,
+                              ignore_index: int = 255, cm: Optional[torch.Tensor] = None, per_frame: bool = False,
+                              want_pred: bool = False, fma_mode: int = 0):
+    """Returns (cm, pred).  cm int64 [C,C] (or [N,C,C] if per_frame) accumulated in place when given."""
+    lib = load()
+    _need(logits_lr, torch.float32, "logits")
+    N, C, h, w = logits_lr.shape
+    H, W = int(size[0]), int(size[1])
+    if num_classes is not None and num_classes != C:
+        raise B200SegError(f"logits have {C} channels but num_classes={num_classes}")
+    if labels is not None:
+        _need(labels, torch.int64, "labels")
+        if labels.numel() != N * H * W:
+            raise B200SegError(f"labels shape {tuple(labels.shape)} does not match N*H*W = {N}*{H}*{W}")
+    stride = 0
+    if labels is not None:
+        if cm is None:
+            cm = torch.zeros((N, C, C) if per_frame else (C, C), dtype=torch.int64, device=logits_lr.device)
+        _need(cm, torch.int64, "cm")
+        stride = C * C if cm.dim() == 3 else 0
+    pred = torch.empty((N, H, W), dtype=torch.int64, device=logits_lr.device) if want_pred else None
+    with torch.cuda.device(logits_lr.device):
+        _check(lib.b200seg_upsample_argmax_confusion(logits_lr.data_ptr(), N, C, h, w, _ptr(labels), H, W, ignore_index,
+                                                     _ptr(cm) if labels is not None else None, stride, _ptr(pred), fma_mode,
+                                                     _stream()))
+    return cm, pred
+
+
+def confusion_from_pred(pd: torch.Tensor, gt: torch.Tensor, num_classes: int, ignore_index: int = 255,
+                        mutate_pd: bool = False, cm: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = load()
+    _need(pd, torch.int64, "pd")
+    _need(gt, torch.int64, "gt")
+    if pd.numel() != gt.numel():
+        raise B200SegError("pd and gt must have the same number of elements")
+    if cm is None:
+        cm = torch.zeros(num_classes, num_classes, dtype=torch.int64, device=pd.device)
+    _need(cm, torch.int64, "cm")
+    with torch.cuda.device(pd.device):
+        _check(lib.b200seg_confusion_from_pred(pd.data_ptr(), gt.data_ptr(), pd.numel(), num_classes, ignore_index,
+                                               1 if mutate_pd else 0, cm.data_ptr(), _stream()))
+    return cm
+
+
+# --------------------------------------------------------------------------------------------
+# K2 + materialising upsample
+# --------------------------------------------------------------------------------------------
+def upsample_ce_forward(logits_lr, labels, ignore_index=255, inv_temperature=1.0, need_grad=True):
+    """Returns (loss_and_count float32[2], workspace) -- workspace feeds upsample_ce_backward."""
+    lib = load()
+    _need(logits_lr, torch.float32, "logits")
+    _need(labels, torch.int64, "labels")
+    N, C, h, w = logits_lr.shape
+    H, W = labels.shape[-2:]
+    if labels.numel() != N * H * W:
+        raise B200SegError(f"labels shape {tuple(labels.shape)} does not match batch {N}")
+    nbytes = lib.b200seg_upsample_ce_workspace_bytes(N, C, h, w, H, W)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=logits_lr.device)
+    out2 = torch.empty(2, dtype=torch.float32, device=logits_lr.device)
+    with torch.cuda.device(logits_lr.device):
+        _check(lib.b200seg_upsample_ce_forward(logits_lr.data_ptr(), N, C, h, w, labels.data_ptr(), H, W, ignore_index,
+                                               float(inv_temperature), 1 if need_grad else 0, ws.data_ptr(), nbytes,
+                                               out2.data_ptr(), _stream()))
+    return out2, ws
+
+
+def upsample_ce_backward(ws, out2, shape_lr, size, inv_temperature=1.0, grad_out: Optional[torch.Tensor] = None):
+    lib = load()
+    N, C, h, w = shape_lr
+    H, W = size
+    if grad_out is not None:
+        grad_out = _need(grad_out.reshape(1).contiguous(), torch.float32, "grad_out")
+    grad = torch.empty((N, C, h, w), dtype=torch.float32, device=ws.device)
+    with torch.cuda.device(ws.device):
+        _check(lib.b200seg_upsample_ce_backward(ws.data_ptr(), N, C, h, w, H, W, float(inv_temperature), out2.data_ptr(),
+                                                _ptr(grad_out), grad.data_ptr(), _stream()))
+    return grad
+
+
+def upsample_bilinear_forward(x: torch.Tensor, size, fma_mode: int = 0) -> torch.Tensor:
+    lib = load()
+    _need(x, torch.float32, "input")
+    N, C, h, w = x.shape
+    H, W = int(size[0]), int(size[1])
+    out = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(lib.b200seg_upsample_bilinear_forward(x.data_ptr(), out.data_ptr(), N * C, h, w, H, W, fma_mode, _stream()))
+    return out
+
+
+def upsample_bilinear_backward(grad_out: torch.Tensor, in_hw) -> torch.Tensor:
+    lib = load()
+    grad_out = _need(grad_out.contiguous(), torch.float32, "grad_output")
+    N, C, H, W = grad_out.shape
+    h, w = in_hw
+    gin = torch.empty((N, C, h, w), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        _check(lib.b200seg_upsample_bilinear_backward(grad_out.data_ptr(), gin.data_ptr(), N * C, h, w, H, W, _stream()))
+    return gin
+
+
+# --------------------------------------------------------------------------------------------
+# K3
+# --------------------------------------------------------------------------------------------
+def soft_ce_forward(pred, soft, weights=None) -> torch.Tensor:
+    lib = load()
+    _need(pred, torch.float32, "pred")
+    _need(soft, torch.float32, "soft_label")
+    if pred.shape != soft.shape or pred.dim() != 4:
+        raise B200SegError(f"pred {tuple(pred.shape)} and soft_label {tuple(soft.shape)} must be equal 4-d shapes")
+    N, K, H, W = pred.shape
+    if weights is not None:
+        _need(weights, torch.float32, "pixel_weights")
+        if weights.numel() != N * H * W:
+            raise B200SegError("pixel_weights must have N*H*W elements")
+    nbytes = lib.b200seg_soft_ce_workspace_bytes()
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=pred.device)
+    out = torch.empty(1, dtype=torch.float32, device=pred.device)
+    with torch.cuda.device(pred.device):
+        _check(lib.b200seg_soft_ce_forward(pred.data_ptr(), soft.data_ptr(), _ptr(weights), N, K, H, W, ws.data_ptr(), nbytes,
+                                           out.data_ptr(), _stream()))
+    return out.reshape(())
+
+
+def soft_ce_backward(pred, soft, weights, grad_out) -> torch.Tensor:
+    lib = load()
+    N, K, H, W = pred.shape
+    grad_out = _need(grad_out.reshape(1).contiguous(), torch.float32, "grad_out")
+    grad = torch.empty_like(pred)
+    with torch.cuda.device(pred.device):
+        _check(lib.b200seg_soft_ce_backward(pred.data_ptr(), soft.data_ptr(), _ptr(weights), grad_out.data_ptr(), N, K, H, W,
+                                            grad.data_ptr(), _stream()))
+    return grad
+
+
+# --------------------------------------------------------------------------------------------
+# K1
+# --------------------------------------------------------------------------------------------
+def _ptr_array(tensors: Sequence[Optional[torch.Tensor]]):
+    arr = (c_vp * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+def aspp_packed_rows(C: int, R: int) -> int:
+    return load().b200seg_aspp_packed_rows(C, R)
+
+
+def aspp_pack_weights(weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]]):
+    """R x [C,Cin,3,3] fp32 (+ R x [C]) -> (Wp bf16 [NJ,Cin], WpT bf16 [Cin,NJ], bias_sum fp32 [C])."""
+    lib = load()
+    R = len(weights)
+    C, Cin = weights[0].shape[:2]
+    for wt in weights:
+        _need(wt, torch.float32, "conv weight")
+        if tuple(wt.shape) != (C, Cin, 3, 3):
+            raise B200SegError(f"conv weight shape {tuple(wt.shape)} != {(C, Cin, 3, 3)}")
+    for b in biases:
+        if b is not None:
+            _need(b, torch.float32, "conv bias")
+    dev = weights[0].device
+    NJ = lib.b200seg_aspp_packed_rows(C, R)
+    Wp = torch.empty((NJ, Cin), dtype=torch.bfloat16, device=dev)
+    WpT = torch.empty((Cin, NJ), dtype=torch.bfloat16, device=dev)
+    bias_sum = torch.empty(C, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.b200seg_aspp_pack_weights(_ptr_array(weights), _ptr_array(biases), R, C, Cin, Wp.data_ptr(), WpT.data_ptr(),
+                                             bias_sum.data_ptr(), _stream()))
+    return Wp, WpT, bias_sum
+
+
+def aspp_pack_features(x: torch.Tensor) -> torch.Tensor:
+    """fp32 NCHW [N,Cin,h,w] -> bf16 pixel-major [N*h*w, Cin]."""
+    lib = load()
+    _need(x, torch.float32, "features")
+    N, Cin, h, w = x.shape
+    Xp = torch.empty((N * h * w, Cin), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(lib.b200seg_aspp_pack_features(x.data_ptr(), N, Cin, h, w, Xp.data_ptr(), _stream()))
+    return Xp
+
+
+_scratch_cache = {}
+
+
+def _scratch(key, nbytes: int, device) -> torch.Tensor:
+    """Grow-only per-device scratch (stream-ordered reuse; contents never outlive one op)."""
+    k = (key, device.index if device.index is not None else torch.cuda.current_device())
+    t = _scratch_cache.get(k)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _scratch_cache[k] = t
+    return t
+
+
+def aspp_forward(Xp: torch.Tensor, Wp: torch.Tensor, bias_sum: torch.Tensor, rates: Sequence[int], N: int, h: int, w: int,
+                 C: int) -> torch.Tensor:
+    lib = load()
+    _need(Xp, torch.bfloat16, "Xp")
+    _need(Wp, torch.bfloat16, "Wp")
+    _need(bias_sum, torch.float32, "bias_sum")
+    Cin = Xp.shape[1]
+    R = len(rates)
+    if Xp.shape[0] != N * h * w:
+        raise B200SegError("Xp rows != N*h*w")
+    nbytes = lib.b200seg_aspp_forward_scratch_bytes(N, C, h, w, R)
+    scratch = _scratch("aspp_fwd", nbytes, Xp.device)
+    logits = torch.empty((N, C, h, w), dtype=torch.float32, device=Xp.device)
+    rates_arr = (c_int * R)(*[int(r) for r in rates])
+    with torch.cuda.device(Xp.device):
+        _check(lib.b200seg_aspp_forward(Xp.data_ptr(), Wp.data_ptr(), bias_sum.data_ptr(), rates_arr, R, N, Cin, C, h, w,
+                                        scratch.data_ptr(), logits.data_ptr(), _stream()))
+    return logits
+
+
+def aspp_backward(grad_logits: torch.Tensor, Xp: torch.Tensor, WpT: torch.Tensor, rates: Sequence[int], N: int, h: int, w: int,
+                  C: int, need_grad_x: bool = True, need_grad_w: bool = True, need_grad_b: bool = True, splits: int = 0):
+    """Returns (grad_x fp32 NCHW | None, [grad_w]*R | None, [grad_b]*R | None)."""
+    lib = load()
+    grad_logits = _need(grad_logits.contiguous(), torch.float32, "grad_logits")
+    Cin = Xp.shape[1]
+    R = len(rates)
+    dev = Xp.device
+    if splits <= 0:
+        splits = default_wgrad_splits(N * h * w, C, Cin, R)
+    nbytes = lib.b200seg_aspp_backward_scratch_bytes(N, Cin, C, h, w, R, splits)
+    scratch = _scratch("aspp_bwd", nbytes, dev)
+    gx = torch.empty((N, Cin, h, w), dtype=torch.float32, device=dev) if need_grad_x else None
+    gws = [torch.empty((C, Cin, 3, 3), dtype=torch.float32, device=dev) for _ in range(R)] if need_grad_w else None
+    gbs = [torch.empty(C, dtype=torch.float32, device=dev) for _ in range(R)] if need_grad_b else None
+    rates_arr = (c_int * R)(*[int(r) for r in rates])
+    with torch.cuda.device(dev):
+        _check(lib.b200seg_aspp_backward(grad_logits.data_ptr(), Xp.data_ptr(), WpT.data_ptr(), rates_arr, R, N, Cin, C, h, w,
+                                         scratch.data_ptr(), nbytes, splits, _ptr(gx),
+                                         _ptr_array(gws) if gws else None, _ptr_array(gbs) if gbs else None, _stream()))
+    return gx, gws, gbs
+
+
+def default_wgrad_splits(P: int, C: int, Cin: int, R: int) -> int:
+    """Split-K factor for the weight-gradient GEMM: fill ~2 waves of SMs without oversplitting."""
+    NJ = aspp_packed_rows(C, R)
+    tiles = ((NJ + 127) // 128) * ((Cin + 255) // 256)
+    kb = (P + 63) // 64
+    sms = 148
+    best = max(1, min(kb, (2 * sms + tiles - 1) // tiles))
+    return int(best)
+
+
+def gemm_selftest(M, N, K, a_mn=False, b_mn=False, splits=1, col_hw=0):
+    lib = load()
+    err, ref = ctypes.c_double(0), ctypes.c_double(0)
+    _check(lib.b200seg_gemm_selftest(M, N, K, int(a_mn), int(b_mn), splits, col_hw, ctypes.byref(err), ctypes.byref(ref)))
+    return err.value, ref.value

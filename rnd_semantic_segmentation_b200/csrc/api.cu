@@ -1,0 +1,188 @@
+// extern "C" boundary of libb200seg.so (declarations + reference citations: include/b200seg.h)
+#include <stdarg.h>
+#include <string.h>
+#include "../../include/b200seg.h"
+#include "common.cuh"
+
+namespace b200seg {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static int cached = 0;
+  if (cached <= 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      return 148;
+  }
+  return cached;
+}
+
+// kernels' host launchers (defined in the other translation units)
+int k4_launch(const float*, int, int, int, int, const long long*, int, int, int, long long*, long long, long long*, int, cudaStream_t);
+int confusion_pairs_launch(long long*, const long long*, long long, int, int, int, long long*, cudaStream_t);
+long long k2_workspace_bytes(int, int, int, int, int, int);
+int k2_forward(const float*, int, int, int, int, const long long*, int, int, int, float, int, void*, long long, float*, cudaStream_t);
+int k2_backward(const void*, int, int, int, int, int, int, float, const float*, const float*, float*, cudaStream_t);
+int upsample_fwd_launch(const float*, float*, int, int, int, int, int, int, cudaStream_t);
+int upsample_bwd_launch(const float*, float*, int, int, int, int, int, cudaStream_t);
+long long k3_workspace_bytes();
+int k3_forward(const float*, const float*, const float*, int, int, int, int, void*, long long, float*, cudaStream_t);
+int k3_backward(const float*, const float*, const float*, const float*, int, int, int, int, float*, cudaStream_t);
+int aspp_nj(int, int);
+int aspp_pack_weights(const float* const*, const float* const*, int, int, int, void*, void*, float*, cudaStream_t);
+int aspp_pack_features(const float*, int, int, int, int, void*, cudaStream_t);
+long long aspp_yt_bytes(int, int, int, int, int);
+int aspp_forward(const void*, const void*, const float*, const int*, int, int, int, int, int, int, float*, float*, cudaStream_t);
+long long aspp_bwd_scratch_bytes(int, int, int, int, int, int, int);
+int aspp_backward(const float*, const void*, const void*, const int*, int, int, int, int, int, int, void*, long long, int, float*,
+                  float* const*, float* const*, cudaStream_t);
+namespace gemm {
+int selftest(int, int, int, int, int, int, int, double*, double*);
+}
+
+static int require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    set_error("no CUDA device available (%s); b200seg has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return B200SEG_ERR_CUDA;
+  }
+  return B200SEG_OK;
+}
+
+}  // namespace b200seg
+
+using namespace b200seg;
+#define S(stream) reinterpret_cast<cudaStream_t>(stream)
+#define REQUIRE_DEVICE()                 \
+  do {                                   \
+    int rc__ = require_device();         \
+    if (rc__) return rc__;               \
+  } while (0)
+
+extern "C" {
+
+int b200seg_abi_version(void) { return B200SEG_ABI_VERSION; }
+const char* b200seg_last_error(void) { return g_err; }
+int b200seg_device_sms(void) {
+  if (require_device()) return -1;
+  return num_sms();
+}
+
+int b200seg_upsample_argmax_confusion(const float* logits, int N, int C, int h, int w, const int64_t* labels, int H, int W,
+                                      int ignore_index, int64_t* cm, int64_t cm_frame_stride, int64_t* pred, int fma_mode,
+                                      void* stream) {
+  REQUIRE_DEVICE();
+  return k4_launch(logits, N, C, h, w, reinterpret_cast<const long long*>(labels), H, W, ignore_index,
+                   reinterpret_cast<long long*>(cm), cm_frame_stride, reinterpret_cast<long long*>(pred), fma_mode, S(stream));
+}
+
+int b200seg_confusion_from_pred(int64_t* pd, const int64_t* gt, int64_t n, int C, int ignore_index, int mutate_pd, int64_t* cm,
+                                void* stream) {
+  REQUIRE_DEVICE();
+  return confusion_pairs_launch(reinterpret_cast<long long*>(pd), reinterpret_cast<const long long*>(gt), n, C, ignore_index,
+                                mutate_pd, reinterpret_cast<long long*>(cm), S(stream));
+}
+
+int64_t b200seg_upsample_ce_workspace_bytes(int N, int C, int h, int w, int H, int W) {
+  if (N <= 0 || C <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return 0;
+  return k2_workspace_bytes(N, C, h, w, H, W);
+}
+
+int b200seg_upsample_ce_forward(const float* logits, int N, int C, int h, int w, const int64_t* labels, int H, int W,
+                                int ignore_index, float inv_temperature, int need_grad, void* workspace, int64_t workspace_bytes,
+                                float* loss_out2, void* stream) {
+  REQUIRE_DEVICE();
+  return k2_forward(logits, N, C, h, w, reinterpret_cast<const long long*>(labels), H, W, ignore_index, inv_temperature,
+                    need_grad, workspace, workspace_bytes, loss_out2, S(stream));
+}
+
+int b200seg_upsample_ce_backward(const void* workspace, int N, int C, int h, int w, int H, int W, float inv_temperature,
+                                 const float* loss_out2, const float* grad_out, float* grad_logits, void* stream) {
+  REQUIRE_DEVICE();
+  return k2_backward(workspace, N, C, h, w, H, W, inv_temperature, loss_out2, grad_out, grad_logits, S(stream));
+}
+
+int b200seg_upsample_bilinear_forward(const float* in, float* out, int NC, int h, int w, int H, int W, int fma_mode, void* stream) {
+  REQUIRE_DEVICE();
+  return upsample_fwd_launch(in, out, NC, h, w, H, W, fma_mode, S(stream));
+}
+
+int b200seg_upsample_bilinear_backward(const float* grad_out, float* grad_in, int NC, int h, int w, int H, int W, void* stream) {
+  REQUIRE_DEVICE();
+  return upsample_bwd_launch(grad_out, grad_in, NC, h, w, H, W, S(stream));
+}
+
+int64_t b200seg_soft_ce_workspace_bytes(void) { return k3_workspace_bytes(); }
+
+int b200seg_soft_ce_forward(const float* pred, const float* soft, const float* weights, int N, int K, int H, int W, void* workspace,
+                            int64_t workspace_bytes, float* loss_out, void* stream) {
+  REQUIRE_DEVICE();
+  return k3_forward(pred, soft, weights, N, K, H, W, workspace, workspace_bytes, loss_out, S(stream));
+}
+
+int b200seg_soft_ce_backward(const float* pred, const float* soft, const float* weights, const float* grad_out, int N, int K, int H,
+                             int W, float* grad_pred, void* stream) {
+  REQUIRE_DEVICE();
+  return k3_backward(pred, soft, weights, grad_out, N, K, H, W, grad_pred, S(stream));
+}
+
+int b200seg_aspp_packed_rows(int C, int R) { return aspp_nj(C, R); }
+
+int b200seg_aspp_pack_weights(const float* const* weights, const float* const* biases, int R, int C, int Cin, void* Wp, void* WpT,
+                              float* bias_sum, void* stream) {
+  REQUIRE_DEVICE();
+  return aspp_pack_weights(weights, biases, R, C, Cin, Wp, WpT, bias_sum, S(stream));
+}
+
+int b200seg_aspp_pack_features(const float* x_nchw, int N, int Cin, int h, int w, void* Xp, void* stream) {
+  REQUIRE_DEVICE();
+  return aspp_pack_features(x_nchw, N, Cin, h, w, Xp, S(stream));
+}
+
+int64_t b200seg_aspp_forward_scratch_bytes(int N, int C, int h, int w, int R) {
+  if (N <= 0 || C <= 0 || h <= 0 || w <= 0 || R <= 0) return 0;
+  return aspp_yt_bytes(N, C, h, w, R);
+}
+
+int b200seg_aspp_forward(const void* Xp, const void* Wp, const float* bias_sum, const int* rates_host, int R, int N, int Cin, int C,
+                         int h, int w, void* scratch, float* logits, void* stream) {
+  REQUIRE_DEVICE();
+  return aspp_forward(Xp, Wp, bias_sum, rates_host, R, N, Cin, C, h, w, reinterpret_cast<float*>(scratch), logits, S(stream));
+}
+
+int64_t b200seg_aspp_backward_scratch_bytes(int N, int Cin, int C, int h, int w, int R, int splits) {
+  if (N <= 0 || C <= 0 || h <= 0 || w <= 0 || R <= 0) return 0;
+  return aspp_bwd_scratch_bytes(N, Cin, C, h, w, R, splits < 1 ? 1 : splits);
+}
+
+int b200seg_aspp_backward(const float* grad_logits, const void* Xp, const void* WpT, const int* rates_host, int R, int N, int Cin,
+                          int C, int h, int w, void* scratch, int64_t scratch_bytes, int splits, float* grad_x, float* const* grad_w,
+                          float* const* grad_b, void* stream) {
+  REQUIRE_DEVICE();
+  return aspp_backward(grad_logits, Xp, WpT, rates_host, R, N, Cin, C, h, w, scratch, scratch_bytes, splits, grad_x, grad_w, grad_b,
+                       S(stream));
+}
+
+int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b_mn_major, int splits, int col_hw, double* max_err,
+                          double* max_ref) {
+  REQUIRE_DEVICE();
+  if (!max_err || !max_ref) {
+    set_error("gemm_selftest: null output pointer");
+    return B200SEG_ERR_ARG;
+  }
+  return gemm::selftest(M, N, K, a_mn_major, b_mn_major, splits, col_hw, max_err, max_ref);
+}
+
+}  // extern "C"

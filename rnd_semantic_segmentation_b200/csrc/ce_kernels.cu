@@ -1,0 +1,467 @@
+// K2: align-corners bilinear upsample fused with softmax cross-entropy (ignore_index) forward
+//     AND the gradient with respect to the LOW-RESOLUTION logits, in one pass over the labels.
+//
+// Replaces (reference file:line):
+//   F.interpolate(out, size, 'bilinear', align_corners=True)     core/models/classifiers/aspp/classifier.py:30-31
+//   src_pred.div(temperature)                                    core/combos/aspp_fada.py:93-94
+//   torch.nn.CrossEntropyLoss(ignore_index=255)(output, label)   core/trainers/aspp_trainer.py:61,91
+//   loss.backward() through both                                 core/trainers/aspp_trainer.py:92
+//
+// The full-resolution logits (76 B/px at C=19) are never written.  Per output pixel the kernel
+// recomputes the C interpolated logits from register-resident horizontal lerps, does one
+// max / exp / sum pass, accumulates the loss, and folds softmax(v) - onehot(label) back onto
+// the two source rows (weights l0y, l1y) in registers.  At every change of source-row pair the
+// 128 columns of the tile are reduced onto their source columns through shared memory, into a
+// per-tile partial block [rows][cols][C] that is written to scratch WITHOUT atomics; a small
+// finalize kernel sums the <= 4 partial blocks that touch each low-res logit in a fixed order
+// and applies grad_out / (n_valid * T).  Results are therefore run-to-run deterministic (ATen's
+// upsample backward scatters with atomicAdd).
+//
+// Also here: materialising align-corners upsample forward / backward (the API-compat path for
+// callers that want the full-resolution tensor, e.g. PixelDiscriminator.forward(x, size)).
+#include "common.cuh"
+
+namespace b200seg {
+
+constexpr int K2_THREADS = 128;
+constexpr int K2_TILE_W = 128;
+constexpr int K2_TILE_H = 32;
+constexpr int K2_STRIP = 8;
+
+struct K2Geom {
+  int N, C, h, w, H, W;
+  int tiles_x, tiles_y;
+  int ispan_max, jspan_max;     // max number of source rows / cols touched by one tile
+  float scale_h, scale_w;
+};
+
+__host__ __device__ __forceinline__ int host_i0(float scale, int dst) { return (int)(scale * (float)dst); }
+
+static void k2_geometry(K2Geom& g, int N, int C, int h, int w, int H, int W) {
+  g.N = N; g.C = C; g.h = h; g.w = w; g.H = H; g.W = W;
+  g.tiles_x = ceil_div(W, K2_TILE_W);
+  g.tiles_y = ceil_div(H, K2_TILE_H);
+  g.scale_h = ac_scale(h, H);
+  g.scale_w = ac_scale(w, W);
+  g.ispan_max = 1; g.jspan_max = 1;
+  for (int ty = 0; ty < g.tiles_y; ++ty) {
+    const int ya = ty * K2_TILE_H, yb = (ya + K2_TILE_H < H ? ya + K2_TILE_H : H) - 1;
+    const int lo = host_i0(g.scale_h, ya);
+    int hi = host_i0(g.scale_h, yb); hi += (hi < h - 1) ? 1 : 0;
+    if (hi - lo + 1 > g.ispan_max) g.ispan_max = hi - lo + 1;
+  }
+  for (int tx = 0; tx < g.tiles_x; ++tx) {
+    const int xa = tx * K2_TILE_W, xb = (xa + K2_TILE_W < W ? xa + K2_TILE_W : W) - 1;
+    const int lo = host_i0(g.scale_w, xa);
+    int hi = host_i0(g.scale_w, xb); hi += (hi < w - 1) ? 1 : 0;
+    if (hi - lo + 1 > g.jspan_max) g.jspan_max = hi - lo + 1;
+  }
+}
+
+// Workspace layout (floats): [tiles] loss partial | [tiles] valid-count partial | [tiles][ispan][jspan][C] blocks
+static long long k2_block_floats(const K2Geom& g) { return (long long)g.ispan_max * g.jspan_max * g.C; }
+static long long k2_tiles(const K2Geom& g) { return (long long)g.N * g.tiles_x * g.tiles_y; }
+
+long long k2_workspace_bytes(int N, int C, int h, int w, int H, int W) {
+  K2Geom g;
+  k2_geometry(g, N, C, h, w, H, W);
+  return (2 * k2_tiles(g) + k2_tiles(g) * k2_block_floats(g)) * 4 + 256;
+}
+
+struct K2Params {
+  K2Geom g;
+  const float* logits;       // [N,C,h,w]
+  const long long* labels;   // [N,H,W]
+  int ignore_index;
+  float inv_T;
+  float* loss_part;          // [tiles]
+  float* cnt_part;           // [tiles]
+  float* blocks;             // [tiles][ispan_max][jspan_max][C]
+};
+
+template <int CT, bool GRAD>
+__global__ void __launch_bounds__(K2_THREADS) k2_upsample_ce_main(const K2Params p) {
+  extern __shared__ __align__(16) float k2_smem[];
+  const K2Geom& g = p.g;
+  const int C = g.C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // smem carve-up
+  float* stageA = k2_smem;                           // [CT][128]  (doubles as the -onehot accumulator)
+  float* stageB = stageA + CT * K2_THREADS;          // [CT][128]
+  float* blk = stageB + CT * K2_THREADS;             // [ispan_max][jspan_max][C]
+  const int blk_floats = g.ispan_max * g.jspan_max * C;
+  float* colw0 = blk + blk_floats;                   // [128] l0x
+  float* colw1 = colw0 + K2_THREADS;                 // [128] l1x
+  int* colx0 = reinterpret_cast<int*>(colw1 + K2_THREADS);   // [128] x0 - j_lo
+  int* colx1 = colx0 + K2_THREADS;                   // [128] x1 - j_lo
+  float* red = reinterpret_cast<float*>(colx1 + K2_THREADS);  // [8]
+
+  const int tile = blockIdx.x;
+  const int tiles_per_frame = g.tiles_x * g.tiles_y;
+  const int n = tile / tiles_per_frame;
+  const int trem = tile - n * tiles_per_frame;
+  const int ty = trem / g.tiles_x;
+  const int tx = trem - ty * g.tiles_x;
+  const long long hw = (long long)g.h * g.w;
+
+  const int x = tx * K2_TILE_W + tid;
+  const bool xvalid = x < g.W;
+  const Tap tapx = ac_tap(g.scale_w, xvalid ? x : g.W - 1, g.w);
+  const int j_lo = (int)(g.scale_w * (float)(tx * K2_TILE_W));
+  const int y_begin = ty * K2_TILE_H;
+  const int y_end = min(g.H, y_begin + K2_TILE_H);
+  const int i_lo = (int)(g.scale_h * (float)y_begin);
+
+  if (GRAD) {
+    for (int i = tid; i < blk_floats; i += K2_THREADS) blk[i] = 0.f;
+    for (int i = tid; i < 2 * CT * K2_THREADS; i += K2_THREADS) stageA[i] = 0.f;
+    colw0[tid] = xvalid ? tapx.l0 : 0.f;
+    colw1[tid] = xvalid ? tapx.l1 : 0.f;
+    colx0[tid] = tapx.i0 - j_lo;
+    colx1[tid] = tapx.i1 - j_lo;
+    __syncthreads();
+  }
+
+  const float* lg = p.logits + (long long)n * C * hw;
+  const long long* lab_base = p.labels + (long long)n * g.H * g.W + x;
+
+  float t[CT], u[CT];
+  float accA[GRAD ? CT : 1], accB[GRAD ? CT : 1];
+  if constexpr (GRAD) {
+#pragma unroll
+    for (int c = 0; c < CT; ++c) { accA[c] = 0.f; accB[c] = 0.f; }
+  }
+  int row_t = -1, row_u = -1;       // source rows currently held in t / u
+  int seg_i0 = -1, seg_i1 = -1;     // source-row pair of the open accumulation segment
+  float loss_acc = 0.f, cnt_acc = 0.f;
+
+  // Reduce the open segment's per-column sums onto source columns and add them to blk.
+  auto flush_segment = [&]() {
+    if constexpr (GRAD) {
+    // stage = acc + (-onehot sums already sitting in stage)
+#pragma unroll
+    for (int c = 0; c < CT; ++c)
+      if (c < C) {
+        stageA[c * K2_THREADS + tid] += accA[c];
+        stageB[c * K2_THREADS + tid] += accB[c];
+        accA[c] = 0.f; accB[c] = 0.f;
+      }
+    __syncthreads();
+    const int jspan = g.jspan_max;
+    const int rowA = seg_i0 - i_lo, rowB = seg_i1 - i_lo;
+    for (int o = tid; o < C * jspan; o += K2_THREADS) {
+      const int c = o / jspan;
+      const int jj = o - c * jspan;
+      float sA = 0.f, sB = 0.f;
+      // columns whose x0 or x1 equals jj: x0 in {jj-1, jj}.  Column -> x0 is monotone, so scan the
+      // 128 columns' window by binary search on colx0.
+      int lo = 0, hi = K2_THREADS;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (colx0[mid] < jj - 1) lo = mid + 1; else hi = mid; }
+      for (int col = lo; col < K2_THREADS && colx0[col] <= jj; ++col) {
+        const float wgt = (colx0[col] == jj ? colw0[col] : 0.f) + (colx1[col] == jj ? colw1[col] : 0.f);
+        sA = fmaf(wgt, stageA[c * K2_THREADS + col], sA);
+        sB = fmaf(wgt, stageB[c * K2_THREADS + col], sB);
+      }
+      blk[(rowA * jspan + jj) * C + c] += sA;
+      blk[(rowB * jspan + jj) * C + c] += sB;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < CT; ++c)
+      if (c < C) {
+        stageA[c * K2_THREADS + tid] = 0.f;
+        stageB[c * K2_THREADS + tid] = 0.f;
+      }
+    // (each thread only touches its own stage column between flushes: no barrier needed here)
+    }
+  };
+
+#pragma unroll 1
+  for (int ys = y_begin; ys < y_end; ys += K2_STRIP) {
+    long long lab[K2_STRIP];
+#pragma unroll
+    for (int r = 0; r < K2_STRIP; ++r) {
+      const int y = ys + r;
+      lab[r] = (xvalid && y < y_end) ? ld_stream_s64(lab_base + (long long)y * g.W) : (long long)p.ignore_index;
+    }
+#pragma unroll 1
+    for (int r = 0; r < K2_STRIP; ++r) {
+      const int y = ys + r;
+      if (y >= y_end) break;                                   // CTA-uniform
+      const Tap tapy = ac_tap(g.scale_h, y, g.h);              // CTA-uniform
+      if (tapy.i0 != seg_i0 || tapy.i1 != seg_i1) {
+        if (seg_i0 >= 0) flush_segment();
+        seg_i0 = tapy.i0; seg_i1 = tapy.i1;
+        if (row_t != tapy.i0) {
+          if (row_u == tapy.i0) {
+#pragma unroll
+            for (int c = 0; c < CT; ++c) t[c] = u[c];
+          } else {
+            const float* r0 = lg + (long long)tapy.i0 * g.w;
+#pragma unroll
+            for (int c = 0; c < CT; ++c)
+              if (c < C) t[c] = p.inv_T * (tapx.l0 * __ldg(r0 + c * hw + tapx.i0) + tapx.l1 * __ldg(r0 + c * hw + tapx.i1));
+          }
+          row_t = tapy.i0;
+        }
+        if (row_u != tapy.i1) {
+          if (row_t == tapy.i1) {
+#pragma unroll
+            for (int c = 0; c < CT; ++c) u[c] = t[c];
+          } else {
+            const float* r1 = lg + (long long)tapy.i1 * g.w;
+#pragma unroll
+            for (int c = 0; c < CT; ++c)
+              if (c < C) u[c] = p.inv_T * (tapx.l0 * __ldg(r1 + c * hw + tapx.i0) + tapx.l1 * __ldg(r1 + c * hw + tapx.i1));
+          }
+          row_u = tapy.i1;
+        }
+      }
+      const long long gl = lab[r];
+      const bool valid = xvalid && gl != (long long)p.ignore_index && gl >= 0 && gl < C;
+      if (valid) {
+        const int gi = (int)gl;
+        float e[CT];
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+          if (c < C) {
+            e[c] = tapy.l0 * t[c] + tapy.l1 * u[c];
+            m = fmaxf(m, e[c]);
+          }
+        // logit of the labelled class: re-interpolate from the (L1-resident) low-res logits
+        const float* q0 = lg + gi * hw + (long long)tapy.i0 * g.w;
+        const float* q1 = lg + gi * hw + (long long)tapy.i1 * g.w;
+        const float vt = p.inv_T * (tapx.l0 * __ldg(q0 + tapx.i0) + tapx.l1 * __ldg(q0 + tapx.i1));
+        const float vu = p.inv_T * (tapx.l0 * __ldg(q1 + tapx.i0) + tapx.l1 * __ldg(q1 + tapx.i1));
+        const float vlab = tapy.l0 * vt + tapy.l1 * vu;
+        float s = 0.f;
+        const float mneg = -m * 1.4426950408889634f;
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+          if (c < C) {
+            e[c] = fast_exp2(fmaf(e[c], 1.4426950408889634f, mneg));
+            s += e[c];
+          }
+        loss_acc += (m + __logf(s)) - vlab;
+        cnt_acc += 1.f;
+        if constexpr (GRAD) {
+          const float inv_s = __fdividef(1.f, s);
+          const float ca = tapy.l0 * inv_s, cb = tapy.l1 * inv_s;
+#pragma unroll
+          for (int c = 0; c < CT; ++c)
+            if (c < C) {
+              accA[c] = fmaf(ca, e[c], accA[c]);
+              accB[c] = fmaf(cb, e[c], accB[c]);
+            }
+          stageA[gi * K2_THREADS + tid] -= tapy.l0;          // -onehot, thread-private column
+          stageB[gi * K2_THREADS + tid] -= tapy.l1;
+        }
+      }
+    }
+  }
+  if (seg_i0 >= 0) flush_segment();
+
+  // per-tile loss / count partials (fixed-order tree => deterministic)
+  loss_acc = warp_sum(loss_acc);
+  cnt_acc = warp_sum(cnt_acc);
+  if (lane == 0) { red[warp] = loss_acc; red[4 + warp] = cnt_acc; }
+  __syncthreads();
+  if (tid == 0) {
+    p.loss_part[tile] = (red[0] + red[1]) + (red[2] + red[3]);
+    p.cnt_part[tile] = (red[4] + red[5]) + (red[6] + red[7]);
+  }
+  if (GRAD) {
+    float* dst = p.blocks + (long long)tile * blk_floats;
+    for (int i = tid; i < blk_floats; i += K2_THREADS) dst[i] = blk[i];
+  }
+}
+
+// loss = sum(loss_part) / sum(cnt_part)  (NaN when no valid pixel, like the reference); out = {loss, n_valid}
+__global__ void __launch_bounds__(256) k2_finalize_loss(const float* loss_part, const float* cnt_part, int tiles, float* out2) {
+  __shared__ double sl[8], sc[8];
+  double l = 0.0, c = 0.0;
+  for (int i = threadIdx.x; i < tiles; i += 256) { l += (double)loss_part[i]; c += (double)cnt_part[i]; }
+  l = warp_sum_d(l); c = warp_sum_d(c);
+  if ((threadIdx.x & 31) == 0) { sl[threadIdx.x >> 5] = l; sc[threadIdx.x >> 5] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double L = 0.0, Cn = 0.0;
+    for (int i = 0; i < 8; ++i) { L += sl[i]; Cn += sc[i]; }
+    out2[0] = (float)(L / Cn);
+    out2[1] = (float)Cn;
+  }
+}
+
+// grad_logits[n,c,i,j] = grad_out * inv_T / n_valid * sum over the tiles touching (i,j) of their partial block.
+__global__ void __launch_bounds__(128) k2_finalize_grad(const K2Geom g, const float* blocks, const float* loss_out2,
+                                                        const float* grad_out, float inv_T, float* grad_logits) {
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  const int i = blockIdx.y;
+  const int n = blockIdx.z;
+  if (j >= g.w) return;
+  const float n_valid = loss_out2[1];
+  const float scale = (grad_out ? grad_out[0] : 1.f) * inv_T / n_valid;
+  // output rows / cols that interpolate from source row i / col j:  dst in [first(i-1), first(i+1))
+  const int ya = ac_first_dst(g.scale_h, i - 1, g.h, g.H), yb = ac_first_dst(g.scale_h, i + 1, g.h, g.H);
+  const int xa = ac_first_dst(g.scale_w, j - 1, g.w, g.W), xb = ac_first_dst(g.scale_w, j + 1, g.w, g.W);
+  const long long blk_floats = (long long)g.ispan_max * g.jspan_max * g.C;
+  const long long hw = (long long)g.h * g.w;
+  float* dst = grad_logits + (long long)n * g.C * hw + (long long)i * g.w + j;
+  if (ya >= yb || xa >= xb) {
+    for (int c = 0; c < g.C; ++c) dst[c * hw] = 0.f;
+    return;
+  }
+  const int ty0 = ya / K2_TILE_H, ty1 = (yb - 1) / K2_TILE_H;
+  const int tx0 = xa / K2_TILE_W, tx1 = (xb - 1) / K2_TILE_W;
+  for (int c = 0; c < g.C; ++c) {
+    float acc = 0.f;
+    for (int ty = ty0; ty <= ty1; ++ty) {
+      const int li = i - (int)(g.scale_h * (float)(ty * K2_TILE_H));
+      if (li < 0 || li >= g.ispan_max) continue;
+      for (int tx = tx0; tx <= tx1; ++tx) {
+        const int lj = j - (int)(g.scale_w * (float)(tx * K2_TILE_W));
+        if (lj < 0 || lj >= g.jspan_max) continue;
+        const long long tile = ((long long)n * g.tiles_y + ty) * g.tiles_x + tx;
+        acc += blocks[tile * blk_floats + ((long long)li * g.jspan_max + lj) * g.C + c];
+      }
+    }
+    dst[c * hw] = acc * scale;
+  }
+}
+
+template <int CT>
+static int k2_main_launch(const K2Params& p, bool grad, cudaStream_t stream) {
+  const K2Geom& g = p.g;
+  const size_t smem = ((size_t)2 * CT * K2_THREADS + (size_t)g.ispan_max * g.jspan_max * g.C + 4 * K2_THREADS + 8) * 4;
+  B200SEG_CHECK_ARG(smem <= 200 * 1024, "upsample_ce: tile footprint %zu B exceeds shared memory (resize ratio too small)", smem);
+  const int tiles = (int)k2_tiles(g);
+  if (grad) {
+    static bool configured = false;
+    if (!configured) {
+      B200SEG_CUDA(cudaFuncSetAttribute(k2_upsample_ce_main<CT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+    k2_upsample_ce_main<CT, true><<<tiles, K2_THREADS, smem, stream>>>(p);
+  } else {
+    static bool configured = false;
+    if (!configured) {
+      B200SEG_CUDA(cudaFuncSetAttribute(k2_upsample_ce_main<CT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+    k2_upsample_ce_main<CT, false><<<tiles, K2_THREADS, smem, stream>>>(p);
+  }
+  B200SEG_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+int k2_forward(const float* logits, int N, int C, int h, int w, const long long* labels, int H, int W, int ignore_index,
+               float inv_T, int need_grad, void* workspace, long long workspace_bytes, float* loss_out2, cudaStream_t stream) {
+  B200SEG_CHECK_ARG(logits && labels && workspace && loss_out2, "upsample_ce_forward: null pointer");
+  B200SEG_CHECK_ARG(N > 0 && C > 0 && h > 0 && w > 0 && H > 0 && W > 0, "upsample_ce_forward: bad shape");
+  B200SEG_CHECK_ARG(C <= 32, "upsample_ce_forward: num_classes=%d > 32 is not supported", C);
+  B200SEG_CHECK_ARG(workspace_bytes >= k2_workspace_bytes(N, C, h, w, H, W), "upsample_ce_forward: workspace too small (%lld < %lld)",
+                    workspace_bytes, k2_workspace_bytes(N, C, h, w, H, W));
+  K2Params p;
+  k2_geometry(p.g, N, C, h, w, H, W);
+  const long long tiles = k2_tiles(p.g);
+  p.logits = logits; p.labels = labels; p.ignore_index = ignore_index; p.inv_T = inv_T;
+  p.loss_part = reinterpret_cast<float*>(workspace);
+  p.cnt_part = p.loss_part + tiles;
+  p.blocks = p.cnt_part + tiles;
+  int rc;
+  if (C <= 2) rc = k2_main_launch<2>(p, need_grad != 0, stream);
+  else if (C <= 19) rc = k2_main_launch<19>(p, need_grad != 0, stream);
+  else rc = k2_main_launch<32>(p, need_grad != 0, stream);
+  if (rc) return rc;
+  k2_finalize_loss<<<1, 256, 0, stream>>>(p.loss_part, p.cnt_part, (int)tiles, loss_out2);
+  B200SEG_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+int k2_backward(const void* workspace, int N, int C, int h, int w, int H, int W, float inv_T, const float* loss_out2,
+                const float* grad_out, float* grad_logits, cudaStream_t stream) {
+  B200SEG_CHECK_ARG(workspace && loss_out2 && grad_logits, "upsample_ce_backward: null pointer");
+  K2Geom g;
+  k2_geometry(g, N, C, h, w, H, W);
+  const long long tiles = k2_tiles(g);
+  const float* blocks = reinterpret_cast<const float*>(workspace) + 2 * tiles;
+  dim3 grid(ceil_div(w, 128), h, N);
+  k2_finalize_grad<<<grid, 128, 0, stream>>>(g, blocks, loss_out2, grad_out, inv_T, grad_logits);
+  B200SEG_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Materialising align-corners bilinear upsample (forward) and its adjoint (gather form, no atomics)
+// ---------------------------------------------------------------------------------------------
+template <int FMA>
+__global__ void __launch_bounds__(256) upsample_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int NC,
+                                                           int h, int w, int H, int W, float sh, float sw) {
+  const int x = blockIdx.x * 256 + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= W) return;
+  const Tap ty = ac_tap(sh, y, h), tx = ac_tap(sw, x, w);
+  for (int nc = blockIdx.z; nc < NC; nc += gridDim.z) {
+    const float* src = in + (long long)nc * h * w;
+    const float a = __ldg(src + (long long)ty.i0 * w + tx.i0), b = __ldg(src + (long long)ty.i0 * w + tx.i1);
+    const float c = __ldg(src + (long long)ty.i1 * w + tx.i0), d = __ldg(src + (long long)ty.i1 * w + tx.i1);
+    float v;
+    if (FMA == 0) v = ty.l0 * (tx.l0 * a + tx.l1 * b) + ty.l1 * (tx.l0 * c + tx.l1 * d);
+    else if (FMA == 1) v = fmaf(ty.l0, fmaf(tx.l0, a, tx.l1 * b), ty.l1 * fmaf(tx.l0, c, tx.l1 * d));
+    else if (FMA == 2) v = fmaf(ty.l1, fmaf(tx.l1, d, tx.l0 * c), ty.l0 * fmaf(tx.l1, b, tx.l0 * a));
+    else v = __fadd_rn(__fmul_rn(ty.l0, __fadd_rn(__fmul_rn(tx.l0, a), __fmul_rn(tx.l1, b))),
+                       __fmul_rn(ty.l1, __fadd_rn(__fmul_rn(tx.l0, c), __fmul_rn(tx.l1, d))));
+    out[((long long)nc * H + y) * W + x] = v;
+  }
+}
+
+int upsample_fwd_launch(const float* in, float* out, int NC, int h, int w, int H, int W, int fma_mode, cudaStream_t stream) {
+  B200SEG_CHECK_ARG(in && out && NC > 0 && h > 0 && w > 0 && H > 0 && W > 0, "upsample_bilinear_forward: bad arguments");
+  dim3 grid(ceil_div(W, 256), H, NC < 64 ? NC : 64);
+  const float sh = ac_scale(h, H), sw = ac_scale(w, W);
+  switch (fma_mode) {
+    case 0: upsample_fwd_kernel<0><<<grid, 256, 0, stream>>>(in, out, NC, h, w, H, W, sh, sw); break;
+    case 1: upsample_fwd_kernel<1><<<grid, 256, 0, stream>>>(in, out, NC, h, w, H, W, sh, sw); break;
+    case 2: upsample_fwd_kernel<2><<<grid, 256, 0, stream>>>(in, out, NC, h, w, H, W, sh, sw); break;
+    default: upsample_fwd_kernel<3><<<grid, 256, 0, stream>>>(in, out, NC, h, w, H, W, sh, sw); break;
+  }
+  B200SEG_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+__global__ void __launch_bounds__(128) upsample_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, int NC,
+                                                           int h, int w, int H, int W, float sh, float sw) {
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= w) return;
+  const int ya = ac_first_dst(sh, i - 1, h, H), yb = ac_first_dst(sh, i + 1, h, H);
+  const int xa = ac_first_dst(sw, j - 1, w, W), xb = ac_first_dst(sw, j + 1, w, W);
+  for (int nc = blockIdx.z; nc < NC; nc += gridDim.z) {
+    const float* src = gout + (long long)nc * H * W;
+    float acc = 0.f;
+    for (int y = ya; y < yb; ++y) {
+      const Tap ty = ac_tap(sh, y, h);
+      const float wy = (ty.i0 == i ? ty.l0 : 0.f) + (ty.i1 == i ? ty.l1 : 0.f);
+      if (wy == 0.f) continue;
+      float racc = 0.f;
+      for (int x = xa; x < xb; ++x) {
+        const Tap tx = ac_tap(sw, x, w);
+        const float wx = (tx.i0 == j ? tx.l0 : 0.f) + (tx.i1 == j ? tx.l1 : 0.f);
+        racc = fmaf(wx, __ldg(src + (long long)y * W + x), racc);
+      }
+      acc = fmaf(wy, racc, acc);
+    }
+    gin[((long long)nc * h + i) * w + j] = acc;
+  }
+}
+
+int upsample_bwd_launch(const float* gout, float* gin, int NC, int h, int w, int H, int W, cudaStream_t stream) {
+  B200SEG_CHECK_ARG(gout && gin && NC > 0 && h > 0 && w > 0 && H > 0 && W > 0, "upsample_bilinear_backward: bad arguments");
+  dim3 grid(ceil_div(w, 128), h, NC < 1024 ? NC : 1024);
+  upsample_bwd_kernel<<<grid, 128, 0, stream>>>(gout, gin, NC, h, w, H, W, ac_scale(h, H), ac_scale(w, W));
+  B200SEG_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+}  // namespace b200seg

@@ -1,0 +1,190 @@
+// Host side of the tcgen05 GEMM core: TMA tensor-map encoding, launch, and an on-device self-test
+// against a naive CUDA-core kernel (used by tests/ to pin descriptors on real hardware).
+#include "gemm_sm100.cuh"
+#include <limits.h>
+
+namespace b200seg {
+namespace gemm {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, outer pitch in elements.
+static int make_tmap(CUtensorMap* m, const __nv_bfloat16* ptr, long long inner, long long outer, long long pitch,
+                     int box_inner, int box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available (driver too old or no GPU)");
+    return B200SEG_ERR_CUDA;
+  }
+  B200SEG_CHECK_ARG((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand pointer must be 16-byte aligned");
+  B200SEG_CHECK_ARG((pitch * 2) % 16 == 0, "TMA operand pitch (%lld elements) must be a multiple of 8", pitch);
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t gstride[1] = {(cuuint64_t)pitch * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner=%lld outer=%lld pitch=%lld box=%dx%d)", (int)r,
+              inner, outer, pitch, box_inner, box_outer);
+    return B200SEG_ERR_CUDA;
+  }
+  return B200SEG_OK;
+}
+
+template <bool A_MN, bool B_MN>
+static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    B200SEG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured = true;
+  }
+  gemm_bf16_kernel<A_MN, B_MN><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+  B200SEG_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, float* out, long long row_stride,
+           int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used) {
+  B200SEG_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem %dx%dx%d", M, N, K);
+  Params p;
+  p.M = M; p.N = N; p.K = K;
+  p.m_tiles = ceil_div(M, BLOCK_M);
+  p.n_tiles = ceil_div(N, BLOCK_N);
+  p.kb_total = ceil_div(K, BLOCK_K);
+  if (splits < 1) splits = 1;
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = ceil_div(p.kb_total, splits);
+  p.splits = ceil_div(p.kb_total, p.kb_per_split);     // every split non-empty
+  p.out = out;
+  p.row_stride = row_stride;
+  p.col_hw = col_hw > 0 ? col_hw : INT_MAX;
+  p.img_stride = img_stride;
+  p.split_stride = split_stride;
+  if (splits_used) *splits_used = p.splits;
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a.mn_major) rc = make_tmap(&ta, a.ptr, K, M, a.pitch, BLOCK_K, BLOCK_M);
+  else rc = make_tmap(&ta, a.ptr, M, K, a.pitch, 64, BLOCK_K);
+  if (rc) return rc;
+  if (!b.mn_major) rc = make_tmap(&tb, b.ptr, K, N, b.pitch, BLOCK_K, BLOCK_N);
+  else rc = make_tmap(&tb, b.ptr, N, K, b.pitch, 64, BLOCK_K);
+  if (rc) return rc;
+
+  const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  if (!a.mn_major && !b.mn_major) return launch_t<false, false>(ta, tb, p, grid, stream);
+  if (a.mn_major && b.mn_major) return launch_t<true, true>(ta, tb, p, grid, stream);
+  if (a.mn_major && !b.mn_major) return launch_t<true, false>(ta, tb, p, grid, stream);
+  return launch_t<false, true>(ta, tb, p, grid, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// Self-test helpers
+// ------------------------------------------------------------------------------------------
+__global__ void fill_bf16_kernel(__nv_bfloat16* p, long long n, uint32_t seed) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t x = (uint32_t)i * 2654435761u + seed;
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  p[i] = __float2bfloat16(((float)(x & 0xFFFF) / 65536.0f - 0.5f) * 2.0f);
+}
+
+__global__ void naive_gemm_kernel(const __nv_bfloat16* A, const __nv_bfloat16* B, float* C, int M, int N, int K, int a_mn,
+                                  int b_mn, long long a_pitch, long long b_pitch) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  int m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) {
+    float a = __bfloat162float(a_mn ? A[(long long)k * a_pitch + m] : A[(long long)m * a_pitch + k]);
+    float b = __bfloat162float(b_mn ? B[(long long)k * b_pitch + n] : B[(long long)n * b_pitch + k]);
+    acc = fmaf(a, b, acc);
+  }
+  C[(long long)m * N + n] = acc;
+}
+
+// max |D - ref| and max |ref| over the (possibly split / image-mapped) output
+__global__ void compare_kernel(const float* D, const float* ref, int M, int N, int splits, long long split_stride,
+                               long long row_stride, int col_hw, long long img_stride, float* out2) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  int m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  int img = n / col_hw;
+  long long off = (long long)img * img_stride + (long long)m * row_stride + (n - img * col_hw);
+  float v = 0.f;
+  for (int z = 0; z < splits; ++z) v += D[z * split_stride + off];
+  float r = ref[(long long)m * N + n];
+  atomicMax(reinterpret_cast<int*>(out2), __float_as_int(fabsf(v - r)));
+  atomicMax(reinterpret_cast<int*>(out2) + 1, __float_as_int(fabsf(r)));
+}
+
+int selftest(int M, int N, int K, int a_mn, int b_mn, int splits, int col_hw, double* max_err, double* max_ref) {
+  const long long a_pitch = a_mn ? ((M + 7) / 8) * 8 : ((K + 7) / 8) * 8;
+  const long long b_pitch = b_mn ? ((N + 7) / 8) * 8 : ((K + 7) / 8) * 8;
+  const long long a_elems = a_pitch * (a_mn ? K : M), b_elems = b_pitch * (b_mn ? K : N);
+  __nv_bfloat16 *A = nullptr, *B = nullptr;
+  float *D = nullptr, *ref = nullptr, *res = nullptr;
+  const int kb_total = ceil_div(K, BLOCK_K);
+  int s = splits < 1 ? 1 : (splits > kb_total ? kb_total : splits);
+  long long row_stride, img_stride = 0, out_elems;
+  if (col_hw > 0) {                       // "NCHW" map: column n -> image n / col_hw, D[img][row][col % hw]
+    const int imgs = ceil_div(N, col_hw);
+    row_stride = col_hw;
+    img_stride = (long long)M * col_hw;
+    out_elems = (long long)imgs * img_stride;
+  } else {
+    row_stride = ((N + 3) / 4) * 4;
+    out_elems = (long long)M * row_stride;
+  }
+  B200SEG_CUDA(cudaMalloc(&A, a_elems * 2));
+  B200SEG_CUDA(cudaMalloc(&B, b_elems * 2));
+  B200SEG_CUDA(cudaMalloc(&D, out_elems * 4 * s));
+  B200SEG_CUDA(cudaMalloc(&ref, (long long)M * N * 4));
+  B200SEG_CUDA(cudaMalloc(&res, 8));
+  B200SEG_CUDA(cudaMemset(res, 0, 8));
+  B200SEG_CUDA(cudaMemset(D, 0xFF, out_elems * 4 * s));      // NaN pattern: unwritten outputs are caught
+  fill_bf16_kernel<<<(unsigned)ceil_div_ll(a_elems, 256), 256>>>(A, a_elems, 1234u);
+  fill_bf16_kernel<<<(unsigned)ceil_div_ll(b_elems, 256), 256>>>(B, b_elems, 777u);
+  dim3 g(ceil_div(N, 128), M);
+  naive_gemm_kernel<<<g, 128>>>(A, B, ref, M, N, K, a_mn, b_mn, a_pitch, b_pitch);
+  B200SEG_LAUNCH_CHECK();
+  Operand oa{A, a_mn != 0, a_pitch}, ob{B, b_mn != 0, b_pitch};
+  int used = 1;
+  int rc = launch(oa, ob, M, N, K, s, D, row_stride, col_hw, img_stride, out_elems, 0, &used);
+  if (rc == B200SEG_OK) {
+    compare_kernel<<<g, 128>>>(D, ref, M, N, used, out_elems, row_stride, col_hw > 0 ? col_hw : INT_MAX, img_stride, res);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      set_error("gemm selftest: kernel failed: %s", cudaGetErrorString(e));
+      rc = B200SEG_ERR_CUDA;
+    } else {
+      float h[2];
+      cudaMemcpy(h, res, 8, cudaMemcpyDeviceToHost);
+      // a NaN difference compares as a huge positive int pattern -> report as inf
+      *max_err = (h[0] != h[0]) ? 1e30 : (double)h[0];
+      *max_ref = (double)h[1];
+    }
+  }
+  cudaFree(A); cudaFree(B); cudaFree(D); cudaFree(ref); cudaFree(res);
+  return rc;
+}
+
+}  // namespace gemm
+}  // namespace b200seg

@@ -1,0 +1,318 @@
+// Hand-written sm_100a GEMM core used by the fused ASPP head (fwd / dgrad / wgrad).
+//
+//   D[M x N] (fp32) = A[M x K] * B[N x K]^T     bf16 operands, fp32 accumulate in TMEM
+//
+// * operands staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) into a 4-stage
+//   shared-memory ring guarded by mbarriers;
+// * tcgen05.mma.cta_group::1.kind::f16, 128 x 256 x 16 per instruction, issued by one thread;
+// * two 256-column fp32 accumulators in TMEM (512 columns) so the epilogue of tile i overlaps
+//   the main loop of tile i+1; persistent CTAs, one per SM;
+// * either operand may be K-major ([rows][K], K contiguous) or MN-major ([K][rows], rows
+//   contiguous) -- the weight-gradient GEMM contracts over pixels and reads both operands
+//   MN-major straight out of the layouts the forward pass already produced;
+// * epilogue: tcgen05.ld -> registers -> padded smem transpose -> 128-byte coalesced stores,
+//   with an optional "column = pixel index split by image" address map so the data-gradient
+//   GEMM writes fp32 NCHW directly; optional split-K writes one partial slab per split.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace b200seg {
+namespace gemm {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_K = 64;          // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
+constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 48 KB
+constexpr int MN_BOX_BYTES = 64 * BLOCK_K * 2;   // one MN-major TMA box: 64 k-rows x 128 B = 8 KB
+constexpr int NUM_THREADS = 256;                 // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
+constexpr int EPI_STAGE_FLOATS = 32 * 33;        // per epilogue warp, padded transpose tile
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 4 * EPI_STAGE_FLOATS * 4 + 256;
+
+struct Params {
+  int M, N, K;
+  int m_tiles, n_tiles, splits, kb_per_split, kb_total;
+  float* out;
+  long long row_stride;     // elements between consecutive rows of D
+  int col_hw;               // columns per image (INT_MAX => plain row-major)
+  long long img_stride;     // elements between images (used when col_hw != INT_MAX)
+  long long split_stride;   // elements between split-K partial slabs
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (sm_100 format): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout type [61,64) (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor for kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+// a_major bit 15, b_major bit 16 (1 = MN-major), N>>3 [17,23), M>>4 [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------
+// The kernel
+// ------------------------------------------------------------------------------------------
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;                                   // 1024-byte aligned (128B swizzle atom)
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 4 * EPI_STAGE_FLOATS * 4);
+  uint64_t* full_bar = bars;                  // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;        // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);           // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_split = p.m_tiles * p.n_tiles;
+  const int num_tiles = tiles_per_split * p.splits;
+
+  if (warp == 0) {
+    // ================= TMA producer (one thread) =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int z = tile / tiles_per_split;
+        const int rem = tile - z * tiles_per_split;
+        const int nt = rem / p.m_tiles;
+        const int mt = rem - nt * p.m_tiles;
+        const int m0 = mt * BLOCK_M, n0 = nt * BLOCK_N;
+        const int kb0 = z * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          const int k0 = kb * BLOCK_K;
+          if (!A_MN) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);            // box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int b = 0; b < BLOCK_M / 64; ++b)                          // box {64 m, 64 k}
+              tma_load_2d(sa + b * MN_BOX_BYTES, &tmap_a, &full_bar[stage], m0 + b * 64, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);            // box {64 k, 256 rows}
+          } else {
+#pragma unroll
+            for (int b = 0; b < BLOCK_N / 64; ++b)
+              tma_load_2d(sb + b * MN_BOX_BYTES, &tmap_b, &full_bar[stage], n0 + b * 64, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BLOCK_M, BLOCK_N);
+      // K-major: 8-row groups 1024 B apart (SBO), LBO unused (1); +32 B per UMMA_K step.
+      // MN-major: 64-element chunks one TMA box (8 KB) apart (LBO), 8-k-row groups 1024 B apart (SBO);
+      //           +16 k-rows = 2048 B per UMMA_K step.
+      constexpr uint32_t a_lbo = A_MN ? MN_BOX_BYTES : 16, a_sbo = 1024, a_step = A_MN ? 2048 : 32;
+      constexpr uint32_t b_lbo = B_MN ? MN_BOX_BYTES : 16, b_sbo = 1024, b_step = B_MN ? 2048 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int z = tile / tiles_per_split;
+        const int kb0 = z * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = make_smem_desc(sa + k * a_step, a_lbo, a_sbo);
+            const uint64_t bdesc = make_smem_desc(sb + k * b_step, b_lbo, b_sbo);
+            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tfull_bar[acc]);              // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue (4 warps; warp w owns TMEM lanes [32*(w-4), +32)) =================
+    const int wq = warp - 4;
+    float* stg = epi_stage + wq * EPI_STAGE_FLOATS;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int z = tile / tiles_per_split;
+      const int rem = tile - z * tiles_per_split;
+      const int nt = rem / p.m_tiles;
+      const int mt = rem - nt * p.m_tiles;
+      const int row_base = mt * BLOCK_M + wq * 32;
+      const int col_base = nt * BLOCK_N;
+      float* out = p.out + (long long)z * p.split_stride;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(r[i]);
+        __syncwarp();
+        const int col = col_base + c * 32 + lane;
+        if (col < p.N) {
+          const int img = col / p.col_hw;
+          float* dst = out + (long long)img * p.img_stride + (long long)(col - img * p.col_hw);
+          const int rows = min(32, p.M - row_base);
+          for (int rr = 0; rr < rows; ++rr) dst[(long long)(row_base + rr) * p.row_stride] = stg[rr * 33 + lane];
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// Host side (gemm_sm100.cu)
+struct Operand {
+  const __nv_bfloat16* ptr;
+  bool mn_major;        // false: [rows][K] K contiguous; true: [K][rows] rows contiguous
+  long long pitch;      // elements between consecutive outer-dimension entries
+};
+int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, float* out, long long row_stride,
+           int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used);
+
+}  // namespace gemm
+}  // namespace b200seg

@@ -1,0 +1,142 @@
+"""Autograd-aware functional ops over the C ABI (the layer the nn.Modules are built from)."""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+
+# --------------------------------------------------------------------------------------------
+# K1  fused multi-dilation ASPP head
+# --------------------------------------------------------------------------------------------
+def _pixel_major_bf16(x: torch.Tensor) -> torch.Tensor:
+    """[N,Cin,h,w] -> bf16 [N*h*w, Cin].  bf16 channels_last input is taken zero-copy."""
+    if not x.is_cuda:
+        raise _lib.B200SegError("ASPP head: expected CUDA features (b200seg has no CPU fallback)")
+    N, Cin, h, w = x.shape
+    if x.dtype == torch.bfloat16:
+        xl = x.permute(0, 2, 3, 1)
+        if not xl.is_contiguous():
+            xl = xl.contiguous()
+        return xl.reshape(N * h * w, Cin)
+    if x.dtype != torch.float32:
+        x = x.float()
+    return _lib.aspp_pack_features(x.contiguous())
+
+
+class _AsppHeadFn(torch.autograd.Function):
+    """out[N,C,h,w] = sum_r conv3x3(x; W_r, b_r, dilation=padding=rates[r])  (classifier.py:26-29)."""
+
+    @staticmethod
+    def forward(ctx, x, rates, packed, *params):
+        R = len(rates)
+        weights, biases = params[:R], params[R:]
+        N, Cin, h, w = x.shape
+        C = weights[0].shape[0]
+        if packed is None:
+            packed = _lib.aspp_pack_weights([p.detach() for p in weights], [None if b is None else b.detach() for b in biases])
+        Wp, WpT, bias_sum = packed
+        Xp = _pixel_major_bf16(x.detach())
+        logits = _lib.aspp_forward(Xp, Wp, bias_sum, rates, N, h, w, C)
+        ctx.rates, ctx.shape, ctx.x_dtype = tuple(rates), (N, Cin, h, w, C), x.dtype
+        ctx.save_for_backward(Xp, WpT)
+        return logits
+
+    @staticmethod
+    def backward(ctx, grad_logits):
+        Xp, WpT = ctx.saved_tensors
+        N, Cin, h, w, C = ctx.shape
+        R = len(ctx.rates)
+        need = ctx.needs_input_grad
+        need_x = need[0]
+        need_w = any(need[3:3 + R])
+        need_b = any(need[3 + R:3 + 2 * R])
+        gx, gws, gbs = _lib.aspp_backward(grad_logits.float(), Xp, WpT, ctx.rates, N, h, w, C, need_x, need_w, need_b)
+        if gx is not None and ctx.x_dtype != torch.float32:
+            gx = gx.to(ctx.x_dtype)
+        out_w = [gws[r] if (gws is not None and need[3 + r]) else None for r in range(R)]
+        out_b = [gbs[r] if (gbs is not None and need[3 + R + r]) else None for r in range(R)]
+        return (gx, None, None, *out_w, *out_b)
+
+
+def aspp_head(x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]],
+              rates: Sequence[int], packed=None) -> torch.Tensor:
+    return _AsppHeadFn.apply(x, tuple(int(r) for r in rates), packed, *weights, *biases)
+
+
+# --------------------------------------------------------------------------------------------
+# materialising align-corners bilinear upsample (API-compat path)
+# --------------------------------------------------------------------------------------------
+class _UpsampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, size):
+        ctx.in_hw = tuple(x.shape[-2:])
+        return _lib.upsample_bilinear_forward(x.detach().float().contiguous(), size)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return _lib.upsample_bilinear_backward(grad_out.float(), ctx.in_hw), None
+
+
+def upsample_bilinear_align_corners(x: torch.Tensor, size) -> torch.Tensor:
+    """F.interpolate(x, size, mode='bilinear', align_corners=True), bit-exact forward on CUDA."""
+    return _UpsampleFn.apply(x, (int(size[0]), int(size[1])))
+
+
+# --------------------------------------------------------------------------------------------
+# K2  upsample + cross-entropy (ignore_index), fused
+# --------------------------------------------------------------------------------------------
+class _UpsampleCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits_lr, labels, ignore_index, temperature):
+        need_grad = bool(ctx.needs_input_grad[0])
+        inv_t = 1.0 / float(temperature)
+        out2, ws = _lib.upsample_ce_forward(logits_lr.detach().float().contiguous(), labels.contiguous(), ignore_index, inv_t,
+                                            need_grad)
+        ctx.meta = (tuple(logits_lr.shape), tuple(labels.shape[-2:]), inv_t, need_grad)
+        ctx.save_for_backward(out2, ws)
+        return out2[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        out2, ws = ctx.saved_tensors
+        shape_lr, size, inv_t, need_grad = ctx.meta
+        if not need_grad:
+            raise _lib.B200SegError("upsample_cross_entropy: forward ran without gradient tracking")
+        g = _lib.upsample_ce_backward(ws, out2, shape_lr, size, inv_t, grad_out.detach().float())
+        return g, None, None, None
+
+
+def upsample_cross_entropy(logits_lr: torch.Tensor, labels: torch.Tensor, ignore_index: int = 255,
+                           temperature: float = 1.0) -> torch.Tensor:
+    """CrossEntropyLoss(ignore_index)(interpolate(logits_lr, labels.shape[-2:]) / temperature, labels) without
+    materialising the full-resolution logits (aspp_trainer.py:88-92, aspp_fada.py:91-96)."""
+    if labels.dtype != torch.int64:
+        labels = labels.long()
+    return _UpsampleCEFn.apply(logits_lr, labels, int(ignore_index), float(temperature))
+
+
+# --------------------------------------------------------------------------------------------
+# K3  soft-label cross-entropy
+# --------------------------------------------------------------------------------------------
+class _SoftCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, soft, weights):
+        pred_c = pred.detach().float().contiguous()
+        soft_c = soft.detach().float().contiguous()
+        w_c = None if weights is None else weights.detach().float().contiguous()
+        ctx.save_for_backward(pred_c, soft_c, w_c)
+        return _lib.soft_ce_forward(pred_c, soft_c, w_c)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        pred_c, soft_c, w_c = ctx.saved_tensors
+        return _lib.soft_ce_backward(pred_c, soft_c, w_c, grad_out.detach().float()), None, None
+
+
+def soft_label_cross_entropy(pred: torch.Tensor, soft_label: torch.Tensor,
+                             pixel_weights: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """core/utils/utility.py:172-177 (differentiable w.r.t. pred only, as every reference caller uses it)."""
+    return _SoftCEFn.apply(pred, soft_label, pixel_weights)

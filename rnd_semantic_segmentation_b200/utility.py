@@ -1,0 +1,235 @@
+"""Drop-in replacements for the hot-path helpers of core/utils/utility.py.
+
+Same names, argument meaning and return conventions as the reference:
+``soft_label_cross_entropy`` (:172-177), ``inference`` (:179-191), ``intersectionAndUnionGPU``
+(:148-161), ``intersectionAndUnion`` (:133-145), ``confusion_matrix`` (:347-359), ``AverageMeter``
+(:24-72) -- plus the fused entry point ``segmentation_eval_step`` that the reference's tester loop
+(core/testers/aspp_tester.py:57-74) collapses into.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _lib, ops
+from .ops import soft_label_cross_entropy  # noqa: F401  (re-exported under the reference's name)
+
+__all__ = ["soft_label_cross_entropy", "inference", "intersectionAndUnion", "intersectionAndUnionGPU",
+           "confusion_matrix", "AverageMeter", "segmentation_eval_step", "iutr_from_confusion", "LazyProbabilities"]
+
+
+# ------------------------------------------------------------------------------------------------
+# AverageMeter (utility.py:24-72) -- host-side scalar bookkeeping, numerically identical
+# ------------------------------------------------------------------------------------------------
+class AverageMeter(object):
+    """Accumulates per-frame intersection / union / target / output areas and IoU / F1 sums."""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.intersection_sum = 0
+        self.union_sum = 0
+        self.target_sum = 0
+        self.res_sum = 0
+        self.count = 0
+        self.iou_sum = 0
+        self.f1_sum = 0
+
+    def update(self, intersection, union, target, res):
+        iou = intersection / (union + 1e-10)
+        f1 = 2 * intersection / (target + res + 1e-10)
+        self.intersection_sum += intersection
+        self.union_sum += union
+        self.target_sum += target
+        self.res_sum += res
+        self.count += 1
+        self.iou_sum += iou
+        self.f1_sum += f1
+
+    def results(self):
+        macro_f1 = self.f1_sum / float(self.count)
+        macro_iou = self.iou_sum / float(self.count)
+        micro_f1 = 2 * self.intersection_sum / (self.target_sum + self.res_sum + 1e-10)
+        micro_iou = self.intersection_sum / (self.union_sum + 1e-10)
+        return dict(macro_iou=macro_iou, macro_f1=macro_f1, micro_iou=micro_iou, micro_f1=micro_f1)
+
+    def summary(self, logger, num_classes=2):
+        r = self.results()
+        logger.info('Macro metric, val result: mIoU/mF1 {:.4f}/{:.4f}.'.format(np.mean(r["macro_iou"]), np.mean(r["macro_f1"])))
+        logger.info('Micro metric, val result: mIoU/mF1 {:.4f}/{:.4f}.'.format(np.mean(r["micro_iou"]), np.mean(r["micro_f1"])))
+        for i in range(num_classes):
+            logger.info('Macro metric, class {} iou/f1 score: {:.4f}/{:.4f}.'.format(i, r["macro_iou"][i], r["macro_f1"][i]))
+            logger.info('Micro metric, class {} iou/f1 score: {:.4f}/{:.4f}.'.format(i, r["micro_iou"][i], r["micro_f1"][i]))
+
+
+# ------------------------------------------------------------------------------------------------
+# fused eval step
+# ------------------------------------------------------------------------------------------------
+def iutr_from_confusion(cm: torch.Tensor):
+    """(intersection, union, target, output) areas of utility.py:148-161 from a confusion matrix whose rows
+    exclude ignored truth: I = diag, T = row sums, O = column sums, U = O + T - I (exact int64)."""
+    inter = torch.diagonal(cm, dim1=-2, dim2=-1)
+    tgt = cm.sum(dim=-1)
+    out = cm.sum(dim=-2)
+    return inter, out + tgt - inter, tgt, out
+
+
+def segmentation_eval_step(logits_lr: torch.Tensor, labels: torch.Tensor, ignore_index: int = 255,
+                           cm: Optional[torch.Tensor] = None, per_frame: bool = False, want_pred: bool = False):
+    """One launch for the whole post-head part of aspp_tester.py:60-72: align-corners upsample to
+    ``labels.shape[-2:]``, softmax, argmax (first index on ties, bit-exact with the reference on CUDA)
+    and the C x C int64 confusion matrix accumulated into ``cm``.  Returns (cm, pred or None)."""
+    if labels.dtype != torch.int64:
+        labels = labels.long()
+    return _lib.upsample_argmax_confusion(logits_lr.float().contiguous(), labels.contiguous(), labels.shape[-2:],
+                                          ignore_index=ignore_index, cm=cm, per_frame=per_frame, want_pred=want_pred)
+
+
+# A prediction produced by LazyProbabilities.max remembers the confusion matrix computed in the same
+# launch, so the reference tester's follow-up calls confusion_matrix(...) / intersectionAndUnionGPU(...)
+# on that very tensor are answered without touching the pixels again.
+_pred_cache = weakref.WeakValueDictionary()
+
+
+class _PredRecord:
+    __slots__ = ("pred", "labels_ptr", "cm", "ignore_index", "__weakref__")
+
+
+class LazyProbabilities:
+    """What ``inference(..., flip=False)`` returns: stands for softmax(interpolate(logits_lr)) [1,C,H,W]
+    without materialising it.  ``.max(1)`` gives (max probability placeholder, int64 argmax) through the fused
+    kernel; any other use materialises the real tensor (``.materialize()`` / ``torch.as_tensor`` semantics)."""
+
+    def __init__(self, logits_lr, label, ignore_index=255):
+        self.logits_lr = logits_lr
+        self.label = label
+        self.ignore_index = ignore_index
+        self._full = None
+
+    @property
+    def shape(self):
+        n, c = self.logits_lr.shape[:2]
+        return torch.Size((n, c) + tuple(self.label.shape[-2:]))
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
+
+    def materialize(self) -> torch.Tensor:
+        if self._full is None:
+            up = ops.upsample_bilinear_align_corners(self.logits_lr, self.label.shape[-2:])
+            self._full = F.softmax(up, dim=1)
+        return self._full
+
+    def max(self, dim=None, keepdim=False):
+        if dim != 1 or keepdim:
+            return self.materialize().max(dim, keepdim) if dim is not None else self.materialize().max()
+        labels = self.label if self.label.dtype == torch.int64 else self.label.long()
+        labels = labels.reshape(self.logits_lr.shape[0], *labels.shape[-2:]).contiguous()
+        cm, pred = _lib.upsample_argmax_confusion(self.logits_lr, labels, labels.shape[-2:],
+                                                  ignore_index=self.ignore_index, per_frame=False, want_pred=True)
+        rec = _PredRecord()
+        rec.pred, rec.labels_ptr, rec.cm, rec.ignore_index = pred, labels.data_ptr(), cm, self.ignore_index
+        _pred_cache[pred.data_ptr()] = rec
+        pred._b200seg_record = rec          # keeps the record alive exactly as long as the prediction tensor
+        return None, pred
+
+    def argmax(self, dim=None, keepdim=False):
+        if dim == 1 and not keepdim:
+            return self.max(1)[1]
+        return self.materialize().argmax(dim, keepdim)
+
+    def cpu(self):
+        return self.materialize().cpu()
+
+    def __getitem__(self, idx):
+        return self.materialize()[idx]
+
+    def __torch_function__(self, func, types, args=(), kwargs=None):   # any torch.* call on the lazy object
+        kwargs = kwargs or {}
+        args = tuple(a.materialize() if isinstance(a, LazyProbabilities) else a for a in args)
+        return func(*args, **kwargs)
+
+
+def inference(feature_extractor, classifier, image, label, flip=True):
+    """utility.py:179-191.  flip=False (what ASPPTester uses, aspp_tester.py:60) returns a LazyProbabilities;
+    flip=True needs the averaged probabilities and therefore materialises them."""
+    size = label.shape[-2:]
+    if flip:
+        image = torch.cat([image, torch.flip(image, [3])], 0)
+    with torch.no_grad():
+        output = classifier(feature_extractor(image))
+    if not flip:
+        return LazyProbabilities(output[:1].contiguous(), label)
+    output = ops.upsample_bilinear_align_corners(output, size)
+    output = F.softmax(output, dim=1)
+    output = (output[0] + output[1].flip(2)) / 2
+    return output.unsqueeze(dim=0)
+
+
+def _cached_record(pd: torch.Tensor, gt: torch.Tensor):
+    rec = _pred_cache.get(pd.data_ptr())
+    if rec is None or rec.pred.numel() != pd.numel():
+        return None
+    if gt.data_ptr() != rec.labels_ptr:
+        return None
+    return rec
+
+
+class _Cfg:
+    pass
+
+
+def confusion_matrix(cfg, pd, gt):
+    """utility.py:347-359: int64 [C,C], rows = truth, cols = prediction, truth == 255 skipped; returned on the
+    CPU like the reference (the tester adds it to a CPU accumulator, aspp_tester.py:69)."""
+    num_classes = cfg.MODEL.NUM_CLASSES if not isinstance(cfg, int) else cfg
+    if not pd.is_cuda:
+        raise _lib.B200SegError("confusion_matrix: expected CUDA tensors (b200seg has no CPU fallback)")
+    rec = _cached_record(pd, gt)
+    if rec is not None and rec.ignore_index == 255 and rec.cm.shape[-1] == num_classes:
+        return rec.cm.cpu()
+    cm = _lib.confusion_from_pred(pd.reshape(-1).long().contiguous(), gt.reshape(-1).long().contiguous(), num_classes, 255)
+    return cm.cpu()
+
+
+def intersectionAndUnionGPU(output, target, K, ignore_index=255):
+    """utility.py:148-161: float32 [K] x4 on the GPU; writes ignore_index into ``output`` where the target is
+    ignored (the reference mutates its argument through a view, :154)."""
+    assert output.dim() in [1, 2, 3]
+    assert output.shape == target.shape
+    if not output.is_cuda:
+        raise _lib.B200SegError("intersectionAndUnionGPU: expected CUDA tensors (b200seg has no CPU fallback)")
+    out_flat = output.view(-1)
+    tgt_flat = target.reshape(-1)
+    if out_flat.dtype != torch.int64 or tgt_flat.dtype != torch.int64 or not tgt_flat.is_contiguous():
+        work = out_flat.long().contiguous()
+        cm = _lib.confusion_from_pred(work, tgt_flat.long().contiguous(), K, ignore_index, mutate_pd=True)
+        out_flat.copy_(work.to(out_flat.dtype))
+    else:
+        cm = _lib.confusion_from_pred(out_flat, tgt_flat, K, ignore_index, mutate_pd=True)
+    i, u, t, o = iutr_from_confusion(cm)
+    return i.float(), u.float(), t.float(), o.float()
+
+
+def intersectionAndUnion(output, target, K, ignore_index=255):
+    """numpy twin, utility.py:133-145 (host-side helper kept for API completeness): areas of
+    intersection / union / target / output per class, ignored-target pixels excluded."""
+    assert output.ndim in [1, 2, 3]
+    assert output.shape == target.shape
+    pd = np.asarray(output).reshape(-1).astype(np.int64)
+    gt = np.asarray(target).reshape(-1).astype(np.int64)
+    keep = gt != ignore_index
+
+    def count(v):
+        v = v[(v >= 0) & (v < K)]
+        return np.bincount(v, minlength=K)[:K]
+
+    area_output = count(pd[keep])
+    area_target = count(gt)
+    area_intersection = count(pd[keep & (pd == gt)])
+    return area_intersection, area_output + area_target - area_intersection, area_target, area_output

@@ -1,0 +1,164 @@
+"""CPU-only tests: C-ABI library loads and exports every symbol include/b200seg.h declares, host logic of the
+drop-in layer (factories, state_dict contract, install(), error behaviour without a GPU), and the N>1 host path
+under gloo with world_size 2."""
+import os
+import re
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from rnd_semantic_segmentation_b200 import _build_ext, _lib
+    _build_ext.build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from rnd_semantic_segmentation_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "b200seg.h")).read()
+    declared = set(re.findall(r"\b(b200seg_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(built_lib, name), name
+    assert built_lib.b200seg_abi_version() == 1
+    assert built_lib.b200seg_aspp_packed_rows(19, 4) == 640          # 33 taps x 19 classes -> 627 -> 640
+    assert built_lib.b200seg_aspp_packed_rows(2, 4) == 128
+    assert built_lib.b200seg_upsample_ce_workspace_bytes(2, 19, 65, 129, 512, 1024) > 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(built_lib):
+    import rnd_semantic_segmentation_b200 as b200
+    from rnd_semantic_segmentation_b200._lib import B200SegError
+    assert built_lib.b200seg_device_sms() < 0
+    assert b"no CUDA device" in built_lib.b200seg_last_error()
+    head = b200.ASPP_Classifier_V2(16, [6, 12, 18, 24], [6, 12, 18, 24], 3)
+    with pytest.raises(B200SegError):
+        head(torch.randn(1, 16, 8, 8))
+    with pytest.raises(B200SegError):
+        b200.soft_label_cross_entropy(torch.randn(1, 4, 3, 3), torch.rand(1, 4, 3, 3))
+    with pytest.raises(B200SegError):
+        b200.upsample_cross_entropy(torch.randn(1, 4, 3, 3), torch.zeros(1, 6, 6, dtype=torch.int64))
+    with pytest.raises(B200SegError):
+        b200.confusion_matrix(4, torch.zeros(5, dtype=torch.int64), torch.zeros(5, dtype=torch.int64))
+
+
+def _cfg(name="deeplab_resnet101", C=19):
+    return types.SimpleNamespace(MODEL=types.SimpleNamespace(NAME=name, NUM_CLASSES=C, WEIGHTS="", FREEZE_BN=True))
+
+
+def test_factories_and_state_dict_contract():
+    import rnd_semantic_segmentation_b200 as b200
+    from oracle import torch_oracle as to
+    torch.manual_seed(3)
+    cls = b200.build_classifier(_cfg())
+    torch.manual_seed(3)
+    ref = to.AsppHeadOracle(2048, [6, 12, 18, 24], [6, 12, 18, 24], 19)
+    assert list(cls.state_dict().keys()) == [f"conv2d_list.{i}.{p}" for i in range(4) for p in ("weight", "bias")]
+    for (ka, va), (kb, vb) in zip(cls.state_dict().items(), ref.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb)                         # same seed, same init order
+    assert sum(p.numel() for p in cls.parameters()) == 1400908
+    assert b200.build_classifier(_cfg("deeplab_vgg16")).conv2d_list[0].in_channels == 1024
+    with pytest.raises(NotImplementedError):
+        b200.build_classifier(_cfg("deeplab_mobilenet"))
+    D = b200.build_adversarial_discriminator(_cfg())
+    assert list(D.state_dict().keys()) == ["D.0.weight", "D.0.bias", "D.2.weight", "D.2.bias", "cls1.weight", "cls1.bias",
+                                           "cls2.weight", "cls2.bias"]
+    assert sum(p.numel() for p in D.parameters()) == 5057702
+    assert b200.build_adversarial_discriminator(_cfg("x_efficientnetb2")).D[0].in_channels == 1408
+    assert b200.build_adversarial_discriminator(_cfg("x_hardnet68"), num_features=77).D[0].in_channels == 77
+    with pytest.raises(NotImplementedError):
+        b200.build_adversarial_discriminator(_cfg("deeplab_foo"))
+    # reference-format checkpoint round trip incl. the 'module.' prefix DDP adds
+    sd = {"module." + k: v for k, v in ref.state_dict().items()}
+    cls.load_state_dict({k[len("module."):]: v for k, v in sd.items()})
+    with pytest.raises(NotImplementedError):
+        b200.ASPP_Classifier_V2(8, [6, 12], [1, 2], 3)._rates()
+
+
+def test_average_meter_and_numpy_iou_match_oracle():
+    import rnd_semantic_segmentation_b200 as b200
+    from oracle import torch_oracle as to
+    rng = np.random.RandomState(0)
+    a, b = b200.AverageMeter(), to.AverageMeterOracle()
+    for _ in range(4):
+        pd = rng.randint(0, 5, (40, 50)); gt = rng.randint(0, 5, (40, 50)); gt[rng.rand(40, 50) < 0.2] = 255
+        i, u, t, r = b200.intersectionAndUnion(pd, gt, 5)
+        i2, u2, t2, r2 = to.intersection_and_union(torch.from_numpy(pd), torch.from_numpy(gt), 5)
+        for x, y in ((i, i2), (u, u2), (t, t2), (r, r2)):
+            np.testing.assert_array_equal(x, y.numpy().astype(np.int64))
+        args = [v.astype(np.float32) for v in (i, u, t, r)]
+        a.update(*args); b.update(*args)
+    ra, rb = a.results(), b.results()
+    for k in ("macro_iou", "macro_f1", "micro_iou", "micro_f1"):
+        np.testing.assert_array_equal(ra[k], rb[k])
+
+
+def test_install_patches_reference_modules(monkeypatch):
+    import rnd_semantic_segmentation_b200 as b200
+    core = types.ModuleType("core"); models = types.ModuleType("core.models"); bld = types.ModuleType("core.models.build")
+    utils = types.ModuleType("core.utils"); util = types.ModuleType("core.utils.utility"); tester = types.ModuleType("core.testers.aspp_tester")
+    bld.build_classifier = models.build_classifier = lambda cfg: "ref"
+    util.confusion_matrix = tester.confusion_matrix = lambda *a: "ref"
+    for m in (core, models, bld, utils, util, tester):
+        monkeypatch.setitem(sys.modules, m.__name__, m)
+    patched = b200.install()
+    assert bld.build_classifier is b200.build_classifier and models.build_classifier is b200.build_classifier
+    assert util.confusion_matrix is b200.confusion_matrix and tester.confusion_matrix is b200.confusion_matrix
+    assert "core.utils.utility.soft_label_cross_entropy" in patched
+
+
+def test_synth_shapes_and_determinism():
+    from rnd_semantic_segmentation_b200 import synth
+    lab = synth.make_labels(2, 100, 130, 19, seed=5)
+    assert lab.shape == (2, 100, 130) and lab.dtype == torch.int64
+    assert set(torch.unique(lab).tolist()) <= set(range(19)) | {255}
+    assert torch.equal(lab, synth.make_labels(2, 100, 130, 19, seed=5))
+    x = synth.make_features(1, 16, 5, 7, seed=2)
+    assert float(x.min()) >= 0 and x.shape == (1, 16, 5, 7)
+    assert synth.WORKLOADS["deeplabv2_r101_src"] == (2, 2048, 65, 129, 512, 1024, 19)
+
+
+def _dist_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    from rnd_semantic_segmentation_b200 import distributed as D
+    import rnd_semantic_segmentation_b200 as b200
+    assert D.init_from_env("gloo")
+    torch.manual_seed(0)
+    head = b200.ASPP_Classifier_V2(8, [6, 12, 18, 24], [6, 12, 18, 24], 3)
+    for i, p in enumerate(head.parameters()):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    bucket = D.allreduce_mean_grads_(head)
+    for i, p in enumerate(head.parameters()):
+        assert torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1)))       # mean of ranks (1, 2)
+        assert p.grad.data_ptr() >= bucket.flat.data_ptr()
+    # eval sharding: frames rank::world, int64 confusion matrix summed exactly
+    frames = D.shard_indices(7, rank, world)
+    cm = torch.zeros(3, 3, dtype=torch.int64)
+    for f in frames:
+        cm[f % 3, (f * 2) % 3] += 10 ** 12 + f            # beyond fp32/fp64-exact accumulation if done in float32
+    D.allreduce_confusion_(cm)
+    want = torch.zeros(3, 3, dtype=torch.int64)
+    for f in range(7):
+        want[f % 3, (f * 2) % 3] += 10 ** 12 + f
+    assert torch.equal(cm, want)
+    torch.save(cm, os.path.join(tmp, f"cm{rank}.pt"))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_distributed_gloo_world2(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_dist_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = torch.load(tmp_path / "cm0.pt"), torch.load(tmp_path / "cm1.pt")
+    assert torch.equal(a, b)
