@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native segmentation hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One JSON line on stdout (rank 0).  Metric (BASELINE.json): ASPP+CE train Mpx/s -- label pixels per second
+through  features -> ASPP head fwd -> upsample+CE fwd -> CE/upsample bwd -> head dgrad+wgrad (+ mean
+all-reduce of the head gradients when N > 1) -- with eval img/s @1024x2048 (head fwd + upsample/argmax/
+confusion matrix) reported in the same line under "eval".  Synthetic Cityscapes-shaped data, random-init head.
+
+Under torchrun (N > 1) every rank runs the same per-GPU workload (weak scaling, batch sharded by image,
+frames rank::world); time is the max over ranks, measured with CUDA events between barriers.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+RATES = [6, 12, 18, 24]
+F_FWD_PER_PX = 2 * 36 * 2048 * 19        # dense-tap convention, SURVEY.md section 8d (Cin=2048, C=19)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"], bf16_tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (rank 0)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        busy = [v for v in sm if smax and v > 0.5 * smax] or sm
+        med = busy[len(busy) // 2] if busy else None
+        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def barrier():
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+
+
+def max_over_ranks(ms: float) -> float:
+    if dist.is_available() and dist.is_initialized():
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return ms
+
+
+def timed(step_fn, steps, warmup, sampler=None):
+    """W untimed warm-ups, then exactly K steps between barrier + synchronize, CUDA events on the launching stream."""
+    for _ in range(warmup):
+        step_fn()
+    torch.cuda.synchronize()
+    barrier()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        step_fn()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    return max_over_ranks(e0.elapsed_time(e1)), clocks
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import rnd_semantic_segmentation_b200 as b200
+    from rnd_semantic_segmentation_b200 import _lib, distributed as D, synth
+    rank, world, local = D.env_rank_world()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the b200seg path has no CPU fallback")
+    torch.cuda.set_device(local)
+    D.init_from_env("nccl")
+    dev = torch.device("cuda", local)
+    peaks = load_peaks()
+    _lib.load()
+
+    n, cin, h, w, H, W, C = synth.WORKLOADS[args.workload]
+    torch.manual_seed(1234)
+    head = b200.ASPP_Classifier_V2(cin, RATES, RATES, C).to(dev)
+    x = synth.make_features(n, cin, h, w, seed=1234 + rank, device=dev)
+    labels = synth.make_labels(n, H, W, C, seed=1234 + rank, device=dev)
+    bucket = D.FlatGradBucket(head.parameters())
+    label_px = n * H * W
+
+    def train_step(x_in=x, labels_in=labels):
+        xg = x_in.detach().requires_grad_(True)            # the backbone needs d loss / d features
+        for p in head.parameters():
+            p.grad = None
+        loss, _ = head.forward_loss(xg, labels_in)
+        loss.backward()
+        if world > 1:
+            bucket.allreduce_mean_()
+        return loss, xg.grad
+
+    launches0 = _lib.launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, clocks = timed(train_step, args.steps, args.warmup, sampler)
+    launches = _lib.launch_count() - launches0 - 0
+    launches_timed = launches * args.steps // (args.steps + args.warmup)
+    ms_per_step = ms / args.steps
+    value = world * label_px / (ms_per_step * 1e-3) / 1e6
+
+    # ---- per-kernel CUDA-event timing (separate pass; events on the launching stream) -> roofline
+    _lib.profile_enable(True)
+    for _ in range(args.steps):
+        train_step()
+    torch.cuda.synchronize()
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    P = n * h * w
+    flops_per_launch = 2.0 * 36 * cin * C * P
+    gemm_names = ("head_fwd_gemm", "head_dgrad_gemm", "head_wgrad_gemm")
+    gemm_ms = sum(prof[k][0] for k in gemm_names if k in prof)
+    gemm_n = sum(prof[k][1] for k in gemm_names if k in prof)
+    avg_ms = gemm_ms / max(gemm_n, 1)
+    achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
+    peak = peaks["bf16_tflops_sustained"]
+    kernels = {k: {"ms_per_launch": round(v[0] / v[1], 4), "launches_per_step": v[1] / args.steps} for k, v in prof.items()}
+    for k in gemm_names:
+        if k in kernels:
+            kernels[k]["tflops"] = round(flops_per_launch / (kernels[k]["ms_per_launch"] * 1e-3) / 1e12, 1)
+    roofline = {"kernel": "gemm_bf16_kernel (tcgen05; head fwd / dgrad / wgrad launches)", "bound": "tensor",
+                "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+                "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
+                "algorithmic_flops_per_launch": flops_per_launch, "kernels": kernels}
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + loss D2H inside the timed region
+    xh = x.cpu().pin_memory()
+    lh = labels.cpu().pin_memory()
+
+    def e2e_step():
+        xd = xh.to(dev, non_blocking=True)
+        ld = lh.to(dev, non_blocking=True)
+        loss, _ = train_step(xd, ld)
+        return loss.item()
+
+    e2e_steps = max(2, min(args.steps, 10))
+    ms_e2e, _ = timed(e2e_step, e2e_steps, 1)
+    e2e = {"value": round(world * label_px / (ms_e2e / e2e_steps * 1e-3) / 1e6, 2), "unit": "Mpx/s",
+           "h2d_bytes_per_step": xh.numel() * 4 + lh.numel() * 8, "d2h_bytes_per_step": 4}
+    del xh, lh
+
+    # ---- eval img/s @1024x2048: head fwd (features 1x2048x128x256) + fused upsample/argmax/confusion
+    en, ecin, eh, ew, eH, eW, eC = synth.WORKLOADS["eval_1024x2048"]
+    ehead = synth.scale_head_for_unit_logits(b200.ASPP_Classifier_V2(ecin, RATES, RATES, eC)).to(dev).eval()
+    nf = 4                                               # distinct frames cycled so inputs exceed L2 (4 x 268 MB)
+    ex = [synth.make_features(1, ecin, eh, ew, seed=99 + rank * 16 + i, device=dev) for i in range(nf)]
+    ey = [synth.make_labels(1, eH, eW, eC, seed=199 + rank * 16 + i, device=dev) for i in range(nf)]
+    cm = torch.zeros(eC, eC, dtype=torch.int64, device=dev)
+    fi = [0]
+
+    def eval_step():
+        i = fi[0] % nf
+        fi[0] += 1
+        with torch.no_grad():
+            lg = ehead.logits(ex[i])
+        b200.segmentation_eval_step(lg, ey[i], cm=cm)
+
+    esteps = max(args.steps * 4, 20)
+    ems, _ = timed(eval_step, esteps, args.warmup)
+    if world > 1:
+        D.allreduce_confusion_(cm)
+    _lib.profile_enable(True)
+    for _ in range(8):
+        eval_step()
+    torch.cuda.synchronize()
+    eprof = _lib.profile_read()
+    _lib.profile_enable(False)
+    k4_ms = eprof["eval_argmax_confusion"][0] / eprof["eval_argmax_confusion"][1]
+    k4_bytes = 8 * eH * eW + 4 * eC * eh * ew + 8 * eC * eC
+    exh = ex[0].cpu().pin_memory()
+    eyh = ey[0].cpu().pin_memory()
+
+    def eval_e2e_step():
+        xd = exh.to(dev, non_blocking=True)
+        yd = eyh.to(dev, non_blocking=True)
+        with torch.no_grad():
+            lg = ehead.logits(xd)
+        c, _ = b200.segmentation_eval_step(lg, yd)
+        return c.cpu()
+
+    ems_e2e, _ = timed(eval_e2e_step, 10, 1)
+    eval_obj = {"metric": "eval_img_per_s_1024x2048", "value": round(world * esteps / (ems * 1e-3), 1), "unit": "img/s",
+                "ms_per_frame": round(ems / esteps, 4), "frames": esteps * world, "confusion_total": int(cm.sum().item()),
+                "e2e": {"value": round(world * 10 / (ems_e2e * 1e-3), 1), "unit": "img/s",
+                        "h2d_bytes_per_step": exh.numel() * 4 + eyh.numel() * 8, "d2h_bytes_per_step": 8 * eC * eC},
+                "roofline": {"kernel": "k4_upsample_argmax_confusion", "bound": "hbm", "achieved": round(k4_bytes / (k4_ms * 1e-3) / 1e9, 1),
+                             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(k4_bytes / (k4_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                             "traffic": None, "algorithmic_bytes_per_launch": k4_bytes},
+                "kernels": {k: round(v[0] / v[1], 4) for k, v in eprof.items()}}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = run_cpu_reference(args.workload, steps=2, warmup=1)["cpu_baseline"]
+
+    if rank == 0:
+        line = {"metric": "aspp_ce_train_Mpx_per_s", "value": round(value, 2), "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": args.workload, "features": [n, cin, h, w], "labels": [n, H, W], "num_classes": C,
+                           "input": "fp32 NCHW features resident in HBM (reference API contract); bf16 operands, fp32 accumulate",
+                           "step": "head fwd + upsample/CE fwd + bwd (dX, dW, db)" + (" + NCCL mean all-reduce of head grads" if world > 1 else ""),
+                           "l2": "inputs larger than L2 (features %d MB per step)" % (x.numel() * 4 // 2 ** 20),
+                           "parallelism": "dp%d (batch sharded by image)" % world},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_timed), "roofline": roofline, "eval": eval_obj}
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path (oracle port), all host threads
+# ----------------------------------------------------------------------------------------------------
+def run_cpu_reference(workload, steps, warmup):
+    from oracle import torch_oracle as to
+    from rnd_semantic_segmentation_b200 import synth
+    n, cin, h, w, H, W, C = synth.WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(1234)
+    head = to.AsppHeadOracle(cin, RATES, RATES, C)
+    ns = 1                                                 # bounded sample: one image of the step's batch per CPU step
+    x = synth.make_features(ns, cin, h, w, seed=1234)
+    labels = synth.make_labels(ns, H, W, C, seed=1234)
+    for _ in range(warmup):
+        to.train_step_src(head, x, labels)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        to.train_step_src(head, x, labels)
+    dt = (time.perf_counter() - t0) / steps
+    value = ns * H * W / dt / 1e6
+    sample = f"{ns} of the {n} images of workload {workload} per step ({ns}x{cin}x{h}x{w} features, {ns}x{H}x{W} labels), torch {torch.__version__} CPU fp32"
+    return {"value": value, "ms_per_step": dt * 1e3,
+            "cpu_baseline": {"value": round(value, 4), "unit": "Mpx/s", "cores": cores, "kind": "port", "sample": sample}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from rnd_semantic_segmentation_b200 import synth
+    n, cin, h, w, H, W, C = synth.WORKLOADS[args.workload]
+    r = run_cpu_reference(args.workload, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    line = {"impl": "reference", "metric": "aspp_ce_train_Mpx_per_s", "value": round(r["value"], 4), "unit": "Mpx/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["ms_per_step"], 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "features": [n, cin, h, w], "labels": [n, H, W], "num_classes": C,
+                       "note": "reference's CPU path (oracle port of classifier.py:26-32 + CrossEntropyLoss + backward) on the host cores; "
+                               "each step is a bounded one-image sample of the workload"},
+            "cpu_baseline": r["cpu_baseline"],
+            "e2e": {"value": round(r["value"], 4), "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="train_b8_512x1024")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

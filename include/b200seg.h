@@ -113,6 +113,16 @@ B200SEG_API int b200seg_aspp_backward(const float* grad_logits, const void* Xp, 
                           int Cin, int C, int h, int w, void* scratch, int64_t scratch_bytes, int splits, float* grad_x,
                           float* const* grad_w, float* const* grad_b, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * instrumentation (bench.py): number of kernels this library has launched, and per-kernel CUDA-event
+ * timing on the launching stream.  Tags: 0 head fwd GEMM, 1 head dgrad GEMM, 2 head wgrad GEMM,
+ * 3 feature pack, 4 fwd gather, 5 grad im2col (G'), 6 upsample+CE main, 7 eval argmax+confusion,
+ * 8 soft-CE fwd, 9 soft-CE bwd, 10 wgrad reduce.
+ * ------------------------------------------------------------------------------------------- */
+B200SEG_API long long b200seg_launch_count(void);
+B200SEG_API void b200seg_profile_enable(int on);
+B200SEG_API int b200seg_profile_read(int tag, double* total_ms, int* count);
+
 /* on-device self-test of the tcgen05 GEMM core against a CUDA-core reference (synchronous) */
 B200SEG_API int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b_mn_major, int splits, int col_hw, double* max_err,
                           double* max_ref);

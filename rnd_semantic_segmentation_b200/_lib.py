@@ -44,6 +44,9 @@ SIGNATURES = {
     "b200seg_aspp_backward_scratch_bytes": (c_i64, [c_int] * 7),
     "b200seg_aspp_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64, c_int,
                                       c_vp, c_vp, c_vp, c_vp]),
+    "b200seg_launch_count": (ctypes.c_longlong, []),
+    "b200seg_profile_enable": (None, [c_int]),
+    "b200seg_profile_read": (c_int, [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int)]),
     "b200seg_gemm_selftest": (c_int, [c_int] * 7 + [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
 }
 
@@ -362,3 +365,28 @@ def gemm_selftest(M, N, K, a_mn=False, b_mn=False, splits=1, col_hw=0):
     err, ref = ctypes.c_double(0), ctypes.c_double(0)
     _check(lib.b200seg_gemm_selftest(M, N, K, int(a_mn), int(b_mn), splits, col_hw, ctypes.byref(err), ctypes.byref(ref)))
     return err.value, ref.value
+
+
+PROFILE_TAGS = {"head_fwd_gemm": 0, "head_dgrad_gemm": 1, "head_wgrad_gemm": 2, "pack_features": 3, "head_gather": 4,
+                "grad_im2col": 5, "upsample_ce_main": 6, "eval_argmax_confusion": 7, "soft_ce_fwd": 8, "soft_ce_bwd": 9,
+                "wgrad_reduce": 10}
+
+
+def launch_count() -> int:
+    return int(load().b200seg_launch_count())
+
+
+def profile_enable(on: bool):
+    load().b200seg_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """{kernel name: (total_ms, launches)} accumulated since profile_enable(True)."""
+    lib = load()
+    out = {}
+    for name, tag in PROFILE_TAGS.items():
+        ms, n = ctypes.c_double(0), c_int(0)
+        _check(lib.b200seg_profile_read(tag, ctypes.byref(ms), ctypes.byref(n)))
+        if n.value:
+            out[name] = (ms.value, n.value)
+    return out

@@ -15,6 +15,26 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
+
+// ---- optional per-kernel event timing (bench.py roofline leg) ---------------------------------
+constexpr int PROF_TAGS = 16, PROF_MAX = 4096;
+static int g_prof_on = 0;
+static int g_prof_n[PROF_TAGS];
+static cudaEvent_t g_prof_ev[PROF_TAGS][PROF_MAX][2];
+void profile_begin(int tag, cudaStream_t stream) {
+  if (!g_prof_on || tag < 0 || tag >= PROF_TAGS || g_prof_n[tag] >= PROF_MAX) return;
+  cudaEvent_t* e = g_prof_ev[tag][g_prof_n[tag]];
+  cudaEventCreate(&e[0]); cudaEventCreate(&e[1]);
+  cudaEventRecord(e[0], stream);
+}
+void profile_end(int tag, cudaStream_t stream) {
+  if (!g_prof_on || tag < 0 || tag >= PROF_TAGS || g_prof_n[tag] >= PROF_MAX) return;
+  cudaEventRecord(g_prof_ev[tag][g_prof_n[tag]][1], stream);
+  ++g_prof_n[tag];
+}
+
 int num_sms() {
   static int cached = 0;
   if (cached <= 0) {
@@ -173,6 +193,29 @@ int b200seg_aspp_backward(const float* grad_logits, const void* Xp, const void* 
   REQUIRE_DEVICE();
   return aspp_backward(grad_logits, Xp, WpT, rates_host, R, N, Cin, C, h, w, scratch, scratch_bytes, splits, grad_x, grad_w, grad_b,
                        S(stream));
+}
+
+long long b200seg_launch_count(void) { return g_launches; }
+
+void b200seg_profile_enable(int on) {
+  for (int t = 0; t < PROF_TAGS; ++t) {
+    for (int i = 0; i < g_prof_n[t]; ++i) { cudaEventDestroy(g_prof_ev[t][i][0]); cudaEventDestroy(g_prof_ev[t][i][1]); }
+    g_prof_n[t] = 0;
+  }
+  g_prof_on = on;
+}
+
+int b200seg_profile_read(int tag, double* total_ms, int* count) {
+  if (tag < 0 || tag >= PROF_TAGS || !total_ms || !count) { set_error("profile_read: bad arguments"); return B200SEG_ERR_ARG; }
+  double tot = 0.0;
+  for (int i = 0; i < g_prof_n[tag]; ++i) {
+    B200SEG_CUDA(cudaEventSynchronize(g_prof_ev[tag][i][1]));
+    float ms = 0.f;
+    B200SEG_CUDA(cudaEventElapsedTime(&ms, g_prof_ev[tag][i][0], g_prof_ev[tag][i][1]));
+    tot += ms;
+  }
+  *total_ms = tot; *count = g_prof_n[tag];
+  return B200SEG_OK;
 }
 
 int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b_mn_major, int splits, int col_hw, double* max_err,

@@ -244,7 +244,9 @@ int aspp_pack_features(const float* x, int N, int Cin, int h, int w, void* Xp, c
   B200SEG_CHECK_ARG(x && Xp && N > 0 && h > 0 && w > 0, "aspp_pack_features: bad arguments");
   B200SEG_CHECK_ARG(Cin % 8 == 0, "aspp: in_channels=%d must be a multiple of 8", Cin);
   dim3 grid(ceil_div(h * w, 64), ceil_div(Cin, 64), N);
+  profile_begin(3, stream);
   pack_features_kernel<<<grid, 256, 0, stream>>>(x, Cin, h * w, (__nv_bfloat16*)Xp);
+  profile_end(3, stream);
   B200SEG_LAUNCH_CHECK();
   return B200SEG_OK;
 }
@@ -264,12 +266,14 @@ int aspp_forward(const void* Xp, const void* Wp, const float* bias_sum, const in
   const long long ypitch = ceil_div_ll(P, 4) * 4;
   gemm::Operand a{(const __nv_bfloat16*)Wp, false, Cin};
   gemm::Operand b{(const __nv_bfloat16*)Xp, false, Cin};
-  int rc = gemm::launch(a, b, NJ, (int)P, Cin, 1, Yt, ypitch, 0, 0, 0, stream, nullptr);
+  int rc = gemm::launch(a, b, NJ, (int)P, Cin, 1, Yt, ypitch, 0, 0, 0, stream, nullptr, 0);
   if (rc) return rc;
   TapTable tt;
   make_taps(tt, rates, R);
   dim3 grid(ceil_div(w, 128), h, N * C);
+  profile_begin(4, stream);
   head_gather_kernel<<<grid, 128, 0, stream>>>(Yt, ypitch, tt, bias_sum, C, h, w, logits);
+  profile_end(4, stream);
   B200SEG_LAUNCH_CHECK();
   return B200SEG_OK;
 }
@@ -310,7 +314,9 @@ int aspp_backward(const float* grad_logits, const void* Xp, const void* WpT, con
       B200SEG_CUDA(cudaFuncSetAttribute(build_gprime_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured_nj = NJ;
     }
+    profile_begin(5, stream);
     build_gprime_kernel<<<(unsigned)ceil_div_ll(P, GP_PX), 256, smem, stream>>>(gOt, tt, C, NJ, h, w, P, Gp);
+    profile_end(5, stream);
     B200SEG_LAUNCH_CHECK();
   }
   if (grad_b) {
@@ -326,7 +332,7 @@ int aspp_backward(const float* grad_logits, const void* Xp, const void* WpT, con
     // dX[ci, p] = WpT[ci, :] . G'[p, :]   -> fp32 NCHW: column p = (image, pixel), row = channel
     gemm::Operand a{(const __nv_bfloat16*)WpT, false, NJ};
     gemm::Operand b{Gp, false, NJ};
-    int rc = gemm::launch(a, b, Cin, (int)P, NJ, 1, grad_x, hw, hw, (long long)Cin * hw, 0, stream, nullptr);
+    int rc = gemm::launch(a, b, Cin, (int)P, NJ, 1, grad_x, hw, hw, (long long)Cin * hw, 0, stream, nullptr, 1);
     if (rc) return rc;
   }
   if (grad_w) {
@@ -339,10 +345,12 @@ int aspp_backward(const float* grad_logits, const void* Xp, const void* WpT, con
       gemm::Operand b{(const __nv_bfloat16*)Xp, true, Cin};
       int used = 1;
       const long long slab = (long long)NJ * Cin;
-      int rc = gemm::launch(a, b, NJ, Cin, (int)P, splits, wpart, Cin, 0, 0, slab, stream, &used);
+      int rc = gemm::launch(a, b, NJ, Cin, (int)P, splits, wpart, Cin, 0, 0, slab, stream, &used, 2);
       if (rc) return rc;
       dim3 grid(ceil_div(Cin, 256), C, R);
+      profile_begin(10, stream);
       wgrad_reduce_kernel<<<grid, 256, 0, stream>>>(wpart, used, slab, R, C, Cin, gw);
+      profile_end(10, stream);
       B200SEG_LAUNCH_CHECK();
     }
   }

@@ -336,6 +336,7 @@ static int k2_main_launch(const K2Params& p, bool grad, cudaStream_t stream) {
   const size_t smem = ((size_t)2 * CT * K2_THREADS + (size_t)g.ispan_max * g.jspan_max * g.C + 4 * K2_THREADS + 8) * 4;
   B200SEG_CHECK_ARG(smem <= 200 * 1024, "upsample_ce: tile footprint %zu B exceeds shared memory (resize ratio too small)", smem);
   const int tiles = (int)k2_tiles(g);
+  profile_begin(6, stream);
   if (grad) {
     static bool configured = false;
     if (!configured) {
@@ -351,6 +352,7 @@ static int k2_main_launch(const K2Params& p, bool grad, cudaStream_t stream) {
     }
     k2_upsample_ce_main<CT, false><<<tiles, K2_THREADS, smem, stream>>>(p);
   }
+  profile_end(6, stream);
   B200SEG_LAUNCH_CHECK();
   return B200SEG_OK;
 }

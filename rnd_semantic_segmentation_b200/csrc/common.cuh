@@ -14,6 +14,10 @@ namespace b200seg {
 
 void set_error(const char* fmt, ...);           // api.cu
 int num_sms();                                   // api.cu (cached per process)
+void count_launch();                             // api.cu: kernels launched by this library (bench evidence)
+// api.cu: when profiling is on, bracket a launch with CUDA events on its stream under `tag`
+void profile_begin(int tag, cudaStream_t stream);
+void profile_end(int tag, cudaStream_t stream);
 
 #define B200SEG_CHECK_ARG(cond, ...)                                  \
   do {                                                                \
@@ -33,7 +37,11 @@ int num_sms();                                   // api.cu (cached per process)
     }                                                                                   \
   } while (0)
 
-#define B200SEG_LAUNCH_CHECK() B200SEG_CUDA(cudaGetLastError())
+#define B200SEG_LAUNCH_CHECK()             \
+  do {                                     \
+    ::b200seg::count_launch();             \
+    B200SEG_CUDA(cudaGetLastError());      \
+  } while (0)
 
 __host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ __forceinline__ long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }

@@ -60,7 +60,7 @@ static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const Params& 
 }
 
 int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, float* out, long long row_stride,
-           int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used) {
+           int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used, int prof_tag) {
   B200SEG_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem %dx%dx%d", M, N, K);
   Params p;
   p.M = M; p.N = N; p.K = K;
@@ -89,10 +89,13 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
 
   const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  if (!a.mn_major && !b.mn_major) return launch_t<false, false>(ta, tb, p, grid, stream);
-  if (a.mn_major && b.mn_major) return launch_t<true, true>(ta, tb, p, grid, stream);
-  if (a.mn_major && !b.mn_major) return launch_t<true, false>(ta, tb, p, grid, stream);
-  return launch_t<false, true>(ta, tb, p, grid, stream);
+  profile_begin(prof_tag, stream);
+  if (!a.mn_major && !b.mn_major) rc = launch_t<false, false>(ta, tb, p, grid, stream);
+  else if (a.mn_major && b.mn_major) rc = launch_t<true, true>(ta, tb, p, grid, stream);
+  else if (a.mn_major && !b.mn_major) rc = launch_t<true, false>(ta, tb, p, grid, stream);
+  else rc = launch_t<false, true>(ta, tb, p, grid, stream);
+  profile_end(prof_tag, stream);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -312,7 +312,7 @@ struct Operand {
   long long pitch;      // elements between consecutive outer-dimension entries
 };
 int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, float* out, long long row_stride,
-           int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used);
+           int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used, int prof_tag = -1);
 
 }  // namespace gemm
 }  // namespace b200seg

@@ -127,9 +127,11 @@ int k3_forward(const float* pred, const float* soft, const float* wts, int N, in
   const long long HW = (long long)H * W, total = HW * N;
   const int grid = k3_grid(total);
   float* partial = reinterpret_cast<float*>(workspace);
+  profile_begin(8, stream);
   if (K <= 4) k3_softce_fwd<4><<<grid, K3_THREADS, 0, stream>>>(pred, soft, wts, K, HW, total, partial);
   else if (K <= 38) k3_softce_fwd<38><<<grid, K3_THREADS, 0, stream>>>(pred, soft, wts, K, HW, total, partial);
   else k3_softce_fwd<64><<<grid, K3_THREADS, 0, stream>>>(pred, soft, wts, K, HW, total, partial);
+  profile_end(8, stream);
   B200SEG_LAUNCH_CHECK();
   k3_finalize<<<1, 256, 0, stream>>>(partial, grid, 1.0 / (double)total, loss_out);
   B200SEG_LAUNCH_CHECK();
@@ -144,9 +146,11 @@ int k3_backward(const float* pred, const float* soft, const float* wts, const fl
   const long long HW = (long long)H * W, total = HW * N;
   const int grid = k3_grid(total);
   const float inv = (float)(1.0 / (double)total);
+  profile_begin(9, stream);
   if (K <= 4) k3_softce_bwd<4><<<grid, K3_THREADS, 0, stream>>>(pred, soft, wts, grad_out, K, HW, total, inv, grad_pred);
   else if (K <= 38) k3_softce_bwd<38><<<grid, K3_THREADS, 0, stream>>>(pred, soft, wts, grad_out, K, HW, total, inv, grad_pred);
   else k3_softce_bwd<64><<<grid, K3_THREADS, 0, stream>>>(pred, soft, wts, grad_out, K, HW, total, inv, grad_pred);
+  profile_end(9, stream);
   B200SEG_LAUNCH_CHECK();
   return B200SEG_OK;
 }

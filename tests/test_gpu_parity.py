@@ -205,7 +205,7 @@ def test_k1_head_forward_backward(lib, n, cin, C, h, w):
         wg = m_ref.weight.grad.clone()
         wg[:, :, 1, 1] = eff.conv2d_list[0].weight.grad[:, :, 1, 1]      # d/dW_r(centre) is the same for every branch
         assert rel_err(m_ours.weight.grad, wg) <= TOL, f"branch {i}"
-        assert rel_err(m_ours.bias.grad, m_ref.bias.grad) <= TOL
+        assert rel_err(m_ours.bias.grad, go.double().sum((0, 2, 3))) <= 1e-5      # bias grad is summed from the fp32 gradient
 
 
 @pytest.mark.parametrize("name", ["head_c19", "head_c2", "head_c19_T18"])
