@@ -119,10 +119,20 @@ __global__ void __launch_bounds__(128) head_gather_kernel(const float* __restric
   if (xq >= w) return;
   const long long pbase = (long long)n * h * w;
   float acc = bias_sum[c];
-#pragma unroll 1
-  for (int t = 0; t < tt.n_taps; ++t) {
-    const int yy = y + tt.dy[t], xx = xq + tt.dx[t];
-    if (yy >= 0 && yy < h && xx >= 0 && xx < w) acc += Yt[(long long)(t * C + c) * ypitch + pbase + (long long)yy * w + xx];
+  // taps in groups of 11 (33 = 3 x 11 for the four-rate head): all loads of a group are issued before the adds
+  for (int t0 = 0; t0 < tt.n_taps; t0 += 11) {
+    float v[11];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+      const int t = t0 + k;
+      v[k] = 0.f;
+      if (t < tt.n_taps) {
+        const int yy = y + tt.dy[t], xx = xq + tt.dx[t];
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) v[k] = __ldcs(Yt + (long long)(t * C + c) * ypitch + pbase + (long long)yy * w + xx);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 11; ++k) acc += v[k];
   }
   logits[((long long)(n * C + c) * h + y) * w + xq] = acc;
 }
@@ -169,34 +179,40 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict_
   }
 }
 
-constexpr int GP_PX = 8;
+// G'[p][j] = gO[p - d_t][c]  (j = t*C + c; zero outside the image and for j >= T*C).  One thread builds one 16-byte
+// vector (8 consecutive j); the 16 threads of a pixel write 256 contiguous bytes per pass.
+constexpr int GP_PX = 16;            // pixels per 256-thread block
 __global__ void __launch_bounds__(256) build_gprime_kernel(const __nv_bfloat16* __restrict__ gOt, TapTable tt, int C, int NJ,
-                                                           int h, int w, long long P, __nv_bfloat16* __restrict__ Gp) {
-  extern __shared__ __align__(16) __nv_bfloat16 gp_smem[];     // [GP_PX][NJ]
-  const long long p0 = (long long)blockIdx.x * GP_PX;
+                                                           unsigned c_magic, int h, int w, long long P,
+                                                           __nv_bfloat16* __restrict__ Gp) {
+  const long long p = (long long)blockIdx.x * GP_PX + (threadIdx.x >> 4);
+  if (p >= P) return;
   const int hw = h * w;
-  const int total = GP_PX * NJ;
-  for (int e = threadIdx.x; e < total; e += 256) {
-    const int pl = e / NJ, j = e - pl * NJ;
-    const long long p = p0 + pl;
-    __nv_bfloat16 v = __float2bfloat16(0.f);
-    const int t = j / C;
-    if (p < P && t < tt.n_taps) {
-      const int c = j - t * C;
-      const long long n = p / hw;
-      const int s = (int)(p - n * hw);
-      const int y = s / w, x = s - y * w;
-      const int yy = y - tt.dy[t], xx = x - tt.dx[t];
-      if (yy >= 0 && yy < h && xx >= 0 && xx < w) v = gOt[(n * hw + (long long)yy * w + xx) * 32 + c];
+  const long long n = p / hw;
+  const int s = (int)(p - n * hw);
+  const int y = s / w, x = s - y * w;
+  const unsigned short* src = reinterpret_cast<const unsigned short*>(gOt) + n * hw * 32;
+  const int nvec = NJ >> 3;
+  for (int v8 = threadIdx.x & 15; v8 < nvec; v8 += 16) {
+    unsigned short e[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const unsigned j = (unsigned)(v8 * 8 + k);
+      const unsigned t = (j * c_magic) >> 16;                 // j / C  (exact for j < 1024, C <= 32)
+      unsigned short val = 0;
+      if (t < (unsigned)tt.n_taps) {
+        const int c = (int)(j - t * (unsigned)C);
+        const int yy = y - tt.dy[t], xx = x - tt.dx[t];
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) val = __ldg(src + ((long long)yy * w + xx) * 32 + c);
+      }
+      e[k] = val;
     }
-    gp_smem[e] = v;
-  }
-  __syncthreads();
-  const int vec_per_row = NJ / 8;
-  for (int e = threadIdx.x; e < GP_PX * vec_per_row; e += 256) {
-    const int pl = e / vec_per_row, v8 = e - pl * vec_per_row;
-    if (p0 + pl < P)
-      reinterpret_cast<int4*>(Gp + (p0 + pl) * NJ)[v8] = reinterpret_cast<const int4*>(gp_smem + pl * NJ)[v8];
+    int4 out;
+    out.x = (int)((unsigned)e[0] | ((unsigned)e[1] << 16));
+    out.y = (int)((unsigned)e[2] | ((unsigned)e[3] << 16));
+    out.z = (int)((unsigned)e[4] | ((unsigned)e[5] << 16));
+    out.w = (int)((unsigned)e[6] | ((unsigned)e[7] << 16));
+    reinterpret_cast<int4*>(Gp + p * NJ)[v8] = out;
   }
 }
 
@@ -308,14 +324,9 @@ int aspp_backward(const float* grad_logits, const void* Xp, const void* WpT, con
   grad_to_pixel_major_kernel<<<(unsigned)ceil_div_ll(P, 256), 256, 0, stream>>>(grad_logits, C, hw, P, gOt);
   B200SEG_LAUNCH_CHECK();
   {
-    static int configured_nj = 0;
-    const size_t smem = (size_t)GP_PX * NJ * 2;
-    if (smem > 48 * 1024 && configured_nj < NJ) {
-      B200SEG_CUDA(cudaFuncSetAttribute(build_gprime_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured_nj = NJ;
-    }
+    const unsigned c_magic = (65536u + (unsigned)C - 1u) / (unsigned)C;
     profile_begin(5, stream);
-    build_gprime_kernel<<<(unsigned)ceil_div_ll(P, GP_PX), 256, smem, stream>>>(gOt, tt, C, NJ, h, w, P, Gp);
+    build_gprime_kernel<<<(unsigned)ceil_div_ll(P, GP_PX), 256, 0, stream>>>(gOt, tt, C, NJ, c_magic, h, w, P, Gp);
     profile_end(5, stream);
     B200SEG_LAUNCH_CHECK();
   }

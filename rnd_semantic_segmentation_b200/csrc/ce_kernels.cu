@@ -32,6 +32,7 @@ struct K2Geom {
   int N, C, h, w, H, W;
   int tiles_x, tiles_y;
   int ispan_max, jspan_max;     // max number of source rows / cols touched by one tile
+  int kmax;                     // max number of tile columns that interpolate from one source column
   float scale_h, scale_w;
 };
 
@@ -56,6 +57,16 @@ static void k2_geometry(K2Geom& g, int N, int C, int h, int w, int H, int W) {
     int hi = host_i0(g.scale_w, xb); hi += (hi < w - 1) ? 1 : 0;
     if (hi - lo + 1 > g.jspan_max) g.jspan_max = hi - lo + 1;
   }
+  // longest run of output columns sharing one x0, doubled (+2): columns with x0 in {j-1, j} feed source column j
+  int run = 0, best = 1, prev = -1;
+  for (int x = 0; x < W; ++x) {
+    const int i0 = host_i0(g.scale_w, x);
+    run = (i0 == prev) ? run + 1 : 1;
+    prev = i0;
+    if (run > best) best = run;
+  }
+  g.kmax = 2 * best + 2;
+  if (g.kmax > K2_TILE_W) g.kmax = K2_TILE_W;
 }
 
 // Workspace layout (floats): [tiles] loss partial | [tiles] valid-count partial | [tiles][ispan][jspan][C] blocks
@@ -79,18 +90,37 @@ struct K2Params {
   float* blocks;             // [tiles][ispan_max][jspan_max][C]
 };
 
+constexpr int K2_PITCH = K2_THREADS + 1;      // stage row pitch (floats): conflict-free for both access patterns
+
+template <int CT>
+__device__ __forceinline__ void k2_load_row(float (&dst)[CT], const float* __restrict__ lg, int C, long long hw, int row, int w,
+                                            const Tap& tapx, float inv_T) {
+  const float* p0 = lg + (long long)row * w + tapx.i0;
+  const float* p1 = lg + (long long)row * w + tapx.i1;
+  const float w0 = inv_T * tapx.l0, w1 = inv_T * tapx.l1;
+#pragma unroll
+  for (int c = 0; c < CT; ++c)
+    if (c < C) {
+      dst[c] = w0 * __ldg(p0) + w1 * __ldg(p1);
+      p0 += hw; p1 += hw;
+    }
+}
+
 template <int CT, bool GRAD>
-__global__ void __launch_bounds__(K2_THREADS) k2_upsample_ce_main(const K2Params p) {
+__global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Params p) {
   extern __shared__ __align__(16) float k2_smem[];
   const K2Geom& g = p.g;
   const int C = g.C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // smem carve-up
-  float* stageA = k2_smem;                           // [CT][128]  (doubles as the -onehot accumulator)
-  float* stageB = stageA + CT * K2_THREADS;          // [CT][128]
-  float* blk = stageB + CT * K2_THREADS;             // [ispan_max][jspan_max][C]
+  float* stage0 = k2_smem;                           // [CT][129]  per-column sums toward register array a0's source row
+  float* stage1 = stage0 + CT * K2_PITCH;            // [CT][129]  ... toward a1's source row  (both start as -onehot sums)
+  float* blk = stage1 + CT * K2_PITCH;               // [ispan_max][jspan_max][C]
   const int blk_floats = g.ispan_max * g.jspan_max * C;
-  float* colw0 = blk + blk_floats;                   // [128] l0x
+  float* wt = blk + blk_floats;                      // [jspan_max][kmax] column -> source-column weights
+  int* red_lo = reinterpret_cast<int*>(wt + g.jspan_max * g.kmax);   // [jspan_max] first contributing column
+  int* red_n = red_lo + g.jspan_max;                 // [jspan_max] number of contributing columns
+  float* colw0 = reinterpret_cast<float*>(red_n + g.jspan_max);      // [128] l0x
   float* colw1 = colw0 + K2_THREADS;                 // [128] l1x
   int* colx0 = reinterpret_cast<int*>(colw1 + K2_THREADS);   // [128] x0 - j_lo
   int* colx1 = colx0 + K2_THREADS;                   // [128] x1 - j_lo
@@ -111,156 +141,158 @@ __global__ void __launch_bounds__(K2_THREADS) k2_upsample_ce_main(const K2Params
   const int y_begin = ty * K2_TILE_H;
   const int y_end = min(g.H, y_begin + K2_TILE_H);
   const int i_lo = (int)(g.scale_h * (float)y_begin);
+  const int jspan = g.jspan_max;
 
   if (GRAD) {
     for (int i = tid; i < blk_floats; i += K2_THREADS) blk[i] = 0.f;
-    for (int i = tid; i < 2 * CT * K2_THREADS; i += K2_THREADS) stageA[i] = 0.f;
+    for (int i = tid; i < 2 * CT * K2_PITCH; i += K2_THREADS) stage0[i] = 0.f;
     colw0[tid] = xvalid ? tapx.l0 : 0.f;
     colw1[tid] = xvalid ? tapx.l1 : 0.f;
     colx0[tid] = tapx.i0 - j_lo;
     colx1[tid] = tapx.i1 - j_lo;
     __syncthreads();
+    if (tid < jspan) {                               // reduce table of source column jj = tid
+      const int jj = tid;
+      int lo = 0, hi = K2_THREADS;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (colx0[mid] < jj - 1) lo = mid + 1; else hi = mid; }
+      int k = 0;
+      for (int col = lo; col < K2_THREADS && colx0[col] <= jj && k < g.kmax; ++col, ++k)
+        wt[jj * g.kmax + k] = (colx0[col] == jj ? colw0[col] : 0.f) + (colx1[col] == jj ? colw1[col] : 0.f);
+      red_lo[jj] = lo;
+      red_n[jj] = k;
+    }
+    __syncthreads();
   }
 
   const float* lg = p.logits + (long long)n * C * hw;
-  const long long* lab_base = p.labels + (long long)n * g.H * g.W + x;
+  const long long* lab_ptr = p.labels + (long long)n * g.H * g.W + x;
 
-  float t[CT], u[CT];
-  float accA[GRAD ? CT : 1], accB[GRAD ? CT : 1];
+  float a0[CT], a1[CT];
+  float acc0[GRAD ? CT : 1], acc1[GRAD ? CT : 1];     // d loss / d a0-row, d loss / d a1-row (softmax part)
   if constexpr (GRAD) {
 #pragma unroll
-    for (int c = 0; c < CT; ++c) { accA[c] = 0.f; accB[c] = 0.f; }
+    for (int c = 0; c < CT; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
   }
-  int row_t = -1, row_u = -1;       // source rows currently held in t / u
-  int seg_i0 = -1, seg_i1 = -1;     // source-row pair of the open accumulation segment
+  int row0 = -1, row1 = -1;         // source rows held in a0 / a1
+  bool swap = false;                // true: a1 is the upper row
+  bool open_seg = false;
   float loss_acc = 0.f, cnt_acc = 0.f;
 
   // Reduce the open segment's per-column sums onto source columns and add them to blk.
   auto flush_segment = [&]() {
     if constexpr (GRAD) {
-    // stage = acc + (-onehot sums already sitting in stage)
 #pragma unroll
-    for (int c = 0; c < CT; ++c)
-      if (c < C) {
-        stageA[c * K2_THREADS + tid] += accA[c];
-        stageB[c * K2_THREADS + tid] += accB[c];
-        accA[c] = 0.f; accB[c] = 0.f;
+      for (int c = 0; c < CT; ++c)
+        if (c < C) {
+          stage0[c * K2_PITCH + tid] += acc0[c];
+          stage1[c * K2_PITCH + tid] += acc1[c];
+          acc0[c] = 0.f; acc1[c] = 0.f;
+        }
+      __syncthreads();
+      const int r0 = row0 - i_lo, r1 = row1 - i_lo;
+      for (int o = tid; o < C * jspan; o += K2_THREADS) {
+        const int jj = o / C;
+        const int c = o - jj * C;
+        const int lo = red_lo[jj], cnt = red_n[jj];
+        const float* wrow = wt + jj * g.kmax;
+        const float* s0 = stage0 + c * K2_PITCH + lo;
+        const float* s1 = stage1 + c * K2_PITCH + lo;
+        float t0 = 0.f, t1 = 0.f;
+        for (int k = 0; k < cnt; ++k) {
+          const float wk = wrow[k];
+          t0 = fmaf(wk, s0[k], t0);
+          t1 = fmaf(wk, s1[k], t1);
+        }
+        blk[(r0 * jspan + jj) * C + c] += t0;
+        blk[(r1 * jspan + jj) * C + c] += t1;
       }
-    __syncthreads();
-    const int jspan = g.jspan_max;
-    const int rowA = seg_i0 - i_lo, rowB = seg_i1 - i_lo;
-    for (int o = tid; o < C * jspan; o += K2_THREADS) {
-      const int c = o / jspan;
-      const int jj = o - c * jspan;
-      float sA = 0.f, sB = 0.f;
-      // columns whose x0 or x1 equals jj: x0 in {jj-1, jj}.  Column -> x0 is monotone, so scan the
-      // 128 columns' window by binary search on colx0.
-      int lo = 0, hi = K2_THREADS;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (colx0[mid] < jj - 1) lo = mid + 1; else hi = mid; }
-      for (int col = lo; col < K2_THREADS && colx0[col] <= jj; ++col) {
-        const float wgt = (colx0[col] == jj ? colw0[col] : 0.f) + (colx1[col] == jj ? colw1[col] : 0.f);
-        sA = fmaf(wgt, stageA[c * K2_THREADS + col], sA);
-        sB = fmaf(wgt, stageB[c * K2_THREADS + col], sB);
-      }
-      blk[(rowA * jspan + jj) * C + c] += sA;
-      blk[(rowB * jspan + jj) * C + c] += sB;
-    }
-    __syncthreads();
+      __syncthreads();
 #pragma unroll
-    for (int c = 0; c < CT; ++c)
-      if (c < C) {
-        stageA[c * K2_THREADS + tid] = 0.f;
-        stageB[c * K2_THREADS + tid] = 0.f;
-      }
-    // (each thread only touches its own stage column between flushes: no barrier needed here)
+      for (int c = 0; c < CT; ++c)
+        if (c < C) {
+          stage0[c * K2_PITCH + tid] = 0.f;
+          stage1[c * K2_PITCH + tid] = 0.f;
+        }
     }
   };
 
+  // label prefetch pipeline, 4 rows deep
+  const long long ign = (long long)p.ignore_index;
+  long long q0 = ign, q1 = ign, q2 = ign, q3 = ign;
+  if (xvalid) {
+    if (y_begin + 0 < y_end) q0 = ld_stream_s64(lab_ptr + (long long)(y_begin + 0) * g.W);
+    if (y_begin + 1 < y_end) q1 = ld_stream_s64(lab_ptr + (long long)(y_begin + 1) * g.W);
+    if (y_begin + 2 < y_end) q2 = ld_stream_s64(lab_ptr + (long long)(y_begin + 2) * g.W);
+    if (y_begin + 3 < y_end) q3 = ld_stream_s64(lab_ptr + (long long)(y_begin + 3) * g.W);
+  }
+
 #pragma unroll 1
-  for (int ys = y_begin; ys < y_end; ys += K2_STRIP) {
-    long long lab[K2_STRIP];
-#pragma unroll
-    for (int r = 0; r < K2_STRIP; ++r) {
-      const int y = ys + r;
-      lab[r] = (xvalid && y < y_end) ? ld_stream_s64(lab_base + (long long)y * g.W) : (long long)p.ignore_index;
-    }
-#pragma unroll 1
-    for (int r = 0; r < K2_STRIP; ++r) {
-      const int y = ys + r;
-      if (y >= y_end) break;                                   // CTA-uniform
-      const Tap tapy = ac_tap(g.scale_h, y, g.h);              // CTA-uniform
-      if (tapy.i0 != seg_i0 || tapy.i1 != seg_i1) {
-        if (seg_i0 >= 0) flush_segment();
-        seg_i0 = tapy.i0; seg_i1 = tapy.i1;
-        if (row_t != tapy.i0) {
-          if (row_u == tapy.i0) {
-#pragma unroll
-            for (int c = 0; c < CT; ++c) t[c] = u[c];
-          } else {
-            const float* r0 = lg + (long long)tapy.i0 * g.w;
-#pragma unroll
-            for (int c = 0; c < CT; ++c)
-              if (c < C) t[c] = p.inv_T * (tapx.l0 * __ldg(r0 + c * hw + tapx.i0) + tapx.l1 * __ldg(r0 + c * hw + tapx.i1));
-          }
-          row_t = tapy.i0;
-        }
-        if (row_u != tapy.i1) {
-          if (row_t == tapy.i1) {
-#pragma unroll
-            for (int c = 0; c < CT; ++c) u[c] = t[c];
-          } else {
-            const float* r1 = lg + (long long)tapy.i1 * g.w;
-#pragma unroll
-            for (int c = 0; c < CT; ++c)
-              if (c < C) u[c] = p.inv_T * (tapx.l0 * __ldg(r1 + c * hw + tapx.i0) + tapx.l1 * __ldg(r1 + c * hw + tapx.i1));
-          }
-          row_u = tapy.i1;
-        }
+  for (int y = y_begin; y < y_end; ++y) {
+    const long long gl = q0;
+    q0 = q1; q1 = q2; q2 = q3;
+    q3 = (xvalid && y + 4 < y_end) ? ld_stream_s64(lab_ptr + (long long)(y + 4) * g.W) : ign;
+
+    const Tap tapy = ac_tap(g.scale_h, y, g.h);              // CTA-uniform
+    const int top = swap ? row1 : row0, bot = swap ? row0 : row1;
+    if (!open_seg || tapy.i0 != top || tapy.i1 != bot) {      // new source-row pair (CTA-uniform branch)
+      if (open_seg) flush_segment();
+      open_seg = true;
+      if (row0 == tapy.i0) {
+        swap = false;
+        if (row1 != tapy.i1) { k2_load_row<CT>(a1, lg, C, hw, tapy.i1, g.w, tapx, p.inv_T); row1 = tapy.i1; }
+      } else if (row1 == tapy.i0) {
+        swap = true;
+        if (row0 != tapy.i1) { k2_load_row<CT>(a0, lg, C, hw, tapy.i1, g.w, tapx, p.inv_T); row0 = tapy.i1; }
+      } else {
+        swap = false;
+        k2_load_row<CT>(a0, lg, C, hw, tapy.i0, g.w, tapx, p.inv_T); row0 = tapy.i0;
+        if (row1 != tapy.i1) { k2_load_row<CT>(a1, lg, C, hw, tapy.i1, g.w, tapx, p.inv_T); row1 = tapy.i1; }
       }
-      const long long gl = lab[r];
-      const bool valid = xvalid && gl != (long long)p.ignore_index && gl >= 0 && gl < C;
-      if (valid) {
-        const int gi = (int)gl;
-        float e[CT];
-        float m = -INFINITY;
+    }
+    const bool valid = xvalid && gl != ign && gl >= 0 && gl < C;
+    if (valid) {
+      const int gi = (int)gl;
+      const float w0 = swap ? tapy.l1 : tapy.l0;             // weight of a0's row, of a1's row
+      const float w1 = swap ? tapy.l0 : tapy.l1;
+      float e[CT];
+      float m = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < CT; ++c)
-          if (c < C) {
-            e[c] = tapy.l0 * t[c] + tapy.l1 * u[c];
-            m = fmaxf(m, e[c]);
-          }
-        // logit of the labelled class: re-interpolate from the (L1-resident) low-res logits
-        const float* q0 = lg + gi * hw + (long long)tapy.i0 * g.w;
-        const float* q1 = lg + gi * hw + (long long)tapy.i1 * g.w;
-        const float vt = p.inv_T * (tapx.l0 * __ldg(q0 + tapx.i0) + tapx.l1 * __ldg(q0 + tapx.i1));
-        const float vu = p.inv_T * (tapx.l0 * __ldg(q1 + tapx.i0) + tapx.l1 * __ldg(q1 + tapx.i1));
-        const float vlab = tapy.l0 * vt + tapy.l1 * vu;
-        float s = 0.f;
-        const float mneg = -m * 1.4426950408889634f;
-#pragma unroll
-        for (int c = 0; c < CT; ++c)
-          if (c < C) {
-            e[c] = fast_exp2(fmaf(e[c], 1.4426950408889634f, mneg));
-            s += e[c];
-          }
-        loss_acc += (m + __logf(s)) - vlab;
-        cnt_acc += 1.f;
-        if constexpr (GRAD) {
-          const float inv_s = __fdividef(1.f, s);
-          const float ca = tapy.l0 * inv_s, cb = tapy.l1 * inv_s;
-#pragma unroll
-          for (int c = 0; c < CT; ++c)
-            if (c < C) {
-              accA[c] = fmaf(ca, e[c], accA[c]);
-              accB[c] = fmaf(cb, e[c], accB[c]);
-            }
-          stageA[gi * K2_THREADS + tid] -= tapy.l0;          // -onehot, thread-private column
-          stageB[gi * K2_THREADS + tid] -= tapy.l1;
+      for (int c = 0; c < CT; ++c)
+        if (c < C) {
+          e[c] = w0 * a0[c] + w1 * a1[c];
+          m = fmaxf(m, e[c]);
         }
+      // logit of the labelled class: re-interpolate from the (L1-resident) low-res logits
+      const float* u0 = lg + gi * hw + (long long)row0 * g.w;
+      const float* u1 = lg + gi * hw + (long long)row1 * g.w;
+      const float v0 = tapx.l0 * __ldg(u0 + tapx.i0) + tapx.l1 * __ldg(u0 + tapx.i1);
+      const float v1 = tapx.l0 * __ldg(u1 + tapx.i0) + tapx.l1 * __ldg(u1 + tapx.i1);
+      const float vlab = p.inv_T * (w0 * v0 + w1 * v1);
+      float s = 0.f;
+      const float mneg = -m * 1.4426950408889634f;
+#pragma unroll
+      for (int c = 0; c < CT; ++c)
+        if (c < C) {
+          e[c] = fast_exp2(fmaf(e[c], 1.4426950408889634f, mneg));
+          s += e[c];
+        }
+      loss_acc += (m + __logf(s)) - vlab;
+      cnt_acc += 1.f;
+      if constexpr (GRAD) {
+        const float inv_s = __fdividef(1.f, s);
+        const float c0 = w0 * inv_s, c1 = w1 * inv_s;
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+          if (c < C) {
+            acc0[c] = fmaf(c0, e[c], acc0[c]);
+            acc1[c] = fmaf(c1, e[c], acc1[c]);
+          }
+        stage0[gi * K2_PITCH + tid] -= w0;                  // -onehot, thread-private column
+        stage1[gi * K2_PITCH + tid] -= w1;
       }
     }
   }
-  if (seg_i0 >= 0) flush_segment();
+  if (open_seg) flush_segment();
 
   // per-tile loss / count partials (fixed-order tree => deterministic)
   loss_acc = warp_sum(loss_acc);
@@ -314,26 +346,32 @@ __global__ void __launch_bounds__(128) k2_finalize_grad(const K2Geom g, const fl
   }
   const int ty0 = ya / K2_TILE_H, ty1 = (yb - 1) / K2_TILE_H;
   const int tx0 = xa / K2_TILE_W, tx1 = (xb - 1) / K2_TILE_W;
-  for (int c = 0; c < g.C; ++c) {
-    float acc = 0.f;
-    for (int ty = ty0; ty <= ty1; ++ty) {
-      const int li = i - (int)(g.scale_h * (float)(ty * K2_TILE_H));
-      if (li < 0 || li >= g.ispan_max) continue;
-      for (int tx = tx0; tx <= tx1; ++tx) {
-        const int lj = j - (int)(g.scale_w * (float)(tx * K2_TILE_W));
-        if (lj < 0 || lj >= g.jspan_max) continue;
-        const long long tile = ((long long)n * g.tiles_y + ty) * g.tiles_x + tx;
-        acc += blocks[tile * blk_floats + ((long long)li * g.jspan_max + lj) * g.C + c];
-      }
+  float acc[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+  for (int ty = ty0; ty <= ty1; ++ty) {
+    const int li = i - (int)(g.scale_h * (float)(ty * K2_TILE_H));
+    if (li < 0 || li >= g.ispan_max) continue;
+    for (int tx = tx0; tx <= tx1; ++tx) {
+      const int lj = j - (int)(g.scale_w * (float)(tx * K2_TILE_W));
+      if (lj < 0 || lj >= g.jspan_max) continue;
+      const long long tile = ((long long)n * g.tiles_y + ty) * g.tiles_x + tx;
+      const float* src = blocks + tile * blk_floats + ((long long)li * g.jspan_max + lj) * g.C;
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < g.C) acc[c] += src[c];
     }
-    dst[c * hw] = acc * scale;
   }
+#pragma unroll
+  for (int c = 0; c < 32; ++c)
+    if (c < g.C) dst[c * hw] = acc[c] * scale;
 }
 
 template <int CT>
 static int k2_main_launch(const K2Params& p, bool grad, cudaStream_t stream) {
   const K2Geom& g = p.g;
-  const size_t smem = ((size_t)2 * CT * K2_THREADS + (size_t)g.ispan_max * g.jspan_max * g.C + 4 * K2_THREADS + 8) * 4;
+  const size_t smem = ((size_t)2 * CT * K2_PITCH + (size_t)g.ispan_max * g.jspan_max * g.C + (size_t)g.jspan_max * (g.kmax + 2) +
+                       4 * K2_THREADS + 8) * 4;
   B200SEG_CHECK_ARG(smem <= 200 * 1024, "upsample_ce: tile footprint %zu B exceeds shared memory (resize ratio too small)", smem);
   const int tiles = (int)k2_tiles(g);
   profile_begin(6, stream);

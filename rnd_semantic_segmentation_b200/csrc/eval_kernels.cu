@@ -52,23 +52,56 @@ __device__ __forceinline__ float lerp2(float wa, float a, float wb, float b) {
   return __fadd_rn(__fmul_rn(wa, a), __fmul_rn(wb, b));       // no contraction
 }
 
-template <int CT, int FMA>
-__device__ __forceinline__ int exact_softmax_argmax(const float (&t)[CT], const float (&u)[CT], int C, float h0, float h1,
-                                                 float m) {
-  // ATen cunn_SpatialSoftMaxForward (dim_threads == 1): sequential float sum, IEEE divide.
+// Exact ATen spatial-softmax sequence for one pixel (rare path): sequential float sum of expf(v - max) in class
+// order, IEEE divide, first maximum.  TOP/BOT select which register array holds the upper source row.
+template <int CT, int FMA, bool SWAP>
+__device__ __forceinline__ int exact_softmax_argmax(const float (&a0)[CT], const float (&a1)[CT], int C, float h0, float h1,
+                                                    float m) {
   float s = 0.f;
 #pragma unroll
   for (int c = 0; c < CT; ++c)
-    if (c < C) s += expf(lerp2<FMA>(h0, t[c], h1, u[c]) - m);
+    if (c < C) s += expf((SWAP ? lerp2<FMA>(h0, a1[c], h1, a0[c]) : lerp2<FMA>(h0, a0[c], h1, a1[c])) - m);
   float pbest = -1.f;
   int idx = 0;
 #pragma unroll
   for (int c = 0; c < CT; ++c)
     if (c < C) {
-      const float pc = expf(lerp2<FMA>(h0, t[c], h1, u[c]) - m) / s;
+      const float pc = expf((SWAP ? lerp2<FMA>(h0, a1[c], h1, a0[c]) : lerp2<FMA>(h0, a0[c], h1, a1[c])) - m) / s;
       if (pc > pbest) { pbest = pc; idx = c; }
     }
   return idx;
+}
+
+// argmax over classes of the interpolated logits of one pixel (first index on ties), with the near-tie rescue.
+template <int CT, int FMA, bool SWAP>
+__device__ __forceinline__ int k4_pixel_argmax(const float (&a0)[CT], const float (&a1)[CT], int C, float h0, float h1) {
+  float best = -INFINITY, second = -INFINITY;
+  int idx = 0;
+#pragma unroll
+  for (int c = 0; c < CT; ++c)
+    if (c < C) {
+      const float v = SWAP ? lerp2<FMA>(h0, a1[c], h1, a0[c]) : lerp2<FMA>(h0, a0[c], h1, a1[c]);
+      const bool gt = v > best;
+      second = fmaxf(second, fminf(best, v));
+      idx = gt ? c : idx;
+      best = fmaxf(best, v);
+    }
+  if (best - second <= K4_NEAR_TIE) idx = exact_softmax_argmax<CT, FMA, SWAP>(a0, a1, C, h0, h1, best);
+  return idx;
+}
+
+// horizontal lerp of one source row for all classes into a register array
+template <int CT, int FMA>
+__device__ __forceinline__ void k4_load_row(float (&dst)[CT], const float* __restrict__ lg, int C, long long hw, int row, int w,
+                                            const Tap& tapx) {
+  const float* p0 = lg + (long long)row * w + tapx.i0;
+  const float* p1 = lg + (long long)row * w + tapx.i1;
+#pragma unroll
+  for (int c = 0; c < CT; ++c)
+    if (c < C) {
+      dst[c] = lerp2<FMA>(tapx.l0, __ldg(p0), tapx.l1, __ldg(p1));
+      p0 += hw; p1 += hw;
+    }
 }
 
 template <int CT, int FMA>
@@ -121,80 +154,62 @@ __global__ void __launch_bounds__(K4_THREADS, 4) k4_upsample_argmax_confusion(co
     const bool xvalid = x < p.W;
     const Tap tapx = ac_tap(p.scale_w, xvalid ? x : p.W - 1, p.w);
     const float* lg = p.logits + (long long)n * C * hw;
-    const long long* lab_base = p.labels ? p.labels + (long long)n * p.H * p.W + x : nullptr;
-    long long* pred_base = p.pred ? p.pred + (long long)n * p.H * p.W + x : nullptr;
+    const long long* lab_ptr = p.labels ? p.labels + (long long)n * p.H * p.W + x : nullptr;
+    long long* pred_ptr = p.pred ? p.pred + (long long)n * p.H * p.W + x : nullptr;
+    const bool load_labels = do_cm && xvalid;
 
-    float t[CT], u[CT];
-    int row_t = -1, row_u = -1;
+    // a0 / a1 hold the horizontally interpolated logits of two source rows; `swap` says which one is the upper row.
+    float a0[CT], a1[CT];
+    int row0 = -1, row1 = -1;
+    bool swap = false;
     const int y_begin = ty * K4_TILE_H;
+    const int y_end = min(p.H, y_begin + K4_TILE_H);
+
+    // label prefetch pipeline, 4 rows deep
+    long long q0 = -1, q1 = -1, q2 = -1, q3 = -1;
+    if (load_labels) {
+      if (y_begin + 0 < y_end) q0 = ld_stream_s64(lab_ptr + (long long)(y_begin + 0) * p.W);
+      if (y_begin + 1 < y_end) q1 = ld_stream_s64(lab_ptr + (long long)(y_begin + 1) * p.W);
+      if (y_begin + 2 < y_end) q2 = ld_stream_s64(lab_ptr + (long long)(y_begin + 2) * p.W);
+      if (y_begin + 3 < y_end) q3 = ld_stream_s64(lab_ptr + (long long)(y_begin + 3) * p.W);
+    }
 
 #pragma unroll 1
-    for (int s = 0; s < K4_TILE_H / K4_STRIP; ++s) {
-      const int ys = y_begin + s * K4_STRIP;
-      if (ys >= p.H) break;
-      long long lab[K4_STRIP];
-#pragma unroll
-      for (int r = 0; r < K4_STRIP; ++r) {
-        const int y = ys + r;
-        lab[r] = (lab_base && xvalid && y < p.H) ? ld_stream_s64(lab_base + (long long)y * p.W) : -1;
+    for (int y = y_begin; y < y_end; ++y) {
+      const long long g = q0;
+      q0 = q1; q1 = q2; q2 = q3;
+      q3 = (load_labels && y + 4 < y_end) ? ld_stream_s64(lab_ptr + (long long)(y + 4) * p.W) : -1;
+
+      const Tap tapy = ac_tap(p.scale_h, y, p.h);                 // warp-uniform
+      const int top = swap ? row1 : row0, bot = swap ? row0 : row1;
+      if (tapy.i0 != top || tapy.i1 != bot) {                      // new source-row pair (uniform branch)
+        if (row0 == tapy.i0) {
+          swap = false;
+          if (row1 != tapy.i1) { k4_load_row<CT, FMA>(a1, lg, C, hw, tapy.i1, p.w, tapx); row1 = tapy.i1; }
+        } else if (row1 == tapy.i0) {
+          swap = true;
+          if (row0 != tapy.i1) { k4_load_row<CT, FMA>(a0, lg, C, hw, tapy.i1, p.w, tapx); row0 = tapy.i1; }
+        } else {
+          swap = false;
+          k4_load_row<CT, FMA>(a0, lg, C, hw, tapy.i0, p.w, tapx); row0 = tapy.i0;
+          if (row1 != tapy.i1) { k4_load_row<CT, FMA>(a1, lg, C, hw, tapy.i1, p.w, tapx); row1 = tapy.i1; }
+        }
       }
-#pragma unroll
-      for (int r = 0; r < K4_STRIP; ++r) {
-        const int y = ys + r;
-        if (y < p.H) {                                            // warp-uniform
-          const Tap tapy = ac_tap(p.scale_h, y, p.h);             // warp-uniform
-          if (row_t != tapy.i0) {
-            if (row_u == tapy.i0) {
-#pragma unroll
-              for (int c = 0; c < CT; ++c) t[c] = u[c];
-            } else {
-              const float* r0 = lg + (long long)tapy.i0 * p.w;
-#pragma unroll
-              for (int c = 0; c < CT; ++c)
-                if (c < C) t[c] = lerp2<FMA>(tapx.l0, __ldg(r0 + c * hw + tapx.i0), tapx.l1, __ldg(r0 + c * hw + tapx.i1));
+      const int idx = swap ? k4_pixel_argmax<CT, FMA, true>(a0, a1, C, tapy.l0, tapy.l1)
+                           : k4_pixel_argmax<CT, FMA, false>(a0, a1, C, tapy.l0, tapy.l1);
+      if (xvalid) {
+        if (pred_ptr) pred_ptr[(long long)y * p.W] = (long long)idx;
+        if (do_cm) {
+          const bool count = (g >= 0) && (g < C) && (g != p.ignore_index);
+          if (p.use_u8) {
+            if (count) {
+              uint8_t* hp = whist + ((int)g * C + idx) * 32 + lane;
+              *hp = (uint8_t)(*hp + 1);
             }
-            row_t = tapy.i0;
-          }
-          if (row_u != tapy.i1) {
-            if (row_t == tapy.i1) {
-#pragma unroll
-              for (int c = 0; c < CT; ++c) u[c] = t[c];
-            } else {
-              const float* r1 = lg + (long long)tapy.i1 * p.w;
-#pragma unroll
-              for (int c = 0; c < CT; ++c)
-                if (c < C) u[c] = lerp2<FMA>(tapx.l0, __ldg(r1 + c * hw + tapx.i0), tapx.l1, __ldg(r1 + c * hw + tapx.i1));
-            }
-            row_u = tapy.i1;
-          }
-          float best = -INFINITY, second = -INFINITY;
-          int idx = 0;
-#pragma unroll
-          for (int c = 0; c < CT; ++c)
-            if (c < C) {
-              const float v = lerp2<FMA>(tapy.l0, t[c], tapy.l1, u[c]);
-              const bool gt = v > best;
-              second = fmaxf(second, fminf(best, v));
-              idx = gt ? c : idx;
-              best = fmaxf(best, v);
-            }
-          if (best - second <= K4_NEAR_TIE) idx = exact_softmax_argmax<CT, FMA>(t, u, C, tapy.l0, tapy.l1, best);
-          if (xvalid) {
-            if (pred_base) pred_base[(long long)y * p.W] = (long long)idx;
-            if (do_cm) {
-              const long long g = lab[r];
-              const bool count = (g >= 0) && (g < C) && (g != p.ignore_index);
-              if (p.use_u8) {
-                if (count) {
-                  uint8_t* hp = whist + ((int)g * C + idx) * 32 + lane;
-                  *hp = (uint8_t)(*hp + 1);
-                }
-              } else {
-                const int bin = count ? (int)g * C + idx : -1;
-                const unsigned peers = __match_any_sync(__activemask(), bin);
-                if (count && lane == (__ffs(peers) - 1)) atomicAdd(&cta_hist[bin], __popc(peers));
-              }
-            }
+          } else {
+            const int bin = count ? (int)g * C + idx : -1;
+            const unsigned peers = __match_any_sync(__activemask(), bin);
+            if (count && lane == (__ffs(peers) - 1)) atomicAdd(&cta_hist[bin], __popc(peers));
           }
         }
       }

@@ -77,6 +77,10 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
   p.img_stride = img_stride;
   p.split_stride = split_stride;
   if (splits_used) *splits_used = p.splits;
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && row_stride % 4 == 0 && split_stride % 4 == 0 &&
+              (col_hw <= 0 || (col_hw % 4 == 0 && img_stride % 4 == 0)))
+                 ? 1
+                 : 0;
 
   CUtensorMap ta, tb;
   int rc;

@@ -29,10 +29,12 @@ constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
 constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;   // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 48 KB
 constexpr int MN_BOX_BYTES = 64 * BLOCK_K * 2;   // one MN-major TMA box: 64 k-rows x 128 B = 8 KB
-constexpr int NUM_THREADS = 256;                 // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
-constexpr int EPI_STAGE_FLOATS = 32 * 33;        // per epilogue warp, padded transpose tile
+constexpr int NUM_THREADS = 384;                 // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-11 epilogue
+constexpr int EPI_WARPS = 8;                     // two per TMEM lane quarter, each owning 128 accumulator columns
+constexpr int EPI_PITCH = 20;                    // floats; 32 rows x 16 cols transpose tile, 16-byte aligned rows
+constexpr int EPI_STAGE_FLOATS = 32 * EPI_PITCH; // per epilogue warp
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 4 * EPI_STAGE_FLOATS * 4 + 256;
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_FLOATS * 4 + 256;
 
 struct Params {
   int M, N, K;
@@ -42,6 +44,7 @@ struct Params {
   int col_hw;               // columns per image (INT_MAX => plain row-major)
   long long img_stride;     // elements between images (used when col_hw != INT_MAX)
   long long split_stride;   // elements between split-K partial slabs
+  int vec_ok;               // output addressing allows 16-byte vector stores
 };
 
 // ------------------------------------------------------------------------------------------
@@ -116,6 +119,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (sm_100 format): start>>4 [0,14), LBO>>4 [16,30),
@@ -147,7 +159,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;                                   // 1024-byte aligned (128B swizzle atom)
   float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 4 * EPI_STAGE_FLOATS * 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_FLOATS * 4);
   uint64_t* full_bar = bars;                  // [STAGES]
   uint64_t* empty_bar = bars + STAGES;        // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
@@ -168,7 +180,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);           // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], EPI_WARPS);   // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -257,9 +269,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    // ================= epilogue (4 warps; warp w owns TMEM lanes [32*(w-4), +32)) =================
-    const int wq = warp - 4;
-    float* stg = epi_stage + wq * EPI_STAGE_FLOATS;
+    // ================= epilogue (8 warps; warp w owns TMEM lanes [32*(w%4), +32) and columns [128*((w-4)/4), +128)) ====
+    const int wq = warp & 3;
+    const int half = (warp - 4) >> 2;
+    float* stg = epi_stage + (warp - 4) * EPI_STAGE_FLOATS;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -268,25 +281,44 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int nt = rem / p.m_tiles;
       const int mt = rem - nt * p.m_tiles;
       const int row_base = mt * BLOCK_M + wq * 32;
-      const int col_base = nt * BLOCK_N;
+      const int col_base = nt * BLOCK_N + half * (BLOCK_N / 2);
       float* out = p.out + (long long)z * p.split_stride;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * (BLOCK_N / 2));
+      const int rows = min(32, p.M - row_base);
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)(c * 32), r);
+      for (int c = 0; c < BLOCK_N / 2 / 16; ++c) {
+        uint32_t r[16];
+        tmem_ld16(taddr + (uint32_t)(c * 16), r);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(r[i]);
+        for (int k = 0; k < 4; ++k)
+          *reinterpret_cast<float4*>(stg + lane * EPI_PITCH + 4 * k) =
+              make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), __uint_as_float(r[4 * k + 2]),
+                          __uint_as_float(r[4 * k + 3]));
         __syncwarp();
-        const int col = col_base + c * 32 + lane;
-        if (col < p.N) {
+        const int col0 = col_base + c * 16;
+        if (p.vec_ok && col0 + 16 <= p.N) {
+          // lane -> (row lane/4 + 8i, 4 columns): every store instruction writes 8 rows x 64 contiguous bytes
+          const int col = col0 + (lane & 3) * 4;
           const int img = col / p.col_hw;
           float* dst = out + (long long)img * p.img_stride + (long long)(col - img * p.col_hw);
-          const int rows = min(32, p.M - row_base);
-          for (int rr = 0; rr < rows; ++rr) dst[(long long)(row_base + rr) * p.row_stride] = stg[rr * 33 + lane];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = (lane >> 2) + 8 * i;
+            if (rr < rows)
+              *reinterpret_cast<float4*>(dst + (long long)(row_base + rr) * p.row_stride) =
+                  *reinterpret_cast<const float4*>(stg + rr * EPI_PITCH + (lane & 3) * 4);
+          }
+        } else {
+          // scalar fallback (ragged N tile or unaligned rows): lane -> (row lane/16 + 2i, column lane%16)
+          const int col = col0 + (lane & 15);
+          if (col < p.N) {
+            const int img = col / p.col_hw;
+            float* dst = out + (long long)img * p.img_stride + (long long)(col - img * p.col_hw);
+            for (int rr = (lane >> 4); rr < rows; rr += 2) dst[(long long)(row_base + rr) * p.row_stride] = stg[rr * EPI_PITCH + (lane & 15)];
+          }
         }
         __syncwarp();
       }

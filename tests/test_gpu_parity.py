@@ -26,7 +26,9 @@ def lib():
     (640, 1024, 2048, False, False, 1, 0),      # fwd shape class
     (640, 777, 2048, False, False, 1, 0),       # ragged N
     (128, 300, 64, False, False, 1, 0),         # single k-block
-    (2048, 1000, 640, False, False, 1, 251),    # dgrad shape class, NCHW column map with odd hw
+    (2048, 1000, 640, False, False, 1, 251),    # dgrad shape class, NCHW column map with odd hw (scalar stores)
+    (2048, 1024, 640, False, False, 1, 256),    # dgrad shape class, aligned images (vector stores)
+    (300, 1000, 128, False, False, 1, 200),
     (640, 2048, 5000, True, True, 3, 0),        # wgrad shape class, MN-major, split-K, ragged K
     (128, 512, 200, True, True, 1, 0),
     (100, 200, 96, False, False, 1, 0),         # ragged M
