@@ -31,6 +31,7 @@ SIGNATURES = {
     "b200seg_upsample_ce_forward": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_f32, c_int, c_vp,
                                             c_i64, c_vp, c_vp]),
     "b200seg_upsample_ce_backward": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp, c_vp]),
+    "b200seg_upsample_ce_backward_packed": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b200seg_upsample_bilinear_forward": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "b200seg_upsample_bilinear_backward": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "b200seg_soft_ce_workspace_bytes": (c_i64, []),
@@ -44,6 +45,8 @@ SIGNATURES = {
     "b200seg_aspp_backward_scratch_bytes": (c_i64, [c_int] * 7),
     "b200seg_aspp_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64, c_int,
                                       c_vp, c_vp, c_vp, c_vp]),
+    "b200seg_aspp_backward_packed": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64, c_int,
+                                             c_vp, c_vp, c_vp]),
     "b200seg_launch_count": (ctypes.c_longlong, []),
     "b200seg_profile_enable": (None, [c_int]),
     "b200seg_profile_read": (c_int, [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int)]),
@@ -188,6 +191,22 @@ def upsample_ce_backward(ws, out2, shape_lr, size, inv_temperature=1.0, grad_out
         _check(lib.b200seg_upsample_ce_backward(ws.data_ptr(), N, C, h, w, H, W, float(inv_temperature), out2.data_ptr(),
                                                 _ptr(grad_out), grad.data_ptr(), _stream()))
     return grad
+
+
+def upsample_ce_backward_packed(ws, out2, shape_lr, size, inv_temperature=1.0, grad_out: Optional[torch.Tensor] = None,
+                                want_bias: bool = True):
+    """Returns (gOt bf16 [N*h*w, 32] pixel-major low-res gradient, bias_grad fp32 [C] | None)."""
+    lib = load()
+    N, C, h, w = shape_lr
+    H, W = size
+    if grad_out is not None:
+        grad_out = _need(grad_out.reshape(1).contiguous(), torch.float32, "grad_out")
+    gOt = torch.empty((N * h * w, 32), dtype=torch.bfloat16, device=ws.device)
+    bias = torch.empty(C, dtype=torch.float32, device=ws.device) if want_bias else None
+    with torch.cuda.device(ws.device):
+        _check(lib.b200seg_upsample_ce_backward_packed(ws.data_ptr(), N, C, h, w, H, W, float(inv_temperature), out2.data_ptr(),
+                                                       _ptr(grad_out), gOt.data_ptr(), _ptr(bias), _stream()))
+    return gOt, bias
 
 
 def upsample_bilinear_forward(x: torch.Tensor, size, fma_mode: int = 0) -> torch.Tensor:
@@ -348,6 +367,28 @@ def aspp_backward(grad_logits: torch.Tensor, Xp: torch.Tensor, WpT: torch.Tensor
                                          scratch.data_ptr(), nbytes, splits, _ptr(gx),
                                          _ptr_array(gws) if gws else None, _ptr_array(gbs) if gbs else None, _stream()))
     return gx, gws, gbs
+
+
+def aspp_backward_packed(gOt: torch.Tensor, Xp: torch.Tensor, WpT: torch.Tensor, rates: Sequence[int], N: int, h: int, w: int,
+                         C: int, need_grad_x: bool = True, need_grad_w: bool = True, splits: int = 0):
+    """Head backward from the packed bf16 gradient.  Returns (grad_x fp32 NCHW | None, [grad_w]*R | None)."""
+    lib = load()
+    _need(gOt, torch.bfloat16, "gOt")
+    Cin = Xp.shape[1]
+    R = len(rates)
+    dev = Xp.device
+    if splits <= 0:
+        splits = default_wgrad_splits(N * h * w, C, Cin, R)
+    nbytes = lib.b200seg_aspp_backward_scratch_bytes(N, Cin, C, h, w, R, splits)
+    scratch = _scratch("aspp_bwd", nbytes, dev)
+    gx = torch.empty((N, Cin, h, w), dtype=torch.float32, device=dev) if need_grad_x else None
+    gws = [torch.empty((C, Cin, 3, 3), dtype=torch.float32, device=dev) for _ in range(R)] if need_grad_w else None
+    rates_arr = (c_int * R)(*[int(r) for r in rates])
+    with torch.cuda.device(dev):
+        _check(lib.b200seg_aspp_backward_packed(gOt.data_ptr(), Xp.data_ptr(), WpT.data_ptr(), rates_arr, R, N, Cin, C, h, w,
+                                                scratch.data_ptr(), nbytes, splits, _ptr(gx), _ptr_array(gws) if gws else None,
+                                                _stream()))
+    return gx, gws
 
 
 def default_wgrad_splits(P: int, C: int, Cin: int, R: int) -> int:

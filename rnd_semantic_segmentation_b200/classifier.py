@@ -64,6 +64,7 @@ class ASPP_Classifier_V2(nn.Module):
     # ---- fused extension (same result as criterion(self(x, size) / T, labels)) --------------
     def forward_loss(self, x, labels, ignore_index: int = 255, temperature: float = 1.0):
         """loss = CrossEntropyLoss(ignore_index)(self(x, labels.shape[-2:]) / temperature, labels) with the
-        upsample fused into the loss (aspp_trainer.py:88-91 / aspp_fada.py:91-95).  Returns (loss, low-res logits)."""
-        logits_lr = self.logits(x)
-        return ops.upsample_cross_entropy(logits_lr, labels, ignore_index, temperature), logits_lr
+        upsample fused into the loss (aspp_trainer.py:88-91 / aspp_fada.py:91-95).  Returns (loss, detached low-res logits);
+        gradients flow through the loss only."""
+        return ops.aspp_head_loss(x, labels, [m.weight for m in self.conv2d_list], [m.bias for m in self.conv2d_list],
+                                  self._rates(), ignore_index, temperature, packed=self._packed_weights())

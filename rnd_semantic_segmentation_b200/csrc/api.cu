@@ -54,6 +54,9 @@ int confusion_pairs_launch(long long*, const long long*, long long, int, int, in
 long long k2_workspace_bytes(int, int, int, int, int, int);
 int k2_forward(const float*, int, int, int, int, const long long*, int, int, int, float, int, void*, long long, float*, cudaStream_t);
 int k2_backward(const void*, int, int, int, int, int, int, float, const float*, const float*, float*, cudaStream_t);
+int k2_backward_packed(void*, int, int, int, int, int, int, float, const float*, const float*, void*, float*, cudaStream_t);
+int aspp_backward_packed(const void*, const void*, const void*, const int*, int, int, int, int, int, int, void*, long long, int, float*,
+                         float* const*, cudaStream_t);
 int upsample_fwd_launch(const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int upsample_bwd_launch(const float*, float*, int, int, int, int, int, cudaStream_t);
 long long k3_workspace_bytes();
@@ -132,6 +135,19 @@ int b200seg_upsample_ce_backward(const void* workspace, int N, int C, int h, int
                                  const float* loss_out2, const float* grad_out, float* grad_logits, void* stream) {
   REQUIRE_DEVICE();
   return k2_backward(workspace, N, C, h, w, H, W, inv_temperature, loss_out2, grad_out, grad_logits, S(stream));
+}
+
+int b200seg_upsample_ce_backward_packed(void* workspace, int N, int C, int h, int w, int H, int W, float inv_temperature,
+                                        const float* loss_out2, const float* grad_out, void* gOt, float* bias_grad, void* stream) {
+  REQUIRE_DEVICE();
+  return k2_backward_packed(workspace, N, C, h, w, H, W, inv_temperature, loss_out2, grad_out, gOt, bias_grad, S(stream));
+}
+
+int b200seg_aspp_backward_packed(const void* gOt, const void* Xp, const void* WpT, const int* rates_host, int R, int N, int Cin, int C,
+                                 int h, int w, void* scratch, int64_t scratch_bytes, int splits, float* grad_x, float* const* grad_w,
+                                 void* stream) {
+  REQUIRE_DEVICE();
+  return aspp_backward_packed(gOt, Xp, WpT, rates_host, R, N, Cin, C, h, w, scratch, scratch_bytes, splits, grad_x, grad_w, S(stream));
 }
 
 int b200seg_upsample_bilinear_forward(const float* in, float* out, int NC, int h, int w, int H, int W, int fma_mode, void* stream) {

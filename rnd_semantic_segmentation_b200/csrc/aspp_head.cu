@@ -185,27 +185,38 @@ constexpr int GP_PX = 16;            // pixels per 256-thread block
 __global__ void __launch_bounds__(256) build_gprime_kernel(const __nv_bfloat16* __restrict__ gOt, TapTable tt, int C, int NJ,
                                                            unsigned c_magic, int h, int w, long long P,
                                                            __nv_bfloat16* __restrict__ Gp) {
+  __shared__ int s_dy[MAX_TAPS + 1], s_dx[MAX_TAPS + 1];
+  if (threadIdx.x <= MAX_TAPS) {
+    const bool in = (int)threadIdx.x < tt.n_taps;
+    s_dy[threadIdx.x] = in ? tt.dy[threadIdx.x] : (1 << 20);      // sentinel: always outside the image
+    s_dx[threadIdx.x] = in ? tt.dx[threadIdx.x] : (1 << 20);
+  }
+  __syncthreads();
   const long long p = (long long)blockIdx.x * GP_PX + (threadIdx.x >> 4);
   if (p >= P) return;
   const int hw = h * w;
   const long long n = p / hw;
   const int s = (int)(p - n * hw);
   const int y = s / w, x = s - y * w;
-  const unsigned short* src = reinterpret_cast<const unsigned short*>(gOt) + n * hw * 32;
+  const unsigned short* img = reinterpret_cast<const unsigned short*>(gOt) + n * hw * 32;
   const int nvec = NJ >> 3;
+  const int ntap = tt.n_taps;
   for (int v8 = threadIdx.x & 15; v8 < nvec; v8 += 16) {
+    const unsigned j0 = (unsigned)(v8 * 8);
+    int t = (int)((j0 * c_magic) >> 16);                       // j0 / C  (exact for j < 1024, C <= 32)
+    int c = (int)(j0 - (unsigned)t * (unsigned)C);
+    const unsigned short* src = nullptr;
+    auto tap_ptr = [&](int tap) -> const unsigned short* {
+      const int tc = tap < ntap ? tap : MAX_TAPS;
+      const int yy = y - s_dy[tc], xx = x - s_dx[tc];
+      return (yy >= 0 && yy < h && xx >= 0 && xx < w) ? img + ((long long)yy * w + xx) * 32 : nullptr;
+    };
+    src = tap_ptr(t);
     unsigned short e[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const unsigned j = (unsigned)(v8 * 8 + k);
-      const unsigned t = (j * c_magic) >> 16;                 // j / C  (exact for j < 1024, C <= 32)
-      unsigned short val = 0;
-      if (t < (unsigned)tt.n_taps) {
-        const int c = (int)(j - t * (unsigned)C);
-        const int yy = y - tt.dy[t], xx = x - tt.dx[t];
-        if (yy >= 0 && yy < h && xx >= 0 && xx < w) val = __ldg(src + ((long long)yy * w + xx) * 32 + c);
-      }
-      e[k] = val;
+      e[k] = src ? __ldg(src + c) : (unsigned short)0;
+      if (++c == C) { c = 0; ++t; src = tap_ptr(t); }
     }
     int4 out;
     out.x = (int)((unsigned)e[0] | ((unsigned)e[1] << 16));
@@ -301,10 +312,23 @@ long long aspp_bwd_scratch_bytes(int N, int Cin, int C, int h, int w, int R, int
   return P * 32 * 2 + 256 + P * NJ * 2 + 256 + (long long)splits * NJ * Cin * 4 + 256;
 }
 
-int aspp_backward(const float* grad_logits, const void* Xp, const void* WpT, const int* rates, int R, int N, int Cin, int C,
-                  int h, int w, void* scratch, long long scratch_bytes, int splits, float* grad_x, float* const* grad_w,
-                  float* const* grad_b, cudaStream_t stream) {
-  B200SEG_CHECK_ARG(grad_logits && Xp && WpT && rates && scratch, "aspp_backward: null pointer");
+// scratch layout: gOt [P][32] bf16 | Gp [P][NJ] bf16 | wpart [S][NJ][Cin] fp32
+static void aspp_bwd_carve(void* scratch, long long P, int NJ, __nv_bfloat16** gOt, __nv_bfloat16** Gp, float** wpart) {
+  uint8_t* sp = reinterpret_cast<uint8_t*>(scratch);
+  *gOt = reinterpret_cast<__nv_bfloat16*>(sp);
+  sp += (P * 32 * 2 + 255) / 256 * 256;
+  *Gp = reinterpret_cast<__nv_bfloat16*>(sp);
+  sp += (P * NJ * 2 + 255) / 256 * 256;
+  *wpart = reinterpret_cast<float*>(sp);
+}
+
+void* aspp_bwd_gOt_ptr(void* scratch) { return scratch; }
+
+// backward GEMMs from the packed bf16 pixel-major output gradient gOt [P][32]
+int aspp_backward_packed(const void* gOt_in, const void* Xp, const void* WpT, const int* rates, int R, int N, int Cin, int C,
+                         int h, int w, void* scratch, long long scratch_bytes, int splits, float* grad_x, float* const* grad_w,
+                         cudaStream_t stream) {
+  B200SEG_CHECK_ARG(gOt_in && Xp && WpT && rates && scratch, "aspp_backward: null pointer");
   B200SEG_CHECK_ARG(R >= 1 && R <= MAX_RATES, "aspp: %d dilation branches unsupported", R);
   B200SEG_CHECK_ARG(C <= 32, "aspp_backward: num_classes=%d > 32 is not supported", C);
   if (splits < 1) splits = 1;
@@ -312,32 +336,18 @@ int aspp_backward(const float* grad_logits, const void* Xp, const void* WpT, con
   const long long P = (long long)N * h * w;
   const int NJ = aspp_nj(C, R);
   const int hw = h * w;
-  uint8_t* sp = reinterpret_cast<uint8_t*>(scratch);
-  __nv_bfloat16* gOt = reinterpret_cast<__nv_bfloat16*>(sp);
-  sp += (P * 32 * 2 + 255) / 256 * 256;
-  __nv_bfloat16* Gp = reinterpret_cast<__nv_bfloat16*>(sp);
-  sp += (P * NJ * 2 + 255) / 256 * 256;
-  float* wpart = reinterpret_cast<float*>(sp);
-
+  __nv_bfloat16 *gOt_own, *Gp;
+  float* wpart;
+  aspp_bwd_carve(scratch, P, NJ, &gOt_own, &Gp, &wpart);
+  const __nv_bfloat16* gOt = reinterpret_cast<const __nv_bfloat16*>(gOt_in);
   TapTable tt;
   make_taps(tt, rates, R);
-  grad_to_pixel_major_kernel<<<(unsigned)ceil_div_ll(P, 256), 256, 0, stream>>>(grad_logits, C, hw, P, gOt);
-  B200SEG_LAUNCH_CHECK();
   {
     const unsigned c_magic = (65536u + (unsigned)C - 1u) / (unsigned)C;
     profile_begin(5, stream);
     build_gprime_kernel<<<(unsigned)ceil_div_ll(P, GP_PX), 256, 0, stream>>>(gOt, tt, C, NJ, c_magic, h, w, P, Gp);
     profile_end(5, stream);
     B200SEG_LAUNCH_CHECK();
-  }
-  if (grad_b) {
-    MutPtrList gb;
-    bool any = false;
-    for (int r = 0; r < MAX_RATES; ++r) { gb.p[r] = r < R ? grad_b[r] : nullptr; any |= gb.p[r] != nullptr; }
-    if (any) {
-      bias_grad_kernel<<<C, 256, 0, stream>>>(grad_logits, N, C, hw, gb, R);
-      B200SEG_LAUNCH_CHECK();
-    }
   }
   if (grad_x) {
     // dX[ci, p] = WpT[ci, :] . G'[p, :]   -> fp32 NCHW: column p = (image, pixel), row = channel
@@ -366,6 +376,32 @@ int aspp_backward(const float* grad_logits, const void* Xp, const void* WpT, con
     }
   }
   return B200SEG_OK;
+}
+
+// backward from the fp32 NCHW output gradient (generic autograd contract)
+int aspp_backward(const float* grad_logits, const void* Xp, const void* WpT, const int* rates, int R, int N, int Cin, int C,
+                  int h, int w, void* scratch, long long scratch_bytes, int splits, float* grad_x, float* const* grad_w,
+                  float* const* grad_b, cudaStream_t stream) {
+  B200SEG_CHECK_ARG(grad_logits && scratch, "aspp_backward: null pointer");
+  B200SEG_CHECK_ARG(R >= 1 && R <= MAX_RATES, "aspp: %d dilation branches unsupported", R);
+  B200SEG_CHECK_ARG(C <= 32, "aspp_backward: num_classes=%d > 32 is not supported", C);
+  if (splits < 1) splits = 1;
+  B200SEG_CHECK_ARG(scratch_bytes >= aspp_bwd_scratch_bytes(N, Cin, C, h, w, R, splits), "aspp_backward: scratch too small");
+  const long long P = (long long)N * h * w;
+  const int hw = h * w;
+  __nv_bfloat16* gOt = reinterpret_cast<__nv_bfloat16*>(scratch);
+  grad_to_pixel_major_kernel<<<(unsigned)ceil_div_ll(P, 256), 256, 0, stream>>>(grad_logits, C, hw, P, gOt);
+  B200SEG_LAUNCH_CHECK();
+  if (grad_b) {
+    MutPtrList gb;
+    bool any = false;
+    for (int r = 0; r < MAX_RATES; ++r) { gb.p[r] = r < R ? grad_b[r] : nullptr; any |= gb.p[r] != nullptr; }
+    if (any) {
+      bias_grad_kernel<<<C, 256, 0, stream>>>(grad_logits, N, C, hw, gb, R);
+      B200SEG_LAUNCH_CHECK();
+    }
+  }
+  return aspp_backward_packed(gOt, Xp, WpT, rates, R, N, Cin, C, h, w, scratch, scratch_bytes, splits, grad_x, grad_w, stream);
 }
 
 }  // namespace b200seg

@@ -73,10 +73,13 @@ static void k2_geometry(K2Geom& g, int N, int C, int h, int w, int H, int W) {
 static long long k2_block_floats(const K2Geom& g) { return (long long)g.ispan_max * g.jspan_max * g.C; }
 static long long k2_tiles(const K2Geom& g) { return (long long)g.N * g.tiles_x * g.tiles_y; }
 
+// per finalize-block partial sums of the low-res gradient (bias gradient), [N*h*ceil(w/128)][32]
+static long long k2_bias_part_floats(const K2Geom& g) { return (long long)g.N * g.h * ceil_div(g.w, 128) * 32; }
+
 long long k2_workspace_bytes(int N, int C, int h, int w, int H, int W) {
   K2Geom g;
   k2_geometry(g, N, C, h, w, H, W);
-  return (2 * k2_tiles(g) + k2_tiles(g) * k2_block_floats(g)) * 4 + 256;
+  return (2 * k2_tiles(g) + k2_tiles(g) * k2_block_floats(g) + k2_bias_part_floats(g)) * 4 + 256;
 }
 
 struct K2Params {
@@ -92,7 +95,7 @@ struct K2Params {
 
 constexpr int K2_PITCH = K2_THREADS + 1;      // stage row pitch (floats): conflict-free for both access patterns
 
-template <int CT>
+template <int CT, bool EXACT>
 __device__ __forceinline__ void k2_load_row(float (&dst)[CT], const float* __restrict__ lg, int C, long long hw, int row, int w,
                                             const Tap& tapx, float inv_T) {
   const float* p0 = lg + (long long)row * w + tapx.i0;
@@ -100,17 +103,17 @@ __device__ __forceinline__ void k2_load_row(float (&dst)[CT], const float* __res
   const float w0 = inv_T * tapx.l0, w1 = inv_T * tapx.l1;
 #pragma unroll
   for (int c = 0; c < CT; ++c)
-    if (c < C) {
+    if (EXACT || c < C) {
       dst[c] = w0 * __ldg(p0) + w1 * __ldg(p1);
       p0 += hw; p1 += hw;
     }
 }
 
-template <int CT, bool GRAD>
+template <int CT, bool GRAD, bool EXACT>
 __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Params p) {
   extern __shared__ __align__(16) float k2_smem[];
   const K2Geom& g = p.g;
-  const int C = g.C;
+  const int C = EXACT ? CT : g.C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // smem carve-up
   float* stage0 = k2_smem;                           // [CT][129]  per-column sums toward register array a0's source row
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
     if constexpr (GRAD) {
 #pragma unroll
       for (int c = 0; c < CT; ++c)
-        if (c < C) {
+        if (EXACT || c < C) {
           stage0[c * K2_PITCH + tid] += acc0[c];
           stage1[c * K2_PITCH + tid] += acc1[c];
           acc0[c] = 0.f; acc1[c] = 0.f;
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
       __syncthreads();
 #pragma unroll
       for (int c = 0; c < CT; ++c)
-        if (c < C) {
+        if (EXACT || c < C) {
           stage0[c * K2_PITCH + tid] = 0.f;
           stage1[c * K2_PITCH + tid] = 0.f;
         }
@@ -239,14 +242,14 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
       open_seg = true;
       if (row0 == tapy.i0) {
         swap = false;
-        if (row1 != tapy.i1) { k2_load_row<CT>(a1, lg, C, hw, tapy.i1, g.w, tapx, p.inv_T); row1 = tapy.i1; }
+        if (row1 != tapy.i1) { k2_load_row<CT, EXACT>(a1, lg, C, hw, tapy.i1, g.w, tapx, p.inv_T); row1 = tapy.i1; }
       } else if (row1 == tapy.i0) {
         swap = true;
-        if (row0 != tapy.i1) { k2_load_row<CT>(a0, lg, C, hw, tapy.i1, g.w, tapx, p.inv_T); row0 = tapy.i1; }
+        if (row0 != tapy.i1) { k2_load_row<CT, EXACT>(a0, lg, C, hw, tapy.i1, g.w, tapx, p.inv_T); row0 = tapy.i1; }
       } else {
         swap = false;
-        k2_load_row<CT>(a0, lg, C, hw, tapy.i0, g.w, tapx, p.inv_T); row0 = tapy.i0;
-        if (row1 != tapy.i1) { k2_load_row<CT>(a1, lg, C, hw, tapy.i1, g.w, tapx, p.inv_T); row1 = tapy.i1; }
+        k2_load_row<CT, EXACT>(a0, lg, C, hw, tapy.i0, g.w, tapx, p.inv_T); row0 = tapy.i0;
+        if (row1 != tapy.i1) { k2_load_row<CT, EXACT>(a1, lg, C, hw, tapy.i1, g.w, tapx, p.inv_T); row1 = tapy.i1; }
       }
     }
     const bool valid = xvalid && gl != ign && gl >= 0 && gl < C;
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
       float m = -INFINITY;
 #pragma unroll
       for (int c = 0; c < CT; ++c)
-        if (c < C) {
+        if (EXACT || c < C) {
           e[c] = w0 * a0[c] + w1 * a1[c];
           m = fmaxf(m, e[c]);
         }
@@ -272,7 +275,7 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
       const float mneg = -m * 1.4426950408889634f;
 #pragma unroll
       for (int c = 0; c < CT; ++c)
-        if (c < C) {
+        if (EXACT || c < C) {
           e[c] = fast_exp2(fmaf(e[c], 1.4426950408889634f, mneg));
           s += e[c];
         }
@@ -283,7 +286,7 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
         const float c0 = w0 * inv_s, c1 = w1 * inv_s;
 #pragma unroll
         for (int c = 0; c < CT; ++c)
-          if (c < C) {
+          if (EXACT || c < C) {
             acc0[c] = fmaf(c0, e[c], acc0[c]);
             acc1[c] = fmaf(c1, e[c], acc1[c]);
           }
@@ -325,49 +328,99 @@ __global__ void __launch_bounds__(256) k2_finalize_loss(const float* loss_part, 
   }
 }
 
-// grad_logits[n,c,i,j] = grad_out * inv_T / n_valid * sum over the tiles touching (i,j) of their partial block.
+// grad[n,c,i,j] = grad_out * inv_T / n_valid * sum over the tiles touching (i,j) of their partial block.
+// PACKED = false: fp32 NCHW grad_logits (the autograd contract of the stand-alone loss op).
+// PACKED = true : bf16 pixel-major gOt[p][32] (what the head's backward GEMMs consume) + per-block fp32 partial sums
+//                 of the gradient per class (-> bias gradient), skipping the NCHW round trip.
+template <bool PACKED>
 __global__ void __launch_bounds__(128) k2_finalize_grad(const K2Geom g, const float* blocks, const float* loss_out2,
-                                                        const float* grad_out, float inv_T, float* grad_logits) {
+                                                        const float* grad_out, float inv_T, float* grad_logits,
+                                                        __nv_bfloat16* gOt, float* bias_part) {
+  __shared__ float wsum[4][32];
   const int j = blockIdx.x * 128 + threadIdx.x;
   const int i = blockIdx.y;
   const int n = blockIdx.z;
-  if (j >= g.w) return;
+  const bool active = j < g.w;
   const float n_valid = loss_out2[1];
   const float scale = (grad_out ? grad_out[0] : 1.f) * inv_T / n_valid;
-  // output rows / cols that interpolate from source row i / col j:  dst in [first(i-1), first(i+1))
-  const int ya = ac_first_dst(g.scale_h, i - 1, g.h, g.H), yb = ac_first_dst(g.scale_h, i + 1, g.h, g.H);
-  const int xa = ac_first_dst(g.scale_w, j - 1, g.w, g.W), xb = ac_first_dst(g.scale_w, j + 1, g.w, g.W);
-  const long long blk_floats = (long long)g.ispan_max * g.jspan_max * g.C;
-  const long long hw = (long long)g.h * g.w;
-  float* dst = grad_logits + (long long)n * g.C * hw + (long long)i * g.w + j;
-  if (ya >= yb || xa >= xb) {
-    for (int c = 0; c < g.C; ++c) dst[c * hw] = 0.f;
-    return;
-  }
-  const int ty0 = ya / K2_TILE_H, ty1 = (yb - 1) / K2_TILE_H;
-  const int tx0 = xa / K2_TILE_W, tx1 = (xb - 1) / K2_TILE_W;
   float acc[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) acc[c] = 0.f;
-  for (int ty = ty0; ty <= ty1; ++ty) {
-    const int li = i - (int)(g.scale_h * (float)(ty * K2_TILE_H));
-    if (li < 0 || li >= g.ispan_max) continue;
-    for (int tx = tx0; tx <= tx1; ++tx) {
-      const int lj = j - (int)(g.scale_w * (float)(tx * K2_TILE_W));
-      if (lj < 0 || lj >= g.jspan_max) continue;
-      const long long tile = ((long long)n * g.tiles_y + ty) * g.tiles_x + tx;
-      const float* src = blocks + tile * blk_floats + ((long long)li * g.jspan_max + lj) * g.C;
+  const long long blk_floats = (long long)g.ispan_max * g.jspan_max * g.C;
+  const long long hw = (long long)g.h * g.w;
+  if (active) {
+    // output rows / cols that interpolate from source row i / col j:  dst in [first(i-1), first(i+1))
+    const int ya = ac_first_dst(g.scale_h, i - 1, g.h, g.H), yb = ac_first_dst(g.scale_h, i + 1, g.h, g.H);
+    const int xa = ac_first_dst(g.scale_w, j - 1, g.w, g.W), xb = ac_first_dst(g.scale_w, j + 1, g.w, g.W);
+    if (ya < yb && xa < xb) {
+      const int ty0 = ya / K2_TILE_H, ty1 = (yb - 1) / K2_TILE_H;
+      const int tx0 = xa / K2_TILE_W, tx1 = (xb - 1) / K2_TILE_W;
+      for (int ty = ty0; ty <= ty1; ++ty) {
+        const int li = i - (int)(g.scale_h * (float)(ty * K2_TILE_H));
+        if (li < 0 || li >= g.ispan_max) continue;
+        for (int tx = tx0; tx <= tx1; ++tx) {
+          const int lj = j - (int)(g.scale_w * (float)(tx * K2_TILE_W));
+          if (lj < 0 || lj >= g.jspan_max) continue;
+          const long long tile = ((long long)n * g.tiles_y + ty) * g.tiles_x + tx;
+          const float* src = blocks + tile * blk_floats + ((long long)li * g.jspan_max + lj) * g.C;
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c < g.C) acc[c] += src[c];
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] *= scale;
+    if (!PACKED) {
+      float* dst = grad_logits + (long long)n * g.C * hw + (long long)i * g.w + j;
 #pragma unroll
       for (int c = 0; c < 32; ++c)
-        if (c < g.C) acc[c] += src[c];
+        if (c < g.C) dst[c * hw] = acc[c];
+    } else {
+      uint32_t wds[16];
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        const __nv_bfloat162 v = __floats2bfloat162_rn(acc[c], acc[c + 1]);     // acc[c >= C] == 0
+        wds[c >> 1] = *reinterpret_cast<const uint32_t*>(&v);
+      }
+      int4* dst = reinterpret_cast<int4*>(gOt + ((long long)n * hw + (long long)i * g.w + j) * 32);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        dst[q] = make_int4((int)wds[4 * q], (int)wds[4 * q + 1], (int)wds[4 * q + 2], (int)wds[4 * q + 3]);
     }
   }
+  if (PACKED) {                       // fixed-order block reduction of the fp32 gradient per class
 #pragma unroll
-  for (int c = 0; c < 32; ++c)
-    if (c < g.C) dst[c * hw] = acc[c] * scale;
+    for (int c = 0; c < 32; ++c) {
+      const float v = warp_sum(acc[c]);
+      if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int c = threadIdx.x;
+      const long long blk_id = ((long long)n * g.h + i) * gridDim.x + blockIdx.x;
+      bias_part[blk_id * 32 + c] = (wsum[0][c] + wsum[1][c]) + (wsum[2][c] + wsum[3][c]);
+    }
+  }
 }
 
-template <int CT>
+// bias_grad[c] = sum over finalize blocks of bias_part[blk][c]  (one block per class, fixed order)
+__global__ void __launch_bounds__(256) k2_bias_from_partials(const float* bias_part, long long nblk, int C, float* bias_grad) {
+  __shared__ double red[8];
+  const int c = blockIdx.x;
+  double acc = 0.0;
+  for (long long b = threadIdx.x; b < nblk; b += 256) acc += (double)bias_part[b * 32 + c];
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int q = 0; q < 8; ++q) t += red[q];
+    bias_grad[c] = (float)t;
+  }
+}
+
+template <int CT, bool EXACT>
 static int k2_main_launch(const K2Params& p, bool grad, cudaStream_t stream) {
   const K2Geom& g = p.g;
   const size_t smem = ((size_t)2 * CT * K2_PITCH + (size_t)g.ispan_max * g.jspan_max * g.C + (size_t)g.jspan_max * (g.kmax + 2) +
@@ -378,17 +431,17 @@ static int k2_main_launch(const K2Params& p, bool grad, cudaStream_t stream) {
   if (grad) {
     static bool configured = false;
     if (!configured) {
-      B200SEG_CUDA(cudaFuncSetAttribute(k2_upsample_ce_main<CT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      B200SEG_CUDA(cudaFuncSetAttribute(k2_upsample_ce_main<CT, true, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       configured = true;
     }
-    k2_upsample_ce_main<CT, true><<<tiles, K2_THREADS, smem, stream>>>(p);
+    k2_upsample_ce_main<CT, true, EXACT><<<tiles, K2_THREADS, smem, stream>>>(p);
   } else {
     static bool configured = false;
     if (!configured) {
-      B200SEG_CUDA(cudaFuncSetAttribute(k2_upsample_ce_main<CT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      B200SEG_CUDA(cudaFuncSetAttribute(k2_upsample_ce_main<CT, false, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       configured = true;
     }
-    k2_upsample_ce_main<CT, false><<<tiles, K2_THREADS, smem, stream>>>(p);
+    k2_upsample_ce_main<CT, false, EXACT><<<tiles, K2_THREADS, smem, stream>>>(p);
   }
   profile_end(6, stream);
   B200SEG_LAUNCH_CHECK();
@@ -410,9 +463,10 @@ int k2_forward(const float* logits, int N, int C, int h, int w, const long long*
   p.cnt_part = p.loss_part + tiles;
   p.blocks = p.cnt_part + tiles;
   int rc;
-  if (C <= 2) rc = k2_main_launch<2>(p, need_grad != 0, stream);
-  else if (C <= 19) rc = k2_main_launch<19>(p, need_grad != 0, stream);
-  else rc = k2_main_launch<32>(p, need_grad != 0, stream);
+  if (C == 2) rc = k2_main_launch<2, true>(p, need_grad != 0, stream);
+  else if (C == 19) rc = k2_main_launch<19, true>(p, need_grad != 0, stream);
+  else if (C <= 8) rc = k2_main_launch<8, false>(p, need_grad != 0, stream);
+  else rc = k2_main_launch<32, false>(p, need_grad != 0, stream);
   if (rc) return rc;
   k2_finalize_loss<<<1, 256, 0, stream>>>(p.loss_part, p.cnt_part, (int)tiles, loss_out2);
   B200SEG_LAUNCH_CHECK();
@@ -427,8 +481,29 @@ int k2_backward(const void* workspace, int N, int C, int h, int w, int H, int W,
   const long long tiles = k2_tiles(g);
   const float* blocks = reinterpret_cast<const float*>(workspace) + 2 * tiles;
   dim3 grid(ceil_div(w, 128), h, N);
-  k2_finalize_grad<<<grid, 128, 0, stream>>>(g, blocks, loss_out2, grad_out, inv_T, grad_logits);
+  k2_finalize_grad<false><<<grid, 128, 0, stream>>>(g, blocks, loss_out2, grad_out, inv_T, grad_logits, nullptr, nullptr);
   B200SEG_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+// Packed form for the fused head+loss path: bf16 pixel-major gradient + bias gradient, no fp32 NCHW tensor.
+int k2_backward_packed(void* workspace, int N, int C, int h, int w, int H, int W, float inv_T, const float* loss_out2,
+                       const float* grad_out, void* gOt, float* bias_grad, cudaStream_t stream) {
+  B200SEG_CHECK_ARG(workspace && loss_out2 && gOt, "upsample_ce_backward_packed: null pointer");
+  B200SEG_CHECK_ARG(C <= 32, "upsample_ce_backward_packed: num_classes=%d > 32 is not supported", C);
+  K2Geom g;
+  k2_geometry(g, N, C, h, w, H, W);
+  const long long tiles = k2_tiles(g);
+  float* base = reinterpret_cast<float*>(workspace);
+  const float* blocks = base + 2 * tiles;
+  float* bias_part = base + 2 * tiles + tiles * k2_block_floats(g);
+  dim3 grid(ceil_div(w, 128), h, N);
+  k2_finalize_grad<true><<<grid, 128, 0, stream>>>(g, blocks, loss_out2, grad_out, inv_T, nullptr, (__nv_bfloat16*)gOt, bias_part);
+  B200SEG_LAUNCH_CHECK();
+  if (bias_grad) {
+    k2_bias_from_partials<<<C, 256, 0, stream>>>(bias_part, (long long)grid.x * grid.y * grid.z, C, bias_grad);
+    B200SEG_LAUNCH_CHECK();
+  }
   return B200SEG_OK;
 }
 

@@ -54,18 +54,18 @@ __device__ __forceinline__ float lerp2(float wa, float a, float wb, float b) {
 
 // Exact ATen spatial-softmax sequence for one pixel (rare path): sequential float sum of expf(v - max) in class
 // order, IEEE divide, first maximum.  TOP/BOT select which register array holds the upper source row.
-template <int CT, int FMA, bool SWAP>
+template <int CT, int FMA, bool SWAP, bool EXACT>
 __device__ __forceinline__ int exact_softmax_argmax(const float (&a0)[CT], const float (&a1)[CT], int C, float h0, float h1,
                                                     float m) {
   float s = 0.f;
 #pragma unroll
   for (int c = 0; c < CT; ++c)
-    if (c < C) s += expf((SWAP ? lerp2<FMA>(h0, a1[c], h1, a0[c]) : lerp2<FMA>(h0, a0[c], h1, a1[c])) - m);
+    if (EXACT || c < C) s += expf((SWAP ? lerp2<FMA>(h0, a1[c], h1, a0[c]) : lerp2<FMA>(h0, a0[c], h1, a1[c])) - m);
   float pbest = -1.f;
   int idx = 0;
 #pragma unroll
   for (int c = 0; c < CT; ++c)
-    if (c < C) {
+    if (EXACT || c < C) {
       const float pc = expf((SWAP ? lerp2<FMA>(h0, a1[c], h1, a0[c]) : lerp2<FMA>(h0, a0[c], h1, a1[c])) - m) / s;
       if (pc > pbest) { pbest = pc; idx = c; }
     }
@@ -73,41 +73,41 @@ __device__ __forceinline__ int exact_softmax_argmax(const float (&a0)[CT], const
 }
 
 // argmax over classes of the interpolated logits of one pixel (first index on ties), with the near-tie rescue.
-template <int CT, int FMA, bool SWAP>
+template <int CT, int FMA, bool SWAP, bool EXACT>
 __device__ __forceinline__ int k4_pixel_argmax(const float (&a0)[CT], const float (&a1)[CT], int C, float h0, float h1) {
   float best = -INFINITY, second = -INFINITY;
   int idx = 0;
 #pragma unroll
   for (int c = 0; c < CT; ++c)
-    if (c < C) {
+    if (EXACT || c < C) {
       const float v = SWAP ? lerp2<FMA>(h0, a1[c], h1, a0[c]) : lerp2<FMA>(h0, a0[c], h1, a1[c]);
       const bool gt = v > best;
       second = fmaxf(second, fminf(best, v));
       idx = gt ? c : idx;
       best = fmaxf(best, v);
     }
-  if (best - second <= K4_NEAR_TIE) idx = exact_softmax_argmax<CT, FMA, SWAP>(a0, a1, C, h0, h1, best);
+  if (best - second <= K4_NEAR_TIE) idx = exact_softmax_argmax<CT, FMA, SWAP, EXACT>(a0, a1, C, h0, h1, best);
   return idx;
 }
 
 // horizontal lerp of one source row for all classes into a register array
-template <int CT, int FMA>
+template <int CT, int FMA, bool EXACT>
 __device__ __forceinline__ void k4_load_row(float (&dst)[CT], const float* __restrict__ lg, int C, long long hw, int row, int w,
                                             const Tap& tapx) {
   const float* p0 = lg + (long long)row * w + tapx.i0;
   const float* p1 = lg + (long long)row * w + tapx.i1;
 #pragma unroll
   for (int c = 0; c < CT; ++c)
-    if (c < C) {
+    if (EXACT || c < C) {
       dst[c] = lerp2<FMA>(tapx.l0, __ldg(p0), tapx.l1, __ldg(p1));
       p0 += hw; p1 += hw;
     }
 }
 
-template <int CT, int FMA>
+template <int CT, int FMA, bool EXACT>
 __global__ void __launch_bounds__(K4_THREADS, 4) k4_upsample_argmax_confusion(const K4Params p) {
   extern __shared__ __align__(16) uint8_t k4_smem[];
-  const int C = p.C, CC = p.C * p.C;
+  const int C = EXACT ? CT : p.C, CC = C * C;
   int* cta_hist = reinterpret_cast<int*>(k4_smem);                       // [CC]
   const int hist_off = ((CC * 4 + 15) / 16) * 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -185,18 +185,18 @@ __global__ void __launch_bounds__(K4_THREADS, 4) k4_upsample_argmax_confusion(co
       if (tapy.i0 != top || tapy.i1 != bot) {                      // new source-row pair (uniform branch)
         if (row0 == tapy.i0) {
           swap = false;
-          if (row1 != tapy.i1) { k4_load_row<CT, FMA>(a1, lg, C, hw, tapy.i1, p.w, tapx); row1 = tapy.i1; }
+          if (row1 != tapy.i1) { k4_load_row<CT, FMA, EXACT>(a1, lg, C, hw, tapy.i1, p.w, tapx); row1 = tapy.i1; }
         } else if (row1 == tapy.i0) {
           swap = true;
-          if (row0 != tapy.i1) { k4_load_row<CT, FMA>(a0, lg, C, hw, tapy.i1, p.w, tapx); row0 = tapy.i1; }
+          if (row0 != tapy.i1) { k4_load_row<CT, FMA, EXACT>(a0, lg, C, hw, tapy.i1, p.w, tapx); row0 = tapy.i1; }
         } else {
           swap = false;
-          k4_load_row<CT, FMA>(a0, lg, C, hw, tapy.i0, p.w, tapx); row0 = tapy.i0;
-          if (row1 != tapy.i1) { k4_load_row<CT, FMA>(a1, lg, C, hw, tapy.i1, p.w, tapx); row1 = tapy.i1; }
+          k4_load_row<CT, FMA, EXACT>(a0, lg, C, hw, tapy.i0, p.w, tapx); row0 = tapy.i0;
+          if (row1 != tapy.i1) { k4_load_row<CT, FMA, EXACT>(a1, lg, C, hw, tapy.i1, p.w, tapx); row1 = tapy.i1; }
         }
       }
-      const int idx = swap ? k4_pixel_argmax<CT, FMA, true>(a0, a1, C, tapy.l0, tapy.l1)
-                           : k4_pixel_argmax<CT, FMA, false>(a0, a1, C, tapy.l0, tapy.l1);
+      const int idx = swap ? k4_pixel_argmax<CT, FMA, true, EXACT>(a0, a1, C, tapy.l0, tapy.l1)
+                           : k4_pixel_argmax<CT, FMA, false, EXACT>(a0, a1, C, tapy.l0, tapy.l1);
       if (xvalid) {
         if (pred_ptr) pred_ptr[(long long)y * p.W] = (long long)idx;
         if (do_cm) {
@@ -244,28 +244,28 @@ __global__ void __launch_bounds__(K4_THREADS, 4) k4_upsample_argmax_confusion(co
   }
 }
 
-template <int CT, int FMA>
+template <int CT, int FMA, bool EXACT>
 static int k4_launch_t(const K4Params& p, int grid, size_t smem, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    B200SEG_CUDA(cudaFuncSetAttribute(k4_upsample_argmax_confusion<CT, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200SEG_CUDA(cudaFuncSetAttribute(k4_upsample_argmax_confusion<CT, FMA, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       100 * 1024));
     configured = true;
   }
   profile_begin(7, stream);
-  k4_upsample_argmax_confusion<CT, FMA><<<grid, K4_THREADS, smem, stream>>>(p);
+  k4_upsample_argmax_confusion<CT, FMA, EXACT><<<grid, K4_THREADS, smem, stream>>>(p);
   profile_end(7, stream);
   B200SEG_LAUNCH_CHECK();
   return B200SEG_OK;
 }
 
-template <int CT>
+template <int CT, bool EXACT>
 static int k4_launch_c(const K4Params& p, int fma_mode, int grid, size_t smem, cudaStream_t stream) {
   switch (fma_mode) {
-    case 0: return k4_launch_t<CT, 0>(p, grid, smem, stream);
-    case 1: return k4_launch_t<CT, 1>(p, grid, smem, stream);
-    case 2: return k4_launch_t<CT, 2>(p, grid, smem, stream);
-    default: return k4_launch_t<CT, 3>(p, grid, smem, stream);
+    case 0: return k4_launch_t<CT, 0, EXACT>(p, grid, smem, stream);
+    case 1: return k4_launch_t<CT, 1, EXACT>(p, grid, smem, stream);
+    case 2: return k4_launch_t<CT, 2, EXACT>(p, grid, smem, stream);
+    default: return k4_launch_t<CT, 3, EXACT>(p, grid, smem, stream);
   }
 }
 
@@ -293,9 +293,10 @@ int k4_launch(const float* logits, int N, int C, int h, int w, const long long* 
   int grid = p.total_tiles < max_ctas ? p.total_tiles : max_ctas;
   p.tiles_per_cta = ceil_div(p.total_tiles, grid);
   grid = ceil_div(p.total_tiles, p.tiles_per_cta);
-  if (C <= 2) return k4_launch_c<2>(p, fma_mode, grid, smem, stream);
-  if (C == 19) return k4_launch_c<19>(p, fma_mode, grid, smem, stream);
-  return k4_launch_c<32>(p, fma_mode, grid, smem, stream);
+  if (C == 2) return k4_launch_c<2, true>(p, fma_mode, grid, smem, stream);
+  if (C == 19) return k4_launch_c<19, true>(p, fma_mode, grid, smem, stream);
+  if (C <= 8) return k4_launch_c<8, false>(p, fma_mode, grid, smem, stream);
+  return k4_launch_c<32, false>(p, fma_mode, grid, smem, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

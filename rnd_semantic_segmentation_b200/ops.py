@@ -66,6 +66,56 @@ def aspp_head(x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence
     return _AsppHeadFn.apply(x, tuple(int(r) for r in rates), packed, *weights, *biases)
 
 
+class _AsppHeadLossFn(torch.autograd.Function):
+    """Fused train slice: head forward -> upsample + CE forward, and in backward CE/upsample backward -> head dgrad /
+    wgrad with the low-res gradient handed over as packed bf16 (no fp32 NCHW gradient, no transposes)."""
+
+    @staticmethod
+    def forward(ctx, x, labels, ignore_index, temperature, rates, packed, *params):
+        R = len(rates)
+        weights, biases = params[:R], params[R:]
+        N, Cin, h, w = x.shape
+        C = weights[0].shape[0]
+        if packed is None:
+            packed = _lib.aspp_pack_weights([p.detach() for p in weights], [None if b is None else b.detach() for b in biases])
+        Wp, WpT, bias_sum = packed
+        Xp = _pixel_major_bf16(x.detach())
+        logits = _lib.aspp_forward(Xp, Wp, bias_sum, rates, N, h, w, C)
+        need_grad = any(ctx.needs_input_grad)
+        inv_t = 1.0 / float(temperature)
+        out2, ws = _lib.upsample_ce_forward(logits, labels.contiguous(), ignore_index, inv_t, need_grad)
+        ctx.meta = (tuple(rates), (N, Cin, h, w, C), tuple(labels.shape[-2:]), inv_t, x.dtype, need_grad)
+        ctx.save_for_backward(Xp, WpT, out2, ws)
+        ctx.mark_non_differentiable(logits)
+        return out2[0].clone(), logits
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_logits_unused):
+        Xp, WpT, out2, ws = ctx.saved_tensors
+        rates, (N, Cin, h, w, C), size, inv_t, x_dtype, need_grad = ctx.meta
+        if not need_grad:
+            raise _lib.B200SegError("forward_loss: forward ran without gradient tracking")
+        R = len(rates)
+        need = ctx.needs_input_grad
+        need_w = any(need[6:6 + R])
+        need_b = any(need[6 + R:6 + 2 * R])
+        gOt, bias = _lib.upsample_ce_backward_packed(ws, out2, (N, C, h, w), size, inv_t, grad_loss.detach().float(), need_b)
+        gx, gws = _lib.aspp_backward_packed(gOt, Xp, WpT, rates, N, h, w, C, need[0], need_w)
+        if gx is not None and x_dtype != torch.float32:
+            gx = gx.to(x_dtype)
+        out_w = [gws[r] if (gws is not None and need[6 + r]) else None for r in range(R)]
+        out_b = [(bias if r == 0 else bias.clone()) if (bias is not None and need[6 + R + r]) else None for r in range(R)]
+        return (gx, None, None, None, None, None, *out_w, *out_b)
+
+
+def aspp_head_loss(x, labels, weights, biases, rates, ignore_index=255, temperature=1.0, packed=None):
+    """(loss, low-res logits [detached]) == CrossEntropyLoss(ignore_index)(interpolate(head(x), labels.shape[-2:]) / T, labels)."""
+    if labels.dtype != torch.int64:
+        labels = labels.long()
+    return _AsppHeadLossFn.apply(x, labels, int(ignore_index), float(temperature), tuple(int(r) for r in rates), packed,
+                                 *weights, *biases)
+
+
 # --------------------------------------------------------------------------------------------
 # materialising align-corners bilinear upsample (API-compat path)
 # --------------------------------------------------------------------------------------------
