@@ -100,6 +100,23 @@ B200SEG_API int b200seg_soft_ce_backward(const float* pred, const float* soft, c
                              int K, int H, int W, float* grad_pred, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K5  FADA PixelDiscriminator loss tail, fused on low-resolution tensors
+ *   replaces  F.interpolate(cat(cls1, cls2), size, align_corners=True)     core/models/discriminator.py:47-49
+ *             softmax(seg_pred / T).detach(); soft[soft > 0.9] = 0.9        core/combos/aspp_fada.py:93-94,99-100,104-108
+ *             cat((soft, 0)) [slot 0]  /  cat((0, soft)) [slot 1]           core/combos/aspp_fada.py:111,120,124
+ *             soft_label_cross_entropy(D_pred, soft_label) + backward       core/utils/utility.py:172-177
+ *   d_logits [N,2C,h,w] f32 (low-res discriminator output), seg_logits [N,C,h,w] f32 (low-res head output, treated
+ *   as constant like the reference's .detach()).  loss_out2 = { loss, N*H*W }.  grad_d_logits [N,2C,h,w] f32.
+ *   Fused instantiations: C == 19 (Cityscapes/GTA5) and C == 2 (Kvasir/BLI); other class counts use the materialised K3 path.
+ * ------------------------------------------------------------------------------------------- */
+B200SEG_API int64_t b200seg_fada_softce_workspace_bytes(int N, int C, int h, int w, int H, int W);
+B200SEG_API int b200seg_fada_softce_forward(const float* d_logits, const float* seg_logits, int N, int C, int h, int w, int H, int W,
+                                float inv_temperature, float clamp, int slot, int need_grad, void* workspace,
+                                int64_t workspace_bytes, float* loss_out2, void* stream);
+B200SEG_API int b200seg_fada_softce_backward(const void* workspace, int N, int C, int h, int w, int H, int W,
+                                 const float* loss_out2, const float* grad_out, float* grad_d_logits, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K1  fused multi-dilation ASPP head (tcgen05 tap-packed GEMMs)
  *   replaces  ASPP_Classifier_V2.forward (size=None part)   core/models/classifiers/aspp/classifier.py:26-29
  *   R dilation branches (padding == dilation), weights R x [C,Cin,3,3] f32, biases R x [C] f32.
@@ -130,7 +147,7 @@ B200SEG_API int b200seg_aspp_backward_packed(const void* gOt, const void* Xp, co
  * instrumentation (bench.py): number of kernels this library has launched, and per-kernel CUDA-event
  * timing on the launching stream.  Tags: 0 head fwd GEMM, 1 head dgrad GEMM, 2 head wgrad GEMM,
  * 3 feature pack, 4 fwd gather, 5 grad im2col (G'), 6 upsample+CE main, 7 eval argmax+confusion,
- * 8 soft-CE fwd, 9 soft-CE bwd, 10 wgrad reduce.
+ * 8 soft-CE fwd, 9 soft-CE bwd, 10 wgrad reduce, 11 fused FADA soft-CE main.
  * ------------------------------------------------------------------------------------------- */
 B200SEG_API long long b200seg_launch_count(void);
 B200SEG_API void b200seg_profile_enable(int on);

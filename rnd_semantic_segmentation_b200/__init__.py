@@ -9,14 +9,14 @@ from .build import build_adversarial_discriminator, build_classifier, build_feat
 from .classifier import ASPP_Classifier_V2
 from .discriminator import PixelDiscriminator
 from .install import install
-from .ops import (aspp_head, soft_label_cross_entropy, upsample_bilinear_align_corners, upsample_cross_entropy)
+from .ops import (aspp_head, aspp_head_loss, fada_soft_label_loss, soft_label_cross_entropy, upsample_bilinear_align_corners, upsample_cross_entropy)
 from .utility import (AverageMeter, confusion_matrix, inference, intersectionAndUnion, intersectionAndUnionGPU,
                       iutr_from_confusion, segmentation_eval_step)
 
 __all__ = [
     "build_feature_extractor", "build_classifier", "build_adversarial_discriminator",
     "ASPP_Classifier_V2", "PixelDiscriminator", "install",
-    "aspp_head", "upsample_bilinear_align_corners", "upsample_cross_entropy", "soft_label_cross_entropy",
+    "aspp_head", "aspp_head_loss", "fada_soft_label_loss", "upsample_bilinear_align_corners", "upsample_cross_entropy", "soft_label_cross_entropy",
     "inference", "intersectionAndUnion", "intersectionAndUnionGPU", "confusion_matrix", "AverageMeter",
     "segmentation_eval_step", "iutr_from_confusion",
 ]

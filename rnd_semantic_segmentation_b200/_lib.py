@@ -37,6 +37,10 @@ SIGNATURES = {
     "b200seg_soft_ce_workspace_bytes": (c_i64, []),
     "b200seg_soft_ce_forward": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_vp]),
     "b200seg_soft_ce_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "b200seg_fada_softce_workspace_bytes": (c_i64, [c_int] * 6),
+    "b200seg_fada_softce_forward": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_f32, c_int, c_int, c_vp, c_i64,
+                                            c_vp, c_vp]),
+    "b200seg_fada_softce_backward": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "b200seg_aspp_packed_rows": (c_int, [c_int, c_int]),
     "b200seg_aspp_pack_weights": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "b200seg_aspp_pack_features": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
@@ -266,6 +270,45 @@ def soft_ce_backward(pred, soft, weights, grad_out) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------
+# K5  fused FADA discriminator loss tail
+# --------------------------------------------------------------------------------------------
+def fada_softce_supported(num_classes: int) -> bool:
+    return num_classes in (2, 19)
+
+
+def fada_softce_forward(d_logits, seg_logits, size, slot: int, inv_temperature: float, clamp: float, need_grad: bool = True):
+    lib = load()
+    _need(d_logits, torch.float32, "d_logits")
+    _need(seg_logits, torch.float32, "seg_logits")
+    N, K, h, w = d_logits.shape
+    C = seg_logits.shape[1]
+    if K != 2 * C or tuple(seg_logits.shape) != (N, C, h, w):
+        raise B200SegError(f"d_logits {tuple(d_logits.shape)} must be [N,2C,h,w] for seg_logits {tuple(seg_logits.shape)}")
+    H, W = int(size[0]), int(size[1])
+    nbytes = lib.b200seg_fada_softce_workspace_bytes(N, C, h, w, H, W)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=d_logits.device)
+    out2 = torch.empty(2, dtype=torch.float32, device=d_logits.device)
+    with torch.cuda.device(d_logits.device):
+        _check(lib.b200seg_fada_softce_forward(d_logits.data_ptr(), seg_logits.data_ptr(), N, C, h, w, H, W, float(inv_temperature),
+                                               float(clamp), int(slot), 1 if need_grad else 0, ws.data_ptr(), nbytes,
+                                               out2.data_ptr(), _stream()))
+    return out2, ws
+
+
+def fada_softce_backward(ws, out2, shape_d, size, grad_out: Optional[torch.Tensor] = None):
+    lib = load()
+    N, K, h, w = shape_d
+    H, W = size
+    if grad_out is not None:
+        grad_out = _need(grad_out.reshape(1).contiguous(), torch.float32, "grad_out")
+    grad = torch.empty((N, K, h, w), dtype=torch.float32, device=ws.device)
+    with torch.cuda.device(ws.device):
+        _check(lib.b200seg_fada_softce_backward(ws.data_ptr(), N, K // 2, h, w, H, W, out2.data_ptr(), _ptr(grad_out),
+                                                grad.data_ptr(), _stream()))
+    return grad
+
+
+# --------------------------------------------------------------------------------------------
 # K1
 # --------------------------------------------------------------------------------------------
 def _ptr_array(tensors: Sequence[Optional[torch.Tensor]]):
@@ -410,7 +453,7 @@ def gemm_selftest(M, N, K, a_mn=False, b_mn=False, splits=1, col_hw=0):
 
 PROFILE_TAGS = {"head_fwd_gemm": 0, "head_dgrad_gemm": 1, "head_wgrad_gemm": 2, "pack_features": 3, "head_gather": 4,
                 "grad_im2col": 5, "upsample_ce_main": 6, "eval_argmax_confusion": 7, "soft_ce_fwd": 8, "soft_ce_bwd": 9,
-                "wgrad_reduce": 10}
+                "wgrad_reduce": 10, "fada_softce_main": 11}
 
 
 def launch_count() -> int:

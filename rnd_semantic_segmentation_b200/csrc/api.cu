@@ -70,6 +70,9 @@ int aspp_forward(const void*, const void*, const float*, const int*, int, int, i
 long long aspp_bwd_scratch_bytes(int, int, int, int, int, int, int);
 int aspp_backward(const float*, const void*, const void*, const int*, int, int, int, int, int, int, void*, long long, int, float*,
                   float* const*, float* const*, cudaStream_t);
+long long k5_workspace_bytes(int, int, int, int, int, int);
+int k5_forward(const float*, const float*, int, int, int, int, int, int, float, float, int, int, void*, long long, float*, cudaStream_t);
+int k5_backward(const void*, int, int, int, int, int, int, const float*, const float*, float*, cudaStream_t);
 namespace gemm {
 int selftest(int, int, int, int, int, int, int, double*, double*);
 }
@@ -172,6 +175,25 @@ int b200seg_soft_ce_backward(const float* pred, const float* soft, const float* 
                              int W, float* grad_pred, void* stream) {
   REQUIRE_DEVICE();
   return k3_backward(pred, soft, weights, grad_out, N, K, H, W, grad_pred, S(stream));
+}
+
+int64_t b200seg_fada_softce_workspace_bytes(int N, int C, int h, int w, int H, int W) {
+  if (N <= 0 || C <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return 0;
+  return k5_workspace_bytes(N, C, h, w, H, W);
+}
+
+int b200seg_fada_softce_forward(const float* d_logits, const float* seg_logits, int N, int C, int h, int w, int H, int W,
+                                float inv_temperature, float clamp, int slot, int need_grad, void* workspace, int64_t workspace_bytes,
+                                float* loss_out2, void* stream) {
+  REQUIRE_DEVICE();
+  return k5_forward(d_logits, seg_logits, N, C, h, w, H, W, inv_temperature, clamp, slot, need_grad, workspace, workspace_bytes,
+                    loss_out2, S(stream));
+}
+
+int b200seg_fada_softce_backward(const void* workspace, int N, int C, int h, int w, int H, int W, const float* loss_out2,
+                                 const float* grad_out, float* grad_d_logits, void* stream) {
+  REQUIRE_DEVICE();
+  return k5_backward(workspace, N, C, h, w, H, W, loss_out2, grad_out, grad_d_logits, S(stream));
 }
 
 int b200seg_aspp_packed_rows(int C, int R) { return aspp_nj(C, R); }

@@ -507,6 +507,353 @@ int k2_backward_packed(void* workspace, int N, int C, int h, int w, int H, int W
   return B200SEG_OK;
 }
 
+// =============================================================================================
+// K5: the FADA PixelDiscriminator loss tail, fully fused on LOW-RESOLUTION tensors.
+//
+// Replaces, per call (reference file:line):
+//   F.interpolate(cat(cls1, cls2), size, 'bilinear', align_corners=True)   core/models/discriminator.py:47-49
+//   F.softmax(seg_pred / 1.8).detach(); soft[soft > 0.9] = 0.9              core/combos/aspp_fada.py:93-94,99-100,104-108
+//   torch.cat((soft, zeros)) / torch.cat((zeros, soft))                     core/combos/aspp_fada.py:111,120,124
+//   soft_label_cross_entropy(D_pred, soft_label) and its backward           core/utils/utility.py:172-177
+// None of the five full-resolution [N,2C,H,W] / [N,C,H,W] tensors is materialised: per output pixel the kernel
+// interpolates the 2C discriminator logits and the C segmentation logits from register-resident horizontal lerps,
+// builds q = min(softmax(seg / T), clamp) on the fly, accumulates  lse(D) * sum(q) - sum_c q_c * D[slot*C + c]  and folds
+// (softmax(D) * sum(q) - q) back onto the low-res discriminator logits with the same deterministic tile-partial scheme
+// as K2.  Purely compute-bound (the only inputs are the low-res tensors).
+// =============================================================================================
+struct K5Params {
+  K2Geom g;                  // geometry with g.C = 2*C (channels of the gradient blocks)
+  const float* dlogits;      // [N, 2C, h, w]
+  const float* slogits;      // [N,  C, h, w]
+  float inv_T, clamp;
+  float* loss_part;          // [tiles]
+  float* blocks;             // [tiles][ispan_max][jspan_max][2C]
+};
+
+template <int NCH, bool EXACT>
+__device__ __forceinline__ void k5_load_row(float (&dst)[NCH], const float* __restrict__ lg, int nch, long long hw, int row, int w,
+                                            const Tap& tapx, float prescale) {
+  const float* p0 = lg + (long long)row * w + tapx.i0;
+  const float* p1 = lg + (long long)row * w + tapx.i1;
+  const float w0 = prescale * tapx.l0, w1 = prescale * tapx.l1;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+    if (EXACT || c < nch) {
+      dst[c] = w0 * __ldg(p0) + w1 * __ldg(p1);
+      p0 += hw; p1 += hw;
+    }
+}
+
+template <int CT, bool GRAD, bool EXACT, int SLOT>
+__global__ void __launch_bounds__(K2_THREADS, 2) k5_fada_softce_main(const K5Params p) {
+  constexpr int KT = 2 * CT;
+  constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+  extern __shared__ __align__(16) float k2_smem[];
+  const K2Geom& g = p.g;
+  const int C = EXACT ? CT : g.C / 2;
+  const int K = 2 * C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* stage0 = k2_smem;                           // [KT][129]
+  float* stage1 = stage0 + KT * K2_PITCH;            // [KT][129]
+  float* blk = stage1 + KT * K2_PITCH;               // [ispan_max][jspan_max][K]
+  const int blk_floats = g.ispan_max * g.jspan_max * K;
+  float* wt = blk + blk_floats;
+  int* red_lo = reinterpret_cast<int*>(wt + g.jspan_max * g.kmax);
+  int* red_n = red_lo + g.jspan_max;
+  float* colw0 = reinterpret_cast<float*>(red_n + g.jspan_max);
+  float* colw1 = colw0 + K2_THREADS;
+  int* colx0 = reinterpret_cast<int*>(colw1 + K2_THREADS);
+  int* colx1 = colx0 + K2_THREADS;
+  float* red = reinterpret_cast<float*>(colx1 + K2_THREADS);
+
+  const int tile = blockIdx.x;
+  const int tiles_per_frame = g.tiles_x * g.tiles_y;
+  const int n = tile / tiles_per_frame;
+  const int trem = tile - n * tiles_per_frame;
+  const int ty = trem / g.tiles_x;
+  const int tx = trem - ty * g.tiles_x;
+  const long long hw = (long long)g.h * g.w;
+  const int x = tx * K2_TILE_W + tid;
+  const bool xvalid = x < g.W;
+  const Tap tapx = ac_tap(g.scale_w, xvalid ? x : g.W - 1, g.w);
+  const int j_lo = (int)(g.scale_w * (float)(tx * K2_TILE_W));
+  const int y_begin = ty * K2_TILE_H;
+  const int y_end = min(g.H, y_begin + K2_TILE_H);
+  const int i_lo = (int)(g.scale_h * (float)y_begin);
+  const int jspan = g.jspan_max;
+
+  if (GRAD) {
+    for (int i = tid; i < blk_floats; i += K2_THREADS) blk[i] = 0.f;
+    colw0[tid] = xvalid ? tapx.l0 : 0.f;
+    colw1[tid] = xvalid ? tapx.l1 : 0.f;
+    colx0[tid] = tapx.i0 - j_lo;
+    colx1[tid] = tapx.i1 - j_lo;
+    __syncthreads();
+    if (tid < jspan) {
+      const int jj = tid;
+      int lo = 0, hi = K2_THREADS;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (colx0[mid] < jj - 1) lo = mid + 1; else hi = mid; }
+      int k = 0;
+      for (int col = lo; col < K2_THREADS && colx0[col] <= jj && k < g.kmax; ++col, ++k)
+        wt[jj * g.kmax + k] = (colx0[col] == jj ? colw0[col] : 0.f) + (colx1[col] == jj ? colw1[col] : 0.f);
+      red_lo[jj] = lo;
+      red_n[jj] = k;
+    }
+    __syncthreads();
+  }
+
+  const float* dl = p.dlogits + (long long)n * K * hw;
+  const float* sl = p.slogits + (long long)n * C * hw;
+
+  // d*: discriminator logits * log2(e); s*: segmentation logits * log2(e) / T   (exp2 domain)
+  float d0[KT], d1[KT], s0[CT], s1[CT];
+  float acc0[GRAD ? KT : 1], acc1[GRAD ? KT : 1];
+  if constexpr (GRAD) {
+#pragma unroll
+    for (int k = 0; k < KT; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; }
+  }
+  int row0 = -1, row1 = -1;
+  bool swap = false, open_seg = false;
+  float loss_acc = 0.f;
+
+  auto flush_segment = [&]() {
+    if constexpr (GRAD) {
+#pragma unroll
+      for (int k = 0; k < KT; ++k)
+        if (EXACT || k < K) {
+          stage0[k * K2_PITCH + tid] = acc0[k];
+          stage1[k * K2_PITCH + tid] = acc1[k];
+          acc0[k] = 0.f; acc1[k] = 0.f;
+        }
+      __syncthreads();
+      const int r0 = row0 - i_lo, r1 = row1 - i_lo;
+      for (int o = tid; o < K * jspan; o += K2_THREADS) {
+        const int jj = o / K;
+        const int k = o - jj * K;
+        const int lo = red_lo[jj], cnt = red_n[jj];
+        const float* wrow = wt + jj * g.kmax;
+        const float* q0 = stage0 + k * K2_PITCH + lo;
+        const float* q1 = stage1 + k * K2_PITCH + lo;
+        float t0 = 0.f, t1 = 0.f;
+        for (int i = 0; i < cnt; ++i) {
+          const float wk = wrow[i];
+          t0 = fmaf(wk, q0[i], t0);
+          t1 = fmaf(wk, q1[i], t1);
+        }
+        blk[(r0 * jspan + jj) * K + k] += t0;
+        blk[(r1 * jspan + jj) * K + k] += t1;
+      }
+      __syncthreads();
+    }
+  };
+
+#pragma unroll 1
+  for (int y = y_begin; y < y_end; ++y) {
+    const Tap tapy = ac_tap(g.scale_h, y, g.h);              // CTA-uniform
+    const int top = swap ? row1 : row0, bot = swap ? row0 : row1;
+    if (!open_seg || tapy.i0 != top || tapy.i1 != bot) {
+      if (open_seg) flush_segment();
+      open_seg = true;
+      bool ld0 = false, ld1 = false;
+      int nr0 = row0, nr1 = row1;
+      if (row0 == tapy.i0) { swap = false; if (row1 != tapy.i1) { ld1 = true; nr1 = tapy.i1; } }
+      else if (row1 == tapy.i0) { swap = true; if (row0 != tapy.i1) { ld0 = true; nr0 = tapy.i1; } }
+      else { swap = false; ld0 = true; nr0 = tapy.i0; if (row1 != tapy.i1) { ld1 = true; nr1 = tapy.i1; } }
+      if (ld0) {
+        k5_load_row<KT, EXACT>(d0, dl, K, hw, nr0, g.w, tapx, LOG2E);
+        k5_load_row<CT, EXACT>(s0, sl, C, hw, nr0, g.w, tapx, LOG2E * p.inv_T);
+        row0 = nr0;
+      }
+      if (ld1) {
+        k5_load_row<KT, EXACT>(d1, dl, K, hw, nr1, g.w, tapx, LOG2E);
+        k5_load_row<CT, EXACT>(s1, sl, C, hw, nr1, g.w, tapx, LOG2E * p.inv_T);
+        row1 = nr1;
+      }
+    }
+    if (xvalid) {
+      const float w0 = swap ? tapy.l1 : tapy.l0;
+      const float w1 = swap ? tapy.l0 : tapy.l1;
+      // soft label q = min(softmax(seg / T), clamp)
+      float ms = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < CT; ++c)
+        if (EXACT || c < C) ms = fmaxf(ms, w0 * s0[c] + w1 * s1[c]);
+      float q[CT];
+      float ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < CT; ++c)
+        if (EXACT || c < C) {
+          q[c] = fast_exp2((w0 * s0[c] + w1 * s1[c]) - ms);
+          ss += q[c];
+        }
+      const float inv_ss = __fdividef(1.f, ss);
+      float sq = 0.f;
+#pragma unroll
+      for (int c = 0; c < CT; ++c)
+        if (EXACT || c < C) {
+          q[c] = fminf(q[c] * inv_ss, p.clamp);
+          sq += q[c];
+        }
+      // discriminator log-sum-exp (exp2 domain)
+      float md = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < KT; ++k)
+        if (EXACT || k < K) md = fmaxf(md, w0 * d0[k] + w1 * d1[k]);
+      float sd = 0.f, sqv = 0.f;
+#pragma unroll
+      for (int k = 0; k < KT; ++k)
+        if (EXACT || k < K) {
+          const float v = w0 * d0[k] + w1 * d1[k];
+          sd += fast_exp2(v - md);
+          if (k >= SLOT * CT && k < SLOT * CT + CT) {
+            if (EXACT || (k - SLOT * CT) < C) sqv = fmaf(q[(k - SLOT * CT) < CT ? (k - SLOT * CT) : 0], v, sqv);
+          }
+        }
+      loss_acc += LN2 * ((md + __log2f(sd)) * sq - sqv);
+      if constexpr (GRAD) {
+        const float scale = sq * __fdividef(1.f, sd);
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+          if (EXACT || k < K) {
+            float gk = fast_exp2((w0 * d0[k] + w1 * d1[k]) - md) * scale;
+            if (k >= SLOT * CT && k < SLOT * CT + CT) gk -= q[(k - SLOT * CT) < CT ? (k - SLOT * CT) : 0];
+            acc0[k] = fmaf(w0, gk, acc0[k]);
+            acc1[k] = fmaf(w1, gk, acc1[k]);
+          }
+      }
+    }
+  }
+  if (open_seg) flush_segment();
+
+  loss_acc = warp_sum(loss_acc);
+  if (lane == 0) red[warp] = loss_acc;
+  __syncthreads();
+  if (tid == 0) p.loss_part[tile] = (red[0] + red[1]) + (red[2] + red[3]);
+  if (GRAD) {
+    float* dst = p.blocks + (long long)tile * blk_floats;
+    for (int i = tid; i < blk_floats; i += K2_THREADS) dst[i] = blk[i];
+  }
+}
+
+__global__ void __launch_bounds__(256) k5_finalize_loss(const float* loss_part, int tiles, double count, float* out2) {
+  __shared__ double sl[8];
+  double l = 0.0;
+  for (int i = threadIdx.x; i < tiles; i += 256) l += (double)loss_part[i];
+  l = warp_sum_d(l);
+  if ((threadIdx.x & 31) == 0) sl[threadIdx.x >> 5] = l;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double L = 0.0;
+    for (int i = 0; i < 8; ++i) L += sl[i];
+    out2[0] = (float)(L / count);
+    out2[1] = (float)count;
+  }
+}
+
+// grad_d[n,k,i,j] = grad_out / (N*H*W) * sum over the tiles touching (i,j) of their partial block (any channel count)
+__global__ void __launch_bounds__(128) k5_finalize_grad(const K2Geom g, const float* blocks, const float* loss_out2,
+                                                        const float* grad_out, float* grad) {
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  const int i = blockIdx.y;
+  const int n = blockIdx.z;
+  if (j >= g.w) return;
+  const float scale = (grad_out ? grad_out[0] : 1.f) / loss_out2[1];
+  const long long blk_floats = (long long)g.ispan_max * g.jspan_max * g.C;
+  const long long hw = (long long)g.h * g.w;
+  float* dst = grad + (long long)n * g.C * hw + (long long)i * g.w + j;
+  const int ya = ac_first_dst(g.scale_h, i - 1, g.h, g.H), yb = ac_first_dst(g.scale_h, i + 1, g.h, g.H);
+  const int xa = ac_first_dst(g.scale_w, j - 1, g.w, g.W), xb = ac_first_dst(g.scale_w, j + 1, g.w, g.W);
+  const float* src[4];
+  int ns = 0;
+  if (ya < yb && xa < xb) {
+    const int ty0 = ya / K2_TILE_H, ty1 = (yb - 1) / K2_TILE_H;
+    const int tx0 = xa / K2_TILE_W, tx1 = (xb - 1) / K2_TILE_W;
+    for (int ty = ty0; ty <= ty1 && ns < 4; ++ty) {
+      const int li = i - (int)(g.scale_h * (float)(ty * K2_TILE_H));
+      if (li < 0 || li >= g.ispan_max) continue;
+      for (int tx = tx0; tx <= tx1 && ns < 4; ++tx) {
+        const int lj = j - (int)(g.scale_w * (float)(tx * K2_TILE_W));
+        if (lj < 0 || lj >= g.jspan_max) continue;
+        const long long tile = ((long long)n * g.tiles_y + ty) * g.tiles_x + tx;
+        src[ns++] = blocks + tile * blk_floats + ((long long)li * g.jspan_max + lj) * g.C;
+      }
+    }
+  }
+  for (int c = 0; c < g.C; ++c) {
+    float acc = 0.f;
+    for (int q = 0; q < ns; ++q) acc += src[q][c];
+    dst[c * hw] = acc * scale;
+  }
+}
+
+long long k5_workspace_bytes(int N, int C, int h, int w, int H, int W) {
+  K2Geom g;
+  k2_geometry(g, N, 2 * C, h, w, H, W);
+  return (k2_tiles(g) + k2_tiles(g) * k2_block_floats(g)) * 4 + 256;
+}
+
+template <int CT, bool EXACT>
+static int k5_main_launch(const K5Params& p, bool grad, int slot, cudaStream_t stream) {
+  const K2Geom& g = p.g;
+  const size_t smem = ((size_t)2 * 2 * CT * K2_PITCH + (size_t)g.ispan_max * g.jspan_max * g.C + (size_t)g.jspan_max * (g.kmax + 2) +
+                       4 * K2_THREADS + 8) * 4;
+  B200SEG_CHECK_ARG(smem <= 200 * 1024, "fada_softce: tile footprint %zu B exceeds shared memory (resize ratio too small)", smem);
+  const int tiles = (int)k2_tiles(g);
+#define K5_LAUNCH(G, S)                                                                                                      \
+  do {                                                                                                                       \
+    static bool configured = false;                                                                                          \
+    if (!configured) {                                                                                                       \
+      B200SEG_CUDA(cudaFuncSetAttribute(k5_fada_softce_main<CT, G, EXACT, S>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                        200 * 1024));                                                                        \
+      configured = true;                                                                                                     \
+    }                                                                                                                        \
+    k5_fada_softce_main<CT, G, EXACT, S><<<tiles, K2_THREADS, smem, stream>>>(p);                                             \
+  } while (0)
+  profile_begin(11, stream);
+  if (grad) { if (slot == 0) K5_LAUNCH(true, 0); else K5_LAUNCH(true, 1); }
+  else { if (slot == 0) K5_LAUNCH(false, 0); else K5_LAUNCH(false, 1); }
+  profile_end(11, stream);
+#undef K5_LAUNCH
+  B200SEG_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+int k5_forward(const float* dlogits, const float* slogits, int N, int C, int h, int w, int H, int W, float inv_T, float clamp,
+               int slot, int need_grad, void* workspace, long long workspace_bytes, float* loss_out2, cudaStream_t stream) {
+  B200SEG_CHECK_ARG(dlogits && slogits && workspace && loss_out2, "fada_softce_forward: null pointer");
+  B200SEG_CHECK_ARG(N > 0 && C > 0 && h > 0 && w > 0 && H > 0 && W > 0, "fada_softce_forward: bad shape");
+  B200SEG_CHECK_ARG(slot == 0 || slot == 1, "fada_softce_forward: slot must be 0 (source) or 1 (target)");
+  B200SEG_CHECK_ARG(C == 19 || C == 2, "fada_softce_forward: fused path is instantiated for num_classes 19 and 2 (got %d); use "
+                    "the materialised soft_ce path", C);
+  B200SEG_CHECK_ARG(workspace_bytes >= k5_workspace_bytes(N, C, h, w, H, W), "fada_softce_forward: workspace too small");
+  K5Params p;
+  k2_geometry(p.g, N, 2 * C, h, w, H, W);
+  const long long tiles = k2_tiles(p.g);
+  p.dlogits = dlogits; p.slogits = slogits; p.inv_T = inv_T; p.clamp = clamp;
+  p.loss_part = reinterpret_cast<float*>(workspace);
+  p.blocks = p.loss_part + tiles;
+  int rc;
+  if (C == 19) rc = k5_main_launch<19, true>(p, need_grad != 0, slot, stream);
+  else rc = k5_main_launch<2, true>(p, need_grad != 0, slot, stream);
+  if (rc) return rc;
+  k5_finalize_loss<<<1, 256, 0, stream>>>(p.loss_part, (int)tiles, (double)N * H * W, loss_out2);
+  B200SEG_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+int k5_backward(const void* workspace, int N, int C, int h, int w, int H, int W, const float* loss_out2, const float* grad_out,
+                float* grad_d, cudaStream_t stream) {
+  B200SEG_CHECK_ARG(workspace && loss_out2 && grad_d, "fada_softce_backward: null pointer");
+  K2Geom g;
+  k2_geometry(g, N, 2 * C, h, w, H, W);
+  const long long tiles = k2_tiles(g);
+  const float* blocks = reinterpret_cast<const float*>(workspace) + tiles;
+  dim3 grid(ceil_div(w, 128), h, N);
+  k5_finalize_grad<<<grid, 128, 0, stream>>>(g, blocks, loss_out2, grad_out, grad_d);
+  B200SEG_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Materialising align-corners bilinear upsample (forward) and its adjoint (gather form, no atomics)
 // ---------------------------------------------------------------------------------------------

@@ -33,3 +33,9 @@ class PixelDiscriminator(nn.Module):
         if size is not None:                                              # discriminator.py:48-49
             out = ops.upsample_bilinear_align_corners(out, size)
         return out
+
+    # ---- fused extension ------------------------------------------------------------------
+    def forward_soft_loss(self, x, seg_logits_lr, size, slot, temperature: float = 1.8, clamp: float = 0.9):
+        """soft_label_cross_entropy(self(x, size), cat-slot(min(softmax(interpolate(seg_logits_lr, size) / T), clamp)))
+        -- aspp_fada.py:110-111 (slot 0), :119-120 (slot 0), :123-124 (slot 1) -- without any full-resolution tensor."""
+        return ops.fada_soft_label_loss(self.logits(x), seg_logits_lr, size, slot, temperature, clamp)

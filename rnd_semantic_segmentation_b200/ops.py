@@ -190,3 +190,43 @@ def soft_label_cross_entropy(pred: torch.Tensor, soft_label: torch.Tensor,
                              pixel_weights: Optional[torch.Tensor] = None) -> torch.Tensor:
     """core/utils/utility.py:172-177 (differentiable w.r.t. pred only, as every reference caller uses it)."""
     return _SoftCEFn.apply(pred, soft_label, pixel_weights)
+
+
+# --------------------------------------------------------------------------------------------
+# K5  fused FADA discriminator loss tail (upsample + soft-label build + soft-label CE on low-res tensors)
+# --------------------------------------------------------------------------------------------
+class _FadaSoftCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, d_logits, seg_logits, size, slot, temperature, clamp):
+        need_grad = bool(ctx.needs_input_grad[0])
+        out2, ws = _lib.fada_softce_forward(d_logits.detach().float().contiguous(), seg_logits.detach().float().contiguous(), size,
+                                            slot, 1.0 / float(temperature), clamp, need_grad)
+        ctx.meta = (tuple(d_logits.shape), tuple(size), need_grad)
+        ctx.save_for_backward(out2, ws)
+        return out2[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        out2, ws = ctx.saved_tensors
+        shape_d, size, need_grad = ctx.meta
+        if not need_grad:
+            raise _lib.B200SegError("fada_soft_label_loss: forward ran without gradient tracking")
+        return _lib.fada_softce_backward(ws, out2, shape_d, size, grad_out.detach().float()), None, None, None, None, None
+
+
+def fada_soft_label_loss(d_logits_lr: torch.Tensor, seg_logits_lr: torch.Tensor, size, slot: int, temperature: float = 1.8,
+                         clamp: float = 0.9) -> torch.Tensor:
+    """soft_label_cross_entropy(interpolate(d_logits_lr, size), q) with q = min(softmax(interpolate(seg_logits_lr, size) / T), clamp)
+    placed in the source slot (0: cat(q, 0)) or the target slot (1: cat(0, q)) -- the three discriminator losses of
+    aspp_fada.py:110-125 -- computed on the low-resolution tensors only.  seg_logits_lr is treated as a constant
+    (the reference detaches the soft labels); the gradient flows to d_logits_lr."""
+    C = seg_logits_lr.shape[1]
+    if not _lib.fada_softce_supported(C):
+        up_d = upsample_bilinear_align_corners(d_logits_lr, size)
+        with torch.no_grad():
+            soft = torch.softmax(upsample_bilinear_align_corners(seg_logits_lr, size) / temperature, dim=1)
+            soft = torch.clamp(soft, max=clamp)
+            zeros = torch.zeros_like(soft)
+            q = torch.cat((soft, zeros) if slot == 0 else (zeros, soft), dim=1)
+        return soft_label_cross_entropy(up_d, q)
+    return _FadaSoftCEFn.apply(d_logits_lr, seg_logits_lr, (int(size[0]), int(size[1])), int(slot), float(temperature), float(clamp))

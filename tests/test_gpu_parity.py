@@ -171,6 +171,30 @@ def test_k3_soft_label_ce(lib, n, K, H, W, weighted):
     assert rel_err(p2.grad, want_g) <= TOL
 
 
+# ------------------------------------------------------------------ K5 (fused FADA discriminator loss tail)
+@pytest.mark.parametrize("n,C,h,w,H,W,slot", [(2, 19, 33, 65, 264, 520, 0), (1, 19, 64, 128, 512, 1024, 1), (2, 2, 44, 44, 352, 352, 1),
+                                             (1, 7, 9, 11, 50, 70, 0), (1, 19, 17, 23, 100, 131, 1), (1, 24, 8, 8, 40, 40, 0)])
+def test_k5_fada_soft_label_loss(lib, n, C, h, w, H, W, slot):
+    import rnd_semantic_segmentation_b200 as b200
+    g = torch.Generator().manual_seed(31 + C + h)
+    d = (1.5 * torch.randn(n, 2 * C, h, w, generator=g)).cuda().requires_grad_(True)
+    seg = (4.0 * torch.randn(n, C, h, w, generator=g)).cuda()
+    # oracle: the reference sequence on materialised full-resolution tensors (aspp_fada.py:93-124)
+    up_d = to.upsample_bilinear_ac(d, (H, W))
+    q = to.build_soft_label(to.upsample_bilinear_ac(seg, (H, W)).div(1.8), slot)
+    want = to.soft_label_cross_entropy(up_d, q)
+    want_g, = torch.autograd.grad(0.5 * want, d)
+    d2 = d.detach().clone().requires_grad_(True)
+    loss = b200.fada_soft_label_loss(d2, seg, (H, W), slot)
+    (0.5 * loss).backward()
+    assert abs(loss.item() - want.item()) <= TOL * abs(want.item())
+    assert rel_err(d2.grad, want_g) <= TOL
+    d3 = d.detach().clone().requires_grad_(True)
+    l3 = b200.fada_soft_label_loss(d3, seg, (H, W), slot)
+    (0.5 * l3).backward()
+    assert torch.equal(l3, loss) and torch.equal(d3.grad, d2.grad)        # deterministic
+
+
 # ------------------------------------------------------------------ K1
 def _head_pair(cin, C, seed):
     torch.manual_seed(seed)
