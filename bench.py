@@ -36,6 +36,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def load_traffic(kernel_key):
+    """dram bytes per launch of the dominant kernel from the committed `ncu --set full` summary (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    try:
+        with open(path) as f:
+            return json.load(f)["kernels"][kernel_key]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -184,7 +194,8 @@ def run_ours(args):
             kernels[k]["tflops"] = round(flops_per_launch / (kernels[k]["ms_per_launch"] * 1e-3) / 1e12, 1)
     roofline = {"kernel": "gemm_bf16_kernel (tcgen05; head fwd / dgrad / wgrad launches)", "bound": "tensor",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": peaks["source"] + ", sustained bf16",
+                "traffic": load_traffic("head_fwd_gemm") if args.workload == "train_b8_512x1024" else None,
+                "peak_source": peaks["source"] + ", sustained bf16",
                 "algorithmic_flops_per_launch": flops_per_launch, "kernels": kernels}
 
     # ---- end to end through the public API with HOST buffers (pinned), H2D + loss D2H inside the timed region
@@ -249,7 +260,7 @@ def run_ours(args):
                         "h2d_bytes_per_step": exh.numel() * 4 + eyh.numel() * 8, "d2h_bytes_per_step": 8 * eC * eC},
                 "roofline": {"kernel": "k4_upsample_argmax_confusion", "bound": "hbm", "achieved": round(k4_bytes / (k4_ms * 1e-3) / 1e9, 1),
                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(k4_bytes / (k4_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
-                             "traffic": None, "algorithmic_bytes_per_launch": k4_bytes},
+                             "traffic": load_traffic("eval_argmax_confusion"), "algorithmic_bytes_per_launch": k4_bytes},
                 "kernels": {k: round(v[0] / v[1], 4) for k, v in eprof.items()}}
 
     cpu_baseline = None
@@ -268,7 +279,7 @@ def run_ours(args):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_timed), "roofline": roofline, "eval": eval_obj}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist.is_initialized():
         dist.destroy_process_group()
 
@@ -314,10 +325,29 @@ def run_reference(args):
                                "each step is a bounded one-image sample of the workload"},
             "cpu_baseline": r["cpu_baseline"],
             "e2e": {"value": round(r["value"], 4), "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Everything libraries print (NCCL banners, warnings) goes to stderr; stdout carries exactly one JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -153,9 +153,12 @@ B200SEG_API long long b200seg_launch_count(void);
 B200SEG_API void b200seg_profile_enable(int on);
 B200SEG_API int b200seg_profile_read(int tag, double* total_ms, int* count);
 
-/* on-device self-test of the tcgen05 GEMM core against a CUDA-core reference (synchronous) */
-B200SEG_API int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b_mn_major, int splits, int col_hw, double* max_err,
-                          double* max_ref);
+/* on-device self-test of the tcgen05 GEMM core against a CUDA-core reference (synchronous).
+ * share: 0 = one CTA per tile, 1 = 2-CTA cluster multicasting the shared B tile, 2 = ... the shared A tile. */
+B200SEG_API int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b_mn_major, int splits, int col_hw, int share,
+                          double* max_err, double* max_ref);
+/* 0 disables the 2-CTA multicast variants inside the ASPP head GEMMs (A/B measurement); default on */
+B200SEG_API void b200seg_gemm_set_sharing(int on);
 
 #ifdef __cplusplus
 }

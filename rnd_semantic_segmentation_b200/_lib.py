@@ -54,7 +54,8 @@ SIGNATURES = {
     "b200seg_launch_count": (ctypes.c_longlong, []),
     "b200seg_profile_enable": (None, [c_int]),
     "b200seg_profile_read": (c_int, [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int)]),
-    "b200seg_gemm_selftest": (c_int, [c_int] * 7 + [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    "b200seg_gemm_selftest": (c_int, [c_int] * 8 + [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    "b200seg_gemm_set_sharing": (None, [c_int]),
 }
 
 
@@ -444,11 +445,15 @@ def default_wgrad_splits(P: int, C: int, Cin: int, R: int) -> int:
     return int(best)
 
 
-def gemm_selftest(M, N, K, a_mn=False, b_mn=False, splits=1, col_hw=0):
+def gemm_selftest(M, N, K, a_mn=False, b_mn=False, splits=1, col_hw=0, share=0):
     lib = load()
     err, ref = ctypes.c_double(0), ctypes.c_double(0)
-    _check(lib.b200seg_gemm_selftest(M, N, K, int(a_mn), int(b_mn), splits, col_hw, ctypes.byref(err), ctypes.byref(ref)))
+    _check(lib.b200seg_gemm_selftest(M, N, K, int(a_mn), int(b_mn), splits, col_hw, int(share), ctypes.byref(err), ctypes.byref(ref)))
     return err.value, ref.value
+
+
+def gemm_set_sharing(on: bool):
+    load().b200seg_gemm_set_sharing(1 if on else 0)
 
 
 PROFILE_TAGS = {"head_fwd_gemm": 0, "head_dgrad_gemm": 1, "head_wgrad_gemm": 2, "pack_features": 3, "head_gather": 4,

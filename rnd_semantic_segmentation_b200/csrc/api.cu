@@ -74,7 +74,8 @@ long long k5_workspace_bytes(int, int, int, int, int, int);
 int k5_forward(const float*, const float*, int, int, int, int, int, int, float, float, int, int, void*, long long, float*, cudaStream_t);
 int k5_backward(const void*, int, int, int, int, int, int, const float*, const float*, float*, cudaStream_t);
 namespace gemm {
-int selftest(int, int, int, int, int, int, int, double*, double*);
+int selftest(int, int, int, int, int, int, int, int, double*, double*);
+void set_sharing(int);
 }
 
 static int require_device() {
@@ -256,14 +257,16 @@ int b200seg_profile_read(int tag, double* total_ms, int* count) {
   return B200SEG_OK;
 }
 
-int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b_mn_major, int splits, int col_hw, double* max_err,
+void b200seg_gemm_set_sharing(int on) { gemm::set_sharing(on); }
+
+int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b_mn_major, int splits, int col_hw, int share, double* max_err,
                           double* max_ref) {
   REQUIRE_DEVICE();
   if (!max_err || !max_ref) {
     set_error("gemm_selftest: null output pointer");
     return B200SEG_ERR_ARG;
   }
-  return gemm::selftest(M, N, K, a_mn_major, b_mn_major, splits, col_hw, max_err, max_ref);
+  return gemm::selftest(M, N, K, a_mn_major, b_mn_major, splits, col_hw, share, max_err, max_ref);
 }
 
 }  // extern "C"

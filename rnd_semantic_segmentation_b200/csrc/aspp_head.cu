@@ -293,7 +293,7 @@ int aspp_forward(const void* Xp, const void* Wp, const float* bias_sum, const in
   const long long ypitch = ceil_div_ll(P, 4) * 4;
   gemm::Operand a{(const __nv_bfloat16*)Wp, false, Cin};
   gemm::Operand b{(const __nv_bfloat16*)Xp, false, Cin};
-  int rc = gemm::launch(a, b, NJ, (int)P, Cin, 1, Yt, ypitch, 0, 0, 0, stream, nullptr, 0);
+  int rc = gemm::launch(a, b, NJ, (int)P, Cin, 1, Yt, ypitch, 0, 0, 0, stream, nullptr, 0, gemm::SHARE_A);
   if (rc) return rc;
   TapTable tt;
   make_taps(tt, rates, R);
@@ -353,7 +353,7 @@ int aspp_backward_packed(const void* gOt_in, const void* Xp, const void* WpT, co
     // dX[ci, p] = WpT[ci, :] . G'[p, :]   -> fp32 NCHW: column p = (image, pixel), row = channel
     gemm::Operand a{(const __nv_bfloat16*)WpT, false, NJ};
     gemm::Operand b{Gp, false, NJ};
-    int rc = gemm::launch(a, b, Cin, (int)P, NJ, 1, grad_x, hw, hw, (long long)Cin * hw, 0, stream, nullptr, 1);
+    int rc = gemm::launch(a, b, Cin, (int)P, NJ, 1, grad_x, hw, hw, (long long)Cin * hw, 0, stream, nullptr, 1, gemm::SHARE_B);
     if (rc) return rc;
   }
   if (grad_w) {
@@ -366,7 +366,7 @@ int aspp_backward_packed(const void* gOt_in, const void* Xp, const void* WpT, co
       gemm::Operand b{(const __nv_bfloat16*)Xp, true, Cin};
       int used = 1;
       const long long slab = (long long)NJ * Cin;
-      int rc = gemm::launch(a, b, NJ, Cin, (int)P, splits, wpart, Cin, 0, 0, slab, stream, &used, 2);
+      int rc = gemm::launch(a, b, NJ, Cin, (int)P, splits, wpart, Cin, 0, 0, slab, stream, &used, 2, gemm::SHARE_A);
       if (rc) return rc;
       dim3 grid(ceil_div(Cin, 256), C, R);
       profile_begin(10, stream);

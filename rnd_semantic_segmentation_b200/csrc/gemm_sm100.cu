@@ -47,21 +47,49 @@ static int make_tmap(CUtensorMap* m, const __nv_bfloat16* ptr, long long inner, 
   return B200SEG_OK;
 }
 
-template <bool A_MN, bool B_MN>
+static int g_share_enabled = 1;      // b200seg_gemm_set_sharing(): 0 disables the 2-CTA multicast variants (A/B testing)
+void set_sharing(int on) { g_share_enabled = on; }
+
+template <bool A_MN, bool B_MN, int SHARE>
 static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    B200SEG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    B200SEG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, SHARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
-  gemm_bf16_kernel<A_MN, B_MN><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+  if (SHARE == SHARE_NONE) {
+    gemm_bf16_kernel<A_MN, B_MN, SHARE><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200SEG_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, SHARE>, ta, tb, p));
+  }
   B200SEG_LAUNCH_CHECK();
   return B200SEG_OK;
 }
 
+template <bool A_MN, bool B_MN>
+static int launch_s(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, int share, cudaStream_t stream) {
+  if (share == SHARE_B) return launch_t<A_MN, B_MN, SHARE_B>(ta, tb, p, grid, stream);
+  if (share == SHARE_A) return launch_t<A_MN, B_MN, SHARE_A>(ta, tb, p, grid, stream);
+  return launch_t<A_MN, B_MN, SHARE_NONE>(ta, tb, p, grid, stream);
+}
+
 int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, float* out, long long row_stride,
-           int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used, int prof_tag) {
+           int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used, int prof_tag,
+           int share) {
   B200SEG_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem %dx%dx%d", M, N, K);
+  if (!g_share_enabled) share = SHARE_NONE;
   Params p;
   p.M = M; p.N = N; p.K = K;
   p.m_tiles = ceil_div(M, BLOCK_M);
@@ -81,23 +109,36 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
               (col_hw <= 0 || (col_hw % 4 == 0 && img_stride % 4 == 0)))
                  ? 1
                  : 0;
+  // a pair needs two tiles along the paired dimension to be worth it
+  if (share == SHARE_B && p.m_tiles < 2) share = SHARE_NONE;
+  if (share == SHARE_A && p.n_tiles < 2) share = SHARE_NONE;
 
+  // the shared operand is loaded in halves (one per CTA of the pair): halve its K-major box
   CUtensorMap ta, tb;
   int rc;
-  if (!a.mn_major) rc = make_tmap(&ta, a.ptr, K, M, a.pitch, BLOCK_K, BLOCK_M);
+  if (!a.mn_major) rc = make_tmap(&ta, a.ptr, K, M, a.pitch, BLOCK_K, share == SHARE_A ? BLOCK_M / 2 : BLOCK_M);
   else rc = make_tmap(&ta, a.ptr, M, K, a.pitch, 64, BLOCK_K);
   if (rc) return rc;
-  if (!b.mn_major) rc = make_tmap(&tb, b.ptr, K, N, b.pitch, BLOCK_K, BLOCK_N);
+  if (!b.mn_major) rc = make_tmap(&tb, b.ptr, K, N, b.pitch, BLOCK_K, share == SHARE_B ? BLOCK_N / 2 : BLOCK_N);
   else rc = make_tmap(&tb, b.ptr, N, K, b.pitch, 64, BLOCK_K);
   if (rc) return rc;
 
-  const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
-  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  int grid;
+  if (share == SHARE_NONE) {
+    const int units = p.m_tiles * p.n_tiles * p.splits;
+    grid = units < num_sms() ? units : num_sms();
+  } else {
+    const int mt = share == SHARE_B ? (p.m_tiles + 1) / 2 : p.m_tiles;
+    const int nt = share == SHARE_A ? (p.n_tiles + 1) / 2 : p.n_tiles;
+    const int units = mt * nt * p.splits;
+    const int clusters = units < num_sms() / 2 ? units : num_sms() / 2;
+    grid = 2 * clusters;
+  }
   profile_begin(prof_tag, stream);
-  if (!a.mn_major && !b.mn_major) rc = launch_t<false, false>(ta, tb, p, grid, stream);
-  else if (a.mn_major && b.mn_major) rc = launch_t<true, true>(ta, tb, p, grid, stream);
-  else if (a.mn_major && !b.mn_major) rc = launch_t<true, false>(ta, tb, p, grid, stream);
-  else rc = launch_t<false, true>(ta, tb, p, grid, stream);
+  if (!a.mn_major && !b.mn_major) rc = launch_s<false, false>(ta, tb, p, grid, share, stream);
+  else if (a.mn_major && b.mn_major) rc = launch_s<true, true>(ta, tb, p, grid, share, stream);
+  else if (a.mn_major && !b.mn_major) rc = launch_s<true, false>(ta, tb, p, grid, share, stream);
+  else rc = launch_s<false, true>(ta, tb, p, grid, share, stream);
   profile_end(prof_tag, stream);
   return rc;
 }
@@ -142,7 +183,7 @@ __global__ void compare_kernel(const float* D, const float* ref, int M, int N, i
   atomicMax(reinterpret_cast<int*>(out2) + 1, __float_as_int(fabsf(r)));
 }
 
-int selftest(int M, int N, int K, int a_mn, int b_mn, int splits, int col_hw, double* max_err, double* max_ref) {
+int selftest(int M, int N, int K, int a_mn, int b_mn, int splits, int col_hw, int share, double* max_err, double* max_ref) {
   const long long a_pitch = a_mn ? ((M + 7) / 8) * 8 : ((K + 7) / 8) * 8;
   const long long b_pitch = b_mn ? ((N + 7) / 8) * 8 : ((K + 7) / 8) * 8;
   const long long a_elems = a_pitch * (a_mn ? K : M), b_elems = b_pitch * (b_mn ? K : N);
@@ -174,7 +215,7 @@ int selftest(int M, int N, int K, int a_mn, int b_mn, int splits, int col_hw, do
   B200SEG_LAUNCH_CHECK();
   Operand oa{A, a_mn != 0, a_pitch}, ob{B, b_mn != 0, b_pitch};
   int used = 1;
-  int rc = launch(oa, ob, M, N, K, s, D, row_stride, col_hw, img_stride, out_elems, 0, &used);
+  int rc = launch(oa, ob, M, N, K, s, D, row_stride, col_hw, img_stride, out_elems, 0, &used, -1, share);
   if (rc == B200SEG_OK) {
     compare_kernel<<<g, 128>>>(D, ref, M, N, used, out_elems, row_stride, col_hw > 0 ? col_hw : INT_MAX, img_stride, res);
     cudaError_t e = cudaDeviceSynchronize();

@@ -151,7 +151,60 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int m, i
 // ------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------
-template <bool A_MN, bool B_MN>
+// Operand sharing inside a 2-CTA cluster (the kernel is bound by SM<->L2 bandwidth, 48 KB per k-block per SM):
+//   SHARE_NONE : plain launch, every CTA loads its whole A and B tiles.
+//   SHARE_B    : the two CTAs of a cluster own M-tiles (2i, 2i+1) of the SAME N-tile; each loads its own A tile and
+//                HALF of the shared B tile and multicasts that half into both CTAs' shared memory (32 KB per k-block).
+//   SHARE_A    : the two CTAs own N-tiles (2i, 2i+1) of the SAME M-tile; each loads its own B tile and half of A (40 KB).
+// Each CTA still issues its own cta_group::1 MMAs into its own TMEM.  A shared-memory stage is released to BOTH
+// producers only when BOTH CTAs' MMAs have drained it (empty barriers count 2, tcgen05.commit multicast to both CTAs).
+constexpr int SHARE_NONE = 0, SHARE_B = 1, SHARE_A = 2;
+
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(smem_dst), "l"(m), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+// work unit -> (split z, M-tile, N-tile) of this CTA
+template <int SHARE>
+struct TileSched {
+  int units, worker, nworkers, rank, m_tiles, n_tiles, per_split;
+  __device__ TileSched(const Params& p) {
+    rank = SHARE != SHARE_NONE ? (int)cluster_cta_rank() : 0;
+    worker = SHARE != SHARE_NONE ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    nworkers = SHARE != SHARE_NONE ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    m_tiles = SHARE == SHARE_B ? (p.m_tiles + 1) >> 1 : p.m_tiles;     // pairs along M
+    n_tiles = SHARE == SHARE_A ? (p.n_tiles + 1) >> 1 : p.n_tiles;     // pairs along N
+    per_split = m_tiles * n_tiles;
+    units = per_split * p.splits;
+  }
+  __device__ void decode(int unit, int& z, int& mt, int& nt) const {
+    z = unit / per_split;
+    const int rem = unit - z * per_split;
+    nt = rem / m_tiles;                  // M fastest: tiles sharing the (large) B operand are adjacent in time
+    mt = rem - nt * m_tiles;
+    if (SHARE == SHARE_B) mt = mt * 2 + rank;
+    if (SHARE == SHARE_A) nt = nt * 2 + rank;
+  }
+};
+
+template <bool A_MN, bool B_MN, int SHARE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -168,6 +221,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr bool CLUSTER = SHARE != SHARE_NONE;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -176,7 +230,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CLUSTER ? 2 : 1);   // cluster: both CTAs' MMA warps release a stage
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -187,22 +241,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER) cluster_sync_all();            // peer barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_per_split = p.m_tiles * p.n_tiles;
-  const int num_tiles = tiles_per_split * p.splits;
+  const TileSched<SHARE> sched(p);
 
   if (warp == 0) {
     // ================= TMA producer (one thread) =================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int z = tile / tiles_per_split;
-        const int rem = tile - z * tiles_per_split;
-        const int nt = rem / p.m_tiles;
-        const int mt = rem - nt * p.m_tiles;
+      for (int unit = sched.worker; unit < sched.units; unit += sched.nworkers) {
+        int z, mt, nt;
+        sched.decode(unit, z, mt, nt);
         const int m0 = mt * BLOCK_M, n0 = nt * BLOCK_N;
         const int kb0 = z * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -210,16 +262,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);   // own loads + the peer's multicast half
           const int k0 = kb * BLOCK_K;
-          if (!A_MN) {
+          // ---- A ----
+          if (SHARE == SHARE_A) {
+            // shared A tile: this CTA loads rows [64*rank, +64) and multicasts them to both CTAs
+            if (!A_MN) tma_load_2d_mc(sa + sched.rank * (A_BYTES / 2), &tmap_a, &full_bar[stage], k0, m0 + sched.rank * 64, 0x3);
+            else tma_load_2d_mc(sa + sched.rank * MN_BOX_BYTES, &tmap_a, &full_bar[stage], m0 + sched.rank * 64, k0, 0x3);
+          } else if (!A_MN) {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);            // box {64 k, 128 rows}
           } else {
 #pragma unroll
             for (int b = 0; b < BLOCK_M / 64; ++b)                          // box {64 m, 64 k}
               tma_load_2d(sa + b * MN_BOX_BYTES, &tmap_a, &full_bar[stage], m0 + b * 64, k0);
           }
-          if (!B_MN) {
+          // ---- B ----
+          if (SHARE == SHARE_B) {
+            // shared B tile: this CTA loads rows [128*rank, +128) and multicasts them to both CTAs
+            if (!B_MN) {
+              tma_load_2d_mc(sb + sched.rank * (B_BYTES / 2), &tmap_b, &full_bar[stage], k0, n0 + sched.rank * 128, 0x3);
+            } else {
+#pragma unroll
+              for (int b = 0; b < 2; ++b)
+                tma_load_2d_mc(sb + (sched.rank * 2 + b) * MN_BOX_BYTES, &tmap_b, &full_bar[stage], n0 + (sched.rank * 2 + b) * 64, k0, 0x3);
+            }
+          } else if (!B_MN) {
             tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);            // box {64 k, 256 rows}
           } else {
 #pragma unroll
@@ -243,8 +310,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int z = tile / tiles_per_split;
+      for (int unit = sched.worker; unit < sched.units; unit += sched.nworkers) {
+        int z, mt, nt;
+        sched.decode(unit, z, mt, nt);
         const int kb0 = z * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
@@ -261,7 +329,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint64_t bdesc = make_smem_desc(sb + k * b_step, b_lbo, b_sbo);
             umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+          if (CLUSTER) umma_commit_mc(&empty_bar[stage], 0x3);   // frees the slot in BOTH CTAs when these MMAs retire
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&tfull_bar[acc]);              // accumulator ready for the epilogue
@@ -275,11 +344,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     float* stg = epi_stage + (warp - 4) * EPI_STAGE_FLOATS;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int z = tile / tiles_per_split;
-      const int rem = tile - z * tiles_per_split;
-      const int nt = rem / p.m_tiles;
-      const int mt = rem - nt * p.m_tiles;
+    for (int unit = sched.worker; unit < sched.units; unit += sched.nworkers) {
+      int z, mt, nt;
+      sched.decode(unit, z, mt, nt);
       const int row_base = mt * BLOCK_M + wq * 32;
       const int col_base = nt * BLOCK_N + half * (BLOCK_N / 2);
       float* out = p.out + (long long)z * p.split_stride;
@@ -287,40 +354,50 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * (BLOCK_N / 2));
       const int rows = min(32, p.M - row_base);
+      if (rows > 0 && col_base < p.N) {
+        // per-lane (image, offset) of its first column, advanced by 16 columns per chunk (no division in the loop)
+        const int lane_col = p.vec_ok ? (lane & 3) * 4 : (lane & 15);
+        int img = (col_base + lane_col) / p.col_hw;
+        int rem = (col_base + lane_col) - img * p.col_hw;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 2 / 16; ++c) {
-        uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)(c * 16), r);
-        tmem_ld_wait();
+        for (int c = 0; c < BLOCK_N / 2 / 16; ++c) {
+          uint32_t r[16];
+          tmem_ld16(taddr + (uint32_t)(c * 16), r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          *reinterpret_cast<float4*>(stg + lane * EPI_PITCH + 4 * k) =
-              make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), __uint_as_float(r[4 * k + 2]),
-                          __uint_as_float(r[4 * k + 3]));
-        __syncwarp();
-        const int col0 = col_base + c * 16;
-        if (p.vec_ok && col0 + 16 <= p.N) {
-          // lane -> (row lane/4 + 8i, 4 columns): every store instruction writes 8 rows x 64 contiguous bytes
-          const int col = col0 + (lane & 3) * 4;
-          const int img = col / p.col_hw;
-          float* dst = out + (long long)img * p.img_stride + (long long)(col - img * p.col_hw);
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<float4*>(stg + lane * EPI_PITCH + 4 * k) =
+                make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), __uint_as_float(r[4 * k + 2]),
+                            __uint_as_float(r[4 * k + 3]));
+          __syncwarp();
+          const int col0 = col_base + c * 16;
+          float* dst = out + (long long)img * p.img_stride + rem + (long long)row_base * p.row_stride;
+          if (p.vec_ok) {
+            // lane -> (row lane/4 + 8i, 4 columns): every store instruction writes 8 rows x 64 contiguous bytes
+            if (col0 + lane_col + 3 < p.N) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int rr = (lane >> 2) + 8 * i;
-            if (rr < rows)
-              *reinterpret_cast<float4*>(dst + (long long)(row_base + rr) * p.row_stride) =
-                  *reinterpret_cast<const float4*>(stg + rr * EPI_PITCH + (lane & 3) * 4);
+              for (int i = 0; i < 4; ++i) {
+                const int rr = (lane >> 2) + 8 * i;
+                if (rr < rows)
+                  *reinterpret_cast<float4*>(dst + (long long)rr * p.row_stride) =
+                      *reinterpret_cast<const float4*>(stg + rr * EPI_PITCH + lane_col);
+              }
+            } else {
+              for (int e = 0; e < 4; ++e)
+                if (col0 + lane_col + e < p.N)
+                  for (int i = 0; i < 4; ++i) {
+                    const int rr = (lane >> 2) + 8 * i;
+                    if (rr < rows) dst[(long long)rr * p.row_stride + e] = stg[rr * EPI_PITCH + lane_col + e];
+                  }
+            }
+          } else if (col0 + lane_col < p.N) {
+            // scalar path (unaligned rows): lane -> (row lane/16 + 2i, column lane%16)
+            for (int rr = (lane >> 4); rr < rows; rr += 2) dst[(long long)rr * p.row_stride] = stg[rr * EPI_PITCH + lane_col];
           }
-        } else {
-          // scalar fallback (ragged N tile or unaligned rows): lane -> (row lane/16 + 2i, column lane%16)
-          const int col = col0 + (lane & 15);
-          if (col < p.N) {
-            const int img = col / p.col_hw;
-            float* dst = out + (long long)img * p.img_stride + (long long)(col - img * p.col_hw);
-            for (int rr = (lane >> 4); rr < rows; rr += 2) dst[(long long)(row_base + rr) * p.row_stride] = stg[rr * EPI_PITCH + (lane & 15)];
-          }
+          rem += 16;
+          while (rem >= p.col_hw) { rem -= p.col_hw; ++img; }
+          __syncwarp();
         }
-        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -331,6 +408,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER) cluster_sync_all();            // the peer may still multicast into / arrive on this CTA until it is done too
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -344,7 +422,8 @@ struct Operand {
   long long pitch;      // elements between consecutive outer-dimension entries
 };
 int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, float* out, long long row_stride,
-           int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used, int prof_tag = -1);
+           int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used, int prof_tag = -1,
+           int share = SHARE_NONE);
 
 }  // namespace gemm
 }  // namespace b200seg

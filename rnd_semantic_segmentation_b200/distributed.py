@@ -61,19 +61,22 @@ class FlatGradBucket:
             off += p.numel()
 
     def gather_grads(self):
-        """Copy (or alias) the parameters' current .grad into the flat buffer."""
+        """Bring the parameters' current .grad into the flat buffer (one concatenation kernel) and alias them to it."""
+        if all(p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(self.params, self.views)):
+            return
+        pieces = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params]
+        torch.cat(pieces, out=self.flat)
         for p, v in zip(self.params, self.views):
-            if p.grad is None:
-                v.zero_()
-            elif p.grad.data_ptr() != v.data_ptr():
-                v.copy_(p.grad)
             p.grad = v
 
     def allreduce_mean_(self, group=None):
         self.gather_grads()
         if is_distributed():
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            self.flat.div_(dist.get_world_size(group))
+            if dist.get_backend(group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)      # mean inside the collective
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+                self.flat.div_(dist.get_world_size(group))
         return self.flat
 
 
