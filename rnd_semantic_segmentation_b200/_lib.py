@@ -14,7 +14,8 @@ from typing import Optional, Sequence
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libb200seg.so")
+# B200SEG_LIB selects another build of the same library (kernel A/B experiments under profiles/)
+LIB_PATH = os.environ.get("B200SEG_LIB") or os.path.join(_PKG, "libb200seg.so")
 _lib = None
 
 c_int, c_i64, c_f32, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p

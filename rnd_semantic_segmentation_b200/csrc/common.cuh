@@ -84,6 +84,75 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// ---- sm_100 packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2: two IEEE fp32 results per issue slot) and the
+//      3-input fp32 max (FMNMX3).  Each half is rounded exactly like the scalar instruction. ---------------------
+__device__ __forceinline__ unsigned long long f2_bits(float2 v) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
+  return r;
+}
+__device__ __forceinline__ float2 bits_f2(unsigned long long r) {
+  float2 v;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(r));
+  return v;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+  return bits_f2(d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return bits_f2(d);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return bits_f2(d);
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// ---- per-thread asynchronous global->shared copies (LDGSTS) ----------------------------------
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gmem_src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ---- explicit shared-space accesses on 32-bit shared addresses (no generic->shared conversion per access) ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float lds_f32(unsigned a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 lds_v4f32(unsigned a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint2 lds_v2u32(unsigned a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void smem_inc_u8(unsigned a) {      // thread-private byte counter += 1
+  asm volatile("{ .reg .u32 t; ld.shared.u8 t, [%0]; add.u32 t, t, 1; st.shared.u8 [%0], t; }" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void cp_async_8s(unsigned smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+
 // ---- warp / block reductions ----------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

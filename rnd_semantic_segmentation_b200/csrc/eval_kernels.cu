@@ -10,26 +10,52 @@
 //
 // Bit-exactness: the upsampled value uses ATen's expression form
 //   h0*(w0*a + w1*b) + h1*(w0*c + w1*d)   (ATen/native/cuda/UpSampleBilinear2d.cu)
-// and argmax(softmax(v)) == first-max(v) unless a lower-indexed class is within ~1 ulp of the
-// maximum after exp/divide; pixels whose top-2 gap is <= 1e-6 re-run ATen's exact spatial-softmax
-// sequence (max, sum of expf(v-max) in class order, expf(v-max)/sum, first maximum).
+// as nvcc contracts it, fma(h0, t, h1*u), and argmax(softmax(v)) == first-max(v) unless another class is within
+// ~1 ulp of the maximum after exp/divide; pixels where a second class lies within 1e-6 of the maximum re-run
+// ATen's exact spatial-softmax sequence (max, sum of expf(v-max) in class order, expf(v-max)/sum, first maximum).
 //
-// Layout / mapping: one thread per output column, warps walk rows (row taps are warp-uniform);
-// the horizontal lerps t_c (upper source row) and u_c (lower source row) of all classes live in
-// registers and are reused for every output row of the same source-row pair.  Labels (int64, the
-// only large stream) are read with streaming 64-bit loads, eight rows in flight per thread.
-// Histogram: each lane owns private uint8 counters hist[bin][lane] in shared memory (no atomics,
-// no contention even for i.i.d. labels), folded into an int32 CTA histogram once per tile and into
+// Layout / mapping: one thread per output column, warps walk rows (row taps are warp-uniform); the horizontal
+// lerps of all classes for the two source rows live in registers as class PAIRS and are reused for every output
+// row of the same source-row pair.  The kernel is issue-bound (C classes per 8-byte label), so the per-pixel
+// instruction count is what is optimised:
+//   * interpolation on packed fp32x2 (FMUL2 + FFMA2: two classes per issue slot, each half IEEE-rounded),
+//   * max over classes as a tree of 3-input FMNMX3,
+//   * argmax + near-tie detection in one pass: bit c of a mask is set when v_c >= max - 1e-6 (FSETP + predicated
+//     add, all independent); one bit set -> that is the argmax, several -> the exact path.
+// Labels (int64, the only large stream) are staged by per-lane 8-byte cp.async into a per-warp shared-memory ring,
+// one 8-row strip ahead (also across tiles), so no registers or issue slots are held by loads in flight.
+// Histogram: each lane owns private uint8 counters hist[bin][lane] in shared memory (no atomics, no contention
+// even for i.i.d. labels), folded with dp4a into an int32 CTA histogram before a counter could overflow and into
 // the int64 global matrix once per frame per CTA.
 #include "common.cuh"
 
 namespace b200seg {
 
+// build-time experiment knobs (profiles/build_variants.sh)
+#ifndef K4_MIN_CTAS
+#define K4_MIN_CTAS 3          // resident CTAs per SM the register allocation is bounded for
+#endif
+#ifndef K4_PAIR_ROWS
+#define K4_PAIR_ROWS 1         // 1: two output rows per loop iteration (interleaved dependency chains)
+#endif
+#ifndef K4_FORCE_ATOMIC_HIST
+#define K4_FORCE_ATOMIC_HIST 0 // 1: warp-aggregated shared-memory atomics instead of per-lane uint8 counters
+#endif
+
 constexpr int K4_THREADS = 128;
+constexpr int K4_WARPS = K4_THREADS / 32;
 constexpr int K4_TILE_W = 128;
-constexpr int K4_TILE_H = 32;
-constexpr int K4_STRIP = 8;
+constexpr int K4_STRIP = 8;                  // rows per label-ring stage
+constexpr int K4_TILE_H_MAX = 32;            // rows per tile: 8, 16 or 32 (chosen per launch; one table row per lane)
+constexpr int K4_SPAN = 8;                   // source columns a warp's 32 output columns may span on the staged path
 constexpr float K4_NEAR_TIE = 1e-6f;
+constexpr float K4_PAD = -1e30f;             // value of the padding classes (never wins, never NaN)
+constexpr int K4_RING_BYTES = K4_WARPS * 2 * K4_STRIP * 32 * 8;
+constexpr int K4_TAB_BYTES = K4_WARPS * K4_TILE_H_MAX * 16;
+constexpr int K4_STAGE_FLOATS = 32 * K4_SPAN;   // per-warp staging buffer of one source row: [CT <= 32][K4_SPAN]
+constexpr int K4_STAGE_BYTES = K4_WARPS * K4_STAGE_FLOATS * 4;
+// per-lane uint8 counters need CT*CT*32 bytes per warp; above 48 KB per CTA fall back to warp-aggregated atomics
+__host__ __device__ constexpr bool k4_use_u8(int CT) { return !K4_FORCE_ATOMIC_HIST && (CT * CT + 1) * 32 * K4_WARPS <= 48 * 1024; }
 
 struct K4Params {
   const float* logits;      // [N, C, h, w]
@@ -40,104 +66,346 @@ struct K4Params {
   int ignore_index;
   long long cm_frame_stride;
   float scale_h, scale_w;
-  int tiles_x, tiles_y, total_tiles, tiles_per_cta;
-  int use_u8;               // per-lane uint8 counters (C*C*32*4 bytes of smem) or aggregated atomics
+  int tiles_x, tiles_y, total_tiles;
+  int tile_h;               // rows per tile (multiple of K4_STRIP, <= K4_TILE_H_MAX)
 };
 
+// wa*a + wb*b with the rounding sequence selected by FMA:
+//   0/1: fma(wa, a, wb*b)  -- what nvcc emits for ATen's source expression (bit-equal to F.interpolate on B200)
+//   2:   fma(wb, b, wa*a)     3: (wa*a) + (wb*b) without contraction          (diagnostic variants)
 template <int FMA>
-__device__ __forceinline__ float lerp2(float wa, float a, float wb, float b) {
-  if (FMA == 0) return wa * a + wb * b;                       // compiler's contraction (same source form as ATen)
-  if (FMA == 1) return fmaf(wa, a, wb * b);
-  if (FMA == 2) return fmaf(wb, b, wa * a);
-  return __fadd_rn(__fmul_rn(wa, a), __fmul_rn(wb, b));       // no contraction
+__device__ __forceinline__ float lerp1(float wa, float a, float wb, float b) {
+  if (FMA <= 1) return fmaf(wa, a, __fmul_rn(wb, b));
+  if (FMA == 2) return fmaf(wb, b, __fmul_rn(wa, a));
+  return __fadd_rn(__fmul_rn(wa, a), __fmul_rn(wb, b));
+}
+template <int FMA>
+__device__ __forceinline__ float2 lerp2(float2 wa, float2 a, float2 wb, float2 b) {
+  if (FMA <= 1) return fma2(wa, a, mul2(wb, b));
+  if (FMA == 2) return fma2(wb, b, mul2(wa, a));
+  return add2(mul2(wa, a), mul2(wb, b));
 }
 
-// Exact ATen spatial-softmax sequence for one pixel (rare path): sequential float sum of expf(v - max) in class
-// order, IEEE divide, first maximum.  TOP/BOT select which register array holds the upper source row.
-template <int CT, int FMA, bool SWAP, bool EXACT>
-__device__ __forceinline__ int exact_softmax_argmax(const float (&a0)[CT], const float (&a1)[CT], int C, float h0, float h1,
-                                                    float m) {
+// Exact ATen spatial-softmax sequence for one pixel (rare path, recomputed from the L1/L2-resident low-res logits so
+// the hot loop keeps no register array alive for it): sequential float sum of expf(v - max) in class order, IEEE
+// divide, first maximum.
+template <int FMA>
+__device__ __noinline__ int k4_exact_softmax_argmax(const float* __restrict__ lg, int C, long long hw, int w, int row_top,
+                                                    int row_bot, int i0, int i1, float l0, float l1, float h0, float h1) {
+  const float* pt = lg + (long long)row_top * w;
+  const float* pb = lg + (long long)row_bot * w;
+  float m = -INFINITY;
+  for (int c = 0; c < C; ++c) {
+    const float t = lerp1<FMA>(l0, __ldg(pt + c * hw + i0), l1, __ldg(pt + c * hw + i1));
+    const float u = lerp1<FMA>(l0, __ldg(pb + c * hw + i0), l1, __ldg(pb + c * hw + i1));
+    m = fmaxf(m, lerp1<FMA>(h0, t, h1, u));
+  }
   float s = 0.f;
-#pragma unroll
-  for (int c = 0; c < CT; ++c)
-    if (EXACT || c < C) s += expf((SWAP ? lerp2<FMA>(h0, a1[c], h1, a0[c]) : lerp2<FMA>(h0, a0[c], h1, a1[c])) - m);
+  for (int c = 0; c < C; ++c) {
+    const float t = lerp1<FMA>(l0, __ldg(pt + c * hw + i0), l1, __ldg(pt + c * hw + i1));
+    const float u = lerp1<FMA>(l0, __ldg(pb + c * hw + i0), l1, __ldg(pb + c * hw + i1));
+    s += expf(lerp1<FMA>(h0, t, h1, u) - m);
+  }
   float pbest = -1.f;
   int idx = 0;
-#pragma unroll
-  for (int c = 0; c < CT; ++c)
-    if (EXACT || c < C) {
-      const float pc = expf((SWAP ? lerp2<FMA>(h0, a1[c], h1, a0[c]) : lerp2<FMA>(h0, a0[c], h1, a1[c])) - m) / s;
-      if (pc > pbest) { pbest = pc; idx = c; }
-    }
+  for (int c = 0; c < C; ++c) {
+    const float t = lerp1<FMA>(l0, __ldg(pt + c * hw + i0), l1, __ldg(pt + c * hw + i1));
+    const float u = lerp1<FMA>(l0, __ldg(pb + c * hw + i0), l1, __ldg(pb + c * hw + i1));
+    const float pc = expf(lerp1<FMA>(h0, t, h1, u) - m) / s;
+    if (pc > pbest) { pbest = pc; idx = c; }
+  }
   return idx;
 }
 
-// argmax over classes of the interpolated logits of one pixel (first index on ties), with the near-tie rescue.
-template <int CT, int FMA, bool SWAP, bool EXACT>
-__device__ __forceinline__ int k4_pixel_argmax(const float (&a0)[CT], const float (&a1)[CT], int C, float h0, float h1) {
-  float best = -INFINITY, second = -INFINITY;
-  int idx = 0;
-#pragma unroll
-  for (int c = 0; c < CT; ++c)
-    if (EXACT || c < C) {
-      const float v = SWAP ? lerp2<FMA>(h0, a1[c], h1, a0[c]) : lerp2<FMA>(h0, a0[c], h1, a1[c]);
-      const bool gt = v > best;
-      second = fmaxf(second, fminf(best, v));
-      idx = gt ? c : idx;
-      best = fmaxf(best, v);
-    }
-  if (best - second <= K4_NEAR_TIE) idx = exact_softmax_argmax<CT, FMA, SWAP, EXACT>(a0, a1, C, h0, h1, best);
-  return idx;
+// max of f[LO..HI) as a tree of 3-input maxima (depth log3 instead of a serial chain)
+template <int LO, int HI, int CT>
+__device__ __forceinline__ float tree_max3(const float (&f)[CT]) {
+  constexpr int n = HI - LO;
+  if constexpr (n == 1) return f[LO];
+  else if constexpr (n == 2) return fmaxf(f[LO], f[LO + 1]);
+  else if constexpr (n == 3) return fmax3(f[LO], f[LO + 1], f[LO + 2]);
+  else {
+    constexpr int a = (n + 2) / 3, b = (n - a + 1) / 2;
+    return fmax3(tree_max3<LO, LO + a, CT>(f), tree_max3<LO + a, LO + a + b, CT>(f), tree_max3<LO + a + b, HI, CT>(f));
+  }
 }
 
-// horizontal lerp of one source row for all classes into a register array
+// acc += K when v >= thr, as FSETP + one predicated add
+template <int K>
+__device__ __forceinline__ void add_if_ge(int& acc, float v, float thr) {
+  asm("{ .reg .pred q; setp.ge.f32 q, %1, %2; @q add.s32 %0, %0, %3; }" : "+r"(acc) : "f"(v), "f"(thr), "n"(K));
+}
+template <int c, int CT, bool EXACT, int NF>
+__device__ __forceinline__ void k4_candidates(int& acc0, int& acc1, const float (&f)[NF], float thr, int C) {
+  if constexpr (c < CT) {
+    if (EXACT || c < C) add_if_ge<256 + c>((c & 1) ? acc1 : acc0, f[c], thr);
+    k4_candidates<c + 1, CT, EXACT>(acc0, acc1, f, thr, C);
+  }
+}
+
+// Candidate accumulator of one pixel: adds (256 + c) for every class c whose interpolated logit is within 1e-6 of
+// the maximum.  Exactly one candidate -> the result is argmax(softmax) in [0, C); none (NaN) or several (near tie)
+// -> the result is outside [0, C) and the caller takes the exact path.  FSETP + predicated add per class, all
+// independent except two short add chains; no transcendental-pipe (POPC/FLO) work.
 template <int CT, int FMA, bool EXACT>
-__device__ __forceinline__ void k4_load_row(float (&dst)[CT], const float* __restrict__ lg, int C, long long hw, int row, int w,
-                                            const Tap& tapx) {
-  const float* p0 = lg + (long long)row * w + tapx.i0;
-  const float* p1 = lg + (long long)row * w + tapx.i1;
+__device__ __forceinline__ int k4_pixel_candidate(const float2 (&top)[(CT + 1) / 2], const float2 (&bot)[(CT + 1) / 2], int C,
+                                                  float h0, float h1) {
+  constexpr int NP = (CT + 1) / 2;
+  const float2 H0 = make_float2(h0, h0), H1 = make_float2(h1, h1);
+  float f[2 * NP];
 #pragma unroll
-  for (int c = 0; c < CT; ++c)
-    if (EXACT || c < C) {
-      dst[c] = lerp2<FMA>(tapx.l0, __ldg(p0), tapx.l1, __ldg(p1));
-      p0 += hw; p1 += hw;
-    }
+  for (int i = 0; i < NP; ++i) {
+    const float2 v = lerp2<FMA>(H0, top[i], H1, bot[i]);
+    f[2 * i] = v.x; f[2 * i + 1] = v.y;
+  }
+  const float thr = tree_max3<0, CT, 2 * NP>(f) - K4_NEAR_TIE;
+  int acc0 = -256, acc1 = 0;
+  k4_candidates<0, CT, EXACT>(acc0, acc1, f, thr, C);
+  return acc0 + acc1;
+}
+
+// ---- source rows --------------------------------------------------------------------------------------------
+// Staged path (the warp's 32 columns span <= K4_SPAN source columns, i.e. any upsampling factor >= ~5.3): the warp
+// copies the CT x K4_SPAN window of a source row into its shared-memory stage with <= CT*K4_SPAN/32 coalesced
+// loads per lane (32-bit element offsets `soff`, fixed per tile) -- k4_row_fetch issues them (one segment ahead, so
+// their latency hides behind a segment of compute), k4_row_commit parks them in the stage -- and every lane then
+// reads its two taps per class with immediate-offset LDS: no per-load 64-bit address arithmetic.
+template <int CT>
+__device__ __forceinline__ void k4_row_fetch(float (&v)[(CT * K4_SPAN + 31) / 32], const float* __restrict__ rb,
+                                             const int (&soff)[(CT * K4_SPAN + 31) / 32]) {
+  constexpr int NS = (CT * K4_SPAN + 31) / 32;
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int q = 0; q < NS; ++q)
+    if (q * 32 + lane < CT * K4_SPAN) v[q] = __ldg(rb + soff[q]);
 }
 
 template <int CT, int FMA, bool EXACT>
-__global__ void __launch_bounds__(K4_THREADS, 4) k4_upsample_argmax_confusion(const K4Params p) {
+__device__ __forceinline__ void k4_row_commit(float2 (&dst)[(CT + 1) / 2], const float (&v)[(CT * K4_SPAN + 31) / 32], int C,
+                                              unsigned stage_s, unsigned t0_s, unsigned t1_s, float l0, float l1) {
+  constexpr int NP = (CT + 1) / 2;
+  constexpr int NS = (CT * K4_SPAN + 31) / 32;
+  const int lane = threadIdx.x & 31;
+  __syncwarp();                                     // every lane has finished reading the previous row from the stage
+#pragma unroll
+  for (int q = 0; q < NS; ++q)
+    if (q * 32 + lane < CT * K4_SPAN) sts_f32(stage_s + (q * 32 + lane) * 4, v[q]);
+  __syncwarp();
+  const float2 L0 = make_float2(l0, l0), L1 = make_float2(l1, l1);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    float2 a = make_float2(K4_PAD, K4_PAD), b = make_float2(K4_PAD, K4_PAD);
+    if (EXACT || 2 * i < C) { a.x = lds_f32(t0_s + (2 * i) * K4_SPAN * 4); b.x = lds_f32(t1_s + (2 * i) * K4_SPAN * 4); }
+    if (2 * i + 1 < CT && (EXACT || 2 * i + 1 < C)) {
+      a.y = lds_f32(t0_s + (2 * i + 1) * K4_SPAN * 4); b.y = lds_f32(t1_s + (2 * i + 1) * K4_SPAN * 4);
+    }
+    dst[i] = lerp2<FMA>(L0, a, L1, b);
+    if (!(EXACT || 2 * i < C)) dst[i].x = K4_PAD;
+    if (!(2 * i + 1 < CT && (EXACT || 2 * i + 1 < C))) dst[i].y = K4_PAD;
+  }
+}
+
+// Fallback for windows wider than K4_SPAN (mild or no upsampling): direct global loads.
+template <int CT, int FMA, bool EXACT>
+__device__ __forceinline__ void k4_row_direct(float2 (&dst)[(CT + 1) / 2], const float* __restrict__ rb, int C, long long hw,
+                                              int i0, int i1, float l0, float l1) {
+  constexpr int NP = (CT + 1) / 2;
+  const char* p0 = reinterpret_cast<const char*>(rb + i0);
+  const char* p1 = reinterpret_cast<const char*>(rb + i1);
+  const long long step = hw * 4;
+  const float2 L0 = make_float2(l0, l0), L1 = make_float2(l1, l1);
+#pragma unroll 1
+  for (int i = 0; i < NP; ++i) {
+    float2 a = make_float2(K4_PAD, K4_PAD), b = make_float2(K4_PAD, K4_PAD);
+    if (EXACT || 2 * i < C) { a.x = __ldg(reinterpret_cast<const float*>(p0)); b.x = __ldg(reinterpret_cast<const float*>(p1)); }
+    p0 += step; p1 += step;
+    if (2 * i + 1 < CT && (EXACT || 2 * i + 1 < C)) {
+      a.y = __ldg(reinterpret_cast<const float*>(p0)); b.y = __ldg(reinterpret_cast<const float*>(p1));
+    }
+    p0 += step; p1 += step;
+    float2 r = lerp2<FMA>(L0, a, L1, b);
+    if (!(EXACT || 2 * i < C)) r.x = K4_PAD;
+    if (!(2 * i + 1 < CT && (EXACT || 2 * i + 1 < C))) r.y = K4_PAD;
+    // dynamic index into a register array would spill: select with an unrolled compare instead
+#pragma unroll
+    for (int j = 0; j < NP; ++j)
+      if (j == i) dst[j] = r;
+  }
+}
+
+struct K4RowCtx {
+  const float* lg;          // frame base of the low-res logits
+  long long* pred;          // this lane's prediction column (row 0 of the frame) or null
+  int* cta_hist;
+  long long hw;
+  unsigned tab_s;           // shared address of this warp's row table: {l0, l1, bits(i0), bits(segment end)} per tile row
+  unsigned lab_s;           // shared address of this lane's label column in the current ring stage (row stride 256 B)
+  unsigned whist_s;         // shared address of this lane's uint8 counters (+ bin * 32)
+  unsigned ign32;           // ignore_index when it fits a non-negative 32-bit value, else 0xffffffff (never a class)
+  unsigned c_lim;           // number of classes for a lane inside the image, 0 for a lane right of it (never counts)
+  int C, w, W, y_tile, y_strip;
+  int i0x, i1x;
+  float l0x, l1x;
+  bool xvalid, do_cm;
+};
+
+// one output pixel: argmax class -> prediction store / histogram update (branch-free on the common path)
+template <int CT, int FMA, bool EXACT, bool U8>
+__device__ __forceinline__ void k4_finish_pixel(const K4RowCtx& k, int y, int cand, int i0y, int i1y, float h0, float h1) {
+  const int C = EXACT ? CT : k.C;
+  int idx = cand;
+  if ((unsigned)cand >= (unsigned)C)                                 // near tie (or NaN): the exact sequence
+    idx = k4_exact_softmax_argmax<FMA>(k.lg, C, k.hw, k.w, i0y, i1y, k.i0x, k.i1x, k.l0x, k.l1x, h0, h1);
+  if (k.pred != nullptr) {                                           // uniform
+    if (k.xvalid) k.pred[(long long)y * k.W] = (long long)idx;
+  }
+  if (k.do_cm) {                                                     // uniform
+    const uint2 g = lds_v2u32(k.lab_s + (y - k.y_strip) * 256);      // int64 label as {lo, hi}
+    const bool count = (g.y == 0u) && (g.x < k.c_lim) && (g.x != k.ign32);
+    if (U8) {
+      const int bin = count ? (int)g.x * C + idx : C * C;            // pixels that do not count land in a spare bin
+      smem_inc_u8(k.whist_s + bin * 32);
+    } else {
+      const int bin = count ? (int)g.x * C + idx : -1;
+      const unsigned peers = __match_any_sync(__activemask(), bin);
+      if (count && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&k.cta_hist[bin], __popc(peers));
+    }
+  }
+}
+
+// rows [y, yend) of one source-row pair (top, bot), two rows per iteration so the two dependency chains interleave
+template <int CT, int FMA, bool EXACT, bool U8>
+__device__ __forceinline__ void k4_rows(const K4RowCtx& k, const float2 (&top)[(CT + 1) / 2], const float2 (&bot)[(CT + 1) / 2],
+                                        int y, int yend, int i0y, int i1y) {
+  unsigned ts = k.tab_s + (y - k.y_tile) * 16;
+#pragma unroll 1
+  for (; K4_PAIR_ROWS && y + 1 < yend; y += 2, ts += 32) {
+    const float4 ta = lds_v4f32(ts), tb = lds_v4f32(ts + 16);
+    const int ca = k4_pixel_candidate<CT, FMA, EXACT>(top, bot, k.C, ta.x, ta.y);
+    const int cb = k4_pixel_candidate<CT, FMA, EXACT>(top, bot, k.C, tb.x, tb.y);
+    k4_finish_pixel<CT, FMA, EXACT, U8>(k, y, ca, i0y, i1y, ta.x, ta.y);
+    k4_finish_pixel<CT, FMA, EXACT, U8>(k, y + 1, cb, i0y, i1y, tb.x, tb.y);
+  }
+#pragma unroll 1
+  for (; y < yend; ++y, ts += 16) {
+    const float4 ta = lds_v4f32(ts);
+    const int ca = k4_pixel_candidate<CT, FMA, EXACT>(top, bot, k.C, ta.x, ta.y);
+    k4_finish_pixel<CT, FMA, EXACT, U8>(k, y, ca, i0y, i1y, ta.x, ta.y);
+  }
+}
+
+template <int CT, int FMA, bool EXACT>
+__global__ void __launch_bounds__(K4_THREADS, K4_MIN_CTAS) k4_upsample_argmax_confusion(const K4Params p) {
+  constexpr int NP = (CT + 1) / 2;
+  constexpr int NS = (CT * K4_SPAN + 31) / 32;
+  constexpr bool U8 = k4_use_u8(CT);
   extern __shared__ __align__(16) uint8_t k4_smem[];
   const int C = EXACT ? CT : p.C, CC = C * C;
-  int* cta_hist = reinterpret_cast<int*>(k4_smem);                       // [CC]
-  const int hist_off = ((CC * 4 + 15) / 16) * 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warp_hist_bytes = ((CC * 32 + 15) / 16) * 16;
-  uint8_t* whist = k4_smem + hist_off + warp * warp_hist_bytes;           // [CC][32] uint8, this warp's
+  // smem: label ring [warps][2][STRIP][32] i64 | row table [warps][TILE_H_MAX] float4 | row stage [warps][32*SPAN] f32 |
+  //       CTA histogram [CC] i32 | per-warp uint8 counters [CC + 1][32]   (bin CC = pixels that do not count)
+  const unsigned ring_s = smem_u32(k4_smem) + (warp * (2 * K4_STRIP * 32) + lane) * 8;
+  float4* tab = reinterpret_cast<float4*>(k4_smem + K4_RING_BYTES) + warp * K4_TILE_H_MAX;
+  const unsigned stage_s = smem_u32(k4_smem + K4_RING_BYTES + K4_TAB_BYTES) + warp * K4_STAGE_FLOATS * 4;
+  int* cta_hist = reinterpret_cast<int*>(k4_smem + K4_RING_BYTES + K4_TAB_BYTES + K4_STAGE_BYTES);
+  const int hist_off = K4_RING_BYTES + K4_TAB_BYTES + K4_STAGE_BYTES + ((CC * 4 + 15) / 16) * 16;
+  const int warp_hist_bytes = (CC + 1) * 32;
+  uint8_t* whist = k4_smem + hist_off + warp * warp_hist_bytes;           // [CC + 1][32] uint8, this warp's
   const bool do_cm = (p.cm != nullptr) && (p.labels != nullptr);
 
   if (do_cm) {
     for (int i = threadIdx.x; i < CC; i += K4_THREADS) cta_hist[i] = 0;
-    if (p.use_u8) {
+    if (U8) {
       int4* z = reinterpret_cast<int4*>(whist);
       for (int i = lane; i < warp_hist_bytes / 16; i += 32) z[i] = make_int4(0, 0, 0, 0);
     }
   }
   __syncthreads();
 
-  const int tile_begin = blockIdx.x * p.tiles_per_cta;
-  const int tile_end = min(p.total_tiles, tile_begin + p.tiles_per_cta);
   const int tiles_per_frame = p.tiles_x * p.tiles_y;
+  const int strips_per_tile = p.tile_h / K4_STRIP;
   const long long hw = (long long)p.h * p.w;
-  int cur_frame = -1;
+  const long long HW = (long long)p.H * p.W;
+  const long long row_bytes = (long long)p.W * 8;
 
-  for (int tile = tile_begin; tile < tile_end; ++tile) {
+  // label staging, one strip (K4_STRIP rows of this lane's column) per commit group.  (pf_tile, pf_st) is the strip
+  // that goes in flight next; pf_src its first label; pf_rows how many of its rows exist.
+  int pf_tile = blockIdx.x, pf_st = 0, pf_stage = 0;
+  const char* pf_src = nullptr;
+  int pf_rows = 0;
+  auto pf_setup_tile = [&]() {                   // first strip of tile pf_tile
+    pf_rows = 0;
+    if (do_cm && pf_tile < p.total_tiles) {
+      const int n = pf_tile / tiles_per_frame;
+      const int trem = pf_tile - n * tiles_per_frame;
+      const int ty = trem / p.tiles_x;
+      const int tx = trem - ty * p.tiles_x;
+      const int x = tx * K4_TILE_W + threadIdx.x;
+      const int y0 = ty * p.tile_h;
+      pf_src = reinterpret_cast<const char*>(p.labels + n * HW + (long long)y0 * p.W + min(x, p.W - 1));
+      pf_rows = (x < p.W) ? min(p.tile_h, p.H - y0) : 0;
+    }
+  };
+  auto issue_strip = [&]() {
+    const unsigned dst = ring_s + pf_stage * (K4_STRIP * 256);
+    const char* src = pf_src;
+#pragma unroll
+    for (int r = 0; r < K4_STRIP; ++r) {
+      if (r < pf_rows) cp_async_8s(dst + r * 256, src);
+      src += row_bytes;
+    }
+    cp_async_commit();
+    pf_src = src;
+    pf_rows -= K4_STRIP;
+    pf_stage ^= 1;
+    if (++pf_st == strips_per_tile) { pf_st = 0; pf_tile += gridDim.x; pf_setup_tile(); }
+  };
+
+  // fold this warp's uint8 counters into the CTA histogram and clear them
+  auto fold_warp_hist = [&]() {
+    __syncwarp();
+    uint4* wh = reinterpret_cast<uint4*>(whist);
+    for (int b = lane; b < CC; b += 32) {
+      const uint4 a = wh[b * 2], c4 = wh[b * 2 + 1];
+      if ((a.x | a.y | a.z | a.w | c4.x | c4.y | c4.z | c4.w) != 0u) {
+        unsigned sum = 0;
+        sum = __dp4a(a.x, 0x01010101u, sum); sum = __dp4a(a.y, 0x01010101u, sum);
+        sum = __dp4a(a.z, 0x01010101u, sum); sum = __dp4a(a.w, 0x01010101u, sum);
+        sum = __dp4a(c4.x, 0x01010101u, sum); sum = __dp4a(c4.y, 0x01010101u, sum);
+        sum = __dp4a(c4.z, 0x01010101u, sum); sum = __dp4a(c4.w, 0x01010101u, sum);
+        atomicAdd(&cta_hist[b], (int)sum);
+        wh[b * 2] = make_uint4(0, 0, 0, 0);
+        wh[b * 2 + 1] = make_uint4(0, 0, 0, 0);
+      }
+    }
+    __syncwarp();
+  };
+
+  K4RowCtx k;
+  k.cta_hist = cta_hist;
+  k.whist_s = smem_u32(whist) + lane;
+  k.hw = hw;
+  k.ign32 = (p.ignore_index >= 0) ? (unsigned)p.ignore_index : 0xffffffffu;
+  k.C = C; k.w = p.w; k.W = p.W;
+  k.tab_s = smem_u32(tab);
+  k.do_cm = do_cm;
+
+  int cur_frame = -1;
+  int rows_since_fold = 0;                       // rows counted into the uint8 counters since the last fold (<= 255)
+  int cur_stage = 0;
+  pf_setup_tile();
+  issue_strip();
+
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     const int n = tile / tiles_per_frame;
     const int trem = tile - n * tiles_per_frame;
     const int ty = trem / p.tiles_x;
     const int tx = trem - ty * p.tiles_x;
+    const int fkey = p.cm_frame_stride ? n : 0;   // one shared matrix: publish once, at the end
 
-    if (do_cm && n != cur_frame) {           // frame boundary: publish this CTA's counts for the finished frame
+    if (do_cm && fkey != cur_frame) {        // frame boundary: publish this CTA's counts for the finished frame
       if (cur_frame >= 0) {
+        if (U8) { fold_warp_hist(); rows_since_fold = 0; }
         __syncthreads();
         long long* dst = p.cm + (long long)cur_frame * p.cm_frame_stride;
         for (int i = threadIdx.x; i < CC; i += K4_THREADS) {
@@ -147,94 +415,105 @@ __global__ void __launch_bounds__(K4_THREADS, 4) k4_upsample_argmax_confusion(co
         }
         __syncthreads();
       }
-      cur_frame = n;
+      cur_frame = fkey;
     }
 
     const int x = tx * K4_TILE_W + threadIdx.x;
-    const bool xvalid = x < p.W;
-    const Tap tapx = ac_tap(p.scale_w, xvalid ? x : p.W - 1, p.w);
-    const float* lg = p.logits + (long long)n * C * hw;
-    const long long* lab_ptr = p.labels ? p.labels + (long long)n * p.H * p.W + x : nullptr;
-    long long* pred_ptr = p.pred ? p.pred + (long long)n * p.H * p.W + x : nullptr;
-    const bool load_labels = do_cm && xvalid;
+    const Tap tapx = ac_tap(p.scale_w, x < p.W ? x : p.W - 1, p.w);
+    const int y_begin = ty * p.tile_h;
+    const int y_tile_end = min(p.H, y_begin + p.tile_h);
+    k.xvalid = x < p.W;
+    k.c_lim = k.xvalid ? (unsigned)C : 0u;
+    k.i0x = tapx.i0; k.i1x = tapx.i1; k.l0x = tapx.l0; k.l1x = tapx.l1;
+    k.lg = p.logits + (long long)n * C * hw;
+    k.pred = p.pred ? p.pred + n * HW + x : nullptr;
+    k.y_tile = y_begin;
 
-    // a0 / a1 hold the horizontally interpolated logits of two source rows; `swap` says which one is the upper row.
-    float a0[CT], a1[CT];
-    int row0 = -1, row1 = -1;
-    bool swap = false;
-    const int y_begin = ty * K4_TILE_H;
-    const int y_end = min(p.H, y_begin + K4_TILE_H);
-
-    // label prefetch pipeline, 4 rows deep
-    long long q0 = -1, q1 = -1, q2 = -1, q3 = -1;
-    if (load_labels) {
-      if (y_begin + 0 < y_end) q0 = ld_stream_s64(lab_ptr + (long long)(y_begin + 0) * p.W);
-      if (y_begin + 1 < y_end) q1 = ld_stream_s64(lab_ptr + (long long)(y_begin + 1) * p.W);
-      if (y_begin + 2 < y_end) q2 = ld_stream_s64(lab_ptr + (long long)(y_begin + 2) * p.W);
-      if (y_begin + 3 < y_end) q3 = ld_stream_s64(lab_ptr + (long long)(y_begin + 3) * p.W);
+    // per-warp row table of the tile: vertical taps and, per row, the end of its run of rows sharing one source-row pair
+    __syncwarp();
+    {
+      const int yy = min(y_begin + lane, p.H - 1);
+      const Tap t = ac_tap(p.scale_h, yy, p.h);
+      const int nxt = __shfl_down_sync(0xffffffffu, t.i0, 1);
+      const bool last = (lane == 31) || (y_begin + lane >= y_tile_end - 1) || (nxt != t.i0);
+      const unsigned ends = __ballot_sync(0xffffffffu, last);
+      const int seg_end = y_begin + lane + __ffs(ends >> lane);            // one past the last row of this row's run
+      tab[lane] = make_float4(t.l0, t.l1, __int_as_float(t.i0), __int_as_float(seg_end));
     }
+    // staged row loads: window of K4_SPAN source columns starting at lane 0's left tap
+    const int j_lo = __shfl_sync(0xffffffffu, tapx.i0, 0);
+    const int j_hi = __shfl_sync(0xffffffffu, tapx.i1, 31);
+    const bool staged = (j_hi - j_lo) < K4_SPAN;
+    int soff[NS];
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+      const int e = q * 32 + lane;
+      const int c = min(e / K4_SPAN, C - 1);
+      soff[q] = c * (int)hw + min(j_lo + (e % K4_SPAN), p.w - 1);
+    }
+    const unsigned t0_s = stage_s + (tapx.i0 - j_lo) * 4, t1_s = stage_s + (tapx.i1 - j_lo) * 4;
+    __syncwarp();
+
+    // a0 / a1 hold the horizontally interpolated logits of two source rows; a0_top says which one is the upper row.
+    float2 a0[NP], a1[NP];
+    float pre[NS];                             // staged path: the window of source row `pre_row`, fetched one segment ahead
+    int row_a0 = -1, row_a1 = -1, pre_row = -1;
+    bool a0_top = true;
 
 #pragma unroll 1
-    for (int y = y_begin; y < y_end; ++y) {
-      const long long g = q0;
-      q0 = q1; q1 = q2; q2 = q3;
-      q3 = (load_labels && y + 4 < y_end) ? ld_stream_s64(lab_ptr + (long long)(y + 4) * p.W) : -1;
-
-      const Tap tapy = ac_tap(p.scale_h, y, p.h);                 // warp-uniform
-      const int top = swap ? row1 : row0, bot = swap ? row0 : row1;
-      if (tapy.i0 != top || tapy.i1 != bot) {                      // new source-row pair (uniform branch)
-        if (row0 == tapy.i0) {
-          swap = false;
-          if (row1 != tapy.i1) { k4_load_row<CT, FMA, EXACT>(a1, lg, C, hw, tapy.i1, p.w, tapx); row1 = tapy.i1; }
-        } else if (row1 == tapy.i0) {
-          swap = true;
-          if (row0 != tapy.i1) { k4_load_row<CT, FMA, EXACT>(a0, lg, C, hw, tapy.i1, p.w, tapx); row0 = tapy.i1; }
-        } else {
-          swap = false;
-          k4_load_row<CT, FMA, EXACT>(a0, lg, C, hw, tapy.i0, p.w, tapx); row0 = tapy.i0;
-          if (row1 != tapy.i1) { k4_load_row<CT, FMA, EXACT>(a1, lg, C, hw, tapy.i1, p.w, tapx); row1 = tapy.i1; }
-        }
-      }
-      const int idx = swap ? k4_pixel_argmax<CT, FMA, true, EXACT>(a0, a1, C, tapy.l0, tapy.l1)
-                           : k4_pixel_argmax<CT, FMA, false, EXACT>(a0, a1, C, tapy.l0, tapy.l1);
-      if (xvalid) {
-        if (pred_ptr) pred_ptr[(long long)y * p.W] = (long long)idx;
-        if (do_cm) {
-          const bool count = (g >= 0) && (g < C) && (g != p.ignore_index);
-          if (p.use_u8) {
-            if (count) {
-              uint8_t* hp = whist + ((int)g * C + idx) * 32 + lane;
-              *hp = (uint8_t)(*hp + 1);
+    for (int ys = y_begin; ys < y_begin + p.tile_h; ys += K4_STRIP) {
+      issue_strip();                           // next strip (possibly of the next tile) goes in flight
+      cp_async_wait<1>();                      // this strip has landed (each lane reads back only its own column)
+      k.lab_s = ring_s + cur_stage * (K4_STRIP * 256);
+      cur_stage ^= 1;
+      if (do_cm && U8 && rows_since_fold + K4_STRIP > 255) { fold_warp_hist(); rows_since_fold = 0; }
+      rows_since_fold += K4_STRIP;
+      const int ye = min(p.H, ys + K4_STRIP);
+      k.y_strip = ys;
+      int y = ys;
+#pragma unroll 1
+      while (y < ye) {
+        const float4 t = lds_v4f32(k.tab_s + (y - y_begin) * 16);
+        const int i0 = __float_as_int(t.z);
+        const int i1 = i0 + ((i0 < p.h - 1) ? 1 : 0);
+        const int yend = min(__float_as_int(t.w), ye);
+        const int top = a0_top ? row_a0 : row_a1, bot = a0_top ? row_a1 : row_a0;
+        if (i0 != top || i1 != bot) {                                    // new source-row pair (warp-uniform)
+          bool need_top = false;
+          if (i0 == bot && i0 != top) a0_top = !a0_top;                  // the old lower row becomes the upper row
+          else if (i0 != top) need_top = true;                           // unrelated pair: load the upper row too
+#pragma unroll 1
+          for (int which = need_top ? 0 : 1; which < 2; ++which) {       // ONE inlined copy of the row loader
+            const int row = which ? i1 : i0;
+            const bool into_a0 = (which == 0) == a0_top;
+            if ((into_a0 ? row_a0 : row_a1) == row) continue;
+            const float* rb = k.lg + (long long)row * p.w;
+            if (staged) {
+              if (pre_row != row) k4_row_fetch<CT>(pre, rb, soff);
+              pre_row = -1;
+              if (into_a0) k4_row_commit<CT, FMA, EXACT>(a0, pre, C, stage_s, t0_s, t1_s, k.l0x, k.l1x);
+              else         k4_row_commit<CT, FMA, EXACT>(a1, pre, C, stage_s, t0_s, t1_s, k.l0x, k.l1x);
+            } else {
+              if (into_a0) k4_row_direct<CT, FMA, EXACT>(a0, rb, C, hw, k.i0x, k.i1x, k.l0x, k.l1x);
+              else         k4_row_direct<CT, FMA, EXACT>(a1, rb, C, hw, k.i0x, k.i1x, k.l0x, k.l1x);
             }
-          } else {
-            const int bin = count ? (int)g * C + idx : -1;
-            const unsigned peers = __match_any_sync(__activemask(), bin);
-            if (count && lane == (__ffs(peers) - 1)) atomicAdd(&cta_hist[bin], __popc(peers));
+            if (into_a0) row_a0 = row; else row_a1 = row;
+          }
+          if (staged && i1 + 1 < p.h) {                                  // the next segment's lower row goes in flight now
+            pre_row = i1 + 1;
+            k4_row_fetch<CT>(pre, k.lg + (long long)pre_row * p.w, soff);
           }
         }
+        if (a0_top) k4_rows<CT, FMA, EXACT, U8>(k, a0, a1, y, yend, i0, i1);
+        else        k4_rows<CT, FMA, EXACT, U8>(k, a1, a0, y, yend, i0, i1);
+        y = yend;
       }
-    }
-
-    if (do_cm && p.use_u8) {                  // fold this warp's uint8 counters (<= 32 per lane per tile)
-      __syncwarp();
-      const uint4* wh = reinterpret_cast<const uint4*>(whist);
-      for (int b = lane; b < CC; b += 32) {
-        const uint4 a = wh[b * 2], c4 = wh[b * 2 + 1];
-        unsigned sum = 0;
-        sum = __dp4a(a.x, 0x01010101u, sum); sum = __dp4a(a.y, 0x01010101u, sum);
-        sum = __dp4a(a.z, 0x01010101u, sum); sum = __dp4a(a.w, 0x01010101u, sum);
-        sum = __dp4a(c4.x, 0x01010101u, sum); sum = __dp4a(c4.y, 0x01010101u, sum);
-        sum = __dp4a(c4.z, 0x01010101u, sum); sum = __dp4a(c4.w, 0x01010101u, sum);
-        if (sum) atomicAdd(&cta_hist[b], (int)sum);
-      }
-      __syncwarp();
-      int4* z = reinterpret_cast<int4*>(whist);
-      for (int i = lane; i < warp_hist_bytes / 16; i += 32) z[i] = make_int4(0, 0, 0, 0);
-      __syncwarp();
     }
   }
+  cp_async_wait<0>();
 
   if (do_cm && cur_frame >= 0) {
+    if (U8) fold_warp_hist();
     __syncthreads();
     long long* dst = p.cm + (long long)cur_frame * p.cm_frame_stride;
     for (int i = threadIdx.x; i < CC; i += K4_THREADS) {
@@ -262,7 +541,7 @@ static int k4_launch_t(const K4Params& p, int grid, size_t smem, cudaStream_t st
 template <int CT, bool EXACT>
 static int k4_launch_c(const K4Params& p, int fma_mode, int grid, size_t smem, cudaStream_t stream) {
   switch (fma_mode) {
-    case 0: return k4_launch_t<CT, 0, EXACT>(p, grid, smem, stream);
+    case 0:
     case 1: return k4_launch_t<CT, 1, EXACT>(p, grid, smem, stream);
     case 2: return k4_launch_t<CT, 2, EXACT>(p, grid, smem, stream);
     default: return k4_launch_t<CT, 3, EXACT>(p, grid, smem, stream);
@@ -284,15 +563,18 @@ int k4_launch(const float* logits, int N, int C, int h, int w, const long long* 
   p.scale_h = ac_scale(h, H);
   p.scale_w = ac_scale(w, W);
   p.tiles_x = ceil_div(W, K4_TILE_W);
-  p.tiles_y = ceil_div(H, K4_TILE_H);
+  // tile height: as tall as possible (fewer source-row loads per output row) while the launch still has >= 4 tiles per
+  // resident CTA, so the static round-robin schedule stays balanced
+  const int max_ctas = num_sms() * K4_MIN_CTAS;
+  p.tile_h = K4_TILE_H_MAX;
+  while (p.tile_h > K4_STRIP && (long long)N * p.tiles_x * ceil_div(H, p.tile_h) < 4LL * max_ctas) p.tile_h /= 2;
+  p.tiles_y = ceil_div(H, p.tile_h);
   p.total_tiles = N * p.tiles_x * p.tiles_y;
   const int CC = C * C;
-  p.use_u8 = (CC * 32 * (K4_THREADS / 32) <= 64 * 1024) ? 1 : 0;
-  const size_t smem = ((CC * 4 + 15) / 16) * 16 + (p.use_u8 ? (size_t)(K4_THREADS / 32) * (((CC * 32 + 15) / 16) * 16) : 0);
-  int max_ctas = num_sms() * (smem > 48 * 1024 ? 3 : 4);
-  int grid = p.total_tiles < max_ctas ? p.total_tiles : max_ctas;
-  p.tiles_per_cta = ceil_div(p.total_tiles, grid);
-  grid = ceil_div(p.total_tiles, p.tiles_per_cta);
+  const int CT = (C == 2) ? 2 : (C == 19) ? 19 : (C <= 8) ? 8 : 32;
+  const size_t smem = (size_t)K4_RING_BYTES + K4_TAB_BYTES + K4_STAGE_BYTES + ((CC * 4 + 15) / 16) * 16 +
+                      (k4_use_u8(CT) ? (size_t)K4_WARPS * ((CC + 1) * 32) : 0);
+  const int grid = p.total_tiles < max_ctas ? p.total_tiles : max_ctas;
   if (C == 2) return k4_launch_c<2, true>(p, fma_mode, grid, smem, stream);
   if (C == 19) return k4_launch_c<19, true>(p, fma_mode, grid, smem, stream);
   if (C <= 8) return k4_launch_c<8, false>(p, fma_mode, grid, smem, stream);
