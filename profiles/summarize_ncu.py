@@ -6,6 +6,7 @@ Runs here (no GPU needed): `ncu -i <rep> --page raw --csv` and keeps, per profil
 statements in DESIGN.md / bench.py rest on.  `traffic_MB` = dram__bytes_read.sum + dram__bytes_write.sum (per launch).
 """
 import csv
+import os
 import io
 import subprocess
 import sys
@@ -60,3 +61,31 @@ def main(rep, out):
 
 if __name__ == "__main__":
     main(sys.argv[1], sys.argv[2])
+
+
+def write_bench_json(summary_csv, out_json, source):
+    """profiles/ncu_summary.json: per-launch DRAM traffic of the kernels bench.py quotes in `roofline.traffic`.
+    The capture is profiles/prof_step.py (one train step of the bench workload, then one eval frame), so the first
+    launch of each kernel below belongs to the train step unless it is the eval kernel."""
+    import json
+    keys = [("head_fwd_gemm", "gemm::gemm_bf16_kernel<0, 0, 2>", 0), ("head_dgrad_gemm", "gemm::gemm_bf16_kernel<0, 0, 1>", 0),
+            ("head_wgrad_gemm", "gemm::gemm_bf16_kernel<1, 1, 2>", 0), ("pack_features", "pack_features_kernel", 0),
+            ("head_gather", "head_gather_kernel", 0), ("grad_im2col", "build_gprime_kernel", 0),
+            ("upsample_ce_main", "k2_upsample_ce_main", 0), ("wgrad_reduce", "wgrad_reduce_kernel", 0),
+            ("eval_argmax_confusion", "k4_upsample_argmax_confusion", 0), ("eval_head_fwd_gemm", "gemm::gemm_bf16_kernel<0, 0, 2>", 1),
+            ("eval_pack_features", "pack_features_kernel", 1), ("eval_head_gather", "head_gather_kernel", 1)]
+    rows = list(csv.DictReader(open(summary_csv)))
+    out = {"source": source, "kernels": {}}
+    for key, pat, nth in keys:
+        hits = [r for r in rows if pat in r["kernel"]]
+        if len(hits) > nth:
+            r = hits[nth]
+            out["kernels"][key] = {"kernel": r["kernel"], "dram_bytes_per_launch": int(float(r["traffic_MB"]) * 1e6),
+                                   "ncu_time_us": float(r["time_us"]), "registers": int(float(r["regs"])) if r["regs"] else None}
+    with open(out_json, "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote", out_json)
+
+
+if __name__ == "__main__" and len(sys.argv) > 3:
+    write_bench_json(sys.argv[2], sys.argv[3], os.path.basename(sys.argv[1]))
