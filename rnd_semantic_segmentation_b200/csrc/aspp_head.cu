@@ -110,31 +110,56 @@ __global__ void __launch_bounds__(256) pack_features_kernel(const float* __restr
 // ------------------------------------------------------------------------------------------
 // forward gather: logits[n,c,y,x] = bias[c] + sum_t Yt[t*C+c][p(n, y+dy_t, x+dx_t)]
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) head_gather_kernel(const float* __restrict__ Yt, long long ypitch, TapTable tt,
-                                                          const float* __restrict__ bias_sum, int C, int h, int w,
-                                                          float* __restrict__ logits) {
-  const int xq = blockIdx.x * 128 + threadIdx.x;
+// One thread per low-res pixel, all classes in registers: per tap one bounds test and C loads at a fixed stride
+// (coalesced along x across the warp), so the kernel issues ~3 instructions per Yt element and runs at the HBM rate
+// of the Yt read instead of being issue-bound on per-element address arithmetic.
+constexpr int GATHER_THREADS = 64;
+template <int CT>
+__global__ void __launch_bounds__(GATHER_THREADS) head_gather_kernel(const float* __restrict__ Yt, long long ypitch, TapTable tt,
+                                                                     const float* __restrict__ bias_sum, int C, int nchunk,
+                                                                     int h, int w, float* __restrict__ logits) {
+  // blockIdx.z = image * nchunk + class chunk; this thread owns classes [c0, c0 + nc) of one pixel (nc <= CT)
+  const int n = blockIdx.z / nchunk;
+  const int c0 = (blockIdx.z - n * nchunk) * CT;
+  const int nc = min(CT, C - c0);
+  const int xq = blockIdx.x * GATHER_THREADS + threadIdx.x;
   const int y = blockIdx.y;
-  const int n = blockIdx.z / C, c = blockIdx.z - n * C;
   if (xq >= w) return;
   const long long pbase = (long long)n * h * w;
-  float acc = bias_sum[c];
-  // taps in groups of 11 (33 = 3 x 11 for the four-rate head): all loads of a group are issued before the adds
-  for (int t0 = 0; t0 < tt.n_taps; t0 += 11) {
-    float v[11];
+  const long long cstep = ypitch * 4;                         // bytes between classes of one tap
+  float acc[CT];
 #pragma unroll
-    for (int k = 0; k < 11; ++k) {
-      const int t = t0 + k;
-      v[k] = 0.f;
-      if (t < tt.n_taps) {
-        const int yy = y + tt.dy[t], xx = xq + tt.dx[t];
-        if (yy >= 0 && yy < h && xx >= 0 && xx < w) v[k] = __ldcs(Yt + (long long)(t * C + c) * ypitch + pbase + (long long)yy * w + xx);
+  for (int c = 0; c < CT; ++c) acc[c] = (c < nc) ? bias_sum[c0 + c] : 0.f;
+  const char* tap_base = reinterpret_cast<const char*>(Yt + pbase + (long long)y * w + xq) + cstep * c0;
+  const long long tstep = cstep * C;                          // bytes between taps
+  constexpr int TG = 3;                                        // taps per batch: TG * CT loads in flight per thread
+#pragma unroll 1
+  for (int t0 = 0; t0 < tt.n_taps; t0 += TG, tap_base += TG * tstep) {
+    float v[TG][CT];
+#pragma unroll
+    for (int k = 0; k < TG; ++k) {
+      const int t = min(t0 + k, tt.n_taps - 1);
+      const int dy = tt.dy[t], dx = tt.dx[t];
+      const int yy = y + dy, xx = xq + dx;
+      const bool inb = (t0 + k < tt.n_taps) && yy >= 0 && yy < h && xx >= 0 && xx < w;
+      const char* src = tap_base + k * tstep + ((long long)dy * w + dx) * 4;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        v[k][c] = 0.f;
+        if (inb && c < nc) v[k][c] = __ldcs(reinterpret_cast<const float*>(src));
+        src += cstep;
       }
     }
 #pragma unroll
-    for (int k = 0; k < 11; ++k) acc += v[k];
+    for (int k = 0; k < TG; ++k)
+#pragma unroll
+      for (int c = 0; c < CT; ++c) acc[c] += v[k][c];
   }
-  logits[((long long)(n * C + c) * h + y) * w + xq] = acc;
+  const long long hw = (long long)h * w;
+  float* dst = logits + ((long long)n * C + c0) * hw + (long long)y * w + xq;
+#pragma unroll
+  for (int c = 0; c < CT; ++c)
+    if (c < nc) dst[c * hw] = acc[c];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -179,51 +204,81 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict_
   }
 }
 
-// G'[p][j] = gO[p - d_t][c]  (j = t*C + c; zero outside the image and for j >= T*C).  One thread builds one 16-byte
-// vector (8 consecutive j); the 16 threads of a pixel write 256 contiguous bytes per pass.
-constexpr int GP_PX = 16;            // pixels per 256-thread block
-__global__ void __launch_bounds__(256) build_gprime_kernel(const __nv_bfloat16* __restrict__ gOt, TapTable tt, int C, int NJ,
-                                                           unsigned c_magic, int h, int w, long long P,
-                                                           __nv_bfloat16* __restrict__ Gp) {
-  __shared__ int s_dy[MAX_TAPS + 1], s_dx[MAX_TAPS + 1];
-  if (threadIdx.x <= MAX_TAPS) {
-    const bool in = (int)threadIdx.x < tt.n_taps;
-    s_dy[threadIdx.x] = in ? tt.dy[threadIdx.x] : (1 << 20);      // sentinel: always outside the image
-    s_dx[threadIdx.x] = in ? tt.dx[threadIdx.x] : (1 << 20);
-  }
-  __syncthreads();
-  const long long p = (long long)blockIdx.x * GP_PX + (threadIdx.x >> 4);
-  if (p >= P) return;
-  const int hw = h * w;
-  const long long n = p / hw;
-  const int s = (int)(p - n * hw);
-  const int y = s / w, x = s - y * w;
-  const unsigned short* img = reinterpret_cast<const unsigned short*>(gOt) + n * hw * 32;
-  const int nvec = NJ >> 3;
+// G'[p][j] = gO[p - d_t][c]  (j = t*C + c; zero outside the image and for j >= T*C).
+// One warp assembles one G' row (NJ bf16) in shared memory: lane t copies the C-element run of tap t from the 64-byte
+// pixel-major gOt row (three 16-byte loads, 2-byte shared stores at the run's unaligned offset t*C), then the warp
+// streams the finished row out with 16-byte coalesced stores.  ~70 warp instructions per pixel instead of ~80 per
+// 16-byte vector: the kernel is bound by the G' write, not by issue.
+constexpr int GP_WARPS = 8;          // warps (= rows in flight) per block
+constexpr int GP_PX_PER_WARP = 8;    // consecutive pixels per warp
+__device__ __forceinline__ void sts_u16(unsigned a, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
+
+template <int CT>                     // CT == C for the instantiated class counts, 0 = runtime C (<= 32)
+__global__ void __launch_bounds__(GP_WARPS * 32) build_gprime_kernel(const __nv_bfloat16* __restrict__ gOt, TapTable tt, int C_rt,
+                                                                     int NJ, int h, int w, long long P,
+                                                                     __nv_bfloat16* __restrict__ Gp) {
+  extern __shared__ __align__(16) uint8_t gp_smem[];
+  const int C = CT ? CT : C_rt;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ntap = tt.n_taps;
-  for (int v8 = threadIdx.x & 15; v8 < nvec; v8 += 16) {
-    const unsigned j0 = (unsigned)(v8 * 8);
-    int t = (int)((j0 * c_magic) >> 16);                       // j0 / C  (exact for j < 1024, C <= 32)
-    int c = (int)(j0 - (unsigned)t * (unsigned)C);
-    const unsigned short* src = nullptr;
-    auto tap_ptr = [&](int tap) -> const unsigned short* {
-      const int tc = tap < ntap ? tap : MAX_TAPS;
-      const int yy = y - s_dy[tc], xx = x - s_dx[tc];
-      return (yy >= 0 && yy < h && xx >= 0 && xx < w) ? img + ((long long)yy * w + xx) * 32 : nullptr;
-    };
-    src = tap_ptr(t);
-    unsigned short e[8];
+  const int row_bytes = NJ * 2;
+  const unsigned row_s = smem_u32(gp_smem) + warp * row_bytes;
+  const int hw = h * w;
+  long long p = ((long long)blockIdx.x * GP_WARPS + warp) * GP_PX_PER_WARP;
+  if (p >= P) return;
+  const long long n0 = p / hw;
+  int s = (int)(p - n0 * hw);
+  int y = s / w, x = s - y * w;
+  const uint4* img = reinterpret_cast<const uint4*>(gOt) + n0 * hw * 4;       // 4 x 16 B per pixel row
+
+  // this lane's taps t = lane, lane + 32, lane + 64 held in registers (a lane-indexed read of the kernel-parameter
+  // table would serialise in the constant cache); absent taps get an offset that is always outside the image
+  constexpr int TS = (MAX_TAPS + 31) / 32;
+  int my_dy[TS], my_dx[TS];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      e[k] = src ? __ldg(src + c) : (unsigned short)0;
-      if (++c == C) { c = 0; ++t; src = tap_ptr(t); }
+  for (int i = 0; i < TS; ++i) {
+    const int t = lane + 32 * i;
+    my_dy[i] = 1 << 20; my_dx[i] = 1 << 20;
+#pragma unroll 1
+    for (int q = 0; q < ntap; ++q)                             // uniform index -> plain constant loads
+      if (q == t) { my_dy[i] = tt.dy[q]; my_dx[i] = tt.dx[q]; }
+  }
+  const int nvec = NJ >> 3;
+  const int pad0 = ntap * C;
+
+  for (int k = 0; k < GP_PX_PER_WARP && p < P; ++k, ++p) {
+#pragma unroll
+    for (int i = 0; i < TS; ++i) {
+      const int t = lane + 32 * i;
+      if (t < ntap) {
+        const int yy = y - my_dy[i], xx = x - my_dx[i];
+        uint4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) q[u] = make_uint4(0, 0, 0, 0);
+        if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+          const uint4* src = img + ((long long)yy * w + xx) * 4;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (u * 8 < C) q[u] = __ldg(src + u);
+        }
+        const unsigned wd[16] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, q[1].z, q[1].w,
+                                 q[2].x, q[2].y, q[2].z, q[2].w, q[3].x, q[3].y, q[3].z, q[3].w};
+        const unsigned dst = row_s + (unsigned)(t * C) * 2;
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c < C) sts_u16(dst + c * 2, (c & 1) ? (wd[c >> 1] >> 16) : wd[c >> 1]);
+      }
     }
-    int4 out;
-    out.x = (int)((unsigned)e[0] | ((unsigned)e[1] << 16));
-    out.y = (int)((unsigned)e[2] | ((unsigned)e[3] << 16));
-    out.z = (int)((unsigned)e[4] | ((unsigned)e[5] << 16));
-    out.w = (int)((unsigned)e[6] | ((unsigned)e[7] << 16));
-    reinterpret_cast<int4*>(Gp + p * NJ)[v8] = out;
+    for (int j = pad0 + lane; j < NJ; j += 32) sts_u16(row_s + j * 2, 0u);              // padding columns
+    __syncwarp();
+    uint4* out = reinterpret_cast<uint4*>(Gp + p * NJ);
+    for (int v = lane; v < nvec; v += 32) {
+      uint4 r;
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(row_s + v * 16));
+      out[v] = r;
+    }
+    __syncwarp();
+    if (++x == w) { x = 0; if (++y == h) { y = 0; img += (long long)hw * 4; } }
   }
 }
 
@@ -297,9 +352,14 @@ int aspp_forward(const void* Xp, const void* Wp, const float* bias_sum, const in
   if (rc) return rc;
   TapTable tt;
   make_taps(tt, rates, R);
-  dim3 grid(ceil_div(w, 128), h, N * C);
+  // class chunks of CT per thread: enough threads in flight to cover the HBM latency of the strided Yt reads
+  const int CT = (C == 19) ? 5 : (C <= 4 ? 4 : 8);
+  const int nchunk = ceil_div(C, CT);
+  dim3 grid(ceil_div(w, GATHER_THREADS), h, N * nchunk);
   profile_begin(4, stream);
-  head_gather_kernel<<<grid, 128, 0, stream>>>(Yt, ypitch, tt, bias_sum, C, h, w, logits);
+  if (CT == 5) head_gather_kernel<5><<<grid, GATHER_THREADS, 0, stream>>>(Yt, ypitch, tt, bias_sum, C, nchunk, h, w, logits);
+  else if (CT == 4) head_gather_kernel<4><<<grid, GATHER_THREADS, 0, stream>>>(Yt, ypitch, tt, bias_sum, C, nchunk, h, w, logits);
+  else head_gather_kernel<8><<<grid, GATHER_THREADS, 0, stream>>>(Yt, ypitch, tt, bias_sum, C, nchunk, h, w, logits);
   profile_end(4, stream);
   B200SEG_LAUNCH_CHECK();
   return B200SEG_OK;
@@ -343,9 +403,11 @@ int aspp_backward_packed(const void* gOt_in, const void* Xp, const void* WpT, co
   TapTable tt;
   make_taps(tt, rates, R);
   {
-    const unsigned c_magic = (65536u + (unsigned)C - 1u) / (unsigned)C;
+    const unsigned blocks = (unsigned)ceil_div_ll(P, (long long)GP_WARPS * GP_PX_PER_WARP);
+    const size_t smem = (size_t)GP_WARPS * NJ * 2;
     profile_begin(5, stream);
-    build_gprime_kernel<<<(unsigned)ceil_div_ll(P, GP_PX), 256, 0, stream>>>(gOt, tt, C, NJ, c_magic, h, w, P, Gp);
+    if (C == 19) build_gprime_kernel<19><<<blocks, GP_WARPS * 32, smem, stream>>>(gOt, tt, C, NJ, h, w, P, Gp);
+    else build_gprime_kernel<0><<<blocks, GP_WARPS * 32, smem, stream>>>(gOt, tt, C, NJ, h, w, P, Gp);
     profile_end(5, stream);
     B200SEG_LAUNCH_CHECK();
   }

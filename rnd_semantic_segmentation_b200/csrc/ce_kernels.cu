@@ -25,7 +25,10 @@ namespace b200seg {
 
 constexpr int K2_THREADS = 128;
 constexpr int K2_TILE_W = 128;
-constexpr int K2_TILE_H = 32;
+#ifndef K2_TILE_H_DEF
+#define K2_TILE_H_DEF 32
+#endif
+constexpr int K2_TILE_H = K2_TILE_H_DEF;        // <= 32 (four label strips in flight)
 constexpr int K2_STRIP = 8;
 
 struct K2Geom {
@@ -95,39 +98,138 @@ struct K2Params {
 
 constexpr int K2_PITCH = K2_THREADS + 1;      // stage row pitch (floats): conflict-free for both access patterns
 
+// ---- K2 main kernel ------------------------------------------------------------------------------------------
+// The kernel is issue-bound (C classes of arithmetic per 8-byte label), so the per-pixel instruction count is what
+// is optimised (same recipe as K4, eval_kernels.cu):
+//   * class PAIRS in registers, all per-pixel arithmetic on packed fp32x2 (FMUL2 / FFMA2 / FADD2), max as a tree of
+//     3-input FMNMX3, exp as ex2.approx on a pre-scaled argument;
+//   * source rows staged per warp through shared memory (coalesced 32-bit-offset loads, immediate-offset LDS) -- the
+//     staged raw windows also serve the labelled-class logit, no dynamic register indexing and no global re-loads;
+//   * labels (int64, the only large stream) brought in by per-lane 8-byte cp.async for the whole tile up front, one
+//     commit group per 8-row strip, so no registers or issue slots are held by loads in flight;
+//   * explicit 32-bit shared-memory addressing for the one-hot updates.
+constexpr int K2_SPAN = 8;                       // source columns a warp's 32 output columns may span on the staged path
+constexpr int K2_PITCH2 = K2_THREADS + 1;        // stage row pitch in float2 (class pair) units
+constexpr float K2_PAD = -1e30f;                 // logit of the padding classes: exp() == 0, never the maximum
+
+__host__ __device__ constexpr int k2_np(int CT) { return (CT + 1) / 2; }
+__host__ __device__ constexpr int k2_ns(int CT) { return (CT * K2_SPAN + 31) / 32; }
+
+// shared-memory carve-up of the main kernel, in bytes from the start of dynamic shared memory
+struct K2Smem {
+  int stage0, stage1, blk, wt, red_lo, red_n, colw0, colw1, colx0, colx1, red, raw, ring, total;
+};
+__host__ __device__ inline K2Smem k2_smem_layout(int CT, int C, int ispan, int jspan, int kmax) {
+  K2Smem L;
+  int o = 0;
+  L.stage0 = o; o += k2_np(CT) * K2_PITCH2 * 8;
+  L.stage1 = o; o += k2_np(CT) * K2_PITCH2 * 8;
+  L.blk = o; o += ispan * jspan * C * 4;
+  L.wt = o; o += jspan * kmax * 4;
+  L.red_lo = o; o += jspan * 4;
+  L.red_n = o; o += jspan * 4;
+  L.colw0 = o; o += K2_THREADS * 4;
+  L.colw1 = o; o += K2_THREADS * 4;
+  L.colx0 = o; o += K2_THREADS * 4;
+  L.colx1 = o; o += K2_THREADS * 4;
+  L.red = o; o += 8 * 4;
+  o = (o + 15) / 16 * 16;
+  L.raw = o; o += (K2_THREADS / 32) * 2 * CT * K2_SPAN * 4;        // [warps][2 rows][CT][SPAN] raw logit windows
+  o = (o + 15) / 16 * 16;
+  L.ring = o; o += K2_TILE_H * K2_THREADS * 8;                     // [TILE_H][128] int64 labels
+  L.total = o;
+  return L;
+}
+
+// Load source row `rb` (frame base + row * w) into the register array `dst` (class pairs, horizontally interpolated
+// and scaled by 1/T) and leave its raw CT x K2_SPAN window in this warp's stage `raw_s` (staged path only).
 template <int CT, bool EXACT>
-__device__ __forceinline__ void k2_load_row(float (&dst)[CT], const float* __restrict__ lg, int C, long long hw, int row, int w,
-                                            const Tap& tapx, float inv_T) {
-  const float* p0 = lg + (long long)row * w + tapx.i0;
-  const float* p1 = lg + (long long)row * w + tapx.i1;
-  const float w0 = inv_T * tapx.l0, w1 = inv_T * tapx.l1;
+__device__ __forceinline__ void k2_row_load(float2 (&dst)[(CT + 1) / 2], const float* __restrict__ rb, int C, long long hw, bool staged,
+                                            unsigned raw_s, int wj_lo, int w, unsigned t0_off, unsigned t1_off, int i0, int i1,
+                                            float w0, float w1) {
+  constexpr int NP = (CT + 1) / 2;
+  constexpr int NS = (CT * K2_SPAN + 31) / 32;
+  const float2 L0 = make_float2(w0, w0), L1 = make_float2(w1, w1);
+  if (staged) {
+    const int lane = threadIdx.x & 31;
+    float v[NS];
 #pragma unroll
-  for (int c = 0; c < CT; ++c)
-    if (EXACT || c < C) {
-      dst[c] = w0 * __ldg(p0) + w1 * __ldg(p1);
-      p0 += hw; p1 += hw;
+    for (int q = 0; q < NS; ++q) {                  // element e of the window: class e / SPAN, column wj_lo + e % SPAN
+      const int e = q * 32 + lane;
+      const int c = min(e / K2_SPAN, C - 1);
+      if (e < CT * K2_SPAN) v[q] = __ldg(rb + c * hw + min(wj_lo + (e % K2_SPAN), w - 1));
     }
+    __syncwarp();                                   // every lane is done with the previous contents of this stage
+#pragma unroll
+    for (int q = 0; q < NS; ++q)
+      if (q * 32 + lane < CT * K2_SPAN) sts_f32(raw_s + (q * 32 + lane) * 4, v[q]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+      if (EXACT || 2 * i < C) { a.x = lds_f32(raw_s + t0_off + (2 * i) * K2_SPAN * 4); b.x = lds_f32(raw_s + t1_off + (2 * i) * K2_SPAN * 4); }
+      if (2 * i + 1 < CT && (EXACT || 2 * i + 1 < C)) {
+        a.y = lds_f32(raw_s + t0_off + (2 * i + 1) * K2_SPAN * 4); b.y = lds_f32(raw_s + t1_off + (2 * i + 1) * K2_SPAN * 4);
+      }
+      dst[i] = fma2(L0, a, mul2(L1, b));
+      if (!(EXACT || 2 * i < C)) dst[i].x = K2_PAD;
+      if (!(2 * i + 1 < CT && (EXACT || 2 * i + 1 < C))) dst[i].y = K2_PAD;
+    }
+  } else {
+    const char* p0 = reinterpret_cast<const char*>(rb + i0);
+    const char* p1 = reinterpret_cast<const char*>(rb + i1);
+    const long long step = hw * 4;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+      if (EXACT || 2 * i < C) { a.x = __ldg(reinterpret_cast<const float*>(p0)); b.x = __ldg(reinterpret_cast<const float*>(p1)); }
+      p0 += step; p1 += step;
+      if (2 * i + 1 < CT && (EXACT || 2 * i + 1 < C)) { a.y = __ldg(reinterpret_cast<const float*>(p0)); b.y = __ldg(reinterpret_cast<const float*>(p1)); }
+      p0 += step; p1 += step;
+      dst[i] = fma2(L0, a, mul2(L1, b));
+      if (!(EXACT || 2 * i < C)) dst[i].x = K2_PAD;
+      if (!(2 * i + 1 < CT && (EXACT || 2 * i + 1 < C))) dst[i].y = K2_PAD;
+    }
+  }
+}
+
+template <int N>
+__device__ __forceinline__ float k2_sum(const float (&p)[N]) {      // pairwise tree on packed adds
+  float2 t[N / 2];
+#pragma unroll
+  for (int i = 0; i < N / 2; ++i) t[i] = make_float2(p[2 * i], p[2 * i + 1]);
+#pragma unroll
+  for (int n = N / 2; n > 1; n = (n + 1) / 2) {
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) t[i] = add2(t[i], t[n - 1 - i]);
+  }
+  return t[0].x + t[0].y;
 }
 
 template <int CT, bool GRAD, bool EXACT>
 __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Params p) {
-  extern __shared__ __align__(16) float k2_smem[];
+  constexpr int NP = (CT + 1) / 2;
+  constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+  extern __shared__ __align__(16) uint8_t k2_smem_raw[];
   const K2Geom& g = p.g;
   const int C = EXACT ? CT : g.C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // smem carve-up
-  float* stage0 = k2_smem;                           // [CT][129]  per-column sums toward register array a0's source row
-  float* stage1 = stage0 + CT * K2_PITCH;            // [CT][129]  ... toward a1's source row  (both start as -onehot sums)
-  float* blk = stage1 + CT * K2_PITCH;               // [ispan_max][jspan_max][C]
+  // shared-memory regions are re-derived from the layout where they are used (setup / flush) instead of being kept
+  // as live generic pointers across the row loop
+#define K2_L k2_smem_layout(CT, C, g.ispan_max, g.jspan_max, g.kmax)
+#define K2_STAGE0 reinterpret_cast<float2*>(k2_smem_raw + K2_L.stage0)   /* [NP][129] per-column sums toward a0's source row */
+#define K2_STAGE1 reinterpret_cast<float2*>(k2_smem_raw + K2_L.stage1)   /* ... toward a1's source row (start as -onehot sums) */
+#define K2_BLK reinterpret_cast<float*>(k2_smem_raw + K2_L.blk)          /* [ispan_max][jspan_max][C] */
+#define K2_WT reinterpret_cast<float*>(k2_smem_raw + K2_L.wt)            /* [jspan_max][kmax] column -> source-column weights */
+#define K2_RED_LO reinterpret_cast<int*>(k2_smem_raw + K2_L.red_lo)      /* [jspan_max] first contributing column */
+#define K2_RED_N reinterpret_cast<int*>(k2_smem_raw + K2_L.red_n)        /* [jspan_max] number of contributing columns */
   const int blk_floats = g.ispan_max * g.jspan_max * C;
-  float* wt = blk + blk_floats;                      // [jspan_max][kmax] column -> source-column weights
-  int* red_lo = reinterpret_cast<int*>(wt + g.jspan_max * g.kmax);   // [jspan_max] first contributing column
-  int* red_n = red_lo + g.jspan_max;                 // [jspan_max] number of contributing columns
-  float* colw0 = reinterpret_cast<float*>(red_n + g.jspan_max);      // [128] l0x
-  float* colw1 = colw0 + K2_THREADS;                 // [128] l1x
-  int* colx0 = reinterpret_cast<int*>(colw1 + K2_THREADS);   // [128] x0 - j_lo
-  int* colx1 = colx0 + K2_THREADS;                   // [128] x1 - j_lo
-  float* red = reinterpret_cast<float*>(colx1 + K2_THREADS);  // [8]
+  const K2Smem L = K2_L;
+  const unsigned smem_s = smem_u32(k2_smem_raw);
+  const unsigned rawA_s = smem_s + L.raw + (warp * 2 + 0) * CT * K2_SPAN * 4;   // raw window of a0's source row
+  const unsigned rawB_s = smem_s + L.raw + (warp * 2 + 1) * CT * K2_SPAN * 4;   // ... of a1's
+  const unsigned ring_s = smem_s + L.ring + tid * 8;                            // this thread's label column, row stride 1 KB
+  const unsigned st0_s = smem_s + L.stage0 + tid * 8, st1_s = smem_s + L.stage1 + tid * 8;
 
   const int tile = blockIdx.x;
   const int tiles_per_frame = g.tiles_x * g.tiles_y;
@@ -146,9 +248,34 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
   const int i_lo = (int)(g.scale_h * (float)y_begin);
   const int jspan = g.jspan_max;
 
+  // labels of the whole tile go in flight first: one commit group per K2_STRIP rows
+  {
+    const char* src = reinterpret_cast<const char*>(p.labels + (long long)n * g.H * g.W + (long long)y_begin * g.W + (xvalid ? x : 0));
+    const long long row_bytes = (long long)g.W * 8;
+#pragma unroll
+    for (int st = 0; st < K2_TILE_H / K2_STRIP; ++st) {
+#pragma unroll
+      for (int r = 0; r < K2_STRIP; ++r) {
+        const int yy = y_begin + st * K2_STRIP + r;
+        if (xvalid && yy < y_end) cp_async_8s(ring_s + (st * K2_STRIP + r) * (K2_THREADS * 8), src);
+        src += row_bytes;
+      }
+      cp_async_commit();
+    }
+  }
+
   if (GRAD) {
+    float* blk = K2_BLK;
+    float2* stage0 = K2_STAGE0;
+    float* wt = K2_WT;
+    int* red_lo = K2_RED_LO;
+    int* red_n = K2_RED_N;
+    float* colw0 = reinterpret_cast<float*>(k2_smem_raw + L.colw0);
+    float* colw1 = reinterpret_cast<float*>(k2_smem_raw + L.colw1);
+    int* colx0 = reinterpret_cast<int*>(k2_smem_raw + L.colx0);
+    int* colx1 = reinterpret_cast<int*>(k2_smem_raw + L.colx1);
     for (int i = tid; i < blk_floats; i += K2_THREADS) blk[i] = 0.f;
-    for (int i = tid; i < 2 * CT * K2_PITCH; i += K2_THREADS) stage0[i] = 0.f;
+    for (int i = tid; i < 2 * NP * K2_PITCH2; i += K2_THREADS) stage0[i] = make_float2(0.f, 0.f);   // stage0 and stage1 are adjacent
     colw0[tid] = xvalid ? tapx.l0 : 0.f;
     colw1[tid] = xvalid ? tapx.l1 : 0.f;
     colx0[tid] = tapx.i0 - j_lo;
@@ -168,13 +295,19 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
   }
 
   const float* lg = p.logits + (long long)n * C * hw;
-  const long long* lab_ptr = p.labels + (long long)n * g.H * g.W + x;
 
-  float a0[CT], a1[CT];
-  float acc0[GRAD ? CT : 1], acc1[GRAD ? CT : 1];     // d loss / d a0-row, d loss / d a1-row (softmax part)
+  // staged row loads: window of K2_SPAN source columns starting at lane 0's left tap
+  const int wj_lo = __shfl_sync(0xffffffffu, tapx.i0, 0);
+  const int wj_hi = __shfl_sync(0xffffffffu, tapx.i1, 31);
+  const bool staged = (wj_hi - wj_lo) < K2_SPAN;
+  const unsigned t0_off = (unsigned)(tapx.i0 - wj_lo) * 4, t1_off = (unsigned)(tapx.i1 - wj_lo) * 4;
+  const float wx0 = p.inv_T * tapx.l0, wx1 = p.inv_T * tapx.l1;
+
+  float2 a0[NP], a1[NP];
+  float2 acc0[GRAD ? NP : 1], acc1[GRAD ? NP : 1];     // d loss / d a0-row, d loss / d a1-row (softmax part)
   if constexpr (GRAD) {
 #pragma unroll
-    for (int c = 0; c < CT; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
+    for (int i = 0; i < NP; ++i) { acc0[i] = make_float2(0.f, 0.f); acc1[i] = make_float2(0.f, 0.f); }
   }
   int row0 = -1, row1 = -1;         // source rows held in a0 / a1
   bool swap = false;                // true: a1 is the upper row
@@ -184,114 +317,131 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
   // Reduce the open segment's per-column sums onto source columns and add them to blk.
   auto flush_segment = [&]() {
     if constexpr (GRAD) {
+      float2* stage0 = K2_STAGE0;
+      float2* stage1 = K2_STAGE1;
+      float* blk = K2_BLK;
+      const float* wt = K2_WT;
+      const int* red_lo = K2_RED_LO;
+      const int* red_n = K2_RED_N;
 #pragma unroll
-      for (int c = 0; c < CT; ++c)
-        if (EXACT || c < C) {
-          stage0[c * K2_PITCH + tid] += acc0[c];
-          stage1[c * K2_PITCH + tid] += acc1[c];
-          acc0[c] = 0.f; acc1[c] = 0.f;
-        }
+      for (int i = 0; i < NP; ++i) {
+        stage0[i * K2_PITCH2 + tid] = add2(stage0[i * K2_PITCH2 + tid], acc0[i]);
+        stage1[i * K2_PITCH2 + tid] = add2(stage1[i * K2_PITCH2 + tid], acc1[i]);
+        acc0[i] = make_float2(0.f, 0.f); acc1[i] = make_float2(0.f, 0.f);
+      }
       __syncthreads();
       const int r0 = row0 - i_lo, r1 = row1 - i_lo;
-      for (int o = tid; o < C * jspan; o += K2_THREADS) {
-        const int jj = o / C;
-        const int c = o - jj * C;
+      for (int o = tid; o < NP * jspan; o += K2_THREADS) {
+        const int jj = o / NP;
+        const int i = o - jj * NP;
         const int lo = red_lo[jj], cnt = red_n[jj];
         const float* wrow = wt + jj * g.kmax;
-        const float* s0 = stage0 + c * K2_PITCH + lo;
-        const float* s1 = stage1 + c * K2_PITCH + lo;
-        float t0 = 0.f, t1 = 0.f;
+        const float2* s0 = stage0 + i * K2_PITCH2 + lo;
+        const float2* s1 = stage1 + i * K2_PITCH2 + lo;
+        float2 t0 = make_float2(0.f, 0.f), t1 = make_float2(0.f, 0.f);
         for (int k = 0; k < cnt; ++k) {
           const float wk = wrow[k];
-          t0 = fmaf(wk, s0[k], t0);
-          t1 = fmaf(wk, s1[k], t1);
+          const float2 W = make_float2(wk, wk);
+          t0 = fma2(W, s0[k], t0);
+          t1 = fma2(W, s1[k], t1);
         }
-        blk[(r0 * jspan + jj) * C + c] += t0;
-        blk[(r1 * jspan + jj) * C + c] += t1;
+        float* b0 = blk + (r0 * jspan + jj) * C + 2 * i;
+        float* b1 = blk + (r1 * jspan + jj) * C + 2 * i;
+        if (2 * i < C) { b0[0] += t0.x; b1[0] += t1.x; }
+        if (2 * i + 1 < C) { b0[1] += t0.y; b1[1] += t1.y; }
       }
       __syncthreads();
 #pragma unroll
-      for (int c = 0; c < CT; ++c)
-        if (EXACT || c < C) {
-          stage0[c * K2_PITCH + tid] = 0.f;
-          stage1[c * K2_PITCH + tid] = 0.f;
-        }
+      for (int i = 0; i < NP; ++i) {
+        stage0[i * K2_PITCH2 + tid] = make_float2(0.f, 0.f);
+        stage1[i * K2_PITCH2 + tid] = make_float2(0.f, 0.f);
+      }
     }
   };
 
-  // label prefetch pipeline, 4 rows deep
-  const long long ign = (long long)p.ignore_index;
-  long long q0 = ign, q1 = ign, q2 = ign, q3 = ign;
-  if (xvalid) {
-    if (y_begin + 0 < y_end) q0 = ld_stream_s64(lab_ptr + (long long)(y_begin + 0) * g.W);
-    if (y_begin + 1 < y_end) q1 = ld_stream_s64(lab_ptr + (long long)(y_begin + 1) * g.W);
-    if (y_begin + 2 < y_end) q2 = ld_stream_s64(lab_ptr + (long long)(y_begin + 2) * g.W);
-    if (y_begin + 3 < y_end) q3 = ld_stream_s64(lab_ptr + (long long)(y_begin + 3) * g.W);
-  }
+  const unsigned ign32 = (p.ignore_index >= 0) ? (unsigned)p.ignore_index : 0xffffffffu;
+  const unsigned c_lim = xvalid ? (unsigned)C : 0u;
 
 #pragma unroll 1
   for (int y = y_begin; y < y_end; ++y) {
-    const long long gl = q0;
-    q0 = q1; q1 = q2; q2 = q3;
-    q3 = (xvalid && y + 4 < y_end) ? ld_stream_s64(lab_ptr + (long long)(y + 4) * g.W) : ign;
-
+    const int yr = y - y_begin;
+    if ((yr & (K2_STRIP - 1)) == 0) {                        // this strip's labels have landed
+      const int pending = K2_TILE_H / K2_STRIP - 1 - yr / K2_STRIP;      // commit groups that may still be in flight
+      if (pending >= 3) cp_async_wait<3>();
+      else if (pending == 2) cp_async_wait<2>();
+      else if (pending == 1) cp_async_wait<1>();
+      else cp_async_wait<0>();
+    }
     const Tap tapy = ac_tap(g.scale_h, y, g.h);              // CTA-uniform
     const int top = swap ? row1 : row0, bot = swap ? row0 : row1;
     if (!open_seg || tapy.i0 != top || tapy.i1 != bot) {      // new source-row pair (CTA-uniform branch)
       if (open_seg) flush_segment();
       open_seg = true;
-      if (row0 == tapy.i0) {
-        swap = false;
-        if (row1 != tapy.i1) { k2_load_row<CT, EXACT>(a1, lg, C, hw, tapy.i1, g.w, tapx, p.inv_T); row1 = tapy.i1; }
-      } else if (row1 == tapy.i0) {
-        swap = true;
-        if (row0 != tapy.i1) { k2_load_row<CT, EXACT>(a0, lg, C, hw, tapy.i1, g.w, tapx, p.inv_T); row0 = tapy.i1; }
-      } else {
-        swap = false;
-        k2_load_row<CT, EXACT>(a0, lg, C, hw, tapy.i0, g.w, tapx, p.inv_T); row0 = tapy.i0;
-        if (row1 != tapy.i1) { k2_load_row<CT, EXACT>(a1, lg, C, hw, tapy.i1, g.w, tapx, p.inv_T); row1 = tapy.i1; }
+      bool need_top = false;
+      if (row0 == tapy.i0) swap = false;
+      else if (row1 == tapy.i0) swap = true;
+      else { swap = false; need_top = true; }
+#pragma unroll 1
+      for (int which = need_top ? 0 : 1; which < 2; ++which) {
+        const int row = which ? tapy.i1 : tapy.i0;
+        const bool into_a0 = (which == 0) != swap;
+        if ((into_a0 ? row0 : row1) == row) continue;
+        const float* rb = lg + (long long)row * g.w;
+        if (into_a0) { k2_row_load<CT, EXACT>(a0, rb, C, hw, staged, rawA_s, wj_lo, g.w, t0_off, t1_off, tapx.i0, tapx.i1, wx0, wx1); row0 = row; }
+        else         { k2_row_load<CT, EXACT>(a1, rb, C, hw, staged, rawB_s, wj_lo, g.w, t0_off, t1_off, tapx.i0, tapx.i1, wx0, wx1); row1 = row; }
       }
     }
-    const bool valid = xvalid && gl != ign && gl >= 0 && gl < C;
+    const uint2 gl = lds_v2u32(ring_s + yr * (K2_THREADS * 8));     // int64 label as {lo, hi}
+    const bool valid = (gl.y == 0u) && (gl.x < c_lim) && (gl.x != ign32);
     if (valid) {
-      const int gi = (int)gl;
+      const int gi = (int)gl.x;
       const float w0 = swap ? tapy.l1 : tapy.l0;             // weight of a0's row, of a1's row
       const float w1 = swap ? tapy.l0 : tapy.l1;
-      float e[CT];
-      float m = -INFINITY;
+      const float2 W0 = make_float2(w0, w0), W1 = make_float2(w1, w1);
+      float f[2 * NP];
 #pragma unroll
-      for (int c = 0; c < CT; ++c)
-        if (EXACT || c < C) {
-          e[c] = w0 * a0[c] + w1 * a1[c];
-          m = fmaxf(m, e[c]);
-        }
-      // logit of the labelled class: re-interpolate from the (L1-resident) low-res logits
-      const float* u0 = lg + gi * hw + (long long)row0 * g.w;
-      const float* u1 = lg + gi * hw + (long long)row1 * g.w;
-      const float v0 = tapx.l0 * __ldg(u0 + tapx.i0) + tapx.l1 * __ldg(u0 + tapx.i1);
-      const float v1 = tapx.l0 * __ldg(u1 + tapx.i0) + tapx.l1 * __ldg(u1 + tapx.i1);
-      const float vlab = p.inv_T * (w0 * v0 + w1 * v1);
-      float s = 0.f;
-      const float mneg = -m * 1.4426950408889634f;
+      for (int i = 0; i < NP; ++i) {
+        const float2 v = fma2(W0, a0[i], mul2(W1, a1[i]));
+        f[2 * i] = v.x; f[2 * i + 1] = v.y;
+      }
+      const float m = tree_max3<0, 2 * NP, 2 * NP>(f);
+      // logit of the labelled class from the staged raw windows (or re-interpolated from global on the fallback path)
+      float vA, vB;
+      if (staged) {
+        const unsigned ga = (unsigned)gi * (K2_SPAN * 4);
+        vA = fmaf(tapx.l0, lds_f32(rawA_s + ga + t0_off), tapx.l1 * lds_f32(rawA_s + ga + t1_off));
+        vB = fmaf(tapx.l0, lds_f32(rawB_s + ga + t0_off), tapx.l1 * lds_f32(rawB_s + ga + t1_off));
+      } else {
+        const float* u0 = lg + gi * hw + (long long)row0 * g.w;
+        const float* u1 = lg + gi * hw + (long long)row1 * g.w;
+        vA = fmaf(tapx.l0, __ldg(u0 + tapx.i0), tapx.l1 * __ldg(u0 + tapx.i1));
+        vB = fmaf(tapx.l0, __ldg(u1 + tapx.i0), tapx.l1 * __ldg(u1 + tapx.i1));
+      }
+      const float vlab = p.inv_T * fmaf(w0, vA, w1 * vB);
+      const float mneg = -m * LOG2E;
+      const float2 K = make_float2(LOG2E, LOG2E), M = make_float2(mneg, mneg);
 #pragma unroll
-      for (int c = 0; c < CT; ++c)
-        if (EXACT || c < C) {
-          e[c] = fast_exp2(fmaf(e[c], 1.4426950408889634f, mneg));
-          s += e[c];
-        }
-      loss_acc += (m + __logf(s)) - vlab;
+      for (int i = 0; i < NP; ++i) {
+        const float2 arg = fma2(make_float2(f[2 * i], f[2 * i + 1]), K, M);
+        f[2 * i] = fast_exp2(arg.x); f[2 * i + 1] = fast_exp2(arg.y);
+      }
+      const float s = k2_sum<2 * NP>(f);
+      loss_acc += fmaf(__log2f(s), LN2, m) - vlab;
       cnt_acc += 1.f;
       if constexpr (GRAD) {
         const float inv_s = __fdividef(1.f, s);
         const float c0 = w0 * inv_s, c1 = w1 * inv_s;
+        const float2 C0 = make_float2(c0, c0), C1 = make_float2(c1, c1);
 #pragma unroll
-        for (int c = 0; c < CT; ++c)
-          if (EXACT || c < C) {
-            acc0[c] = fmaf(c0, e[c], acc0[c]);
-            acc1[c] = fmaf(c1, e[c], acc1[c]);
-          }
-        stage0[gi * K2_PITCH + tid] -= w0;                  // -onehot, thread-private column
-        stage1[gi * K2_PITCH + tid] -= w1;
+        for (int i = 0; i < NP; ++i) {
+          const float2 pr = make_float2(f[2 * i], f[2 * i + 1]);
+          acc0[i] = fma2(C0, pr, acc0[i]);
+          acc1[i] = fma2(C1, pr, acc1[i]);
+        }
+        // -onehot, thread-private column of the stage: element (class gi) of pair gi/2
+        const unsigned oh = (unsigned)(gi >> 1) * (K2_PITCH2 * 8) + (unsigned)(gi & 1) * 4;
+        sts_f32(st0_s + oh, lds_f32(st0_s + oh) - w0);
+        sts_f32(st1_s + oh, lds_f32(st1_s + oh) - w1);
       }
     }
   }
@@ -300,6 +450,7 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
   // per-tile loss / count partials (fixed-order tree => deterministic)
   loss_acc = warp_sum(loss_acc);
   cnt_acc = warp_sum(cnt_acc);
+  float* red = reinterpret_cast<float*>(k2_smem_raw + K2_L.red);
   if (lane == 0) { red[warp] = loss_acc; red[4 + warp] = cnt_acc; }
   __syncthreads();
   if (tid == 0) {
@@ -307,9 +458,17 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
     p.cnt_part[tile] = (red[4] + red[5]) + (red[6] + red[7]);
   }
   if (GRAD) {
+    const float* blk = K2_BLK;
     float* dst = p.blocks + (long long)tile * blk_floats;
     for (int i = tid; i < blk_floats; i += K2_THREADS) dst[i] = blk[i];
   }
+#undef K2_L
+#undef K2_STAGE0
+#undef K2_STAGE1
+#undef K2_BLK
+#undef K2_WT
+#undef K2_RED_LO
+#undef K2_RED_N
 }
 
 // loss = sum(loss_part) / sum(cnt_part)  (NaN when no valid pixel, like the reference); out = {loss, n_valid}
@@ -423,8 +582,7 @@ __global__ void __launch_bounds__(256) k2_bias_from_partials(const float* bias_p
 template <int CT, bool EXACT>
 static int k2_main_launch(const K2Params& p, bool grad, cudaStream_t stream) {
   const K2Geom& g = p.g;
-  const size_t smem = ((size_t)2 * CT * K2_PITCH + (size_t)g.ispan_max * g.jspan_max * g.C + (size_t)g.jspan_max * (g.kmax + 2) +
-                       4 * K2_THREADS + 8) * 4;
+  const size_t smem = (size_t)k2_smem_layout(CT, g.C, g.ispan_max, g.jspan_max, g.kmax).total;
   B200SEG_CHECK_ARG(smem <= 200 * 1024, "upsample_ce: tile footprint %zu B exceeds shared memory (resize ratio too small)", smem);
   const int tiles = (int)k2_tiles(g);
   profile_begin(6, stream);

@@ -117,19 +117,6 @@ __device__ __noinline__ int k4_exact_softmax_argmax(const float* __restrict__ lg
   return idx;
 }
 
-// max of f[LO..HI) as a tree of 3-input maxima (depth log3 instead of a serial chain)
-template <int LO, int HI, int CT>
-__device__ __forceinline__ float tree_max3(const float (&f)[CT]) {
-  constexpr int n = HI - LO;
-  if constexpr (n == 1) return f[LO];
-  else if constexpr (n == 2) return fmaxf(f[LO], f[LO + 1]);
-  else if constexpr (n == 3) return fmax3(f[LO], f[LO + 1], f[LO + 2]);
-  else {
-    constexpr int a = (n + 2) / 3, b = (n - a + 1) / 2;
-    return fmax3(tree_max3<LO, LO + a, CT>(f), tree_max3<LO + a, LO + a + b, CT>(f), tree_max3<LO + a + b, HI, CT>(f));
-  }
-}
-
 // acc += K when v >= thr, as FSETP + one predicated add
 template <int K>
 __device__ __forceinline__ void add_if_ge(int& acc, float v, float thr) {
