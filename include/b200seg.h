@@ -74,9 +74,10 @@ B200SEG_API int b200seg_upsample_ce_backward(const void* workspace, int N, int C
                                  float inv_temperature, const float* loss_out2, const float* grad_out,
                                  float* grad_logits, void* stream);
 
-/* Packed backward for the fused head+loss path: writes the low-res gradient as bf16 pixel-major gOt [N*h*w][32]
- * (classes >= C zero) -- the operand layout b200seg_aspp_backward_packed consumes -- and, if bias_grad != NULL, the
- * per-class sum of the fp32 gradient (= d loss / d bias of every ASPP branch).  No fp32 NCHW gradient is materialised. */
+/* Packed backward for the fused head+loss path: writes the low-res gradient as bf16 class planes gOt [N][C][h*w]
+ * (the NCHW layout at half the bytes; the buffer must hold N*h*w*32 elements) -- the operand layout
+ * b200seg_aspp_backward_packed consumes -- and, if bias_grad != NULL, the per-class sum of the fp32 gradient
+ * (= d loss / d bias of every ASPP branch).  No fp32 NCHW gradient is materialised. */
 B200SEG_API int b200seg_upsample_ce_backward_packed(void* workspace, int N, int C, int h, int w, int H, int W,
                                         float inv_temperature, const float* loss_out2, const float* grad_out, void* gOt,
                                         float* bias_grad, void* stream);
@@ -137,7 +138,7 @@ B200SEG_API int b200seg_aspp_backward(const float* grad_logits, const void* Xp, 
                           int Cin, int C, int h, int w, void* scratch, int64_t scratch_bytes, int splits, float* grad_x,
                           float* const* grad_w, float* const* grad_b, void* stream);
 
-/* same as b200seg_aspp_backward but from the packed bf16 pixel-major gradient gOt [N*h*w][32] (bias gradient comes
+/* same as b200seg_aspp_backward but from the packed bf16 gradient planes gOt [N][C][h*w] (bias gradient comes
  * from b200seg_upsample_ce_backward_packed) */
 B200SEG_API int b200seg_aspp_backward_packed(const void* gOt, const void* Xp, const void* WpT, const int* rates_host, int R, int N,
                                  int Cin, int C, int h, int w, void* scratch, int64_t scratch_bytes, int splits,

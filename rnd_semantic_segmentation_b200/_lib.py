@@ -201,7 +201,7 @@ def upsample_ce_backward(ws, out2, shape_lr, size, inv_temperature=1.0, grad_out
 
 def upsample_ce_backward_packed(ws, out2, shape_lr, size, inv_temperature=1.0, grad_out: Optional[torch.Tensor] = None,
                                 want_bias: bool = True):
-    """Returns (gOt bf16 [N*h*w, 32] pixel-major low-res gradient, bias_grad fp32 [C] | None)."""
+    """Returns (gOt: bf16 low-res gradient as class planes [N][C][h*w] in a [N*h*w, 32] buffer, bias_grad fp32 [C] | None)."""
     lib = load()
     N, C, h, w = shape_lr
     H, W = size

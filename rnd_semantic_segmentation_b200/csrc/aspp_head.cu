@@ -165,23 +165,15 @@ __global__ void __launch_bounds__(GATHER_THREADS) head_gather_kernel(const float
 // ------------------------------------------------------------------------------------------
 // backward prep: gO fp32 NCHW [N,C,hw] -> gOt bf16 [P][32]; bias grad; G' bf16 [P][NJ]
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) grad_to_pixel_major_kernel(const float* __restrict__ g, int C, int hw, long long P,
-                                                                  __nv_bfloat16* __restrict__ gOt) {
-  const long long p = blockIdx.x * 256LL + threadIdx.x;
-  if (p >= P) return;
-  const long long n = p / hw, s = p - n * hw;
-  uint32_t wds[16];
-#pragma unroll
-  for (int c = 0; c < 32; c += 2) {
-    const float a = c < C ? g[(n * C + c) * hw + s] : 0.f;
-    const float b = c + 1 < C ? g[(n * C + c + 1) * hw + s] : 0.f;
-    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    wds[c >> 1] = *reinterpret_cast<const uint32_t*>(&v);
+// gO fp32 NCHW -> gOc bf16 [N][C][hw] (same layout, half the bytes): the operand build_gprime_t_kernel shifts
+__global__ void __launch_bounds__(256) grad_to_bf16_planes_kernel(const float* __restrict__ g, long long n,
+                                                                  __nv_bfloat16* __restrict__ gOc) {
+  const long long i = (blockIdx.x * 256LL + threadIdx.x) * 2;
+  if (i + 1 < n) {
+    *reinterpret_cast<__nv_bfloat162*>(gOc + i) = __floats2bfloat162_rn(g[i], g[i + 1]);
+  } else if (i < n) {
+    gOc[i] = __float2bfloat16(g[i]);
   }
-  int4* dst = reinterpret_cast<int4*>(gOt + p * 32);
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    dst[i] = make_int4((int)wds[4 * i], (int)wds[4 * i + 1], (int)wds[4 * i + 2], (int)wds[4 * i + 3]);
 }
 
 // deterministic per-class sum over all pixels (bias gradient), one block per class
@@ -204,81 +196,110 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict_
   }
 }
 
-// G'[p][j] = gO[p - d_t][c]  (j = t*C + c; zero outside the image and for j >= T*C).
-// One warp assembles one G' row (NJ bf16) in shared memory: lane t copies the C-element run of tap t from the 64-byte
-// pixel-major gOt row (three 16-byte loads, 2-byte shared stores at the run's unaligned offset t*C), then the warp
-// streams the finished row out with 16-byte coalesced stores.  ~70 warp instructions per pixel instead of ~80 per
-// 16-byte vector: the kernel is bound by the G' write, not by issue.
-constexpr int GP_WARPS = 8;          // warps (= rows in flight) per block
-constexpr int GP_PX_PER_WARP = 8;    // consecutive pixels per warp
-__device__ __forceinline__ void sts_u16(unsigned a, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
-
-template <int CT>                     // CT == C for the instantiated class counts, 0 = runtime C (<= 32)
-__global__ void __launch_bounds__(GP_WARPS * 32) build_gprime_kernel(const __nv_bfloat16* __restrict__ gOt, TapTable tt, int C_rt,
-                                                                     int NJ, int h, int w, long long P,
-                                                                     __nv_bfloat16* __restrict__ Gp) {
-  extern __shared__ __align__(16) uint8_t gp_smem[];
-  const int C = CT ? CT : C_rt;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ntap = tt.n_taps;
-  const int row_bytes = NJ * 2;
-  const unsigned row_s = smem_u32(gp_smem) + warp * row_bytes;
+// G't[j][p] = gO[c][p - d_t]  (j = t*C + c; zero outside the image and for j >= T*C), bf16 [NJ][Ppitch].
+// In this (tap, class)-major layout every row is a SHIFTED COPY of one class plane of the output gradient with zero
+// fill at the image borders, so the "im2col of the gradient" is a pure streaming copy: one thread per 4-byte word
+// (two pixels), coalesced 128-byte loads and stores.  FAST: w even and every dx even (the DeepLab rates 6/12/18/24),
+// so a word never straddles an image row and the shifted source word is 4-byte aligned; otherwise two 2-byte loads.
+// dgrad consumes G't as the MN-major B operand, wgrad as the K-major A operand of the same tcgen05 kernel.
+constexpr int GPT_ITERS = 8;                 // 4-byte words per thread; a block covers 256 * 2 * GPT_ITERS pixels of one row
+template <bool FAST>
+__global__ void __launch_bounds__(256) build_gprime_t_kernel(const __nv_bfloat16* __restrict__ gOc, TapTable tt, int C, int h, int w,
+                                                             int N, long long Ppitch, __nv_bfloat16* __restrict__ Gp) {
+  const int j = blockIdx.y;                                  // row of G't
+  const int t = j / C, c = j - t * C;
   const int hw = h * w;
-  long long p = ((long long)blockIdx.x * GP_WARPS + warp) * GP_PX_PER_WARP;
-  if (p >= P) return;
-  const long long n0 = p / hw;
-  int s = (int)(p - n0 * hw);
-  int y = s / w, x = s - y * w;
-  const uint4* img = reinterpret_cast<const uint4*>(gOt) + n0 * hw * 4;       // 4 x 16 B per pixel row
-
-  // this lane's taps t = lane, lane + 32, lane + 64 held in registers (a lane-indexed read of the kernel-parameter
-  // table would serialise in the constant cache); absent taps get an offset that is always outside the image
-  constexpr int TS = (MAX_TAPS + 31) / 32;
-  int my_dy[TS], my_dx[TS];
+  const long long P = (long long)N * hw;
+  long long p0 = (long long)blockIdx.x * (512 * GPT_ITERS) + threadIdx.x * 2;     // first of this thread's two pixels
+  uint32_t* out = reinterpret_cast<uint32_t*>(Gp + (long long)j * Ppitch);          // Ppitch is even: words are aligned
+  if (t >= tt.n_taps) {                                      // padding rows of the packed dimension
 #pragma unroll
-  for (int i = 0; i < TS; ++i) {
-    const int t = lane + 32 * i;
-    my_dy[i] = 1 << 20; my_dx[i] = 1 << 20;
-#pragma unroll 1
-    for (int q = 0; q < ntap; ++q)                             // uniform index -> plain constant loads
-      if (q == t) { my_dy[i] = tt.dy[q]; my_dx[i] = tt.dx[q]; }
+    for (int it = 0; it < GPT_ITERS; ++it, p0 += 512)
+      if (p0 < P) out[p0 >> 1] = 0u;
+    return;
   }
-  const int nvec = NJ >> 3;
-  const int pad0 = ntap * C;
-
-  for (int k = 0; k < GP_PX_PER_WARP && p < P; ++k, ++p) {
+  const int dy = tt.dy[t], dx = tt.dx[t];
+  const unsigned short* planes = reinterpret_cast<const unsigned short*>(gOc);
+  if (FAST) {
+    // (image, row, column) of p0, advanced by 512 pixels per iteration without divisions
+    int n = (int)(p0 / hw);
+    int sidx = (int)(p0 - (long long)n * hw);
+    int y = sidx / w, x = sidx - y * w;
+    const int step_y = 512 / w, step_x = 512 - step_y * w;
 #pragma unroll
-    for (int i = 0; i < TS; ++i) {
-      const int t = lane + 32 * i;
-      if (t < ntap) {
-        const int yy = y - my_dy[i], xx = x - my_dx[i];
-        uint4 q[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) q[u] = make_uint4(0, 0, 0, 0);
-        if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
-          const uint4* src = img + ((long long)yy * w + xx) * 4;
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (u * 8 < C) q[u] = __ldg(src + u);
-        }
-        const unsigned wd[16] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, q[1].z, q[1].w,
-                                 q[2].x, q[2].y, q[2].z, q[2].w, q[3].x, q[3].y, q[3].z, q[3].w};
-        const unsigned dst = row_s + (unsigned)(t * C) * 2;
-#pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (c < C) sts_u16(dst + c * 2, (c & 1) ? (wd[c >> 1] >> 16) : wd[c >> 1]);
+    for (int it = 0; it < GPT_ITERS; ++it, p0 += 512) {
+      if (p0 < P) {
+        const int ys = y - dy, xs = x - dx;
+        uint32_t word = 0;
+        if (ys >= 0 && ys < h && xs >= 0 && xs < w)
+          word = __ldg(reinterpret_cast<const uint32_t*>(planes + ((long long)n * C + c) * hw + ys * w + xs));
+        out[p0 >> 1] = word;
       }
+      x += step_x; y += step_y;
+      if (x >= w) { x -= w; ++y; }
+      while (y >= h) { y -= h; ++n; }
     }
-    for (int j = pad0 + lane; j < NJ; j += 32) sts_u16(row_s + j * 2, 0u);              // padding columns
-    __syncwarp();
-    uint4* out = reinterpret_cast<uint4*>(Gp + p * NJ);
-    for (int v = lane; v < nvec; v += 32) {
-      uint4 r;
-      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(row_s + v * 16));
-      out[v] = r;
+  } else {
+#pragma unroll 1
+    for (int it = 0; it < GPT_ITERS; ++it, p0 += 512) {
+      if (p0 >= P) break;
+      uint32_t word = 0;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const long long pp = p0 + e;
+        if (pp < P) {
+          const int n = (int)(pp / hw);
+          const int sidx = (int)(pp - (long long)n * hw);
+          const int y = sidx / w, x = sidx - y * w;
+          const int ys = y - dy, xs = x - dx;
+          if (ys >= 0 && ys < h && xs >= 0 && xs < w)
+            word |= (uint32_t)__ldg(planes + ((long long)n * C + c) * hw + (long long)ys * w + xs) << (16 * e);
+        }
+      }
+      out[p0 >> 1] = word;                                   // may spill one element into the row padding
     }
-    __syncwarp();
-    if (++x == w) { x = 0; if (++y == h) { y = 0; img += (long long)hw * 4; } }
+  }
+}
+
+// Same copy with 16-byte stores: one thread per 8 pixels (requires w % 8 == 0 so a vector never straddles an image row,
+// and even dx so the four shifted source words are 4-byte aligned).
+constexpr int GPT8_ITERS = 2;                // 16-byte vectors per thread; a block covers 256 * 8 * GPT8_ITERS pixels
+__global__ void __launch_bounds__(256) build_gprime_t8_kernel(const __nv_bfloat16* __restrict__ gOc, TapTable tt, int C, int h, int w,
+                                                              int N, long long Ppitch, __nv_bfloat16* __restrict__ Gp) {
+  const int j = blockIdx.y;
+  const int t = j / C, c = j - t * C;
+  const int hw = h * w;
+  const long long P = (long long)N * hw;
+  long long p0 = (long long)blockIdx.x * (2048 * GPT8_ITERS) + threadIdx.x * 8;
+  uint4* out = reinterpret_cast<uint4*>(Gp + (long long)j * Ppitch);
+  if (t >= tt.n_taps) {
+#pragma unroll
+    for (int it = 0; it < GPT8_ITERS; ++it, p0 += 2048)
+      if (p0 < P) out[p0 >> 3] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const int dy = tt.dy[t], dx = tt.dx[t];
+  const unsigned short* planes = reinterpret_cast<const unsigned short*>(gOc);
+  int n = (int)(p0 / hw);
+  int sidx = (int)(p0 - (long long)n * hw);
+  int y = sidx / w, x = sidx - y * w;
+  const int step_y = 2048 / w, step_x = 2048 - step_y * w;
+#pragma unroll
+  for (int it = 0; it < GPT8_ITERS; ++it, p0 += 2048) {
+    if (p0 < P) {
+      const int ys = y - dy, xs = x - dx;
+      uint32_t wd[4] = {0u, 0u, 0u, 0u};
+      if (ys >= 0 && ys < h) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(planes + ((long long)n * C + c) * hw + ys * w + xs);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (xs + 2 * k >= 0 && xs + 2 * k < w) wd[k] = __ldg(src + k);
+      }
+      out[p0 >> 3] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    }
+    x += step_x; y += step_y;
+    if (x >= w) { x -= w; ++y; }
+    while (y >= h) { y -= h; ++n; }
   }
 }
 
@@ -365,20 +386,20 @@ int aspp_forward(const void* Xp, const void* Wp, const float* bias_sum, const in
   return B200SEG_OK;
 }
 
-// scratch: gOt [P][32] bf16 | Gp [P][NJ] bf16 | wpart [S][NJ][Cin] fp32
+// scratch: gOc bf16 [N][C][hw] (P*32 elements reserved) | G't [NJ][Ppitch] bf16 | wpart [S][NJ][Cin] fp32
 long long aspp_bwd_scratch_bytes(int N, int Cin, int C, int h, int w, int R, int splits) {
   const long long P = (long long)N * h * w;
   const int NJ = aspp_nj(C, R);
-  return P * 32 * 2 + 256 + P * NJ * 2 + 256 + (long long)splits * NJ * Cin * 4 + 256;
+  const long long Ppitch = ceil_div_ll(P, 8) * 8;
+  return P * 32 * 2 + 256 + Ppitch * NJ * 2 + 256 + (long long)splits * NJ * Cin * 4 + 256;
 }
 
-// scratch layout: gOt [P][32] bf16 | Gp [P][NJ] bf16 | wpart [S][NJ][Cin] fp32
 static void aspp_bwd_carve(void* scratch, long long P, int NJ, __nv_bfloat16** gOt, __nv_bfloat16** Gp, float** wpart) {
   uint8_t* sp = reinterpret_cast<uint8_t*>(scratch);
   *gOt = reinterpret_cast<__nv_bfloat16*>(sp);
   sp += (P * 32 * 2 + 255) / 256 * 256;
   *Gp = reinterpret_cast<__nv_bfloat16*>(sp);
-  sp += (P * NJ * 2 + 255) / 256 * 256;
+  sp += (ceil_div_ll(P, 8) * 8 * NJ * 2 + 255) / 256 * 256;
   *wpart = reinterpret_cast<float*>(sp);
 }
 
@@ -402,19 +423,26 @@ int aspp_backward_packed(const void* gOt_in, const void* Xp, const void* WpT, co
   const __nv_bfloat16* gOt = reinterpret_cast<const __nv_bfloat16*>(gOt_in);
   TapTable tt;
   make_taps(tt, rates, R);
+  const long long Ppitch = ceil_div_ll(P, 8) * 8;
   {
-    const unsigned blocks = (unsigned)ceil_div_ll(P, (long long)GP_WARPS * GP_PX_PER_WARP);
-    const size_t smem = (size_t)GP_WARPS * NJ * 2;
+    bool fast = (w % 2 == 0);
+    for (int t = 0; t < tt.n_taps; ++t) fast = fast && (tt.dx[t] % 2 == 0);
     profile_begin(5, stream);
-    if (C == 19) build_gprime_kernel<19><<<blocks, GP_WARPS * 32, smem, stream>>>(gOt, tt, C, NJ, h, w, P, Gp);
-    else build_gprime_kernel<0><<<blocks, GP_WARPS * 32, smem, stream>>>(gOt, tt, C, NJ, h, w, P, Gp);
+    if (fast && w % 8 == 0) {
+      dim3 grid((unsigned)ceil_div_ll(P, 2048 * GPT8_ITERS), (unsigned)NJ);
+      build_gprime_t8_kernel<<<grid, 256, 0, stream>>>(gOt, tt, C, h, w, N, Ppitch, Gp);
+    } else {
+      dim3 grid((unsigned)ceil_div_ll(P, 512 * GPT_ITERS), (unsigned)NJ);
+      if (fast) build_gprime_t_kernel<true><<<grid, 256, 0, stream>>>(gOt, tt, C, h, w, N, Ppitch, Gp);
+      else build_gprime_t_kernel<false><<<grid, 256, 0, stream>>>(gOt, tt, C, h, w, N, Ppitch, Gp);
+    }
     profile_end(5, stream);
     B200SEG_LAUNCH_CHECK();
   }
   if (grad_x) {
-    // dX[ci, p] = WpT[ci, :] . G'[p, :]   -> fp32 NCHW: column p = (image, pixel), row = channel
+    // dX[ci, p] = WpT[ci, :] . G't[:, p]   -> fp32 NCHW: column p = (image, pixel), row = channel
     gemm::Operand a{(const __nv_bfloat16*)WpT, false, NJ};
-    gemm::Operand b{Gp, false, NJ};
+    gemm::Operand b{Gp, true, Ppitch};
     int rc = gemm::launch(a, b, Cin, (int)P, NJ, 1, grad_x, hw, hw, (long long)Cin * hw, 0, stream, nullptr, 1, gemm::SHARE_B);
     if (rc) return rc;
   }
@@ -423,8 +451,8 @@ int aspp_backward_packed(const void* gOt_in, const void* Xp, const void* WpT, co
     bool any = false;
     for (int r = 0; r < MAX_RATES; ++r) { gw.p[r] = r < R ? grad_w[r] : nullptr; any |= gw.p[r] != nullptr; }
     if (any) {
-      // dWp[j, ci] = sum_p G'[p, j] * Xp[p, ci]   both operands MN-major, split-K over pixels
-      gemm::Operand a{Gp, true, NJ};
+      // dWp[j, ci] = sum_p G't[j, p] * Xp[p, ci]   A K-major, B MN-major, split-K over pixels
+      gemm::Operand a{Gp, false, Ppitch};
       gemm::Operand b{(const __nv_bfloat16*)Xp, true, Cin};
       int used = 1;
       const long long slab = (long long)NJ * Cin;
@@ -452,7 +480,7 @@ int aspp_backward(const float* grad_logits, const void* Xp, const void* WpT, con
   const long long P = (long long)N * h * w;
   const int hw = h * w;
   __nv_bfloat16* gOt = reinterpret_cast<__nv_bfloat16*>(scratch);
-  grad_to_pixel_major_kernel<<<(unsigned)ceil_div_ll(P, 256), 256, 0, stream>>>(grad_logits, C, hw, P, gOt);
+  grad_to_bf16_planes_kernel<<<(unsigned)ceil_div_ll(P * C, 512), 256, 0, stream>>>(grad_logits, P * C, gOt);
   B200SEG_LAUNCH_CHECK();
   if (grad_b) {
     MutPtrList gb;

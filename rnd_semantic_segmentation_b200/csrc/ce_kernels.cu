@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(256) k2_finalize_loss(const float* loss_part, 
 
 // grad[n,c,i,j] = grad_out * inv_T / n_valid * sum over the tiles touching (i,j) of their partial block.
 // PACKED = false: fp32 NCHW grad_logits (the autograd contract of the stand-alone loss op).
-// PACKED = true : bf16 pixel-major gOt[p][32] (what the head's backward GEMMs consume) + per-block fp32 partial sums
+// PACKED = true : bf16 class planes gOc[n][c][hw] (what the head's backward consumes) + per-block fp32 partial sums
 //                 of the gradient per class (-> bias gradient), skipping the NCHW round trip.
 template <bool PACKED>
 __global__ void __launch_bounds__(128) k2_finalize_grad(const K2Geom g, const float* blocks, const float* loss_out2,
@@ -535,17 +535,11 @@ __global__ void __launch_bounds__(128) k2_finalize_grad(const K2Geom g, const fl
 #pragma unroll
       for (int c = 0; c < 32; ++c)
         if (c < g.C) dst[c * hw] = acc[c];
-    } else {
-      uint32_t wds[16];
+    } else {                           // bf16 class planes [N][C][hw], coalesced along x
+      __nv_bfloat16* dst = gOt + (long long)n * g.C * hw + (long long)i * g.w + j;
 #pragma unroll
-      for (int c = 0; c < 32; c += 2) {
-        const __nv_bfloat162 v = __floats2bfloat162_rn(acc[c], acc[c + 1]);     // acc[c >= C] == 0
-        wds[c >> 1] = *reinterpret_cast<const uint32_t*>(&v);
-      }
-      int4* dst = reinterpret_cast<int4*>(gOt + ((long long)n * hw + (long long)i * g.w + j) * 32);
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        dst[q] = make_int4((int)wds[4 * q], (int)wds[4 * q + 1], (int)wds[4 * q + 2], (int)wds[4 * q + 3]);
+      for (int c = 0; c < 32; ++c)
+        if (c < g.C) dst[c * hw] = __float2bfloat16(acc[c]);
     }
   }
   if (PACKED) {                       // fixed-order block reduction of the fp32 gradient per class
