@@ -198,6 +198,15 @@ def run_ours(args):
                 "peak_source": peaks["source"] + ", sustained bf16",
                 "algorithmic_flops_per_launch": flops_per_launch, "kernels": kernels}
 
+    # ---- seam format: bf16 channels_last features in, bf16 channels_last feature gradient out.
+    #      Reported beside the headline, which stays on the reference's fp32 NCHW contract.
+    xs = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    ms_seam, _ = timed(lambda: train_step(xs, labels), args.steps, args.warmup)
+    seam = {"value": round(world * label_px / (ms_seam / args.steps * 1e-3) / 1e6, 2), "unit": "Mpx/s",
+            "ms_per_step": round(ms_seam / args.steps, 4),
+            "input": "bf16 channels_last features (zero-copy GEMM operand), bf16 channels_last feature gradient from the dgrad epilogue"}
+    del xs
+
     # ---- end to end through the public API with HOST buffers (pinned), H2D + loss D2H inside the timed region
     xh = x.cpu().pin_memory()
     lh = labels.cpu().pin_memory()
@@ -276,7 +285,8 @@ def run_ours(args):
                            "step": "head fwd + upsample/CE fwd + bwd (dX, dW, db)" + (" + NCCL mean all-reduce of head grads" if world > 1 else ""),
                            "l2": "inputs larger than L2 (features %d MB per step)" % (x.numel() * 4 // 2 ** 20),
                            "parallelism": "dp%d (batch sharded by image)" % world},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_timed), "roofline": roofline, "eval": eval_obj}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_timed), "roofline": roofline, "eval": eval_obj,
+                "seam_bf16_nhwc": seam}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         emit(line)

@@ -144,6 +144,13 @@ B200SEG_API int b200seg_aspp_backward_packed(const void* gOt, const void* Xp, co
                                  int Cin, int C, int h, int w, void* scratch, int64_t scratch_bytes, int splits,
                                  float* grad_x, float* const* grad_w, void* stream);
 
+/* Seam-format variant (the backbone hands over bf16 channels_last features): the feature
+ * gradient is written as bf16 pixel-major [N*h*w][Cin] (= NHWC / channels_last), half the bytes of the fp32 NCHW
+ * gradient, by the same tcgen05 kernel with a bf16 epilogue.  Xp is then the backbone's own output, zero-copy. */
+B200SEG_API int b200seg_aspp_backward_packed_nhwc(const void* gOt, const void* Xp, const void* WpT, const int* rates_host, int R, int N,
+                                      int Cin, int C, int h, int w, void* scratch, int64_t scratch_bytes, int splits,
+                                      void* grad_x_nhwc_bf16, float* const* grad_w, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * instrumentation (bench.py): number of kernels this library has launched, and per-kernel CUDA-event
  * timing on the launching stream.  Tags: 0 head fwd GEMM, 1 head dgrad GEMM, 2 head wgrad GEMM,

@@ -52,6 +52,8 @@ SIGNATURES = {
                                       c_vp, c_vp, c_vp, c_vp]),
     "b200seg_aspp_backward_packed": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64, c_int,
                                              c_vp, c_vp, c_vp]),
+    "b200seg_aspp_backward_packed_nhwc": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64,
+                                                  c_int, c_vp, c_vp, c_vp]),
     "b200seg_launch_count": (ctypes.c_longlong, []),
     "b200seg_profile_enable": (None, [c_int]),
     "b200seg_profile_read": (c_int, [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int)]),
@@ -415,8 +417,9 @@ def aspp_backward(grad_logits: torch.Tensor, Xp: torch.Tensor, WpT: torch.Tensor
 
 
 def aspp_backward_packed(gOt: torch.Tensor, Xp: torch.Tensor, WpT: torch.Tensor, rates: Sequence[int], N: int, h: int, w: int,
-                         C: int, need_grad_x: bool = True, need_grad_w: bool = True, splits: int = 0):
-    """Head backward from the packed bf16 gradient.  Returns (grad_x fp32 NCHW | None, [grad_w]*R | None)."""
+                         C: int, need_grad_x: bool = True, need_grad_w: bool = True, splits: int = 0, nhwc_bf16: bool = False):
+    """Head backward from the packed bf16 gradient.  Returns (grad_x | None, [grad_w]*R | None); grad_x is fp32 NCHW, or with
+    ``nhwc_bf16`` a bf16 channels_last tensor of logical shape [N,Cin,h,w] (the seam format, written directly by the GEMM)."""
     lib = load()
     _need(gOt, torch.bfloat16, "gOt")
     Cin = Xp.shape[1]
@@ -426,9 +429,16 @@ def aspp_backward_packed(gOt: torch.Tensor, Xp: torch.Tensor, WpT: torch.Tensor,
         splits = default_wgrad_splits(N * h * w, C, Cin, R)
     nbytes = lib.b200seg_aspp_backward_scratch_bytes(N, Cin, C, h, w, R, splits)
     scratch = _scratch("aspp_bwd", nbytes, dev)
-    gx = torch.empty((N, Cin, h, w), dtype=torch.float32, device=dev) if need_grad_x else None
     gws = [torch.empty((C, Cin, 3, 3), dtype=torch.float32, device=dev) for _ in range(R)] if need_grad_w else None
     rates_arr = (c_int * R)(*[int(r) for r in rates])
+    if nhwc_bf16 and need_grad_x:
+        gx_nhwc = torch.empty((N, h, w, Cin), dtype=torch.bfloat16, device=dev)
+        with torch.cuda.device(dev):
+            _check(lib.b200seg_aspp_backward_packed_nhwc(gOt.data_ptr(), Xp.data_ptr(), WpT.data_ptr(), rates_arr, R, N, Cin, C, h, w,
+                                                         scratch.data_ptr(), nbytes, splits, gx_nhwc.data_ptr(),
+                                                         _ptr_array(gws) if gws else None, _stream()))
+        return gx_nhwc.permute(0, 3, 1, 2), gws
+    gx = torch.empty((N, Cin, h, w), dtype=torch.float32, device=dev) if need_grad_x else None
     with torch.cuda.device(dev):
         _check(lib.b200seg_aspp_backward_packed(gOt.data_ptr(), Xp.data_ptr(), WpT.data_ptr(), rates_arr, R, N, Cin, C, h, w,
                                                 scratch.data_ptr(), nbytes, splits, _ptr(gx), _ptr_array(gws) if gws else None,

@@ -56,7 +56,7 @@ int k2_forward(const float*, int, int, int, int, const long long*, int, int, int
 int k2_backward(const void*, int, int, int, int, int, int, float, const float*, const float*, float*, cudaStream_t);
 int k2_backward_packed(void*, int, int, int, int, int, int, float, const float*, const float*, void*, float*, cudaStream_t);
 int aspp_backward_packed(const void*, const void*, const void*, const int*, int, int, int, int, int, int, void*, long long, int, float*,
-                         float* const*, cudaStream_t);
+                         float* const*, cudaStream_t, void*);
 int upsample_fwd_launch(const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int upsample_bwd_launch(const float*, float*, int, int, int, int, int, cudaStream_t);
 long long k3_workspace_bytes();
@@ -151,7 +151,16 @@ int b200seg_aspp_backward_packed(const void* gOt, const void* Xp, const void* Wp
                                  int h, int w, void* scratch, int64_t scratch_bytes, int splits, float* grad_x, float* const* grad_w,
                                  void* stream) {
   REQUIRE_DEVICE();
-  return aspp_backward_packed(gOt, Xp, WpT, rates_host, R, N, Cin, C, h, w, scratch, scratch_bytes, splits, grad_x, grad_w, S(stream));
+  return aspp_backward_packed(gOt, Xp, WpT, rates_host, R, N, Cin, C, h, w, scratch, scratch_bytes, splits, grad_x, grad_w, S(stream),
+                              nullptr);
+}
+
+int b200seg_aspp_backward_packed_nhwc(const void* gOt, const void* Xp, const void* WpT, const int* rates_host, int R, int N, int Cin,
+                                      int C, int h, int w, void* scratch, int64_t scratch_bytes, int splits, void* grad_x_nhwc_bf16,
+                                      float* const* grad_w, void* stream) {
+  REQUIRE_DEVICE();
+  return aspp_backward_packed(gOt, Xp, WpT, rates_host, R, N, Cin, C, h, w, scratch, scratch_bytes, splits, nullptr, grad_w, S(stream),
+                              grad_x_nhwc_bf16);
 }
 
 int b200seg_upsample_bilinear_forward(const float* in, float* out, int NC, int h, int w, int H, int W, int fma_mode, void* stream) {

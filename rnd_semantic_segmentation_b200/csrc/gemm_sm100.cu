@@ -87,8 +87,11 @@ static int launch_s(const CUtensorMap& ta, const CUtensorMap& tb, const Params& 
 
 int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, float* out, long long row_stride,
            int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used, int prof_tag,
-           int share) {
+           int share, bool out_bf16) {
   B200SEG_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem %dx%dx%d", M, N, K);
+  B200SEG_CHECK_ARG(!out_bf16 || (col_hw <= 0 && N % 8 == 0 && row_stride % 8 == 0 && split_stride % 8 == 0 &&
+                                  (reinterpret_cast<uintptr_t>(out) & 15) == 0),
+                    "gemm: bf16 output needs plain row-major D with N, row pitch multiples of 8 and a 16-byte aligned base");
   if (!g_share_enabled) share = SHARE_NONE;
   Params p;
   p.M = M; p.N = N; p.K = K;
@@ -104,6 +107,7 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
   p.col_hw = col_hw > 0 ? col_hw : INT_MAX;
   p.img_stride = img_stride;
   p.split_stride = split_stride;
+  p.out_bf16 = out_bf16 ? 1 : 0;
   if (splits_used) *splits_used = p.splits;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && row_stride % 4 == 0 && split_stride % 4 == 0 &&
               (col_hw <= 0 || (col_hw % 4 == 0 && img_stride % 4 == 0)))

@@ -45,6 +45,7 @@ struct Params {
   long long img_stride;     // elements between images (used when col_hw != INT_MAX)
   long long split_stride;   // elements between split-K partial slabs
   int vec_ok;               // output addressing allows 16-byte vector stores
+  int out_bf16;             // D is written as bf16 (plain row-major [M][row_stride], 16-byte aligned rows) instead of fp32
 };
 
 // ------------------------------------------------------------------------------------------
@@ -354,7 +355,43 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * (BLOCK_N / 2));
       const int rows = min(32, p.M - row_base);
-      if (rows > 0 && col_base < p.N) {
+      if (p.out_bf16) {
+        // bf16 row-major D (the NHWC feature gradient): 32 columns per pass, converted before the smem transpose, every
+        // store instruction writes 8 rows x 64 contiguous bytes
+        if (rows > 0 && col_base < p.N) {
+          __nv_bfloat16* outb = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)z * p.split_stride;
+          uint32_t* stw = reinterpret_cast<uint32_t*>(stg);
+#pragma unroll 1
+          for (int c = 0; c < BLOCK_N / 2 / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld16(taddr + (uint32_t)(c * 32), r);
+            tmem_ld16(taddr + (uint32_t)(c * 32 + 16), r + 16);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              uint32_t w4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(r[8 * k + 2 * e]), __uint_as_float(r[8 * k + 2 * e + 1]));
+                w4[e] = *reinterpret_cast<const uint32_t*>(&v);
+              }
+              *reinterpret_cast<uint4*>(stw + lane * EPI_PITCH + 4 * k) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+            __syncwarp();
+            const int col0 = col_base + c * 32 + (lane & 3) * 8;
+            if (col0 < p.N) {                                  // N and row_stride are multiples of 8 on this path
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rr = (lane >> 2) + 8 * i;
+                if (rr < rows)
+                  *reinterpret_cast<uint4*>(outb + (long long)(row_base + rr) * p.row_stride + col0) =
+                      *reinterpret_cast<const uint4*>(stw + rr * EPI_PITCH + (lane & 3) * 4);
+              }
+            }
+            __syncwarp();
+          }
+        }
+      } else if (rows > 0 && col_base < p.N) {
         // per-lane (image, offset) of its first column, advanced by 16 columns per chunk (no division in the loop)
         const int lane_col = p.vec_ok ? (lane & 3) * 4 : (lane & 15);
         int img = (col_base + lane_col) / p.col_hw;
@@ -423,7 +460,7 @@ struct Operand {
 };
 int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, float* out, long long row_stride,
            int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used, int prof_tag = -1,
-           int share = SHARE_NONE);
+           int share = SHARE_NONE, bool out_bf16 = false);
 
 }  // namespace gemm
 }  // namespace b200seg

@@ -100,8 +100,10 @@ class _AsppHeadLossFn(torch.autograd.Function):
         need_w = any(need[6:6 + R])
         need_b = any(need[6 + R:6 + 2 * R])
         gOt, bias = _lib.upsample_ce_backward_packed(ws, out2, (N, C, h, w), size, inv_t, grad_loss.detach().float(), need_b)
-        gx, gws = _lib.aspp_backward_packed(gOt, Xp, WpT, rates, N, h, w, C, need[0], need_w)
-        if gx is not None and x_dtype != torch.float32:
+        # bf16 features (the channels_last seam format): the dgrad GEMM writes the bf16 NHWC gradient itself
+        seam = x_dtype == torch.bfloat16 and Cin % 8 == 0
+        gx, gws = _lib.aspp_backward_packed(gOt, Xp, WpT, rates, N, h, w, C, need[0], need_w, nhwc_bf16=seam)
+        if gx is not None and gx.dtype != x_dtype:
             gx = gx.to(x_dtype)
         out_w = [gws[r] if (gws is not None and need[6 + r]) else None for r in range(R)]
         out_b = [(bias if r == 0 else bias.clone()) if (bias is not None and need[6 + R + r]) else None for r in range(R)]

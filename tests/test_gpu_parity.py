@@ -236,6 +236,34 @@ def test_k1_head_forward_backward(lib, n, cin, C, h, w):
         assert rel_err(m_ours.bias.grad, go.double().sum((0, 2, 3))) <= 1e-5      # bias grad is summed from the fp32 gradient
 
 
+@pytest.mark.parametrize("n,cin,C,h,w,H,W", [(2, 256, 19, 16, 32, 128, 256), (1, 2048, 19, 33, 65, 264, 520), (2, 128, 2, 44, 44, 352, 352)])
+def test_seam_format_bf16_channels_last(lib, n, cin, C, h, w, H, W):
+    """bf16 channels_last features in (zero-copy operand), bf16 channels_last gradient out (written by the
+    dgrad GEMM's bf16 epilogue).  Same loss / weight gradients as the fp32 NCHW contract fed the same bf16-rounded features;
+    the feature gradient equals the fp32 one rounded to bf16 (tolerance: one bf16 ulp of the largest entry, 2^-8 relative)."""
+    from rnd_semantic_segmentation_b200 import ASPP_Classifier_V2
+    torch.manual_seed(5)
+    head = ASPP_Classifier_V2(cin, RATES, RATES, C).cuda()
+    g = torch.Generator().manual_seed(6)
+    x = bf16_round(torch.relu(torch.randn(n, cin, h, w, generator=g)))
+    labels = make_labels(n, H, W, C, 0.1, 7).cuda()
+    xa = x.cuda().requires_grad_(True)                                         # reference contract: fp32 NCHW
+    la, _ = head.forward_loss(xa, labels)
+    la.backward()
+    want_w = [p.grad.clone() for p in head.parameters()]
+    for p in head.parameters():
+        p.grad = None
+    xb = x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    lb, _ = head.forward_loss(xb, labels)
+    lb.backward()
+    assert xb.grad.dtype == torch.bfloat16 and xb.grad.shape == xb.shape
+    assert xb.grad.is_contiguous(memory_format=torch.channels_last)
+    assert abs(la.item() - lb.item()) <= 1e-6 * abs(la.item())
+    assert rel_err(xb.grad, xa.grad) <= 2.0 ** -8
+    for p, wgrad in zip(head.parameters(), want_w):
+        assert rel_err(p.grad, wgrad) <= 1e-6
+
+
 @pytest.mark.parametrize("name", ["head_c19", "head_c2", "head_c19_T18"])
 def test_k1_k2_against_reference_golden(lib, golden, name):
     """End to end (head -> fused upsample+CE -> backward) against fixtures produced by the reference's own code.
