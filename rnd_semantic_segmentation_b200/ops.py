@@ -87,6 +87,7 @@ class _AsppHeadLossFn(torch.autograd.Function):
         ctx.meta = (tuple(rates), (N, Cin, h, w, C), tuple(labels.shape[-2:]), inv_t, x.dtype, need_grad)
         ctx.save_for_backward(Xp, WpT, out2, ws)
         ctx.mark_non_differentiable(logits)
+        ctx.set_materialize_grads(False)       # no zero tensor for the (non-differentiable) logits output in backward
         return out2[0].clone(), logits
 
     @staticmethod
@@ -99,6 +100,8 @@ class _AsppHeadLossFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         need_w = any(need[6:6 + R])
         need_b = any(need[6 + R:6 + 2 * R])
+        if grad_loss is None:
+            return (None,) * (6 + 2 * R)
         gOt, bias = _lib.upsample_ce_backward_packed(ws, out2, (N, C, h, w), size, inv_t, grad_loss.detach().float(), need_b)
         # bf16 features (the channels_last seam format): the dgrad GEMM writes the bf16 NHWC gradient itself
         seam = x_dtype == torch.bfloat16 and Cin % 8 == 0
