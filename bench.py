@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -113,13 +113,16 @@ def max_over_ranks(ms: float) -> float:
 
 
 def timed(step_fn, steps, warmup, sampler=None):
-    """W untimed warm-ups, then exactly K steps between barrier + synchronize, CUDA events on the launching stream."""
+    """W untimed warm-ups, then exactly K steps between barrier + synchronize, CUDA events on the launching stream.
+    The clock sampler (an nvidia-smi subprocess on rank 0) is started BEFORE the warm-up: it then samples the same workload
+    under load for the warm-up plus the timed region, and its fork cannot desynchronise the ranks between the barrier and
+    the first timed step."""
+    if sampler:
+        sampler.start()
     for _ in range(warmup):
         step_fn()
     torch.cuda.synchronize()
     barrier()
-    if sampler:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
@@ -152,17 +155,19 @@ def run_ours(args):
     head = b200.ASPP_Classifier_V2(cin, RATES, RATES, C).to(dev)
     x = synth.make_features(n, cin, h, w, seed=1234 + rank, device=dev)
     labels = synth.make_labels(n, H, W, C, seed=1234 + rank, device=dev)
-    bucket = D.FlatGradBucket(head.parameters())
+    bucket = D.HeadGradBucket(head) if world > 1 else None
     label_px = n * H * W
 
     def train_step(x_in=x, labels_in=labels):
         xg = x_in.detach().requires_grad_(True)            # the backbone needs d loss / d features
         for p in head.parameters():
             p.grad = None
-        loss, _ = head.forward_loss(xg, labels_in)
+        # N > 1: weight gradients land in the flat bucket and its NCCL mean all-reduce runs on a second stream underneath
+        # the data-gradient GEMM; wait() joins the streams (the all-reduce is inside the timed step)
+        loss, _ = head.forward_loss(xg, labels_in, grad_bucket=bucket)
         loss.backward()
-        if world > 1:
-            bucket.allreduce_mean_()
+        if bucket is not None:
+            bucket.wait()
         return loss, xg.grad
 
     launches0 = _lib.launch_count()
@@ -282,7 +287,7 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": args.workload, "features": [n, cin, h, w], "labels": [n, H, W], "num_classes": C,
                            "input": "fp32 NCHW features resident in HBM (reference API contract); bf16 operands, fp32 accumulate",
-                           "step": "head fwd + upsample/CE fwd + bwd (dX, dW, db)" + (" + NCCL mean all-reduce of head grads" if world > 1 else ""),
+                           "step": "head fwd + upsample/CE fwd + bwd (dX, dW, db)" + (" + NCCL mean all-reduce of head grads (overlapped with the dgrad GEMM)" if world > 1 else ""),
                            "l2": "inputs larger than L2 (features %d MB per step)" % (x.numel() * 4 // 2 ** 20),
                            "parallelism": "dp%d (batch sharded by image)" % world},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_timed), "roofline": roofline, "eval": eval_obj,

@@ -151,6 +151,14 @@ B200SEG_API int b200seg_aspp_backward_packed_nhwc(const void* gOt, const void* X
                                       int Cin, int C, int h, int w, void* scratch, int64_t scratch_bytes, int splits,
                                       void* grad_x_nhwc_bf16, float* const* grad_w, void* stream);
 
+/* Superset of the two entries above.  The weight gradients are computed FIRST; `weights_ready_event` (a cudaEvent_t,
+ * may be NULL) is recorded on `stream` as soon as they are complete, before the data-gradient GEMM is enqueued, so a
+ * data-parallel caller can run their NCCL all-reduce on a second stream underneath the data-gradient GEMM
+ * (DDP semantics of train_distill.py:54-62).  Give at most one of grad_x (fp32 NCHW) / grad_x_nhwc_bf16. */
+B200SEG_API int b200seg_aspp_backward_packed_ex(const void* gOt, const void* Xp, const void* WpT, const int* rates_host, int R, int N,
+                                    int Cin, int C, int h, int w, void* scratch, int64_t scratch_bytes, int splits, float* grad_x,
+                                    void* grad_x_nhwc_bf16, float* const* grad_w, void* weights_ready_event, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * instrumentation (bench.py): number of kernels this library has launched, and per-kernel CUDA-event
  * timing on the launching stream.  Tags: 0 head fwd GEMM, 1 head dgrad GEMM, 2 head wgrad GEMM,
@@ -167,6 +175,10 @@ B200SEG_API int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b
                           double* max_err, double* max_ref);
 /* 0 disables the 2-CTA multicast variants inside the ASPP head GEMMs (A/B measurement); default on */
 B200SEG_API void b200seg_gemm_set_sharing(int on);
+/* SMs the data-gradient GEMM leaves free when b200seg_aspp_backward_packed_ex is given a weights_ready_event, so that the
+ * caller's all-reduce kernel can be resident underneath it (the persistent GEMM otherwise fills every SM's shared memory);
+ * default 8 */
+B200SEG_API void b200seg_gemm_set_overlap_sms(int n);
 
 #ifdef __cplusplus
 }

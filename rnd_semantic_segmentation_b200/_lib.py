@@ -54,6 +54,9 @@ SIGNATURES = {
                                              c_vp, c_vp, c_vp]),
     "b200seg_aspp_backward_packed_nhwc": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64,
                                                   c_int, c_vp, c_vp, c_vp]),
+    "b200seg_aspp_backward_packed_ex": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64,
+                                                c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "b200seg_gemm_set_overlap_sms": (None, [c_int]),
     "b200seg_launch_count": (ctypes.c_longlong, []),
     "b200seg_profile_enable": (None, [c_int]),
     "b200seg_profile_read": (c_int, [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int)]),
@@ -417,9 +420,12 @@ def aspp_backward(grad_logits: torch.Tensor, Xp: torch.Tensor, WpT: torch.Tensor
 
 
 def aspp_backward_packed(gOt: torch.Tensor, Xp: torch.Tensor, WpT: torch.Tensor, rates: Sequence[int], N: int, h: int, w: int,
-                         C: int, need_grad_x: bool = True, need_grad_w: bool = True, splits: int = 0, nhwc_bf16: bool = False):
+                         C: int, need_grad_x: bool = True, need_grad_w: bool = True, splits: int = 0, nhwc_bf16: bool = False,
+                         out_w: Optional[Sequence[torch.Tensor]] = None, weights_ready_event: Optional[torch.cuda.Event] = None):
     """Head backward from the packed bf16 gradient.  Returns (grad_x | None, [grad_w]*R | None); grad_x is fp32 NCHW, or with
-    ``nhwc_bf16`` a bf16 channels_last tensor of logical shape [N,Cin,h,w] (the seam format, written directly by the GEMM)."""
+    ``nhwc_bf16`` a bf16 channels_last tensor of logical shape [N,Cin,h,w] (the seam format, written directly by the GEMM).
+    ``out_w``: R preallocated fp32 [C,Cin,3,3] buffers to write the weight gradients into (e.g. views of a flat DDP bucket);
+    ``weights_ready_event`` is recorded on the current stream once they are complete, before the data-gradient GEMM."""
     lib = load()
     _need(gOt, torch.bfloat16, "gOt")
     Cin = Xp.shape[1]
@@ -429,20 +435,28 @@ def aspp_backward_packed(gOt: torch.Tensor, Xp: torch.Tensor, WpT: torch.Tensor,
         splits = default_wgrad_splits(N * h * w, C, Cin, R)
     nbytes = lib.b200seg_aspp_backward_scratch_bytes(N, Cin, C, h, w, R, splits)
     scratch = _scratch("aspp_bwd", nbytes, dev)
-    gws = [torch.empty((C, Cin, 3, 3), dtype=torch.float32, device=dev) for _ in range(R)] if need_grad_w else None
+    gws = None
+    if need_grad_w:
+        if out_w is not None:
+            gws = [_need(t, torch.float32, "out_w") for t in out_w]
+            if len(gws) != R or any(tuple(t.shape) != (C, Cin, 3, 3) for t in gws):
+                raise B200SegError("out_w: expected R contiguous fp32 [C,Cin,3,3] buffers")
+        else:
+            gws = [torch.empty((C, Cin, 3, 3), dtype=torch.float32, device=dev) for _ in range(R)]
     rates_arr = (c_int * R)(*[int(r) for r in rates])
-    if nhwc_bf16 and need_grad_x:
-        gx_nhwc = torch.empty((N, h, w, Cin), dtype=torch.bfloat16, device=dev)
-        with torch.cuda.device(dev):
-            _check(lib.b200seg_aspp_backward_packed_nhwc(gOt.data_ptr(), Xp.data_ptr(), WpT.data_ptr(), rates_arr, R, N, Cin, C, h, w,
-                                                         scratch.data_ptr(), nbytes, splits, gx_nhwc.data_ptr(),
-                                                         _ptr_array(gws) if gws else None, _stream()))
-        return gx_nhwc.permute(0, 3, 1, 2), gws
-    gx = torch.empty((N, Cin, h, w), dtype=torch.float32, device=dev) if need_grad_x else None
+    gx = gx_nhwc = None
+    if need_grad_x:
+        if nhwc_bf16:
+            gx_nhwc = torch.empty((N, h, w, Cin), dtype=torch.bfloat16, device=dev)
+        else:
+            gx = torch.empty((N, Cin, h, w), dtype=torch.float32, device=dev)
+    ev = None if weights_ready_event is None else weights_ready_event.cuda_event
     with torch.cuda.device(dev):
-        _check(lib.b200seg_aspp_backward_packed(gOt.data_ptr(), Xp.data_ptr(), WpT.data_ptr(), rates_arr, R, N, Cin, C, h, w,
-                                                scratch.data_ptr(), nbytes, splits, _ptr(gx), _ptr_array(gws) if gws else None,
-                                                _stream()))
+        _check(lib.b200seg_aspp_backward_packed_ex(gOt.data_ptr(), Xp.data_ptr(), WpT.data_ptr(), rates_arr, R, N, Cin, C, h, w,
+                                                   scratch.data_ptr(), nbytes, splits, _ptr(gx), _ptr(gx_nhwc),
+                                                   _ptr_array(gws) if gws else None, ev, _stream()))
+    if gx_nhwc is not None:
+        gx = gx_nhwc.permute(0, 3, 1, 2)
     return gx, gws
 
 
@@ -474,6 +488,10 @@ PROFILE_TAGS = {"head_fwd_gemm": 0, "head_dgrad_gemm": 1, "head_wgrad_gemm": 2, 
 
 def launch_count() -> int:
     return int(load().b200seg_launch_count())
+
+
+def gemm_set_overlap_sms(n: int):
+    load().b200seg_gemm_set_overlap_sms(int(n))
 
 
 def profile_enable(on: bool):

@@ -62,9 +62,11 @@ class ASPP_Classifier_V2(nn.Module):
         return out
 
     # ---- fused extension (same result as criterion(self(x, size) / T, labels)) --------------
-    def forward_loss(self, x, labels, ignore_index: int = 255, temperature: float = 1.0):
+    def forward_loss(self, x, labels, ignore_index: int = 255, temperature: float = 1.0, grad_bucket=None):
         """loss = CrossEntropyLoss(ignore_index)(self(x, labels.shape[-2:]) / temperature, labels) with the
         upsample fused into the loss (aspp_trainer.py:88-91 / aspp_fada.py:91-95).  Returns (loss, detached low-res logits);
-        gradients flow through the loss only."""
+        gradients flow through the loss only.  ``grad_bucket``: a distributed.HeadGradBucket built over this module -- the
+        parameter gradients then land in the bucket and its mean all-reduce overlaps the data-gradient GEMM."""
         return ops.aspp_head_loss(x, labels, [m.weight for m in self.conv2d_list], [m.bias for m in self.conv2d_list],
-                                  self._rates(), ignore_index, temperature, packed=self._packed_weights())
+                                  self._rates(), ignore_index, temperature, packed=self._packed_weights(),
+                                  grad_bucket=grad_bucket)

@@ -56,7 +56,7 @@ int k2_forward(const float*, int, int, int, int, const long long*, int, int, int
 int k2_backward(const void*, int, int, int, int, int, int, float, const float*, const float*, float*, cudaStream_t);
 int k2_backward_packed(void*, int, int, int, int, int, int, float, const float*, const float*, void*, float*, cudaStream_t);
 int aspp_backward_packed(const void*, const void*, const void*, const int*, int, int, int, int, int, int, void*, long long, int, float*,
-                         float* const*, cudaStream_t, void*);
+                         float* const*, cudaStream_t, void*, cudaEvent_t);
 int upsample_fwd_launch(const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int upsample_bwd_launch(const float*, float*, int, int, int, int, int, cudaStream_t);
 long long k3_workspace_bytes();
@@ -76,6 +76,7 @@ int k5_backward(const void*, int, int, int, int, int, int, const float*, const f
 namespace gemm {
 int selftest(int, int, int, int, int, int, int, int, double*, double*);
 void set_sharing(int);
+void set_overlap_sms(int);
 }
 
 static int require_device() {
@@ -152,7 +153,7 @@ int b200seg_aspp_backward_packed(const void* gOt, const void* Xp, const void* Wp
                                  void* stream) {
   REQUIRE_DEVICE();
   return aspp_backward_packed(gOt, Xp, WpT, rates_host, R, N, Cin, C, h, w, scratch, scratch_bytes, splits, grad_x, grad_w, S(stream),
-                              nullptr);
+                              nullptr, nullptr);
 }
 
 int b200seg_aspp_backward_packed_nhwc(const void* gOt, const void* Xp, const void* WpT, const int* rates_host, int R, int N, int Cin,
@@ -160,7 +161,15 @@ int b200seg_aspp_backward_packed_nhwc(const void* gOt, const void* Xp, const voi
                                       float* const* grad_w, void* stream) {
   REQUIRE_DEVICE();
   return aspp_backward_packed(gOt, Xp, WpT, rates_host, R, N, Cin, C, h, w, scratch, scratch_bytes, splits, nullptr, grad_w, S(stream),
-                              grad_x_nhwc_bf16);
+                              grad_x_nhwc_bf16, nullptr);
+}
+
+int b200seg_aspp_backward_packed_ex(const void* gOt, const void* Xp, const void* WpT, const int* rates_host, int R, int N, int Cin,
+                                    int C, int h, int w, void* scratch, int64_t scratch_bytes, int splits, float* grad_x,
+                                    void* grad_x_nhwc_bf16, float* const* grad_w, void* weights_ready_event, void* stream) {
+  REQUIRE_DEVICE();
+  return aspp_backward_packed(gOt, Xp, WpT, rates_host, R, N, Cin, C, h, w, scratch, scratch_bytes, splits, grad_x, grad_w, S(stream),
+                              grad_x_nhwc_bf16, reinterpret_cast<cudaEvent_t>(weights_ready_event));
 }
 
 int b200seg_upsample_bilinear_forward(const float* in, float* out, int NC, int h, int w, int H, int W, int fma_mode, void* stream) {
@@ -267,6 +276,7 @@ int b200seg_profile_read(int tag, double* total_ms, int* count) {
 }
 
 void b200seg_gemm_set_sharing(int on) { gemm::set_sharing(on); }
+void b200seg_gemm_set_overlap_sms(int n) { gemm::set_overlap_sms(n); }
 
 int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b_mn_major, int splits, int col_hw, int share, double* max_err,
                           double* max_ref) {

@@ -21,6 +21,7 @@
 #include "gemm_sm100.cuh"
 
 namespace b200seg {
+namespace gemm { int overlap_sms(); }
 
 constexpr int MAX_RATES = 8;
 constexpr int MAX_TAPS = 8 * MAX_RATES + 1;
@@ -408,7 +409,7 @@ void* aspp_bwd_gOt_ptr(void* scratch) { return scratch; }
 // backward GEMMs from the packed bf16 pixel-major output gradient gOt [P][32]
 int aspp_backward_packed(const void* gOt_in, const void* Xp, const void* WpT, const int* rates, int R, int N, int Cin, int C,
                          int h, int w, void* scratch, long long scratch_bytes, int splits, float* grad_x, float* const* grad_w,
-                         cudaStream_t stream, void* grad_x_nhwc_bf16) {
+                         cudaStream_t stream, void* grad_x_nhwc_bf16, cudaEvent_t weights_ready) {
   B200SEG_CHECK_ARG(gOt_in && Xp && WpT && rates && scratch, "aspp_backward: null pointer");
   B200SEG_CHECK_ARG(R >= 1 && R <= MAX_RATES, "aspp: %d dilation branches unsupported", R);
   B200SEG_CHECK_ARG(C <= 32, "aspp_backward: num_classes=%d > 32 is not supported", C);
@@ -439,22 +440,6 @@ int aspp_backward_packed(const void* gOt_in, const void* Xp, const void* WpT, co
     profile_end(5, stream);
     B200SEG_LAUNCH_CHECK();
   }
-  if (grad_x) {
-    // dX[ci, p] = WpT[ci, :] . G't[:, p]   -> fp32 NCHW: column p = (image, pixel), row = channel
-    gemm::Operand a{(const __nv_bfloat16*)WpT, false, NJ};
-    gemm::Operand b{Gp, true, Ppitch};
-    int rc = gemm::launch(a, b, Cin, (int)P, NJ, 1, grad_x, hw, hw, (long long)Cin * hw, 0, stream, nullptr, 1, gemm::SHARE_B);
-    if (rc) return rc;
-  }
-  if (grad_x_nhwc_bf16) {
-    // seam format: dXt[p, ci] = G't[:, p] . WpT[ci, :]  written as bf16 pixel-major [P][Cin] (= channels_last NHWC),
-    // half the bytes of the fp32 NCHW gradient, so the GEMM is MMA-bound instead of store-bound
-    gemm::Operand a{Gp, true, Ppitch};
-    gemm::Operand b{(const __nv_bfloat16*)WpT, false, NJ};
-    int rc = gemm::launch(a, b, (int)P, Cin, NJ, 1, reinterpret_cast<float*>(grad_x_nhwc_bf16), Cin, 0, 0, 0, stream, nullptr, 1,
-                          gemm::SHARE_B, true);
-    if (rc) return rc;
-  }
   if (grad_w) {
     MutPtrList gw;
     bool any = false;
@@ -473,6 +458,26 @@ int aspp_backward_packed(const void* gOt_in, const void* Xp, const void* WpT, co
       profile_end(10, stream);
       B200SEG_LAUNCH_CHECK();
     }
+  }
+  // the weight gradients are complete here: a caller that all-reduces them on another stream can start while the
+  // data-gradient GEMM below is still running
+  if (weights_ready) B200SEG_CUDA(cudaEventRecord(weights_ready, stream));
+  if (grad_x) {
+    // dX[ci, p] = WpT[ci, :] . G't[:, p]   -> fp32 NCHW: column p = (image, pixel), row = channel
+    gemm::Operand a{(const __nv_bfloat16*)WpT, false, NJ};
+    gemm::Operand b{Gp, true, Ppitch};
+    int rc = gemm::launch(a, b, Cin, (int)P, NJ, 1, grad_x, hw, hw, (long long)Cin * hw, 0, stream, nullptr, 1, gemm::SHARE_B, false,
+                          weights_ready ? gemm::overlap_sms() : 0);
+    if (rc) return rc;
+  }
+  if (grad_x_nhwc_bf16) {
+    // seam format: dXt[p, ci] = G't[:, p] . WpT[ci, :]  written as bf16 pixel-major [P][Cin] (= channels_last NHWC),
+    // half the bytes of the fp32 NCHW gradient, so the GEMM is MMA-bound instead of store-bound
+    gemm::Operand a{Gp, true, Ppitch};
+    gemm::Operand b{(const __nv_bfloat16*)WpT, false, NJ};
+    int rc = gemm::launch(a, b, (int)P, Cin, NJ, 1, reinterpret_cast<float*>(grad_x_nhwc_bf16), Cin, 0, 0, 0, stream, nullptr, 1,
+                          gemm::SHARE_B, true, weights_ready ? gemm::overlap_sms() : 0);
+    if (rc) return rc;
   }
   return B200SEG_OK;
 }
@@ -500,7 +505,7 @@ int aspp_backward(const float* grad_logits, const void* Xp, const void* WpT, con
       B200SEG_LAUNCH_CHECK();
     }
   }
-  return aspp_backward_packed(gOt, Xp, WpT, rates, R, N, Cin, C, h, w, scratch, scratch_bytes, splits, grad_x, grad_w, stream, nullptr);
+  return aspp_backward_packed(gOt, Xp, WpT, rates, R, N, Cin, C, h, w, scratch, scratch_bytes, splits, grad_x, grad_w, stream, nullptr, nullptr);
 }
 
 }  // namespace b200seg

@@ -47,6 +47,9 @@ static int make_tmap(CUtensorMap* m, const __nv_bfloat16* ptr, long long inner, 
   return B200SEG_OK;
 }
 
+static int g_overlap_sms = 8;         // b200seg_gemm_set_overlap_sms(): SMs left free while an all-reduce overlaps the dgrad GEMM
+void set_overlap_sms(int n) { g_overlap_sms = n < 0 ? 0 : n; }
+int overlap_sms() { return g_overlap_sms; }
 static int g_share_enabled = 1;      // b200seg_gemm_set_sharing(): 0 disables the 2-CTA multicast variants (A/B testing)
 void set_sharing(int on) { g_share_enabled = on; }
 
@@ -87,7 +90,7 @@ static int launch_s(const CUtensorMap& ta, const CUtensorMap& tb, const Params& 
 
 int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, float* out, long long row_stride,
            int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used, int prof_tag,
-           int share, bool out_bf16) {
+           int share, bool out_bf16, int sm_reserve) {
   B200SEG_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem %dx%dx%d", M, N, K);
   B200SEG_CHECK_ARG(!out_bf16 || (col_hw <= 0 && N % 8 == 0 && row_stride % 8 == 0 && split_stride % 8 == 0 &&
                                   (reinterpret_cast<uintptr_t>(out) & 15) == 0),
@@ -127,15 +130,19 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
   else rc = make_tmap(&tb, b.ptr, N, K, b.pitch, 64, BLOCK_K);
   if (rc) return rc;
 
+  // persistent CTAs, one per SM, minus the SMs the caller wants left free for a concurrent kernel (the NCCL all-reduce
+  // of the weight gradients running underneath the data-gradient GEMM)
+  int sms = num_sms() - (sm_reserve > 0 ? sm_reserve : 0);
+  if (sms < 2) sms = 2;
   int grid;
   if (share == SHARE_NONE) {
     const int units = p.m_tiles * p.n_tiles * p.splits;
-    grid = units < num_sms() ? units : num_sms();
+    grid = units < sms ? units : sms;
   } else {
     const int mt = share == SHARE_B ? (p.m_tiles + 1) / 2 : p.m_tiles;
     const int nt = share == SHARE_A ? (p.n_tiles + 1) / 2 : p.n_tiles;
     const int units = mt * nt * p.splits;
-    const int clusters = units < num_sms() / 2 ? units : num_sms() / 2;
+    const int clusters = units < sms / 2 ? units : sms / 2;
     grid = 2 * clusters;
   }
   profile_begin(prof_tag, stream);

@@ -460,7 +460,7 @@ struct Operand {
 };
 int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, float* out, long long row_stride,
            int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used, int prof_tag = -1,
-           int share = SHARE_NONE, bool out_bf16 = false);
+           int share = SHARE_NONE, bool out_bf16 = false, int sm_reserve = 0);
 
 }  // namespace gemm
 }  // namespace b200seg

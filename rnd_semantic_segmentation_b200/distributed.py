@@ -80,6 +80,67 @@ class FlatGradBucket:
         return self.flat
 
 
+class HeadGradBucket(FlatGradBucket):
+    """Flat gradient bucket of an ASPP_Classifier_V2 whose all-reduce OVERLAPS the head's data-gradient GEMM.
+
+    ``head.forward_loss(x, labels, grad_bucket=bucket)`` makes the backward write the weight gradients straight into the
+    bucket (no concatenation pass), record ``ready_event`` right after the weight-gradient GEMM, and call
+    ``begin_allreduce_()``, which runs the MEAN all-reduce on the bucket's own stream while the compute stream goes on
+    with the data-gradient GEMM.  ``wait()`` joins the two streams before the optimizer (or anything else) reads .grad.
+    Gradients are overwritten each step, not accumulated (zero_grad-every-step semantics of the reference trainers)."""
+
+    def __init__(self, head: torch.nn.Module, group=None, overlap_ctas: int = 8):
+        convs = list(head.conv2d_list)
+        # bucket order: the R weights, then the R biases as one [R, C] block
+        super().__init__([m.weight for m in convs] + [m.bias for m in convs])
+        self.R = len(convs)
+        # The persistent dgrad GEMM fills every SM's shared memory, so nothing else can be resident beside it: it leaves
+        # `overlap_ctas` SMs free, and the all-reduce runs on a dedicated NCCL communicator capped at that many CTAs.
+        if group is None and is_distributed() and dist.get_backend() == "nccl" and overlap_ctas > 0:
+            try:
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = int(overlap_ctas)
+                opts.config.min_ctas = 1
+                group = dist.new_group(backend="nccl", pg_options=opts)
+            except Exception:                        # older torch / NCCL without per-communicator CTA limits
+                group = None
+        if overlap_ctas > 0 and self.flat.is_cuda:
+            from . import _lib
+            _lib.gemm_set_overlap_sms(overlap_ctas)
+        self.group = group
+        self.stream = torch.cuda.Stream(device=self.flat.device)
+        self.ready_event = torch.cuda.Event()
+        self.ready_event.record()                    # materialise the CUDA event: its handle is passed through the C ABI
+        self._pending = False
+        nb = sum(m.bias.numel() for m in convs)
+        self._bias_block = self.flat[self.flat.numel() - nb:].view(self.R, -1)
+
+    def weight_buffers(self):
+        return self.views[:self.R]
+
+    def set_bias_grads_(self, bias_grad: torch.Tensor):
+        self._bias_block.copy_(bias_grad.unsqueeze(0).expand_as(self._bias_block))     # d/d b_r is the same for every branch
+
+    def begin_allreduce_(self):
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+        if not is_distributed():
+            return
+        self.stream.wait_event(self.ready_event)     # weight gradients (and the bias block enqueued before them) are complete
+        with torch.cuda.stream(self.stream):
+            if dist.get_backend(self.group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat.div_(dist.get_world_size(self.group))
+        self._pending = True
+
+    def wait(self):
+        if self._pending:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self._pending = False
+
+
 def allreduce_mean_grads_(module: torch.nn.Module, group=None, bucket: Optional[FlatGradBucket] = None) -> FlatGradBucket:
     bucket = bucket or FlatGradBucket(module.parameters())
     bucket.allreduce_mean_(group)

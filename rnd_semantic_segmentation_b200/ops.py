@@ -71,8 +71,9 @@ class _AsppHeadLossFn(torch.autograd.Function):
     wgrad with the low-res gradient handed over as packed bf16 (no fp32 NCHW gradient, no transposes)."""
 
     @staticmethod
-    def forward(ctx, x, labels, ignore_index, temperature, rates, packed, *params):
+    def forward(ctx, x, labels, ignore_index, temperature, rates, packed, grad_bucket, *params):
         R = len(rates)
+        ctx.grad_bucket = grad_bucket
         weights, biases = params[:R], params[R:]
         N, Cin, h, w = x.shape
         C = weights[0].shape[0]
@@ -98,27 +99,41 @@ class _AsppHeadLossFn(torch.autograd.Function):
             raise _lib.B200SegError("forward_loss: forward ran without gradient tracking")
         R = len(rates)
         need = ctx.needs_input_grad
-        need_w = any(need[6:6 + R])
-        need_b = any(need[6 + R:6 + 2 * R])
+        need_w = any(need[7:7 + R])
+        need_b = any(need[7 + R:7 + 2 * R])
         if grad_loss is None:
-            return (None,) * (6 + 2 * R)
+            return (None,) * (7 + 2 * R)
         gOt, bias = _lib.upsample_ce_backward_packed(ws, out2, (N, C, h, w), size, inv_t, grad_loss.detach().float(), need_b)
         # bf16 features (the channels_last seam format): the dgrad GEMM writes the bf16 NHWC gradient itself
         seam = x_dtype == torch.bfloat16 and Cin % 8 == 0
+        bucket = ctx.grad_bucket
+        if bucket is not None and need_w and need_b:
+            # data-parallel path: the weight / bias gradients are written straight into the flat bucket (the parameters'
+            # .grad alias it), and the bucket's all-reduce starts on its own stream as soon as they are complete --
+            # underneath the data-gradient GEMM.  Autograd gets no parameter gradients from this node.
+            bucket.set_bias_grads_(bias)              # enqueued before the GEMMs, so ready_event covers it too
+            gx, _ = _lib.aspp_backward_packed(gOt, Xp, WpT, rates, N, h, w, C, need[0], True, nhwc_bf16=seam,
+                                              out_w=bucket.weight_buffers(), weights_ready_event=bucket.ready_event)
+            bucket.begin_allreduce_()
+            if gx is not None and gx.dtype != x_dtype:
+                gx = gx.to(x_dtype)
+            return (gx,) + (None,) * (6 + 2 * R)
         gx, gws = _lib.aspp_backward_packed(gOt, Xp, WpT, rates, N, h, w, C, need[0], need_w, nhwc_bf16=seam)
         if gx is not None and gx.dtype != x_dtype:
             gx = gx.to(x_dtype)
-        out_w = [gws[r] if (gws is not None and need[6 + r]) else None for r in range(R)]
-        out_b = [(bias if r == 0 else bias.clone()) if (bias is not None and need[6 + R + r]) else None for r in range(R)]
-        return (gx, None, None, None, None, None, *out_w, *out_b)
+        out_w = [gws[r] if (gws is not None and need[7 + r]) else None for r in range(R)]
+        out_b = [(bias if r == 0 else bias.clone()) if (bias is not None and need[7 + R + r]) else None for r in range(R)]
+        return (gx, None, None, None, None, None, None, *out_w, *out_b)
 
 
-def aspp_head_loss(x, labels, weights, biases, rates, ignore_index=255, temperature=1.0, packed=None):
-    """(loss, low-res logits [detached]) == CrossEntropyLoss(ignore_index)(interpolate(head(x), labels.shape[-2:]) / T, labels)."""
+def aspp_head_loss(x, labels, weights, biases, rates, ignore_index=255, temperature=1.0, packed=None, grad_bucket=None):
+    """(loss, low-res logits [detached]) == CrossEntropyLoss(ignore_index)(interpolate(head(x), labels.shape[-2:]) / T, labels).
+    ``grad_bucket`` (distributed.HeadGradBucket): write the parameter gradients into the bucket and overlap its all-reduce
+    with the data-gradient GEMM instead of returning them through autograd."""
     if labels.dtype != torch.int64:
         labels = labels.long()
     return _AsppHeadLossFn.apply(x, labels, int(ignore_index), float(temperature), tuple(int(r) for r in rates), packed,
-                                 *weights, *biases)
+                                 grad_bucket, *weights, *biases)
 
 
 # --------------------------------------------------------------------------------------------

@@ -264,6 +264,33 @@ def test_seam_format_bf16_channels_last(lib, n, cin, C, h, w, H, W):
         assert rel_err(p.grad, wgrad) <= 1e-6
 
 
+def test_head_grad_bucket_matches_autograd(lib):
+    """distributed.HeadGradBucket: gradients written straight into the flat bucket (and all-reduced from a side stream when
+    a process group exists) are bit-identical to the ones autograd returns without a bucket."""
+    from rnd_semantic_segmentation_b200 import ASPP_Classifier_V2, distributed as D
+    torch.manual_seed(9)
+    head = ASPP_Classifier_V2(256, RATES, RATES, 19).cuda()
+    g = torch.Generator().manual_seed(10)
+    x = torch.relu(torch.randn(2, 256, 16, 32, generator=g)).cuda()
+    labels = make_labels(2, 128, 256, 19, 0.1, 11).cuda()
+    xa = x.clone().requires_grad_(True)
+    la, _ = head.forward_loss(xa, labels)
+    la.backward()
+    want = {k: p.grad.clone() for k, p in head.named_parameters()}
+    for p in head.parameters():
+        p.grad = None
+    bucket = D.HeadGradBucket(head)
+    for step in range(2):                                  # second step: gradients are overwritten, not accumulated
+        xb = x.clone().requires_grad_(True)
+        lb, _ = head.forward_loss(xb, labels, grad_bucket=bucket)
+        lb.backward()
+        bucket.wait()
+        assert torch.equal(xb.grad, xa.grad)
+        for k, p in head.named_parameters():
+            assert p.grad is not None and torch.equal(p.grad, want[k]), k
+            assert p.grad.data_ptr() >= bucket.flat.data_ptr() and p.grad.data_ptr() < bucket.flat.data_ptr() + bucket.flat.numel() * 4
+
+
 @pytest.mark.parametrize("name", ["head_c19", "head_c2", "head_c19_T18"])
 def test_k1_k2_against_reference_golden(lib, golden, name):
     """End to end (head -> fused upsample+CE -> backward) against fixtures produced by the reference's own code.
