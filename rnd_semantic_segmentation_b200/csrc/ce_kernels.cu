@@ -119,7 +119,7 @@ __host__ __device__ constexpr int k2_ns(int CT) { return (CT * K2_SPAN + 31) / 3
 struct K2Smem {
   int stage0, stage1, blk, wt, red_lo, red_n, colw0, colw1, colx0, colx1, red, raw, ring, total;
 };
-__host__ __device__ inline K2Smem k2_smem_layout(int CT, int C, int ispan, int jspan, int kmax) {
+__host__ __device__ inline K2Smem k2_smem_layout(int CT, int C, int ispan, int jspan, int kmax, int nwarps) {
   K2Smem L;
   int o = 0;
   L.stage0 = o; o += k2_np(CT) * K2_PITCH2 * 8;
@@ -132,22 +132,21 @@ __host__ __device__ inline K2Smem k2_smem_layout(int CT, int C, int ispan, int j
   L.colw1 = o; o += K2_THREADS * 4;
   L.colx0 = o; o += K2_THREADS * 4;
   L.colx1 = o; o += K2_THREADS * 4;
-  L.red = o; o += 8 * 4;
+  L.red = o; o += 2 * 8 * 4;
   o = (o + 15) / 16 * 16;
-  L.raw = o; o += (K2_THREADS / 32) * 2 * CT * K2_SPAN * 4;        // [warps][2 rows][CT][SPAN] raw logit windows
+  L.raw = o; o += nwarps * 2 * CT * K2_SPAN * 4;                   // [warps][2 rows][CT][SPAN] raw logit windows
   o = (o + 15) / 16 * 16;
   L.ring = o; o += K2_TILE_H * K2_THREADS * 8;                     // [TILE_H][128] int64 labels
   L.total = o;
   return L;
 }
 
-// Load source row `rb` (frame base + row * w) into the register array `dst` (class pairs, horizontally interpolated
-// and scaled by 1/T) and leave its raw CT x K2_SPAN window in this warp's stage `raw_s` (staged path only).
-template <int CT, bool EXACT>
-__device__ __forceinline__ void k2_row_load(float2 (&dst)[(CT + 1) / 2], const float* __restrict__ rb, int C, long long hw, bool staged,
+// Load source row `rb` (frame base + row * w): leave its raw CT x K2_SPAN window in this warp's stage `raw_s` (staged
+// path) and fill `dst` with this thread's class pairs [pbase, pbase + NPH), horizontally interpolated and scaled by 1/T.
+template <int CT, int NPH, bool EXACT>
+__device__ __forceinline__ void k2_row_load(float2 (&dst)[NPH], int pbase, const float* __restrict__ rb, int C, long long hw, bool staged,
                                             unsigned raw_s, int wj_lo, int w, unsigned t0_off, unsigned t1_off, int i0, int i1,
                                             float w0, float w1) {
-  constexpr int NP = (CT + 1) / 2;
   constexpr int NS = (CT * K2_SPAN + 31) / 32;
   const float2 L0 = make_float2(w0, w0), L1 = make_float2(w1, w1);
   if (staged) {
@@ -164,31 +163,33 @@ __device__ __forceinline__ void k2_row_load(float2 (&dst)[(CT + 1) / 2], const f
     for (int q = 0; q < NS; ++q)
       if (q * 32 + lane < CT * K2_SPAN) sts_f32(raw_s + (q * 32 + lane) * 4, v[q]);
     __syncwarp();
+    const unsigned base0 = raw_s + t0_off + (unsigned)(2 * pbase) * (K2_SPAN * 4);
+    const unsigned base1 = raw_s + t1_off + (unsigned)(2 * pbase) * (K2_SPAN * 4);
 #pragma unroll
-    for (int i = 0; i < NP; ++i) {
+    for (int i = 0; i < NPH; ++i) {
+      const int c0 = 2 * (pbase + i), c1 = c0 + 1;
       float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
-      if (EXACT || 2 * i < C) { a.x = lds_f32(raw_s + t0_off + (2 * i) * K2_SPAN * 4); b.x = lds_f32(raw_s + t1_off + (2 * i) * K2_SPAN * 4); }
-      if (2 * i + 1 < CT && (EXACT || 2 * i + 1 < C)) {
-        a.y = lds_f32(raw_s + t0_off + (2 * i + 1) * K2_SPAN * 4); b.y = lds_f32(raw_s + t1_off + (2 * i + 1) * K2_SPAN * 4);
-      }
+      if (c0 < C) { a.x = lds_f32(base0 + (2 * i) * K2_SPAN * 4); b.x = lds_f32(base1 + (2 * i) * K2_SPAN * 4); }
+      if (c1 < C) { a.y = lds_f32(base0 + (2 * i + 1) * K2_SPAN * 4); b.y = lds_f32(base1 + (2 * i + 1) * K2_SPAN * 4); }
       dst[i] = fma2(L0, a, mul2(L1, b));
-      if (!(EXACT || 2 * i < C)) dst[i].x = K2_PAD;
-      if (!(2 * i + 1 < CT && (EXACT || 2 * i + 1 < C))) dst[i].y = K2_PAD;
+      if (c0 >= C) dst[i].x = K2_PAD;
+      if (c1 >= C) dst[i].y = K2_PAD;
     }
   } else {
-    const char* p0 = reinterpret_cast<const char*>(rb + i0);
-    const char* p1 = reinterpret_cast<const char*>(rb + i1);
     const long long step = hw * 4;
+    const char* p0 = reinterpret_cast<const char*>(rb + i0) + step * (2 * pbase);
+    const char* p1 = reinterpret_cast<const char*>(rb + i1) + step * (2 * pbase);
 #pragma unroll
-    for (int i = 0; i < NP; ++i) {
+    for (int i = 0; i < NPH; ++i) {
+      const int c0 = 2 * (pbase + i), c1 = c0 + 1;
       float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
-      if (EXACT || 2 * i < C) { a.x = __ldg(reinterpret_cast<const float*>(p0)); b.x = __ldg(reinterpret_cast<const float*>(p1)); }
+      if (c0 < C) { a.x = __ldg(reinterpret_cast<const float*>(p0)); b.x = __ldg(reinterpret_cast<const float*>(p1)); }
       p0 += step; p1 += step;
-      if (2 * i + 1 < CT && (EXACT || 2 * i + 1 < C)) { a.y = __ldg(reinterpret_cast<const float*>(p0)); b.y = __ldg(reinterpret_cast<const float*>(p1)); }
+      if (c1 < C) { a.y = __ldg(reinterpret_cast<const float*>(p0)); b.y = __ldg(reinterpret_cast<const float*>(p1)); }
       p0 += step; p1 += step;
       dst[i] = fma2(L0, a, mul2(L1, b));
-      if (!(EXACT || 2 * i < C)) dst[i].x = K2_PAD;
-      if (!(2 * i + 1 < CT && (EXACT || 2 * i + 1 < C))) dst[i].y = K2_PAD;
+      if (c0 >= C) dst[i].x = K2_PAD;
+      if (c1 >= C) dst[i].y = K2_PAD;
     }
   }
 }
@@ -206,17 +207,28 @@ __device__ __forceinline__ float k2_sum(const float (&p)[N]) {      // pairwise 
   return t[0].x + t[0].y;
 }
 
-template <int CT, bool GRAD, bool EXACT>
-__global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Params p) {
+// SPLIT threads share one output column: thread `half` of a column owns class pairs [half * NPH, (half + 1) * NPH), the
+// per-pixel max and sum are exchanged with one shuffle each.  SPLIT = 2 halves the register arrays (a0, a1, acc0, acc1),
+// which is what bounds the resident warps of this latency-bound kernel; used for the larger class counts.
+#ifndef K2_SPLIT_MINB
+#define K2_SPLIT_MINB 2
+#endif
+template <int CT, bool GRAD, bool EXACT, int SPLIT>
+__global__ void __launch_bounds__(K2_THREADS * SPLIT, SPLIT == 1 ? 3 : K2_SPLIT_MINB) k2_upsample_ce_main(const K2Params p) {
   constexpr int NP = (CT + 1) / 2;
+  constexpr int NPH = (NP + SPLIT - 1) / SPLIT;
+  constexpr int NT = K2_THREADS * SPLIT;
+  constexpr int NWARPS = NT / 32;
   constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   extern __shared__ __align__(16) uint8_t k2_smem_raw[];
   const K2Geom& g = p.g;
   const int C = EXACT ? CT : g.C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int col = tid / SPLIT, half = tid - col * SPLIT;
+  const int pbase = half * NPH;
   // shared-memory regions are re-derived from the layout where they are used (setup / flush) instead of being kept
   // as live generic pointers across the row loop
-#define K2_L k2_smem_layout(CT, C, g.ispan_max, g.jspan_max, g.kmax)
+#define K2_L k2_smem_layout(CT, C, g.ispan_max, g.jspan_max, g.kmax, NWARPS)
 #define K2_STAGE0 reinterpret_cast<float2*>(k2_smem_raw + K2_L.stage0)   /* [NP][129] per-column sums toward a0's source row */
 #define K2_STAGE1 reinterpret_cast<float2*>(k2_smem_raw + K2_L.stage1)   /* ... toward a1's source row (start as -onehot sums) */
 #define K2_BLK reinterpret_cast<float*>(k2_smem_raw + K2_L.blk)          /* [ispan_max][jspan_max][C] */
@@ -228,8 +240,8 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
   const unsigned smem_s = smem_u32(k2_smem_raw);
   const unsigned rawA_s = smem_s + L.raw + (warp * 2 + 0) * CT * K2_SPAN * 4;   // raw window of a0's source row
   const unsigned rawB_s = smem_s + L.raw + (warp * 2 + 1) * CT * K2_SPAN * 4;   // ... of a1's
-  const unsigned ring_s = smem_s + L.ring + tid * 8;                            // this thread's label column, row stride 1 KB
-  const unsigned st0_s = smem_s + L.stage0 + tid * 8, st1_s = smem_s + L.stage1 + tid * 8;
+  const unsigned ring_s = smem_s + L.ring + col * 8;                            // this column's labels, row stride 1 KB
+  const unsigned st0_s = smem_s + L.stage0 + col * 8, st1_s = smem_s + L.stage1 + col * 8;
 
   const int tile = blockIdx.x;
   const int tiles_per_frame = g.tiles_x * g.tiles_y;
@@ -239,7 +251,7 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
   const int tx = trem - ty * g.tiles_x;
   const long long hw = (long long)g.h * g.w;
 
-  const int x = tx * K2_TILE_W + tid;
+  const int x = tx * K2_TILE_W + col;
   const bool xvalid = x < g.W;
   const Tap tapx = ac_tap(g.scale_w, xvalid ? x : g.W - 1, g.w);
   const int j_lo = (int)(g.scale_w * (float)(tx * K2_TILE_W));
@@ -248,7 +260,7 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
   const int i_lo = (int)(g.scale_h * (float)y_begin);
   const int jspan = g.jspan_max;
 
-  // labels of the whole tile go in flight first: one commit group per K2_STRIP rows
+  // labels of the whole tile go in flight first: one commit group per K2_STRIP rows (issued by thread 0 of each column)
   {
     const char* src = reinterpret_cast<const char*>(p.labels + (long long)n * g.H * g.W + (long long)y_begin * g.W + (xvalid ? x : 0));
     const long long row_bytes = (long long)g.W * 8;
@@ -257,7 +269,7 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
 #pragma unroll
       for (int r = 0; r < K2_STRIP; ++r) {
         const int yy = y_begin + st * K2_STRIP + r;
-        if (xvalid && yy < y_end) cp_async_8s(ring_s + (st * K2_STRIP + r) * (K2_THREADS * 8), src);
+        if (half == 0 && xvalid && yy < y_end) cp_async_8s(ring_s + (st * K2_STRIP + r) * (K2_THREADS * 8), src);
         src += row_bytes;
       }
       cp_async_commit();
@@ -274,20 +286,22 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
     float* colw1 = reinterpret_cast<float*>(k2_smem_raw + L.colw1);
     int* colx0 = reinterpret_cast<int*>(k2_smem_raw + L.colx0);
     int* colx1 = reinterpret_cast<int*>(k2_smem_raw + L.colx1);
-    for (int i = tid; i < blk_floats; i += K2_THREADS) blk[i] = 0.f;
-    for (int i = tid; i < 2 * NP * K2_PITCH2; i += K2_THREADS) stage0[i] = make_float2(0.f, 0.f);   // stage0 and stage1 are adjacent
-    colw0[tid] = xvalid ? tapx.l0 : 0.f;
-    colw1[tid] = xvalid ? tapx.l1 : 0.f;
-    colx0[tid] = tapx.i0 - j_lo;
-    colx1[tid] = tapx.i1 - j_lo;
+    for (int i = tid; i < blk_floats; i += NT) blk[i] = 0.f;
+    for (int i = tid; i < 2 * NP * K2_PITCH2; i += NT) stage0[i] = make_float2(0.f, 0.f);   // stage0 and stage1 are adjacent
+    if (half == 0) {
+      colw0[col] = xvalid ? tapx.l0 : 0.f;
+      colw1[col] = xvalid ? tapx.l1 : 0.f;
+      colx0[col] = tapx.i0 - j_lo;
+      colx1[col] = tapx.i1 - j_lo;
+    }
     __syncthreads();
     if (tid < jspan) {                               // reduce table of source column jj = tid
       const int jj = tid;
       int lo = 0, hi = K2_THREADS;
       while (lo < hi) { const int mid = (lo + hi) >> 1; if (colx0[mid] < jj - 1) lo = mid + 1; else hi = mid; }
       int k = 0;
-      for (int col = lo; col < K2_THREADS && colx0[col] <= jj && k < g.kmax; ++col, ++k)
-        wt[jj * g.kmax + k] = (colx0[col] == jj ? colw0[col] : 0.f) + (colx1[col] == jj ? colw1[col] : 0.f);
+      for (int cc = lo; cc < K2_THREADS && colx0[cc] <= jj && k < g.kmax; ++cc, ++k)
+        wt[jj * g.kmax + k] = (colx0[cc] == jj ? colw0[cc] : 0.f) + (colx1[cc] == jj ? colw1[cc] : 0.f);
       red_lo[jj] = lo;
       red_n[jj] = k;
     }
@@ -303,11 +317,11 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
   const unsigned t0_off = (unsigned)(tapx.i0 - wj_lo) * 4, t1_off = (unsigned)(tapx.i1 - wj_lo) * 4;
   const float wx0 = p.inv_T * tapx.l0, wx1 = p.inv_T * tapx.l1;
 
-  float2 a0[NP], a1[NP];
-  float2 acc0[GRAD ? NP : 1], acc1[GRAD ? NP : 1];     // d loss / d a0-row, d loss / d a1-row (softmax part)
+  float2 a0[NPH], a1[NPH];
+  float2 acc0[GRAD ? NPH : 1], acc1[GRAD ? NPH : 1];     // d loss / d a0-row, d loss / d a1-row (softmax part)
   if constexpr (GRAD) {
 #pragma unroll
-    for (int i = 0; i < NP; ++i) { acc0[i] = make_float2(0.f, 0.f); acc1[i] = make_float2(0.f, 0.f); }
+    for (int i = 0; i < NPH; ++i) { acc0[i] = make_float2(0.f, 0.f); acc1[i] = make_float2(0.f, 0.f); }
   }
   int row0 = -1, row1 = -1;         // source rows held in a0 / a1
   bool swap = false;                // true: a1 is the upper row
@@ -324,14 +338,15 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
       const int* red_lo = K2_RED_LO;
       const int* red_n = K2_RED_N;
 #pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        stage0[i * K2_PITCH2 + tid] = add2(stage0[i * K2_PITCH2 + tid], acc0[i]);
-        stage1[i * K2_PITCH2 + tid] = add2(stage1[i * K2_PITCH2 + tid], acc1[i]);
-        acc0[i] = make_float2(0.f, 0.f); acc1[i] = make_float2(0.f, 0.f);
-      }
+      for (int i = 0; i < NPH; ++i)
+        if (pbase + i < NP) {
+          stage0[(pbase + i) * K2_PITCH2 + col] = add2(stage0[(pbase + i) * K2_PITCH2 + col], acc0[i]);
+          stage1[(pbase + i) * K2_PITCH2 + col] = add2(stage1[(pbase + i) * K2_PITCH2 + col], acc1[i]);
+          acc0[i] = make_float2(0.f, 0.f); acc1[i] = make_float2(0.f, 0.f);
+        }
       __syncthreads();
       const int r0 = row0 - i_lo, r1 = row1 - i_lo;
-      for (int o = tid; o < NP * jspan; o += K2_THREADS) {
+      for (int o = tid; o < NP * jspan; o += NT) {
         const int jj = o / NP;
         const int i = o - jj * NP;
         const int lo = red_lo[jj], cnt = red_n[jj];
@@ -352,10 +367,11 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
       }
       __syncthreads();
 #pragma unroll
-      for (int i = 0; i < NP; ++i) {
-        stage0[i * K2_PITCH2 + tid] = make_float2(0.f, 0.f);
-        stage1[i * K2_PITCH2 + tid] = make_float2(0.f, 0.f);
-      }
+      for (int i = 0; i < NPH; ++i)
+        if (pbase + i < NP) {
+          stage0[(pbase + i) * K2_PITCH2 + col] = make_float2(0.f, 0.f);
+          stage1[(pbase + i) * K2_PITCH2 + col] = make_float2(0.f, 0.f);
+        }
     }
   };
 
@@ -371,6 +387,7 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
       else if (pending == 2) cp_async_wait<2>();
       else if (pending == 1) cp_async_wait<1>();
       else cp_async_wait<0>();
+      if (SPLIT > 1) __syncwarp();                           // the copies were issued by the column's thread 0
     }
     const Tap tapy = ac_tap(g.scale_h, y, g.h);              // CTA-uniform
     const int top = swap ? row1 : row0, bot = swap ? row0 : row1;
@@ -387,24 +404,27 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
         const bool into_a0 = (which == 0) != swap;
         if ((into_a0 ? row0 : row1) == row) continue;
         const float* rb = lg + (long long)row * g.w;
-        if (into_a0) { k2_row_load<CT, EXACT>(a0, rb, C, hw, staged, rawA_s, wj_lo, g.w, t0_off, t1_off, tapx.i0, tapx.i1, wx0, wx1); row0 = row; }
-        else         { k2_row_load<CT, EXACT>(a1, rb, C, hw, staged, rawB_s, wj_lo, g.w, t0_off, t1_off, tapx.i0, tapx.i1, wx0, wx1); row1 = row; }
+        if (into_a0) { k2_row_load<CT, NPH, EXACT>(a0, pbase, rb, C, hw, staged, rawA_s, wj_lo, g.w, t0_off, t1_off, tapx.i0, tapx.i1, wx0, wx1); row0 = row; }
+        else         { k2_row_load<CT, NPH, EXACT>(a1, pbase, rb, C, hw, staged, rawB_s, wj_lo, g.w, t0_off, t1_off, tapx.i0, tapx.i1, wx0, wx1); row1 = row; }
       }
     }
     const uint2 gl = lds_v2u32(ring_s + yr * (K2_THREADS * 8));     // int64 label as {lo, hi}
     const bool valid = (gl.y == 0u) && (gl.x < c_lim) && (gl.x != ign32);
+    // lanes of the warp that take the branch (both threads of a column always do together): the mask of the shuffles
+    const unsigned vmask = SPLIT > 1 ? __ballot_sync(0xffffffffu, valid) : 0u;
     if (valid) {
       const int gi = (int)gl.x;
       const float w0 = swap ? tapy.l1 : tapy.l0;             // weight of a0's row, of a1's row
       const float w1 = swap ? tapy.l0 : tapy.l1;
       const float2 W0 = make_float2(w0, w0), W1 = make_float2(w1, w1);
-      float f[2 * NP];
+      float f[2 * NPH];
 #pragma unroll
-      for (int i = 0; i < NP; ++i) {
+      for (int i = 0; i < NPH; ++i) {
         const float2 v = fma2(W0, a0[i], mul2(W1, a1[i]));
         f[2 * i] = v.x; f[2 * i + 1] = v.y;
       }
-      const float m = tree_max3<0, 2 * NP, 2 * NP>(f);
+      float m = tree_max3<0, 2 * NPH, 2 * NPH>(f);
+      if (SPLIT > 1) m = fmaxf(m, __shfl_xor_sync(vmask, m, 1));
       // logit of the labelled class from the staged raw windows (or re-interpolated from global on the fallback path)
       float vA, vB;
       if (staged) {
@@ -421,27 +441,32 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
       const float mneg = -m * LOG2E;
       const float2 K = make_float2(LOG2E, LOG2E), M = make_float2(mneg, mneg);
 #pragma unroll
-      for (int i = 0; i < NP; ++i) {
+      for (int i = 0; i < NPH; ++i) {
         const float2 arg = fma2(make_float2(f[2 * i], f[2 * i + 1]), K, M);
         f[2 * i] = fast_exp2(arg.x); f[2 * i + 1] = fast_exp2(arg.y);
       }
-      const float s = k2_sum<2 * NP>(f);
-      loss_acc += fmaf(__log2f(s), LN2, m) - vlab;
-      cnt_acc += 1.f;
+      float s = k2_sum<2 * NPH>(f);
+      if (SPLIT > 1) s += __shfl_xor_sync(vmask, s, 1);
+      if (half == 0) {                                       // one thread per column carries the loss
+        loss_acc += fmaf(__log2f(s), LN2, m) - vlab;
+        cnt_acc += 1.f;
+      }
       if constexpr (GRAD) {
         const float inv_s = __fdividef(1.f, s);
         const float c0 = w0 * inv_s, c1 = w1 * inv_s;
         const float2 C0 = make_float2(c0, c0), C1 = make_float2(c1, c1);
 #pragma unroll
-        for (int i = 0; i < NP; ++i) {
+        for (int i = 0; i < NPH; ++i) {
           const float2 pr = make_float2(f[2 * i], f[2 * i + 1]);
           acc0[i] = fma2(C0, pr, acc0[i]);
           acc1[i] = fma2(C1, pr, acc1[i]);
         }
-        // -onehot, thread-private column of the stage: element (class gi) of pair gi/2
-        const unsigned oh = (unsigned)(gi >> 1) * (K2_PITCH2 * 8) + (unsigned)(gi & 1) * 4;
-        sts_f32(st0_s + oh, lds_f32(st0_s + oh) - w0);
-        sts_f32(st1_s + oh, lds_f32(st1_s + oh) - w1);
+        // -onehot into the column's stage slot, by the thread that owns the labelled class
+        if ((gi >> 1) / NPH == half) {
+          const unsigned oh = (unsigned)(gi >> 1) * (K2_PITCH2 * 8) + (unsigned)(gi & 1) * 4;
+          sts_f32(st0_s + oh, lds_f32(st0_s + oh) - w0);
+          sts_f32(st1_s + oh, lds_f32(st1_s + oh) - w1);
+        }
       }
     }
   }
@@ -451,16 +476,19 @@ __global__ void __launch_bounds__(K2_THREADS, 3) k2_upsample_ce_main(const K2Par
   loss_acc = warp_sum(loss_acc);
   cnt_acc = warp_sum(cnt_acc);
   float* red = reinterpret_cast<float*>(k2_smem_raw + K2_L.red);
-  if (lane == 0) { red[warp] = loss_acc; red[4 + warp] = cnt_acc; }
+  if (lane == 0) { red[warp] = loss_acc; red[8 + warp] = cnt_acc; }
   __syncthreads();
   if (tid == 0) {
-    p.loss_part[tile] = (red[0] + red[1]) + (red[2] + red[3]);
-    p.cnt_part[tile] = (red[4] + red[5]) + (red[6] + red[7]);
+    float ls = 0.f, cs = 0.f;
+#pragma unroll
+    for (int q = 0; q < NWARPS; ++q) { ls += red[q]; cs += red[8 + q]; }
+    p.loss_part[tile] = ls;
+    p.cnt_part[tile] = cs;
   }
   if (GRAD) {
     const float* blk = K2_BLK;
     float* dst = p.blocks + (long long)tile * blk_floats;
-    for (int i = tid; i < blk_floats; i += K2_THREADS) dst[i] = blk[i];
+    for (int i = tid; i < blk_floats; i += NT) dst[i] = blk[i];
   }
 #undef K2_L
 #undef K2_STAGE0
@@ -573,27 +601,27 @@ __global__ void __launch_bounds__(256) k2_bias_from_partials(const float* bias_p
   }
 }
 
-template <int CT, bool EXACT>
+template <int CT, bool EXACT, int SPLIT>
 static int k2_main_launch(const K2Params& p, bool grad, cudaStream_t stream) {
   const K2Geom& g = p.g;
-  const size_t smem = (size_t)k2_smem_layout(CT, g.C, g.ispan_max, g.jspan_max, g.kmax).total;
+  const size_t smem = (size_t)k2_smem_layout(CT, g.C, g.ispan_max, g.jspan_max, g.kmax, K2_THREADS * SPLIT / 32).total;
   B200SEG_CHECK_ARG(smem <= 200 * 1024, "upsample_ce: tile footprint %zu B exceeds shared memory (resize ratio too small)", smem);
   const int tiles = (int)k2_tiles(g);
   profile_begin(6, stream);
   if (grad) {
     static bool configured = false;
     if (!configured) {
-      B200SEG_CUDA(cudaFuncSetAttribute(k2_upsample_ce_main<CT, true, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      B200SEG_CUDA(cudaFuncSetAttribute(k2_upsample_ce_main<CT, true, EXACT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       configured = true;
     }
-    k2_upsample_ce_main<CT, true, EXACT><<<tiles, K2_THREADS, smem, stream>>>(p);
+    k2_upsample_ce_main<CT, true, EXACT, SPLIT><<<tiles, K2_THREADS * SPLIT, smem, stream>>>(p);
   } else {
     static bool configured = false;
     if (!configured) {
-      B200SEG_CUDA(cudaFuncSetAttribute(k2_upsample_ce_main<CT, false, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      B200SEG_CUDA(cudaFuncSetAttribute(k2_upsample_ce_main<CT, false, EXACT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       configured = true;
     }
-    k2_upsample_ce_main<CT, false, EXACT><<<tiles, K2_THREADS, smem, stream>>>(p);
+    k2_upsample_ce_main<CT, false, EXACT, SPLIT><<<tiles, K2_THREADS * SPLIT, smem, stream>>>(p);
   }
   profile_end(6, stream);
   B200SEG_LAUNCH_CHECK();
@@ -615,10 +643,13 @@ int k2_forward(const float* logits, int N, int C, int h, int w, const long long*
   p.cnt_part = p.loss_part + tiles;
   p.blocks = p.cnt_part + tiles;
   int rc;
-  if (C == 2) rc = k2_main_launch<2, true>(p, need_grad != 0, stream);
-  else if (C == 19) rc = k2_main_launch<19, true>(p, need_grad != 0, stream);
-  else if (C <= 8) rc = k2_main_launch<8, false>(p, need_grad != 0, stream);
-  else rc = k2_main_launch<32, false>(p, need_grad != 0, stream);
+#ifndef K2_SPLIT_DEF
+#define K2_SPLIT_DEF 1   /* 2 = class dimension split over lane pairs: measured 135 us vs 108 us at C = 19 (profiles/README.md) */
+#endif
+  if (C == 2) rc = k2_main_launch<2, true, 1>(p, need_grad != 0, stream);
+  else if (C == 19) rc = k2_main_launch<19, true, K2_SPLIT_DEF>(p, need_grad != 0, stream);
+  else if (C <= 8) rc = k2_main_launch<8, false, 1>(p, need_grad != 0, stream);
+  else rc = k2_main_launch<32, false, K2_SPLIT_DEF>(p, need_grad != 0, stream);
   if (rc) return rc;
   k2_finalize_loss<<<1, 256, 0, stream>>>(p.loss_part, p.cnt_part, (int)tiles, loss_out2);
   B200SEG_LAUNCH_CHECK();
