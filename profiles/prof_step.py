@@ -1,4 +1,4 @@
-"""Short program for ncu: 2 warm-up + 1 profiled train step and eval frame of the bench workloads.
+"""Short program for ncu: 2 warm-up + 1 profiled (cudaProfilerStart/Stop) train step and eval frame of the bench workloads.
     python profiles/prof_step.py [train_workload]
 """
 import os
@@ -23,6 +23,9 @@ ey = synth.make_labels(1, eH, eW, eC, seed=6, device=dev)
 ehead = synth.scale_head_for_unit_logits(b200.ASPP_Classifier_V2(ecin, RATES, RATES, eC)).to(dev).eval()
 cm = torch.zeros(eC, eC, dtype=torch.int64, device=dev)
 for it in range(3):
+    if it == 2:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()            # ncu --profile-from-start off: only the third iteration is captured
     xg = x.detach().requires_grad_(True)
     for p in head.parameters():
         p.grad = None
@@ -32,4 +35,5 @@ for it in range(3):
         lg = ehead.logits(ex)
     b200.segmentation_eval_step(lg, ey, cm=cm)
     torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("ok", loss.item(), int(cm.sum()))
