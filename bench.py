@@ -319,6 +319,44 @@ def run_ours(args):
                 "seam_bf16_nhwc": {"value": round(world * esteps / (ems_seam * 1e-3), 1), "unit": "img/s",
                                    "ms_per_frame": round(ems_seam / esteps, 4)}}
 
+    # ---- the other loss kernels of the scope table at the adversarial config: N=4, 2C=38, 512x1024
+    from rnd_semantic_segmentation_b200 import ops as bops
+    an, _, ah, aw, aH, aW, aC = synth.WORKLOADS["deeplabv2_r101_adv"]
+    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    sets3 = []
+    for _ in range(2):                                    # 2 x (319 + 319 MB) > L2
+        pred = torch.randn(an, 2 * aC, aH, aW, device=dev, generator=gen)
+        soft = torch.softmax(torch.randn(an, 2 * aC, aH, aW, device=dev, generator=gen), 1)
+        sets3.append((pred, soft))
+    i3 = [0]
+
+    def k3_step():
+        pred, soft = sets3[i3[0] & 1]
+        i3[0] += 1
+        pr = pred.requires_grad_(True)
+        pr.grad = None
+        bops.soft_label_cross_entropy(pr, soft).backward()
+
+    k3_ms, _ = timed(k3_step, 6, 3)
+    k3_bytes = 20 * 2 * aC * an * aH * aW
+    del sets3
+    d_lr = torch.randn(an, 2 * aC, ah, aw, device=dev, generator=gen)
+    s_lr = torch.randn(an, aC, ah, aw, device=dev, generator=gen)
+
+    def k5_step():
+        dl = d_lr.requires_grad_(True)
+        dl.grad = None
+        bops.fada_soft_label_loss(dl, s_lr, (aH, aW), slot=0).backward()
+
+    k5_ms, _ = timed(k5_step, 10, 3)
+    aux = {"k3_soft_label_ce_fwd_bwd": {"ms": round(k3_ms / 6, 4), "algorithmic_bytes": k3_bytes, "bound": "hbm",
+                                        "achieved_gbs": round(k3_bytes / (k3_ms / 6 * 1e-3) / 1e9, 1),
+                                        "frac": round(k3_bytes / (k3_ms / 6 * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                                        "shape": [an, 2 * aC, aH, aW]},
+           "k5_fused_fada_loss_tail_fwd_bwd": {"ms": round(k5_ms / 10, 4), "replaces_bytes_of_materialised_path": k3_bytes + 16 * 2 * aC * an * aH * aW,
+                                               "shape_lowres": [an, 2 * aC, ah, aw], "size": [aH, aW],
+                                               "note": "compute-bound: only low-resolution tensors are read"}}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = run_cpu_reference(args.workload, steps=2, warmup=1)["cpu_baseline"]
@@ -333,7 +371,7 @@ def run_ours(args):
                            "l2": "inputs larger than L2 (features %d MB per step)" % (x.numel() * 4 // 2 ** 20),
                            "parallelism": "dp%d (batch sharded by image)" % world},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_timed), "roofline": roofline, "eval": eval_obj,
-                "seam_bf16_nhwc": seam}
+                "seam_bf16_nhwc": seam, "aux_kernels": aux}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         emit(line)

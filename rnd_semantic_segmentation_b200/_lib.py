@@ -38,6 +38,9 @@ SIGNATURES = {
     "b200seg_soft_ce_workspace_bytes": (c_i64, []),
     "b200seg_soft_ce_forward": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_vp]),
     "b200seg_soft_ce_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "b200seg_soft_ce_stats_bytes": (c_i64, [c_int, c_int, c_int]),
+    "b200seg_soft_ce_forward_stats": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "b200seg_soft_ce_backward_stats": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "b200seg_fada_softce_workspace_bytes": (c_i64, [c_int] * 6),
     "b200seg_fada_softce_forward": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_f32, c_int, c_int, c_vp, c_i64,
                                             c_vp, c_vp]),
@@ -245,7 +248,9 @@ def upsample_bilinear_backward(grad_out: torch.Tensor, in_hw) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 # K3
 # --------------------------------------------------------------------------------------------
-def soft_ce_forward(pred, soft, weights=None) -> torch.Tensor:
+def soft_ce_forward(pred, soft, weights=None, want_stats: bool = False):
+    """loss (0-d); with ``want_stats`` also the per-pixel {lse, sum q} planes for soft_ce_backward (None when the shapes do
+    not allow the vectorised path)."""
     lib = load()
     _need(pred, torch.float32, "pred")
     _need(soft, torch.float32, "soft_label")
@@ -259,17 +264,29 @@ def soft_ce_forward(pred, soft, weights=None) -> torch.Tensor:
     nbytes = lib.b200seg_soft_ce_workspace_bytes()
     ws = torch.empty(nbytes, dtype=torch.uint8, device=pred.device)
     out = torch.empty(1, dtype=torch.float32, device=pred.device)
+    stats = None
+    if want_stats and (H * W) % 4 == 0 and all(t is None or t.data_ptr() % 16 == 0 for t in (pred, soft, weights)):
+        stats = torch.empty(lib.b200seg_soft_ce_stats_bytes(N, H, W) // 4, dtype=torch.float32, device=pred.device)
     with torch.cuda.device(pred.device):
-        _check(lib.b200seg_soft_ce_forward(pred.data_ptr(), soft.data_ptr(), _ptr(weights), N, K, H, W, ws.data_ptr(), nbytes,
-                                           out.data_ptr(), _stream()))
-    return out.reshape(())
+        if stats is not None:
+            _check(lib.b200seg_soft_ce_forward_stats(pred.data_ptr(), soft.data_ptr(), _ptr(weights), N, K, H, W, ws.data_ptr(),
+                                                     nbytes, stats.data_ptr(), out.data_ptr(), _stream()))
+        else:
+            _check(lib.b200seg_soft_ce_forward(pred.data_ptr(), soft.data_ptr(), _ptr(weights), N, K, H, W, ws.data_ptr(), nbytes,
+                                               out.data_ptr(), _stream()))
+    return (out.reshape(()), stats) if want_stats else out.reshape(())
 
 
-def soft_ce_backward(pred, soft, weights, grad_out) -> torch.Tensor:
+def soft_ce_backward(pred, soft, weights, grad_out, stats=None) -> torch.Tensor:
     lib = load()
     N, K, H, W = pred.shape
     grad_out = _need(grad_out.reshape(1).contiguous(), torch.float32, "grad_out")
     grad = torch.empty_like(pred)
+    if stats is not None:
+        with torch.cuda.device(pred.device):
+            _check(lib.b200seg_soft_ce_backward_stats(pred.data_ptr(), soft.data_ptr(), _ptr(weights), stats.data_ptr(),
+                                                      grad_out.data_ptr(), N, K, H, W, grad.data_ptr(), _stream()))
+        return grad
     with torch.cuda.device(pred.device):
         _check(lib.b200seg_soft_ce_backward(pred.data_ptr(), soft.data_ptr(), _ptr(weights), grad_out.data_ptr(), N, K, H, W,
                                             grad.data_ptr(), _stream()))

@@ -60,8 +60,9 @@ int aspp_backward_packed(const void*, const void*, const void*, const int*, int,
 int upsample_fwd_launch(const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int upsample_bwd_launch(const float*, float*, int, int, int, int, int, cudaStream_t);
 long long k3_workspace_bytes();
-int k3_forward(const float*, const float*, const float*, int, int, int, int, void*, long long, float*, cudaStream_t);
-int k3_backward(const float*, const float*, const float*, const float*, int, int, int, int, float*, cudaStream_t);
+long long k3_stats_bytes(int, int, int);
+int k3_forward(const float*, const float*, const float*, int, int, int, int, void*, long long, float*, cudaStream_t, float*);
+int k3_backward(const float*, const float*, const float*, const float*, int, int, int, int, float*, cudaStream_t, const float*);
 int aspp_nj(int, int);
 int aspp_pack_weights(const float* const*, const float* const*, int, int, int, void*, void*, float*, cudaStream_t);
 int aspp_pack_features(const float*, int, int, int, int, void*, cudaStream_t);
@@ -187,13 +188,28 @@ int64_t b200seg_soft_ce_workspace_bytes(void) { return k3_workspace_bytes(); }
 int b200seg_soft_ce_forward(const float* pred, const float* soft, const float* weights, int N, int K, int H, int W, void* workspace,
                             int64_t workspace_bytes, float* loss_out, void* stream) {
   REQUIRE_DEVICE();
-  return k3_forward(pred, soft, weights, N, K, H, W, workspace, workspace_bytes, loss_out, S(stream));
+  return k3_forward(pred, soft, weights, N, K, H, W, workspace, workspace_bytes, loss_out, S(stream), nullptr);
 }
 
 int b200seg_soft_ce_backward(const float* pred, const float* soft, const float* weights, const float* grad_out, int N, int K, int H,
                              int W, float* grad_pred, void* stream) {
   REQUIRE_DEVICE();
-  return k3_backward(pred, soft, weights, grad_out, N, K, H, W, grad_pred, S(stream));
+  return k3_backward(pred, soft, weights, grad_out, N, K, H, W, grad_pred, S(stream), nullptr);
+}
+
+int64_t b200seg_soft_ce_stats_bytes(int N, int H, int W) { return k3_stats_bytes(N, H, W); }
+
+int b200seg_soft_ce_forward_stats(const float* pred, const float* soft, const float* weights, int N, int K, int H, int W,
+                                  void* workspace, int64_t workspace_bytes, float* stats, float* loss_out, void* stream) {
+  REQUIRE_DEVICE();
+  return k3_forward(pred, soft, weights, N, K, H, W, workspace, workspace_bytes, loss_out, S(stream), stats);
+}
+
+int b200seg_soft_ce_backward_stats(const float* pred, const float* soft, const float* weights, const float* stats,
+                                   const float* grad_out, int N, int K, int H, int W, float* grad_pred, void* stream) {
+  REQUIRE_DEVICE();
+  B200SEG_CHECK_ARG(stats != nullptr, "soft_ce_backward_stats: stats is null");
+  return k3_backward(pred, soft, weights, grad_out, N, K, H, W, grad_pred, S(stream), stats);
 }
 
 int64_t b200seg_fada_softce_workspace_bytes(int N, int C, int h, int w, int H, int W) {

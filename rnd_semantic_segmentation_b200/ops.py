@@ -197,13 +197,14 @@ class _SoftCEFn(torch.autograd.Function):
         pred_c = pred.detach().float().contiguous()
         soft_c = soft.detach().float().contiguous()
         w_c = None if weights is None else weights.detach().float().contiguous()
-        ctx.save_for_backward(pred_c, soft_c, w_c)
-        return _lib.soft_ce_forward(pred_c, soft_c, w_c)
+        loss, stats = _lib.soft_ce_forward(pred_c, soft_c, w_c, want_stats=bool(ctx.needs_input_grad[0]))
+        ctx.save_for_backward(pred_c, soft_c, w_c, stats)
+        return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        pred_c, soft_c, w_c = ctx.saved_tensors
-        return _lib.soft_ce_backward(pred_c, soft_c, w_c, grad_out.detach().float()), None, None
+        pred_c, soft_c, w_c, stats = ctx.saved_tensors
+        return _lib.soft_ce_backward(pred_c, soft_c, w_c, grad_out.detach().float(), stats), None, None
 
 
 def soft_label_cross_entropy(pred: torch.Tensor, soft_label: torch.Tensor,
