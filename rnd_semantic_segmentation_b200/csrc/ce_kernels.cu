@@ -1061,10 +1061,65 @@ __global__ void __launch_bounds__(256) upsample_fwd_kernel(const float* __restri
   }
 }
 
+// Streaming form for W % 4 == 0 (the ATen-exact contraction, modes 0/1): one thread owns four adjacent output columns of
+// one plane and walks UPS_ROWS output rows; the horizontal lerps of the two source rows live in registers and are reused
+// for every output row between them, so an output float4 costs ~15 instructions and one 16-byte streaming store.
+// 8 x 19 x 512 x 1024 (319 MB written): 50 us = 6.4 TB/s, the HBM write rate of a plain fill (47 us); the
+// one-element-per-thread kernel it replaces took 197 us.
+constexpr int UPS_ROWS = 16;
+__global__ void __launch_bounds__(256) upsample_fwd_v4_kernel(const float* __restrict__ in, float* __restrict__ out, int h, int w,
+                                                              int H, int W, float sh, float sw) {
+  const int x0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (x0 >= W) return;
+  const long long nc = blockIdx.z;
+  const float* src = in + nc * h * w;
+  Tap tx[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) tx[e] = ac_tap(sw, x0 + e, w);
+  const int y_begin = blockIdx.y * UPS_ROWS, y_end = min(H, y_begin + UPS_ROWS);
+  float t[4], u[4];                          // horizontal lerps of source rows r0 (upper) / r1 (lower)
+  int r0 = -1, r1 = -1;
+  float* dst = out + (nc * H + y_begin) * W + x0;
+  for (int y = y_begin; y < y_end; ++y, dst += W) {
+    const Tap ty = ac_tap(sh, y, h);
+    if (ty.i0 != r0 || ty.i1 != r1) {
+      if (ty.i0 == r1) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) t[e] = u[e];
+      } else {
+        const float* p = src + (long long)ty.i0 * w;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) t[e] = fmaf(tx[e].l0, __ldg(p + tx[e].i0), tx[e].l1 * __ldg(p + tx[e].i1));
+      }
+      if (ty.i1 == ty.i0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) u[e] = t[e];
+      } else {
+        const float* p = src + (long long)ty.i1 * w;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) u[e] = fmaf(tx[e].l0, __ldg(p + tx[e].i0), tx[e].l1 * __ldg(p + tx[e].i1));
+      }
+      r0 = ty.i0; r1 = ty.i1;
+    }
+    float4 v;
+    v.x = fmaf(ty.l0, t[0], ty.l1 * u[0]);
+    v.y = fmaf(ty.l0, t[1], ty.l1 * u[1]);
+    v.z = fmaf(ty.l0, t[2], ty.l1 * u[2]);
+    v.w = fmaf(ty.l0, t[3], ty.l1 * u[3]);
+    st_stream_f4(dst, v);
+  }
+}
+
 int upsample_fwd_launch(const float* in, float* out, int NC, int h, int w, int H, int W, int fma_mode, cudaStream_t stream) {
   B200SEG_CHECK_ARG(in && out && NC > 0 && h > 0 && w > 0 && H > 0 && W > 0, "upsample_bilinear_forward: bad arguments");
-  dim3 grid(ceil_div(W, 256), H, NC < 64 ? NC : 64);
   const float sh = ac_scale(h, H), sw = ac_scale(w, W);
+  if (fma_mode <= 1 && W % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && NC <= 65535) {
+    dim3 grid(ceil_div(W, 1024), ceil_div(H, UPS_ROWS), NC);
+    upsample_fwd_v4_kernel<<<grid, 256, 0, stream>>>(in, out, h, w, H, W, sh, sw);
+    B200SEG_LAUNCH_CHECK();
+    return B200SEG_OK;
+  }
+  dim3 grid(ceil_div(W, 256), H, NC < 64 ? NC : 64);
   switch (fma_mode) {
     case 0: upsample_fwd_kernel<0><<<grid, 256, 0, stream>>>(in, out, NC, h, w, H, W, sh, sw); break;
     case 1: upsample_fwd_kernel<1><<<grid, 256, 0, stream>>>(in, out, NC, h, w, H, W, sh, sw); break;
