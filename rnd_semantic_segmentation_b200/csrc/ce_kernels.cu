@@ -1156,8 +1156,80 @@ __global__ void __launch_bounds__(128) upsample_bwd_kernel(const float* __restri
   }
 }
 
+// Streaming adjoint for W % 4 == 0, W <= 1024 (one 256-thread block spans a whole output row).  A block owns UPB_ROWS
+// low-res rows of one plane: its threads own four adjacent output columns each and walk the output rows that feed those
+// low-res rows (16-byte streaming loads), reducing VERTICALLY in registers; each time a low-res row is complete the block
+// parks the 4 KB row of vertical sums in shared memory and the first w threads reduce it HORIZONTALLY over their column
+// windows.  Every low-res element is produced by exactly one thread in a fixed order: deterministic, no atomics.
+constexpr int UPB_ROWS = 8;
+__global__ void __launch_bounds__(256) upsample_bwd_v4_kernel(const float* __restrict__ gout, float* __restrict__ gin, int h, int w,
+                                                              int H, int W, float sh, float sw) {
+  __shared__ __align__(16) float vrow[1024];
+  const int x0 = threadIdx.x * 4;
+  const bool xin = x0 < W;
+  const long long nc = blockIdx.z;
+  const int ia = blockIdx.y * UPB_ROWS, ib = min(h, ia + UPB_ROWS);
+  const int ya = ac_first_dst(sh, ia - 1, h, H), yb = ac_first_dst(sh, ib, h, H);     // output rows touching rows [ia, ib)
+  // horizontal window of source column j = threadIdx.x
+  const int j = threadIdx.x;
+  int xa = 0, xb = 0;
+  if (j < w) { xa = ac_first_dst(sw, j - 1, w, W); xb = ac_first_dst(sw, j + 1, w, W); }
+  const float* src = gout + nc * H * W + x0;
+  float* dstp = gin + nc * h * w;
+  float accA[4] = {0.f, 0.f, 0.f, 0.f}, accB[4] = {0.f, 0.f, 0.f, 0.f};     // vertical sums of low-res rows r, r + 1
+  int r = (ya < yb) ? (int)(sh * (float)ya) : ia;
+
+  auto emit = [&](int row) {                // block-uniform: park row `row`'s vertical sums, reduce them horizontally
+    __syncthreads();                        // previous readers of vrow are done
+    if (xin) *reinterpret_cast<float4*>(&vrow[x0]) = make_float4(accA[0], accA[1], accA[2], accA[3]);
+    __syncthreads();
+    if (j < w && row >= ia && row < ib) {
+      float a = 0.f;
+      for (int x = xa; x < xb; ++x) {
+        const Tap tx = ac_tap(sw, x, w);
+        const float wx = (tx.i0 == j ? tx.l0 : 0.f) + (tx.i1 == j ? tx.l1 : 0.f);
+        a = fmaf(wx, vrow[x], a);
+      }
+      dstp[(long long)row * w + j] = a;
+    }
+  };
+
+  for (int y = ya; y < yb; ++y) {
+    const Tap ty = ac_tap(sh, y, h);
+    while (ty.i0 > r) {                     // row r is complete (block-uniform)
+      emit(r);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { accA[e] = accB[e]; accB[e] = 0.f; }
+      ++r;
+    }
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (xin) g = ld_stream_f4(src + (long long)y * W);
+    const float wa = (ty.i1 == ty.i0) ? ty.l0 + ty.l1 : ty.l0;               // bottom border: both taps on row i0
+    const float wb = (ty.i1 == ty.i0) ? 0.f : ty.l1;
+    accA[0] = fmaf(wa, g.x, accA[0]); accA[1] = fmaf(wa, g.y, accA[1]); accA[2] = fmaf(wa, g.z, accA[2]); accA[3] = fmaf(wa, g.w, accA[3]);
+    accB[0] = fmaf(wb, g.x, accB[0]); accB[1] = fmaf(wb, g.y, accB[1]); accB[2] = fmaf(wb, g.z, accB[2]); accB[3] = fmaf(wb, g.w, accB[3]);
+  }
+  // rows r and r + 1 are still open; rows of [ia, ib) that no output row touches (downsampling) are zero
+  for (int row = r; row < ib; ++row) {
+    emit(row);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { accA[e] = accB[e]; accB[e] = 0.f; }
+  }
+  if (ya >= yb || (int)(sh * (float)ya) > ia) {                              // leading rows without contributions
+    const int first = (ya < yb) ? (int)(sh * (float)ya) : ib;
+    for (int row = ia; row < min(first, ib); ++row)
+      if (j < w) dstp[(long long)row * w + j] = 0.f;
+  }
+}
+
 int upsample_bwd_launch(const float* gout, float* gin, int NC, int h, int w, int H, int W, cudaStream_t stream) {
   B200SEG_CHECK_ARG(gout && gin && NC > 0 && h > 0 && w > 0 && H > 0 && W > 0, "upsample_bilinear_backward: bad arguments");
+  if (W % 4 == 0 && W <= 1024 && w <= 256 && NC <= 65535 && (reinterpret_cast<uintptr_t>(gout) & 15) == 0) {
+    dim3 gridv(1, ceil_div(h, UPB_ROWS), NC);
+    upsample_bwd_v4_kernel<<<gridv, 256, 0, stream>>>(gout, gin, h, w, H, W, ac_scale(h, H), ac_scale(w, W));
+    B200SEG_LAUNCH_CHECK();
+    return B200SEG_OK;
+  }
   dim3 grid(ceil_div(w, 128), h, NC < 1024 ? NC : 1024);
   upsample_bwd_kernel<<<grid, 128, 0, stream>>>(gout, gin, NC, h, w, H, W, ac_scale(h, H), ac_scale(w, W));
   B200SEG_LAUNCH_CHECK();

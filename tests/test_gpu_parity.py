@@ -54,7 +54,10 @@ def test_upsample_forward_bit_exact_and_mode_report(lib):
 
 
 @pytest.mark.parametrize("shape,size", [((2, 5, 9, 11), (50, 70)), ((1, 19, 64, 128), (512, 1024)), ((3, 2, 44, 44), (352, 352)),
-                                        ((1, 3, 7, 5), (7, 5)), ((1, 4, 16, 16), (17, 31))])
+                                        ((1, 3, 7, 5), (7, 5)), ((1, 4, 16, 16), (17, 31)),
+                                        # streaming float4 paths (W % 4 == 0): identity, downsampling, 1-row / 1-column sources
+                                        ((1, 3, 8, 8), (8, 8)), ((1, 2, 20, 24), (10, 12)), ((2, 2, 5, 6), (40, 64)),
+                                        ((1, 2, 1, 7), (16, 32)), ((1, 2, 6, 1), (24, 8)), ((1, 19, 65, 129), (512, 1024))])
 def test_upsample_backward_is_adjoint(lib, shape, size):
     torch.manual_seed(1)
     x = torch.randn(*shape, device="cuda", requires_grad=True)
