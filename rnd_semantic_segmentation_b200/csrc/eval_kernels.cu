@@ -603,11 +603,107 @@ __global__ void __launch_bounds__(256) confusion_pairs_kernel(long long* pd, con
   }
 }
 
+// Same histogram with K4's per-lane uint8 counters (no atomics, no match.any) and 16-byte loads (two int64 per load):
+// used when the counters fit shared memory (C <= 19) and the maps are 16-byte aligned.
+constexpr int CP_THREADS = 128;
+__global__ void __launch_bounds__(CP_THREADS) confusion_pairs_u8_kernel(long long* pd, const long long* gt, long long n, int C,
+                                                                        int ignore_index, int mutate_pd, long long* cm) {
+  extern __shared__ __align__(16) uint8_t cp_smem[];
+  const int CC = C * C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* cta_hist = reinterpret_cast<int*>(cp_smem);
+  const int hist_off = ((CC * 4 + 15) / 16) * 16;
+  uint8_t* whist = cp_smem + hist_off + warp * ((CC + 1) * 32);
+  for (int i = threadIdx.x; i < CC; i += CP_THREADS) cta_hist[i] = 0;
+  {
+    int4* z = reinterpret_cast<int4*>(whist);
+    for (int i = lane; i < (CC + 1) * 2; i += 32) z[i] = make_int4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  const unsigned whist_s = smem_u32(whist) + lane;
+  const unsigned ign32 = ignore_index >= 0 ? (unsigned)ignore_index : 0xffffffffu;
+  const long long ign = ignore_index;
+
+  auto fold = [&]() {
+    __syncwarp();
+    uint4* wh = reinterpret_cast<uint4*>(whist);
+    for (int b = lane; b < CC; b += 32) {
+      const uint4 a = wh[b * 2], c4 = wh[b * 2 + 1];
+      if ((a.x | a.y | a.z | a.w | c4.x | c4.y | c4.z | c4.w) != 0u) {
+        unsigned sum = 0;
+        sum = __dp4a(a.x, 0x01010101u, sum); sum = __dp4a(a.y, 0x01010101u, sum);
+        sum = __dp4a(a.z, 0x01010101u, sum); sum = __dp4a(a.w, 0x01010101u, sum);
+        sum = __dp4a(c4.x, 0x01010101u, sum); sum = __dp4a(c4.y, 0x01010101u, sum);
+        sum = __dp4a(c4.z, 0x01010101u, sum); sum = __dp4a(c4.w, 0x01010101u, sum);
+        atomicAdd(&cta_hist[b], (int)sum);
+        wh[b * 2] = make_uint4(0, 0, 0, 0);
+        wh[b * 2 + 1] = make_uint4(0, 0, 0, 0);
+      }
+    }
+    __syncwarp();
+  };
+
+  const long long pairs = n >> 1;
+  int since_fold = 0;                                   // increments per lane since the last fold (<= 255)
+  // block-uniform trip count (the in-loop fold synchronises the warp); CP_U pair-loads of each map in flight per thread
+  constexpr int CP_U = 4;
+  for (long long base = blockIdx.x * (long long)(CP_THREADS * CP_U); base < pairs + 1; base += (long long)gridDim.x * (CP_THREADS * CP_U)) {
+    int4 qv[CP_U], gv[CP_U];
+#pragma unroll
+    for (int u = 0; u < CP_U; ++u) {
+      const long long i2 = base + u * CP_THREADS + threadIdx.x;
+      if (i2 < pairs) { qv[u] = ld_stream_v4(pd + 2 * i2); gv[u] = ld_stream_v4(gt + 2 * i2); }
+    }
+#pragma unroll
+    for (int u = 0; u < CP_U; ++u) {
+      const long long i2 = base + u * CP_THREADS + threadIdx.x;
+      long long q[2] = {-1, -1}, g[2] = {-1, -1};
+      int cnt = 0;
+      if (i2 < pairs) {
+        q[0] = ((long long)(unsigned)qv[u].x) | ((long long)qv[u].y << 32); q[1] = ((long long)(unsigned)qv[u].z) | ((long long)qv[u].w << 32);
+        g[0] = ((long long)(unsigned)gv[u].x) | ((long long)gv[u].y << 32); g[1] = ((long long)(unsigned)gv[u].z) | ((long long)gv[u].w << 32);
+        cnt = 2;
+      } else if (i2 == pairs && (n & 1)) {               // odd tail element
+        q[0] = pd[n - 1]; g[0] = gt[n - 1];
+        cnt = 1;
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        if (e < cnt) {
+          const bool is_ign = g[e] == ign;
+          if (is_ign && mutate_pd) pd[(i2 < pairs ? 2 * i2 : n - 1) + e] = ign;
+          const bool valid = !is_ign && (unsigned long long)g[e] < (unsigned long long)C && (unsigned long long)q[e] < (unsigned long long)C;
+          const int bin = valid ? (int)g[e] * C + (int)q[e] : CC;
+          smem_inc_u8(whist_s + bin * 32);
+        }
+    }
+    since_fold += 2 * CP_U;
+    if (since_fold > 255 - 2 * CP_U) { fold(); since_fold = 0; }
+  }
+  fold();
+  __syncthreads();
+  for (int i = threadIdx.x; i < CC; i += CP_THREADS) {
+    const int v = cta_hist[i];
+    if (v) atomicAdd(reinterpret_cast<unsigned long long*>(cm + i), (unsigned long long)v);
+  }
+  (void)ign32;
+}
+
 int confusion_pairs_launch(long long* pd, const long long* gt, long long n, int C, int ignore_index, int mutate_pd,
                            long long* cm, cudaStream_t stream) {
   B200SEG_CHECK_ARG(pd && gt && cm, "confusion_from_pred: null pointer");
   B200SEG_CHECK_ARG(C > 0 && C <= 104, "confusion_from_pred: num_classes=%d unsupported (1..104)", C);
   if (n <= 0) return B200SEG_OK;
+  const int CC = C * C;
+  const size_t smem_u8 = ((CC * 4 + 15) / 16) * 16 + (size_t)(CP_THREADS / 32) * (CC + 1) * 32;
+  if (smem_u8 <= 48 * 1024 && ((reinterpret_cast<uintptr_t>(pd) | reinterpret_cast<uintptr_t>(gt)) & 15) == 0) {
+    long long blocks = ceil_div_ll((n >> 1) + 1, CP_THREADS * 4 * 4);
+    const long long capu = (long long)num_sms() * 4;
+    if (blocks > capu) blocks = capu;
+    confusion_pairs_u8_kernel<<<(unsigned)blocks, CP_THREADS, smem_u8, stream>>>(pd, gt, n, C, ignore_index, mutate_pd, cm);
+    B200SEG_LAUNCH_CHECK();
+    return B200SEG_OK;
+  }
   long long blocks = ceil_div_ll(n, 256 * 8);
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
