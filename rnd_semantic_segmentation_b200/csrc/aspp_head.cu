@@ -309,21 +309,32 @@ __global__ void __launch_bounds__(256) build_gprime_t8_kernel(const __nv_bfloat1
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int S, long long slab, int R, int C,
                                                            int Cin, MutPtrList gw) {
-  const int ci = blockIdx.x * 256 + threadIdx.x;
+  // reads: coalesced along ci for every (split, tap); writes: the block's [256 ci][9] outputs are contiguous in the
+  // [C, Cin, 3, 3] gradient, so they are transposed through shared memory and stored as coalesced 16-byte vectors
+  __shared__ __align__(16) float sm[256 * 9];
+  const int ci0 = blockIdx.x * 256;
+  const int ci = ci0 + threadIdx.x;
   const int c = blockIdx.y, r = blockIdx.z;
-  if (ci >= Cin || !gw.p[r]) return;
-  float out[9];
+  if (!gw.p[r]) return;
+  if (ci < Cin) {
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    const int t = (k == 4) ? 8 * R : r * 8 + (k < 4 ? k : k - 1);
-    const long long off = (long long)(t * C + c) * Cin + ci;
-    float acc = 0.f;
-    for (int s = 0; s < S; ++s) acc += part[s * slab + off];
-    out[k] = acc;
+    for (int k = 0; k < 9; ++k) {
+      const int t = (k == 4) ? 8 * R : r * 8 + (k < 4 ? k : k - 1);
+      const long long off = (long long)(t * C + c) * Cin + ci;
+      float acc = 0.f;
+      for (int s = 0; s < S; ++s) acc += __ldcs(part + s * slab + off);
+      sm[threadIdx.x * 9 + k] = acc;
+    }
   }
-  float* dst = gw.p[r] + ((long long)c * Cin + ci) * 9;
-#pragma unroll
-  for (int k = 0; k < 9; ++k) dst[k] = out[k];
+  __syncthreads();
+  const int nci = min(256, Cin - ci0);
+  float* dst = gw.p[r] + ((long long)c * Cin + ci0) * 9;
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (nci * 9) % 4 == 0) {
+    for (int i = threadIdx.x; i < nci * 9 / 4; i += 256)
+      reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(sm)[i];
+  } else {
+    for (int i = threadIdx.x; i < nci * 9; i += 256) dst[i] = sm[i];
+  }
 }
 
 // ------------------------------------------------------------------------------------------
