@@ -178,10 +178,11 @@ B200SEG_API void b200seg_profile_enable(int on);
 B200SEG_API int b200seg_profile_read(int tag, double* total_ms, int* count);
 
 /* on-device self-test of the tcgen05 GEMM core against a CUDA-core reference (synchronous).
- * share: 0 = one CTA per tile, 1 = 2-CTA cluster multicasting the shared B tile, 2 = ... the shared A tile. */
+ * share: 0 = one CTA per tile, 1 = 2-CTA cluster multicasting the shared B tile, 2 = ... the shared A tile,
+ *        3 = 2 x 2 cluster multicasting both. */
 B200SEG_API int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b_mn_major, int splits, int col_hw, int share,
                           double* max_err, double* max_ref);
-/* 0 disables the 2-CTA multicast variants inside the ASPP head GEMMs (A/B measurement); default on */
+/* operand multicast inside the ASPP head GEMMs: 0 none, 1 (default) 2-CTA pairs, 2 2 x 2 clusters sharing both operands */
 B200SEG_API void b200seg_gemm_set_sharing(int on);
 /* SMs the data-gradient GEMM leaves free when b200seg_aspp_backward_packed_ex is given a weights_ready_event, so that the
  * caller's all-reduce kernel can be resident underneath it (the persistent GEMM otherwise fills every SM's shared memory);

@@ -1,4 +1,4 @@
-"""A/B: head GEMMs with and without the 2-CTA multicast variants (per-kernel CUDA-event timing)."""
+"""A/B: head GEMMs without multicast (0), with 2-CTA pairs (1), with 2 x 2 clusters (2); per-kernel CUDA-event timing."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -16,7 +16,7 @@ def step():
     for p in head.parameters(): p.grad = None
     loss, _ = head.forward_loss(xg, labels); loss.backward()
     return loss
-for on in (False, True, False, True):
+for on in (1, 2, 0, 1, 2):
     _lib.gemm_set_sharing(on)
     for _ in range(3): step()
     torch.cuda.synchronize()

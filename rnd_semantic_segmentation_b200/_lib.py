@@ -494,8 +494,9 @@ def gemm_selftest(M, N, K, a_mn=False, b_mn=False, splits=1, col_hw=0, share=0):
     return err.value, ref.value
 
 
-def gemm_set_sharing(on: bool):
-    load().b200seg_gemm_set_sharing(1 if on else 0)
+def gemm_set_sharing(mode):
+    """0 / False: no multicast; 1 / True: 2-CTA pairs (default); 2: 2 x 2 clusters multicasting both operands (slower: kept for A/B)."""
+    load().b200seg_gemm_set_sharing(int(mode))
 
 
 PROFILE_TAGS = {"head_fwd_gemm": 0, "head_dgrad_gemm": 1, "head_wgrad_gemm": 2, "pack_features": 3, "head_gather": 4,

@@ -159,7 +159,11 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int m, i
 //   SHARE_A    : the two CTAs own N-tiles (2i, 2i+1) of the SAME M-tile; each loads its own B tile and half of A (40 KB).
 // Each CTA still issues its own cta_group::1 MMAs into its own TMEM.  A shared-memory stage is released to BOTH
 // producers only when BOTH CTAs' MMAs have drained it (empty barriers count 2, tcgen05.commit multicast to both CTAs).
-constexpr int SHARE_NONE = 0, SHARE_B = 1, SHARE_A = 2;
+//   SHARE_AB   : 2 x 2 cluster (rank = rm + 2 * rn): CTA (rm, rn) owns M-tile 2i+rm and N-tile 2j+rn, loads half rn of its A
+//                tile (multicast to the CTA with the same rm) and half rm of its B tile (multicast to the CTA with the same
+//                rn): 24 KB per k-block per SM.  The kernel is bound by the L2 -> SM rate (~6.3 KB/clk chip-wide: at 32-40 KB
+//                per k-block the loads of a k-block take longer than its four MMAs), so this is what buys tensor-pipe time.
+constexpr int SHARE_NONE = 0, SHARE_B = 1, SHARE_A = 2, SHARE_AB = 3;
 
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
                                                uint16_t cta_mask) {
@@ -187,11 +191,12 @@ template <int SHARE>
 struct TileSched {
   int units, worker, nworkers, rank, m_tiles, n_tiles, per_split;
   __device__ TileSched(const Params& p) {
+    constexpr int CS = SHARE == SHARE_NONE ? 1 : (SHARE == SHARE_AB ? 4 : 2);      // CTAs per cluster
     rank = SHARE != SHARE_NONE ? (int)cluster_cta_rank() : 0;
-    worker = SHARE != SHARE_NONE ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    nworkers = SHARE != SHARE_NONE ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    m_tiles = SHARE == SHARE_B ? (p.m_tiles + 1) >> 1 : p.m_tiles;     // pairs along M
-    n_tiles = SHARE == SHARE_A ? (p.n_tiles + 1) >> 1 : p.n_tiles;     // pairs along N
+    worker = (int)blockIdx.x / CS;
+    nworkers = (int)gridDim.x / CS;
+    m_tiles = (SHARE == SHARE_B || SHARE == SHARE_AB) ? (p.m_tiles + 1) >> 1 : p.m_tiles;     // pairs along M
+    n_tiles = (SHARE == SHARE_A || SHARE == SHARE_AB) ? (p.n_tiles + 1) >> 1 : p.n_tiles;     // pairs along N
     per_split = m_tiles * n_tiles;
     units = per_split * p.splits;
   }
@@ -202,6 +207,7 @@ struct TileSched {
     mt = rem - nt * m_tiles;
     if (SHARE == SHARE_B) mt = mt * 2 + rank;
     if (SHARE == SHARE_A) nt = nt * 2 + rank;
+    if (SHARE == SHARE_AB) { mt = mt * 2 + (rank & 1); nt = nt * 2 + (rank >> 1); }
   }
 };
 
@@ -231,7 +237,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CLUSTER ? 2 : 1);   // cluster: both CTAs' MMA warps release a stage
+      mbar_init(&empty_bar[s], SHARE == SHARE_AB ? 3 : (CLUSTER ? 2 : 1));   // cluster: every CTA this one writes into releases the stage
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -266,10 +272,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);   // own loads + the peer's multicast half
           const int k0 = kb * BLOCK_K;
           // ---- A ----
-          if (SHARE == SHARE_A) {
-            // shared A tile: this CTA loads rows [64*rank, +64) and multicasts them to both CTAs
-            if (!A_MN) tma_load_2d_mc(sa + sched.rank * (A_BYTES / 2), &tmap_a, &full_bar[stage], k0, m0 + sched.rank * 64, 0x3);
-            else tma_load_2d_mc(sa + sched.rank * MN_BOX_BYTES, &tmap_a, &full_bar[stage], m0 + sched.rank * 64, k0, 0x3);
+          if (SHARE == SHARE_A || SHARE == SHARE_AB) {
+            // shared A tile: this CTA loads rows [64*ha, +64) and multicasts them to the CTAs that own the same M-tile
+            const int ha = SHARE == SHARE_A ? sched.rank : (sched.rank >> 1);
+            const uint16_t am = SHARE == SHARE_A ? (uint16_t)0x3 : (uint16_t)((1u << (sched.rank & 1)) | (1u << ((sched.rank & 1) + 2)));
+            if (!A_MN) tma_load_2d_mc(sa + ha * (A_BYTES / 2), &tmap_a, &full_bar[stage], k0, m0 + ha * 64, am);
+            else tma_load_2d_mc(sa + ha * MN_BOX_BYTES, &tmap_a, &full_bar[stage], m0 + ha * 64, k0, am);
           } else if (!A_MN) {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);            // box {64 k, 128 rows}
           } else {
@@ -278,14 +286,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               tma_load_2d(sa + b * MN_BOX_BYTES, &tmap_a, &full_bar[stage], m0 + b * 64, k0);
           }
           // ---- B ----
-          if (SHARE == SHARE_B) {
-            // shared B tile: this CTA loads rows [128*rank, +128) and multicasts them to both CTAs
+          if (SHARE == SHARE_B || SHARE == SHARE_AB) {
+            // shared B tile: this CTA loads rows [128*hb, +128) and multicasts them to the CTAs that own the same N-tile
+            const int hb = SHARE == SHARE_B ? sched.rank : (sched.rank & 1);
+            const uint16_t bm = SHARE == SHARE_B ? (uint16_t)0x3 : (uint16_t)(0x3u << (2 * (sched.rank >> 1)));
             if (!B_MN) {
-              tma_load_2d_mc(sb + sched.rank * (B_BYTES / 2), &tmap_b, &full_bar[stage], k0, n0 + sched.rank * 128, 0x3);
+              tma_load_2d_mc(sb + hb * (B_BYTES / 2), &tmap_b, &full_bar[stage], k0, n0 + hb * 128, bm);
             } else {
 #pragma unroll
               for (int b = 0; b < 2; ++b)
-                tma_load_2d_mc(sb + (sched.rank * 2 + b) * MN_BOX_BYTES, &tmap_b, &full_bar[stage], n0 + (sched.rank * 2 + b) * 64, k0, 0x3);
+                tma_load_2d_mc(sb + (hb * 2 + b) * MN_BOX_BYTES, &tmap_b, &full_bar[stage], n0 + (hb * 2 + b) * 64, k0, bm);
             }
           } else if (!B_MN) {
             tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);            // box {64 k, 256 rows}
@@ -330,7 +340,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint64_t bdesc = make_smem_desc(sb + k * b_step, b_lbo, b_sbo);
             umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          if (CLUSTER) umma_commit_mc(&empty_bar[stage], 0x3);   // frees the slot in BOTH CTAs when these MMAs retire
+          // frees the slot in every CTA that multicasts into this one (itself included) when these MMAs retire
+          if (SHARE == SHARE_AB) umma_commit_mc(&empty_bar[stage], (uint16_t)((1u << sched.rank) | (1u << (sched.rank ^ 1)) | (1u << (sched.rank ^ 2))));
+          else if (CLUSTER) umma_commit_mc(&empty_bar[stage], 0x3);
           else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
