@@ -168,10 +168,47 @@ B200SEG_API int b200seg_aspp_backward_packed_ex(const void* gOt, const void* Xp,
                                     void* grad_x_nhwc_bf16, float* const* grad_w, void* weights_ready_event, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K6  3x3 convolution layers as tcgen05 implicit GEMMs: the PixelDiscriminator conv stack
+ *   replaces  D = Conv2d(Cin,ndf,3,1,1)+LeakyReLU(0.2)+Conv2d(ndf,ndf/2,3,1,1)+LeakyReLU(0.2)   core/models/discriminator.py:34-39
+ *             cls1 / cls2 = Conv2d(ndf/2, C, 3, 1, 1)                                            core/models/discriminator.py:40-41
+ *             their application and torch.cat                                                   core/models/discriminator.py:45-47
+ *             and the autograd backward of those layers (call sites core/trainers/aspp_fada.py:110,119,123)
+ *   Activations are bf16 NHWC [N,h,w,pitch] (pitch = channels rounded to a multiple of 8); weights are packed once per
+ *   parameter update.  Stride 1, padding == dilation.  The zero padding is the TMA unit's out-of-bounds fill.
+ * ------------------------------------------------------------------------------------------- */
+/* n_parts weight tensors fp32 [part_co[i]][Ci][3][3], concatenated along the output-channel axis (cls1 | cls2 = torch.cat(dim=1)):
+ *   Wf bf16 [9][Co][Ci]        forward operand (Co = sum part_co)           (may be NULL)
+ *   Wb bf16 [9][Ci][co_pitch]  data-gradient operand, caller zero-fills the padding columns co_pitch > Co   (may be NULL) */
+B200SEG_API int b200seg_conv3x3_pack_weights(const float* const* weights, const int* part_co_host, int n_parts, int Ci, void* Wf,
+                                             void* Wb, int co_pitch, void* stream);
+/* out = [LeakyReLU_slope](conv3x3(act; Wf) + bias): exactly one of out_bf16_nhwc ([N,h,w,out_pitch]) / out_f32_nchw ([N,Co,h,w]);
+ * bias may be NULL; lrelu != 0 applies the activation */
+B200SEG_API int b200seg_conv3x3_forward(const void* act_nhwc_bf16, int N, int h, int w, int Ci, int64_t act_pitch, const void* Wf, int Co,
+                                        int dilation, const float* bias, int lrelu, float slope, void* out_bf16_nhwc,
+                                        int64_t out_pitch, float* out_f32_nchw, void* stream);
+/* gin = conv3x3_transposed(g; Wb) [* LeakyReLU'(mask)]: g bf16 NHWC [N,h,w,g_pitch] with Cg = the pitch of Wb's last axis;
+ * mask (optional, bf16 NHWC, same layout as out_bf16_nhwc) is the saved post-activation output of the layer below:
+ * the gradient is multiplied by 1 where mask > 0 and by slope elsewhere (LeakyReLU backward fused in the epilogue) */
+B200SEG_API int b200seg_conv3x3_dgrad(const void* g_nhwc_bf16, int N, int h, int w, int Cg, int64_t g_pitch, const void* Wb, int Ci,
+                                      int dilation, const void* mask_nhwc_bf16, float slope, void* out_bf16_nhwc, int64_t out_pitch,
+                                      float* out_f32_nchw, void* stream);
+/* grad_w[i] fp32 [part_co[i]][Ci][3][3] = sum_pixels g[pixel, co] * x[pixel + tap, ci]; splits <= 0 picks the split-K factor */
+B200SEG_API int64_t b200seg_conv3x3_wgrad_scratch_bytes(int N, int h, int w, int Co, int Ci, int splits);
+B200SEG_API int b200seg_conv3x3_wgrad(const void* g_nhwc_bf16, int Co, int64_t g_pitch, const void* x_nhwc_bf16, int Ci, int64_t x_pitch,
+                                      int N, int h, int w, int dilation, int splits, void* scratch, int64_t scratch_bytes,
+                                      float* const* grad_w, const int* part_co_host, int n_parts, void* stream);
+/* fp32 NCHW [N,C,hw] -> bf16 NHWC [N*hw][pitch] (channels >= C zero): the output gradient of the last layer */
+B200SEG_API int b200seg_nchw_to_nhwc_bf16(const float* src, int N, int C, int hw, void* dst, int pitch, void* stream);
+/* bias gradient: out[c] = sum_pixels g[pixel][c], deterministic (fixed-order two-phase sum) */
+B200SEG_API int64_t b200seg_nhwc_colsum_scratch_bytes(int pitch);
+B200SEG_API int b200seg_nhwc_bf16_colsum(const void* g_nhwc_bf16, int64_t P, int C, int pitch, void* scratch, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * instrumentation (bench.py): number of kernels this library has launched, and per-kernel CUDA-event
  * timing on the launching stream.  Tags: 0 head fwd GEMM, 1 head dgrad GEMM, 2 head wgrad GEMM,
  * 3 feature pack, 4 fwd gather, 5 grad im2col (G'), 6 upsample+CE main, 7 eval argmax+confusion,
- * 8 soft-CE fwd, 9 soft-CE bwd, 10 wgrad reduce, 11 fused FADA soft-CE main.
+ * 8 soft-CE fwd, 9 soft-CE bwd, 10 wgrad reduce, 11 fused FADA soft-CE main, 12 conv3x3 fwd, 13 conv3x3 dgrad,
+ * 14 conv3x3 wgrad.
  * ------------------------------------------------------------------------------------------- */
 B200SEG_API long long b200seg_launch_count(void);
 B200SEG_API void b200seg_profile_enable(int on);

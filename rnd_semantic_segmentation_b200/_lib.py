@@ -59,6 +59,17 @@ SIGNATURES = {
                                                   c_int, c_vp, c_vp, c_vp]),
     "b200seg_aspp_backward_packed_ex": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64,
                                                 c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "b200seg_conv3x3_pack_weights": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
+    "b200seg_conv3x3_forward": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_i64, c_vp, c_int, c_int, c_vp, c_int, c_f32, c_vp, c_i64,
+                                        c_vp, c_vp]),
+    "b200seg_conv3x3_dgrad": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_i64, c_vp, c_int, c_int, c_vp, c_f32, c_vp, c_i64, c_vp,
+                                      c_vp]),
+    "b200seg_conv3x3_wgrad_scratch_bytes": (c_i64, [c_int] * 6),
+    "b200seg_conv3x3_wgrad": (c_int, [c_vp, c_int, c_i64, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp,
+                                      c_vp, c_int, c_vp]),
+    "b200seg_nchw_to_nhwc_bf16": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp]),
+    "b200seg_nhwc_colsum_scratch_bytes": (c_i64, [c_int]),
+    "b200seg_nhwc_bf16_colsum": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
     "b200seg_gemm_set_overlap_sms": (None, [c_int]),
     "b200seg_launch_count": (ctypes.c_longlong, []),
     "b200seg_profile_enable": (None, [c_int]),
@@ -477,6 +488,144 @@ def aspp_backward_packed(gOt: torch.Tensor, Xp: torch.Tensor, WpT: torch.Tensor,
     return gx, gws
 
 
+# --------------------------------------------------------------------------------------------
+# K6  3x3 conv layers as tcgen05 implicit GEMMs (PixelDiscriminator stack), bf16 NHWC activations
+# --------------------------------------------------------------------------------------------
+def _round8(v: int) -> int:
+    return (int(v) + 7) // 8 * 8
+
+
+def conv3x3_pack_weights(weights: Sequence[torch.Tensor]):
+    """[Co_i,Ci,3,3] fp32 tensors (concatenated along Co) -> (Wf bf16 [9,Co,Ci], Wb bf16 [9,Ci,round8(Co)])."""
+    lib = load()
+    Ci = weights[0].shape[1]
+    for wt in weights:
+        _need(wt, torch.float32, "conv weight")
+        if wt.dim() != 4 or tuple(wt.shape[1:]) != (Ci, 3, 3):
+            raise B200SegError(f"conv weight shape {tuple(wt.shape)}: expected [Co,{Ci},3,3]")
+    if Ci % 8 != 0:
+        raise B200SegError(f"conv3x3: in_channels={Ci} must be a multiple of 8")
+    parts = [int(wt.shape[0]) for wt in weights]
+    Co = sum(parts)
+    dev = weights[0].device
+    Wf = torch.empty((9, Co, Ci), dtype=torch.bfloat16, device=dev)
+    Wb = torch.zeros((9, Ci, _round8(Co)), dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.b200seg_conv3x3_pack_weights(_ptr_array(weights), (c_int * len(parts))(*parts), len(parts), Ci, Wf.data_ptr(),
+                                                Wb.data_ptr(), Wb.shape[2], _stream()))
+    return Wf, Wb
+
+
+def _need_nhwc(t: torch.Tensor, name: str):
+    _need(t, torch.bfloat16, name)
+    if t.dim() != 4 or t.shape[3] % 8 != 0:
+        raise B200SegError(f"{name}: expected bf16 NHWC [N,h,w,C] with C a multiple of 8, got {tuple(t.shape)}")
+    return t.shape
+
+
+def conv3x3_forward(act: torch.Tensor, Wf: torch.Tensor, bias: Optional[torch.Tensor], lrelu_slope: Optional[float] = None,
+                    dilation: int = 1, out_f32_nchw: bool = False) -> torch.Tensor:
+    """[LeakyReLU](conv3x3(act) + bias) with padding == dilation.  act bf16 NHWC [N,h,w,Ci]; returns bf16 NHWC [N,h,w,round8(Co)]
+    (requires Co % 8 == 0) or, with ``out_f32_nchw``, fp32 NCHW [N,Co,h,w]."""
+    lib = load()
+    N, h, w, pitch = _need_nhwc(act, "act")
+    _need(Wf, torch.bfloat16, "Wf")
+    Co, Ci = int(Wf.shape[1]), int(Wf.shape[2])
+    if Ci != pitch:
+        raise B200SegError(f"conv3x3_forward: activations have {pitch} channels, weights expect {Ci}")
+    if bias is not None:
+        _need(bias, torch.float32, "bias")
+    out_b = out_f = None
+    if out_f32_nchw:
+        out_f = torch.empty((N, Co, h, w), dtype=torch.float32, device=act.device)
+    else:
+        if Co % 8 != 0:
+            raise B200SegError(f"conv3x3_forward: bf16 NHWC output needs out_channels={Co} to be a multiple of 8")
+        out_b = torch.empty((N, h, w, Co), dtype=torch.bfloat16, device=act.device)
+    with torch.cuda.device(act.device):
+        _check(lib.b200seg_conv3x3_forward(act.data_ptr(), N, h, w, Ci, pitch, Wf.data_ptr(), Co, int(dilation), _ptr(bias),
+                                           0 if lrelu_slope is None else 1, 0.0 if lrelu_slope is None else float(lrelu_slope),
+                                           _ptr(out_b), Co, _ptr(out_f), _stream()))
+    return out_f if out_f32_nchw else out_b
+
+
+def conv3x3_dgrad(g: torch.Tensor, Wb: torch.Tensor, mask: Optional[torch.Tensor] = None, slope: float = 0.2, dilation: int = 1,
+                  out_f32_nchw: bool = False) -> torch.Tensor:
+    """Data gradient of conv3x3 (padding == dilation): g bf16 NHWC [N,h,w,round8(Co)], Wb bf16 [9,Ci,round8(Co)].  ``mask`` (bf16
+    NHWC [N,h,w,Ci], the saved LeakyReLU output of the layer below) fuses the activation's backward into the epilogue."""
+    lib = load()
+    N, h, w, gp = _need_nhwc(g, "g")
+    _need(Wb, torch.bfloat16, "Wb")
+    Ci, Cg = int(Wb.shape[1]), int(Wb.shape[2])
+    if Cg != gp:
+        raise B200SegError(f"conv3x3_dgrad: gradient has {gp} channels, Wb expects {Cg}")
+    out_b = out_f = None
+    if out_f32_nchw:
+        if mask is not None:
+            raise B200SegError("conv3x3_dgrad: the fused activation mask needs the bf16 NHWC output")
+        out_f = torch.empty((N, Ci, h, w), dtype=torch.float32, device=g.device)
+    else:
+        if Ci % 8 != 0:
+            raise B200SegError(f"conv3x3_dgrad: bf16 NHWC output needs in_channels={Ci} to be a multiple of 8")
+        out_b = torch.empty((N, h, w, Ci), dtype=torch.bfloat16, device=g.device)
+        if mask is not None and tuple(_need_nhwc(mask, "mask")) != (N, h, w, Ci):
+            raise B200SegError(f"conv3x3_dgrad: mask shape {tuple(mask.shape)} != {(N, h, w, Ci)}")
+    with torch.cuda.device(g.device):
+        _check(lib.b200seg_conv3x3_dgrad(g.data_ptr(), N, h, w, Cg, gp, Wb.data_ptr(), Ci, int(dilation), _ptr(mask), float(slope),
+                                         _ptr(out_b), Ci, _ptr(out_f), _stream()))
+    return out_f if out_f32_nchw else out_b
+
+
+def conv3x3_wgrad(g: torch.Tensor, x: torch.Tensor, parts: Sequence[int], dilation: int = 1, splits: int = 0,
+                  out: Optional[Sequence[Optional[torch.Tensor]]] = None):
+    """Weight gradients [parts[i],Ci,3,3] fp32 from the bf16 NHWC output gradient g [N,h,w,round8(sum parts)] and input x."""
+    lib = load()
+    N, h, w, gp = _need_nhwc(g, "g")
+    if tuple(_need_nhwc(x, "x"))[:3] != (N, h, w):
+        raise B200SegError("conv3x3_wgrad: g and x must share [N,h,w]")
+    Ci = int(x.shape[3])
+    Co = int(sum(parts))
+    if _round8(Co) != gp:
+        raise B200SegError(f"conv3x3_wgrad: gradient has {gp} channels, parts sum to {Co}")
+    nbytes = lib.b200seg_conv3x3_wgrad_scratch_bytes(N, h, w, Co, Ci, int(splits))
+    scratch = _scratch("conv_wgrad", nbytes, g.device)
+    if out is None:
+        out = [torch.empty((int(pc), Ci, 3, 3), dtype=torch.float32, device=g.device) for pc in parts]
+    for t, pc in zip(out, parts):
+        if t is not None and (tuple(_need(t, torch.float32, "grad_w").shape) != (int(pc), Ci, 3, 3)):
+            raise B200SegError("conv3x3_wgrad: bad output buffer shape")
+    with torch.cuda.device(g.device):
+        _check(lib.b200seg_conv3x3_wgrad(g.data_ptr(), Co, gp, x.data_ptr(), Ci, Ci, N, h, w, int(dilation), int(splits),
+                                         scratch.data_ptr(), nbytes, _ptr_array(out), (c_int * len(parts))(*[int(v) for v in parts]),
+                                         len(parts), _stream()))
+    return list(out)
+
+
+def nchw_to_nhwc_bf16(src: torch.Tensor, pitch: Optional[int] = None) -> torch.Tensor:
+    """fp32 NCHW [N,C,h,w] -> bf16 NHWC [N,h,w,pitch] (pitch = round8(C) by default; channels >= C are zero)."""
+    lib = load()
+    _need(src, torch.float32, "src")
+    N, C, h, w = src.shape
+    pitch = _round8(C) if pitch is None else int(pitch)
+    dst = torch.empty((N, h, w, pitch), dtype=torch.bfloat16, device=src.device)
+    with torch.cuda.device(src.device):
+        _check(lib.b200seg_nchw_to_nhwc_bf16(src.data_ptr(), N, C, h * w, dst.data_ptr(), pitch, _stream()))
+    return dst
+
+
+def nhwc_bf16_colsum(g: torch.Tensor, C: Optional[int] = None) -> torch.Tensor:
+    """out[c] = sum over pixels of g[..., c] (bias gradient), fp32 [C], deterministic."""
+    lib = load()
+    N, h, w, pitch = _need_nhwc(g, "g")
+    C = pitch if C is None else int(C)
+    nbytes = lib.b200seg_nhwc_colsum_scratch_bytes(pitch)
+    scratch = _scratch("colsum", nbytes, g.device)
+    out = torch.empty(C, dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        _check(lib.b200seg_nhwc_bf16_colsum(g.data_ptr(), N * h * w, C, pitch, scratch.data_ptr(), out.data_ptr(), _stream()))
+    return out
+
+
 def default_wgrad_splits(P: int, C: int, Cin: int, R: int) -> int:
     """Split-K factor for the weight-gradient GEMM: fill ~2 waves of SMs without oversplitting."""
     NJ = aspp_packed_rows(C, R)
@@ -501,7 +650,7 @@ def gemm_set_sharing(mode):
 
 PROFILE_TAGS = {"head_fwd_gemm": 0, "head_dgrad_gemm": 1, "head_wgrad_gemm": 2, "pack_features": 3, "head_gather": 4,
                 "grad_im2col": 5, "upsample_ce_main": 6, "eval_argmax_confusion": 7, "soft_ce_fwd": 8, "soft_ce_bwd": 9,
-                "wgrad_reduce": 10, "fada_softce_main": 11}
+                "wgrad_reduce": 10, "fada_softce_main": 11, "conv3x3_fwd": 12, "conv3x3_dgrad": 13, "conv3x3_wgrad": 14}
 
 
 def launch_count() -> int:

@@ -74,6 +74,17 @@ int aspp_backward(const float*, const void*, const void*, const int*, int, int, 
 long long k5_workspace_bytes(int, int, int, int, int, int);
 int k5_forward(const float*, const float*, int, int, int, int, int, int, float, float, int, int, void*, long long, float*, cudaStream_t);
 int k5_backward(const void*, int, int, int, int, int, int, const float*, const float*, float*, cudaStream_t);
+int conv3x3_pack_weights(const float* const*, const int*, int, int, void*, void*, int, cudaStream_t);
+int conv3x3_forward(const void*, int, int, int, int, long long, const void*, int, int, const float*, int, float, void*, long long, float*,
+                    cudaStream_t);
+int conv3x3_dgrad(const void*, int, int, int, int, long long, const void*, int, int, const void*, float, void*, long long, float*,
+                  cudaStream_t);
+long long conv3x3_wgrad_scratch_bytes(int, int, int, int, int, int);
+int conv3x3_wgrad(const void*, int, long long, const void*, int, long long, int, int, int, int, int, void*, long long, float* const*,
+                  const int*, int, cudaStream_t);
+int nchw_to_nhwc_bf16(const float*, int, int, int, void*, int, cudaStream_t);
+long long nhwc_colsum_scratch_bytes(int);
+int nhwc_bf16_colsum(const void*, long long, int, int, void*, float*, cudaStream_t);
 namespace gemm {
 int selftest(int, int, int, int, int, int, int, int, double*, double*);
 void set_sharing(int);
@@ -266,6 +277,51 @@ int b200seg_aspp_backward(const float* grad_logits, const void* Xp, const void* 
   REQUIRE_DEVICE();
   return aspp_backward(grad_logits, Xp, WpT, rates_host, R, N, Cin, C, h, w, scratch, scratch_bytes, splits, grad_x, grad_w, grad_b,
                        S(stream));
+}
+
+int b200seg_conv3x3_pack_weights(const float* const* weights, const int* part_co_host, int n_parts, int Ci, void* Wf, void* Wb,
+                                 int co_pitch, void* stream) {
+  REQUIRE_DEVICE();
+  return conv3x3_pack_weights(weights, part_co_host, n_parts, Ci, Wf, Wb, co_pitch, S(stream));
+}
+
+int b200seg_conv3x3_forward(const void* act, int N, int h, int w, int Ci, int64_t act_pitch, const void* Wf, int Co, int dilation,
+                            const float* bias, int lrelu, float slope, void* out_bf16_nhwc, int64_t out_pitch, float* out_f32_nchw,
+                            void* stream) {
+  REQUIRE_DEVICE();
+  return conv3x3_forward(act, N, h, w, Ci, act_pitch, Wf, Co, dilation, bias, lrelu, slope, out_bf16_nhwc, out_pitch, out_f32_nchw,
+                         S(stream));
+}
+
+int b200seg_conv3x3_dgrad(const void* g, int N, int h, int w, int Cg, int64_t g_pitch, const void* Wb, int Ci, int dilation,
+                          const void* mask, float slope, void* out_bf16_nhwc, int64_t out_pitch, float* out_f32_nchw, void* stream) {
+  REQUIRE_DEVICE();
+  return conv3x3_dgrad(g, N, h, w, Cg, g_pitch, Wb, Ci, dilation, mask, slope, out_bf16_nhwc, out_pitch, out_f32_nchw, S(stream));
+}
+
+int64_t b200seg_conv3x3_wgrad_scratch_bytes(int N, int h, int w, int Co, int Ci, int splits) {
+  if (N <= 0 || h <= 0 || w <= 0 || Co <= 0 || Ci <= 0) return 0;
+  return conv3x3_wgrad_scratch_bytes(N, h, w, Co, Ci, splits);
+}
+
+int b200seg_conv3x3_wgrad(const void* g, int Co, int64_t g_pitch, const void* x, int Ci, int64_t x_pitch, int N, int h, int w,
+                          int dilation, int splits, void* scratch, int64_t scratch_bytes, float* const* grad_w,
+                          const int* part_co_host, int n_parts, void* stream) {
+  REQUIRE_DEVICE();
+  return conv3x3_wgrad(g, Co, g_pitch, x, Ci, x_pitch, N, h, w, dilation, splits, scratch, scratch_bytes, grad_w, part_co_host,
+                       n_parts, S(stream));
+}
+
+int b200seg_nchw_to_nhwc_bf16(const float* src, int N, int C, int hw, void* dst, int pitch, void* stream) {
+  REQUIRE_DEVICE();
+  return nchw_to_nhwc_bf16(src, N, C, hw, dst, pitch, S(stream));
+}
+
+int64_t b200seg_nhwc_colsum_scratch_bytes(int pitch) { return pitch > 0 ? nhwc_colsum_scratch_bytes(pitch) : 0; }
+
+int b200seg_nhwc_bf16_colsum(const void* g, int64_t P, int C, int pitch, void* scratch, float* out, void* stream) {
+  REQUIRE_DEVICE();
+  return nhwc_bf16_colsum(g, P, C, pitch, scratch, out, S(stream));
 }
 
 long long b200seg_launch_count(void) { return g_launches; }

@@ -465,6 +465,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 // Host side (gemm_sm100.cu)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn();            // cuTensorMapEncodeTiled through the runtime's driver entry point (nullptr if unavailable)
+
 struct Operand {
   const __nv_bfloat16* ptr;
   bool mn_major;        // false: [rows][K] K contiguous; true: [K][rows] rows contiguous

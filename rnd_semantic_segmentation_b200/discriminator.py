@@ -1,9 +1,11 @@
 """PixelDiscriminator -- drop-in for core/models/discriminator.py:31-50.
 
 Parameter owners and state_dict keys (``D.0``, ``D.2``, ``cls1``, ``cls2``) are identical to the
-reference.  The three 3x3 conv layers stay on the library path ("next"); what
-is ours is the tail -- cat + align-corners upsample (+ the soft-label loss, see
-``forward_soft_loss``).
+reference (real ``nn.Conv2d`` children, created in the same order with the default init).  The
+arithmetic is NOT cuDNN: the three 3x3 layers run as tcgen05 implicit GEMMs on bf16 NHWC activations
+with bias / LeakyReLU / LeakyReLU-backward fused into the epilogues (csrc/conv_sm100.cu, SURVEY.md
+section 8f rank 1), cls1 | cls2 as ONE layer with 2C outputs written as fp32 NCHW; then the tail --
+align-corners upsample, or the fused soft-label loss (``forward_soft_loss``).
 """
 from __future__ import annotations
 
@@ -24,9 +26,27 @@ class PixelDiscriminator(nn.Module):
         self.cls1 = nn.Conv2d(ndf // 2, num_classes, kernel_size=3, stride=1, padding=1)
         self.cls2 = nn.Conv2d(ndf // 2, num_classes, kernel_size=3, stride=1, padding=1)
 
+        self._packed = None
+        self._packed_key = None
+
+    def _params(self):
+        return [self.D[0].weight, self.D[0].bias, self.D[2].weight, self.D[2].bias,
+                self.cls1.weight, self.cls1.bias, self.cls2.weight, self.cls2.bias]
+
+    def _packed_weights(self):
+        """bf16 packed weights of the three layers, re-packed only when a parameter changed."""
+        params = self._params()
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._packed is None or key != self._packed_key:
+            w1, _, w2, _, wc1, bc1, wc2, bc2 = params
+            self._packed = ops.pack_discriminator_weights(w1, w2, wc1, wc2, bc1, bc2)
+            self._packed_key = key
+        return self._packed
+
     def logits(self, x):
-        mid = self.D(x)
-        return torch.cat((self.cls1(mid), self.cls2(mid)), dim=1)       # discriminator.py:45-47
+        """Low-resolution logits [N,2C,h,w] = cat(cls1(D(x)), cls2(D(x)))  (discriminator.py:45-47)."""
+        return ops.pixel_discriminator_logits(x, *self._params(), slope=self.D[1].negative_slope,
+                                              packed=self._packed_weights())
 
     def forward(self, x, size=None):
         out = self.logits(x)

@@ -355,6 +355,131 @@ def test_eval_dropin_against_reference_golden(lib, golden):
     np.testing.assert_allclose(meter.f1_sum, g["meter_f1_sum"], rtol=1e-6)
 
 
+# ------------------------------------------------------------------ K6: 3x3 conv layers as tcgen05 implicit GEMMs
+def _nhwc_bf16(t):
+    return t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+
+
+def _nchw(t_nhwc, C=None):
+    t = t_nhwc.float().cpu().permute(0, 3, 1, 2)
+    return t if C is None else t[:, :C]
+
+
+@pytest.mark.parametrize("n,ci,co,h,w,dil", [
+    (2, 128, 256, 64, 128, 1),     # one 1 x 128 rectangle per image row, exact tiles
+    (1, 256, 128, 33, 65, 1),      # ragged 8 x 16 rectangles, half-empty N tile
+    (2, 64, 40, 9, 11, 1),         # tiny image, Co = 40 (the 2C = 38 -> 40 class of the cls layer)
+    (1, 24, 16, 20, 27, 1),        # Ci < one 64-channel k-block (TMA zero-fills the rest)
+    (1, 192, 64, 17, 40, 2),       # dilation 2 (padding 2)
+])
+def test_conv3x3_layer_forward_dgrad_wgrad(lib, n, ci, co, h, w, dil):
+    g = torch.Generator().manual_seed(100 + h + ci)
+    x = bf16_round(torch.randn(n, ci, h, w, generator=g))
+    wt = bf16_round(torch.randn(co, ci, 3, 3, generator=g) * 0.05)
+    b = torch.randn(co, generator=g) * 0.1
+    go = bf16_round(torch.randn(n, co, h, w, generator=g))
+    xd, wd = x.double().requires_grad_(True), wt.double().requires_grad_(True)
+    z = F.conv2d(xd, wd, b.double(), padding=dil, dilation=dil)
+    gx_want, gw_want = torch.autograd.grad(z, (xd, wd), go.double())
+    Wf, Wb = lib.conv3x3_pack_weights([wt.cuda()])
+    xq, gq = _nhwc_bf16(x), _nhwc_bf16(go)
+    # forward: fp32 NCHW (exact up to accumulation order) and bf16 NHWC with the fused LeakyReLU (one bf16 rounding)
+    out_f = lib.conv3x3_forward(xq, Wf, b.cuda(), None, dilation=dil, out_f32_nchw=True)
+    assert rel_err(out_f, z) <= TOL
+    out_b = lib.conv3x3_forward(xq, Wf, b.cuda(), 0.2, dilation=dil)
+    assert rel_err(_nchw(out_b), F.leaky_relu(z, 0.2)) <= 2.0 ** -8
+    assert rel_err(_nchw(lib.conv3x3_forward(xq, Wf, None, None, dilation=dil)), z - b.double().view(1, -1, 1, 1)) <= 2.0 ** -8
+    # data gradient: fp32 NCHW, and bf16 NHWC with the LeakyReLU' mask of a saved activation
+    assert rel_err(lib.conv3x3_dgrad(gq, Wb, dilation=dil, out_f32_nchw=True), gx_want) <= TOL
+    mask_src = torch.randn(n, ci, h, w, generator=g)
+    mask_src[0, 0, 0, :3] = 0.0                                     # LeakyReLU'(0) = slope
+    got = lib.conv3x3_dgrad(gq, Wb, mask=_nhwc_bf16(mask_src), slope=0.2, dilation=dil)
+    assert rel_err(_nchw(got), gx_want * torch.where(bf16_round(mask_src) > 0, 1.0, 0.2)) <= 2.0 ** -8
+    # weight gradient (split-K chosen by the library, and forced to 1 / 3 splits); bias gradient
+    for splits in (0, 1, 3):
+        gw, = lib.conv3x3_wgrad(gq, xq, [co], dilation=dil, splits=splits)
+        assert rel_err(gw, gw_want) <= TOL, f"splits={splits}"
+    assert rel_err(lib.nhwc_bf16_colsum(gq), go.double().sum((0, 2, 3))) <= 1e-5
+    a, bb = lib.nhwc_bf16_colsum(gq), lib.nhwc_bf16_colsum(gq)
+    assert torch.equal(a, bb)                                       # deterministic
+
+
+def test_conv3x3_concatenated_parts_and_nchw_pack(lib):
+    """cls1 | cls2 as one layer: two [C,Ci,3,3] tensors packed side by side, 2C = 38 padded to 40 in the gradient operand."""
+    g = torch.Generator().manual_seed(7)
+    C, ci, n, h, w = 19, 128, 2, 12, 20
+    w1, w2 = (bf16_round(torch.randn(C, ci, 3, 3, generator=g) * 0.05) for _ in range(2))
+    x = bf16_round(torch.randn(n, ci, h, w, generator=g))
+    go = torch.randn(n, 2 * C, h, w, generator=g)
+    Wf, Wb = lib.conv3x3_pack_weights([w1.cuda(), w2.cuda()])
+    assert tuple(Wf.shape) == (9, 38, ci) and tuple(Wb.shape) == (9, ci, 40)
+    xd = x.double().requires_grad_(True)
+    wd = [t.double().requires_grad_(True) for t in (w1, w2)]
+    z = torch.cat([F.conv2d(xd, t, padding=1) for t in wd], 1)
+    out = lib.conv3x3_forward(_nhwc_bf16(x), Wf, None, None, out_f32_nchw=True)
+    assert rel_err(out, z) <= TOL
+    G = lib.nchw_to_nhwc_bf16(go.cuda())
+    assert tuple(G.shape) == (n, h, w, 40) and float(G[..., 38:].abs().max()) == 0.0
+    assert torch.equal(_nchw(G, 38), bf16_round(go))
+    gx_want, g1_want, g2_want = torch.autograd.grad(z, (xd, *wd), bf16_round(go).double())
+    assert rel_err(lib.conv3x3_dgrad(G, Wb, out_f32_nchw=True), gx_want) <= TOL
+    g1, g2 = lib.conv3x3_wgrad(G, _nhwc_bf16(x), [C, C])
+    assert rel_err(g1, g1_want) <= TOL and rel_err(g2, g2_want) <= TOL
+    assert rel_err(lib.nhwc_bf16_colsum(G, 38), bf16_round(go).double().sum((0, 2, 3))) <= 1e-5
+
+
+@pytest.mark.parametrize("n,cin,ndf,C,h,w", [(2, 256, 64, 19, 33, 65), (1, 2048, 256, 19, 32, 64), (2, 64, 32, 2, 44, 44), (1, 24, 16, 3, 20, 27)])
+def test_discriminator_stack_forward_backward(lib, n, cin, ndf, C, h, w):
+    """PixelDiscriminator.logits / backward (tcgen05 conv stack) against the oracle module applying the same bf16 roundings.
+    Every single layer meets 1e-3 (test_conv3x3_layer_*).  Through the CHAIN the bar is 3e-3: an fp32-vs-fp64 accumulation
+    difference of ~1e-6 relative flips the bf16 rounding of about one stored activation in a thousand by one ulp (2^-8), and
+    those flips propagate through the next layers -- the floor of any comparison across bf16-stored activations."""
+    STACK_TOL = 3e-3
+    import copy
+    import rnd_semantic_segmentation_b200 as b200
+    from helpers import discriminator_bf16_oracle
+    torch.manual_seed(40 + C)
+    ref = to.PixelDiscriminatorOracle(cin, ndf, num_classes=C)
+    torch.manual_seed(40 + C)
+    ours = b200.PixelDiscriminator(cin, ndf, num_classes=C)
+    for (ka, va), (kb, vb) in zip(ref.state_dict().items(), ours.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb)
+    ours.cuda()
+    g = torch.Generator().manual_seed(41 + h)
+    x = torch.relu(torch.randn(n, cin, h, w, generator=g))
+    go = torch.randn(n, 2 * C, h, w, generator=g) * 1e-3
+    xc = x.cuda().requires_grad_(True)
+    got = ours(xc)
+    assert tuple(got.shape) == (n, 2 * C, h, w)
+    # the sign masks of the stored activations (recomputed through the same layer calls)
+    with torch.no_grad():
+        (Wf1, _), (Wf2, _), _, _ = ours._packed_weights()
+        A1 = lib.conv3x3_forward(_nhwc_bf16(x), Wf1, ours.D[0].bias.detach(), 0.2)
+        A2 = lib.conv3x3_forward(A1, Wf2, ours.D[2].bias.detach(), 0.2)
+    masks = (_nchw(A1) > 0, _nchw(A2) > 0)
+    refd = copy.deepcopy(ref).double()
+    xr = x.double().requires_grad_(True)
+    want = discriminator_bf16_oracle(refd, xr, masks)
+    assert rel_err(got, want) <= STACK_TOL
+    print("D logits rel err vs same-rounding oracle:", rel_err(got, want), " vs fp32 reference module:", rel_err(got, ref(x)))
+    assert rel_err(got, ref(x)) <= 2e-2
+    want.backward(go.double())
+    got.backward(go.cuda())
+    assert rel_err(xc.grad, xr.grad) <= STACK_TOL
+    for (name, p_ref), (_, p_ours) in zip(refd.named_parameters(), ours.named_parameters()):
+        assert rel_err(p_ours.grad, p_ref.grad) <= STACK_TOL, name
+    # weights-only backward (the discriminator's own update on detached features, aspp_fada.py:119-125) and determinism
+    ours.zero_grad()
+    out2 = ours(x.cuda())
+    out2.backward(go.cuda())
+    g_first = [p.grad.clone() for p in ours.parameters()]
+    for p_ours, (name, p_ref) in zip(ours.parameters(), refd.named_parameters()):
+        assert rel_err(p_ours.grad, p_ref.grad) <= STACK_TOL, name
+    ours.zero_grad()
+    ours(x.cuda()).backward(go.cuda())
+    assert all(torch.equal(a, p.grad) for a, p in zip(g_first, ours.parameters()))
+
+
 def test_discriminator_tail_and_soft_ce_golden(lib, golden):
     import rnd_semantic_segmentation_b200 as b200
     g = golden("discriminator")
@@ -364,13 +489,16 @@ def test_discriminator_tail_and_soft_ce_golden(lib, golden):
     D.cuda()
     x = torch.from_numpy(g["x"]).cuda()
     out_hr = D(x, (20, 27))
-    assert rel_err(out_hr, torch.from_numpy(g["out_hr"])) <= TOL      # cuDNN convs (TF32 off by default) + our upsample
+    # tcgen05 conv stack with bf16 operands / activations against the reference's fp32 fixture: the bf16 rounding of three
+    # chained layers bounds this comparison (the same-rounding oracle comparison at 1e-3 is test_discriminator_stack_*)
+    print("D(x, size) rel err vs the reference's fp32 golden:", rel_err(out_hr, torch.from_numpy(g["out_hr"])))
+    assert rel_err(out_hr, torch.from_numpy(g["out_hr"])) <= 1e-2
     soft = torch.from_numpy(g["soft"]).cuda()
     q0 = torch.cat((soft, torch.zeros_like(soft)), 1)
     loss = b200.soft_label_cross_entropy(out_hr, q0)
-    assert abs(loss.item() - float(g["loss_slot0"])) <= TOL * float(g["loss_slot0"])
+    assert abs(loss.item() - float(g["loss_slot0"])) <= 5e-3 * float(g["loss_slot0"])
     gw, = torch.autograd.grad(loss, D.cls1.weight)
-    assert rel_err(gw, torch.from_numpy(g["grad_cls1_weight_slot0"])) <= TOL
+    assert rel_err(gw, torch.from_numpy(g["grad_cls1_weight_slot0"])) <= 1e-2
 
 
 def test_full_size_properties_config1(lib):
