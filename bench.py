@@ -184,6 +184,9 @@ def run_ours(args):
     _lib.load()
 
     n, cin, h, w, H, W, C = synth.WORKLOADS[args.workload]
+    # the loops below feed the SAME synthetic feature tensor every step; the cross-module conversion cache would turn the
+    # per-step fp32 -> bf16 feature pack into a hit, i.e. skip work a real iteration (new features every step) performs
+    b200.set_feature_pack_cache(0)
     torch.manual_seed(1234)
     head = b200.ASPP_Classifier_V2(cin, RATES, RATES, C).to(dev)
     x = synth.make_features(n, cin, h, w, seed=1234 + rank, device=dev)
@@ -357,6 +360,9 @@ def run_ours(args):
                                                "shape_lowres": [an, 2 * aC, ah, aw], "size": [aH, aW],
                                                "note": "compute-bound: only low-resolution tensors are read"}}
 
+    del d_lr, s_lr
+    adv = run_adv_step(b200, _lib, synth, dev, rank, world, peaks, args)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = run_cpu_reference(args.workload, steps=2, warmup=1)["cpu_baseline"]
@@ -371,12 +377,78 @@ def run_ours(args):
                            "l2": "inputs larger than L2 (features %d MB per step)" % (x.numel() * 4 // 2 ** 20),
                            "parallelism": "dp%d (batch sharded by image)" % world},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_timed), "roofline": roofline, "eval": eval_obj,
-                "seam_bf16_nhwc": seam, "aux_kernels": aux}
+                "seam_bf16_nhwc": seam, "aux_kernels": aux, "adv_step": adv}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         emit(line)
     if dist.is_initialized():
         dist.destroy_process_group()
+
+
+def run_adv_step(b200, _lib, synth, dev, rank, world, peaks, args):
+    """BASELINE.json configs[2] (deeplabv2_r101_adv): everything after the backbone of one FADA iteration, aspp_fada.py:91-125 --
+    head fwd + CE fwd/bwd on the source batch, head fwd on the target batch, and three PixelDiscriminator passes with their
+    soft-label losses (adversarial: gradient to the target features; discriminator update: weight gradients on detached
+    features).  Optimizer steps excluded.  The discriminator convolutions run on the tcgen05 implicit-GEMM kernel (K6)."""
+    an, cin, ah, aw, aH, aW, aC = synth.WORKLOADS["deeplabv2_r101_adv"]
+    torch.manual_seed(4321)
+    head = b200.ASPP_Classifier_V2(cin, RATES, RATES, aC).to(dev)
+    model_D = b200.PixelDiscriminator(cin, 256, num_classes=aC).to(dev)
+    src = synth.make_features(an, cin, ah, aw, seed=555 + rank, device=dev)
+    tgt = synth.make_features(an, cin, ah, aw, seed=777 + rank, device=dev)
+    lab = synth.make_labels(an, aH, aW, aC, seed=555 + rank, device=dev)
+    size = (aH, aW)
+    b200.set_feature_pack_cache(2)
+
+    def adv_step():
+        b200.clear_feature_pack_cache()                       # new features every iteration: 2 conversions per step, not 0
+        for p in list(head.parameters()) + list(model_D.parameters()):
+            p.grad = None
+        src_fea = src.detach().requires_grad_(True)
+        tgt_fea = tgt.detach().requires_grad_(True)
+        loss_seg, src_lr = head.forward_loss(src_fea, lab, temperature=1.8)              # aspp_fada.py:91-96
+        loss_seg.backward()
+        with torch.no_grad():
+            tgt_lr = head.logits(tgt_fea)                                                # :101-104 (soft labels are detached)
+        loss_adv = 0.001 * model_D.forward_soft_loss(tgt_fea, tgt_lr, size, slot=0)      # :110-112
+        loss_adv.backward()
+        for p in model_D.parameters():                                                   # optimizer_D.zero_grad(), :117
+            p.grad = None
+        loss_d_src = 0.5 * model_D.forward_soft_loss(src_fea.detach(), src_lr, size, slot=0)   # :119-121
+        loss_d_src.backward()
+        loss_d_tgt = 0.5 * model_D.forward_soft_loss(tgt_fea.detach(), tgt_lr, size, slot=1)   # :123-125
+        loss_d_tgt.backward()
+        return loss_seg, loss_adv, loss_d_src, loss_d_tgt
+
+    l0 = _lib.launch_count()
+    ms, _ = timed(adv_step, args.steps, args.warmup)
+    launches = (_lib.launch_count() - l0) * args.steps // (args.steps + args.warmup)
+    ms_step = ms / args.steps
+    _lib.profile_enable(True)
+    for _ in range(4):
+        adv_step()
+    torch.cuda.synchronize()
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    b200.set_feature_pack_cache(0)
+    P = an * ah * aw
+    # algorithmic FLOPs of one discriminator conv-stack pass (true channel counts, dense 3x3 taps)
+    f_pass = 2.0 * 9 * P * (cin * 256 + 256 * 128 + 128 * 2 * aC)
+    conv_names = ("conv3x3_fwd", "conv3x3_dgrad", "conv3x3_wgrad")
+    conv_ms = sum(prof[k][0] for k in conv_names if k in prof) / 4
+    # per step: 3 forward passes, 3 weight-gradient passes, 3 data-gradient passes of layers 3/2 and one of layer 1
+    f_step = f_pass * 6 + 2.0 * 9 * P * (3 * (256 * 128 + 128 * 2 * aC) + cin * 256)
+    tf = f_step / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    return {"metric": "fada_adv_step_Mpx_per_s", "value": round(world * 2 * an * aH * aW / (ms_step * 1e-3) / 1e6, 2), "unit": "Mpx/s",
+            "ms_per_step": round(ms_step, 4), "gpu_launches": int(launches),
+            "config": {"workload": "deeplabv2_r101_adv", "features_per_domain": [an, cin, ah, aw], "labels": [an, aH, aW],
+                       "num_classes": aC, "discriminator": "PixelDiscriminator(2048, ndf=256) -> 2 x 19",
+                       "step": "aspp_fada.py:91-125 after the backbone, optimizer steps excluded; source + target label pixels counted"},
+            "roofline": {"kernel": "conv_gemm_kernel (tcgen05 implicit GEMM; discriminator fwd / dgrad / wgrad launches)", "bound": "tensor",
+                         "achieved": round(tf, 1), "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": round(tf / peaks["bf16_tflops_sustained"], 4), "traffic": load_traffic("conv3x3_fwd"),
+                         "algorithmic_flops_per_step": f_step, "conv_ms_per_step": round(conv_ms, 4)},
+            "kernels": {k: {"ms_per_step": round(v[0] / 4, 4), "launches_per_step": v[1] / 4} for k, v in prof.items()}}
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -9,7 +9,7 @@ from .build import build_adversarial_discriminator, build_classifier, build_feat
 from .classifier import ASPP_Classifier_V2
 from .discriminator import PixelDiscriminator
 from .install import install
-from .ops import (aspp_head, aspp_head_loss, fada_soft_label_loss, soft_label_cross_entropy, upsample_bilinear_align_corners, upsample_cross_entropy)
+from .ops import (aspp_head, aspp_head_loss, clear_feature_pack_cache, fada_soft_label_loss, set_feature_pack_cache, soft_label_cross_entropy, upsample_bilinear_align_corners, upsample_cross_entropy)
 from .utility import (AverageMeter, confusion_matrix, inference, intersectionAndUnion, intersectionAndUnionGPU,
                       iutr_from_confusion, segmentation_eval_step)
 

@@ -11,6 +11,26 @@ from . import _lib
 # --------------------------------------------------------------------------------------------
 # K1  fused multi-dilation ASPP head
 # --------------------------------------------------------------------------------------------
+# The same feature tensor is consumed by several modules per iteration (FADA: classifier(tgt_fea) and model_D(tgt_fea),
+# classifier(src_fea) and model_D(src_fea.detach()), aspp_fada.py:91-123), and each would convert it to the bf16 pixel-major
+# GEMM operand again (an HBM pass of 12 B per element).  A small LRU keeps the last conversions.  An entry holds a reference
+# to the source storage (through a detached alias), so its address cannot be handed to another tensor while the entry lives,
+# and it is keyed on the version counter, so any in-place update through torch invalidates it.
+_PACK_CACHE_SLOTS = 2
+_pack_cache = []            # [(key, source alias, Xp)]
+
+
+def set_feature_pack_cache(slots: int):
+    """Number of converted feature tensors kept (0 disables the cache and drops the entries)."""
+    global _PACK_CACHE_SLOTS
+    _PACK_CACHE_SLOTS = max(0, int(slots))
+    del _pack_cache[_PACK_CACHE_SLOTS:]
+
+
+def clear_feature_pack_cache():
+    del _pack_cache[:]
+
+
 def _pixel_major_bf16(x: torch.Tensor) -> torch.Tensor:
     """[N,Cin,h,w] -> bf16 [N*h*w, Cin].  bf16 channels_last input is taken zero-copy."""
     if not x.is_cuda:
@@ -23,7 +43,18 @@ def _pixel_major_bf16(x: torch.Tensor) -> torch.Tensor:
         return xl.reshape(N * h * w, Cin)
     if x.dtype != torch.float32:
         x = x.float()
-    return _lib.aspp_pack_features(x.contiguous())
+    x = x.contiguous()
+    if _PACK_CACHE_SLOTS <= 0:
+        return _lib.aspp_pack_features(x)
+    key = (x.data_ptr(), x._version, tuple(x.shape), x.device.index, torch.cuda.current_stream(x.device).cuda_stream)
+    for i, (k, _, Xp) in enumerate(_pack_cache):
+        if k == key:
+            _pack_cache.insert(0, _pack_cache.pop(i))
+            return Xp
+    Xp = _lib.aspp_pack_features(x)
+    _pack_cache.insert(0, (key, x.detach(), Xp))
+    del _pack_cache[_PACK_CACHE_SLOTS:]
+    return Xp
 
 
 class _AsppHeadFn(torch.autograd.Function):
