@@ -933,40 +933,47 @@ __global__ void __launch_bounds__(256) k5_finalize_loss(const float* loss_part, 
   }
 }
 
-// grad_d[n,k,i,j] = grad_out / (N*H*W) * sum over the tiles touching (i,j) of their partial block (any channel count)
-__global__ void __launch_bounds__(128) k5_finalize_grad(const K2Geom g, const float* blocks, const float* loss_out2,
-                                                        const float* grad_out, float* grad) {
+// grad_d[n,k,i,j] = grad_out / (N*H*W) * sum over the tiles touching (i,j) of their partial block (any channel count).
+// blockIdx.z = image * nchunk + channel chunk: a thread owns K5F_CC channels of one low-res pixel in registers, so the
+// (strided) partial-block reads of a pixel are all in flight at once instead of one dependent load per channel.
+constexpr int K5F_CC = 20;
+__global__ void __launch_bounds__(128) k5_finalize_grad(const K2Geom g, const float* __restrict__ blocks, const float* loss_out2,
+                                                        const float* grad_out, float* __restrict__ grad, int nchunk) {
   const int j = blockIdx.x * 128 + threadIdx.x;
   const int i = blockIdx.y;
-  const int n = blockIdx.z;
+  const int n = blockIdx.z / nchunk;
+  const int c0 = (blockIdx.z - n * nchunk) * K5F_CC;
   if (j >= g.w) return;
+  const int nc = min(K5F_CC, g.C - c0);
   const float scale = (grad_out ? grad_out[0] : 1.f) / loss_out2[1];
   const long long blk_floats = (long long)g.ispan_max * g.jspan_max * g.C;
   const long long hw = (long long)g.h * g.w;
-  float* dst = grad + (long long)n * g.C * hw + (long long)i * g.w + j;
+  float acc[K5F_CC];
+#pragma unroll
+  for (int c = 0; c < K5F_CC; ++c) acc[c] = 0.f;
   const int ya = ac_first_dst(g.scale_h, i - 1, g.h, g.H), yb = ac_first_dst(g.scale_h, i + 1, g.h, g.H);
   const int xa = ac_first_dst(g.scale_w, j - 1, g.w, g.W), xb = ac_first_dst(g.scale_w, j + 1, g.w, g.W);
-  const float* src[4];
-  int ns = 0;
   if (ya < yb && xa < xb) {
     const int ty0 = ya / K2_TILE_H, ty1 = (yb - 1) / K2_TILE_H;
     const int tx0 = xa / K2_TILE_W, tx1 = (xb - 1) / K2_TILE_W;
-    for (int ty = ty0; ty <= ty1 && ns < 4; ++ty) {
+    for (int ty = ty0; ty <= ty1; ++ty) {                         // same tile order as before: identical sums
       const int li = i - (int)(g.scale_h * (float)(ty * K2_TILE_H));
       if (li < 0 || li >= g.ispan_max) continue;
-      for (int tx = tx0; tx <= tx1 && ns < 4; ++tx) {
+      for (int tx = tx0; tx <= tx1; ++tx) {
         const int lj = j - (int)(g.scale_w * (float)(tx * K2_TILE_W));
         if (lj < 0 || lj >= g.jspan_max) continue;
         const long long tile = ((long long)n * g.tiles_y + ty) * g.tiles_x + tx;
-        src[ns++] = blocks + tile * blk_floats + ((long long)li * g.jspan_max + lj) * g.C;
+        const float* src = blocks + tile * blk_floats + ((long long)li * g.jspan_max + lj) * g.C + c0;
+#pragma unroll
+        for (int c = 0; c < K5F_CC; ++c)
+          if (c < nc) acc[c] += src[c];
       }
     }
   }
-  for (int c = 0; c < g.C; ++c) {
-    float acc = 0.f;
-    for (int q = 0; q < ns; ++q) acc += src[q][c];
-    dst[c * hw] = acc * scale;
-  }
+  float* dst = grad + ((long long)n * g.C + c0) * hw + (long long)i * g.w + j;
+#pragma unroll
+  for (int c = 0; c < K5F_CC; ++c)
+    if (c < nc) dst[c * hw] = acc[c] * scale;
 }
 
 long long k5_workspace_bytes(int N, int C, int h, int w, int H, int W) {
@@ -1031,8 +1038,9 @@ int k5_backward(const void* workspace, int N, int C, int h, int w, int H, int W,
   k2_geometry(g, N, 2 * C, h, w, H, W);
   const long long tiles = k2_tiles(g);
   const float* blocks = reinterpret_cast<const float*>(workspace) + tiles;
-  dim3 grid(ceil_div(w, 128), h, N);
-  k5_finalize_grad<<<grid, 128, 0, stream>>>(g, blocks, loss_out2, grad_out, grad_d);
+  const int nchunk = ceil_div(g.C, K5F_CC);
+  dim3 grid(ceil_div(w, 128), h, N * nchunk);
+  k5_finalize_grad<<<grid, 128, 0, stream>>>(g, blocks, loss_out2, grad_out, grad_d, nchunk);
   B200SEG_LAUNCH_CHECK();
   return B200SEG_OK;
 }

@@ -36,7 +36,13 @@ namespace conv {
 constexpr int MAX_T = 9;
 constexpr int MODE_CONV = 0, MODE_WGRAD = 1;
 constexpr int OUT_BF16_NHWC = 0, OUT_F32_NCHW = 1;
-constexpr int CONV_SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256;
+// BN = accumulator columns per tile: 256, or 128 for layers with <= 128 output channels (half the MMA work of a padded 256)
+template <int BN> struct Cfg {
+  static constexpr int B_BYTES_T = BN * BLOCK_K * 2;
+  static constexpr int STAGE_T = A_BYTES + B_BYTES_T;
+  static constexpr int NSTAGE = BN == 256 ? 4 : 6;
+  static constexpr int SMEM = 1024 + NSTAGE * STAGE_T + 256;
+};
 
 struct ConvParams {
   int N, h, w;
@@ -107,13 +113,15 @@ __device__ __forceinline__ Unit decode_unit(const ConvParams& p, int unit) {
   return u;
 }
 
-template <int MODE>
+template <int MODE, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
+  constexpr int STAGES = Cfg<BN>::NSTAGE, STAGE_BYTES = Cfg<BN>::STAGE_T;      // shadow the 256-column constants of gemm::
+  constexpr int BLOCK_N = BN;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
@@ -379,16 +387,16 @@ static void fill_taps(ConvParams& p, int dilation, int sign) {
 
 static int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
 
-template <int MODE>
+template <int MODE, int BN>
 static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    B200SEG_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM_BYTES));
+    B200SEG_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
     configured = true;
   }
   const int sms = num_sms();
   const int grid = p.units < sms ? p.units : sms;
-  conv_gemm_kernel<MODE><<<grid, NUM_THREADS, CONV_SMEM_BYTES, stream>>>(ta, tb, p);
+  conv_gemm_kernel<MODE, BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM, stream>>>(ta, tb, p);
   B200SEG_LAUNCH_CHECK();
   return B200SEG_OK;
 }
@@ -414,8 +422,9 @@ int conv3x3_run(const void* act, int N, int h, int w, int Ck, long long act_pitc
   fill_taps(p, dilation, sign);
   p.KC = ceil_div(Ck, BLOCK_K);
   p.Co = Co; p.Ci = 0;
+  const int BN = Co <= 128 ? 128 : 256;
   p.m_tiles = N * p.tiles_x * p.tiles_y;
-  p.n_tiles = ceil_div(Co, BLOCK_N);
+  p.n_tiles = ceil_div(Co, BN);
   p.units = p.m_tiles * p.n_tiles;
   p.splits = 1;
   p.kb_total = p.T * p.KC;
@@ -430,12 +439,12 @@ int conv3x3_run(const void* act, int N, int h, int w, int Ck, long long act_pitc
   {
     cuuint64_t gdim[3] = {(cuuint64_t)Ck, (cuuint64_t)Co, (cuuint64_t)p.T};
     cuuint64_t gstr[2] = {(cuuint64_t)Ck * 2, (cuuint64_t)Ck * 2 * Co};
-    cuuint32_t box[3] = {64, (cuuint32_t)BLOCK_N, 1};
+    cuuint32_t box[3] = {64, (cuuint32_t)BN, 1};
     rc = make_tmap_nd(&tb, wt, 3, gdim, gstr, box);
     if (rc) return rc;
   }
   profile_begin(prof_tag, stream);
-  rc = launch_conv<MODE_CONV>(ta, tb, p, stream);
+  rc = BN == 128 ? launch_conv<MODE_CONV, 128>(ta, tb, p, stream) : launch_conv<MODE_CONV, 256>(ta, tb, p, stream);
   profile_end(prof_tag, stream);
   return rc;
 }
@@ -444,7 +453,7 @@ int conv3x3_wgrad_splits(int N, int h, int w, int Co, int Ci) {
   int TW = 64, TH = 1;
   pick_rect(h, w, BLOCK_K, &TW, &TH);
   const int kb_total = N * ceil_div(w, TW) * ceil_div(h, TH);
-  const int units = 9 * ceil_div(Co, BLOCK_M) * ceil_div(Ci, BLOCK_N);
+  const int units = 9 * ceil_div(Co, BLOCK_M) * ceil_div(Ci, Ci <= 128 ? 128 : 256);
   int s = num_sms() / units;
   if (s < 1) s = 1;
   if (s > kb_total) s = kb_total;
@@ -467,8 +476,9 @@ int conv3x3_wgrad_run(const void* g, int Co, long long g_pitch, const void* x, i
   fill_taps(p, dilation, 1);
   p.KC = 0;
   p.Co = Co; p.Ci = Ci;
+  const int BN = Ci <= 128 ? 128 : 256;
   p.m_tiles = ceil_div(Co, BLOCK_M);
-  p.n_tiles = ceil_div(Ci, BLOCK_N);
+  p.n_tiles = ceil_div(Ci, BN);
   p.kb_total = N * p.tiles_x * p.tiles_y;
   if (splits < 1) splits = 1;
   if (splits > p.kb_total) splits = p.kb_total;
@@ -486,7 +496,7 @@ int conv3x3_wgrad_run(const void* g, int Co, long long g_pitch, const void* x, i
   rc = make_act_tmap(&tb, x, N, h, w, Ci, x_pitch, p.TW, p.TH);
   if (rc) return rc;
   profile_begin(prof_tag, stream);
-  rc = launch_conv<MODE_WGRAD>(ta, tb, p, stream);
+  rc = BN == 128 ? launch_conv<MODE_WGRAD, 128>(ta, tb, p, stream) : launch_conv<MODE_WGRAD, 256>(ta, tb, p, stream);
   profile_end(prof_tag, stream);
   return rc;
 }
@@ -561,12 +571,15 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16
     part[(long long)blockIdx.x * pitch + 2 * cp + 1] = acc.y;
   }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ part, int blocks, int pitch, int C, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, int blocks, int pitch, int C,
+                                                          float* __restrict__ out) {
+  // one warp per channel; lane l sums partials l, l+32, ... in order, then a fixed shuffle tree: run-to-run identical
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   double s = 0.0;
-  for (int b = 0; b < blocks; ++b) s += (double)part[(long long)b * pitch + c];
-  out[c] = (float)s;
+  for (int b = lane; b < blocks; b += 32) s += (double)part[(long long)b * pitch + c];
+  s = warp_sum_d(s);
+  if (lane == 0) out[c] = (float)s;
 }
 
 // split-K slabs [S][9][Co_total][Ci] -> gw [Co_part][Ci][3][3] for rows co0 .. co0 + Co_part
@@ -594,6 +607,21 @@ __global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* __r
   } else {
     for (int i = threadIdx.x; i < nci * 9; i += 256) dst[i] = sm[i];
   }
+}
+
+// the same reduction for small layers (everything L2-resident): one thread per output element, so a [19][128][3][3] gradient
+// is 86 blocks of independent loads instead of 19 blocks each walking 9 x S dependent ones
+__global__ void __launch_bounds__(256) conv_wgrad_reduce_flat_kernel(const float* __restrict__ part, int S, long long slab, int Co_total,
+                                                                     int Co_part, int Ci, int co0, float* __restrict__ gw) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= Co_part * Ci * 9) return;
+  const int k = idx % 9, rem = idx / 9;
+  const int ci = rem % Ci, co = rem / Ci;
+  const float* src = part + ((long long)k * Co_total + co0 + co) * Ci + ci;
+  float acc = 0.f;
+#pragma unroll 4
+  for (int s = 0; s < S; ++s) acc += __ldg(src + s * slab);
+  gw[idx] = acc;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -631,7 +659,7 @@ int nhwc_bf16_colsum(const void* g, long long P, int C, int pitch, void* scratch
                     "nhwc_bf16_colsum: bad arguments (pitch must be even and <= 512)");
   colsum_partial_kernel<<<COLSUM_BLOCKS, 256, 0, stream>>>((const __nv_bfloat16*)g, P, pitch, (float*)scratch);
   B200SEG_LAUNCH_CHECK();
-  colsum_final_kernel<<<ceil_div(C, 128), 128, 0, stream>>>((const float*)scratch, COLSUM_BLOCKS, pitch, C, out);
+  colsum_final_kernel<<<ceil_div(C, 8), 256, 0, stream>>>((const float*)scratch, COLSUM_BLOCKS, pitch, C, out);
   B200SEG_LAUNCH_CHECK();
   return B200SEG_OK;
 }
@@ -656,8 +684,13 @@ int conv3x3_wgrad(const void* g, int Co, long long g_pitch, const void* x, int C
   int co0 = 0;
   for (int i = 0; i < n_parts; ++i) {
     if (grad_w[i]) {
-      dim3 grid(ceil_div(Ci, 256), part_co[i]);
-      conv_wgrad_reduce_kernel<<<grid, 256, 0, stream>>>((const float*)scratch, used, (long long)9 * Co * Ci, Co, Ci, co0, grad_w[i]);
+      if ((long long)part_co[i] * Ci * 9 <= (1 << 20)) {
+        conv_wgrad_reduce_flat_kernel<<<ceil_div(part_co[i] * Ci * 9, 256), 256, 0, stream>>>((const float*)scratch, used,
+                                                                                              (long long)9 * Co * Ci, Co, part_co[i], Ci, co0, grad_w[i]);
+      } else {
+        dim3 grid(ceil_div(Ci, 256), part_co[i]);
+        conv_wgrad_reduce_kernel<<<grid, 256, 0, stream>>>((const float*)scratch, used, (long long)9 * Co * Ci, Co, Ci, co0, grad_w[i]);
+      }
       B200SEG_LAUNCH_CHECK();
     }
     co0 += part_co[i];
