@@ -87,5 +87,26 @@ def write_bench_json(summary_csv, out_json, source):
     print("wrote", out_json)
 
 
-if __name__ == "__main__" and len(sys.argv) > 3:
+def merge_disc_json(summary_csv, out_json, source):
+    """Add the discriminator conv-stack launches (capture of profiles/prof_disc.py: layer 1 is the first forward launch,
+    the last weight-gradient launch and the last data-gradient launch) to profiles/ncu_summary.json."""
+    import json
+    rows = list(csv.DictReader(open(summary_csv)))
+    conv = [r for r in rows if "conv_gemm_kernel<0" in r["kernel"]]
+    wg = [r for r in rows if "conv_gemm_kernel<1" in r["kernel"]]
+    out = json.load(open(out_json)) if os.path.exists(out_json) else {"kernels": {}}
+    out["source_disc"] = source
+    for key, r in (("conv3x3_fwd", conv[0]), ("conv3x3_dgrad", conv[-1]), ("conv3x3_wgrad", wg[-1])):
+        out["kernels"][key] = {"kernel": r["kernel"], "layer": "2048 -> 256 at 4 x 64 x 128 (layer 1 of the discriminator)",
+                               "dram_bytes_per_launch": int(float(r["traffic_MB"]) * 1e6), "ncu_time_us": float(r["time_us"]),
+                               "registers": int(float(r["regs"])) if r["regs"] else None,
+                               "tensor_pipe_pct_of_active": float(r["tensor_pipe_pct"]) if r["tensor_pipe_pct"] else None}
+    with open(out_json, "w") as f:
+        json.dump(out, f, indent=1)
+    print("merged", out_json)
+
+
+if __name__ == "__main__" and len(sys.argv) > 4 and sys.argv[4] == "disc":
+    merge_disc_json(sys.argv[2], sys.argv[3], os.path.basename(sys.argv[1]))
+elif __name__ == "__main__" and len(sys.argv) > 3:
     write_bench_json(sys.argv[2], sys.argv[3], os.path.basename(sys.argv[1]))
