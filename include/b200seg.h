@@ -219,6 +219,9 @@ B200SEG_API int b200seg_profile_read(int tag, double* total_ms, int* count);
  *        3 = 2 x 2 cluster multicasting both. */
 B200SEG_API int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b_mn_major, int splits, int col_hw, int share,
                           double* max_err, double* max_ref);
+/* K6 conv kernel: 1 (default) = CTA pairs driving one tcgen05.mma.cta_group::2 (M = 256) wherever a layer has two M-tiles,
+ * 0 = one CTA per tile (A/B experiments) */
+B200SEG_API void b200seg_conv_set_pair(int on);
 /* operand multicast inside the ASPP head GEMMs: 0 none, 1 (default) 2-CTA pairs, 2 2 x 2 clusters sharing both operands */
 B200SEG_API void b200seg_gemm_set_sharing(int on);
 /* SMs the data-gradient GEMM leaves free when b200seg_aspp_backward_packed_ex is given a weights_ready_event, so that the

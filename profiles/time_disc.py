@@ -44,6 +44,10 @@ def fwdbwd(mod, inp, need_x):
     mod(inp).backward(go)
 
 
+_lib.conv_set_pair(os.environ.get("B200SEG_CONV_PAIR", "1") != "0")
+print("conv pair (cta_group::2):", os.environ.get("B200SEG_CONV_PAIR", "1") != "0")
+import rnd_semantic_segmentation_b200 as _b
+_b.set_feature_pack_cache(0)
 P = N * h * w
 flops_fwd = 2 * 9 * P * (2048 * 256 + 256 * 128 + 128 * 2 * C)
 print(f"N={N} P={P} fwd GFLOP={flops_fwd / 1e9:.1f}")

@@ -76,6 +76,7 @@ SIGNATURES = {
     "b200seg_profile_read": (c_int, [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int)]),
     "b200seg_gemm_selftest": (c_int, [c_int] * 8 + [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "b200seg_gemm_set_sharing": (None, [c_int]),
+    "b200seg_conv_set_pair": (None, [c_int]),
 }
 
 
@@ -641,6 +642,11 @@ def gemm_selftest(M, N, K, a_mn=False, b_mn=False, splits=1, col_hw=0, share=0):
     err, ref = ctypes.c_double(0), ctypes.c_double(0)
     _check(lib.b200seg_gemm_selftest(M, N, K, int(a_mn), int(b_mn), splits, col_hw, int(share), ctypes.byref(err), ctypes.byref(ref)))
     return err.value, ref.value
+
+
+def conv_set_pair(on):
+    """K6: True (default) = CTA pairs on one tcgen05.mma.cta_group::2 where a layer has two M-tiles; False = one CTA per tile."""
+    load().b200seg_conv_set_pair(1 if on else 0)
 
 
 def gemm_set_sharing(mode):

@@ -85,6 +85,7 @@ int conv3x3_wgrad(const void*, int, long long, const void*, int, long long, int,
 int nchw_to_nhwc_bf16(const float*, int, int, int, void*, int, cudaStream_t);
 long long nhwc_colsum_scratch_bytes(int);
 int nhwc_bf16_colsum(const void*, long long, int, int, void*, float*, cudaStream_t);
+namespace gemm { namespace conv { void set_pair(int); } }
 namespace gemm {
 int selftest(int, int, int, int, int, int, int, int, double*, double*);
 void set_sharing(int);
@@ -347,6 +348,7 @@ int b200seg_profile_read(int tag, double* total_ms, int* count) {
   return B200SEG_OK;
 }
 
+void b200seg_conv_set_pair(int on) { gemm::conv::set_pair(on); }
 void b200seg_gemm_set_sharing(int on) { gemm::set_sharing(on); }
 void b200seg_gemm_set_overlap_sms(int n) { gemm::set_overlap_sms(n); }
 

@@ -37,12 +37,63 @@ constexpr int MAX_T = 9;
 constexpr int MODE_CONV = 0, MODE_WGRAD = 1;
 constexpr int OUT_BF16_NHWC = 0, OUT_F32_NCHW = 1;
 // BN = accumulator columns per tile: 256, or 128 for layers with <= 128 output channels (half the MMA work of a padded 256)
-template <int BN> struct Cfg {
-  static constexpr int B_BYTES_T = BN * BLOCK_K * 2;
+// PAIR = two CTAs of a cluster drive ONE tcgen05.mma.cta_group::2 (M = 256: 128 rows per CTA, N = BN): each CTA stages its own
+// A tile and only HALF of the B tile (the tensor core reads the other half from the peer's shared memory), so the bytes a
+// CTA pulls from L2 and the shared-memory operand reads per MMA drop by a third / a half.
+template <int BN, bool PAIR> struct Cfg {
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;                 // B rows (output channels) staged per CTA
+  static constexpr int B_BYTES_T = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_T = A_BYTES + B_BYTES_T;
-  static constexpr int NSTAGE = BN == 256 ? 4 : 6;
+  static constexpr int NSTAGE = (200 * 1024) / STAGE_T > 8 ? 8 : (200 * 1024) / STAGE_T;     // 4 / 6 / 6 / 8
   static constexpr int SMEM = 1024 + NSTAGE * STAGE_T + 256;
 };
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads whose completion is signalled on a barrier given as a shared::cluster address; with PAIR (.cta_group::2) that
+// barrier may live in the peer CTA (the leader's full barrier collects the bytes of both CTAs)
+template <bool PAIR>
+__device__ __forceinline__ void tma_ld3(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  if (PAIR)
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+template <bool PAIR>
+__device__ __forceinline__ void tma_ld4(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  if (PAIR)
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
 
 struct ConvParams {
   int N, h, w;
@@ -90,8 +141,9 @@ __device__ __forceinline__ void rect_origin(const ConvParams& p, int idx, int& i
 struct Unit {
   int z, t, mt, nt, kb0, kb1;
 };
-template <int MODE>
-__device__ __forceinline__ Unit decode_unit(const ConvParams& p, int unit) {
+// p.m_tiles counts PAIRS of M-tiles when the kernel runs as CTA pairs: CTA `rank` of the pair owns M-tile 2 * pm + rank
+template <int MODE, bool PAIR>
+__device__ __forceinline__ Unit decode_unit(const ConvParams& p, int unit, int rank) {
   Unit u;
   if (MODE == MODE_CONV) {
     u.z = 0; u.t = 0;
@@ -110,18 +162,23 @@ __device__ __forceinline__ Unit decode_unit(const ConvParams& p, int unit) {
     u.kb0 = u.z * p.kb_per_split;
     u.kb1 = min(p.kb_total, u.kb0 + p.kb_per_split);
   }
+  if (PAIR) u.mt = u.mt * 2 + rank;
   return u;
 }
 
-template <int MODE, int BN>
+template <int MODE, int BN, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
-  constexpr int STAGES = Cfg<BN>::NSTAGE, STAGE_BYTES = Cfg<BN>::STAGE_T;      // shadow the 256-column constants of gemm::
+  constexpr int STAGES = Cfg<BN, PAIR>::NSTAGE, STAGE_BYTES = Cfg<BN, PAIR>::STAGE_T;      // shadow the constants of gemm::
   constexpr int BLOCK_N = BN;
+  constexpr int B_ROWS = Cfg<BN, PAIR>::B_ROWS;
+  constexpr int NCTA = PAIR ? 2 : 1;
+  const int rank = PAIR ? (int)cluster_cta_rank() : 0;
+  const int worker = (int)blockIdx.x / NCTA, nworkers = (int)gridDim.x / NCTA;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
@@ -144,13 +201,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], EPI_WARPS);
+      mbar_init(&tempty_bar[a], EPI_WARPS * NCTA);        // the leader's MMA thread waits for the epilogue warps of BOTH CTAs
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc2(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();              // the peer's barriers are initialised before any remote arrive / TMA completion
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -159,28 +220,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-        const Unit u = decode_unit<MODE>(p, unit);
+      for (int unit = worker; unit < p.units; unit += nworkers) {
+        const Unit u = decode_unit<MODE, PAIR>(p, unit, rank);
         int img = 0, y0 = 0, x0 = 0;
         if (MODE == MODE_CONV) rect_origin(p, u.mt, img, y0, x0);
         for (int kb = u.kb0; kb < u.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          // PAIR: both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of both
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES * NCTA);
+          const uint32_t fb = PAIR ? mapa_u32(smem_u32(&full_bar[stage]), 0) : smem_u32(&full_bar[stage]);
           if (MODE == MODE_CONV) {
             const int t = kb / p.KC, kc = kb - t * p.KC;
-            tma_load_4d(sa, &tmap_a, &full_bar[stage], kc * BLOCK_K, x0 + p.dx[t], y0 + p.dy[t], img);
-            tma_load_3d(sb, &tmap_b, &full_bar[stage], kc * BLOCK_K, u.nt * BLOCK_N, t);
+            tma_ld4<PAIR>(sa, &tmap_a, fb, kc * BLOCK_K, x0 + p.dx[t], y0 + p.dy[t], img);
+            tma_ld3<PAIR>(sb, &tmap_b, fb, kc * BLOCK_K, u.nt * BLOCK_N + rank * B_ROWS, t);
           } else {
             rect_origin(p, kb, img, y0, x0);
 #pragma unroll
             for (int b = 0; b < BLOCK_M / 64; ++b)
-              tma_load_4d(sa + b * MN_BOX_BYTES, &tmap_a, &full_bar[stage], u.mt * BLOCK_M + b * 64, x0, y0, img);
+              tma_ld4<PAIR>(sa + b * MN_BOX_BYTES, &tmap_a, fb, u.mt * BLOCK_M + b * 64, x0, y0, img);
             const int xs = x0 + p.dx[u.t], ys = y0 + p.dy[u.t];
 #pragma unroll
-            for (int b = 0; b < BLOCK_N / 64; ++b)
-              tma_load_4d(sb + b * MN_BOX_BYTES, &tmap_b, &full_bar[stage], u.nt * BLOCK_N + b * 64, xs, ys, img);
+            for (int b = 0; b < B_ROWS / 64; ++b)
+              tma_ld4<PAIR>(sb + b * MN_BOX_BYTES, &tmap_b, fb, u.nt * BLOCK_N + rank * B_ROWS + b * 64, xs, ys, img);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -188,15 +251,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(MN, MN, BLOCK_M, BLOCK_N);
+    if (lane == 0 && rank == 0) {                                    // PAIR: the leader CTA issues for both
+      constexpr uint32_t idesc = make_idesc(MN, MN, BLOCK_M * NCTA, BLOCK_N);
       constexpr uint32_t lbo = MN ? MN_BOX_BYTES : 16, sbo = 1024, step = MN ? 2048 : 32;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-        const Unit u = decode_unit<MODE>(p, unit);
+      for (int unit = worker; unit < p.units; unit += nworkers) {
+        const Unit u = decode_unit<MODE, PAIR>(p, unit, rank);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -209,12 +272,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc(sa + k * step, lbo, sbo);
             const uint64_t bdesc = make_smem_desc(sb + k * step, lbo, sbo);
-            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > u.kb0 || k > 0) ? 1u : 0u);
+            if (PAIR) umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (kb > u.kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > u.kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          if (PAIR) umma_commit_2sm(&empty_bar[stage], 0x3);         // frees the stage in both CTAs
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tfull_bar[acc]);
+        if (PAIR) umma_commit_2sm(&tfull_bar[acc], 0x3);
+        else umma_commit(&tfull_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -224,8 +290,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int half = (warp - 4) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-      const Unit u = decode_unit<MODE>(p, unit);
+    for (int unit = worker; unit < p.units; unit += nworkers) {
+      const Unit u = decode_unit<MODE, PAIR>(p, unit, rank);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * (BLOCK_N / 2));
@@ -235,7 +301,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         rect_origin(p, u.mt, img, y0, x0);
         const int yy = row >> p.tw_shift, xx = row & (p.TW - 1);
         const int y = y0 + yy, x = x0 + xx;
-        const bool valid = y < p.h && x < p.w;
+        const bool valid = y < p.h && x < p.w && img < p.N;      // img >= N: the odd M-tile of the last pair
         const long long pix = ((long long)img * p.h + y) * p.w + x;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 2 / 32; ++c) {
@@ -320,16 +386,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();              // the leader's MMAs read the peer's shared memory; remote arrives must have landed
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc2(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -387,18 +458,43 @@ static void fill_taps(ConvParams& p, int dilation, int sign) {
 
 static int ilog2(int v) { int s = 0; while ((1 << s) < v) ++s; return s; }
 
-template <int MODE, int BN>
-static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t stream) {
+static int g_pair = 1;                 // b200seg_conv_set_pair(): 0 = one CTA per tile, 1 = CTA pairs (cta_group::2) where two M-tiles exist
+void set_pair(int on) { g_pair = on; }
+
+template <int MODE, int BN, bool PAIR>
+static int launch_conv_t(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    B200SEG_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
+    B200SEG_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<MODE, BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, PAIR>::SMEM));
     configured = true;
   }
   const int sms = num_sms();
-  const int grid = p.units < sms ? p.units : sms;
-  conv_gemm_kernel<MODE, BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM, stream>>>(ta, tb, p);
+  if (!PAIR) {
+    const int grid = p.units < sms ? p.units : sms;
+    conv_gemm_kernel<MODE, BN, PAIR><<<grid, NUM_THREADS, Cfg<BN, PAIR>::SMEM, stream>>>(ta, tb, p);
+  } else {
+    const int pairs = p.units < sms / 2 ? p.units : sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg<BN, PAIR>::SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200SEG_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<MODE, BN, PAIR>, ta, tb, p));
+  }
   B200SEG_LAUNCH_CHECK();
   return B200SEG_OK;
+}
+template <int MODE>
+static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, int BN, bool pair, cudaStream_t stream) {
+  if (BN == 128) return pair ? launch_conv_t<MODE, 128, true>(ta, tb, p, stream) : launch_conv_t<MODE, 128, false>(ta, tb, p, stream);
+  return pair ? launch_conv_t<MODE, 256, true>(ta, tb, p, stream) : launch_conv_t<MODE, 256, false>(ta, tb, p, stream);
 }
 
 // D[pixel, co] = sum_t sum_ck act[pixel + sign*d_t, ck] * wt[t][co][ck]  (+ epilogue), see the header comment
@@ -424,6 +520,8 @@ int conv3x3_run(const void* act, int N, int h, int w, int Ck, long long act_pitc
   p.Co = Co; p.Ci = 0;
   const int BN = Co <= 128 ? 128 : 256;
   p.m_tiles = N * p.tiles_x * p.tiles_y;
+  const bool pair = g_pair && p.m_tiles >= 2;
+  if (pair) p.m_tiles = ceil_div(p.m_tiles, 2);       // pairs of M-tiles
   p.n_tiles = ceil_div(Co, BN);
   p.units = p.m_tiles * p.n_tiles;
   p.splits = 1;
@@ -439,12 +537,12 @@ int conv3x3_run(const void* act, int N, int h, int w, int Ck, long long act_pitc
   {
     cuuint64_t gdim[3] = {(cuuint64_t)Ck, (cuuint64_t)Co, (cuuint64_t)p.T};
     cuuint64_t gstr[2] = {(cuuint64_t)Ck * 2, (cuuint64_t)Ck * 2 * Co};
-    cuuint32_t box[3] = {64, (cuuint32_t)BN, 1};
+    cuuint32_t box[3] = {64, (cuuint32_t)(pair ? BN / 2 : BN), 1};
     rc = make_tmap_nd(&tb, wt, 3, gdim, gstr, box);
     if (rc) return rc;
   }
   profile_begin(prof_tag, stream);
-  rc = BN == 128 ? launch_conv<MODE_CONV, 128>(ta, tb, p, stream) : launch_conv<MODE_CONV, 256>(ta, tb, p, stream);
+  rc = launch_conv<MODE_CONV>(ta, tb, p, BN, pair, stream);
   profile_end(prof_tag, stream);
   return rc;
 }
@@ -453,8 +551,11 @@ int conv3x3_wgrad_splits(int N, int h, int w, int Co, int Ci) {
   int TW = 64, TH = 1;
   pick_rect(h, w, BLOCK_K, &TW, &TH);
   const int kb_total = N * ceil_div(w, TW) * ceil_div(h, TH);
-  const int units = 9 * ceil_div(Co, BLOCK_M) * ceil_div(Ci, Ci <= 128 ? 128 : 256);
-  int s = num_sms() / units;
+  int mt = ceil_div(Co, BLOCK_M);
+  const bool pair = g_pair && mt >= 2;
+  if (pair) mt = ceil_div(mt, 2);
+  const int units = 9 * mt * ceil_div(Ci, Ci <= 128 ? 128 : 256);
+  int s = (pair ? num_sms() / 2 : num_sms()) / units;
   if (s < 1) s = 1;
   if (s > kb_total) s = kb_total;
   return s;
@@ -478,6 +579,8 @@ int conv3x3_wgrad_run(const void* g, int Co, long long g_pitch, const void* x, i
   p.Co = Co; p.Ci = Ci;
   const int BN = Ci <= 128 ? 128 : 256;
   p.m_tiles = ceil_div(Co, BLOCK_M);
+  const bool pair = g_pair && p.m_tiles >= 2;
+  if (pair) p.m_tiles = ceil_div(p.m_tiles, 2);
   p.n_tiles = ceil_div(Ci, BN);
   p.kb_total = N * p.tiles_x * p.tiles_y;
   if (splits < 1) splits = 1;
@@ -496,7 +599,7 @@ int conv3x3_wgrad_run(const void* g, int Co, long long g_pitch, const void* x, i
   rc = make_act_tmap(&tb, x, N, h, w, Ci, x_pitch, p.TW, p.TH);
   if (rc) return rc;
   profile_begin(prof_tag, stream);
-  rc = BN == 128 ? launch_conv<MODE_WGRAD, 128>(ta, tb, p, stream) : launch_conv<MODE_WGRAD, 256>(ta, tb, p, stream);
+  rc = launch_conv<MODE_WGRAD>(ta, tb, p, BN, pair, stream);
   profile_end(prof_tag, stream);
   return rc;
 }
