@@ -105,6 +105,10 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
     if lib.b200seg_abi_version() != 1:
         raise B200SegError("libb200seg.so ABI version mismatch")
     _lib = lib
+    if os.environ.get("B200SEG_GEMM_SHARING"):        # A/B experiments (profiles/): operand-sharing mode of the head GEMMs
+        lib.b200seg_gemm_set_sharing(int(os.environ["B200SEG_GEMM_SHARING"]))
+    if os.environ.get("B200SEG_CONV_PAIR"):
+        lib.b200seg_conv_set_pair(int(os.environ["B200SEG_CONV_PAIR"]))
     return lib
 
 

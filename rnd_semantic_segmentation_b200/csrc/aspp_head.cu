@@ -486,8 +486,10 @@ int aspp_backward_packed(const void* gOt_in, const void* Xp, const void* WpT, co
     // half the bytes of the fp32 NCHW gradient, so the GEMM is MMA-bound instead of store-bound
     gemm::Operand a{Gp, true, Ppitch};
     gemm::Operand b{(const __nv_bfloat16*)WpT, false, NJ};
+    // CTA pairs on one tcgen05.mma.cta_group::2 (M = 256 pixels): 164 vs 170 us with the multicast pairs.  (The fp32 NCHW
+    // dgrad above is bound by its 537 MB store, where the 2-SM MMA measured 5 us SLOWER, so it keeps the multicast pairs.)
     int rc = gemm::launch(a, b, (int)P, Cin, NJ, 1, reinterpret_cast<float*>(grad_x_nhwc_bf16), Cin, 0, 0, 0, stream, nullptr, 1,
-                          gemm::SHARE_B, true, weights_ready ? gemm::overlap_sms() : 0);
+                          gemm::SHARE_PAIR, true, weights_ready ? gemm::overlap_sms() : 0);
     if (rc) return rc;
   }
   return B200SEG_OK;

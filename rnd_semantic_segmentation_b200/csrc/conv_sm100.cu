@@ -48,14 +48,6 @@ template <int BN, bool PAIR> struct Cfg {
   static constexpr int SMEM = 1024 + NSTAGE * STAGE_T + 256;
 };
 
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
 // TMA loads whose completion is signalled on a barrier given as a shared::cluster address; with PAIR (.cta_group::2) that
 // barrier may live in the peer CTA (the leader's full barrier collects the bytes of both CTAs)
 template <bool PAIR>
@@ -76,25 +68,6 @@ __device__ __forceinline__ void tma_ld4(uint32_t smem_dst, const CUtensorMap* m,
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(smem_dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
-__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"(cta_mask)
-               : "memory");
-}
-
 struct ConvParams {
   int N, h, w;
   int tw_shift, TW, TH, tiles_x, tiles_y;   // pixel rectangle: M-tile (CONV, TW*TH = 128) or K-chunk (WGRAD, TW*TH = 64)
@@ -206,7 +179,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     fence_mbar_init();
   }
   if (warp == 2) {
-    if (PAIR) tmem_alloc2(tmem_slot, TMEM_COLS);
+    if (PAIR) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
     else tmem_alloc(tmem_slot, TMEM_COLS);
   }
   tc_fence_before();
@@ -399,7 +372,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (PAIR) cluster_sync_all();              // the leader's MMAs read the peer's shared memory; remote arrives must have landed
   if (warp == 2) {
     tc_fence_after();
-    if (PAIR) tmem_dealloc2(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
     else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }

@@ -46,7 +46,7 @@ static int make_tmap(CUtensorMap* m, const __nv_bfloat16* ptr, long long inner, 
 static int g_overlap_sms = 8;         // b200seg_gemm_set_overlap_sms(): SMs left free while an all-reduce overlaps the dgrad GEMM
 void set_overlap_sms(int n) { g_overlap_sms = n < 0 ? 0 : n; }
 int overlap_sms() { return g_overlap_sms; }
-static int g_share_enabled = 1;      // b200seg_gemm_set_sharing(): 0 no multicast, 1 2-CTA pairs (default), 2 2 x 2 clusters (measured ~1.9x slower: 37 four-CTA clusters do not all fit the GPCs)
+static int g_share_enabled = 1;      // b200seg_gemm_set_sharing(): 0 no multicast, 1 (default) 2-CTA multicast pairs, 2 2 x 2 clusters (measured ~1.9x slower: 37 four-CTA clusters do not all fit the GPCs), 3 = 1 + cta_group::2 pairs where the caller shares B along M (measured: no gain on the store-bound dgrad)
 void set_sharing(int on) { g_share_enabled = on; }
 
 template <bool A_MN, bool B_MN, int SHARE>
@@ -79,6 +79,7 @@ static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const Params& 
 
 template <bool A_MN, bool B_MN>
 static int launch_s(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, int share, cudaStream_t stream) {
+  if (share == SHARE_PAIR) return launch_t<A_MN, B_MN, SHARE_PAIR>(ta, tb, p, grid, stream);
   if (share == SHARE_AB) return launch_t<A_MN, B_MN, SHARE_AB>(ta, tb, p, grid, stream);
   if (share == SHARE_B) return launch_t<A_MN, B_MN, SHARE_B>(ta, tb, p, grid, stream);
   if (share == SHARE_A) return launch_t<A_MN, B_MN, SHARE_A>(ta, tb, p, grid, stream);
@@ -92,9 +93,11 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
   B200SEG_CHECK_ARG(!out_bf16 || (col_hw <= 0 && N % 8 == 0 && row_stride % 8 == 0 && split_stride % 8 == 0 &&
                                   (reinterpret_cast<uintptr_t>(out) & 15) == 0),
                     "gemm: bf16 output needs plain row-major D with N, row pitch multiples of 8 and a 16-byte aligned base");
+  const bool explicit_pair = share == SHARE_PAIR;                           // the self-test asks for the mode by number
   if (!g_share_enabled) share = SHARE_NONE;
-  if (g_share_enabled >= 2 && share != SHARE_NONE) share = SHARE_AB;        // callers name the operand worth sharing; 2 x 2 shares both
-  if (g_share_enabled == 1 && share == SHARE_AB) share = SHARE_A;
+  if (g_share_enabled == 2 && share != SHARE_NONE) share = SHARE_AB;        // callers name the operand worth sharing; 2 x 2 shares both
+  if (g_share_enabled != 2 && share == SHARE_AB) share = SHARE_A;
+  if ((g_share_enabled == 3 && share == SHARE_B) || (g_share_enabled && explicit_pair)) share = SHARE_PAIR;   // pairs along M sharing B: one 2-SM MMA
   Params p;
   p.M = M; p.N = N; p.K = K;
   p.m_tiles = ceil_div(M, BLOCK_M);
@@ -119,6 +122,7 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
   if (share == SHARE_AB && p.m_tiles < 2) share = SHARE_A;
   if (share == SHARE_AB && p.n_tiles < 2) share = SHARE_B;
   if (share == SHARE_B && p.m_tiles < 2) share = SHARE_NONE;
+  if (share == SHARE_PAIR && p.m_tiles < 2) share = SHARE_NONE;
   if (share == SHARE_A && p.n_tiles < 2) share = SHARE_NONE;
 
   // the shared operand is loaded in halves (one per CTA of the pair): halve its K-major box
@@ -127,7 +131,7 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
   if (!a.mn_major) rc = make_tmap(&ta, a.ptr, K, M, a.pitch, BLOCK_K, (share == SHARE_A || share == SHARE_AB) ? BLOCK_M / 2 : BLOCK_M);
   else rc = make_tmap(&ta, a.ptr, M, K, a.pitch, 64, BLOCK_K);
   if (rc) return rc;
-  if (!b.mn_major) rc = make_tmap(&tb, b.ptr, K, N, b.pitch, BLOCK_K, (share == SHARE_B || share == SHARE_AB) ? BLOCK_N / 2 : BLOCK_N);
+  if (!b.mn_major) rc = make_tmap(&tb, b.ptr, K, N, b.pitch, BLOCK_K, (share == SHARE_B || share == SHARE_AB || share == SHARE_PAIR) ? BLOCK_N / 2 : BLOCK_N);
   else rc = make_tmap(&tb, b.ptr, N, K, b.pitch, 64, BLOCK_K);
   if (rc) return rc;
 
@@ -141,7 +145,7 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
     grid = units < sms ? units : sms;
   } else {
     const int cs = share == SHARE_AB ? 4 : 2;
-    const int mt = (share == SHARE_B || share == SHARE_AB) ? (p.m_tiles + 1) / 2 : p.m_tiles;
+    const int mt = (share == SHARE_B || share == SHARE_AB || share == SHARE_PAIR) ? (p.m_tiles + 1) / 2 : p.m_tiles;
     const int nt = (share == SHARE_A || share == SHARE_AB) ? (p.n_tiles + 1) / 2 : p.n_tiles;
     const int units = mt * nt * p.splits;
     const int clusters = units < sms / cs ? units : sms / cs;

@@ -163,7 +163,47 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int m, i
 //                tile (multicast to the CTA with the same rm) and half rm of its B tile (multicast to the CTA with the same
 //                rn): 24 KB per k-block per SM.  The kernel is bound by the L2 -> SM rate (~6.3 KB/clk chip-wide: at 32-40 KB
 //                per k-block the loads of a k-block take longer than its four MMAs), so this is what buys tensor-pipe time.
-constexpr int SHARE_NONE = 0, SHARE_B = 1, SHARE_A = 2, SHARE_AB = 3;
+//   SHARE_PAIR : the two CTAs own M-tiles (2i, 2i+1) of the same N-tile and drive ONE tcgen05.mma.cta_group::2 (M = 256):
+//                each stages its own A tile and HALF of the B tile (the tensor core reads the other half from the peer's
+//                shared memory): 32 KB per k-block per SM, half the B operand reads per MMA, 6 stages instead of 4.  The
+//                leader CTA issues; both CTAs' TMA bytes complete on the leader's full barrier; commits are multicast.
+constexpr int SHARE_NONE = 0, SHARE_B = 1, SHARE_A = 2, SHARE_AB = 3, SHARE_PAIR = 4;
+constexpr int PAIR_STAGES = 6;
+constexpr int PAIR_STAGE_BYTES = A_BYTES + B_BYTES / 2;          // 32 KB; 6 x 32 KB = 4 x 48 KB
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// 2-SM TMA load: the completion barrier is a shared::cluster address and may live in the peer (leader) CTA
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(m), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
 
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
                                                uint16_t cta_mask) {
@@ -195,7 +235,7 @@ struct TileSched {
     rank = SHARE != SHARE_NONE ? (int)cluster_cta_rank() : 0;
     worker = (int)blockIdx.x / CS;
     nworkers = (int)gridDim.x / CS;
-    m_tiles = (SHARE == SHARE_B || SHARE == SHARE_AB) ? (p.m_tiles + 1) >> 1 : p.m_tiles;     // pairs along M
+    m_tiles = (SHARE == SHARE_B || SHARE == SHARE_AB || SHARE == SHARE_PAIR) ? (p.m_tiles + 1) >> 1 : p.m_tiles;     // pairs along M
     n_tiles = (SHARE == SHARE_A || SHARE == SHARE_AB) ? (p.n_tiles + 1) >> 1 : p.n_tiles;     // pairs along N
     per_split = m_tiles * n_tiles;
     units = per_split * p.splits;
@@ -205,7 +245,7 @@ struct TileSched {
     const int rem = unit - z * per_split;
     nt = rem / m_tiles;                  // M fastest: tiles sharing the (large) B operand are adjacent in time
     mt = rem - nt * m_tiles;
-    if (SHARE == SHARE_B) mt = mt * 2 + rank;
+    if (SHARE == SHARE_B || SHARE == SHARE_PAIR) mt = mt * 2 + rank;
     if (SHARE == SHARE_A) nt = nt * 2 + rank;
     if (SHARE == SHARE_AB) { mt = mt * 2 + (rank & 1); nt = nt * 2 + (rank >> 1); }
   }
@@ -218,6 +258,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;                                   // 1024-byte aligned (128B swizzle atom)
+  constexpr bool PAIR = SHARE == SHARE_PAIR;
+  constexpr int STAGES = PAIR ? PAIR_STAGES : gemm::STAGES;         // same total bytes either way
+  constexpr int STAGE_BYTES = PAIR ? PAIR_STAGE_BYTES : gemm::STAGE_BYTES;
+  static_assert(PAIR_STAGES * PAIR_STAGE_BYTES == gemm::STAGES * gemm::STAGE_BYTES, "epilogue staging / barriers sit behind the ring");
   float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_FLOATS * 4);
   uint64_t* full_bar = bars;                  // [STAGES]
@@ -237,15 +281,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], SHARE == SHARE_AB ? 3 : (CLUSTER ? 2 : 1));   // cluster: every CTA this one writes into releases the stage
+      mbar_init(&empty_bar[s], PAIR ? 1 : (SHARE == SHARE_AB ? 3 : (CLUSTER ? 2 : 1)));   // multicast modes: every CTA this one writes into releases the stage
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], EPI_WARPS);   // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], PAIR ? 2 * EPI_WARPS : EPI_WARPS);   // one arrive per epilogue warp (PAIR: of both CTAs, on the leader)
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    else tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
   if (CLUSTER) cluster_sync_all();            // peer barriers are initialised before any remote arrive / multicast
@@ -269,8 +316,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);   // own loads + the peer's multicast half
           const int k0 = kb * BLOCK_K;
+          if (PAIR) {
+            // own A tile + own half of B; both CTAs' bytes complete on the leader's full barrier
+            if (sched.rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+            const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (!A_MN) tma_load_2d_2sm(sa, &tmap_a, fb, k0, m0);
+            else {
+#pragma unroll
+              for (int b = 0; b < BLOCK_M / 64; ++b) tma_load_2d_2sm(sa + b * MN_BOX_BYTES, &tmap_a, fb, m0 + b * 64, k0);
+            }
+            const int nh = n0 + sched.rank * (BLOCK_N / 2);
+            if (!B_MN) tma_load_2d_2sm(sb, &tmap_b, fb, k0, nh);
+            else {
+#pragma unroll
+              for (int b = 0; b < BLOCK_N / 2 / 64; ++b) tma_load_2d_2sm(sb + b * MN_BOX_BYTES, &tmap_b, fb, nh + b * 64, k0);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            continue;
+          }
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);   // own loads + the peer's multicast half
           // ---- A ----
           if (SHARE == SHARE_A || SHARE == SHARE_AB) {
             // shared A tile: this CTA loads rows [64*ha, +64) and multicasts them to the CTAs that own the same M-tile
@@ -310,8 +375,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp == 1) {
     // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(A_MN, B_MN, BLOCK_M, BLOCK_N);
+    if (lane == 0 && (!PAIR || sched.rank == 0)) {
+      constexpr uint32_t idesc = make_idesc(A_MN, B_MN, PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
       // K-major: 8-row groups 1024 B apart (SBO), LBO unused (1); +32 B per UMMA_K step.
       // MN-major: 64-element chunks one TMA box (8 KB) apart (LBO), 8-k-row groups 1024 B apart (SBO);
       //           +16 k-rows = 2048 B per UMMA_K step.
@@ -338,15 +403,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc(sa + k * a_step, a_lbo, a_sbo);
             const uint64_t bdesc = make_smem_desc(sb + k * b_step, b_lbo, b_sbo);
-            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (PAIR) umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           // frees the slot in every CTA that multicasts into this one (itself included) when these MMAs retire
-          if (SHARE == SHARE_AB) umma_commit_mc(&empty_bar[stage], (uint16_t)((1u << sched.rank) | (1u << (sched.rank ^ 1)) | (1u << (sched.rank ^ 2))));
+          if (PAIR) umma_commit_2sm(&empty_bar[stage], 0x3);
+          else if (SHARE == SHARE_AB) umma_commit_mc(&empty_bar[stage], (uint16_t)((1u << sched.rank) | (1u << (sched.rank ^ 1)) | (1u << (sched.rank ^ 2))));
           else if (CLUSTER) umma_commit_mc(&empty_bar[stage], 0x3);
           else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tfull_bar[acc]);              // accumulator ready for the epilogue
+        if (PAIR) umma_commit_2sm(&tfull_bar[acc], 0x3);
+        else umma_commit(&tfull_bar[acc]);         // accumulator ready for the epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -450,7 +518,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -460,7 +531,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (CLUSTER) cluster_sync_all();            // the peer may still multicast into / arrive on this CTA until it is done too
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
