@@ -481,6 +481,43 @@ def test_discriminator_stack_forward_backward(lib, n, cin, ndf, C, h, w):
     assert all(torch.equal(a, p.grad) for a, p in zip(g_first, ours.parameters()))
 
 
+def test_conv3x3_full_size_adversarial_layer1(lib):
+    """BASELINE configs[2] at full size (4 x 2048 x 64 x 128 -> 256): forward, data gradient and weight gradient of the dominant
+    layer against torch's strict-fp32 convolution on the GPU, fed the same bf16-rounded operands; both tile modes (one CTA per
+    tile, CTA pairs on tcgen05.mma.cta_group::2) must agree with it and give bit-identical results run to run."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n, ci, co, h, w = 4, 2048, 256, 64, 128
+    x = bf16_round(torch.relu(torch.randn(n, ci, h, w, device="cuda", generator=g)))
+    wt = bf16_round(torch.randn(co, ci, 3, 3, device="cuda", generator=g) * 0.01)
+    go = bf16_round(torch.randn(n, co, h, w, device="cuda", generator=g) * 1e-3)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        xr, wr = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+        z = F.conv2d(xr, wr, padding=1)
+        gx_want, gw_want = torch.autograd.grad(z, (xr, wr), go)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    Wf, Wb = lib.conv3x3_pack_weights([wt])
+    xq = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    gq = go.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    outs = {}
+    for pair in (False, True):
+        lib.conv_set_pair(pair)
+        try:
+            out = lib.conv3x3_forward(xq, Wf, None, None, out_f32_nchw=True)
+            gx = lib.conv3x3_dgrad(gq, Wb, out_f32_nchw=True)
+            gw, = lib.conv3x3_wgrad(gq, xq, [co])
+            assert torch.equal(out, lib.conv3x3_forward(xq, Wf, None, None, out_f32_nchw=True))
+            assert torch.equal(gw, lib.conv3x3_wgrad(gq, xq, [co])[0])
+        finally:
+            lib.conv_set_pair(True)
+        assert rel_err(out, z) <= TOL and rel_err(gx, gx_want) <= TOL and rel_err(gw, gw_want) <= TOL, f"pair={pair}"
+        outs[pair] = (out, gx, gw)
+    # both modes accumulate each output in the same k order: identical bits
+    assert all(torch.equal(a, b) for a, b in zip(outs[False], outs[True]))
+
+
 def test_discriminator_tail_and_soft_ce_golden(lib, golden):
     import rnd_semantic_segmentation_b200 as b200
     g = golden("discriminator")
