@@ -366,6 +366,8 @@ def run_ours(args):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = run_cpu_reference(args.workload, steps=2, warmup=1)["cpu_baseline"]
+        eval_obj["cpu_baseline"] = run_cpu_eval_reference()
+        adv["cpu_baseline"] = run_cpu_adv_reference()
 
     if rank == 0:
         line = {"metric": "aspp_ce_train_Mpx_per_s", "value": round(value, 2), "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
@@ -475,6 +477,55 @@ def run_cpu_reference(workload, steps, warmup):
     sample = f"{ns} of the {n} images of workload {workload} per step ({ns}x{cin}x{h}x{w} features, {ns}x{H}x{W} labels), torch {torch.__version__} CPU fp32"
     return {"value": value, "ms_per_step": dt * 1e3,
             "cpu_baseline": {"value": round(value, 4), "unit": "Mpx/s", "cores": cores, "kind": "port", "sample": sample}}
+
+
+def run_cpu_eval_reference():
+    """the reference's eval frame on the host cores -- head forward, interpolate + softmax + max(1)[1]
+    (utility.py:183-186, aspp_tester.py:63), then the confusion matrix: the reference's literal per-pixel Python loop
+    (utility.py:347-359) timed on a 1/64 crop and extrapolated, and the vectorised bincount equivalent as the fair CPU row."""
+    from oracle import torch_oracle as to
+    from rnd_semantic_segmentation_b200 import synth
+    n, cin, h, w, H, W, C = synth.WORKLOADS["eval_1024x2048"]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(99)
+    head = synth.scale_head_for_unit_logits(to.AsppHeadOracle(cin, RATES, RATES, C))
+    x = synth.make_features(1, cin, h, w, seed=99)
+    y = synth.make_labels(1, H, W, C, seed=199)
+    to.eval_frame(head, x, y, C)                                            # warm-up
+    t0 = time.perf_counter()
+    pred, _, _ = to.eval_frame(head, x, y, C)
+    dt = time.perf_counter() - t0
+    crop = (slice(None), slice(0, H // 8), slice(0, W // 8))
+    t0 = time.perf_counter()
+    to.confusion_matrix_loop(C, pred[crop].flatten(), y[crop].flatten())
+    dt_loop = (time.perf_counter() - t0) * 64
+    return {"value": round(1.0 / dt, 3), "unit": "img/s", "cores": cores, "kind": "port",
+            "sample": f"1 frame 1x{cin}x{h}x{w} -> {H}x{W}: head fwd + interpolate/softmax/argmax + bincount confusion matrix + intersectionAndUnion",
+            "with_reference_python_loop_confusion_matrix": {"value": round(1.0 / (dt + dt_loop), 4), "unit": "img/s",
+                                                            "note": "utility.py:347-359 per-pixel loop timed on a 1/64 crop, x64"}}
+
+
+def run_cpu_adv_reference():
+    """the full aspp_fada.py:91-125 sequence after the backbone (forward AND backward) on the host cores, on a
+    bounded sample: 1 source + 1 target image of the 4 + 4 of BASELINE configs[2]."""
+    from oracle import torch_oracle as to
+    from rnd_semantic_segmentation_b200 import synth
+    n, cin, h, w, H, W, C = synth.WORKLOADS["deeplabv2_r101_adv"]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(4321)
+    head = to.AsppHeadOracle(cin, RATES, RATES, C)
+    model_D = to.PixelDiscriminatorOracle(cin, 256, num_classes=C)
+    src = synth.make_features(1, cin, h, w, seed=555)
+    tgt = synth.make_features(1, cin, h, w, seed=777)
+    lab = synth.make_labels(1, H, W, C, seed=555)
+    to.fada_step(head, model_D, src, tgt, lab)                              # warm-up
+    t0 = time.perf_counter()
+    to.fada_step(head, model_D, src, tgt, lab)
+    dt = time.perf_counter() - t0
+    return {"value": round(2 * H * W / dt / 1e6, 4), "unit": "Mpx/s", "cores": cores, "kind": "port", "ms_per_step": round(dt * 1e3, 1),
+            "sample": f"1 + 1 of the {n} + {n} images of workload deeplabv2_r101_adv per step, torch {torch.__version__} CPU fp32"}
 
 
 def run_reference(args):

@@ -275,3 +275,31 @@ def fada_losses(head: nn.Module, model_D: nn.Module, src_fea, tgt_fea, src_label
     loss_D_src = 0.5 * soft_label_cross_entropy(model_D(src_fea.detach(), size), src_q0)
     loss_D_tgt = 0.5 * soft_label_cross_entropy(model_D(tgt_fea.detach(), size), tgt_q1)
     return dict(loss_seg=loss_seg, loss_adv_tgt=loss_adv_tgt, loss_D_src=loss_D_src, loss_D_tgt=loss_D_tgt)
+
+
+def fada_step(head: nn.Module, model_D: nn.Module, src_fea, tgt_fea, src_label,
+              temperature: float = 1.8, ignore_index: int = 255):
+    """One adversarial iteration after the backbone INCLUDING the backward passes, in the reference's order
+    (aspp_fada.py:91-125; optimizer steps excluded, so all three D passes see the same D weights).
+    Returns the four scalar losses."""
+    size = src_label.shape[-2:]
+    for p in list(head.parameters()) + list(model_D.parameters()):
+        p.grad = None
+    src_fea = src_fea.detach().requires_grad_(True)
+    tgt_fea = tgt_fea.detach().requires_grad_(True)
+    src_pred = head(src_fea, size).div(temperature)                                  # :92-94
+    loss_seg = hard_cross_entropy(src_pred, src_label, ignore_index)
+    loss_seg.backward()                                                              # :96
+    src_soft = build_soft_label(src_pred.detach(), slot=0)                           # :99-100 (+ cat of :120)
+    tgt_pred = head(tgt_fea, size).div(temperature)                                  # :103-104
+    tgt_q0 = build_soft_label(tgt_pred.detach(), slot=0)                             # :105-108, cat of :111
+    tgt_q1 = build_soft_label(tgt_pred.detach(), slot=1)                             # cat of :124
+    loss_adv_tgt = 0.001 * soft_label_cross_entropy(model_D(tgt_fea, size), tgt_q0)  # :110-112
+    loss_adv_tgt.backward()
+    for p in model_D.parameters():                                                   # optimizer_D.zero_grad(), :117
+        p.grad = None
+    loss_D_src = 0.5 * soft_label_cross_entropy(model_D(src_fea.detach(), size), src_soft)   # :119-121
+    loss_D_src.backward()
+    loss_D_tgt = 0.5 * soft_label_cross_entropy(model_D(tgt_fea.detach(), size), tgt_q1)     # :123-125
+    loss_D_tgt.backward()
+    return loss_seg.detach(), loss_adv_tgt.detach(), loss_D_src.detach(), loss_D_tgt.detach()
