@@ -402,6 +402,8 @@ def run_adv_step(b200, _lib, synth, dev, rank, world, peaks, args):
     size = (aH, aW)
     b200.set_feature_pack_cache(2)
 
+    freeze = [False]
+
     def adv_step():
         b200.clear_feature_pack_cache()                       # new features every iteration: 2 conversions per step, not 0
         for p in list(head.parameters()) + list(model_D.parameters()):
@@ -412,10 +414,14 @@ def run_adv_step(b200, _lib, synth, dev, rank, world, peaks, args):
         loss_seg.backward()
         with torch.no_grad():
             tgt_lr = head.logits(tgt_fea)                                                # :101-104 (soft labels are detached)
+        if freeze[0]:                                         # variant: D's own gradients of this pass are discarded at :117 anyway
+            for p in model_D.parameters():
+                p.requires_grad_(False)
         loss_adv = 0.001 * model_D.forward_soft_loss(tgt_fea, tgt_lr, size, slot=0)      # :110-112
         loss_adv.backward()
         for p in model_D.parameters():                                                   # optimizer_D.zero_grad(), :117
             p.grad = None
+            p.requires_grad_(True)
         loss_d_src = 0.5 * model_D.forward_soft_loss(src_fea.detach(), src_lr, size, slot=0)   # :119-121
         loss_d_src.backward()
         loss_d_tgt = 0.5 * model_D.forward_soft_loss(tgt_fea.detach(), tgt_lr, size, slot=1)   # :123-125
@@ -432,6 +438,9 @@ def run_adv_step(b200, _lib, synth, dev, rank, world, peaks, args):
     torch.cuda.synchronize()
     prof = _lib.profile_read()
     _lib.profile_enable(False)
+    freeze[0] = True
+    ms_frozen, _ = timed(adv_step, args.steps, args.warmup)
+    freeze[0] = False
     b200.set_feature_pack_cache(0)
     P = an * ah * aw
     # algorithmic FLOPs of one discriminator conv-stack pass (true channel counts, dense 3x3 taps)
@@ -450,6 +459,10 @@ def run_adv_step(b200, _lib, synth, dev, rank, world, peaks, args):
                          "achieved": round(tf, 1), "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": round(tf / peaks["bf16_tflops_sustained"], 4), "traffic": load_traffic("conv3x3_fwd"),
                          "algorithmic_flops_per_step": f_step, "conv_ms_per_step": round(conv_ms, 4)},
+            "variants": {"discriminator_frozen_in_adversarial_pass": {
+                "ms_per_step": round(ms_frozen / args.steps, 4),
+                "note": "model_D parameters set requires_grad=False around aspp_fada.py:110-112: the weight gradients that pass "
+                        "would compute are zeroed at :117 before anyone reads them, so the parameter updates are identical"}},
             "kernels": {k: {"ms_per_step": round(v[0] / 4, 4), "launches_per_step": v[1] / 4} for k, v in prof.items()}}
 
 

@@ -10,7 +10,7 @@ from .classifier import ASPP_Classifier_V2
 from .discriminator import PixelDiscriminator
 from .install import install
 from .ops import (aspp_head, aspp_head_loss, clear_feature_pack_cache, fada_soft_label_loss, set_feature_pack_cache, soft_label_cross_entropy, upsample_bilinear_align_corners, upsample_cross_entropy)
-from .utility import (AverageMeter, confusion_matrix, inference, intersectionAndUnion, intersectionAndUnionGPU,
+from .utility import (AverageMeter, OverlappedEvaluator, confusion_matrix, inference, intersectionAndUnion, intersectionAndUnionGPU,
                       iutr_from_confusion, segmentation_eval_step)
 
 __all__ = [
@@ -18,5 +18,5 @@ __all__ = [
     "ASPP_Classifier_V2", "PixelDiscriminator", "install",
     "aspp_head", "aspp_head_loss", "fada_soft_label_loss", "upsample_bilinear_align_corners", "upsample_cross_entropy", "soft_label_cross_entropy",
     "inference", "intersectionAndUnion", "intersectionAndUnionGPU", "confusion_matrix", "AverageMeter",
-    "segmentation_eval_step", "iutr_from_confusion",
+    "segmentation_eval_step", "iutr_from_confusion", "OverlappedEvaluator", "set_feature_pack_cache", "clear_feature_pack_cache",
 ]

@@ -561,6 +561,27 @@ def test_fada_iteration_losses_match_oracle(lib):
         assert ((got - exp).norm() / exp.norm()).item() <= 3e-2, name
 
 
+def test_overlapped_evaluator_bit_exact(lib):
+    """Two-stream eval loop (K4 of frame i underneath the head of frame i+1): same int64 confusion matrix as the sequential loop."""
+    import rnd_semantic_segmentation_b200 as b200
+    from rnd_semantic_segmentation_b200 import synth
+    C = 19
+    torch.manual_seed(3)
+    head = synth.scale_head_for_unit_logits(b200.ASPP_Classifier_V2(256, RATES, RATES, C)).cuda().eval()
+    frames = [(torch.relu(torch.randn(1, 256, 32, 64, generator=torch.Generator().manual_seed(10 + i))).cuda(),
+               make_labels(1, 256, 512, C, 0.1, 20 + i).cuda()) for i in range(7)]
+    cm_seq = torch.zeros(C, C, dtype=torch.int64, device="cuda")
+    for x, y in frames:
+        with torch.no_grad():
+            b200.segmentation_eval_step(head.logits(x), y, cm=cm_seq)
+    for _ in range(3):                                   # repeated: a stream-ordering bug would show up as a flaky difference
+        ov = b200.OverlappedEvaluator(head, C)
+        for x, y in frames:
+            ov.step(x, y)
+        assert torch.equal(ov.finish(), cm_seq)
+    assert int(cm_seq.sum()) == sum(int((y != 255).sum()) for _, y in frames)
+
+
 def test_discriminator_tail_and_soft_ce_golden(lib, golden):
     import rnd_semantic_segmentation_b200 as b200
     g = golden("discriminator")
