@@ -89,7 +89,15 @@ class HeadGradBucket(FlatGradBucket):
     with the data-gradient GEMM.  ``wait()`` joins the two streams before the optimizer (or anything else) reads .grad.
     Gradients are overwritten each step, not accumulated (zero_grad-every-step semantics of the reference trainers)."""
 
-    def __init__(self, head: torch.nn.Module, group=None, overlap_ctas: int = 8):
+    def __init__(self, head: torch.nn.Module, group=None, overlap_ctas: Optional[int] = None):
+        # CTAs of the overlapped all-reduce = SMs the dgrad GEMM leaves free.  The collective has to finish inside the
+        # ~180 us dgrad window: measured on B200 boxes (profiles/n8_probe.py, step time in ms, 5.6 MB bucket)
+        #   2 ranks:  4 -> 0.928   8 -> 0.842   16 -> 0.846   32 -> 0.890   (no all-reduce 0.851, all-reduce afterwards 0.885)
+        #   4 ranks:  4 -> 0.989   8 -> 0.885   16 -> 0.857   32 -> 0.868   (no all-reduce 0.852, all-reduce afterwards 0.892)
+        #   8 ranks:  4 -> 1.277   8 -> 1.068   16 -> 0.971   32 -> 0.867   (no all-reduce 0.854, all-reduce afterwards 0.944)
+        if overlap_ctas is None:
+            world = dist.get_world_size() if is_distributed() else 1
+            overlap_ctas = 8 if world <= 2 else (16 if world <= 4 else 32)
         convs = list(head.conv2d_list)
         # bucket order: the R weights, then the R biases as one [R, C] block
         super().__init__([m.weight for m in convs] + [m.bias for m in convs])
