@@ -122,6 +122,13 @@ class HeadGradBucket(FlatGradBucket):
         self._pending = False
         nb = sum(m.bias.numel() for m in convs)
         self._bias_block = self.flat[self.flat.numel() - nb:].view(self.R, -1)
+        # NCCL builds a communicator's channels lazily on its first collectives (tens of ms): do that here, on the (all-zero)
+        # bucket, instead of inside the first training steps
+        if is_distributed() and self.flat.is_cuda:
+            with torch.cuda.stream(self.stream):
+                for _ in range(3):
+                    dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            torch.cuda.current_stream().wait_stream(self.stream)
 
     def weight_buffers(self):
         return self.views[:self.R]

@@ -50,6 +50,16 @@ def test_no_cpu_fallback(built_lib):
         b200.upsample_cross_entropy(torch.randn(1, 4, 3, 3), torch.zeros(1, 6, 6, dtype=torch.int64))
     with pytest.raises(B200SegError):
         b200.confusion_matrix(4, torch.zeros(5, dtype=torch.int64), torch.zeros(5, dtype=torch.int64))
+    # the discriminator's conv stack is ours too (K6): no cuDNN / CPU path behind it
+    D = b200.PixelDiscriminator(16, 16, num_classes=3)
+    with pytest.raises(B200SegError):
+        D(torch.randn(1, 16, 8, 8))
+    with pytest.raises(B200SegError):
+        D.forward_soft_loss(torch.randn(1, 16, 8, 8), torch.randn(1, 3, 8, 8), (16, 16), slot=0)
+    # C-ABI argument errors are reported, not crashed on, without a device
+    assert built_lib.b200seg_conv3x3_wgrad_scratch_bytes(4, 64, 128, 256, 2048, 1) == 9 * 256 * 2048 * 4 + 256
+    assert built_lib.b200seg_nhwc_colsum_scratch_bytes(256) > 0
+    assert built_lib.b200seg_conv3x3_forward(None, 1, 8, 8, 16, 16, None, 16, 1, None, 0, 0.0, None, 16, None, None) != 0
 
 
 def _cfg(name="deeplab_resnet101", C=19):
