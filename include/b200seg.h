@@ -219,6 +219,9 @@ B200SEG_API int b200seg_profile_read(int tag, double* total_ms, int* count);
  *        3 = 2 x 2 cluster multicasting both, 4 = CTA pair on one tcgen05.mma.cta_group::2 (M = 256). */
 B200SEG_API int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b_mn_major, int splits, int col_hw, int share,
                           double* max_err, double* max_ref);
+/* head forward GEMM: 1 (default) = the tile width (256 / 224 / 192 accumulator columns) is chosen per problem so that the tile
+ * count is a near-multiple of the SM count (wave quantisation), 0 = always 256 */
+B200SEG_API void b200seg_gemm_set_narrow_tiles(int on);
 /* K6 conv kernel: 1 (default) = CTA pairs driving one tcgen05.mma.cta_group::2 (M = 256) wherever a layer has two M-tiles,
  * 0 = one CTA per tile (A/B experiments) */
 B200SEG_API void b200seg_conv_set_pair(int on);

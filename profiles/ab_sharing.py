@@ -1,5 +1,5 @@
-"""A/B: head GEMMs without multicast (0), with 2-CTA multicast pairs (1), with 2 x 2 clusters (2), with cta_group::2 pairs on the
-data-gradient GEMM (3); per-kernel CUDA-event timing."""
+"""A/B of the head GEMMs' operand-sharing modes (b200seg_gemm_set_sharing): 5 = 2-CTA multicast pairs only (the earlier default),
+1 = cta_group::2 pairs for forward / weight gradient (current default); per-kernel CUDA-event timing."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -18,7 +18,7 @@ def step():
     loss, _ = head.forward_loss(xg, labels); loss.backward()
     return loss
 b200.set_feature_pack_cache(0)
-for on in (1, 3, 0, 1, 3):
+for on in (5, 1, 5, 1):
     _lib.gemm_set_sharing(on)
     for _ in range(3): step()
     torch.cuda.synchronize()

@@ -77,6 +77,7 @@ SIGNATURES = {
     "b200seg_gemm_selftest": (c_int, [c_int] * 8 + [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "b200seg_gemm_set_sharing": (None, [c_int]),
     "b200seg_conv_set_pair": (None, [c_int]),
+    "b200seg_gemm_set_narrow_tiles": (None, [c_int]),
 }
 
 
@@ -107,6 +108,8 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
     _lib = lib
     if os.environ.get("B200SEG_GEMM_SHARING"):        # A/B experiments (profiles/): operand-sharing mode of the head GEMMs
         lib.b200seg_gemm_set_sharing(int(os.environ["B200SEG_GEMM_SHARING"]))
+    if os.environ.get("B200SEG_GEMM_NARROW"):
+        lib.b200seg_gemm_set_narrow_tiles(int(os.environ["B200SEG_GEMM_NARROW"]))
     if os.environ.get("B200SEG_CONV_PAIR"):
         lib.b200seg_conv_set_pair(int(os.environ["B200SEG_CONV_PAIR"]))
     return lib
@@ -632,13 +635,23 @@ def nhwc_bf16_colsum(g: torch.Tensor, C: Optional[int] = None) -> torch.Tensor:
 
 
 def default_wgrad_splits(P: int, C: int, Cin: int, R: int) -> int:
-    """Split-K factor for the weight-gradient GEMM: fill ~2 waves of SMs without oversplitting."""
+    """Split-K factor for the weight-gradient GEMM.  It runs as CTA pairs (two M-tiles per pair, 74 pairs): take the smallest
+    factor >= 4 whose pair-unit count fills whole rounds of the 74 pairs best (NJ = 640, Cin = 2048: 3 x 8 x 6 = 144 units = 2 rounds
+    at 97 %)."""
     NJ = aspp_packed_rows(C, R)
-    tiles = ((NJ + 127) // 128) * ((Cin + 255) // 256)
+    pairs_m = ((NJ + 127) // 128 + 1) // 2
+    tiles = pairs_m * ((Cin + 255) // 256)
     kb = (P + 63) // 64
-    sms = 148
-    best = max(1, min(kb, (2 * sms + tiles - 1) // tiles))
-    return int(best)
+    workers = 74
+    best, best_eff = 1, -1.0
+    for s in range(1, 17):
+        if s > kb:
+            break
+        units = tiles * s
+        eff = units / (((units + workers - 1) // workers) * workers)
+        if s >= 4 and eff > best_eff + 1e-9:
+            best, best_eff = s, eff
+    return int(best if best_eff > 0 else max(1, min(kb, 4)))
 
 
 def gemm_selftest(M, N, K, a_mn=False, b_mn=False, splits=1, col_hw=0, share=0):
@@ -646,6 +659,11 @@ def gemm_selftest(M, N, K, a_mn=False, b_mn=False, splits=1, col_hw=0, share=0):
     err, ref = ctypes.c_double(0), ctypes.c_double(0)
     _check(lib.b200seg_gemm_selftest(M, N, K, int(a_mn), int(b_mn), splits, col_hw, int(share), ctypes.byref(err), ctypes.byref(ref)))
     return err.value, ref.value
+
+
+def gemm_set_narrow_tiles(on):
+    """Head forward GEMM: True (default) = 256 / 224 / 192-column tiles chosen per problem against wave quantisation."""
+    load().b200seg_gemm_set_narrow_tiles(1 if on else 0)
 
 
 def conv_set_pair(on):

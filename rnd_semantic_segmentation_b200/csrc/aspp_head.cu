@@ -381,7 +381,9 @@ int aspp_forward(const void* Xp, const void* Wp, const float* bias_sum, const in
   const long long ypitch = ceil_div_ll(P, 4) * 4;
   gemm::Operand a{(const __nv_bfloat16*)Wp, false, Cin};
   gemm::Operand b{(const __nv_bfloat16*)Xp, false, Cin};
-  int rc = gemm::launch(a, b, NJ, (int)P, Cin, 1, Yt, ypitch, 0, 0, 0, stream, nullptr, 0, gemm::SHARE_A);
+  // CTA pairs on one tcgen05.mma.cta_group::2 along M (NJ = 640 = 5 M-tiles -> 3 pairs, the last one half empty): each SM
+  // pulls 32 KB per k-block instead of 48 KB -- 143 vs 154 us at the bench workload although a sixth of the pair slots idles
+  int rc = gemm::launch(a, b, NJ, (int)P, Cin, 1, Yt, ypitch, 0, 0, 0, stream, nullptr, 0, gemm::SHARE_PAIR, false, 0, gemm::SHARE_A);
   if (rc) return rc;
   TapTable tt;
   make_taps(tt, rates, R);
@@ -461,7 +463,8 @@ int aspp_backward_packed(const void* gOt_in, const void* Xp, const void* WpT, co
       gemm::Operand b{(const __nv_bfloat16*)Xp, true, Cin};
       int used = 1;
       const long long slab = (long long)NJ * Cin;
-      int rc = gemm::launch(a, b, NJ, Cin, (int)P, splits, wpart, Cin, 0, 0, slab, stream, &used, 2, gemm::SHARE_A);
+      int rc = gemm::launch(a, b, NJ, Cin, (int)P, splits, wpart, Cin, 0, 0, slab, stream, &used, 2, gemm::SHARE_PAIR, false, 0,
+                            gemm::SHARE_A);                       // cta_group::2 pairs: 138 vs 165 us
       if (rc) return rc;
       dim3 grid(ceil_div(Cin, 256), C, R);
       profile_begin(10, stream);

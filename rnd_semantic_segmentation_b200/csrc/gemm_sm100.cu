@@ -43,21 +43,27 @@ static int make_tmap(CUtensorMap* m, const __nv_bfloat16* ptr, long long inner, 
   return B200SEG_OK;
 }
 
+static int sms_total() { return num_sms(); }
 static int g_overlap_sms = 8;         // b200seg_gemm_set_overlap_sms(): SMs left free while an all-reduce overlaps the dgrad GEMM
 void set_overlap_sms(int n) { g_overlap_sms = n < 0 ? 0 : n; }
 int overlap_sms() { return g_overlap_sms; }
-static int g_share_enabled = 1;      // b200seg_gemm_set_sharing(): 0 no multicast, 1 (default) 2-CTA multicast pairs, 2 2 x 2 clusters (measured ~1.9x slower: 37 four-CTA clusters do not all fit the GPCs), 3 = 1 + cta_group::2 pairs where the caller shares B along M (measured: no gain on the store-bound dgrad)
+// b200seg_gemm_set_sharing(): 0 one CTA per tile; 1 (default) what each caller asks for -- cta_group::2 pairs for the forward,
+// weight-gradient and seam-format data-gradient GEMMs, 2-CTA multicast pairs for the fp32 NCHW data gradient; 2 2 x 2 clusters
+// (measured ~1.9x slower: 37 four-CTA clusters do not all fit the GPCs); 3 = 1 with the fp32 data gradient as cta_group::2
+// pairs too (measured 5 us slower: it is store-bound); 4 = every shared GEMM as cta_group::2 pairs; 5 = no cta_group::2 (the
+// multicast pairs of the earlier rounds)
+static int g_share_enabled = 1;
 void set_sharing(int on) { g_share_enabled = on; }
 
-template <bool A_MN, bool B_MN, int SHARE>
+template <bool A_MN, bool B_MN, int SHARE, int BN = 256>
 static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    B200SEG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, SHARE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    B200SEG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, SHARE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
   if (SHARE == SHARE_NONE) {
-    gemm_bf16_kernel<A_MN, B_MN, SHARE><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+    gemm_bf16_kernel<A_MN, B_MN, SHARE, BN><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -71,10 +77,25 @@ static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const Params& 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    B200SEG_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, SHARE>, ta, tb, p));
+    B200SEG_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, SHARE, BN>, ta, tb, p));
   }
   B200SEG_LAUNCH_CHECK();
   return B200SEG_OK;
+}
+
+static int g_narrow_tiles = 1;        // b200seg_gemm_set_narrow_tiles(): 0 = always 256-column tiles
+void set_narrow_tiles(int on) { g_narrow_tiles = on; }
+
+// K-major x K-major, fp32 out, unshared B: tile width chosen by the caller (wave quantisation)
+static int launch_kk(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, int share, int bn, cudaStream_t stream) {
+  if (share == SHARE_A) {
+    if (bn == 224) return launch_t<false, false, SHARE_A, 224>(ta, tb, p, grid, stream);
+    if (bn == 192) return launch_t<false, false, SHARE_A, 192>(ta, tb, p, grid, stream);
+    return launch_t<false, false, SHARE_A, 256>(ta, tb, p, grid, stream);
+  }
+  if (bn == 224) return launch_t<false, false, SHARE_NONE, 224>(ta, tb, p, grid, stream);
+  if (bn == 192) return launch_t<false, false, SHARE_NONE, 192>(ta, tb, p, grid, stream);
+  return launch_t<false, false, SHARE_NONE, 256>(ta, tb, p, grid, stream);
 }
 
 template <bool A_MN, bool B_MN>
@@ -88,16 +109,18 @@ static int launch_s(const CUtensorMap& ta, const CUtensorMap& tb, const Params& 
 
 int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, float* out, long long row_stride,
            int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used, int prof_tag,
-           int share, bool out_bf16, int sm_reserve) {
+           int share, bool out_bf16, int sm_reserve, int pair_fallback) {
   B200SEG_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem %dx%dx%d", M, N, K);
   B200SEG_CHECK_ARG(!out_bf16 || (col_hw <= 0 && N % 8 == 0 && row_stride % 8 == 0 && split_stride % 8 == 0 &&
                                   (reinterpret_cast<uintptr_t>(out) & 15) == 0),
                     "gemm: bf16 output needs plain row-major D with N, row pitch multiples of 8 and a 16-byte aligned base");
-  const bool explicit_pair = share == SHARE_PAIR;                           // the self-test asks for the mode by number
+  // callers name the sharing geometry they want; the global mode (A/B experiments) can veto or override it
   if (!g_share_enabled) share = SHARE_NONE;
-  if (g_share_enabled == 2 && share != SHARE_NONE) share = SHARE_AB;        // callers name the operand worth sharing; 2 x 2 shares both
+  if (g_share_enabled == 2 && share != SHARE_NONE) share = SHARE_AB;        // 2 x 2 clusters sharing both operands
   if (g_share_enabled != 2 && share == SHARE_AB) share = SHARE_A;
-  if ((g_share_enabled == 3 && share == SHARE_B) || (g_share_enabled && explicit_pair)) share = SHARE_PAIR;   // pairs along M sharing B: one 2-SM MMA
+  if (g_share_enabled == 3 && share == SHARE_B) share = SHARE_PAIR;         // also the store-bound fp32 dgrad as 2-SM pairs
+  if (g_share_enabled == 4 && (share == SHARE_A || share == SHARE_B)) share = SHARE_PAIR;
+  if (g_share_enabled == 5 && share == SHARE_PAIR) share = pair_fallback;   // no cta_group::2: the multicast pairs used before
   Params p;
   p.M = M; p.N = N; p.K = K;
   p.m_tiles = ceil_div(M, BLOCK_M);
@@ -125,13 +148,29 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
   if (share == SHARE_PAIR && p.m_tiles < 2) share = SHARE_NONE;
   if (share == SHARE_A && p.n_tiles < 2) share = SHARE_NONE;
 
+  // tile width: with K-major operands, fp32 output and an unshared B tile, a narrower tile that makes the tile count a
+  // near-multiple of the worker count beats 256 columns (rounds x columns is the cost)
+  int bn = BLOCK_N;
+  if (g_narrow_tiles && !a.mn_major && !b.mn_major && !out_bf16 && (share == SHARE_NONE || share == SHARE_A)) {
+    const int workers = share == SHARE_A ? sms_total() / 2 : sms_total();
+    long long best = -1;
+    for (int cand : {256, 224, 192}) {
+      const int nt = ceil_div(N, cand);
+      if (share == SHARE_A && nt < 2) continue;
+      const long long units = (long long)p.m_tiles * (share == SHARE_A ? (nt + 1) / 2 : nt) * p.splits;
+      const long long cost = ceil_div_ll(units, workers) * cand;
+      if (best < 0 || cost < best) { best = cost; bn = cand; }
+    }
+    p.n_tiles = ceil_div(N, bn);
+  }
+
   // the shared operand is loaded in halves (one per CTA of the pair): halve its K-major box
   CUtensorMap ta, tb;
   int rc;
   if (!a.mn_major) rc = make_tmap(&ta, a.ptr, K, M, a.pitch, BLOCK_K, (share == SHARE_A || share == SHARE_AB) ? BLOCK_M / 2 : BLOCK_M);
   else rc = make_tmap(&ta, a.ptr, M, K, a.pitch, 64, BLOCK_K);
   if (rc) return rc;
-  if (!b.mn_major) rc = make_tmap(&tb, b.ptr, K, N, b.pitch, BLOCK_K, (share == SHARE_B || share == SHARE_AB || share == SHARE_PAIR) ? BLOCK_N / 2 : BLOCK_N);
+  if (!b.mn_major) rc = make_tmap(&tb, b.ptr, K, N, b.pitch, BLOCK_K, (share == SHARE_B || share == SHARE_AB || share == SHARE_PAIR) ? BLOCK_N / 2 : bn);
   else rc = make_tmap(&tb, b.ptr, N, K, b.pitch, 64, BLOCK_K);
   if (rc) return rc;
 
@@ -152,7 +191,8 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
     grid = cs * clusters;
   }
   profile_begin(prof_tag, stream);
-  if (!a.mn_major && !b.mn_major) rc = launch_s<false, false>(ta, tb, p, grid, share, stream);
+  if (!a.mn_major && !b.mn_major && bn != BLOCK_N) rc = launch_kk(ta, tb, p, grid, share, bn, stream);
+  else if (!a.mn_major && !b.mn_major) rc = launch_s<false, false>(ta, tb, p, grid, share, stream);
   else if (a.mn_major && b.mn_major) rc = launch_s<true, true>(ta, tb, p, grid, share, stream);
   else if (a.mn_major && !b.mn_major) rc = launch_s<true, false>(ta, tb, p, grid, share, stream);
   else rc = launch_s<false, true>(ta, tb, p, grid, share, stream);

@@ -251,7 +251,11 @@ struct TileSched {
   }
 };
 
-template <bool A_MN, bool B_MN, int SHARE>
+// BN = accumulator columns per tile (256 by default).  A narrower tile (224 / 192) is picked by the host when it makes the
+// tile count a near-multiple of the SM count: 5 M-tiles x 128 N-tiles of 256 on 148 SMs are 4.3 waves = 5 rounds; the same
+// problem in 224-column tiles is 5 x 147 = 4.97 waves = 5 rounds of 12.5 % less work each.  K-major operands, fp32 output,
+// SHARE_NONE / SHARE_A only.
+template <bool A_MN, bool B_MN, int SHARE, int BN = 256>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -259,8 +263,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;                                   // 1024-byte aligned (128B swizzle atom)
   constexpr bool PAIR = SHARE == SHARE_PAIR;
+  static_assert(BN == 256 || (!A_MN && !B_MN && (SHARE == SHARE_NONE || SHARE == SHARE_A)), "narrow tiles: K-major, unshared B only");
+  static_assert(BN % 32 == 0 && BN <= 256, "epilogue halves are BN / 2 columns in chunks of 16");
+  constexpr int BLOCK_N = BN;                                       // shadows gemm::BLOCK_N below
+  constexpr int B_BYTES = BN * BLOCK_K * 2;
   constexpr int STAGES = PAIR ? PAIR_STAGES : gemm::STAGES;         // same total bytes either way
-  constexpr int STAGE_BYTES = PAIR ? PAIR_STAGE_BYTES : gemm::STAGE_BYTES;
+  constexpr int STAGE_BYTES = PAIR ? PAIR_STAGE_BYTES : gemm::STAGE_BYTES;     // ring stride (a narrow B tile leaves its tail unused)
+  constexpr int STAGE_TX = PAIR ? PAIR_STAGE_BYTES : A_BYTES + B_BYTES;        // bytes that land in a stage per k-block
   static_assert(PAIR_STAGES * PAIR_STAGE_BYTES == gemm::STAGES * gemm::STAGE_BYTES, "epilogue staging / barriers sit behind the ring");
   float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_FLOATS * 4);
@@ -319,7 +328,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const int k0 = kb * BLOCK_K;
           if (PAIR) {
             // own A tile + own half of B; both CTAs' bytes complete on the leader's full barrier
-            if (sched.rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+            if (sched.rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_TX);
             const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
             if (!A_MN) tma_load_2d_2sm(sa, &tmap_a, fb, k0, m0);
             else {
@@ -335,7 +344,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             continue;
           }
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);   // own loads + the peer's multicast half
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_TX);      // own loads + the peer's multicast half
           // ---- A ----
           if (SHARE == SHARE_A || SHARE == SHARE_AB) {
             // shared A tile: this CTA loads rows [64*ha, +64) and multicasts them to the CTAs that own the same M-tile
@@ -393,7 +402,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * gemm::BLOCK_N);      // accumulators 256 columns apart for every BN
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -433,7 +442,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       float* out = p.out + (long long)z * p.split_stride;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * (BLOCK_N / 2));
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * gemm::BLOCK_N + half * (BLOCK_N / 2));
       const int rows = min(32, p.M - row_base);
       if (p.out_bf16) {
         // bf16 row-major D (the NHWC feature gradient): 32 columns per pass, converted before the smem transpose, every
@@ -549,7 +558,7 @@ struct Operand {
 };
 int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, float* out, long long row_stride,
            int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used, int prof_tag = -1,
-           int share = SHARE_NONE, bool out_bf16 = false, int sm_reserve = 0);
+           int share = SHARE_NONE, bool out_bf16 = false, int sm_reserve = 0, int pair_fallback = SHARE_B);
 
 }  // namespace gemm
 }  // namespace b200seg

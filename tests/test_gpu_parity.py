@@ -201,6 +201,21 @@ def test_k5_fada_soft_label_loss(lib, n, C, h, w, H, W, slot):
     assert torch.equal(l3, loss) and torch.equal(d3.grad, d2.grad)        # deterministic
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 148 * 224, 64), (640, 148 * 192, 128), (100, 148 * 224 - 52, 96), (640, 32768, 192)])
+@pytest.mark.parametrize("share", [0, 2])
+def test_gemm_core_narrow_tiles(lib, M, N, K, share):
+    """Tile widths 224 / 192 (picked when they turn the tile count into whole rounds of the 148 SMs; the last shape is the eval
+    head GEMM's: 5 x 128 tiles of 256 = 5 rounds, 5 x 147 tiles of 224 = 5 shorter rounds) against the CUDA-core reference, with and
+    without 2-CTA multicast of A (odd N-tile counts leave the last pair half empty)."""
+    for narrow in (True, False):
+        lib.gemm_set_narrow_tiles(narrow)
+        try:
+            err, ref = lib.gemm_selftest(M, N, K, False, False, 1, 0, share)
+        finally:
+            lib.gemm_set_narrow_tiles(True)
+        assert ref > 0 and err <= 1e-3 * ref, (narrow, err, ref)
+
+
 # ------------------------------------------------------------------ K1
 def _head_pair(cin, C, seed):
     torch.manual_seed(seed)
