@@ -239,6 +239,23 @@ def run_ours(args):
                 "peak_source": peaks["source"] + ", sustained bf16",
                 "algorithmic_flops_per_launch": flops_per_launch, "kernels": kernels}
 
+    # ---- the same step captured once in a CUDA graph and replayed (no Python / launch overhead at all): equal to the eager
+    #      number when the step is GPU-bound.  Single-rank only (the bucket's NCCL all-reduce stays out of graphs here).
+    graph_ms = None
+    if world == 1:
+        try:
+            for p in head.parameters():
+                p.grad = None
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                train_step()
+            ms_g, _ = timed(g.replay, args.steps, args.warmup)
+            graph_ms = round(ms_g / args.steps, 4)
+            del g
+        except Exception as e:                                   # never let the extra leg break the headline line
+            log("graph replay leg skipped:", repr(e))
+            torch.cuda.synchronize()
+
     # ---- seam format: bf16 channels_last features in, bf16 channels_last feature gradient out.
     #      Reported beside the headline, which stays on the reference's fp32 NCHW contract.
     xs = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
@@ -379,7 +396,8 @@ def run_ours(args):
                            "l2": "inputs larger than L2 (features %d MB per step)" % (x.numel() * 4 // 2 ** 20),
                            "parallelism": "dp%d (batch sharded by image)" % world},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_timed), "roofline": roofline, "eval": eval_obj,
-                "seam_bf16_nhwc": seam, "aux_kernels": aux, "adv_step": adv}
+                "seam_bf16_nhwc": seam, "aux_kernels": aux, "adv_step": adv,
+                "cuda_graph_replay_ms_per_step": graph_ms}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         emit(line)

@@ -403,8 +403,10 @@ _scratch_cache = {}
 
 
 def _scratch(key, nbytes: int, device) -> torch.Tensor:
-    """Grow-only per-device scratch (stream-ordered reuse; contents never outlive one op)."""
-    k = (key, device.index if device.index is not None else torch.cuda.current_device())
+    """Grow-only scratch per (purpose, device, STREAM): reuse is ordered by the stream it is used on (contents never outlive
+    one op), and ops issued concurrently on different streams never share a buffer."""
+    dev_index = device.index if device.index is not None else torch.cuda.current_device()
+    k = (key, dev_index, torch.cuda.current_stream(device).cuda_stream)
     t = _scratch_cache.get(k)
     if t is None or t.numel() < nbytes:
         t = torch.empty(int(nbytes), dtype=torch.uint8, device=device)

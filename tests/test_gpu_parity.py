@@ -576,6 +576,62 @@ def test_fada_iteration_losses_match_oracle(lib):
         assert ((got - exp).norm() / exp.norm()).item() <= 3e-2, name
 
 
+def test_cuda_graph_capture_train_eval_and_discriminator(lib):
+    """the ops are capture-safe.  One train step (head forward_loss + backward), one eval step (head logits + fused
+    argmax / confusion) and one discriminator loss step are captured in CUDA graphs; after the inputs are overwritten in place the
+    replays must give exactly what the eager calls give on the new inputs."""
+    import rnd_semantic_segmentation_b200 as b200
+    from rnd_semantic_segmentation_b200 import synth
+    C, cin, h, w, H, W = 19, 256, 16, 32, 128, 256
+    torch.manual_seed(11)
+    head = synth.scale_head_for_unit_logits(b200.ASPP_Classifier_V2(cin, RATES, RATES, C), 5.0).cuda()
+    D = b200.PixelDiscriminator(cin, 64, num_classes=C).cuda()
+    params = list(head.parameters()) + list(D.parameters())
+    gen = torch.Generator().manual_seed(12)
+    xs = [torch.relu(torch.randn(2, cin, h, w, generator=gen)).cuda() for _ in range(2)]
+    ys = [make_labels(2, H, W, C, 0.1, 13 + i).cuda() for i in range(2)]
+    x, y = xs[0].clone(), ys[0].clone()
+    cm = torch.zeros(C, C, dtype=torch.int64, device="cuda")
+    b200.set_feature_pack_cache(0)
+    try:
+        def step(x_in, y_in, cm_in):
+            for p in params:
+                p.grad = None
+            xg = x_in.detach().requires_grad_(True)
+            loss, lg = head.forward_loss(xg, y_in)
+            loss.backward()
+            b200.segmentation_eval_step(lg, y_in, cm=cm_in)
+            xd = x_in.detach().requires_grad_(True)
+            loss_d = D.forward_soft_loss(xd, lg, (H, W), slot=1)
+            loss_d.backward()
+            return loss, xg.grad, loss_d, xd.grad
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                     # warm-up: lazy kernel attributes, packed weights, scratch
+            for _ in range(3):
+                step(x, y, cm)
+        torch.cuda.current_stream().wait_stream(side)
+        for p in params:
+            p.grad = None
+        cm.zero_()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            outs = step(x, y, cm)
+            grads = [p.grad for p in params]
+        for i in (1, 0, 1):
+            x.copy_(xs[i]); y.copy_(ys[i]); cm.zero_()
+            graph.replay()
+            torch.cuda.synchronize()
+            got = [t.clone() for t in outs] + [g.clone() for g in grads] + [cm.clone()]
+            cm_e = torch.zeros_like(cm)
+            want = list(step(xs[i], ys[i], cm_e)) + [p.grad for p in params] + [cm_e]
+            for a, b in zip(got, want):
+                assert torch.equal(a, b)
+    finally:
+        b200.set_feature_pack_cache(2)
+
+
 def test_overlapped_evaluator_bit_exact(lib):
     """Two-stream eval loop (K4 of frame i underneath the head of frame i+1): same int64 confusion matrix as the sequential loop."""
     import rnd_semantic_segmentation_b200 as b200
