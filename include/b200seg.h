@@ -222,6 +222,9 @@ B200SEG_API int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b
 /* head forward GEMM: 1 (default) = the tile width (256 / 224 / 192 accumulator columns) is chosen per problem so that the tile
  * count is a near-multiple of the SM count (wave quantisation), 0 = always 256 */
 B200SEG_API void b200seg_gemm_set_narrow_tiles(int on);
+/* fp32 NCHW data-gradient GEMM tile order: 1 = consecutive tiles walk along the pixel axis (each channel row of dX is written as
+ * long sequential runs), 0 = along the channel axis (tiles sharing the gradient operand adjacent in time) */
+B200SEG_API void b200seg_gemm_set_dgrad_n_fastest(int on);
 /* K6 conv kernel: 1 (default) = CTA pairs driving one tcgen05.mma.cta_group::2 (M = 256) wherever a layer has two M-tiles,
  * 0 = one CTA per tile (A/B experiments) */
 B200SEG_API void b200seg_conv_set_pair(int on);

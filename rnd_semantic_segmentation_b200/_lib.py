@@ -78,6 +78,7 @@ SIGNATURES = {
     "b200seg_gemm_set_sharing": (None, [c_int]),
     "b200seg_conv_set_pair": (None, [c_int]),
     "b200seg_gemm_set_narrow_tiles": (None, [c_int]),
+    "b200seg_gemm_set_dgrad_n_fastest": (None, [c_int]),
 }
 
 
@@ -108,6 +109,8 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
     _lib = lib
     if os.environ.get("B200SEG_GEMM_SHARING"):        # A/B experiments (profiles/): operand-sharing mode of the head GEMMs
         lib.b200seg_gemm_set_sharing(int(os.environ["B200SEG_GEMM_SHARING"]))
+    if os.environ.get("B200SEG_DGRAD_N_FASTEST"):
+        lib.b200seg_gemm_set_dgrad_n_fastest(int(os.environ["B200SEG_DGRAD_N_FASTEST"]))
     if os.environ.get("B200SEG_GEMM_NARROW"):
         lib.b200seg_gemm_set_narrow_tiles(int(os.environ["B200SEG_GEMM_NARROW"]))
     if os.environ.get("B200SEG_CONV_PAIR"):

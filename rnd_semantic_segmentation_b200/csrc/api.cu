@@ -91,6 +91,7 @@ int selftest(int, int, int, int, int, int, int, int, double*, double*);
 void set_sharing(int);
 void set_overlap_sms(int);
 void set_narrow_tiles(int);
+void set_n_fastest(int);
 }
 
 static int require_device() {
@@ -352,6 +353,7 @@ int b200seg_profile_read(int tag, double* total_ms, int* count) {
 void b200seg_conv_set_pair(int on) { gemm::conv::set_pair(on); }
 void b200seg_gemm_set_sharing(int on) { gemm::set_sharing(on); }
 void b200seg_gemm_set_narrow_tiles(int on) { gemm::set_narrow_tiles(on); }
+void b200seg_gemm_set_dgrad_n_fastest(int on) { gemm::set_n_fastest(on); }
 void b200seg_gemm_set_overlap_sms(int n) { gemm::set_overlap_sms(n); }
 
 int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b_mn_major, int splits, int col_hw, int share, double* max_err,

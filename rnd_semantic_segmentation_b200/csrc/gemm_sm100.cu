@@ -83,6 +83,8 @@ static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const Params& 
   return B200SEG_OK;
 }
 
+static int g_n_fastest = 0;
+void set_n_fastest(int on) { g_n_fastest = on; }
 static int g_narrow_tiles = 1;        // b200seg_gemm_set_narrow_tiles(): 0 = always 256-column tiles
 void set_narrow_tiles(int on) { g_narrow_tiles = on; }
 
@@ -136,6 +138,7 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
   p.img_stride = img_stride;
   p.split_stride = split_stride;
   p.out_bf16 = out_bf16 ? 1 : 0;
+  p.n_fastest = g_n_fastest && col_hw > 0 ? 1 : 0;          // the fp32 NCHW data gradient (store-bound)
   if (splits_used) *splits_used = p.splits;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && row_stride % 4 == 0 && split_stride % 4 == 0 &&
               (col_hw <= 0 || (col_hw % 4 == 0 && img_stride % 4 == 0)))

@@ -46,6 +46,7 @@ struct Params {
   long long split_stride;   // elements between split-K partial slabs
   int vec_ok;               // output addressing allows 16-byte vector stores
   int out_bf16;             // D is written as bf16 (plain row-major [M][row_stride], 16-byte aligned rows) instead of fp32
+  int n_fastest;            // tile order: consecutive work units walk along N (rows of D are written as long sequential runs)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -229,8 +230,9 @@ __device__ __forceinline__ uint32_t cluster_cta_rank() {
 // work unit -> (split z, M-tile, N-tile) of this CTA
 template <int SHARE>
 struct TileSched {
-  int units, worker, nworkers, rank, m_tiles, n_tiles, per_split;
+  int units, worker, nworkers, rank, m_tiles, n_tiles, per_split, n_fastest;
   __device__ TileSched(const Params& p) {
+    n_fastest = p.n_fastest;
     constexpr int CS = SHARE == SHARE_NONE ? 1 : (SHARE == SHARE_AB ? 4 : 2);      // CTAs per cluster
     rank = SHARE != SHARE_NONE ? (int)cluster_cta_rank() : 0;
     worker = (int)blockIdx.x / CS;
@@ -243,8 +245,13 @@ struct TileSched {
   __device__ void decode(int unit, int& z, int& mt, int& nt) const {
     z = unit / per_split;
     const int rem = unit - z * per_split;
-    nt = rem / m_tiles;                  // M fastest: tiles sharing the (large) B operand are adjacent in time
-    mt = rem - nt * m_tiles;
+    if (n_fastest) {
+      mt = rem / n_tiles;                // N fastest: the CTAs running together write neighbouring column ranges of the same rows
+      nt = rem - mt * n_tiles;
+    } else {
+      nt = rem / m_tiles;                // M fastest: tiles sharing the (large) B operand are adjacent in time
+      mt = rem - nt * m_tiles;
+    }
     if (SHARE == SHARE_B || SHARE == SHARE_PAIR) mt = mt * 2 + rank;
     if (SHARE == SHARE_A) nt = nt * 2 + rank;
     if (SHARE == SHARE_AB) { mt = mt * 2 + (rank & 1); nt = nt * 2 + (rank >> 1); }
@@ -485,11 +492,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int lane_col = p.vec_ok ? (lane & 3) * 4 : (lane & 15);
         int img = (col_base + lane_col) / p.col_hw;
         int rem = (col_base + lane_col) - img * p.col_hw;
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 2 / 16; ++c) {
-          uint32_t r[16];
-          tmem_ld16(taddr + (uint32_t)(c * 16), r);
+        // software pipeline: the TMEM load of chunk c + 1 is in flight while chunk c goes through the smem transpose and
+        // out to global memory (two register sets, loop fully unrolled so both are statically indexed)
+        constexpr int NCH = BLOCK_N / 2 / 16;
+        uint32_t rbuf[2][16];
+        tmem_ld16(taddr, rbuf[0]);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
           tmem_ld_wait();
+          const uint32_t* r = rbuf[c & 1];
+          if (c + 1 < NCH) tmem_ld16(taddr + (uint32_t)((c + 1) * 16), rbuf[(c + 1) & 1]);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             *reinterpret_cast<float4*>(stg + lane * EPI_PITCH + 4 * k) =
