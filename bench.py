@@ -459,6 +459,22 @@ def run_adv_step(b200, _lib, synth, dev, rank, world, peaks, args):
     freeze[0] = True
     ms_frozen, _ = timed(adv_step, args.steps, args.warmup)
     freeze[0] = False
+    # the whole iteration (~100 launches) captured once in a CUDA graph and replayed: what the launch gaps cost
+    graph_ms = None
+    try:
+        for p in list(head.parameters()) + list(model_D.parameters()):
+            p.grad = None
+        b200.clear_feature_pack_cache()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            adv_step()
+        b200.clear_feature_pack_cache()                      # drop the references into the graph's memory pool
+        ms_g, _ = timed(g.replay, args.steps, args.warmup)
+        graph_ms = round(ms_g / args.steps, 4)
+        del g
+    except Exception as e:
+        log("adv graph replay leg skipped:", repr(e))
+        torch.cuda.synchronize()
     b200.set_feature_pack_cache(0)
     P = an * ah * aw
     # algorithmic FLOPs of one discriminator conv-stack pass (true channel counts, dense 3x3 taps)
@@ -477,6 +493,7 @@ def run_adv_step(b200, _lib, synth, dev, rank, world, peaks, args):
                          "achieved": round(tf, 1), "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": round(tf / peaks["bf16_tflops_sustained"], 4), "traffic": load_traffic("conv3x3_fwd"),
                          "algorithmic_flops_per_step": f_step, "conv_ms_per_step": round(conv_ms, 4)},
+            "cuda_graph_replay_ms_per_step": graph_ms,
             "variants": {"discriminator_frozen_in_adversarial_pass": {
                 "ms_per_step": round(ms_frozen / args.steps, 4),
                 "note": "model_D parameters set requires_grad=False around aspp_fada.py:110-112: the weight gradients that pass "
