@@ -138,7 +138,7 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
   p.img_stride = img_stride;
   p.split_stride = split_stride;
   p.out_bf16 = out_bf16 ? 1 : 0;
-  p.n_fastest = g_n_fastest && col_hw > 0 ? 1 : 0;          // the fp32 NCHW data gradient (store-bound)
+  p.n_fastest = g_n_fastest && col_hw > 0 ? 1 : 0;          // the fp32 NCHW data gradient (store-bound)          // the fp32 NCHW data gradient (store-bound)
   if (splits_used) *splits_used = p.splits;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && row_stride % 4 == 0 && split_stride % 4 == 0 &&
               (col_hw <= 0 || (col_hw % 4 == 0 && img_stride % 4 == 0)))
