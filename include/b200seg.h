@@ -222,6 +222,10 @@ B200SEG_API int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b
 /* head forward GEMM: 1 (default) = the tile width (256 / 224 / 192 accumulator columns) is chosen per problem so that the tile
  * count is a near-multiple of the SM count (wave quantisation), 0 = always 256 */
 B200SEG_API void b200seg_gemm_set_narrow_tiles(int on);
+/* fp32 NCHW data-gradient epilogue: 1 = TMA bulk stores from swizzled shared-memory boxes (needs h*w % 16 == 0),
+ * 0 (default) = shared-memory transpose + 16-byte LSU stores.  Measured equal (180.8 vs 179.4 us): the 537 MB of writes
+ * themselves, not the store instructions, are what the kernel waits for */
+B200SEG_API void b200seg_gemm_set_tma_store(int on);
 /* fp32 NCHW data-gradient GEMM tile order: 1 = consecutive tiles walk along the pixel axis (each channel row of dX is written as
  * long sequential runs), 0 = along the channel axis (tiles sharing the gradient operand adjacent in time) */
 B200SEG_API void b200seg_gemm_set_dgrad_n_fastest(int on);

@@ -79,6 +79,7 @@ SIGNATURES = {
     "b200seg_conv_set_pair": (None, [c_int]),
     "b200seg_gemm_set_narrow_tiles": (None, [c_int]),
     "b200seg_gemm_set_dgrad_n_fastest": (None, [c_int]),
+    "b200seg_gemm_set_tma_store": (None, [c_int]),
 }
 
 
@@ -111,6 +112,8 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
         lib.b200seg_gemm_set_sharing(int(os.environ["B200SEG_GEMM_SHARING"]))
     if os.environ.get("B200SEG_DGRAD_N_FASTEST"):
         lib.b200seg_gemm_set_dgrad_n_fastest(int(os.environ["B200SEG_DGRAD_N_FASTEST"]))
+    if os.environ.get("B200SEG_TMA_STORE"):
+        lib.b200seg_gemm_set_tma_store(int(os.environ["B200SEG_TMA_STORE"]))
     if os.environ.get("B200SEG_GEMM_NARROW"):
         lib.b200seg_gemm_set_narrow_tiles(int(os.environ["B200SEG_GEMM_NARROW"]))
     if os.environ.get("B200SEG_CONV_PAIR"):
@@ -664,6 +667,11 @@ def gemm_selftest(M, N, K, a_mn=False, b_mn=False, splits=1, col_hw=0, share=0):
     err, ref = ctypes.c_double(0), ctypes.c_double(0)
     _check(lib.b200seg_gemm_selftest(M, N, K, int(a_mn), int(b_mn), splits, col_hw, int(share), ctypes.byref(err), ctypes.byref(ref)))
     return err.value, ref.value
+
+
+def gemm_set_tma_store(on):
+    """fp32 NCHW data-gradient epilogue through TMA bulk stores instead of LSU stores (default off: measured equal)."""
+    load().b200seg_gemm_set_tma_store(1 if on else 0)
 
 
 def gemm_set_narrow_tiles(on):

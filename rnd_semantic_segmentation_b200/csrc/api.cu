@@ -92,6 +92,7 @@ void set_sharing(int);
 void set_overlap_sms(int);
 void set_narrow_tiles(int);
 void set_n_fastest(int);
+void set_tma_store(int);
 }
 
 static int require_device() {
@@ -354,6 +355,7 @@ void b200seg_conv_set_pair(int on) { gemm::conv::set_pair(on); }
 void b200seg_gemm_set_sharing(int on) { gemm::set_sharing(on); }
 void b200seg_gemm_set_narrow_tiles(int on) { gemm::set_narrow_tiles(on); }
 void b200seg_gemm_set_dgrad_n_fastest(int on) { gemm::set_n_fastest(on); }
+void b200seg_gemm_set_tma_store(int on) { gemm::set_tma_store(on); }
 void b200seg_gemm_set_overlap_sms(int n) { gemm::set_overlap_sms(n); }
 
 int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b_mn_major, int splits, int col_hw, int share, double* max_err,

@@ -56,14 +56,14 @@ static int g_share_enabled = 1;
 void set_sharing(int on) { g_share_enabled = on; }
 
 template <bool A_MN, bool B_MN, int SHARE, int BN = 256>
-static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, cudaStream_t stream) {
+static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const Params& p, int grid, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     B200SEG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, SHARE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
   if (SHARE == SHARE_NONE) {
-    gemm_bf16_kernel<A_MN, B_MN, SHARE, BN><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, p);
+    gemm_bf16_kernel<A_MN, B_MN, SHARE, BN><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, to, p);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -77,36 +77,40 @@ static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const Params& 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    B200SEG_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, SHARE, BN>, ta, tb, p));
+    B200SEG_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, SHARE, BN>, ta, tb, to, p));
   }
   B200SEG_LAUNCH_CHECK();
   return B200SEG_OK;
 }
 
+static int g_tma_store = 0;          // b200seg_gemm_set_tma_store(): 1 = fp32 NCHW epilogue through TMA bulk stores (measured equal to the LSU stores: 180.8 vs 179.4 us)
+void set_tma_store(int on) { g_tma_store = on; }
 static int g_n_fastest = 0;
 void set_n_fastest(int on) { g_n_fastest = on; }
 static int g_narrow_tiles = 1;        // b200seg_gemm_set_narrow_tiles(): 0 = always 256-column tiles
 void set_narrow_tiles(int on) { g_narrow_tiles = on; }
 
 // K-major x K-major, fp32 out, unshared B: tile width chosen by the caller (wave quantisation)
-static int launch_kk(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, int share, int bn, cudaStream_t stream) {
+static int launch_kk(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const Params& p, int grid, int share, int bn,
+                     cudaStream_t stream) {
   if (share == SHARE_A) {
-    if (bn == 224) return launch_t<false, false, SHARE_A, 224>(ta, tb, p, grid, stream);
-    if (bn == 192) return launch_t<false, false, SHARE_A, 192>(ta, tb, p, grid, stream);
-    return launch_t<false, false, SHARE_A, 256>(ta, tb, p, grid, stream);
+    if (bn == 224) return launch_t<false, false, SHARE_A, 224>(ta, tb, to, p, grid, stream);
+    if (bn == 192) return launch_t<false, false, SHARE_A, 192>(ta, tb, to, p, grid, stream);
+    return launch_t<false, false, SHARE_A, 256>(ta, tb, to, p, grid, stream);
   }
-  if (bn == 224) return launch_t<false, false, SHARE_NONE, 224>(ta, tb, p, grid, stream);
-  if (bn == 192) return launch_t<false, false, SHARE_NONE, 192>(ta, tb, p, grid, stream);
-  return launch_t<false, false, SHARE_NONE, 256>(ta, tb, p, grid, stream);
+  if (bn == 224) return launch_t<false, false, SHARE_NONE, 224>(ta, tb, to, p, grid, stream);
+  if (bn == 192) return launch_t<false, false, SHARE_NONE, 192>(ta, tb, to, p, grid, stream);
+  return launch_t<false, false, SHARE_NONE, 256>(ta, tb, to, p, grid, stream);
 }
 
 template <bool A_MN, bool B_MN>
-static int launch_s(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int grid, int share, cudaStream_t stream) {
-  if (share == SHARE_PAIR) return launch_t<A_MN, B_MN, SHARE_PAIR>(ta, tb, p, grid, stream);
-  if (share == SHARE_AB) return launch_t<A_MN, B_MN, SHARE_AB>(ta, tb, p, grid, stream);
-  if (share == SHARE_B) return launch_t<A_MN, B_MN, SHARE_B>(ta, tb, p, grid, stream);
-  if (share == SHARE_A) return launch_t<A_MN, B_MN, SHARE_A>(ta, tb, p, grid, stream);
-  return launch_t<A_MN, B_MN, SHARE_NONE>(ta, tb, p, grid, stream);
+static int launch_s(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const Params& p, int grid, int share,
+                    cudaStream_t stream) {
+  if (share == SHARE_PAIR) return launch_t<A_MN, B_MN, SHARE_PAIR>(ta, tb, to, p, grid, stream);
+  if (share == SHARE_AB) return launch_t<A_MN, B_MN, SHARE_AB>(ta, tb, to, p, grid, stream);
+  if (share == SHARE_B) return launch_t<A_MN, B_MN, SHARE_B>(ta, tb, to, p, grid, stream);
+  if (share == SHARE_A) return launch_t<A_MN, B_MN, SHARE_A>(ta, tb, to, p, grid, stream);
+  return launch_t<A_MN, B_MN, SHARE_NONE>(ta, tb, to, p, grid, stream);
 }
 
 int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, float* out, long long row_stride,
@@ -177,6 +181,22 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
   else rc = make_tmap(&tb, b.ptr, N, K, b.pitch, 64, BLOCK_K);
   if (rc) return rc;
 
+  // fp32 NCHW output (the data gradient): TMA bulk stores when every 16-column chunk stays inside one image
+  CUtensorMap to = ta;
+  p.tma_store = 0;
+  if (g_tma_store && !out_bf16 && col_hw > 0 && col_hw % 16 == 0 && p.vec_ok && N % col_hw == 0) {
+    EncodeTiledFn fn = encode_fn();
+    cuuint64_t gdim[3] = {(cuuint64_t)col_hw, (cuuint64_t)M, (cuuint64_t)(N / col_hw)};
+    cuuint64_t gstr[2] = {(cuuint64_t)row_stride * 4, (cuuint64_t)img_stride * 4};
+    cuuint32_t box[3] = {16, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (fn && fn(&to, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+      p.tma_store = 1;
+    else
+      to = ta;
+  }
+
   // persistent CTAs, one per SM, minus the SMs the caller wants left free for a concurrent kernel (the NCCL all-reduce
   // of the weight gradients running underneath the data-gradient GEMM)
   int sms = num_sms() - (sm_reserve > 0 ? sm_reserve : 0);
@@ -194,11 +214,11 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
     grid = cs * clusters;
   }
   profile_begin(prof_tag, stream);
-  if (!a.mn_major && !b.mn_major && bn != BLOCK_N) rc = launch_kk(ta, tb, p, grid, share, bn, stream);
-  else if (!a.mn_major && !b.mn_major) rc = launch_s<false, false>(ta, tb, p, grid, share, stream);
-  else if (a.mn_major && b.mn_major) rc = launch_s<true, true>(ta, tb, p, grid, share, stream);
-  else if (a.mn_major && !b.mn_major) rc = launch_s<true, false>(ta, tb, p, grid, share, stream);
-  else rc = launch_s<false, true>(ta, tb, p, grid, share, stream);
+  if (!a.mn_major && !b.mn_major && bn != BLOCK_N) rc = launch_kk(ta, tb, to, p, grid, share, bn, stream);
+  else if (!a.mn_major && !b.mn_major) rc = launch_s<false, false>(ta, tb, to, p, grid, share, stream);
+  else if (a.mn_major && b.mn_major) rc = launch_s<true, true>(ta, tb, to, p, grid, share, stream);
+  else if (a.mn_major && !b.mn_major) rc = launch_s<true, false>(ta, tb, to, p, grid, share, stream);
+  else rc = launch_s<false, true>(ta, tb, to, p, grid, share, stream);
   profile_end(prof_tag, stream);
   return rc;
 }

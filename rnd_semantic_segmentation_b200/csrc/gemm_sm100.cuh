@@ -32,7 +32,8 @@ constexpr int MN_BOX_BYTES = 64 * BLOCK_K * 2;   // one MN-major TMA box: 64 k-r
 constexpr int NUM_THREADS = 384;                 // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-11 epilogue
 constexpr int EPI_WARPS = 8;                     // two per TMEM lane quarter, each owning 128 accumulator columns
 constexpr int EPI_PITCH = 20;                    // floats; 32 rows x 16 cols transpose tile, 16-byte aligned rows
-constexpr int EPI_STAGE_FLOATS = 32 * EPI_PITCH; // per epilogue warp
+constexpr int EPI_STAGE_FLOATS = 1024;           // per epilogue warp: the padded transpose tile (640 floats), or two dense
+                                                 // 32 x 16 fp32 boxes (2 x 2 KB, 64-byte swizzle) for the TMA-store epilogue
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_FLOATS * 4 + 256;
 
@@ -47,6 +48,7 @@ struct Params {
   int vec_ok;               // output addressing allows 16-byte vector stores
   int out_bf16;             // D is written as bf16 (plain row-major [M][row_stride], 16-byte aligned rows) instead of fp32
   int n_fastest;            // tile order: consecutive work units walk along N (rows of D are written as long sequential runs)
+  int tma_store;            // fp32 image-mapped D (NCHW) written by TMA bulk stores from swizzled shared-memory boxes
 };
 
 // ------------------------------------------------------------------------------------------
@@ -130,6 +132,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+// TMA bulk store of a {16 cols, 32 rows, 1 image} fp32 box from shared memory (3-D map: column-in-image, row, image)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(m), "r"(smem_src), "r"(c0),
+               "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (sm_100 format): start>>4 [0,14), LBO>>4 [16,30),
@@ -264,7 +277,8 @@ struct TileSched {
 // SHARE_NONE / SHARE_A only.
 template <bool A_MN, bool B_MN, int SHARE, int BN = 256>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_out, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
@@ -487,6 +501,46 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             __syncwarp();
           }
         }
+      } else if (p.tma_store) {
+        // fp32 NCHW D through the TMA unit: each 32 x 16 chunk goes TMEM -> registers -> a dense, 64-byte-swizzled
+        // shared-memory box (conflict-free 16-byte stores) -> one cp.async.bulk.tensor store that clips rows >= M and
+        // images >= N/hw itself.  No shared-memory read-back and no global stores through the LSU / L1: the SM-local
+        // memory pipe was this epilogue's limiter.  Two boxes per warp, so chunk c is staged while c - 1 drains.
+        if (rows > 0 && col_base < p.N) {
+          constexpr int NCH = BLOCK_N / 2 / 16;
+          uint8_t* sbuf = reinterpret_cast<uint8_t*>(stg);
+          int img = col_base / p.col_hw;
+          int rem = col_base - img * p.col_hw;
+          const uint32_t sw = (uint32_t)((lane >> 1) & 3);          // 64-byte swizzle: 16-byte chunk ^= (row / 2) % 4
+          uint32_t rbuf[2][16];
+          tmem_ld16(taddr, rbuf[0]);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            tmem_ld_wait();
+            const uint32_t* r = rbuf[c & 1];
+            if (c + 1 < NCH) tmem_ld16(taddr + (uint32_t)((c + 1) * 16), rbuf[(c + 1) & 1]);
+            uint8_t* buf = sbuf + (c & 1) * 2048;
+            if (c >= 2) {                                            // the store of chunk c - 2 has finished reading this box
+              if (lane == 0) bulk_wait_read<1>();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              *reinterpret_cast<float4*>(buf + lane * 64 + (((uint32_t)k ^ sw) << 4)) =
+                  make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), __uint_as_float(r[4 * k + 2]),
+                              __uint_as_float(r[4 * k + 3]));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&tmap_out, smem_u32(buf), rem, row_base, img);
+              bulk_commit();
+            }
+            rem += 16;
+            while (rem >= p.col_hw) { rem -= p.col_hw; ++img; }
+          }
+          if (lane == 0) bulk_wait_read<0>();                        // both boxes are free for the next tile
+          __syncwarp();
+        }
       } else if (rows > 0 && col_base < p.N) {
         // per-lane (image, offset) of its first column, advanced by 16 columns per chunk (no division in the loop)
         const int lane_col = p.vec_ok ? (lane & 3) * 4 : (lane & 15);
@@ -547,6 +601,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   }
 
+  if (warp >= 4 && lane == 0 && p.tma_store) bulk_wait_all();       // every bulk store of this warp has been written out
   tc_fence_before();
   __syncthreads();
   if (CLUSTER) cluster_sync_all();            // the peer may still multicast into / arrive on this CTA until it is done too

@@ -216,6 +216,18 @@ def test_gemm_core_narrow_tiles(lib, M, N, K, share):
         assert ref > 0 and err <= 1e-3 * ref, (narrow, err, ref)
 
 
+@pytest.mark.parametrize("M,N,K,b_mn,col_hw,share", [(2048, 1024, 640, True, 256, 1), (300, 4096, 128, False, 512, 0), (2048, 2048, 640, True, 1024, 4)])
+def test_gemm_core_tma_store_epilogue(lib, M, N, K, b_mn, col_hw, share):
+    """fp32 image-mapped (NCHW) output through TMA bulk stores from 64-byte-swizzled shared-memory boxes (optional epilogue of the
+    data-gradient GEMM), ragged M included (the TMA unit clips rows >= M)."""
+    lib.gemm_set_tma_store(True)
+    try:
+        err, ref = lib.gemm_selftest(M, N, K, False, b_mn, 1, col_hw, share)
+    finally:
+        lib.gemm_set_tma_store(False)
+    assert ref > 0 and err <= 1e-3 * ref, (err, ref)
+
+
 # ------------------------------------------------------------------ K1
 def _head_pair(cin, C, seed):
     torch.manual_seed(seed)
