@@ -126,8 +126,38 @@ def _check(rc: int):
         raise B200SegError(load().b200seg_last_error().decode("utf-8", "replace"))
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
+def _stream(device=None) -> int:
+    """cudaStream_t of torch's current stream (on ``device``, default: the current device).  The raw getter costs a fraction
+    of a microsecond; torch.cuda.current_stream() builds a Stream object and resolves the device index (~15 us) -- with a
+    dozen launches per step that alone was 0.1 ms of host time per step."""
+    if device is not None and not isinstance(device, int):
+        device = device.index
+    if device is None:
+        device = torch.cuda.current_device()
+    if _raw_stream is not None:
+        return _raw_stream(device)
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _on_device:
+    """``with _on_device(dev)`` only when ``dev`` is not already current (the context manager costs ~10 us a call)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        self.ctx = None if idx == torch.cuda.current_device() else torch.cuda.device(idx)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -174,7 +204,7 @@ def upsample_argmax_confusion(logits_lr: torch.Tensor, labels: Optional[torch.Te
         _need(cm, torch.int64, "cm")
         stride = C * C if cm.dim() == 3 else 0
     pred = torch.empty((N, H, W), dtype=torch.int64, device=logits_lr.device) if want_pred else None
-    with torch.cuda.device(logits_lr.device):
+    with _on_device(logits_lr.device):
         _check(lib.b200seg_upsample_argmax_confusion(logits_lr.data_ptr(), N, C, h, w, _ptr(labels), H, W, ignore_index,
                                                      _ptr(cm) if labels is not None else None, stride, _ptr(pred), fma_mode,
                                                      _stream()))
@@ -191,7 +221,7 @@ def confusion_from_pred(pd: torch.Tensor, gt: torch.Tensor, num_classes: int, ig
     if cm is None:
         cm = torch.zeros(num_classes, num_classes, dtype=torch.int64, device=pd.device)
     _need(cm, torch.int64, "cm")
-    with torch.cuda.device(pd.device):
+    with _on_device(pd.device):
         _check(lib.b200seg_confusion_from_pred(pd.data_ptr(), gt.data_ptr(), pd.numel(), num_classes, ignore_index,
                                                1 if mutate_pd else 0, cm.data_ptr(), _stream()))
     return cm
@@ -212,7 +242,7 @@ def upsample_ce_forward(logits_lr, labels, ignore_index=255, inv_temperature=1.0
     nbytes = lib.b200seg_upsample_ce_workspace_bytes(N, C, h, w, H, W)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=logits_lr.device)
     out2 = torch.empty(2, dtype=torch.float32, device=logits_lr.device)
-    with torch.cuda.device(logits_lr.device):
+    with _on_device(logits_lr.device):
         _check(lib.b200seg_upsample_ce_forward(logits_lr.data_ptr(), N, C, h, w, labels.data_ptr(), H, W, ignore_index,
                                                float(inv_temperature), 1 if need_grad else 0, ws.data_ptr(), nbytes,
                                                out2.data_ptr(), _stream()))
@@ -226,7 +256,7 @@ def upsample_ce_backward(ws, out2, shape_lr, size, inv_temperature=1.0, grad_out
     if grad_out is not None:
         grad_out = _need(grad_out.reshape(1).contiguous(), torch.float32, "grad_out")
     grad = torch.empty((N, C, h, w), dtype=torch.float32, device=ws.device)
-    with torch.cuda.device(ws.device):
+    with _on_device(ws.device):
         _check(lib.b200seg_upsample_ce_backward(ws.data_ptr(), N, C, h, w, H, W, float(inv_temperature), out2.data_ptr(),
                                                 _ptr(grad_out), grad.data_ptr(), _stream()))
     return grad
@@ -242,7 +272,7 @@ def upsample_ce_backward_packed(ws, out2, shape_lr, size, inv_temperature=1.0, g
         grad_out = _need(grad_out.reshape(1).contiguous(), torch.float32, "grad_out")
     gOt = torch.empty((N * h * w, 32), dtype=torch.bfloat16, device=ws.device)
     bias = torch.empty(C, dtype=torch.float32, device=ws.device) if want_bias else None
-    with torch.cuda.device(ws.device):
+    with _on_device(ws.device):
         _check(lib.b200seg_upsample_ce_backward_packed(ws.data_ptr(), N, C, h, w, H, W, float(inv_temperature), out2.data_ptr(),
                                                        _ptr(grad_out), gOt.data_ptr(), _ptr(bias), _stream()))
     return gOt, bias
@@ -254,7 +284,7 @@ def upsample_bilinear_forward(x: torch.Tensor, size, fma_mode: int = 0) -> torch
     N, C, h, w = x.shape
     H, W = int(size[0]), int(size[1])
     out = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         _check(lib.b200seg_upsample_bilinear_forward(x.data_ptr(), out.data_ptr(), N * C, h, w, H, W, fma_mode, _stream()))
     return out
 
@@ -265,7 +295,7 @@ def upsample_bilinear_backward(grad_out: torch.Tensor, in_hw) -> torch.Tensor:
     N, C, H, W = grad_out.shape
     h, w = in_hw
     gin = torch.empty((N, C, h, w), dtype=torch.float32, device=grad_out.device)
-    with torch.cuda.device(grad_out.device):
+    with _on_device(grad_out.device):
         _check(lib.b200seg_upsample_bilinear_backward(grad_out.data_ptr(), gin.data_ptr(), N * C, h, w, H, W, _stream()))
     return gin
 
@@ -292,7 +322,7 @@ def soft_ce_forward(pred, soft, weights=None, want_stats: bool = False):
     stats = None
     if want_stats and (H * W) % 4 == 0 and all(t is None or t.data_ptr() % 16 == 0 for t in (pred, soft, weights)):
         stats = torch.empty(lib.b200seg_soft_ce_stats_bytes(N, H, W) // 4, dtype=torch.float32, device=pred.device)
-    with torch.cuda.device(pred.device):
+    with _on_device(pred.device):
         if stats is not None:
             _check(lib.b200seg_soft_ce_forward_stats(pred.data_ptr(), soft.data_ptr(), _ptr(weights), N, K, H, W, ws.data_ptr(),
                                                      nbytes, stats.data_ptr(), out.data_ptr(), _stream()))
@@ -308,11 +338,11 @@ def soft_ce_backward(pred, soft, weights, grad_out, stats=None) -> torch.Tensor:
     grad_out = _need(grad_out.reshape(1).contiguous(), torch.float32, "grad_out")
     grad = torch.empty_like(pred)
     if stats is not None:
-        with torch.cuda.device(pred.device):
+        with _on_device(pred.device):
             _check(lib.b200seg_soft_ce_backward_stats(pred.data_ptr(), soft.data_ptr(), _ptr(weights), stats.data_ptr(),
                                                       grad_out.data_ptr(), N, K, H, W, grad.data_ptr(), _stream()))
         return grad
-    with torch.cuda.device(pred.device):
+    with _on_device(pred.device):
         _check(lib.b200seg_soft_ce_backward(pred.data_ptr(), soft.data_ptr(), _ptr(weights), grad_out.data_ptr(), N, K, H, W,
                                             grad.data_ptr(), _stream()))
     return grad
@@ -337,7 +367,7 @@ def fada_softce_forward(d_logits, seg_logits, size, slot: int, inv_temperature: 
     nbytes = lib.b200seg_fada_softce_workspace_bytes(N, C, h, w, H, W)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=d_logits.device)
     out2 = torch.empty(2, dtype=torch.float32, device=d_logits.device)
-    with torch.cuda.device(d_logits.device):
+    with _on_device(d_logits.device):
         _check(lib.b200seg_fada_softce_forward(d_logits.data_ptr(), seg_logits.data_ptr(), N, C, h, w, H, W, float(inv_temperature),
                                                float(clamp), int(slot), 1 if need_grad else 0, ws.data_ptr(), nbytes,
                                                out2.data_ptr(), _stream()))
@@ -351,7 +381,7 @@ def fada_softce_backward(ws, out2, shape_d, size, grad_out: Optional[torch.Tenso
     if grad_out is not None:
         grad_out = _need(grad_out.reshape(1).contiguous(), torch.float32, "grad_out")
     grad = torch.empty((N, K, h, w), dtype=torch.float32, device=ws.device)
-    with torch.cuda.device(ws.device):
+    with _on_device(ws.device):
         _check(lib.b200seg_fada_softce_backward(ws.data_ptr(), N, K // 2, h, w, H, W, out2.data_ptr(), _ptr(grad_out),
                                                 grad.data_ptr(), _stream()))
     return grad
@@ -388,7 +418,7 @@ def aspp_pack_weights(weights: Sequence[torch.Tensor], biases: Sequence[Optional
     Wp = torch.empty((NJ, Cin), dtype=torch.bfloat16, device=dev)
     WpT = torch.empty((Cin, NJ), dtype=torch.bfloat16, device=dev)
     bias_sum = torch.empty(C, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check(lib.b200seg_aspp_pack_weights(_ptr_array(weights), _ptr_array(biases), R, C, Cin, Wp.data_ptr(), WpT.data_ptr(),
                                              bias_sum.data_ptr(), _stream()))
     return Wp, WpT, bias_sum
@@ -400,7 +430,7 @@ def aspp_pack_features(x: torch.Tensor) -> torch.Tensor:
     _need(x, torch.float32, "features")
     N, Cin, h, w = x.shape
     Xp = torch.empty((N * h * w, Cin), dtype=torch.bfloat16, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         _check(lib.b200seg_aspp_pack_features(x.data_ptr(), N, Cin, h, w, Xp.data_ptr(), _stream()))
     return Xp
 
@@ -412,7 +442,7 @@ def _scratch(key, nbytes: int, device) -> torch.Tensor:
     """Grow-only scratch per (purpose, device, STREAM): reuse is ordered by the stream it is used on (contents never outlive
     one op), and ops issued concurrently on different streams never share a buffer."""
     dev_index = device.index if device.index is not None else torch.cuda.current_device()
-    k = (key, dev_index, torch.cuda.current_stream(device).cuda_stream)
+    k = (key, dev_index, _stream(dev_index))
     t = _scratch_cache.get(k)
     if t is None or t.numel() < nbytes:
         t = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
@@ -434,7 +464,7 @@ def aspp_forward(Xp: torch.Tensor, Wp: torch.Tensor, bias_sum: torch.Tensor, rat
     scratch = _scratch("aspp_fwd", nbytes, Xp.device)
     logits = torch.empty((N, C, h, w), dtype=torch.float32, device=Xp.device)
     rates_arr = (c_int * R)(*[int(r) for r in rates])
-    with torch.cuda.device(Xp.device):
+    with _on_device(Xp.device):
         _check(lib.b200seg_aspp_forward(Xp.data_ptr(), Wp.data_ptr(), bias_sum.data_ptr(), rates_arr, R, N, Cin, C, h, w,
                                         scratch.data_ptr(), logits.data_ptr(), _stream()))
     return logits
@@ -456,7 +486,7 @@ def aspp_backward(grad_logits: torch.Tensor, Xp: torch.Tensor, WpT: torch.Tensor
     gws = [torch.empty((C, Cin, 3, 3), dtype=torch.float32, device=dev) for _ in range(R)] if need_grad_w else None
     gbs = [torch.empty(C, dtype=torch.float32, device=dev) for _ in range(R)] if need_grad_b else None
     rates_arr = (c_int * R)(*[int(r) for r in rates])
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check(lib.b200seg_aspp_backward(grad_logits.data_ptr(), Xp.data_ptr(), WpT.data_ptr(), rates_arr, R, N, Cin, C, h, w,
                                          scratch.data_ptr(), nbytes, splits, _ptr(gx),
                                          _ptr_array(gws) if gws else None, _ptr_array(gbs) if gbs else None, _stream()))
@@ -495,7 +525,7 @@ def aspp_backward_packed(gOt: torch.Tensor, Xp: torch.Tensor, WpT: torch.Tensor,
         else:
             gx = torch.empty((N, Cin, h, w), dtype=torch.float32, device=dev)
     ev = None if weights_ready_event is None else weights_ready_event.cuda_event
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check(lib.b200seg_aspp_backward_packed_ex(gOt.data_ptr(), Xp.data_ptr(), WpT.data_ptr(), rates_arr, R, N, Cin, C, h, w,
                                                    scratch.data_ptr(), nbytes, splits, _ptr(gx), _ptr(gx_nhwc),
                                                    _ptr_array(gws) if gws else None, ev, _stream()))
@@ -526,7 +556,7 @@ def conv3x3_pack_weights(weights: Sequence[torch.Tensor]):
     dev = weights[0].device
     Wf = torch.empty((9, Co, Ci), dtype=torch.bfloat16, device=dev)
     Wb = torch.zeros((9, Ci, _round8(Co)), dtype=torch.bfloat16, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         _check(lib.b200seg_conv3x3_pack_weights(_ptr_array(weights), (c_int * len(parts))(*parts), len(parts), Ci, Wf.data_ptr(),
                                                 Wb.data_ptr(), Wb.shape[2], _stream()))
     return Wf, Wb
@@ -558,7 +588,7 @@ def conv3x3_forward(act: torch.Tensor, Wf: torch.Tensor, bias: Optional[torch.Te
         if Co % 8 != 0:
             raise B200SegError(f"conv3x3_forward: bf16 NHWC output needs out_channels={Co} to be a multiple of 8")
         out_b = torch.empty((N, h, w, Co), dtype=torch.bfloat16, device=act.device)
-    with torch.cuda.device(act.device):
+    with _on_device(act.device):
         _check(lib.b200seg_conv3x3_forward(act.data_ptr(), N, h, w, Ci, pitch, Wf.data_ptr(), Co, int(dilation), _ptr(bias),
                                            0 if lrelu_slope is None else 1, 0.0 if lrelu_slope is None else float(lrelu_slope),
                                            _ptr(out_b), Co, _ptr(out_f), _stream()))
@@ -586,7 +616,7 @@ def conv3x3_dgrad(g: torch.Tensor, Wb: torch.Tensor, mask: Optional[torch.Tensor
         out_b = torch.empty((N, h, w, Ci), dtype=torch.bfloat16, device=g.device)
         if mask is not None and tuple(_need_nhwc(mask, "mask")) != (N, h, w, Ci):
             raise B200SegError(f"conv3x3_dgrad: mask shape {tuple(mask.shape)} != {(N, h, w, Ci)}")
-    with torch.cuda.device(g.device):
+    with _on_device(g.device):
         _check(lib.b200seg_conv3x3_dgrad(g.data_ptr(), N, h, w, Cg, gp, Wb.data_ptr(), Ci, int(dilation), _ptr(mask), float(slope),
                                          _ptr(out_b), Ci, _ptr(out_f), _stream()))
     return out_f if out_f32_nchw else out_b
@@ -610,7 +640,7 @@ def conv3x3_wgrad(g: torch.Tensor, x: torch.Tensor, parts: Sequence[int], dilati
     for t, pc in zip(out, parts):
         if t is not None and (tuple(_need(t, torch.float32, "grad_w").shape) != (int(pc), Ci, 3, 3)):
             raise B200SegError("conv3x3_wgrad: bad output buffer shape")
-    with torch.cuda.device(g.device):
+    with _on_device(g.device):
         _check(lib.b200seg_conv3x3_wgrad(g.data_ptr(), Co, gp, x.data_ptr(), Ci, Ci, N, h, w, int(dilation), int(splits),
                                          scratch.data_ptr(), nbytes, _ptr_array(out), (c_int * len(parts))(*[int(v) for v in parts]),
                                          len(parts), _stream()))
@@ -624,7 +654,7 @@ def nchw_to_nhwc_bf16(src: torch.Tensor, pitch: Optional[int] = None) -> torch.T
     N, C, h, w = src.shape
     pitch = _round8(C) if pitch is None else int(pitch)
     dst = torch.empty((N, h, w, pitch), dtype=torch.bfloat16, device=src.device)
-    with torch.cuda.device(src.device):
+    with _on_device(src.device):
         _check(lib.b200seg_nchw_to_nhwc_bf16(src.data_ptr(), N, C, h * w, dst.data_ptr(), pitch, _stream()))
     return dst
 
@@ -637,7 +667,7 @@ def nhwc_bf16_colsum(g: torch.Tensor, C: Optional[int] = None) -> torch.Tensor:
     nbytes = lib.b200seg_nhwc_colsum_scratch_bytes(pitch)
     scratch = _scratch("colsum", nbytes, g.device)
     out = torch.empty(C, dtype=torch.float32, device=g.device)
-    with torch.cuda.device(g.device):
+    with _on_device(g.device):
         _check(lib.b200seg_nhwc_bf16_colsum(g.data_ptr(), N * h * w, C, pitch, scratch.data_ptr(), out.data_ptr(), _stream()))
     return out
 

@@ -46,7 +46,7 @@ def _pixel_major_bf16(x: torch.Tensor) -> torch.Tensor:
     x = x.contiguous()
     if _PACK_CACHE_SLOTS <= 0:
         return _lib.aspp_pack_features(x)
-    key = (x.data_ptr(), x._version, tuple(x.shape), x.device.index, torch.cuda.current_stream(x.device).cuda_stream)
+    key = (x.data_ptr(), x._version, tuple(x.shape), x.device.index, _lib._stream(x.device))
     for i, (k, _, Xp) in enumerate(_pack_cache):
         if k == key:
             _pack_cache.insert(0, _pack_cache.pop(i))
