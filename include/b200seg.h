@@ -192,6 +192,14 @@ B200SEG_API int b200seg_conv3x3_forward(const void* act_nhwc_bf16, int N, int h,
 B200SEG_API int b200seg_conv3x3_dgrad(const void* g_nhwc_bf16, int N, int h, int w, int Cg, int64_t g_pitch, const void* Wb, int Ci,
                                       int dilation, const void* mask_nhwc_bf16, float slope, void* out_bf16_nhwc, int64_t out_pitch,
                                       float* out_f32_nchw, void* stream);
+/* the same data gradient (bf16 NHWC output only) that also returns colsum_out[ci] = sum_pixels out[pixel][ci] (fp32 [Ci]): the bias
+ * gradient of the layer below (what autograd derives for discriminator.py:35,37's Conv2d biases), accumulated in the GEMM epilogue
+ * from the stored (bf16-rounded) values and finished by one fixed-order reduction -- no second pass over the tensor */
+B200SEG_API int64_t b200seg_conv3x3_dgrad_colsum_scratch_bytes(int N, int h, int w, int64_t out_pitch);
+B200SEG_API int b200seg_conv3x3_dgrad_colsum(const void* g_nhwc_bf16, int N, int h, int w, int Cg, int64_t g_pitch, const void* Wb, int Ci,
+                                             int dilation, const void* mask_nhwc_bf16, float slope, void* out_bf16_nhwc,
+                                             int64_t out_pitch, void* colsum_scratch, int64_t colsum_scratch_bytes, float* colsum_out,
+                                             void* stream);
 /* grad_w[i] fp32 [part_co[i]][Ci][3][3] = sum_pixels g[pixel, co] * x[pixel + tap, ci]; splits <= 0 picks the split-K factor */
 B200SEG_API int64_t b200seg_conv3x3_wgrad_scratch_bytes(int N, int h, int w, int Co, int Ci, int splits);
 B200SEG_API int b200seg_conv3x3_wgrad(const void* g_nhwc_bf16, int Co, int64_t g_pitch, const void* x_nhwc_bf16, int Ci, int64_t x_pitch,
@@ -204,11 +212,45 @@ B200SEG_API int64_t b200seg_nhwc_colsum_scratch_bytes(int pitch);
 B200SEG_API int b200seg_nhwc_bf16_colsum(const void* g_nhwc_bf16, int64_t P, int C, int pitch, void* scratch, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K7  test-time augmentation fused with argmax + confusion matrix.
+ * Replaces inference(..., flip=True) (core/utils/utility.py:179-191), multi_scale_inference (utility.py:193-209), the
+ * output.max(1)[1] / output.argmax(0) that follow (core/testers/aspp_tester.py:63,42) and confusion_matrix /
+ * intersectionAndUnionGPU (utility.py:347-359,148-161) for ONE frame:
+ *   prob = (sum_m flip_m(softmax(upsample(logits_lr[m], (H,W))))) / divisors[0] [/ divisors[1]];  pred = first argmax(prob)
+ * logits_lr: HOST array of n_members (<= 8) device pointers to fp32 [C, h[m], w[m]]; flip[m] != 0: the member was computed on
+ * the horizontally mirrored image, its probabilities are mirrored back.  Members are summed in array order (the reference's
+ * order: scale-major, plain before flipped).  div_exact = 0 multiplies by the fp32 reciprocal of each divisor (what ATen's CUDA
+ * `tensor / python_scalar` does), 1 divides (ATen's CPU kernel).  Outputs, each optional (NULL): cm int64 [C,C] accumulated
+ * into (rows = truth, needs labels int64 [H,W]; truth == ignore_index or outside [0,C) skipped), pred int64 [H,W], probs fp32
+ * [C,H,W] (the tensor the reference returns).
+ * ------------------------------------------------------------------------------------------- */
+B200SEG_API int b200seg_tta_argmax_confusion(const float* const* logits_lr, const int* h, const int* w, const int* flip, int n_members,
+                                             int C, const int64_t* labels, int H, int W, int ignore_index, const float* divisors,
+                                             int n_div, int div_exact, int64_t* cm, int64_t* pred, float* probs, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K8  multi-tensor optimizer steps, one launch per group of <= 16 tensors.  The pointer arrays are HOST
+ * arrays of device pointers, numels the element counts.  grad_scale multiplies every gradient as it is read (1/world_size after
+ * a SUM all-reduce = DDP's mean, train_distill.py:54-62; 1.0f = off).
+ * b200seg_sgd_step  = torch.optim.SGD(lr, momentum, dampening, weight_decay, nesterov).step()
+ *                     (core/trainers/aspp_trainer.py:25-26,94-95); first_step != 0: the momentum buffers are uninitialised and
+ *                     are set to the gradient (torch's momentum_buffer is None case); momentum_bufs may be NULL when momentum == 0.
+ * b200seg_adam_step = torch.optim.Adam(lr, betas, eps, weight_decay).step() (core/adapters/fada_adapter.py:24), step = the
+ *                     update count INCLUDING this one (>= 1); exp_avg / exp_avg_sq start at zero.
+ * ------------------------------------------------------------------------------------------- */
+B200SEG_API int b200seg_sgd_step(int n_tensors, float* const* params, const float* const* grads, float* const* momentum_bufs,
+                                 const int64_t* numels, float lr, float momentum, float dampening, float weight_decay, int nesterov,
+                                 int first_step, float grad_scale, void* stream);
+B200SEG_API int b200seg_adam_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                                  float* const* exp_avg_sq, const int64_t* numels, float lr, float beta1, float beta2, float eps,
+                                  float weight_decay, int64_t step, float grad_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * instrumentation (bench.py): number of kernels this library has launched, and per-kernel CUDA-event
  * timing on the launching stream.  Tags: 0 head fwd GEMM, 1 head dgrad GEMM, 2 head wgrad GEMM,
  * 3 feature pack, 4 fwd gather, 5 grad im2col (G'), 6 upsample+CE main, 7 eval argmax+confusion,
  * 8 soft-CE fwd, 9 soft-CE bwd, 10 wgrad reduce, 11 fused FADA soft-CE main, 12 conv3x3 fwd, 13 conv3x3 dgrad,
- * 14 conv3x3 wgrad.
+ * 14 conv3x3 wgrad, 15 test-time-augmentation argmax+confusion.
  * ------------------------------------------------------------------------------------------- */
 B200SEG_API long long b200seg_launch_count(void);
 B200SEG_API void b200seg_profile_enable(int on);

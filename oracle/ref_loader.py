@@ -58,6 +58,8 @@ def load_reference():
         PixelDiscriminator=discriminator.PixelDiscriminator,
         soft_label_cross_entropy=utility.soft_label_cross_entropy,
         inference=utility.inference,
+        multi_scale_inference=utility.multi_scale_inference,
+        adjust_learning_rate=_load("_ref_adapt_lr", "core/utils/adapt_lr.py").adjust_learning_rate,
         intersectionAndUnion=utility.intersectionAndUnion,
         confusion_matrix=utility.confusion_matrix,
         AverageMeter=utility.AverageMeter,

@@ -145,6 +145,87 @@ def eval_argmax(logits_lr: torch.Tensor, size) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------
+# 8f-3  test-time augmentation: inference(flip=True) and multi_scale_inference
+#        (core/utils/utility.py:179-191 and :193-209)
+# --------------------------------------------------------------------------
+def inference(feature_extractor, classifier, image, label, flip: bool = True) -> torch.Tensor:
+    """utility.py:179-191 line by line: [1,C,H,W] probabilities, flip-averaged when ``flip``."""
+    size = label.shape[-2:]
+    if flip:
+        image = torch.cat([image, torch.flip(image, [3])], 0)            # :182
+    with torch.no_grad():
+        output = classifier(feature_extractor(image))                    # :184
+    output = upsample_bilinear_ac(output, size)                          # :185
+    output = F.softmax(output, dim=1)                                    # :186
+    if flip:
+        output = (output[0] + output[1].flip(2)) / 2                     # :188
+    else:
+        output = output[0]
+    return output.unsqueeze(dim=0)
+
+
+def multi_scale_inference(feature_extractor, classifier, image, label, flip: bool = True,
+                          scales=(0.7, 1.0, 1.3)) -> torch.Tensor:
+    """utility.py:193-209 line by line."""
+    output = None
+    size = image.shape[-2:]
+    for s in scales:
+        x = F.interpolate(image, size=(int(size[0] * s), int(size[1] * s)), mode='bilinear', align_corners=True)
+        pred = inference(feature_extractor, classifier, x, label, flip=False)
+        output = pred if output is None else output + pred
+        if flip:
+            x_flip = torch.flip(x, [3])
+            pred = inference(feature_extractor, classifier, x_flip, label, flip=False)
+            output = output + pred.flip(3)
+    if flip:
+        return output / len(scales) / 2
+    return output / len(scales)
+
+
+def tta_probabilities(members: Sequence[torch.Tensor], flips: Sequence[bool], size, divisors: Sequence[float] = ()) -> torch.Tensor:
+    """The same ensembles starting from the members' low-res logits [1,C,h_m,w_m] (what the fused kernel is given):
+    sum over members, in order, of the (un-mirrored) softmax of the upsampled logits, then the scalar divisions in order."""
+    total = None
+    for lg, fl in zip(members, flips):
+        pr = F.softmax(upsample_bilinear_ac(lg, size), dim=1)
+        if fl:
+            pr = pr.flip(3)
+        total = pr if total is None else total + pr
+    for d in divisors:
+        total = total / d
+    return total
+
+
+# --------------------------------------------------------------------------
+# 8f-4  optimizer steps: torch.optim.SGD / Adam exactly as the reference builds them
+#        (core/trainers/aspp_trainer.py:25-26,77-81,94-95; core/adapters/fada_adapter.py:24; core/utils/adapt_lr.py:12-17)
+# --------------------------------------------------------------------------
+def adjust_learning_rate(method, base_lr, iters, max_iter, power):
+    """adapt_lr.py:12-17."""
+    if method == 'poly':
+        return base_lr * ((1 - float(iters) / max_iter) ** (power))
+    raise NotImplementedError
+
+
+def optimizer_steps(kind: str, params: Sequence[torch.Tensor], grads_per_step: Sequence[Sequence[torch.Tensor]],
+                    lrs: Optional[Sequence[float]] = None, **hyper):
+    """Run ``len(grads_per_step)`` steps of torch.optim.SGD / torch.optim.Adam (single-tensor eager path) on copies of
+    ``params``; ``lrs[k]`` is written into the param group before step k as aspp_trainer.py:78-81 does.  Returns (params,
+    state tensors per parameter: [momentum_buffer] for SGD, [exp_avg, exp_avg_sq] for Adam)."""
+    ps = [torch.nn.Parameter(p.detach().clone()) for p in params]
+    opt = (torch.optim.SGD if kind == "sgd" else torch.optim.Adam)(ps, foreach=False, **hyper)
+    for k, grads in enumerate(grads_per_step):
+        if lrs is not None:
+            for grp in opt.param_groups:
+                grp["lr"] = lrs[k]
+        for p, g in zip(ps, grads):
+            p.grad = g.detach().clone()
+        opt.step()
+    keys = ("momentum_buffer",) if kind == "sgd" else ("exp_avg", "exp_avg_sq")
+    return [p.detach() for p in ps], [[opt.state[p].get(k) for k in keys] for p in ps]
+
+
+# --------------------------------------------------------------------------
 # a10  confusion_matrix  (core/utils/utility.py:347-359)
 # --------------------------------------------------------------------------
 def confusion_matrix_loop(num_classes: int, pd: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:

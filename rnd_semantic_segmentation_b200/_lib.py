@@ -64,6 +64,9 @@ SIGNATURES = {
                                         c_vp, c_vp]),
     "b200seg_conv3x3_dgrad": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_i64, c_vp, c_int, c_int, c_vp, c_f32, c_vp, c_i64, c_vp,
                                       c_vp]),
+    "b200seg_conv3x3_dgrad_colsum_scratch_bytes": (c_i64, [c_int, c_int, c_int, c_i64]),
+    "b200seg_conv3x3_dgrad_colsum": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_i64, c_vp, c_int, c_int, c_vp, c_f32, c_vp, c_i64,
+                                             c_vp, c_i64, c_vp, c_vp]),
     "b200seg_conv3x3_wgrad_scratch_bytes": (c_i64, [c_int] * 6),
     "b200seg_conv3x3_wgrad": (c_int, [c_vp, c_int, c_i64, c_vp, c_int, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64, c_vp,
                                       c_vp, c_int, c_vp]),
@@ -78,6 +81,10 @@ SIGNATURES = {
     "b200seg_gemm_set_sharing": (None, [c_int]),
     "b200seg_conv_set_pair": (None, [c_int]),
     "b200seg_gemm_set_narrow_tiles": (None, [c_int]),
+    "b200seg_tta_argmax_confusion": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp, c_int, c_int,
+                                             c_vp, c_vp, c_vp, c_vp]),
+    "b200seg_sgd_step": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_f32, c_f32, c_f32, c_f32, c_int, c_int, c_f32, c_vp]),
+    "b200seg_adam_step": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_f32, c_vp]),
     "b200seg_gemm_set_dgrad_n_fastest": (None, [c_int]),
     "b200seg_gemm_set_tma_store": (None, [c_int]),
 }
@@ -209,6 +216,102 @@ def upsample_argmax_confusion(logits_lr: torch.Tensor, labels: Optional[torch.Te
                                                      _ptr(cm) if labels is not None else None, stride, _ptr(pred), fma_mode,
                                                      _stream()))
     return cm, pred
+
+
+def tta_argmax_confusion(members: Sequence[torch.Tensor], flips: Sequence[bool], size, labels: Optional[torch.Tensor] = None,
+                         divisors: Sequence[float] = (), ignore_index: int = 255, cm: Optional[torch.Tensor] = None,
+                         want_pred: bool = False, want_probs: bool = False, div_exact: bool = False):
+    """K7: fused test-time augmentation for ONE frame.  ``members``: fp32 [C,h_m,w_m] (or [1,C,h_m,w_m]) low-res logit maps,
+    ``flips[m]``: member m was computed on the mirrored image.  Returns (cm | None, pred int64 [H,W] | None, probs fp32 [C,H,W] | None)
+    with probs = (sum_m unflip(softmax(upsample(member_m)))) / divisors[0] [/ divisors[1]] and pred its first argmax."""
+    lib = load()
+    if len(members) == 0 or len(members) != len(flips):
+        raise B200SegError("tta_argmax_confusion: members and flips must be non-empty and of equal length")
+    maps = []
+    for m, t in enumerate(members):
+        _need(t, torch.float32, f"members[{m}]")
+        if t.dim() == 4 and t.shape[0] == 1:
+            t = t[0]
+        if t.dim() != 3:
+            raise B200SegError(f"members[{m}]: expected [C,h,w] or [1,C,h,w], got {tuple(t.shape)}")
+        if maps and t.shape[0] != maps[0].shape[0]:
+            raise B200SegError("tta_argmax_confusion: members disagree on the number of classes")
+        if t.device != members[0].device:
+            raise B200SegError("tta_argmax_confusion: members must live on one device")
+        maps.append(t)
+    C = int(maps[0].shape[0])
+    H, W = int(size[0]), int(size[1])
+    dev = maps[0].device
+    if labels is not None:
+        _need(labels, torch.int64, "labels")
+        if labels.numel() != H * W:
+            raise B200SegError(f"labels shape {tuple(labels.shape)} does not match H*W = {H}*{W}")
+        if cm is None:
+            cm = torch.zeros((C, C), dtype=torch.int64, device=dev)
+        _need(cm, torch.int64, "cm")
+    elif cm is not None:
+        raise B200SegError("tta_argmax_confusion: a confusion matrix needs labels")
+    if len(divisors) > 2:
+        raise B200SegError("tta_argmax_confusion: at most two divisors")
+    pred = torch.empty((H, W), dtype=torch.int64, device=dev) if want_pred else None
+    probs = torch.empty((C, H, W), dtype=torch.float32, device=dev) if want_probs else None
+    n = len(maps)
+    hs = (c_int * n)(*[int(t.shape[1]) for t in maps])
+    ws = (c_int * n)(*[int(t.shape[2]) for t in maps])
+    fl = (c_int * n)(*[1 if f else 0 for f in flips])
+    dv = (c_f32 * max(1, len(divisors)))(*[float(d) for d in divisors])
+    with _on_device(dev):
+        _check(lib.b200seg_tta_argmax_confusion(_ptr_array(maps), hs, ws, fl, n, C, _ptr(labels), H, W, int(ignore_index), dv,
+                                                len(divisors), 1 if div_exact else 0, _ptr(cm), _ptr(pred), _ptr(probs), _stream()))
+    return cm, pred, probs
+
+
+def _optim_tables(params, grads, *states):
+    n = len(params)
+    for i, (p, g) in enumerate(zip(params, grads)):
+        _need(p, torch.float32, f"params[{i}]")
+        _need(g, torch.float32, f"grads[{i}]")
+        if g.numel() != p.numel() or g.device != p.device:
+            raise B200SegError(f"optimizer step: gradient {i} does not match its parameter")
+    for st in states:
+        if st is None:
+            continue
+        if len(st) != n:
+            raise B200SegError("optimizer step: state list length != number of parameters")
+        for i, (p, b) in enumerate(zip(params, st)):
+            _need(b, torch.float32, f"state[{i}]")
+            if b.numel() != p.numel() or b.device != p.device:
+                raise B200SegError(f"optimizer step: state tensor {i} does not match its parameter")
+    numels = (c_i64 * n)(*[int(p.numel()) for p in params])
+    return n, numels
+
+
+def sgd_step(params: Sequence[torch.Tensor], grads: Sequence[torch.Tensor], momentum_bufs: Optional[Sequence[torch.Tensor]], lr: float,
+             momentum: float = 0.0, dampening: float = 0.0, weight_decay: float = 0.0, nesterov: bool = False,
+             first_step: bool = False, grad_scale: float = 1.0):
+    """K8: torch.optim.SGD's update of a whole parameter group in one launch (in place on params / momentum_bufs)."""
+    lib = load()
+    if not params:
+        return
+    n, numels = _optim_tables(params, grads, momentum_bufs if momentum != 0 else None)
+    with _on_device(params[0].device):
+        _check(lib.b200seg_sgd_step(n, _ptr_array(params), _ptr_array(grads), _ptr_array(momentum_bufs) if momentum != 0 else None,
+                                    numels, float(lr), float(momentum), float(dampening), float(weight_decay), 1 if nesterov else 0,
+                                    1 if first_step else 0, float(grad_scale), _stream()))
+
+
+def adam_step(params: Sequence[torch.Tensor], grads: Sequence[torch.Tensor], exp_avg: Sequence[torch.Tensor],
+              exp_avg_sq: Sequence[torch.Tensor], step: int, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
+              weight_decay: float = 0.0, grad_scale: float = 1.0):
+    """K8: torch.optim.Adam's update of a whole parameter group in one launch; ``step`` counts this update (>= 1)."""
+    lib = load()
+    if not params:
+        return
+    n, numels = _optim_tables(params, grads, exp_avg, exp_avg_sq)
+    with _on_device(params[0].device):
+        _check(lib.b200seg_adam_step(n, _ptr_array(params), _ptr_array(grads), _ptr_array(exp_avg), _ptr_array(exp_avg_sq), numels,
+                                     float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+                                     float(grad_scale), _stream()))
 
 
 def confusion_from_pred(pd: torch.Tensor, gt: torch.Tensor, num_classes: int, ignore_index: int = 255,
@@ -596,9 +699,11 @@ def conv3x3_forward(act: torch.Tensor, Wf: torch.Tensor, bias: Optional[torch.Te
 
 
 def conv3x3_dgrad(g: torch.Tensor, Wb: torch.Tensor, mask: Optional[torch.Tensor] = None, slope: float = 0.2, dilation: int = 1,
-                  out_f32_nchw: bool = False) -> torch.Tensor:
+                  out_f32_nchw: bool = False, want_colsum: bool = False):
     """Data gradient of conv3x3 (padding == dilation): g bf16 NHWC [N,h,w,round8(Co)], Wb bf16 [9,Ci,round8(Co)].  ``mask`` (bf16
-    NHWC [N,h,w,Ci], the saved LeakyReLU output of the layer below) fuses the activation's backward into the epilogue."""
+    NHWC [N,h,w,Ci], the saved LeakyReLU output of the layer below) fuses the activation's backward into the epilogue.
+    ``want_colsum`` (bf16 NHWC output only) returns (gradient, fp32 [Ci] per-channel sums of the gradient) -- the bias gradient of
+    the layer below, accumulated in the same epilogue."""
     lib = load()
     N, h, w, gp = _need_nhwc(g, "g")
     _need(Wb, torch.bfloat16, "Wb")
@@ -616,6 +721,17 @@ def conv3x3_dgrad(g: torch.Tensor, Wb: torch.Tensor, mask: Optional[torch.Tensor
         out_b = torch.empty((N, h, w, Ci), dtype=torch.bfloat16, device=g.device)
         if mask is not None and tuple(_need_nhwc(mask, "mask")) != (N, h, w, Ci):
             raise B200SegError(f"conv3x3_dgrad: mask shape {tuple(mask.shape)} != {(N, h, w, Ci)}")
+    if want_colsum:
+        if out_f32_nchw:
+            raise B200SegError("conv3x3_dgrad: the fused column sums need the bf16 NHWC output")
+        nbytes = lib.b200seg_conv3x3_dgrad_colsum_scratch_bytes(N, h, w, Ci)
+        scratch = _scratch("dgrad_colsum", nbytes, g.device)
+        colsum = torch.empty(Ci, dtype=torch.float32, device=g.device)
+        with _on_device(g.device):
+            _check(lib.b200seg_conv3x3_dgrad_colsum(g.data_ptr(), N, h, w, Cg, gp, Wb.data_ptr(), Ci, int(dilation), _ptr(mask),
+                                                    float(slope), out_b.data_ptr(), Ci, scratch.data_ptr(), nbytes,
+                                                    colsum.data_ptr(), _stream()))
+        return out_b, colsum
     with _on_device(g.device):
         _check(lib.b200seg_conv3x3_dgrad(g.data_ptr(), N, h, w, Cg, gp, Wb.data_ptr(), Ci, int(dilation), _ptr(mask), float(slope),
                                          _ptr(out_b), Ci, _ptr(out_f), _stream()))
@@ -721,7 +837,7 @@ def gemm_set_sharing(mode):
 
 PROFILE_TAGS = {"head_fwd_gemm": 0, "head_dgrad_gemm": 1, "head_wgrad_gemm": 2, "pack_features": 3, "head_gather": 4,
                 "grad_im2col": 5, "upsample_ce_main": 6, "eval_argmax_confusion": 7, "soft_ce_fwd": 8, "soft_ce_bwd": 9,
-                "wgrad_reduce": 10, "fada_softce_main": 11, "conv3x3_fwd": 12, "conv3x3_dgrad": 13, "conv3x3_wgrad": 14}
+                "wgrad_reduce": 10, "fada_softce_main": 11, "conv3x3_fwd": 12, "conv3x3_dgrad": 13, "conv3x3_wgrad": 14, "tta": 15}
 
 
 def launch_count() -> int:

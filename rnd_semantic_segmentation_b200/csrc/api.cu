@@ -78,13 +78,20 @@ int conv3x3_pack_weights(const float* const*, const int*, int, int, void*, void*
 int conv3x3_forward(const void*, int, int, int, int, long long, const void*, int, int, const float*, int, float, void*, long long, float*,
                     cudaStream_t);
 int conv3x3_dgrad(const void*, int, int, int, int, long long, const void*, int, int, const void*, float, void*, long long, float*,
-                  cudaStream_t);
+                  cudaStream_t, void*, long long, float*);
+long long conv3x3_dgrad_colsum_scratch_bytes(int, int, int, long long);
 long long conv3x3_wgrad_scratch_bytes(int, int, int, int, int, int);
 int conv3x3_wgrad(const void*, int, long long, const void*, int, long long, int, int, int, int, int, void*, long long, float* const*,
                   const int*, int, cudaStream_t);
 int nchw_to_nhwc_bf16(const float*, int, int, int, void*, int, cudaStream_t);
 long long nhwc_colsum_scratch_bytes(int);
 int nhwc_bf16_colsum(const void*, long long, int, int, void*, float*, cudaStream_t);
+int tta_launch(const float* const*, const int*, const int*, const int*, int, int, const long long*, int, int, int, const float*, int, int,
+               long long*, long long*, float*, cudaStream_t);
+int sgd_step(int, float* const*, const float* const*, float* const*, const long long*, float, float, float, float, int, int, float,
+             cudaStream_t);
+int adam_step(int, float* const*, const float* const*, float* const*, float* const*, const long long*, float, float, float, float,
+              float, long long, float, cudaStream_t);
 namespace gemm { namespace conv { void set_pair(int); } }
 namespace gemm {
 int selftest(int, int, int, int, int, int, int, int, double*, double*);
@@ -300,7 +307,22 @@ int b200seg_conv3x3_forward(const void* act, int N, int h, int w, int Ci, int64_
 int b200seg_conv3x3_dgrad(const void* g, int N, int h, int w, int Cg, int64_t g_pitch, const void* Wb, int Ci, int dilation,
                           const void* mask, float slope, void* out_bf16_nhwc, int64_t out_pitch, float* out_f32_nchw, void* stream) {
   REQUIRE_DEVICE();
-  return conv3x3_dgrad(g, N, h, w, Cg, g_pitch, Wb, Ci, dilation, mask, slope, out_bf16_nhwc, out_pitch, out_f32_nchw, S(stream));
+  return conv3x3_dgrad(g, N, h, w, Cg, g_pitch, Wb, Ci, dilation, mask, slope, out_bf16_nhwc, out_pitch, out_f32_nchw, S(stream),
+                       nullptr, 0, nullptr);
+}
+
+int64_t b200seg_conv3x3_dgrad_colsum_scratch_bytes(int N, int h, int w, int64_t out_pitch) {
+  if (N <= 0 || h <= 0 || w <= 0 || out_pitch <= 0) return 0;
+  return conv3x3_dgrad_colsum_scratch_bytes(N, h, w, out_pitch);
+}
+
+int b200seg_conv3x3_dgrad_colsum(const void* g, int N, int h, int w, int Cg, int64_t g_pitch, const void* Wb, int Ci, int dilation,
+                                 const void* mask, float slope, void* out_bf16_nhwc, int64_t out_pitch, void* colsum_scratch,
+                                 int64_t colsum_scratch_bytes, float* colsum_out, void* stream) {
+  REQUIRE_DEVICE();
+  if (!colsum_out) { set_error("b200seg_conv3x3_dgrad_colsum: colsum_out is null"); return B200SEG_ERR_ARG; }
+  return conv3x3_dgrad(g, N, h, w, Cg, g_pitch, Wb, Ci, dilation, mask, slope, out_bf16_nhwc, out_pitch, nullptr, S(stream),
+                       colsum_scratch, colsum_scratch_bytes, colsum_out);
 }
 
 int64_t b200seg_conv3x3_wgrad_scratch_bytes(int N, int h, int w, int Co, int Ci, int splits) {
@@ -319,6 +341,30 @@ int b200seg_conv3x3_wgrad(const void* g, int Co, int64_t g_pitch, const void* x,
 int b200seg_nchw_to_nhwc_bf16(const float* src, int N, int C, int hw, void* dst, int pitch, void* stream) {
   REQUIRE_DEVICE();
   return nchw_to_nhwc_bf16(src, N, C, hw, dst, pitch, S(stream));
+}
+
+int b200seg_tta_argmax_confusion(const float* const* logits_lr, const int* h, const int* w, const int* flip, int n_members, int C,
+                                 const int64_t* labels, int H, int W, int ignore_index, const float* divisors, int n_div,
+                                 int div_exact, int64_t* cm, int64_t* pred, float* probs, void* stream) {
+  REQUIRE_DEVICE();
+  return tta_launch(logits_lr, h, w, flip, n_members, C, reinterpret_cast<const long long*>(labels), H, W, ignore_index, divisors,
+                    n_div, div_exact, reinterpret_cast<long long*>(cm), reinterpret_cast<long long*>(pred), probs, S(stream));
+}
+
+int b200seg_sgd_step(int n_tensors, float* const* params, const float* const* grads, float* const* momentum_bufs,
+                     const int64_t* numels, float lr, float momentum, float dampening, float weight_decay, int nesterov,
+                     int first_step, float grad_scale, void* stream) {
+  REQUIRE_DEVICE();
+  return sgd_step(n_tensors, params, grads, momentum_bufs, reinterpret_cast<const long long*>(numels), lr, momentum, dampening,
+                  weight_decay, nesterov, first_step, grad_scale, S(stream));
+}
+
+int b200seg_adam_step(int n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                      float* const* exp_avg_sq, const int64_t* numels, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, int64_t step, float grad_scale, void* stream) {
+  REQUIRE_DEVICE();
+  return adam_step(n_tensors, params, grads, exp_avg, exp_avg_sq, reinterpret_cast<const long long*>(numels), lr, beta1, beta2, eps,
+                   weight_decay, step, grad_scale, S(stream));
 }
 
 int64_t b200seg_nhwc_colsum_scratch_bytes(int pitch) { return pitch > 0 ? nhwc_colsum_scratch_bytes(pitch) : 0; }

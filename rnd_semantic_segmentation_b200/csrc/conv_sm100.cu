@@ -86,6 +86,8 @@ struct ConvParams {
   float slope;
   const __nv_bfloat16* mask;   // saved post-activation output of the layer below ([pixels][out_pitch]): multiply by LeakyReLU'
   long long split_stride;  // WGRAD: elements between split-K slabs
+  float* colsum_part;      // CONV + bf16 NHWC output: per (M-tile, warp row quarter) column sums of the STORED (bf16-rounded) values,
+  int m_tiles_real;        //   [m_tiles_real * 4][out_pitch] -> the bias gradient without another pass over the tensor
 };
 
 __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
@@ -312,22 +314,41 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               }
             }
           }
-          if (valid) {
-            if (p.out_mode == OUT_BF16_NHWC) {
+          if (p.out_mode == OUT_BF16_NHWC) {
+            uint32_t w16[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+              w16[e] = *reinterpret_cast<const uint32_t*>(&b2);
+              if (p.colsum_part) {                                 // sum what is stored, so the result equals a pass over the tensor
+                v[2 * e] = valid ? __low2float(b2) : 0.f;
+                v[2 * e + 1] = valid ? __high2float(b2) : 0.f;
+              }
+            }
+            if (valid) {
               uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_pitch + col0);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                if (col0 + 8 * k < p.Co) {
-                  uint32_t w4[4];
+              for (int k = 0; k < 4; ++k)
+                if (col0 + 8 * k < p.Co) op[k] = make_uint4(w16[4 * k], w16[4 * k + 1], w16[4 * k + 2], w16[4 * k + 3]);
+            }
+            if (p.colsum_part) {
+              // 32 rows (lanes) x 32 columns -> lane l ends up with the sum of column l over the warp's rows: five exchange
+              // steps, each halving the values a lane carries (31 shuffles instead of 32 x 5); fixed order => deterministic
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * k + 2 * e], v[8 * k + 2 * e + 1]);
-                    w4[e] = *reinterpret_cast<const uint32_t*>(&b2);
-                  }
-                  op[k] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+              for (int sft = 16; sft >= 1; sft >>= 1) {
+                const bool up = (lane & sft) != 0;
+#pragma unroll
+                for (int i = 0; i < sft; ++i) {
+                  const float send = up ? v[i] : v[i + sft];
+                  const float keep = up ? v[i + sft] : v[i];
+                  v[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
                 }
               }
-            } else {
+              if (u.mt < p.m_tiles_real && col0 + lane < p.Co)
+                p.colsum_part[((long long)u.mt * 4 + wq) * p.out_pitch + col0 + lane] = v[0];
+            }
+          } else if (valid) {
+            {
               const long long hw = (long long)p.h * p.w;
               float* op = reinterpret_cast<float*>(p.out) + ((long long)img * p.Co + col0) * hw + (long long)y * p.w + x;
 #pragma unroll
@@ -473,8 +494,9 @@ static int launch_conv(const CUtensorMap& ta, const CUtensorMap& tb, const ConvP
 // D[pixel, co] = sum_t sum_ck act[pixel + sign*d_t, ck] * wt[t][co][ck]  (+ epilogue), see the header comment
 int conv3x3_run(const void* act, int N, int h, int w, int Ck, long long act_pitch, const void* wt, int Co, int dilation, int sign,
                 const float* bias, int lrelu, float slope, const void* mask, void* out, int out_mode, long long out_pitch,
-                cudaStream_t stream, int prof_tag) {
+                cudaStream_t stream, int prof_tag, float* colsum_part = nullptr) {
   B200SEG_CHECK_ARG(act && wt && out, "conv3x3: null pointer");
+  B200SEG_CHECK_ARG(!colsum_part || out_mode == OUT_BF16_NHWC, "conv3x3: fused column sums need the bf16 NHWC output");
   B200SEG_CHECK_ARG(N > 0 && h > 0 && w > 0 && Ck > 0 && Co > 0 && dilation > 0, "conv3x3: bad geometry");
   B200SEG_CHECK_ARG(Ck % 8 == 0 && act_pitch % 8 == 0 && act_pitch >= Ck, "conv3x3: input channels (%d, pitch %lld) must be multiples of 8", Ck, act_pitch);
   B200SEG_CHECK_ARG((long long)N * h * w < (1LL << 31), "conv3x3: too many pixels");
@@ -493,6 +515,8 @@ int conv3x3_run(const void* act, int N, int h, int w, int Ck, long long act_pitc
   p.Co = Co; p.Ci = 0;
   const int BN = Co <= 128 ? 128 : 256;
   p.m_tiles = N * p.tiles_x * p.tiles_y;
+  p.m_tiles_real = p.m_tiles;
+  p.colsum_part = colsum_part;
   const bool pair = g_pair && p.m_tiles >= 2;
   if (pair) p.m_tiles = ceil_div(p.m_tiles, 2);       // pairs of M-tiles
   p.n_tiles = ceil_div(Co, BN);
@@ -518,6 +542,13 @@ int conv3x3_run(const void* act, int N, int h, int w, int Ck, long long act_pitc
   rc = launch_conv<MODE_CONV>(ta, tb, p, BN, pair, stream);
   profile_end(prof_tag, stream);
   return rc;
+}
+
+// rows of the fused column-sum partials: one per (M-tile, epilogue warp quarter)
+int conv3x3_colsum_rows(int N, int h, int w) {
+  int TW = 64, TH = 1;
+  pick_rect(h, w, BLOCK_M, &TW, &TH);
+  return N * ceil_div(w, TW) * ceil_div(h, TH) * 4;
 }
 
 int conv3x3_wgrad_splits(int N, int h, int w, int Co, int Ci) {
@@ -786,10 +817,28 @@ int conv3x3_forward(const void* act, int N, int h, int w, int Ck, long long act_
 }
 
 // data gradient: gin[pixel, ci] = (sum_t sum_co g[pixel - d_t, co] * Wb[t][ci][co]) * LeakyReLU'(mask[pixel, ci])
+long long conv3x3_dgrad_colsum_scratch_bytes(int N, int h, int w, long long out_pitch) {
+  return (long long)gemm::conv::conv3x3_colsum_rows(N, h, w) * out_pitch * 4;
+}
+
+// colsum_out (optional, with colsum_scratch): fp32 [Ci] column sums of the stored bf16 gradient = the bias gradient of the layer
+// below, accumulated in the GEMM epilogue (per M-tile and warp quarter) and finished by one small fixed-order reduction
 int conv3x3_dgrad(const void* g, int N, int h, int w, int Cg, long long g_pitch, const void* Wb, int Ci, int dilation, const void* mask,
-                  float slope, void* out_bf16_nhwc, long long out_pitch, float* out_f32_nchw, cudaStream_t stream) {
+                  float slope, void* out_bf16_nhwc, long long out_pitch, float* out_f32_nchw, cudaStream_t stream,
+                  void* colsum_scratch = nullptr, long long colsum_scratch_bytes = 0, float* colsum_out = nullptr) {
   B200SEG_CHECK_ARG((out_bf16_nhwc != nullptr) != (out_f32_nchw != nullptr), "conv3x3_dgrad: give exactly one output");
   B200SEG_CHECK_ARG(!mask || out_bf16_nhwc, "conv3x3_dgrad: the activation mask needs the bf16 NHWC output");
+  if (colsum_out) {
+    B200SEG_CHECK_ARG(out_bf16_nhwc && colsum_scratch, "conv3x3_dgrad: fused column sums need the bf16 NHWC output and a scratch buffer");
+    B200SEG_CHECK_ARG(colsum_scratch_bytes >= conv3x3_dgrad_colsum_scratch_bytes(N, h, w, out_pitch), "conv3x3_dgrad: column-sum scratch too small");
+    int rc = gemm::conv::conv3x3_run(g, N, h, w, Cg, g_pitch, Wb, Ci, dilation, -1, nullptr, 0, slope, mask, out_bf16_nhwc,
+                                     gemm::conv::OUT_BF16_NHWC, out_pitch, stream, 13, (float*)colsum_scratch);
+    if (rc) return rc;
+    colsum_final_kernel<<<ceil_div(Ci, 8), 256, 0, stream>>>((const float*)colsum_scratch, gemm::conv::conv3x3_colsum_rows(N, h, w),
+                                                            (int)out_pitch, Ci, colsum_out);
+    B200SEG_LAUNCH_CHECK();
+    return B200SEG_OK;
+  }
   if (out_bf16_nhwc)
     return gemm::conv::conv3x3_run(g, N, h, w, Cg, g_pitch, Wb, Ci, dilation, -1, nullptr, 0, slope, mask, out_bf16_nhwc,
                                    gemm::conv::OUT_BF16_NHWC, out_pitch, stream, 13);

@@ -1,0 +1,184 @@
+// K7: test-time augmentation (horizontal flip and/or multi-scale) fused with the argmax and the confusion matrix.
+//
+// Replaces, for one frame (reference file:line):
+//   inference(..., flip=True)          core/utils/utility.py:179-191   (output[0] + output[1].flip(2)) / 2
+//   multi_scale_inference(...)         core/utils/utility.py:193-209   sum over scales (and flips) of inference(flip=False),
+//                                                                      then / len(scales) [/ 2]
+//   output.max(1)[1]                   core/testers/aspp_tester.py:63
+//   output.argmax(0) (pseudo labels)   core/testers/aspp_tester.py:42  (save_distill)
+//   confusion_matrix / intersectionAndUnionGPU                          utility.py:347-359, 148-161
+//
+// The reference materialises, per member of the ensemble, the upsampled logits and their softmax at label resolution
+// (2 x 159 MB at 19 x 1024 x 2048) plus the flipped copy and the running sum.  Here every label pixel reads the (L1/L2
+// resident) low-res logits of all members, computes each member's softmax probabilities in registers, sums them in the
+// reference's order and scales them -- nothing at label resolution is written unless the caller asks for the probabilities.
+//
+// Bit-exactness: unlike K4 the argmax here depends on the probabilities themselves, so EVERY pixel runs ATen's sequences:
+//   upsample   h0*(w0*a + w1*b) + h1*(w0*c + w1*d) as nvcc contracts it, fma(h0, t, h1*u)      (UpSampleBilinear2d.cu)
+//   softmax    max over classes; fp32 sum of expf(v - max) in class order; expf(v - max) / sum (IEEE) (SoftMax.cu, spatial)
+//   sum        fp32 adds in member order
+//   division   tensor / python_scalar on CUDA multiplies by the fp32 reciprocal of the scalar     (BinaryDivTrueKernel.cu);
+//              div_exact = 1 selects the IEEE division ATen's CPU kernel performs instead
+//   argmax     first maximum
+//
+// Mapping: one thread per label pixel; a CTA owns a run of consecutive rows of one 128-column strip (consecutive rows share
+// source rows, which stay in L1).  Confusion counts go to a shared-memory int32 histogram (atomics), published once per CTA.
+#include "common.cuh"
+
+namespace b200seg {
+
+constexpr int TTA_MAX_MAPS = 8;
+constexpr int TTA_THREADS = 128;
+
+struct TtaMap {
+  const float* logits;     // [C, h, w]
+  int h, w, flip;
+  float scale_h, scale_w;
+};
+struct TtaParams {
+  TtaMap maps[TTA_MAX_MAPS];
+  int n_maps, C, H, W, ignore_index;
+  int n_div;               // 0, 1 or 2 scalar divisions after the sum
+  int div_exact;           // 0: multiply by the fp32 reciprocal (ATen CUDA), 1: IEEE divide (ATen CPU)
+  float div[2];
+  const long long* labels; // [H, W] or null
+  long long* cm;           // [C, C] or null (accumulated into)
+  long long* pred;         // [H, W] or null
+  float* probs;            // [C, H, W] or null
+};
+
+__device__ __forceinline__ float tta_lerp(float wa, float a, float wb, float b) { return fmaf(wa, a, __fmul_rn(wb, b)); }
+
+template <int CT>
+__global__ void __launch_bounds__(TTA_THREADS) tta_argmax_confusion_kernel(const TtaParams p) {
+  extern __shared__ int tta_hist[];
+  const int C = p.C, CC = p.C * p.C;
+  if (p.cm) {
+    for (int i = threadIdx.x; i < CC; i += TTA_THREADS) tta_hist[i] = 0;
+    __syncthreads();
+  }
+  const int tiles_x = ceil_div(p.W, TTA_THREADS);
+  const long long units = (long long)tiles_x * p.H;
+  const long long plane = (long long)p.H * p.W;
+  const long long chunk = ceil_div_ll(units, gridDim.x);                 // a CTA walks DOWN one 128-column strip: 8 or so consecutive
+  const long long u_end = min(units, (blockIdx.x + 1) * chunk);         // rows share their source-row pair, which stays in L1
+  for (long long unit = blockIdx.x * chunk; unit < u_end; ++unit) {
+    const int y = (int)(unit % p.H);
+    const int x = (int)(unit / p.H) * TTA_THREADS + threadIdx.x;
+    if (x >= p.W) continue;
+    float acc[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) acc[c] = 0.f;
+#pragma unroll 1
+    for (int m = 0; m < p.n_maps; ++m) {
+      const TtaMap& mp = p.maps[m];
+      const int xs = mp.flip ? p.W - 1 - x : x;              // the member saw the mirrored image: un-mirror its probabilities
+      const Tap ty = ac_tap(mp.scale_h, y, mp.h);
+      const Tap tx = ac_tap(mp.scale_w, xs, mp.w);
+      const long long hw = (long long)mp.h * mp.w;
+      const float* r0 = mp.logits + (long long)ty.i0 * mp.w;
+      const float* r1 = mp.logits + (long long)ty.i1 * mp.w;
+      float v[CT];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        if (c < C) {
+          const float t = tta_lerp(tx.l0, __ldg(r0 + c * hw + tx.i0), tx.l1, __ldg(r0 + c * hw + tx.i1));
+          const float u = tta_lerp(tx.l0, __ldg(r1 + c * hw + tx.i0), tx.l1, __ldg(r1 + c * hw + tx.i1));
+          v[c] = tta_lerp(ty.l0, t, ty.l1, u);
+          mx = fmaxf(mx, v[c]);
+        }
+      }
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        if (c < C) {
+          v[c] = expf(v[c] - mx);
+          s += v[c];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        if (c < C) {
+          const float pc = __fdiv_rn(v[c], s);
+          acc[c] = (m == 0) ? pc : __fadd_rn(acc[c], pc);
+        }
+      }
+    }
+#pragma unroll 1
+    for (int k = 0; k < p.n_div; ++k) {
+      const float d = p.div[k];
+      const float r = __fdiv_rn(1.0f, d);
+#pragma unroll
+      for (int c = 0; c < CT; ++c) acc[c] = p.div_exact ? __fdiv_rn(acc[c], d) : __fmul_rn(acc[c], r);
+    }
+    float best = acc[0];
+    int idx = 0;
+#pragma unroll
+    for (int c = 1; c < CT; ++c) {
+      if (c < C && acc[c] > best) { best = acc[c]; idx = c; }
+    }
+    const long long pix = (long long)y * p.W + x;
+    if (p.probs) {
+#pragma unroll
+      for (int c = 0; c < CT; ++c)
+        if (c < C) __stcs(p.probs + c * plane + pix, acc[c]);
+    }
+    if (p.pred) p.pred[pix] = idx;
+    if (p.cm) {
+      const long long lab = ld_stream_s64(p.labels + pix);
+      if (lab != p.ignore_index && lab >= 0 && lab < C) atomicAdd(&tta_hist[(int)lab * C + idx], 1);
+    }
+  }
+  if (p.cm) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < CC; i += TTA_THREADS) {
+      const int v = tta_hist[i];
+      if (v) atomicAdd(reinterpret_cast<unsigned long long*>(p.cm + i), (unsigned long long)v);
+    }
+  }
+}
+
+// logits[m]: fp32 [C, h[m], w[m]] (device pointers in a HOST array); flip[m] != 0: the member saw the mirrored image
+int tta_launch(const float* const* logits, const int* hs, const int* ws, const int* flips, int n_maps, int C, const long long* labels,
+               int H, int W, int ignore_index, const float* divisors, int n_div, int div_exact, long long* cm, long long* pred,
+               float* probs, cudaStream_t stream) {
+  B200SEG_CHECK_ARG(logits && hs && ws && flips, "tta_argmax_confusion: null member table");
+  B200SEG_CHECK_ARG(n_maps >= 1 && n_maps <= TTA_MAX_MAPS, "tta_argmax_confusion: %d members (1..%d supported)", n_maps, TTA_MAX_MAPS);
+  B200SEG_CHECK_ARG(C > 0 && C <= 32, "tta_argmax_confusion: num_classes=%d not in 1..32", C);
+  B200SEG_CHECK_ARG(H > 0 && W > 0, "tta_argmax_confusion: bad label size %d x %d", H, W);
+  B200SEG_CHECK_ARG(n_div >= 0 && n_div <= 2 && (n_div == 0 || divisors), "tta_argmax_confusion: 0..2 divisors");
+  B200SEG_CHECK_ARG(cm == nullptr || labels != nullptr, "tta_argmax_confusion: confusion matrix requested without labels");
+  B200SEG_CHECK_ARG(cm || pred || probs, "tta_argmax_confusion: nothing to compute (cm, pred and probs all null)");
+  TtaParams p = {};
+  for (int m = 0; m < n_maps; ++m) {
+    B200SEG_CHECK_ARG(logits[m] && hs[m] > 0 && ws[m] > 0, "tta_argmax_confusion: member %d has a null pointer or an empty shape", m);
+    p.maps[m].logits = logits[m];
+    p.maps[m].h = hs[m];
+    p.maps[m].w = ws[m];
+    p.maps[m].flip = flips[m] ? 1 : 0;
+    p.maps[m].scale_h = ac_scale(hs[m], H);
+    p.maps[m].scale_w = ac_scale(ws[m], W);
+  }
+  p.n_maps = n_maps; p.C = C; p.H = H; p.W = W; p.ignore_index = ignore_index;
+  p.n_div = n_div; p.div_exact = div_exact ? 1 : 0;
+  for (int k = 0; k < n_div; ++k) {
+    B200SEG_CHECK_ARG(divisors[k] != 0.f, "tta_argmax_confusion: zero divisor");
+    p.div[k] = divisors[k];
+  }
+  p.labels = labels; p.cm = cm; p.pred = pred; p.probs = probs;
+  const long long units = (long long)ceil_div(W, TTA_THREADS) * H;
+  const long long cap = (long long)num_sms() * 8;
+  const int grid = (int)(units < cap ? units : cap);
+  const size_t smem = cm ? (size_t)C * C * 4 : 0;
+  profile_begin(15, stream);
+  if (C <= 2) tta_argmax_confusion_kernel<2><<<grid, TTA_THREADS, smem, stream>>>(p);
+  else if (C <= 8) tta_argmax_confusion_kernel<8><<<grid, TTA_THREADS, smem, stream>>>(p);
+  else if (C <= 19) tta_argmax_confusion_kernel<19><<<grid, TTA_THREADS, smem, stream>>>(p);
+  else tta_argmax_confusion_kernel<32><<<grid, TTA_THREADS, smem, stream>>>(p);
+  profile_end(15, stream);
+  B200SEG_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+}  // namespace b200seg

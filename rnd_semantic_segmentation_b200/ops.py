@@ -213,15 +213,17 @@ class _PixelDiscriminatorFn(torch.autograd.Function):
             gwc1, gwc2 = _lib.conv3x3_wgrad(G3, A2, [C, C])
             gwc1, gwc2 = (gwc1 if need[7] else None), (gwc2 if need[9] else None)
         if any(need[i] for i in (0, 3, 4, 5, 6)):
-            dZ2 = _lib.conv3x3_dgrad(G3, Wb3, mask=A2, slope=slope)
-            if need[6]:
-                gb2 = _lib.nhwc_bf16_colsum(dZ2)
+            if need[6]:        # bias gradient = column sums of dZ2, accumulated in the dgrad epilogue
+                dZ2, gb2 = _lib.conv3x3_dgrad(G3, Wb3, mask=A2, slope=slope, want_colsum=True)
+            else:
+                dZ2 = _lib.conv3x3_dgrad(G3, Wb3, mask=A2, slope=slope)
             if need[5]:
                 gw2, = _lib.conv3x3_wgrad(dZ2, A1, [dZ2.shape[3]])
             if any(need[i] for i in (0, 3, 4)):
-                dZ1 = _lib.conv3x3_dgrad(dZ2, Wb2, mask=A1, slope=slope)
                 if need[4]:
-                    gb1 = _lib.nhwc_bf16_colsum(dZ1)
+                    dZ1, gb1 = _lib.conv3x3_dgrad(dZ2, Wb2, mask=A1, slope=slope, want_colsum=True)
+                else:
+                    dZ1 = _lib.conv3x3_dgrad(dZ2, Wb2, mask=A1, slope=slope)
                 if need[3]:
                     gw1, = _lib.conv3x3_wgrad(dZ1, Xp, [dZ1.shape[3]])
                 if need[0]:

@@ -18,7 +18,7 @@ import torch.nn.functional as F
 from . import _lib, ops
 from .ops import soft_label_cross_entropy  # noqa: F401  (re-exported under the reference's name)
 
-__all__ = ["soft_label_cross_entropy", "inference", "intersectionAndUnion", "intersectionAndUnionGPU",
+__all__ = ["soft_label_cross_entropy", "inference", "multi_scale_inference", "intersectionAndUnion", "intersectionAndUnionGPU",
            "confusion_matrix", "AverageMeter", "segmentation_eval_step", "iutr_from_confusion", "LazyProbabilities"]
 
 
@@ -141,15 +141,27 @@ class _PredRecord:
 
 
 class LazyProbabilities:
-    """What ``inference(..., flip=False)`` returns: stands for softmax(interpolate(logits_lr)) [1,C,H,W]
-    without materialising it.  ``.max(1)`` gives (max probability placeholder, int64 argmax) through the fused
-    kernel; any other use materialises the real tensor (``.materialize()`` / ``torch.as_tensor`` semantics)."""
+    """What ``inference`` / ``multi_scale_inference`` return: stands for the [1,C,H,W] probability tensor of the reference
+    (softmax of the upsampled logits; with test-time augmentation the average over the flipped / rescaled members) without
+    materialising it.  ``.max(1)`` gives (None, int64 argmax) through the fused kernels -- K4 for a single member, K7
+    (``tta_argmax_confusion``) for an ensemble -- together with the confusion matrix of the same launch; any other use
+    materialises the real tensor (``.materialize()`` / ``torch.as_tensor`` semantics).
 
-    def __init__(self, logits_lr, label, ignore_index=255):
-        self.logits_lr = logits_lr
+    ``members``: low-res logits [1,C,h_m,w_m]; ``flips[m]``: member m saw the mirrored image; ``divisors``: the scalar
+    divisions the reference applies to the sum, in order (utility.py:188, :207-209)."""
+
+    def __init__(self, logits_lr, label, ignore_index=255, members=None, flips=None, divisors=()):
+        self.members = [logits_lr] if members is None else list(members)
+        self.flips = [False] * len(self.members) if flips is None else [bool(f) for f in flips]
+        self.divisors = tuple(float(d) for d in divisors)
+        self.logits_lr = self.members[0]
         self.label = label
         self.ignore_index = ignore_index
         self._full = None
+
+    @property
+    def is_ensemble(self):
+        return len(self.members) > 1 or any(self.flips) or len(self.divisors) > 0
 
     @property
     def shape(self):
@@ -159,10 +171,18 @@ class LazyProbabilities:
     def size(self, dim=None):
         return self.shape if dim is None else self.shape[dim]
 
+    def _members32(self):
+        return [m.detach().float().contiguous() for m in self.members]
+
     def materialize(self) -> torch.Tensor:
         if self._full is None:
-            up = ops.upsample_bilinear_align_corners(self.logits_lr, self.label.shape[-2:])
-            self._full = F.softmax(up, dim=1)
+            if self.is_ensemble:
+                _, _, probs = _lib.tta_argmax_confusion(self._members32(), self.flips, self.label.shape[-2:],
+                                                        divisors=self.divisors, want_probs=True)
+                self._full = probs.unsqueeze(0)
+            else:
+                up = ops.upsample_bilinear_align_corners(self.logits_lr, self.label.shape[-2:])
+                self._full = F.softmax(up, dim=1)
         return self._full
 
     def max(self, dim=None, keepdim=False):
@@ -170,8 +190,13 @@ class LazyProbabilities:
             return self.materialize().max(dim, keepdim) if dim is not None else self.materialize().max()
         labels = self.label if self.label.dtype == torch.int64 else self.label.long()
         labels = labels.reshape(self.logits_lr.shape[0], *labels.shape[-2:]).contiguous()
-        cm, pred = _lib.upsample_argmax_confusion(self.logits_lr, labels, labels.shape[-2:],
-                                                  ignore_index=self.ignore_index, per_frame=False, want_pred=True)
+        if self.is_ensemble:
+            cm, pred, _ = _lib.tta_argmax_confusion(self._members32(), self.flips, labels.shape[-2:], labels=labels,
+                                                    divisors=self.divisors, ignore_index=self.ignore_index, want_pred=True)
+            pred = pred.unsqueeze(0)
+        else:
+            cm, pred = _lib.upsample_argmax_confusion(self.logits_lr, labels, labels.shape[-2:],
+                                                      ignore_index=self.ignore_index, per_frame=False, want_pred=True)
         rec = _PredRecord()
         rec.pred, rec.labels_ptr, rec.cm, rec.ignore_index = pred, labels.data_ptr(), cm, self.ignore_index
         _pred_cache[pred.data_ptr()] = rec
@@ -196,19 +221,36 @@ class LazyProbabilities:
 
 
 def inference(feature_extractor, classifier, image, label, flip=True):
-    """utility.py:179-191.  flip=False (what ASPPTester uses, aspp_tester.py:60) returns a LazyProbabilities;
-    flip=True needs the averaged probabilities and therefore materialises them."""
-    size = label.shape[-2:]
+    """utility.py:179-191.  Returns a LazyProbabilities standing for the reference's [1,C,H,W] tensor: flip=False (what
+    ASPPTester uses, aspp_tester.py:60) is one member; flip=True is the two-member ensemble
+    (softmax(up(head(image))) + mirror(softmax(up(head(mirror(image)))))) / 2, evaluated per label pixel by K7."""
     if flip:
         image = torch.cat([image, torch.flip(image, [3])], 0)
     with torch.no_grad():
         output = classifier(feature_extractor(image))
     if not flip:
         return LazyProbabilities(output[:1].contiguous(), label)
-    output = ops.upsample_bilinear_align_corners(output, size)
-    output = F.softmax(output, dim=1)
-    output = (output[0] + output[1].flip(2)) / 2
-    return output.unsqueeze(dim=0)
+    return LazyProbabilities(None, label, members=[output[0:1].contiguous(), output[1:2].contiguous()], flips=[False, True],
+                             divisors=(2,))
+
+
+def multi_scale_inference(feature_extractor, classifier, image, label, flip=True, scales=[0.7, 1.0, 1.3]):
+    """utility.py:193-209: the backbone + head run once per scale (and once more on the mirrored image when ``flip``); the
+    reference then upsamples, soft-maxes, un-mirrors and sums 2 * len(scales) full-resolution tensors and divides by
+    len(scales) and by 2.  Here the low-res logits of all members go to ONE K7 launch, summed in the reference's order."""
+    size = image.shape[-2:]
+    members, flips = [], []
+    with torch.no_grad():
+        for s in scales:
+            x = F.interpolate(image, size=(int(size[0] * s), int(size[1] * s)), mode='bilinear', align_corners=True)
+            members.append(classifier(feature_extractor(x))[:1].contiguous())
+            flips.append(False)
+            if flip:
+                members.append(classifier(feature_extractor(torch.flip(x, [3])))[:1].contiguous())
+                flips.append(True)
+    if len(members) > 8:
+        raise _lib.B200SegError(f"multi_scale_inference: {len(members)} ensemble members, at most 8 are supported")
+    return LazyProbabilities(None, label, members=members, flips=flips, divisors=(len(scales), 2) if flip else (len(scales),))
 
 
 def _cached_record(pd: torch.Tensor, gt: torch.Tensor):

@@ -423,6 +423,20 @@ def test_conv3x3_layer_forward_dgrad_wgrad(lib, n, ci, co, h, w, dil):
     mask_src[0, 0, 0, :3] = 0.0                                     # LeakyReLU'(0) = slope
     got = lib.conv3x3_dgrad(gq, Wb, mask=_nhwc_bf16(mask_src), slope=0.2, dilation=dil)
     assert rel_err(_nchw(got), gx_want * torch.where(bf16_round(mask_src) > 0, 1.0, 0.2)) <= 2.0 ** -8
+    if ci % 8 == 0:
+        # the same launch with the bias gradient of the layer below folded into the epilogue: identical tensor, and column sums
+        # equal to a separate pass over what was stored (both in pair mode and with one CTA per tile)
+        for pair in (1, 0):
+            lib.conv_set_pair(pair)
+            try:
+                got2, cs = lib.conv3x3_dgrad(gq, Wb, mask=_nhwc_bf16(mask_src), slope=0.2, dilation=dil, want_colsum=True)
+                got_ref = lib.conv3x3_dgrad(gq, Wb, mask=_nhwc_bf16(mask_src), slope=0.2, dilation=dil)
+            finally:
+                lib.conv_set_pair(True)
+            assert torch.equal(got2, got_ref)
+            assert rel_err(cs, got2.double().sum((0, 1, 2))) <= 1e-5, f"pair={pair}"
+            cs2 = lib.conv3x3_dgrad(gq, Wb, mask=_nhwc_bf16(mask_src), slope=0.2, dilation=dil, want_colsum=True)[1]
+            assert torch.equal(cs, cs2)                             # deterministic
     # weight gradient (split-K chosen by the library, and forced to 1 / 3 splits); bias gradient
     for splits in (0, 1, 3):
         gw, = lib.conv3x3_wgrad(gq, xq, [co], dilation=dil, splits=splits)
@@ -704,3 +718,215 @@ def test_full_size_properties_config1(lib):
     assert lg.grad.sum(1).abs().max().item() <= 1e-6 * lg.grad.abs().max().item() * 19 + 1e-12
     cm, _ = ops._lib.upsample_argmax_confusion(y1, labels, (512, 1024))
     assert int(cm.sum()) == int((labels != 255).sum())
+
+
+# ------------------------------------------------------------------ K7: fused test-time augmentation
+def _tta_members(C, shapes, sigma, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [(torch.randn(1, C, h, w, generator=g) * sigma).cuda() for h, w in shapes]
+
+
+@pytest.mark.parametrize("C,shapes,flips,divisors,H,W", [
+    (19, [(64, 128), (64, 128)], [False, True], (2,), 512, 1024),                       # inference(flip=True), train-crop size
+    (19, [(128, 256), (128, 256)], [False, True], (2,), 1024, 2048),                    # ... at the 1024 x 2048 eval size
+    (19, [(45, 90), (45, 90), (64, 128), (64, 128), (84, 167), (84, 167)], [False, True] * 3, (3, 2), 512, 1024),  # multi-scale + flip
+    (19, [(23, 45), (33, 65), (43, 84)], [False] * 3, (3,), 260, 517),                  # multi-scale, no flip, odd sizes
+    (2, [(44, 44), (44, 44)], [False, True], (2,), 352, 352),                           # kvasir polyp head
+    (7, [(9, 11)], [True], (), 50, 70),                                                 # one mirrored member, no division
+    (30, [(8, 8), (12, 10)], [False, False], (2,), 64, 61),                             # CT = 32 path
+])
+@pytest.mark.parametrize("sigma", [1.0, 0.01])
+def test_k7_tta_bit_exact_against_torch_cuda(lib, C, shapes, flips, divisors, H, W, sigma):
+    """Probabilities, argmax and confusion matrix of the fused kernel against the reference's op sequence (utility.py:179-209)
+    run with torch CUDA ops on the same low-res logits: bit-exact (sigma = 0.01 puts many classes within a few ulp)."""
+    members = _tta_members(C, shapes, sigma, seed=300 + C + len(shapes))
+    labels = make_labels(1, H, W, C, 0.1, 17).cuda()
+    want = to.tta_probabilities(members, flips, (H, W), divisors)
+    want_pred = want.max(1)[1]
+    cm, pred, probs = lib.tta_argmax_confusion(members, flips, (H, W), labels=labels, divisors=divisors, want_pred=True,
+                                               want_probs=True)
+    assert rel_err(probs.unsqueeze(0), want) <= 1e-6
+    assert torch.equal(probs.unsqueeze(0), want), f"max abs diff {(probs.unsqueeze(0) - want).abs().max().item():.3e}"
+    assert torch.equal(pred.unsqueeze(0), want_pred)
+    assert torch.equal(cm.cpu(), to.confusion_matrix_bincount(C, want_pred.flatten().cpu(), labels.flatten().cpu()))
+    # outputs are independent of each other, and the matrix accumulates
+    cm2, pred2, probs2 = lib.tta_argmax_confusion(members, flips, (H, W), labels=labels, divisors=divisors, cm=cm.clone())
+    assert pred2 is None and probs2 is None and torch.equal(cm2, 2 * cm)
+    _, pred3, _ = lib.tta_argmax_confusion(members, flips, (H, W), divisors=divisors, want_pred=True)
+    assert torch.equal(pred3, pred)
+
+
+def test_k7_flip_symmetry_and_errors(lib):
+    """Size-independent properties: mirroring every member and toggling every flip flag mirrors the output; a member averaged
+    with its own mirror image (flagged as mirrored) reproduces the single member; IEEE-division mode equals reciprocal mode for
+    powers of two."""
+    C, H, W = 19, 96, 160
+    a, b = _tta_members(C, [(12, 20), (17, 31)], 1.0, 5)
+    _, pred, probs = lib.tta_argmax_confusion([a, b], [False, True], (H, W), divisors=(2,), want_pred=True, want_probs=True)
+    _, pred_m, probs_m = lib.tta_argmax_confusion([a.flip(3).contiguous(), b.flip(3).contiguous()], [True, False], (H, W),
+                                                  divisors=(2,), want_pred=True, want_probs=True)
+    assert rel_err(probs_m.flip(2), probs) <= 1e-6
+    _, _, probs_s = lib.tta_argmax_confusion([a, a.flip(3).contiguous()], [False, True], (H, W), divisors=(2,), want_probs=True)
+    _, _, probs_1 = lib.tta_argmax_confusion([a], [False], (H, W), want_probs=True)
+    assert rel_err(probs_s, probs_1) <= 1e-5
+    assert torch.equal(probs_1.unsqueeze(0), to.eval_probabilities(a, (H, W)))             # one plain member == inference(flip=False)
+    _, pred_e, probs_e = lib.tta_argmax_confusion([a, b], [False, True], (H, W), divisors=(2,), want_pred=True, want_probs=True,
+                                                  div_exact=True)
+    assert torch.equal(probs_e, probs) and torch.equal(pred_e, pred)
+    with pytest.raises(lib.B200SegError):
+        lib.tta_argmax_confusion([a] * 9, [False] * 9, (H, W), want_pred=True)
+    with pytest.raises(lib.B200SegError):
+        lib.tta_argmax_confusion([a, b], [False, True], (H, W), divisors=(2,))            # nothing to compute
+    with pytest.raises(lib.B200SegError):
+        lib.tta_argmax_confusion([a.cpu()], [False], (H, W), want_pred=True)              # no CPU fallback
+
+
+def test_k7_dropin_against_reference_golden(lib, golden):
+    """b200.inference(flip=True) / b200.multi_scale_inference driven like core/testers/aspp_tester.py:60-72, on the member logits
+    the REFERENCE produced (tests/golden/tta.npz, CPU): probabilities to 1e-6, argmax equal wherever the top two are > 1e-6 apart."""
+    import types
+    import rnd_semantic_segmentation_b200 as b200
+    g = golden("tta")
+    C = int(g["num_classes"])
+    cfg = types.SimpleNamespace(MODEL=types.SimpleNamespace(NUM_CLASSES=C, NAME="deeplab_resnet101"))
+    image, label = torch.from_numpy(g["image"]).cuda(), torch.from_numpy(g["label"]).cuda()
+
+    class Replay(torch.nn.Module):
+        def __init__(self, outs):
+            super().__init__()
+            self.outs, self.k = outs, 0
+
+        def forward(self, feats, size=None):
+            out = self.outs[self.k]
+            self.k += 1
+            return out
+
+    def check(out, name):
+        want = torch.from_numpy(g[f"{name}.probs"])
+        assert tuple(out.shape) == tuple(want.shape)
+        pred = out.max(1)[1]
+        assert tuple(pred.shape) == (1,) + tuple(label.shape[-2:]) and pred.dtype == torch.int64
+        top2 = want.topk(2, dim=1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 1e-6
+        assert torch.equal(pred.cpu()[clear], torch.from_numpy(g[f"{name}.pred"])[clear])
+        cm = b200.confusion_matrix(cfg, torch.flatten(pred), torch.flatten(label))
+        assert torch.equal(cm, to.confusion_matrix_bincount(C, pred.flatten().cpu(), label.flatten().cpu()))
+        np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=2e-6, atol=1e-7)      # materialises (the API-compat path)
+
+    both = torch.cat([torch.from_numpy(g["flip.member0"]), torch.from_numpy(g["flip.member1"])], 0).cuda()
+    check(b200.inference(torch.nn.Identity(), Replay([both]), image, label, flip=True), "flip")
+    for name, flip in (("ms", True), ("ms_noflip", False)):
+        members = [torch.from_numpy(g[f"{name}.member{k}"]).cuda() for k in range(int(g[f"{name}.n_members"]))]
+        out = b200.multi_scale_inference(torch.nn.Identity(), Replay(members), image, label, flip=flip,
+                                         scales=[float(s) for s in g["scales"]])
+        check(out, name)
+
+
+# ------------------------------------------------------------------ K8: fused optimizer steps (SURVEY 8f rank 4)
+OPT_TOL = 1e-6      # relative (max-abs / max-abs): one-ulp rounding differences of single intermediates against torch.optim
+
+
+def test_k8_fused_sgd_adam_against_reference_golden(lib, golden):
+    """FusedSGD / FusedAdam driven exactly as aspp_trainer.py:77-81,94-95 drives torch.optim (lr rewritten in the param groups
+    every iteration from the poly schedule) against the parameters and optimizer states the reference's own setup produced."""
+    import rnd_semantic_segmentation_b200 as b200
+    g = golden("optim")
+    n, steps = int(g["n"]), int(g["steps"])
+
+    def run(ctor, scale):
+        ps = [torch.nn.Parameter(torch.from_numpy(g[f"p0.{i}"]).cuda()) for i in range(n)]
+        opt = ctor(ps)
+        for k in range(steps):
+            lr = b200.adjust_learning_rate('poly', float(g["base_lr"]), k, int(g["max_iter"]), float(g["power"]))
+            assert lr == float(g["lrs"][k])
+            for grp in opt.param_groups:
+                grp['lr'] = lr * scale
+            opt.zero_grad()
+            for i, p in enumerate(ps):
+                p.grad = torch.from_numpy(g[f"g{k}.{i}"]).cuda()
+            opt.step()
+        return ps, opt
+
+    launches0 = lib.load().b200seg_launch_count()
+    ps, opt = run(lambda ps: b200.FusedSGD(ps, lr=float(g["base_lr"]) * 10, momentum=0.9, weight_decay=5e-4), 10)
+    assert lib.load().b200seg_launch_count() - launches0 == steps              # one launch per step for the whole group
+    for i, p in enumerate(ps):
+        assert rel_err(p, torch.from_numpy(g[f"sgd.p.{i}"])) <= OPT_TOL
+        assert rel_err(opt.state[p]["momentum_buffer"], torch.from_numpy(g[f"sgd.buf.{i}"])) <= OPT_TOL
+    ps, opt = run(lambda ps: b200.FusedAdam(ps, lr=1e-4, betas=(0.9, 0.99)), 0.4)
+    for i, p in enumerate(ps):
+        assert rel_err(p, torch.from_numpy(g[f"adam.p.{i}"])) <= OPT_TOL
+        assert rel_err(opt.state[p]["exp_avg"], torch.from_numpy(g[f"adam.m.{i}"])) <= OPT_TOL
+        assert rel_err(opt.state[p]["exp_avg_sq"], torch.from_numpy(g[f"adam.v.{i}"])) <= 4 * OPT_TOL
+        assert float(opt.state[p]["step"]) == steps
+
+
+@pytest.mark.parametrize("kind,hyper", [
+    ("sgd", dict(lr=0.0025, momentum=0.9, weight_decay=5e-4)),
+    ("sgd", dict(lr=0.01, momentum=0.9, nesterov=True)),
+    ("sgd", dict(lr=0.01, momentum=0.8, dampening=0.1, weight_decay=1e-3)),
+    ("sgd", dict(lr=0.05)),
+    ("adam", dict(lr=1e-4, betas=(0.9, 0.99))),
+    ("adam", dict(lr=1e-3, betas=(0.5, 0.999), eps=1e-6, weight_decay=1e-2)),
+])
+def test_k8_matches_torch_optim_and_interchanges_state(lib, kind, hyper):
+    """Real parameter sets (ASPP head 8 tensors; 20 tensors = two launches), five steps against torch.optim on the GPU (both the
+    single-tensor and the foreach path), a mid-run state_dict hand-over in both directions, and the folded gradient scale."""
+    import rnd_semantic_segmentation_b200 as b200
+    g = torch.Generator().manual_seed(8)
+    shapes = [(19, 256, 3, 3), (19,)] * 4 + [(33, 5)] * 12
+    p0 = [torch.randn(s, generator=g).cuda() * 0.05 for s in shapes]
+    grads = [[torch.randn(s, generator=g).cuda() * 0.01 for s in shapes] for _ in range(5)]
+    fused_cls = b200.FusedSGD if kind == "sgd" else b200.FusedAdam
+    torch_cls = torch.optim.SGD if kind == "sgd" else torch.optim.Adam
+
+    def steps(opt, ps, ks, scale=1.0):
+        for k in ks:
+            for p, gr in zip(ps, grads[k]):
+                p.grad = gr.clone() * scale
+            opt.step()
+
+    def fresh():
+        return [torch.nn.Parameter(p.clone()) for p in p0]
+
+    pa, pb, pc = fresh(), fresh(), fresh()
+    oa, ob, oc = fused_cls(pa, **hyper), torch_cls(pb, foreach=False, **hyper), torch_cls(pc, foreach=True, **hyper)
+    steps(oa, pa, range(5)); steps(ob, pb, range(5)); steps(oc, pc, range(5))
+    for a, b, c in zip(pa, pb, pc):
+        assert rel_err(a, b) <= OPT_TOL and rel_err(a, c) <= OPT_TOL
+    # hand-over: 2 steps torch -> state_dict -> 3 steps fused, and the other way round
+    pd_, pe = fresh(), fresh()
+    od, oe = torch_cls(pd_, foreach=False, **hyper), fused_cls(pe, **hyper)
+    steps(od, pd_, range(2))
+    with torch.no_grad():
+        for e, d in zip(pe, pd_):
+            e.copy_(d)
+    oe.load_state_dict(od.state_dict())
+    steps(oe, pe, range(2, 5))
+    for e, b in zip(pe, pb):
+        assert rel_err(e, b) <= OPT_TOL
+    pf, pg = fresh(), fresh()
+    of, og = fused_cls(pf, **hyper), torch_cls(pg, foreach=False, **hyper)
+    steps(of, pf, range(2))
+    with torch.no_grad():
+        for t, f in zip(pg, pf):
+            t.copy_(f)
+    og.load_state_dict(of.state_dict())
+    steps(og, pg, range(2, 5))
+    for t, b in zip(pg, pb):
+        assert rel_err(t, b) <= OPT_TOL
+    # gradient scale folded into the step == scaling the gradients first (DDP mean after a SUM all-reduce over 8 ranks)
+    ph = fresh()
+    oh = fused_cls(ph, grad_scale=0.125, **hyper)
+    steps(oh, ph, range(5), scale=8.0)
+    for h_, a in zip(ph, pa):
+        assert rel_err(h_, a) <= OPT_TOL
+
+
+def test_k8_rejects_cpu_parameters(lib):
+    import rnd_semantic_segmentation_b200 as b200
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    for cls, kw in ((b200.FusedSGD, dict(lr=0.1, momentum=0.9)), (b200.FusedAdam, dict(lr=0.1))):
+        with pytest.raises(lib.B200SegError):
+            cls([p], **kw).step()

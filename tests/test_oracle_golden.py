@@ -164,3 +164,85 @@ def test_oracle_equals_live_reference():
     assert torch.equal(da(x, (20, 20)), db(x, (20, 20)))
     p = torch.randn(2, 14, 5, 6); q = torch.rand(2, 14, 5, 6)
     assert torch.equal(ref.soft_label_cross_entropy(p, q), to.soft_label_cross_entropy(p, q))
+
+
+# ------------------------------------------------------------------ 8f-3: test-time augmentation (flip / multi-scale)
+class _Replay(torch.nn.Module):
+    """Stands in for classifier(feature_extractor(.)): returns the recorded member logits in call order."""
+
+    def __init__(self, outputs):
+        super().__init__()
+        self.outputs, self.k = outputs, 0
+
+    def forward(self, feats, size=None):
+        out = self.outputs[self.k]
+        self.k += 1
+        return out
+
+
+def _assert_pred_equal_off_ties(probs, want_pred, gap=1e-6):
+    top2 = probs.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > gap
+    got = probs.max(1)[1]
+    assert torch.equal(got[clear], torch.from_numpy(want_pred)[clear])
+    assert float(clear.float().mean()) > 0.99
+
+
+def test_tta_oracle_matches_reference_golden(golden):
+    g = golden("tta")
+    image, label = torch.from_numpy(g["image"]), torch.from_numpy(g["label"])
+    size = label.shape[-2:]
+    # inference(flip=True): the oracle's line-by-line restatement fed the recorded head outputs, and the from-members form
+    both = torch.cat([torch.from_numpy(g["flip.member0"]), torch.from_numpy(g["flip.member1"])], 0)
+    probs = to.inference(torch.nn.Identity(), _Replay([both]), image, label, flip=True)
+    np.testing.assert_array_equal(probs.numpy(), g["flip.probs"])
+    # member by member the CPU kernels vectorise differently than on the batch of two: equal to an ulp, not bit for bit
+    probs2 = to.tta_probabilities([both[0:1], both[1:2]], [False, True], size, divisors=(2,))
+    np.testing.assert_allclose(probs2.numpy(), g["flip.probs"], rtol=1e-6, atol=1e-7)
+    _assert_pred_equal_off_ties(probs2, g["flip.pred"])
+    np.testing.assert_allclose(probs2.sum(1).numpy(), 1.0, atol=1e-5)
+    # multi_scale_inference with and without flips
+    for name, flip in (("ms", True), ("ms_noflip", False)):
+        members = [torch.from_numpy(g[f"{name}.member{k}"]) for k in range(int(g[f"{name}.n_members"]))]
+        scales = [float(s) for s in g["scales"]]
+        probs = to.multi_scale_inference(torch.nn.Identity(), _Replay(members), image, label, flip=flip, scales=scales)
+        np.testing.assert_array_equal(probs.numpy(), g[f"{name}.probs"])
+        flips = [bool(k % 2) for k in range(len(members))] if flip else [False] * len(members)
+        probs2 = to.tta_probabilities(members, flips, size, divisors=(len(scales), 2) if flip else (len(scales),))
+        np.testing.assert_allclose(probs2.numpy(), g[f"{name}.probs"], rtol=1e-6, atol=1e-7)
+        _assert_pred_equal_off_ties(probs2, g[f"{name}.pred"])
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree not present")
+def test_tta_oracle_matches_live_reference():
+    ref = load_reference()
+    torch.manual_seed(5)
+    fe = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, stride=4, padding=1), torch.nn.ReLU())
+    head = to.AsppHeadOracle(8, RATES, RATES, 5)
+    image, label = torch.randn(1, 3, 40, 56), torch.zeros(1, 37, 61, dtype=torch.int64)
+    for flip in (True, False):
+        assert torch.equal(to.inference(fe, head, image, label, flip=flip), ref.inference(fe, head, image, label, flip=flip))
+        assert torch.equal(to.multi_scale_inference(fe, head, image, label, flip=flip),
+                           ref.multi_scale_inference(fe, head, image, label, flip=flip))
+    assert to.adjust_learning_rate('poly', 2.5e-4, 7, 100, 0.9) == ref.adjust_learning_rate('poly', 2.5e-4, 7, 100, 0.9)
+    with pytest.raises(NotImplementedError):
+        to.adjust_learning_rate('step', 1.0, 1, 2, 0.9)
+
+
+# ------------------------------------------------------------------ 8f-4: optimizer steps
+def test_optimizer_oracle_matches_reference_golden(golden):
+    g = golden("optim")
+    n, steps = int(g["n"]), int(g["steps"])
+    p0 = [torch.from_numpy(g[f"p0.{i}"]) for i in range(n)]
+    grads = [[torch.from_numpy(g[f"g{k}.{i}"]) for i in range(n)] for k in range(steps)]
+    lrs = [to.adjust_learning_rate('poly', float(g["base_lr"]), k, int(g["max_iter"]), float(g["power"])) for k in range(steps)]
+    np.testing.assert_array_equal(np.asarray(lrs), g["lrs"])
+    ps, st = to.optimizer_steps("sgd", p0, grads, lrs=[lr * 10 for lr in lrs], lr=lrs[0] * 10, momentum=0.9, weight_decay=5e-4)
+    for i in range(n):
+        np.testing.assert_array_equal(ps[i].numpy(), g[f"sgd.p.{i}"])
+        np.testing.assert_array_equal(st[i][0].numpy(), g[f"sgd.buf.{i}"])
+    ps, st = to.optimizer_steps("adam", p0, grads, lrs=[lr * 0.4 for lr in lrs], lr=1e-4, betas=(0.9, 0.99))
+    for i in range(n):
+        np.testing.assert_array_equal(ps[i].numpy(), g[f"adam.p.{i}"])
+        np.testing.assert_array_equal(st[i][0].numpy(), g[f"adam.m.{i}"])
+        np.testing.assert_array_equal(st[i][1].numpy(), g[f"adam.v.{i}"])
