@@ -378,6 +378,7 @@ def run_ours(args):
                                                "note": "compute-bound: only low-resolution tensors are read"}}
 
     del d_lr, s_lr
+    aux.update(run_tta_and_optim(b200, _lib, dev, rank, peaks))
     adv = run_adv_step(b200, _lib, synth, dev, rank, world, peaks, args)
 
     cpu_baseline = None
@@ -403,6 +404,62 @@ def run_ours(args):
         emit(line)
     if dist.is_initialized():
         dist.destroy_process_group()
+
+
+def run_tta_and_optim(b200, _lib, dev, rank, peaks):
+    """K7 (flip test-time augmentation fused with argmax + confusion matrix, one 1024x2048 frame per
+    launch, members = head logits of the frame and of its mirror image at 128x256) and K8 (one-launch optimizer steps of the head's
+    SGD and the discriminator's Adam parameter groups; device time from back-to-back raw C-ABI calls, host-inclusive time through
+    the torch.optim-compatible classes)."""
+    import ctypes
+    gen = torch.Generator(device=dev).manual_seed(777 + rank)
+    C, H, W, h, w = 19, 1024, 2048, 128, 256
+    frames = [([torch.randn(1, C, h, w, device=dev, generator=gen) for _ in range(2)],
+               torch.randint(0, C, (1, H, W), device=dev, generator=gen)) for _ in range(8)]       # 8 x 16.8 MB of labels > L2
+    cm = torch.zeros(C, C, dtype=torch.int64, device=dev)
+    k = [0]
+
+    def k7_step():
+        members, labels = frames[k[0] & 7]
+        k[0] += 1
+        _lib.tta_argmax_confusion(members, [False, True], (H, W), labels=labels, divisors=(2,), cm=cm)
+
+    k7_ms, _ = timed(k7_step, 16, 4)
+    k7_bytes = 8 * H * W + 2 * 4 * C * h * w
+    out = {"k7_flip_tta_argmax_confusion": {"ms_per_frame": round(k7_ms / 16, 4), "frames_per_s": round(16 / (k7_ms * 1e-3), 1),
+                                            "algorithmic_bytes": k7_bytes, "members": [[C, h, w]] * 2, "size": [H, W],
+                                            "replaces_bytes_of_materialised_path": 2 * 4 * C * H * W * 6,
+                                            "note": "compute-bound (2 x 19 expf + correctly rounded divisions per label pixel); "
+                                                    "bit-exact against the torch CUDA op sequence of utility.py:179-191"}}
+    del frames
+    lib = _lib.load()
+    for name, shapes, kind in (("k8_head_sgd_step", [(19, 2048, 3, 3), (19,)] * 4, "sgd"),
+                               ("k8_discriminator_adam_step", [(256, 2048, 3, 3), (256,), (128, 256, 3, 3), (128,), (19, 128, 3, 3), (19,),
+                                                               (19, 128, 3, 3), (19,)], "adam")):
+        ps = [torch.nn.Parameter(torch.randn(s, device=dev, generator=gen) * 0.01) for s in shapes]
+        for p_ in ps:
+            p_.grad = torch.randn(p_.shape, device=dev, generator=gen) * 0.01
+        opt = b200.FusedSGD(ps, lr=2.5e-3, momentum=0.9, weight_decay=5e-4) if kind == "sgd" else b200.FusedAdam(ps, lr=1e-4, betas=(0.9, 0.99))
+        api_ms, _ = timed(opt.step, 50, 5)
+        n = len(ps)
+        arr = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() for t in ts])  # noqa: E731
+        numels = (ctypes.c_int64 * n)(*[p_.numel() for p_ in ps])
+        pa, ga = arr(ps), arr([p_.grad for p_ in ps])
+        stream = torch.cuda.current_stream().cuda_stream
+        if kind == "sgd":
+            ba = arr([opt.state[p_]["momentum_buffer"] for p_ in ps])
+            raw = lambda: lib.b200seg_sgd_step(n, pa, ga, ba, numels, 2.5e-3, 0.9, 0.0, 5e-4, 0, 0, 1.0, stream)  # noqa: E731
+        else:
+            ma, va = arr([opt.state[p_]["exp_avg"] for p_ in ps]), arr([opt.state[p_]["exp_avg_sq"] for p_ in ps])
+            raw = lambda: lib.b200seg_adam_step(n, pa, ga, ma, va, numels, 1e-4, 0.9, 0.99, 1e-8, 0.0, 100, 1.0, stream)  # noqa: E731
+        dev_ms, _ = timed(raw, 50, 5)
+        nbytes = sum(p_.numel() for p_ in ps) * (20 if kind == "sgd" else 28)
+        out[name] = {"us_device": round(dev_ms / 50 * 1e3, 2), "us_through_optimizer_api": round(api_ms / 50 * 1e3, 2),
+                     "elements": sum(p_.numel() for p_ in ps), "algorithmic_bytes": nbytes, "bound": "hbm",
+                     "achieved_gbs": round(nbytes / (dev_ms / 50 * 1e-3) / 1e9, 1),
+                     "frac": round(nbytes / (dev_ms / 50 * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                     "note": "parameter group smaller than L2: launch-bound, one launch per group"}
+    return out
 
 
 def run_adv_step(b200, _lib, synth, dev, rank, world, peaks, args):

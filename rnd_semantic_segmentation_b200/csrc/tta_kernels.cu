@@ -15,7 +15,8 @@
 //
 // Bit-exactness: unlike K4 the argmax here depends on the probabilities themselves, so EVERY pixel runs ATen's sequences:
 //   upsample   h0*(w0*a + w1*b) + h1*(w0*c + w1*d) as nvcc contracts it, fma(h0, t, h1*u)      (UpSampleBilinear2d.cu)
-//   softmax    max over classes; fp32 sum of expf(v - max) in class order; expf(v - max) / sum (IEEE) (SoftMax.cu, spatial)
+//   softmax    max over classes; fp32 sum of expf(v - max) in class order; expf(v - max) / sum (IEEE) (SoftMax.cu, spatial);
+//              the 19 IEEE divisions by the same sum share one reciprocal (tta_div: identical results, 3 instructions each)
 //   sum        fp32 adds in member order
 //   division   tensor / python_scalar on CUDA multiplies by the fp32 reciprocal of the scalar     (BinaryDivTrueKernel.cu);
 //              div_exact = 1 selects the IEEE division ATen's CPU kernel performs instead
@@ -49,10 +50,20 @@ struct TtaParams {
 
 __device__ __forceinline__ float tta_lerp(float wa, float a, float wb, float b) { return fmaf(wa, a, __fmul_rn(wb, b)); }
 
-template <int CT>
+// v / s for every class with ONE reciprocal: r = rn(1/s); q = rn(v*r); q' = fma(fma(-q, s, v), r, q) is the correctly rounded
+// quotient (Markstein) as long as nothing is subnormal -- here s is in [1, 32] and v in (0, 1], so only a tiny v needs the generic
+// IEEE division (checked against v / s on 4e8 random pairs, and bit for bit against torch on the GPU by the tests).
+__device__ __forceinline__ float tta_div(float v, float s, float r) {
+  const float q = __fmul_rn(v, r);
+  return fmaf(fmaf(-q, s, v), r, q);
+}
+constexpr float TTA_TINY = 1e-30f;
+
+// EXACT: the class count is the compile-time CT (no per-class predicates)
+template <int CT, bool EXACT>
 __global__ void __launch_bounds__(TTA_THREADS) tta_argmax_confusion_kernel(const TtaParams p) {
   extern __shared__ int tta_hist[];
-  const int C = p.C, CC = p.C * p.C;
+  const int C = EXACT ? CT : p.C, CC = C * C;
   if (p.cm) {
     for (int i = threadIdx.x; i < CC; i += TTA_THREADS) tta_hist[i] = 0;
     __syncthreads();
@@ -75,54 +86,67 @@ __global__ void __launch_bounds__(TTA_THREADS) tta_argmax_confusion_kernel(const
       const int xs = mp.flip ? p.W - 1 - x : x;              // the member saw the mirrored image: un-mirror its probabilities
       const Tap ty = ac_tap(mp.scale_h, y, mp.h);
       const Tap tx = ac_tap(mp.scale_w, xs, mp.w);
-      const long long hw = (long long)mp.h * mp.w;
-      const float* r0 = mp.logits + (long long)ty.i0 * mp.w;
-      const float* r1 = mp.logits + (long long)ty.i1 * mp.w;
+      const unsigned hw = (unsigned)(mp.h * mp.w);           // C * h * w < 2^31 (checked by the launcher): 32-bit element offsets
+      unsigned o00 = (unsigned)(ty.i0 * mp.w + tx.i0), o01 = (unsigned)(ty.i0 * mp.w + tx.i1);
+      unsigned o10 = (unsigned)(ty.i1 * mp.w + tx.i0), o11 = (unsigned)(ty.i1 * mp.w + tx.i1);
+      const float* __restrict__ lg = mp.logits;
       float v[CT];
       float mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < CT; ++c) {
-        if (c < C) {
-          const float t = tta_lerp(tx.l0, __ldg(r0 + c * hw + tx.i0), tx.l1, __ldg(r0 + c * hw + tx.i1));
-          const float u = tta_lerp(tx.l0, __ldg(r1 + c * hw + tx.i0), tx.l1, __ldg(r1 + c * hw + tx.i1));
+        if (EXACT || c < C) {
+          const float t = tta_lerp(tx.l0, __ldg(lg + o00), tx.l1, __ldg(lg + o01));
+          const float u = tta_lerp(tx.l0, __ldg(lg + o10), tx.l1, __ldg(lg + o11));
           v[c] = tta_lerp(ty.l0, t, ty.l1, u);
           mx = fmaxf(mx, v[c]);
+          o00 += hw; o01 += hw; o10 += hw; o11 += hw;
         }
       }
       float s = 0.f;
+      bool tiny = false;                                     // some class is a non-zero value below TTA_TINY (a logit ~69 below the maximum)
 #pragma unroll
       for (int c = 0; c < CT; ++c) {
-        if (c < C) {
+        if (EXACT || c < C) {
           v[c] = expf(v[c] - mx);
           s += v[c];
+          tiny |= (v[c] < TTA_TINY) & (v[c] != 0.f);
         }
       }
+      // acc starts at +0 and the probabilities are >= +0, so the first member's 0 + p is p itself
+      if (!tiny) {
+        const float r = __frcp_rn(s);
 #pragma unroll
-      for (int c = 0; c < CT; ++c) {
-        if (c < C) {
-          const float pc = __fdiv_rn(v[c], s);
-          acc[c] = (m == 0) ? pc : __fadd_rn(acc[c], pc);
-        }
+        for (int c = 0; c < CT; ++c)
+          if (EXACT || c < C) acc[c] = __fadd_rn(acc[c], tta_div(v[c], s, r));
+      } else {
+#pragma unroll
+        for (int c = 0; c < CT; ++c)                         // (unrolled as well: a dynamically indexed acc[] would live in local memory)
+          if (EXACT || c < C) acc[c] = __fadd_rn(acc[c], __fdiv_rn(v[c], s));
       }
     }
 #pragma unroll 1
     for (int k = 0; k < p.n_div; ++k) {
       const float d = p.div[k];
-      const float r = __fdiv_rn(1.0f, d);
+      if (!p.div_exact) {
+        const float r = __fdiv_rn(1.0f, d);
 #pragma unroll
-      for (int c = 0; c < CT; ++c) acc[c] = p.div_exact ? __fdiv_rn(acc[c], d) : __fmul_rn(acc[c], r);
+        for (int c = 0; c < CT; ++c) acc[c] = __fmul_rn(acc[c], r);
+      } else {
+#pragma unroll
+        for (int c = 0; c < CT; ++c) acc[c] = __fdiv_rn(acc[c], d);
+      }
     }
     float best = acc[0];
     int idx = 0;
 #pragma unroll
     for (int c = 1; c < CT; ++c) {
-      if (c < C && acc[c] > best) { best = acc[c]; idx = c; }
+      if ((EXACT || c < C) && acc[c] > best) { best = acc[c]; idx = c; }
     }
     const long long pix = (long long)y * p.W + x;
     if (p.probs) {
 #pragma unroll
       for (int c = 0; c < CT; ++c)
-        if (c < C) __stcs(p.probs + c * plane + pix, acc[c]);
+        if (EXACT || c < C) __stcs(p.probs + c * plane + pix, acc[c]);
     }
     if (p.pred) p.pred[pix] = idx;
     if (p.cm) {
@@ -153,6 +177,7 @@ int tta_launch(const float* const* logits, const int* hs, const int* ws, const i
   TtaParams p = {};
   for (int m = 0; m < n_maps; ++m) {
     B200SEG_CHECK_ARG(logits[m] && hs[m] > 0 && ws[m] > 0, "tta_argmax_confusion: member %d has a null pointer or an empty shape", m);
+    B200SEG_CHECK_ARG((long long)C * hs[m] * ws[m] < (1LL << 31), "tta_argmax_confusion: member %d is too large", m);
     p.maps[m].logits = logits[m];
     p.maps[m].h = hs[m];
     p.maps[m].w = ws[m];
@@ -172,10 +197,11 @@ int tta_launch(const float* const* logits, const int* hs, const int* ws, const i
   const int grid = (int)(units < cap ? units : cap);
   const size_t smem = cm ? (size_t)C * C * 4 : 0;
   profile_begin(15, stream);
-  if (C <= 2) tta_argmax_confusion_kernel<2><<<grid, TTA_THREADS, smem, stream>>>(p);
-  else if (C <= 8) tta_argmax_confusion_kernel<8><<<grid, TTA_THREADS, smem, stream>>>(p);
-  else if (C <= 19) tta_argmax_confusion_kernel<19><<<grid, TTA_THREADS, smem, stream>>>(p);
-  else tta_argmax_confusion_kernel<32><<<grid, TTA_THREADS, smem, stream>>>(p);
+  if (C == 2) tta_argmax_confusion_kernel<2, true><<<grid, TTA_THREADS, smem, stream>>>(p);
+  else if (C == 19) tta_argmax_confusion_kernel<19, true><<<grid, TTA_THREADS, smem, stream>>>(p);
+  else if (C <= 8) tta_argmax_confusion_kernel<8, false><<<grid, TTA_THREADS, smem, stream>>>(p);
+  else if (C <= 20) tta_argmax_confusion_kernel<20, false><<<grid, TTA_THREADS, smem, stream>>>(p);
+  else tta_argmax_confusion_kernel<32, false><<<grid, TTA_THREADS, smem, stream>>>(p);
   profile_end(15, stream);
   B200SEG_LAUNCH_CHECK();
   return B200SEG_OK;

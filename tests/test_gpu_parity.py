@@ -757,7 +757,8 @@ def test_k7_tta_bit_exact_against_torch_cuda(lib, C, shapes, flips, divisors, H,
 
 
 def test_k7_flip_symmetry_and_errors(lib):
-    """Size-independent properties: mirroring every member and toggling every flip flag mirrors the output; a member averaged
+    """Size-independent properties: mirroring every member and toggling every flip flag leaves the output unchanged (up to
+    the rounding of the mirrored sampling positions); a member averaged
     with its own mirror image (flagged as mirrored) reproduces the single member; IEEE-division mode equals reciprocal mode for
     powers of two."""
     C, H, W = 19, 96, 160
@@ -765,7 +766,7 @@ def test_k7_flip_symmetry_and_errors(lib):
     _, pred, probs = lib.tta_argmax_confusion([a, b], [False, True], (H, W), divisors=(2,), want_pred=True, want_probs=True)
     _, pred_m, probs_m = lib.tta_argmax_confusion([a.flip(3).contiguous(), b.flip(3).contiguous()], [True, False], (H, W),
                                                   divisors=(2,), want_pred=True, want_probs=True)
-    assert rel_err(probs_m.flip(2), probs) <= 1e-6
+    assert rel_err(probs_m, probs) <= 1e-5 and (pred_m != pred).float().mean().item() < 1e-3
     _, _, probs_s = lib.tta_argmax_confusion([a, a.flip(3).contiguous()], [False, True], (H, W), divisors=(2,), want_probs=True)
     _, _, probs_1 = lib.tta_argmax_confusion([a], [False], (H, W), want_probs=True)
     assert rel_err(probs_s, probs_1) <= 1e-5
