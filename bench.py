@@ -458,7 +458,7 @@ def run_tta_and_optim(b200, _lib, dev, rank, peaks):
                      "elements": sum(p_.numel() for p_ in ps), "algorithmic_bytes": nbytes, "bound": "hbm",
                      "achieved_gbs": round(nbytes / (dev_ms / 50 * 1e-3) / 1e9, 1),
                      "frac": round(nbytes / (dev_ms / 50 * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
-                     "note": "parameter group smaller than L2: launch-bound, one launch per group"}
+                     "note": "parameter group of the size of L2 or smaller, re-touched every step: largely L2-resident (a fraction above 1 means L2 hits), launch-bound; one launch per group"}
     return out
 
 
