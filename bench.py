@@ -478,6 +478,9 @@ def run_adv_step(b200, _lib, synth, dev, rank, world, peaks, args):
     b200.set_feature_pack_cache(2)
 
     freeze = [False]
+    with_opt = [False]
+    opt_cls = b200.FusedSGD(head.parameters(), lr=2.5e-3, momentum=0.9, weight_decay=5e-4)     # aspp_trainer.py:26
+    opt_d = b200.FusedAdam(model_D.parameters(), lr=1e-4, betas=(0.9, 0.99))                   # fada_adapter.py:24
 
     def adv_step():
         b200.clear_feature_pack_cache()                       # new features every iteration: 2 conversions per step, not 0
@@ -494,6 +497,8 @@ def run_adv_step(b200, _lib, synth, dev, rank, world, peaks, args):
                 p.requires_grad_(False)
         loss_adv = 0.001 * model_D.forward_soft_loss(tgt_fea, tgt_lr, size, slot=0)      # :110-112
         loss_adv.backward()
+        if with_opt[0]:
+            opt_cls.step()                                                               # :115 (K8)
         for p in model_D.parameters():                                                   # optimizer_D.zero_grad(), :117
             p.grad = None
             p.requires_grad_(True)
@@ -501,6 +506,8 @@ def run_adv_step(b200, _lib, synth, dev, rank, world, peaks, args):
         loss_d_src.backward()
         loss_d_tgt = 0.5 * model_D.forward_soft_loss(tgt_fea.detach(), tgt_lr, size, slot=1)   # :123-125
         loss_d_tgt.backward()
+        if with_opt[0]:
+            opt_d.step()                                                                 # :127 (K8)
         return loss_seg, loss_adv, loss_d_src, loss_d_tgt
 
     l0 = _lib.launch_count()
@@ -516,6 +523,9 @@ def run_adv_step(b200, _lib, synth, dev, rank, world, peaks, args):
     freeze[0] = True
     ms_frozen, _ = timed(adv_step, args.steps, args.warmup)
     freeze[0] = False
+    with_opt[0] = True                                       # the same iteration with the head's SGD and the discriminator's Adam step
+    ms_opt, _ = timed(adv_step, args.steps, args.warmup)
+    with_opt[0] = False
     # the whole iteration (~100 launches) captured once in a CUDA graph and replayed: what the launch gaps cost
     graph_ms = None
     try:
@@ -551,7 +561,10 @@ def run_adv_step(b200, _lib, synth, dev, rank, world, peaks, args):
                          "frac": round(tf / peaks["bf16_tflops_sustained"], 4), "traffic": load_traffic("conv3x3_fwd"),
                          "algorithmic_flops_per_step": f_step, "conv_ms_per_step": round(conv_ms, 4)},
             "cuda_graph_replay_ms_per_step": graph_ms,
-            "variants": {"discriminator_frozen_in_adversarial_pass": {
+            "variants": {"with_optimizer_steps": {
+                "ms_per_step": round(ms_opt / args.steps, 4),
+                "note": "plus optimizer_cls.step() (aspp_fada.py:115, FusedSGD) and optimizer_D.step() (:127, FusedAdam): one K8 launch each"},
+                         "discriminator_frozen_in_adversarial_pass": {
                 "ms_per_step": round(ms_frozen / args.steps, 4),
                 "note": "model_D parameters set requires_grad=False around aspp_fada.py:110-112: the weight gradients that pass "
                         "would compute are zeroed at :117 before anyone reads them, so the parameter updates are identical"}},

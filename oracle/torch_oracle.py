@@ -384,3 +384,34 @@ def fada_step(head: nn.Module, model_D: nn.Module, src_fea, tgt_fea, src_label,
     loss_D_tgt = 0.5 * soft_label_cross_entropy(model_D(tgt_fea.detach(), size), tgt_q1)     # :123-125
     loss_D_tgt.backward()
     return loss_seg.detach(), loss_adv_tgt.detach(), loss_D_src.detach(), loss_D_tgt.detach()
+
+
+def fada_iteration(head: nn.Module, model_D: nn.Module, optimizer_cls, optimizer_D, src_fea, tgt_fea, src_label,
+                   temperature: float = 1.8, ignore_index: int = 255):
+    """The same iteration WITH the optimizer steps where the reference takes them (aspp_fada.py:80-127 after the backbone;
+    optimizer_fea belongs to the backbone and is out of scope): zero_grad :80-82, optimizer_cls.step() after the adversarial
+    backward :114-115, optimizer_D.zero_grad() :117, optimizer_D.step() :127 -- so the two discriminator-update passes see the
+    discriminator weights of the start of the iteration and the head's step does not feed back into this iteration's losses
+    (the soft labels were taken before it).  Returns the four scalar losses."""
+    size = src_label.shape[-2:]
+    optimizer_cls.zero_grad()
+    optimizer_D.zero_grad()
+    src_fea = src_fea.detach().requires_grad_(True)
+    tgt_fea = tgt_fea.detach().requires_grad_(True)
+    src_pred = head(src_fea, size).div(temperature)
+    loss_seg = hard_cross_entropy(src_pred, src_label, ignore_index)
+    loss_seg.backward()
+    src_soft = build_soft_label(src_pred.detach(), slot=0)
+    tgt_pred = head(tgt_fea, size).div(temperature)
+    tgt_q0 = build_soft_label(tgt_pred.detach(), slot=0)
+    tgt_q1 = build_soft_label(tgt_pred.detach(), slot=1)
+    loss_adv_tgt = 0.001 * soft_label_cross_entropy(model_D(tgt_fea, size), tgt_q0)
+    loss_adv_tgt.backward()
+    optimizer_cls.step()                                                             # :115
+    optimizer_D.zero_grad()                                                          # :117
+    loss_D_src = 0.5 * soft_label_cross_entropy(model_D(src_fea.detach(), size), src_soft)
+    loss_D_src.backward()
+    loss_D_tgt = 0.5 * soft_label_cross_entropy(model_D(tgt_fea.detach(), size), tgt_q1)
+    loss_D_tgt.backward()
+    optimizer_D.step()                                                               # :127
+    return loss_seg.detach(), loss_adv_tgt.detach(), loss_D_src.detach(), loss_D_tgt.detach()

@@ -602,6 +602,72 @@ def test_fada_iteration_losses_match_oracle(lib):
         assert ((got - exp).norm() / exp.norm()).item() <= 3e-2, name
 
 
+def test_fada_iterations_with_optimizer_steps_match_oracle(lib):
+    """Three consecutive adversarial iterations INCLUDING the optimizer steps where the reference takes them (aspp_fada.py:
+    80-127 after the backbone: optimizer_cls.step() after the adversarial backward, optimizer_D.step() at the end, poly learning
+    rates rewritten into the param groups) -- FusedSGD / FusedAdam on the gradients our kernels produce, against torch.optim on
+    the oracle's: losses of every iteration, and the parameter UPDATES accumulated over the three iterations."""
+    import copy
+    import rnd_semantic_segmentation_b200 as b200
+    n, cin, C, h, w, H, W = 2, 256, 19, 16, 32, 128, 256
+    torch.manual_seed(91)
+    ref_head = to.AsppHeadOracle(cin, RATES, RATES, C)
+    ref_D = to.PixelDiscriminatorOracle(cin, 64, num_classes=C)
+    head = b200.ASPP_Classifier_V2(cin, RATES, RATES, C)
+    head.load_state_dict(ref_head.state_dict())
+    D = b200.PixelDiscriminator(cin, 64, num_classes=C)
+    D.load_state_dict(ref_D.state_dict())
+    head.cuda(), D.cuda()
+    head0, D0 = copy.deepcopy(ref_head.state_dict()), copy.deepcopy(ref_D.state_dict())
+    base_lr, base_lr_d, max_iter = 2.5e-4, 1e-4, 10
+    ref_cls = torch.optim.SGD(ref_head.parameters(), lr=base_lr * 10, momentum=0.9, weight_decay=5e-4)       # aspp_trainer.py:26
+    ref_opt_d = torch.optim.Adam(ref_D.parameters(), lr=base_lr_d, betas=(0.9, 0.99))                        # fada_adapter.py:24
+    opt_cls = b200.FusedSGD(head.parameters(), lr=base_lr * 10, momentum=0.9, weight_decay=5e-4)
+    opt_d = b200.FusedAdam(D.parameters(), lr=base_lr_d, betas=(0.9, 0.99))
+    g = torch.Generator().manual_seed(92)
+    size = (H, W)
+    for it in range(3):
+        src, tgt = (torch.relu(torch.randn(n, cin, h, w, generator=g)) for _ in range(2))
+        lab = make_labels(n, H, W, C, 0.1, 93 + it)
+        lr = b200.adjust_learning_rate('poly', base_lr, it, max_iter, 0.9)
+        lr_d = b200.adjust_learning_rate('poly', base_lr_d, it, max_iter, 0.9)
+        for o in (ref_cls, opt_cls):
+            for grp in o.param_groups:
+                grp['lr'] = lr * 10
+        for o in (ref_opt_d, opt_d):
+            for grp in o.param_groups:
+                grp['lr'] = lr_d
+        want = to.fada_iteration(ref_head, ref_D, ref_cls, ref_opt_d, src, tgt, lab)
+        opt_cls.zero_grad()
+        opt_d.zero_grad()
+        src_fea, tgt_fea = src.cuda().requires_grad_(True), tgt.cuda().requires_grad_(True)
+        loss_seg, src_lr = head.forward_loss(src_fea, lab.cuda(), temperature=1.8)
+        loss_seg.backward()
+        with torch.no_grad():
+            tgt_lr = head.logits(tgt_fea)
+        loss_adv = 0.001 * D.forward_soft_loss(tgt_fea, tgt_lr, size, slot=0)
+        loss_adv.backward()
+        opt_cls.step()
+        opt_d.zero_grad()
+        loss_d_src = 0.5 * D.forward_soft_loss(src_fea.detach(), src_lr, size, slot=0)
+        loss_d_src.backward()
+        loss_d_tgt = 0.5 * D.forward_soft_loss(tgt_fea.detach(), tgt_lr, size, slot=1)
+        loss_d_tgt.backward()
+        opt_d.step()
+        for name, got, exp in zip(("seg", "adv_tgt", "D_src", "D_tgt"), (loss_seg, loss_adv, loss_d_src, loss_d_tgt), want):
+            assert abs(got.item() - exp.item()) <= 5e-3 * abs(exp.item()), (it, name, got.item(), exp.item())
+    # updates (parameter minus its initial value): SGD's follow the gradients (bf16-operand tolerance of the K1 tests, 2e-2);
+    # Adam's are lr * m / sqrt(v) ~ lr * sign-like, so elements whose gradient is near zero amplify any gradient difference:
+    # compare those in L2
+    for (name, p), pr in zip(head.named_parameters(), ref_head.parameters()):
+        d_got, d_exp = p.detach().cpu().double() - head0[name].double(), pr.detach().double() - head0[name].double()
+        assert float(d_exp.abs().max()) > 0 and rel_err(d_got, d_exp) <= 2e-2, name
+    for (name, p), pr in zip(D.named_parameters(), ref_D.parameters()):
+        d_got, d_exp = p.detach().cpu().double() - D0[name].double(), pr.detach().double() - D0[name].double()
+        assert float(d_exp.norm()) > 0 and ((d_got - d_exp).norm() / d_exp.norm()).item() <= 0.1, name
+    assert float(opt_d.state[next(iter(D.parameters()))]["step"]) == 3
+
+
 def test_cuda_graph_capture_train_eval_and_discriminator(lib):
     """the ops are capture-safe.  One train step (head forward_loss + backward), one eval step (head logits + fused
     argmax / confusion) and one discriminator loss step are captured in CUDA graphs; after the inputs are overwritten in place the

@@ -246,3 +246,24 @@ def test_optimizer_oracle_matches_reference_golden(golden):
         np.testing.assert_array_equal(ps[i].numpy(), g[f"adam.p.{i}"])
         np.testing.assert_array_equal(st[i][0].numpy(), g[f"adam.m.{i}"])
         np.testing.assert_array_equal(st[i][1].numpy(), g[f"adam.v.{i}"])
+
+
+def test_fada_iteration_oracle_equals_fada_step_losses_and_moves_parameters():
+    """The iteration with optimizer steps (aspp_fada.py:80-127) logs the same four losses as the step without them -- the head's
+    step comes after its last use in the iteration, the discriminator's at the very end -- and leaves updated parameters."""
+    import copy
+    torch.manual_seed(3)
+    head = to.AsppHeadOracle(8, RATES, RATES, 5)
+    D = to.PixelDiscriminatorOracle(8, 8, num_classes=5)
+    head2, D2 = copy.deepcopy(head), copy.deepcopy(D)
+    src, tgt = torch.relu(torch.randn(1, 8, 6, 7)), torch.relu(torch.randn(1, 8, 6, 7))
+    lab = torch.randint(0, 5, (1, 24, 28))
+    lab[0, :3] = 255
+    want = to.fada_step(head, D, src, tgt, lab)
+    oc = torch.optim.SGD(head2.parameters(), lr=2.5e-3, momentum=0.9, weight_decay=5e-4)
+    od = torch.optim.Adam(D2.parameters(), lr=1e-4, betas=(0.9, 0.99))
+    got = to.fada_iteration(head2, D2, oc, od, src, tgt, lab)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    assert all(not torch.equal(p, q) for p, q in zip(head.parameters(), head2.parameters()))
+    assert all(not torch.equal(p, q) for p, q in zip(D.parameters(), D2.parameters()))
