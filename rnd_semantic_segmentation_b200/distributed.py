@@ -150,6 +150,16 @@ class HeadGradBucket(FlatGradBucket):
                 self.flat.div_(dist.get_world_size(self.group))
         self._pending = True
 
+    def step(self, optimizer):
+        """``optimizer.step()`` for the bucket's parameters, enqueued on the bucket's stream directly behind the all-reduce
+        (SURVEY 8f rank 4): with ``FusedSGD`` that is one K8 launch, so all-reduce + update both run underneath the
+        data-gradient GEMM and the host never waits for the collective.  Safe while that GEMM is in flight: it reads the
+        PACKED bf16 weights of this step's forward, not the parameters.  ``wait()`` (before the next forward) joins."""
+        if not self._pending:
+            return optimizer.step()
+        with torch.cuda.stream(self.stream):
+            return optimizer.step()
+
     def wait(self):
         if self._pending:
             torch.cuda.current_stream().wait_stream(self.stream)

@@ -69,6 +69,15 @@ def _launch(fn, device, *args):
         _lib._check(fn(*args, _lib._stream()))
 
 
+def _touched(params, *states):
+    """The kernels write through raw pointers: tell autograd's version counters, so that whatever keys a cache on
+    ``tensor._version`` (the modules' packed bf16 weights do) or saved a tensor for backward sees the in-place update."""
+    torch.autograd.graph.increment_version(params)
+    for st in states:
+        if st:
+            torch.autograd.graph.increment_version(st)
+
+
 class _PlanMixin:
     """Per-group launch plans: the state tensors of a group are stable objects between ``load_state_dict`` calls, so their
     pointer tables (and the element counts) are built once; a step then costs one pass over the gradients on the host."""
@@ -120,6 +129,7 @@ class FusedSGD(_PlanMixin, torch.optim.SGD):
             if plan is not None:
                 _launch(lib.b200seg_sgd_step, params[0].device, len(params), _ptrs(params), _ptrs(grads), plan["bufs"], plan["numels"],
                         *hyper, 0, self.grad_scale)
+                _touched(params, plan["keep"])
                 continue
             state = self.state
             is_fresh = [momentum != 0 and state[p].get("momentum_buffer") is None for p in params]
@@ -139,6 +149,7 @@ class FusedSGD(_PlanMixin, torch.optim.SGD):
                 numels = (_lib.c_i64 * len(ps))(*[p.numel() for p in ps])
                 _launch(lib.b200seg_sgd_step, ps[0].device, len(ps), _ptrs(ps), _ptrs(gs), _ptrs(bufs) if bufs else None, numels,
                         *hyper, 1 if first else 0, self.grad_scale)
+                _touched(ps, bufs)
             bufs = [state[p]["momentum_buffer"] for p in params] if momentum != 0 else None
             self._plans[gi] = dict(ids=[id(p) for p in params], keep=bufs, bufs=_ptrs(bufs) if bufs else None,
                                    numels=(_lib.c_i64 * len(params))(*[p.numel() for p in params]))
@@ -178,6 +189,7 @@ class FusedAdam(_PlanMixin, torch.optim.Adam):
                 plan["step"] += 1
                 _launch(lib.b200seg_adam_step, params[0].device, len(params), _ptrs(params), _ptrs(grads), plan["m"], plan["v"],
                         plan["numels"], *hyper, plan["step"], self.grad_scale)
+                _touched(params, *plan["keep"])
                 continue
             by_step = {}
             for p, g in zip(params, grads):
@@ -196,6 +208,7 @@ class FusedAdam(_PlanMixin, torch.optim.Adam):
                 numels = (_lib.c_i64 * len(ps))(*[p.numel() for p in ps])
                 _launch(lib.b200seg_adam_step, ps[0].device, len(ps), _ptrs(ps), _ptrs([it[1] for it in items]), _ptrs(ms), _ptrs(vs),
                         numels, *hyper, step, self.grad_scale)
+                _touched(ps, ms, vs)
             if len(by_step) == 1 and all(not self.state[p]["step"].is_cuda for p in params):
                 ms, vs = [self.state[p]["exp_avg"] for p in params], [self.state[p]["exp_avg_sq"] for p in params]
                 step = next(iter(by_step))

@@ -997,3 +997,30 @@ def test_k8_rejects_cpu_parameters(lib):
     for cls, kw in ((b200.FusedSGD, dict(lr=0.1, momentum=0.9)), (b200.FusedAdam, dict(lr=0.1))):
         with pytest.raises(lib.B200SegError):
             cls([p], **kw).step()
+
+
+def test_k8_step_invalidates_packed_weight_caches(lib):
+    """The kernels update parameters through raw pointers; the modules cache their packed bf16 weights keyed on the parameters'
+    version counters, so a fused step must bump them: the next forward uses the updated weights."""
+    import rnd_semantic_segmentation_b200 as b200
+    torch.manual_seed(12)
+    head = b200.ASPP_Classifier_V2(64, RATES, RATES, 19).cuda()
+    D = b200.PixelDiscriminator(64, 16, num_classes=19).cuda()
+    x = torch.relu(torch.randn(1, 64, 20, 24, device="cuda"))
+    for mod, opt in ((head, b200.FusedSGD(head.parameters(), lr=0.5, momentum=0.9)), (D, b200.FusedAdam(D.parameters(), lr=0.05))):
+        for step in range(2):                                 # first step (state creation path) and a planned step
+            with torch.no_grad():
+                before = mod(x).clone()
+            versions = [p._version for p in mod.parameters()]
+            for p in mod.parameters():
+                p.grad = torch.randn_like(p)
+            opt.step()
+            assert all(p._version > v for p, v in zip(mod.parameters(), versions))
+            with torch.no_grad():
+                after = mod(x)
+            fresh = type(mod)(64, RATES, RATES, 19) if mod is head else type(mod)(64, 16, num_classes=19)
+            fresh.load_state_dict(mod.state_dict())
+            fresh.cuda()
+            with torch.no_grad():
+                want = fresh(x)
+            assert not torch.equal(after, before) and torch.equal(after, want), (type(mod).__name__, step)
