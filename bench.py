@@ -198,6 +198,9 @@ def run_ours(args):
         xg = x_in.detach().requires_grad_(True)            # the backbone needs d loss / d features
         for p in head.parameters():
             p.grad = None
+        # in training the weights change every step, so the bf16 weight pack is part of every step: invalidate the module's
+        # packed-weight cache (keyed on the parameters' version counters) exactly as an optimizer step would
+        torch.autograd.graph.increment_version(head.conv2d_list[0].weight)
         # N > 1: weight gradients land in the flat bucket and its NCCL mean all-reduce runs on a second stream underneath
         # the data-gradient GEMM; wait() joins the streams (the all-reduce is inside the timed step)
         loss, _ = head.forward_loss(xg, labels_in, grad_bucket=bucket)
@@ -393,7 +396,7 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": args.workload, "features": [n, cin, h, w], "labels": [n, H, W], "num_classes": C,
                            "input": "fp32 NCHW features resident in HBM (reference API contract); bf16 operands, fp32 accumulate",
-                           "step": "head fwd + upsample/CE fwd + bwd (dX, dW, db)" + (" + NCCL mean all-reduce of head grads (overlapped with the dgrad GEMM)" if world > 1 else ""),
+                           "step": "bf16 weight pack + head fwd + upsample/CE fwd + bwd (dX, dW, db)" + (" + NCCL mean all-reduce of head grads (overlapped with the dgrad GEMM)" if world > 1 else ""),
                            "l2": "inputs larger than L2 (features %d MB per step)" % (x.numel() * 4 // 2 ** 20),
                            "parallelism": "dp%d (batch sharded by image)" % world},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_timed), "roofline": roofline, "eval": eval_obj,
@@ -486,6 +489,8 @@ def run_adv_step(b200, _lib, synth, dev, rank, world, peaks, args):
         b200.clear_feature_pack_cache()                       # new features every iteration: 2 conversions per step, not 0
         for p in list(head.parameters()) + list(model_D.parameters()):
             p.grad = None
+        # weights change every iteration in training: both modules re-pack their bf16 weights once per step
+        torch.autograd.graph.increment_version([head.conv2d_list[0].weight, model_D.cls1.weight])
         src_fea = src.detach().requires_grad_(True)
         tgt_fea = tgt.detach().requires_grad_(True)
         loss_seg, src_lr = head.forward_loss(src_fea, lab, temperature=1.8)              # aspp_fada.py:91-96
