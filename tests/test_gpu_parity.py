@@ -1024,3 +1024,32 @@ def test_k8_step_invalidates_packed_weight_caches(lib):
             with torch.no_grad():
                 want = fresh(x)
             assert not torch.equal(after, before) and torch.equal(after, want), (type(mod).__name__, step)
+
+
+def test_k8_unaligned_views_and_two_launch_groups(lib):
+    """25 parameters that are 4-byte-aligned views into one buffer (scalar head/tail paths, > 16 tensors = two launches, lengths
+    1 .. 4097) with guard elements between them: the update equals torch.optim's and nothing outside the views is touched."""
+    import rnd_semantic_segmentation_b200 as b200
+    g = torch.Generator().manual_seed(21)
+    shapes = [(19, 64, 3, 3), (19,), (4097,), (3, 5), (1,)] * 5
+    total = sum(torch.Size(s).numel() + 3 for s in shapes) + 8
+    for kind, hyper in (("sgd", dict(lr=0.1, momentum=0.9, weight_decay=1e-3)), ("adam", dict(lr=1e-3, betas=(0.9, 0.99)))):
+        base0 = torch.randn(total, generator=g)
+        base = base0.clone().cuda()
+        ours, refs, mask, off = [], [], torch.zeros(total, dtype=torch.bool), 1
+        for s in shapes:
+            nel = torch.Size(s).numel()
+            ours.append(torch.nn.Parameter(base[off:off + nel].view(s)))
+            refs.append(torch.nn.Parameter(base0[off:off + nel].view(s).clone().cuda()))
+            mask[off:off + nel] = True
+            off += nel + 3                                   # three guard elements after every tensor
+        oa = (b200.FusedSGD if kind == "sgd" else b200.FusedAdam)(ours, **hyper)
+        ob = (torch.optim.SGD if kind == "sgd" else torch.optim.Adam)(refs, foreach=False, **hyper)
+        for _ in range(3):
+            for a, b in zip(ours, refs):
+                gr = torch.randn(a.shape, generator=g).cuda()
+                a.grad, b.grad = gr.clone(), gr.clone()
+            oa.step(); ob.step()
+        for a, b in zip(ours, refs):
+            assert rel_err(a, b) <= OPT_TOL
+        assert torch.equal(base.cpu()[~mask], base0[~mask])     # guards untouched
