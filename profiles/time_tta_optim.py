@@ -42,6 +42,10 @@ for name, shapes, flips, divs in (("flip", [(128, 256)] * 2, [False, True], (2,)
                                                          pred_mismatch=int((pred.unsqueeze(0) != want.max(1)[1]).sum()))
     cm = torch.zeros(C, C, dtype=torch.int64, device="cuda")
     rec["fused_pred_cm_ms"] = timeit(lambda: _lib.tta_argmax_confusion(members, flips, (H, W), labels=labels, divisors=divs, cm=cm, want_pred=True))
+    if len(members) <= 2:
+        _lib.tta_set_row_walk(False)
+        rec["fused_pred_cm_per_pixel_kernel_ms"] = timeit(lambda: _lib.tta_argmax_confusion(members, flips, (H, W), labels=labels, divisors=divs, cm=cm, want_pred=True))
+        _lib.tta_set_row_walk(True)
     rec["fused_cm_only_ms"] = timeit(lambda: _lib.tta_argmax_confusion(members, flips, (H, W), labels=labels, divisors=divs, cm=cm))
     rec["fused_probs_ms"] = timeit(lambda: _lib.tta_argmax_confusion(members, flips, (H, W), divisors=divs, want_probs=True))
 

@@ -83,6 +83,7 @@ SIGNATURES = {
     "b200seg_gemm_set_narrow_tiles": (None, [c_int]),
     "b200seg_tta_argmax_confusion": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp, c_int, c_int,
                                              c_vp, c_vp, c_vp, c_vp]),
+    "b200seg_tta_set_row_walk": (None, [c_int]),
     "b200seg_sgd_step": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_f32, c_f32, c_f32, c_f32, c_int, c_int, c_f32, c_vp]),
     "b200seg_adam_step": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_f32, c_vp]),
     "b200seg_gemm_set_dgrad_n_fastest": (None, [c_int]),
@@ -264,6 +265,11 @@ def tta_argmax_confusion(members: Sequence[torch.Tensor], flips: Sequence[bool],
         _check(lib.b200seg_tta_argmax_confusion(_ptr_array(maps), hs, ws, fl, n, C, _ptr(labels), H, W, int(ignore_index), dv,
                                                 len(divisors), 1 if div_exact else 0, _ptr(cm), _ptr(pred), _ptr(probs), _stream()))
     return cm, pred, probs
+
+
+def tta_set_row_walk(on):
+    """K7 A/B: row-walking kernel for <= 2 members (default) vs the per-pixel kernel."""
+    load().b200seg_tta_set_row_walk(1 if on else 0)
 
 
 def _optim_tables(params, grads, *states):

@@ -88,6 +88,7 @@ long long nhwc_colsum_scratch_bytes(int);
 int nhwc_bf16_colsum(const void*, long long, int, int, void*, float*, cudaStream_t);
 int tta_launch(const float* const*, const int*, const int*, const int*, int, int, const long long*, int, int, int, const float*, int, int,
                long long*, long long*, float*, cudaStream_t);
+void tta_set_row_walk(int);
 int sgd_step(int, float* const*, const float* const*, float* const*, const long long*, float, float, float, float, int, int, float,
              cudaStream_t);
 int adam_step(int, float* const*, const float* const*, float* const*, float* const*, const long long*, float, float, float, float,
@@ -350,6 +351,8 @@ int b200seg_tta_argmax_confusion(const float* const* logits_lr, const int* h, co
   return tta_launch(logits_lr, h, w, flip, n_members, C, reinterpret_cast<const long long*>(labels), H, W, ignore_index, divisors,
                     n_div, div_exact, reinterpret_cast<long long*>(cm), reinterpret_cast<long long*>(pred), probs, S(stream));
 }
+
+void b200seg_tta_set_row_walk(int on) { tta_set_row_walk(on); }
 
 int b200seg_sgd_step(int n_tensors, float* const* params, const float* const* grads, float* const* momentum_bufs,
                      const int64_t* numels, float lr, float momentum, float dampening, float weight_decay, int nesterov,

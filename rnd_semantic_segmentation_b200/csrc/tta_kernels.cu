@@ -163,6 +163,172 @@ __global__ void __launch_bounds__(TTA_THREADS) tta_argmax_confusion_kernel(const
   }
 }
 
+// ---- row-walking variant for ensembles of one or two members (inference(flip=True), the reference's default) ----------------
+// The horizontal lerps of a source row do not depend on the output row: a thread (= one output column) keeps, per member and
+// class, the pair {t, u} = horizontal lerps on the two source rows of the current output row in SHARED memory, laid out
+// [member][class][thread] (8-byte accesses, conflict-free, private to the thread: no barriers), and refreshes it only when the
+// source-row pair changes (every (H-1)/(h-1) ~ 8 rows; moving down by one source row re-uses u as the new t).  Per pixel and member
+// that leaves one LDS.64 + the vertical lerp per class instead of four global loads and three lerps -- identical arithmetic,
+// ~2x fewer instructions.  A unit is TTA_RB consecutive rows of one 128-column strip.
+constexpr int TTA_RB = 8;
+constexpr int TTA_ROWS_MAX_MAPS = 2;
+
+template <int CT, bool EXACT>
+__device__ __forceinline__ void tta_hrow(const TtaMap& mp, int C, int row, const Tap& tx, float (&out)[CT]) {
+  const unsigned hw = (unsigned)(mp.h * mp.w);
+  unsigned o0 = (unsigned)(row * mp.w + tx.i0), o1 = (unsigned)(row * mp.w + tx.i1);
+  const float* __restrict__ lg = mp.logits;
+#pragma unroll
+  for (int c = 0; c < CT; ++c) {
+    if (EXACT || c < C) {
+      out[c] = tta_lerp(tx.l0, __ldg(lg + o0), tx.l1, __ldg(lg + o1));
+      o0 += hw; o1 += hw;
+    }
+  }
+}
+
+template <int CT, bool EXACT>
+__global__ void __launch_bounds__(TTA_THREADS) tta_rows_kernel(const TtaParams p) {
+  extern __shared__ __align__(16) unsigned char tta_smem_raw[];
+  // [n_maps][CT][TTA_THREADS] float2 pairs, then the int32 histogram
+  float2* pairs = reinterpret_cast<float2*>(tta_smem_raw);
+  int* hist = reinterpret_cast<int*>(tta_smem_raw + (size_t)p.n_maps * CT * TTA_THREADS * sizeof(float2));
+  const int C = EXACT ? CT : p.C, CC = C * C;
+  if (p.cm) {
+    for (int i = threadIdx.x; i < CC; i += TTA_THREADS) hist[i] = 0;
+    __syncthreads();
+  }
+  const int tiles_x = ceil_div(p.W, TTA_THREADS), blocks_y = ceil_div(p.H, TTA_RB);
+  const int units = tiles_x * blocks_y;
+  const long long plane = (long long)p.H * p.W;
+  for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    const int x = (unit / blocks_y) * TTA_THREADS + threadIdx.x;        // consecutive units walk DOWN a strip
+    const int y0 = (unit % blocks_y) * TTA_RB, y1 = min(p.H, y0 + TTA_RB);
+    if (x >= p.W) continue;
+    int cur0[TTA_ROWS_MAX_MAPS], cur1[TTA_ROWS_MAX_MAPS];
+#pragma unroll
+    for (int m = 0; m < TTA_ROWS_MAX_MAPS; ++m) cur0[m] = cur1[m] = -1;
+    for (int y = y0; y < y1; ++y) {
+      float acc[CT];
+#pragma unroll
+      for (int c = 0; c < CT; ++c) acc[c] = 0.f;
+#pragma unroll
+      for (int m = 0; m < TTA_ROWS_MAX_MAPS; ++m) {
+        if (m < p.n_maps) {
+          const TtaMap& mp = p.maps[m];
+          const Tap ty = ac_tap(mp.scale_h, y, mp.h);
+          float2* mine = pairs + (size_t)m * CT * TTA_THREADS + threadIdx.x;
+          if (ty.i0 != cur0[m] || ty.i1 != cur1[m]) {                   // CTA-uniform: depends on the row only
+            const int xs = mp.flip ? p.W - 1 - x : x;                   // the member saw the mirrored image: un-mirror it
+            const Tap tx = ac_tap(mp.scale_w, xs, mp.w);
+            float u[CT];
+            tta_hrow<CT, EXACT>(mp, C, ty.i1, tx, u);
+            if (ty.i0 == cur1[m]) {                                     // one source row down: the old u is the new t
+#pragma unroll
+              for (int c = 0; c < CT; ++c)
+                if (EXACT || c < C) mine[c * TTA_THREADS] = make_float2(mine[c * TTA_THREADS].y, u[c]);
+            } else {
+              float t[CT];
+              tta_hrow<CT, EXACT>(mp, C, ty.i0, tx, t);
+#pragma unroll
+              for (int c = 0; c < CT; ++c)
+                if (EXACT || c < C) mine[c * TTA_THREADS] = make_float2(t[c], u[c]);
+            }
+            cur0[m] = ty.i0;
+            cur1[m] = ty.i1;
+          }
+          float v[CT];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < CT; ++c) {
+            if (EXACT || c < C) {
+              const float2 tu = mine[c * TTA_THREADS];
+              v[c] = tta_lerp(ty.l0, tu.x, ty.l1, tu.y);
+              mx = fmaxf(mx, v[c]);
+            }
+          }
+          float s = 0.f;
+          bool tiny = false;
+#pragma unroll
+          for (int c = 0; c < CT; ++c) {
+            if (EXACT || c < C) {
+              v[c] = expf(v[c] - mx);
+              s += v[c];
+              tiny |= (v[c] < TTA_TINY) & (v[c] != 0.f);
+            }
+          }
+          if (!tiny) {
+            const float r = __frcp_rn(s);
+#pragma unroll
+            for (int c = 0; c < CT; ++c)
+              if (EXACT || c < C) acc[c] = __fadd_rn(acc[c], tta_div(v[c], s, r));
+          } else {
+#pragma unroll
+            for (int c = 0; c < CT; ++c)
+              if (EXACT || c < C) acc[c] = __fadd_rn(acc[c], __fdiv_rn(v[c], s));
+          }
+        }
+      }
+#pragma unroll 1
+      for (int k = 0; k < p.n_div; ++k) {
+        const float d = p.div[k];
+        if (!p.div_exact) {
+          const float r = __fdiv_rn(1.0f, d);
+#pragma unroll
+          for (int c = 0; c < CT; ++c) acc[c] = __fmul_rn(acc[c], r);
+        } else {
+#pragma unroll
+          for (int c = 0; c < CT; ++c) acc[c] = __fdiv_rn(acc[c], d);
+        }
+      }
+      float best = acc[0];
+      int idx = 0;
+#pragma unroll
+      for (int c = 1; c < CT; ++c) {
+        if ((EXACT || c < C) && acc[c] > best) { best = acc[c]; idx = c; }
+      }
+      const long long pix = (long long)y * p.W + x;
+      if (p.probs) {
+#pragma unroll
+        for (int c = 0; c < CT; ++c)
+          if (EXACT || c < C) __stcs(p.probs + c * plane + pix, acc[c]);
+      }
+      if (p.pred) p.pred[pix] = idx;
+      if (p.cm) {
+        const long long lab = ld_stream_s64(p.labels + pix);
+        if (lab != p.ignore_index && lab >= 0 && lab < C) atomicAdd(&hist[(int)lab * C + idx], 1);
+      }
+    }
+  }
+  if (p.cm) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < CC; i += TTA_THREADS) {
+      const int v = hist[i];
+      if (v) atomicAdd(reinterpret_cast<unsigned long long*>(p.cm + i), (unsigned long long)v);
+    }
+  }
+}
+
+static int g_tta_rows = 1;      // b200seg_tta_set_row_walk(): 0 = always the per-pixel kernel (A/B)
+void tta_set_row_walk(int on) { g_tta_rows = on; }
+
+template <int CT, bool EXACT>
+static int tta_rows_launch(const TtaParams& p, cudaStream_t stream) {
+  const size_t smem = (size_t)p.n_maps * CT * TTA_THREADS * sizeof(float2) + (p.cm ? (size_t)p.C * p.C * 4 : 0);
+  static size_t configured = 0;
+  if (smem > configured) {
+    B200SEG_CUDA(cudaFuncSetAttribute(tta_rows_kernel<CT, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int per_sm = 1;
+  B200SEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tta_rows_kernel<CT, EXACT>, TTA_THREADS, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int units = ceil_div(p.W, TTA_THREADS) * ceil_div(p.H, TTA_RB);
+  const int cap = num_sms() * per_sm;
+  tta_rows_kernel<CT, EXACT><<<units < cap ? units : cap, TTA_THREADS, smem, stream>>>(p);
+  return B200SEG_OK;
+}
+
 // logits[m]: fp32 [C, h[m], w[m]] (device pointers in a HOST array); flip[m] != 0: the member saw the mirrored image
 int tta_launch(const float* const* logits, const int* hs, const int* ws, const int* flips, int n_maps, int C, const long long* labels,
                int H, int W, int ignore_index, const float* divisors, int n_div, int div_exact, long long* cm, long long* pred,
@@ -196,6 +362,19 @@ int tta_launch(const float* const* logits, const int* hs, const int* ws, const i
   const long long cap = (long long)num_sms() * 8;
   const int grid = (int)(units < cap ? units : cap);
   const size_t smem = cm ? (size_t)C * C * 4 : 0;
+  if (g_tta_rows && n_maps <= TTA_ROWS_MAX_MAPS) {
+    profile_begin(15, stream);
+    int rc;
+    if (C == 2) rc = tta_rows_launch<2, true>(p, stream);
+    else if (C == 19) rc = tta_rows_launch<19, true>(p, stream);
+    else if (C <= 8) rc = tta_rows_launch<8, false>(p, stream);
+    else if (C <= 20) rc = tta_rows_launch<20, false>(p, stream);
+    else rc = tta_rows_launch<32, false>(p, stream);
+    profile_end(15, stream);
+    if (rc) return rc;
+    B200SEG_LAUNCH_CHECK();
+    return B200SEG_OK;
+  }
   profile_begin(15, stream);
   if (C == 2) tta_argmax_confusion_kernel<2, true><<<grid, TTA_THREADS, smem, stream>>>(p);
   else if (C == 19) tta_argmax_confusion_kernel<19, true><<<grid, TTA_THREADS, smem, stream>>>(p);

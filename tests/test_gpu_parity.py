@@ -1053,3 +1053,28 @@ def test_k8_unaligned_views_and_two_launch_groups(lib):
         for a, b in zip(ours, refs):
             assert rel_err(a, b) <= OPT_TOL
         assert torch.equal(base.cpu()[~mask], base0[~mask])     # guards untouched
+
+
+@pytest.mark.parametrize("C,shapes,flips,divisors,H,W", [
+    (19, [(64, 128), (64, 128)], [False, True], (2,), 512, 1024),
+    (19, [(33, 65), (17, 40)], [True, False], (2,), 263, 517),            # members of different sizes, ragged strip and row block
+    (2, [(44, 44)], [True], (), 352, 352),
+    (7, [(9, 11), (9, 11)], [False, True], (2,), 5, 300),                 # fewer rows than a row block
+    (30, [(8, 8), (12, 10)], [False, False], (2,), 64, 61),
+    (19, [(8, 8)], [False], (), 8, 8),                                    # no upsampling at all: every row changes the source pair
+])
+def test_k7_row_walking_kernel_equals_per_pixel_kernel(lib, C, shapes, flips, divisors, H, W):
+    """Ensembles of <= 2 members run the row-walking kernel (source-row lerps cached per thread in shared memory); the per-pixel
+    kernel (larger ensembles) must give bit-identical probabilities, labels and counts, and both must equal torch."""
+    members = _tta_members(C, shapes, 1.0, seed=400 + C + H)
+    labels = make_labels(1, H, W, C, 0.1, 23).cuda()
+    outs = []
+    for row_walk in (True, False):
+        lib.tta_set_row_walk(row_walk)
+        try:
+            outs.append(lib.tta_argmax_confusion(members, flips, (H, W), labels=labels, divisors=divisors, want_pred=True, want_probs=True))
+        finally:
+            lib.tta_set_row_walk(True)
+    (cm_a, pred_a, probs_a), (cm_b, pred_b, probs_b) = outs
+    assert torch.equal(probs_a, probs_b) and torch.equal(pred_a, pred_b) and torch.equal(cm_a, cm_b)
+    assert torch.equal(probs_a.unsqueeze(0), to.tta_probabilities(members, flips, (H, W), divisors))
