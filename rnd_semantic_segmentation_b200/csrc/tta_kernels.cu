@@ -57,7 +57,94 @@ __device__ __forceinline__ float tta_div(float v, float s, float r) {
   const float q = __fmul_rn(v, r);
   return fmaf(fmaf(-q, s, v), r, q);
 }
-constexpr float TTA_TINY = 1e-30f;
+constexpr float TTA_SPREAD = 68.0f;      // expf(-68) = 2.9e-30: with a logit spread <= 68 no class is a non-zero value below 1e-30
+
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+  float d;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+template <int LO, int HI, int CT>
+__device__ __forceinline__ float tree_min3(const float (&f)[CT]) {
+  constexpr int n = HI - LO;
+  if constexpr (n == 1) return f[LO];
+  else if constexpr (n == 2) return fminf(f[LO], f[LO + 1]);
+  else if constexpr (n == 3) return fmin3(f[LO], f[LO + 1], f[LO + 2]);
+  else {
+    constexpr int a = (n + 2) / 3, b = (n - a + 1) / 2;
+    return fmin3(tree_min3<LO, LO + a, CT>(f), tree_min3<LO + a, LO + a + b, CT>(f), tree_min3<LO + a + b, HI, CT>(f));
+  }
+}
+
+// acc[c] += softmax(v)[c] with ATen's sequence (max; sequential fp32 sum of expf(v - max) in class order; IEEE division).
+// Maximum and minimum are order-independent, so they are 3-input trees; the minimum only decides whether the shared-reciprocal
+// division is safe (both division paths are correctly rounded, so the conservative test changes no result).
+template <int CT, bool EXACT>
+__device__ __forceinline__ void tta_softmax_add(float (&v)[CT], int C, float (&acc)[CT]) {
+  float mx, mn;
+  if (EXACT) {
+    mx = tree_max3<0, CT, CT>(v);
+    mn = tree_min3<0, CT, CT>(v);
+  } else {
+    mx = v[0];
+    mn = v[0];
+#pragma unroll
+    for (int c = 1; c < CT; ++c)
+      if (c < C) { mx = fmaxf(mx, v[c]); mn = fminf(mn, v[c]); }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < CT; ++c) {
+    if (EXACT || c < C) {
+      v[c] = expf(v[c] - mx);
+      s += v[c];
+    }
+  }
+  // acc starts at +0 and the probabilities are >= +0, so the first member's 0 + p is p itself
+  if (!(mx - mn > TTA_SPREAD)) {
+    const float r = __frcp_rn(s);
+#pragma unroll
+    for (int c = 0; c < CT; ++c)
+      if (EXACT || c < C) acc[c] = __fadd_rn(acc[c], tta_div(v[c], s, r));
+  } else {
+#pragma unroll
+    for (int c = 0; c < CT; ++c)                             // (unrolled as well: a dynamically indexed acc[] would live in local memory)
+      if (EXACT || c < C) acc[c] = __fadd_rn(acc[c], __fdiv_rn(v[c], s));
+  }
+}
+
+// scalar divisions, first-maximum argmax, outputs of one pixel
+template <int CT, bool EXACT>
+__device__ __forceinline__ void tta_finish(const TtaParams& p, float (&acc)[CT], int C, long long pix, long long plane, int* hist) {
+#pragma unroll 1
+  for (int k = 0; k < p.n_div; ++k) {
+    const float d = p.div[k];
+    if (!p.div_exact) {
+      const float r = __fdiv_rn(1.0f, d);
+#pragma unroll
+      for (int c = 0; c < CT; ++c) acc[c] = __fmul_rn(acc[c], r);
+    } else {
+#pragma unroll
+      for (int c = 0; c < CT; ++c) acc[c] = __fdiv_rn(acc[c], d);
+    }
+  }
+  float best = acc[0];
+  int idx = 0;
+#pragma unroll
+  for (int c = 1; c < CT; ++c) {
+    if ((EXACT || c < C) && acc[c] > best) { best = acc[c]; idx = c; }
+  }
+  if (p.probs) {
+#pragma unroll
+    for (int c = 0; c < CT; ++c)
+      if (EXACT || c < C) __stcs(p.probs + c * plane + pix, acc[c]);
+  }
+  if (p.pred) p.pred[pix] = idx;
+  if (p.cm) {
+    const long long lab = ld_stream_s64(p.labels + pix);
+    if (lab != p.ignore_index && lab >= 0 && lab < C) atomicAdd(&hist[(int)lab * C + idx], 1);
+  }
+}
 
 // EXACT: the class count is the compile-time CT (no per-class predicates)
 template <int CT, bool EXACT>
@@ -91,68 +178,18 @@ __global__ void __launch_bounds__(TTA_THREADS) tta_argmax_confusion_kernel(const
       unsigned o10 = (unsigned)(ty.i1 * mp.w + tx.i0), o11 = (unsigned)(ty.i1 * mp.w + tx.i1);
       const float* __restrict__ lg = mp.logits;
       float v[CT];
-      float mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < CT; ++c) {
         if (EXACT || c < C) {
           const float t = tta_lerp(tx.l0, __ldg(lg + o00), tx.l1, __ldg(lg + o01));
           const float u = tta_lerp(tx.l0, __ldg(lg + o10), tx.l1, __ldg(lg + o11));
           v[c] = tta_lerp(ty.l0, t, ty.l1, u);
-          mx = fmaxf(mx, v[c]);
           o00 += hw; o01 += hw; o10 += hw; o11 += hw;
         }
       }
-      float s = 0.f;
-      bool tiny = false;                                     // some class is a non-zero value below TTA_TINY (a logit ~69 below the maximum)
-#pragma unroll
-      for (int c = 0; c < CT; ++c) {
-        if (EXACT || c < C) {
-          v[c] = expf(v[c] - mx);
-          s += v[c];
-          tiny |= (v[c] < TTA_TINY) & (v[c] != 0.f);
-        }
-      }
-      // acc starts at +0 and the probabilities are >= +0, so the first member's 0 + p is p itself
-      if (!tiny) {
-        const float r = __frcp_rn(s);
-#pragma unroll
-        for (int c = 0; c < CT; ++c)
-          if (EXACT || c < C) acc[c] = __fadd_rn(acc[c], tta_div(v[c], s, r));
-      } else {
-#pragma unroll
-        for (int c = 0; c < CT; ++c)                         // (unrolled as well: a dynamically indexed acc[] would live in local memory)
-          if (EXACT || c < C) acc[c] = __fadd_rn(acc[c], __fdiv_rn(v[c], s));
-      }
+      tta_softmax_add<CT, EXACT>(v, C, acc);
     }
-#pragma unroll 1
-    for (int k = 0; k < p.n_div; ++k) {
-      const float d = p.div[k];
-      if (!p.div_exact) {
-        const float r = __fdiv_rn(1.0f, d);
-#pragma unroll
-        for (int c = 0; c < CT; ++c) acc[c] = __fmul_rn(acc[c], r);
-      } else {
-#pragma unroll
-        for (int c = 0; c < CT; ++c) acc[c] = __fdiv_rn(acc[c], d);
-      }
-    }
-    float best = acc[0];
-    int idx = 0;
-#pragma unroll
-    for (int c = 1; c < CT; ++c) {
-      if ((EXACT || c < C) && acc[c] > best) { best = acc[c]; idx = c; }
-    }
-    const long long pix = (long long)y * p.W + x;
-    if (p.probs) {
-#pragma unroll
-      for (int c = 0; c < CT; ++c)
-        if (EXACT || c < C) __stcs(p.probs + c * plane + pix, acc[c]);
-    }
-    if (p.pred) p.pred[pix] = idx;
-    if (p.cm) {
-      const long long lab = ld_stream_s64(p.labels + pix);
-      if (lab != p.ignore_index && lab >= 0 && lab < C) atomicAdd(&tta_hist[(int)lab * C + idx], 1);
-    }
+    tta_finish<CT, EXACT>(p, acc, C, (long long)y * p.W + x, plane, tta_hist);
   }
   if (p.cm) {
     __syncthreads();
@@ -238,66 +275,17 @@ __global__ void __launch_bounds__(TTA_THREADS) tta_rows_kernel(const TtaParams p
             cur1[m] = ty.i1;
           }
           float v[CT];
-          float mx = -INFINITY;
 #pragma unroll
           for (int c = 0; c < CT; ++c) {
             if (EXACT || c < C) {
               const float2 tu = mine[c * TTA_THREADS];
               v[c] = tta_lerp(ty.l0, tu.x, ty.l1, tu.y);
-              mx = fmaxf(mx, v[c]);
             }
           }
-          float s = 0.f;
-          bool tiny = false;
-#pragma unroll
-          for (int c = 0; c < CT; ++c) {
-            if (EXACT || c < C) {
-              v[c] = expf(v[c] - mx);
-              s += v[c];
-              tiny |= (v[c] < TTA_TINY) & (v[c] != 0.f);
-            }
-          }
-          if (!tiny) {
-            const float r = __frcp_rn(s);
-#pragma unroll
-            for (int c = 0; c < CT; ++c)
-              if (EXACT || c < C) acc[c] = __fadd_rn(acc[c], tta_div(v[c], s, r));
-          } else {
-#pragma unroll
-            for (int c = 0; c < CT; ++c)
-              if (EXACT || c < C) acc[c] = __fadd_rn(acc[c], __fdiv_rn(v[c], s));
-          }
+          tta_softmax_add<CT, EXACT>(v, C, acc);
         }
       }
-#pragma unroll 1
-      for (int k = 0; k < p.n_div; ++k) {
-        const float d = p.div[k];
-        if (!p.div_exact) {
-          const float r = __fdiv_rn(1.0f, d);
-#pragma unroll
-          for (int c = 0; c < CT; ++c) acc[c] = __fmul_rn(acc[c], r);
-        } else {
-#pragma unroll
-          for (int c = 0; c < CT; ++c) acc[c] = __fdiv_rn(acc[c], d);
-        }
-      }
-      float best = acc[0];
-      int idx = 0;
-#pragma unroll
-      for (int c = 1; c < CT; ++c) {
-        if ((EXACT || c < C) && acc[c] > best) { best = acc[c]; idx = c; }
-      }
-      const long long pix = (long long)y * p.W + x;
-      if (p.probs) {
-#pragma unroll
-        for (int c = 0; c < CT; ++c)
-          if (EXACT || c < C) __stcs(p.probs + c * plane + pix, acc[c]);
-      }
-      if (p.pred) p.pred[pix] = idx;
-      if (p.cm) {
-        const long long lab = ld_stream_s64(p.labels + pix);
-        if (lab != p.ignore_index && lab >= 0 && lab < C) atomicAdd(&hist[(int)lab * C + idx], 1);
-      }
+      tta_finish<CT, EXACT>(p, acc, C, (long long)y * p.W + x, plane, hist);
     }
   }
   if (p.cm) {
