@@ -30,7 +30,8 @@ for it in range(3):
     if it == 2:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-    _lib.tta_argmax_confusion(members, [False, True], (H, W), labels=labels, divisors=(2,), cm=cm)
+    _lib.tta_argmax_confusion(members, [False, True], (H, W), labels=labels, divisors=(2,), cm=cm)          # row-walking kernel
+    _lib.tta_argmax_confusion(members + members[:1], [False, True, False], (H, W), labels=labels, divisors=(3,), cm=cm)   # per-pixel kernel
     sgd.step()
     adam.step()
     torch.cuda.synchronize()
