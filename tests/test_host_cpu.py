@@ -56,7 +56,27 @@ def test_no_cpu_fallback(built_lib):
         D(torch.randn(1, 16, 8, 8))
     with pytest.raises(B200SegError):
         D.forward_soft_loss(torch.randn(1, 16, 8, 8), torch.randn(1, 3, 8, 8), (16, 16), slot=0)
+    # test-time augmentation (K7) and the fused optimizer steps (K8): same rule
+    label = torch.zeros(1, 16, 16, dtype=torch.int64)
+    out = b200.inference(torch.nn.Identity(), lambda feats, size=None: feats, torch.randn(1, 3, 4, 4), label, flip=True)
+    assert tuple(out.shape) == (1, 3, 16, 16)                   # lazy: nothing has run yet
+    with pytest.raises(B200SegError):
+        out.max(1)
+    with pytest.raises(B200SegError):
+        out.cpu()
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    for opt in (b200.FusedSGD([p], lr=0.1, momentum=0.9), b200.FusedAdam([p], lr=0.1)):
+        with pytest.raises(B200SegError):
+            opt.step()
+    assert float(p.detach().sum()) == 0.0                       # nothing was updated on the way to the error
+    assert b200.adjust_learning_rate('poly', 2.5e-4, 0, 100, 0.9) == 2.5e-4
+    with pytest.raises(NotImplementedError):
+        b200.adjust_learning_rate('cosine', 2.5e-4, 0, 100, 0.9)
     # C-ABI argument errors are reported, not crashed on, without a device
+    assert built_lib.b200seg_tta_argmax_confusion(None, None, None, None, 2, 19, None, 8, 8, 255, None, 0, 0, None, None, None, None) != 0
+    assert built_lib.b200seg_sgd_step(1, None, None, None, None, 0.1, 0.9, 0.0, 0.0, 0, 0, 1.0, None) != 0
+    assert built_lib.b200seg_conv3x3_dgrad_colsum_scratch_bytes(4, 64, 128, 256) == 4 * 64 * 4 * 256 * 4
     assert built_lib.b200seg_conv3x3_wgrad_scratch_bytes(4, 64, 128, 256, 2048, 1) == 9 * 256 * 2048 * 4 + 256
     assert built_lib.b200seg_nhwc_colsum_scratch_bytes(256) > 0
     assert built_lib.b200seg_conv3x3_forward(None, 1, 8, 8, 16, 16, None, 16, 1, None, 0, 0.0, None, 16, None, None) != 0
