@@ -59,6 +59,7 @@ def load_reference():
         soft_label_cross_entropy=utility.soft_label_cross_entropy,
         inference=utility.inference,
         multi_scale_inference=utility.multi_scale_inference,
+        get_color_palette=utility.get_color_palette,
         adjust_learning_rate=_load("_ref_adapt_lr", "core/utils/adapt_lr.py").adjust_learning_rate,
         intersectionAndUnion=utility.intersectionAndUnion,
         confusion_matrix=utility.confusion_matrix,

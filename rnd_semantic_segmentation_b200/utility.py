@@ -19,7 +19,8 @@ from . import _lib, ops
 from .ops import soft_label_cross_entropy  # noqa: F401  (re-exported under the reference's name)
 
 __all__ = ["soft_label_cross_entropy", "inference", "multi_scale_inference", "intersectionAndUnion", "intersectionAndUnionGPU",
-           "confusion_matrix", "AverageMeter", "segmentation_eval_step", "iutr_from_confusion", "LazyProbabilities"]
+           "confusion_matrix", "AverageMeter", "segmentation_eval_step", "iutr_from_confusion", "LazyProbabilities",
+           "pseudo_label_map", "get_color_palette", "save_pseudo_label"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -251,6 +252,29 @@ def multi_scale_inference(feature_extractor, classifier, image, label, flip=True
     if len(members) > 8:
         raise _lib.B200SegError(f"multi_scale_inference: {len(members)} ensemble members, at most 8 are supported")
     return LazyProbabilities(None, label, members=members, flips=flips, divisors=(len(scales), 2) if flip else (len(scales),))
+
+
+def pseudo_label_map(output) -> np.ndarray:
+    """H x W uint8 label map of a (lazy or real) [1,C,H,W] probability tensor: what ``save_distill`` (aspp_tester.py:40-42)
+    derives with ``output.cpu().numpy().squeeze().argmax(0)`` -- but through the fused argmax, so 2 MB of labels cross PCIe
+    instead of the 159 MB probability tensor (first index on ties in both)."""
+    pred = output.max(1)[1] if isinstance(output, LazyProbabilities) else torch.as_tensor(output).max(1)[1]
+    return pred.reshape(pred.shape[-2:]).to(torch.uint8).cpu().numpy()
+
+
+def get_color_palette(pred, palette):
+    """utility.py:211-217: ``pred`` H x W numpy array with label ids -> PIL image in mode 'P' carrying ``palette``."""
+    from PIL import Image
+    label = Image.fromarray(np.asarray(pred).astype('uint8')).convert('P')
+    label.putpalette(palette)
+    return label
+
+
+def save_pseudo_label(output, path: str, palette):
+    """The body of ``ASPPTester.save_distill`` (aspp_tester.py:33-45) after the folder handling: argmax -> palette PNG."""
+    mask = get_color_palette(pseudo_label_map(output), palette)
+    mask.save(path)
+    return mask
 
 
 def _cached_record(pd: torch.Tensor, gt: torch.Tensor):

@@ -1078,3 +1078,27 @@ def test_k7_row_walking_kernel_equals_per_pixel_kernel(lib, C, shapes, flips, di
     (cm_a, pred_a, probs_a), (cm_b, pred_b, probs_b) = outs
     assert torch.equal(probs_a, probs_b) and torch.equal(pred_a, pred_b) and torch.equal(cm_a, cm_b)
     assert torch.equal(probs_a.unsqueeze(0), to.tta_probabilities(members, flips, (H, W), divisors))
+
+
+def test_pseudo_label_map_and_png_writer(lib, tmp_path):
+    """save_distill's argmax (aspp_tester.py:40-42) through the fused kernels: equal to the argmax of the materialised
+    probabilities for a plain frame (K4) and for the flip ensemble (K7); the PNG holds exactly those labels."""
+    import rnd_semantic_segmentation_b200 as b200
+    from PIL import Image
+    g = torch.Generator().manual_seed(31)
+    label = torch.zeros(1, 120, 200, dtype=torch.int64).cuda()
+    both = torch.randn(2, 19, 15, 25, generator=g).cuda()
+    palette = list(range(256)) * 3
+    outs = {
+        "plain": b200.utility.LazyProbabilities(both[:1].contiguous(), label),
+        "flip": b200.utility.LazyProbabilities(None, label, members=[both[0:1].contiguous(), both[1:2].contiguous()], flips=[False, True],
+                                               divisors=(2,)),
+    }
+    for name, out in outs.items():
+        want = out.materialize().cpu().numpy().squeeze().argmax(0)           # the reference's save_distill arithmetic
+        got = b200.pseudo_label_map(out)
+        assert got.dtype == np.uint8 and got.shape == (120, 200)
+        np.testing.assert_array_equal(got, want.astype(np.uint8))
+        path = tmp_path / f"{name}.png"
+        b200.save_pseudo_label(out, str(path), palette)
+        np.testing.assert_array_equal(np.asarray(Image.open(path)), got)

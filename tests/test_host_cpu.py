@@ -192,3 +192,27 @@ def test_distributed_gloo_world2(tmp_path):
     mp.spawn(_dist_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     a, b = torch.load(tmp_path / "cm0.pt"), torch.load(tmp_path / "cm1.pt")
     assert torch.equal(a, b)
+
+
+def test_color_palette_png_round_trip(tmp_path):
+    """get_color_palette (utility.py:211-217): mode-'P' image whose indices are the label ids and whose palette is the given one;
+    equal to the reference's own function when the reference tree is present."""
+    import rnd_semantic_segmentation_b200 as b200
+    from PIL import Image
+    from oracle.ref_loader import load_reference, reference_available
+    rng = np.random.default_rng(0)
+    pred = rng.integers(0, 19, size=(37, 53)).astype(np.int64)
+    palette = [int(v) for v in rng.integers(0, 256, size=19 * 3)] + [0] * (256 * 3 - 19 * 3)
+    img = b200.get_color_palette(pred, palette)
+    assert img.mode == "P" and img.size == (53, 37)
+    np.testing.assert_array_equal(np.asarray(img), pred.astype(np.uint8))
+    assert img.getpalette()[:57] == palette[:57]
+    path = tmp_path / "mask.png"
+    img.save(path)
+    back = Image.open(path)
+    np.testing.assert_array_equal(np.asarray(back), pred.astype(np.uint8))
+    np.testing.assert_array_equal(np.asarray(back.convert("RGB")), np.asarray(palette[:57], dtype=np.uint8).reshape(19, 3)[pred])
+    if reference_available():
+        ref_img = load_reference().get_color_palette(pred, palette)
+        assert ref_img.mode == img.mode and ref_img.getpalette() == img.getpalette()
+        np.testing.assert_array_equal(np.asarray(ref_img), np.asarray(img))
