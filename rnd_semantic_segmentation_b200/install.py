@@ -4,26 +4,64 @@
     b200seg.install()          # before train_src.py / train_adv.py / test.py build their models
 
 After this, ``core.models.build.build_classifier`` / ``build_adversarial_discriminator`` and
-``core.utils.utility.{soft_label_cross_entropy,inference,intersectionAndUnionGPU,confusion_matrix,AverageMeter}``
-resolve to this package's implementations; the scripts themselves stay unmodified.
+``core.utils.utility.{soft_label_cross_entropy,inference,multi_scale_inference,intersectionAndUnionGPU,confusion_matrix,
+AverageMeter,get_color_palette}`` and ``core.utils.adapt_lr.adjust_learning_rate`` resolve to this package's implementations; the
+scripts themselves stay unmodified.  ``install(optimizers=True)`` additionally makes the trainers'
+``torch.optim.SGD`` / ``torch.optim.Adam`` constructions (aspp_trainer.py:25-26, fada_adapter.py:24) build FusedSGD / FusedAdam for
+parameter sets that live on a CUDA device (everything else keeps the stock classes).
 """
 from __future__ import annotations
 
 import importlib
 import sys
 
+import torch
+
 from . import build as _build
+from . import optim as _optim
 from . import utility as _utility
 
 _BUILD_NAMES = ("build_classifier", "build_adversarial_discriminator")
-_UTIL_NAMES = ("soft_label_cross_entropy", "inference", "intersectionAndUnionGPU", "confusion_matrix", "AverageMeter")
+_UTIL_NAMES = ("soft_label_cross_entropy", "inference", "multi_scale_inference", "intersectionAndUnionGPU", "confusion_matrix",
+               "AverageMeter", "get_color_palette")
+_LR_NAMES = ("adjust_learning_rate",)
+_stock_optimizers = {}
 
 
-def install(strict: bool = False):
+def _optimizer_factory(stock, fused):
+    """``torch.optim.SGD(...)``-compatible callable: the fused subclass for all-CUDA fp32 parameter sets, the stock class otherwise
+    (the backbone's optimizer_fea is one of those calls too; it takes the fused path just the same when it is on the GPU)."""
+
+    def make(params, *args, **kwargs):
+        params = list(params)
+        flat = [p for g in params for p in g["params"]] if params and isinstance(params[0], dict) else params
+        if flat and all(isinstance(p, torch.Tensor) and p.is_cuda and p.dtype == torch.float32 for p in flat):
+            return fused(params, *args, **kwargs)
+        return stock(params, *args, **kwargs)
+
+    make.__wrapped__ = stock
+    return make
+
+
+def install_optimizers():
+    """torch.optim.SGD / torch.optim.Adam -> factories that build FusedSGD / FusedAdam for CUDA fp32 parameters."""
+    if not _stock_optimizers:
+        _stock_optimizers.update(SGD=torch.optim.SGD, Adam=torch.optim.Adam)
+        torch.optim.SGD = _optimizer_factory(_stock_optimizers["SGD"], _optim.FusedSGD)
+        torch.optim.Adam = _optimizer_factory(_stock_optimizers["Adam"], _optim.FusedAdam)
+    return ["torch.optim.SGD", "torch.optim.Adam"]
+
+
+def uninstall_optimizers():
+    if _stock_optimizers:
+        torch.optim.SGD, torch.optim.Adam = _stock_optimizers.pop("SGD"), _stock_optimizers.pop("Adam")
+
+
+def install(strict: bool = False, optimizers: bool = False):
     """Returns the list of 'module.attr' names that were patched."""
-    patched = []
+    patched = install_optimizers() if optimizers else []
     targets = (("core.models.build", _build, _BUILD_NAMES), ("core.models", _build, _BUILD_NAMES),
-               ("core.utils.utility", _utility, _UTIL_NAMES))
+               ("core.utils.utility", _utility, _UTIL_NAMES), ("core.utils.adapt_lr", _optim, _LR_NAMES))
     for modname, src, names in targets:
         mod = sys.modules.get(modname)
         if mod is None:
@@ -39,9 +77,9 @@ def install(strict: bool = False):
     # modules that did `from core.utils.utility import X` / `from core.models import build_*` before install()
     for mod in list(sys.modules.values()):
         name = getattr(mod, "__name__", "")
-        if not name.startswith("core.") or name in ("core.models.build", "core.models", "core.utils.utility"):
+        if not name.startswith("core.") or name in ("core.models.build", "core.models", "core.utils.utility", "core.utils.adapt_lr"):
             continue
-        for src, names in ((_build, _BUILD_NAMES), (_utility, _UTIL_NAMES)):
+        for src, names in ((_build, _BUILD_NAMES), (_utility, _UTIL_NAMES), (_optim, _LR_NAMES)):
             for n in names:
                 if n in getattr(mod, "__dict__", {}):
                     setattr(mod, n, getattr(src, n))

@@ -145,6 +145,18 @@ def test_install_patches_reference_modules(monkeypatch):
     assert bld.build_classifier is b200.build_classifier and models.build_classifier is b200.build_classifier
     assert util.confusion_matrix is b200.confusion_matrix and tester.confusion_matrix is b200.confusion_matrix
     assert "core.utils.utility.soft_label_cross_entropy" in patched
+    assert util.multi_scale_inference is b200.multi_scale_inference and util.get_color_palette is b200.get_color_palette
+    # optional: the trainers' torch.optim.SGD / Adam constructions build the fused subclasses for CUDA parameters only
+    inst = sys.modules["rnd_semantic_segmentation_b200.install"]      # (the package attribute `install` is the function)
+    stock_sgd, stock_adam = torch.optim.SGD, torch.optim.Adam
+    try:
+        assert "torch.optim.SGD" in b200.install(optimizers=True)
+        cpu_opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(2))], lr=0.1, momentum=0.9)
+        assert type(cpu_opt) is stock_sgd                       # CPU parameters keep the stock optimizer
+        assert type(torch.optim.Adam([{"params": [torch.nn.Parameter(torch.zeros(2))]}], lr=0.1)) is stock_adam
+    finally:
+        inst.uninstall_optimizers()
+    assert torch.optim.SGD is stock_sgd and torch.optim.Adam is stock_adam
 
 
 def test_synth_shapes_and_determinism():
