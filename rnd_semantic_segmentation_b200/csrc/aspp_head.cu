@@ -57,29 +57,57 @@ struct MutPtrList {
 // ------------------------------------------------------------------------------------------
 // pack weights: R x [C, Cin, 3, 3] fp32 -> Wp [NJ, Cin] bf16, WpT [Cin, NJ] bf16, bias_sum [C]
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pack_weights_kernel(PtrList w, PtrList b, int R, int C, int Cin, int NJ,
-                                                           __nv_bfloat16* __restrict__ Wp, __nv_bfloat16* __restrict__ WpT,
-                                                           float* __restrict__ bias_sum) {
-  const long long idx = blockIdx.x * 256LL + threadIdx.x;
-  if (idx < C) {
-    float s = b.p[0] ? b.p[0][idx] : 0.f;
-    for (int r = 1; r < R; ++r) s += b.p[r] ? b.p[r][idx] : 0.f;        // ((b0+b1)+b2)+b3, the reference's order
-    bias_sum[idx] = s;
-  }
-  if (idx >= (long long)NJ * Cin) return;
-  const int j = (int)(idx / Cin), ci = (int)(idx - (long long)j * Cin);
+// A block owns 8 input channels x all classes x all branches: it reads, per (branch, class), the 72 contiguous floats
+// w[r][c][ci0 .. ci0+8)[3][3] into shared memory (coalesced), then writes 8 full rows of WpT (contiguous along j) and one 16-byte
+// segment of every Wp row -- no strided 2-byte scatter (the per-element version took ~30 us of every training step; the weights
+// change every step).  Element values and the centre-tap summation order ((w0+w1)+w2)+w3 are those of the per-element version.
+constexpr int PW_CI = 8;
+__device__ __forceinline__ float packed_weight(const float* __restrict__ w_s, int R, int C, int j, int ci_l) {
   const int t = j / C, c = j - t * C;
-  float v = 0.f;
   if (t < 8 * R) {
     const int r = t >> 3, q = t & 7;
     const int k = q < 4 ? q : q + 1;                                       // skip the centre (k == 4)
-    v = w.p[r][((long long)c * Cin + ci) * 9 + k];
-  } else if (t == 8 * R) {
-    for (int r = 0; r < R; ++r) v += w.p[r][((long long)c * Cin + ci) * 9 + 4];
+    return w_s[((r * C + c) * PW_CI + ci_l) * 9 + k];
   }
-  const __nv_bfloat16 h = __float2bfloat16(v);
-  Wp[idx] = h;
-  WpT[(long long)ci * NJ + j] = h;
+  float v = 0.f;
+  if (t == 8 * R)
+    for (int r = 0; r < R; ++r) v += w_s[((r * C + c) * PW_CI + ci_l) * 9 + 4];
+  return v;                                                                // rows beyond (8R+1)*C are zero padding
+}
+__global__ void __launch_bounds__(256) pack_weights_kernel(PtrList w, PtrList b, int R, int C, int Cin, int NJ,
+                                                           __nv_bfloat16* __restrict__ Wp, __nv_bfloat16* __restrict__ WpT,
+                                                           float* __restrict__ bias_sum) {
+  extern __shared__ float pw_s[];                                          // [R][C][PW_CI][9]
+  const int ci0 = blockIdx.x * PW_CI;
+  if (blockIdx.x == 0 && threadIdx.x < C) {
+    const int idx = threadIdx.x;
+    float s = b.p[0] ? b.p[0][idx] : 0.f;
+    for (int r = 1; r < R; ++r) s += b.p[r] ? b.p[r][idx] : 0.f;          // ((b0+b1)+b2)+b3, the reference's order
+    bias_sum[idx] = s;
+  }
+  constexpr int SEG = PW_CI * 9;
+  for (int i = threadIdx.x; i < R * C * SEG; i += 256) {
+    const int rc = i / SEG, off = i - rc * SEG;
+    const int r = rc / C, c = rc - r * C;
+    pw_s[i] = __ldg(w.p[r] + ((long long)c * Cin + ci0) * 9 + off);
+  }
+  __syncthreads();
+  // WpT[ci][j]: pairs of j (NJ is a multiple of 128), contiguous along j
+  for (int i = threadIdx.x; i < PW_CI * (NJ / 2); i += 256) {
+    const int ci_l = i / (NJ / 2), j = 2 * (i - ci_l * (NJ / 2));
+    const __nv_bfloat162 v = __floats2bfloat162_rn(packed_weight(pw_s, R, C, j, ci_l), packed_weight(pw_s, R, C, j + 1, ci_l));
+    *reinterpret_cast<__nv_bfloat162*>(WpT + (long long)(ci0 + ci_l) * NJ + j) = v;
+  }
+  // Wp[j][ci0 .. ci0+8): one 16-byte store per row
+  for (int j = threadIdx.x; j < NJ; j += 256) {
+    uint32_t w4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat162 v = __floats2bfloat162_rn(packed_weight(pw_s, R, C, j, 2 * e), packed_weight(pw_s, R, C, j, 2 * e + 1));
+      w4[e] = *reinterpret_cast<const uint32_t*>(&v);
+    }
+    *reinterpret_cast<uint4*>(Wp + (long long)j * Cin + ci0) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -348,9 +376,13 @@ int aspp_pack_weights(const float* const* w, const float* const* b, int R, int C
   PtrList pw, pb;
   for (int r = 0; r < MAX_RATES; ++r) { pw.p[r] = r < R ? w[r] : nullptr; pb.p[r] = (r < R && b) ? b[r] : nullptr; }
   const int NJ = aspp_nj(C, R);
-  const long long total = (long long)NJ * Cin;
-  pack_weights_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(pw, pb, R, C, Cin, NJ, (__nv_bfloat16*)Wp,
-                                                                               (__nv_bfloat16*)WpT, bias_sum);
+  B200SEG_CHECK_ARG(C <= 256 && (reinterpret_cast<uintptr_t>(Wp) & 15) == 0 && (reinterpret_cast<uintptr_t>(WpT) & 3) == 0,
+                    "aspp_pack_weights: at most 256 classes, Wp 16-byte aligned");
+  const size_t smem = (size_t)R * C * PW_CI * 9 * sizeof(float);
+  B200SEG_CHECK_ARG(smem <= 200 * 1024, "aspp_pack_weights: %d branches x %d classes do not fit the staging buffer", R, C);
+  if (smem > 48 * 1024)
+    B200SEG_CUDA(cudaFuncSetAttribute(pack_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pack_weights_kernel<<<Cin / PW_CI, 256, smem, stream>>>(pw, pb, R, C, Cin, NJ, (__nv_bfloat16*)Wp, (__nv_bfloat16*)WpT, bias_sum);
   B200SEG_LAUNCH_CHECK();
   return B200SEG_OK;
 }

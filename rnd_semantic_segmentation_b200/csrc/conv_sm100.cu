@@ -614,24 +614,34 @@ int conv3x3_wgrad_run(const void* g, int Co, long long g_pitch, const void* x, i
 // ------------------------------------------------------------------------------------------
 // helper kernels
 // ------------------------------------------------------------------------------------------
-// w fp32 [Co_part][Ci][3][3] -> Wf bf16 [9][Co_total][Ci] (rows co0 + co) and Wb bf16 [9][Ci][co_pitch] (columns co0 + co)
+// w fp32 [Co_part][Ci][3][3] -> Wf bf16 [9][Co_total][Ci] (rows co0 + co) and Wb bf16 [9][Ci][co_pitch] (columns co0 + co).
+// A block owns 16 output x 64 input channels: 16 contiguous runs of 576 floats in (coalesced), then Wf as 128-byte runs along ci
+// and Wb as 32-byte runs along co -- both full sectors (the earlier version scattered Wb as single 2-byte elements, ~70 us per
+// discriminator re-pack, which training pays every step).
+constexpr int CPW_CO = 16, CPW_CI = 64, CPW_PITCH = CPW_CI * 9 + 1;      // odd pitch: the co-fastest reads are conflict-free
 __global__ void __launch_bounds__(256) conv_pack_weights_kernel(const float* __restrict__ wsrc, int Co_part, int Ci, int co0, int Co_total,
                                                                 int co_pitch, __nv_bfloat16* __restrict__ Wf,
                                                                 __nv_bfloat16* __restrict__ Wb) {
-  // a block owns (co, 256 ci): reads 256*9 contiguous floats, writes 9 coalesced ci-runs of Wf and 9 strided columns of Wb
-  __shared__ float sm[256 * 9];
-  const int ci0 = blockIdx.x * 256, co = blockIdx.y;
-  const int nci = min(256, Ci - ci0);
-  const float* src = wsrc + ((long long)co * Ci + ci0) * 9;
-  for (int i = threadIdx.x; i < nci * 9; i += 256) sm[i] = __ldg(src + i);
+  __shared__ float sm[CPW_CO * CPW_PITCH];
+  const int ci0 = blockIdx.x * CPW_CI, cop0 = blockIdx.y * CPW_CO;
+  const int nci = min(CPW_CI, Ci - ci0), nco = min(CPW_CO, Co_part - cop0);
+  for (int i = threadIdx.x; i < nco * nci * 9; i += 256) {
+    const int co_l = i / (nci * 9), off = i - co_l * (nci * 9);
+    sm[co_l * CPW_PITCH + off] = __ldg(wsrc + ((long long)(cop0 + co_l) * Ci + ci0) * 9 + off);
+  }
   __syncthreads();
-  const int ci = ci0 + threadIdx.x;
-  if (threadIdx.x < nci) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      const __nv_bfloat16 v = __float2bfloat16(sm[threadIdx.x * 9 + k]);
-      if (Wf) Wf[((long long)k * Co_total + co0 + co) * Ci + ci] = v;
-      if (Wb) Wb[((long long)k * Ci + ci) * co_pitch + co0 + co] = v;
+  if (Wf) {
+    for (int i = threadIdx.x; i < 9 * nco * CPW_CI; i += 256) {            // ci fastest
+      const int ci_l = i % CPW_CI, kc = i / CPW_CI, co_l = kc % nco, k = kc / nco;
+      if (ci_l < nci)
+        Wf[((long long)k * Co_total + co0 + cop0 + co_l) * Ci + ci0 + ci_l] = __float2bfloat16(sm[co_l * CPW_PITCH + ci_l * 9 + k]);
+    }
+  }
+  if (Wb) {
+    for (int i = threadIdx.x; i < 9 * nci * CPW_CO; i += 256) {            // co fastest
+      const int co_l = i % CPW_CO, kc = i / CPW_CO, ci_l = kc % nci, k = kc / nci;
+      if (co_l < nco)
+        Wb[((long long)k * Ci + ci0 + ci_l) * co_pitch + co0 + cop0 + co_l] = __float2bfloat16(sm[co_l * CPW_PITCH + ci_l * 9 + k]);
     }
   }
 }
@@ -742,7 +752,7 @@ int conv3x3_pack_weights(const float* const* weights, const int* part_co, int n_
   B200SEG_CHECK_ARG(!Wb || co_pitch >= Co_total, "conv3x3_pack_weights: co_pitch %d < total output channels %d", co_pitch, Co_total);
   int co0 = 0;
   for (int i = 0; i < n_parts; ++i) {
-    dim3 grid(ceil_div(Ci, 256), part_co[i]);
+    dim3 grid(ceil_div(Ci, CPW_CI), ceil_div(part_co[i], CPW_CO));
     conv_pack_weights_kernel<<<grid, 256, 0, stream>>>(weights[i], part_co[i], Ci, co0, Co_total, co_pitch, (__nv_bfloat16*)Wf,
                                                        (__nv_bfloat16*)Wb);
     B200SEG_LAUNCH_CHECK();

@@ -1102,3 +1102,42 @@ def test_pseudo_label_map_and_png_writer(lib, tmp_path):
         path = tmp_path / f"{name}.png"
         b200.save_pseudo_label(out, str(path), palette)
         np.testing.assert_array_equal(np.asarray(Image.open(path)), got)
+
+
+@pytest.mark.parametrize("C,Cin,R", [(19, 2048, 4), (2, 64, 4), (30, 128, 3), (7, 24, 1)])
+def test_head_weight_pack_layouts_exact(lib, C, Cin, R):
+    """Wp [NJ,Cin] / WpT [Cin,NJ] / bias_sum of the tiled pack kernel against the layout definition built with torch: rows
+    (r*8+q)*C + c = the 8 off-centre taps of branch r, rows 8R*C + c = the fp32 sum of the R centre taps, rounded once to bf16;
+    padding rows zero."""
+    g = torch.Generator().manual_seed(C + Cin)
+    ws = [(torch.randn(C, Cin, 3, 3, generator=g) * 0.05).cuda() for _ in range(R)]
+    bs = [torch.randn(C, generator=g).cuda() for _ in range(R)]
+    Wp, WpT, bias_sum = lib.aspp_pack_weights(ws, bs)
+    NJ = Wp.shape[0]
+    want = torch.zeros(NJ, Cin, device="cuda")
+    for r in range(R):
+        flat = ws[r].reshape(C, Cin, 9)
+        for q in range(8):
+            k = q if q < 4 else q + 1
+            want[(r * 8 + q) * C:(r * 8 + q + 1) * C] = flat[:, :, k]
+    centre = ws[0].reshape(C, Cin, 9)[:, :, 4].clone()
+    for r in range(1, R):
+        centre = centre + ws[r].reshape(C, Cin, 9)[:, :, 4]
+    want[8 * R * C:(8 * R + 1) * C] = centre
+    want = want.to(torch.bfloat16)
+    assert torch.equal(Wp, want) and torch.equal(WpT, want.t().contiguous())
+    bsum = bs[0].clone()
+    for r in range(1, R):
+        bsum = bsum + bs[r]
+    assert torch.equal(bias_sum, bsum)
+
+
+@pytest.mark.parametrize("parts,Ci", [([256], 2048), ([19, 19], 128), ([40], 64), ([16], 24), ([5, 3], 72)])
+def test_conv_weight_pack_layouts_exact(lib, parts, Ci):
+    g = torch.Generator().manual_seed(sum(parts) + Ci)
+    ws = [(torch.randn(co, Ci, 3, 3, generator=g) * 0.05).cuda() for co in parts]
+    Wf, Wb = lib.conv3x3_pack_weights(ws)
+    allw = torch.cat(ws, 0).reshape(sum(parts), Ci, 9).to(torch.bfloat16)          # [Co, Ci, 9]
+    assert torch.equal(Wf, allw.permute(2, 0, 1).contiguous())
+    Co = sum(parts)
+    assert torch.equal(Wb[:, :, :Co], allw.permute(2, 1, 0).contiguous()) and float(Wb[:, :, Co:].abs().sum()) == 0.0
