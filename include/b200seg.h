@@ -181,6 +181,14 @@ B200SEG_API int b200seg_aspp_backward_packed_ex(const void* gOt, const void* Xp,
  *   Wb bf16 [9][Ci][co_pitch]  data-gradient operand, caller zero-fills the padding columns co_pitch > Co   (may be NULL) */
 B200SEG_API int b200seg_conv3x3_pack_weights(const float* const* weights, const int* part_co_host, int n_parts, int Ci, void* Wf,
                                              void* Wb, int co_pitch, void* stream);
+/* the same for a whole stack of layers in ONE launch (training re-packs every step): layer l owns parts_per_layer[l] consecutive
+ * entries of weights / part_co (all HOST arrays; weights holds device pointers), writes Wf[l] / Wb[l] (either may be NULL) with
+ * row pitch co_pitch[l]; the padding columns of every Wb are zero-filled by the kernel.  bias_parts (n_bias <= 4 device pointers,
+ * NULL = zeros, lengths bias_len) are concatenated into bias_out -- the cls1 | cls2 bias of discriminator.py:39-40,47 */
+B200SEG_API int b200seg_conv3x3_pack_weights_stack(int n_layers, const float* const* weights, const int* part_co_host,
+                                                   const int* parts_per_layer_host, const int* Ci_host, void* const* Wf, void* const* Wb,
+                                                   const int* co_pitch_host, const float* const* bias_parts, const int* bias_len_host,
+                                                   int n_bias, float* bias_out, void* stream);
 /* out = [LeakyReLU_slope](conv3x3(act; Wf) + bias): exactly one of out_bf16_nhwc ([N,h,w,out_pitch]) / out_f32_nchw ([N,Co,h,w]);
  * bias may be NULL; lrelu != 0 applies the activation */
 B200SEG_API int b200seg_conv3x3_forward(const void* act_nhwc_bf16, int N, int h, int w, int Ci, int64_t act_pitch, const void* Wf, int Co,

@@ -60,6 +60,7 @@ SIGNATURES = {
     "b200seg_aspp_backward_packed_ex": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64,
                                                 c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b200seg_conv3x3_pack_weights": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
+    "b200seg_conv3x3_pack_weights_stack": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     "b200seg_conv3x3_forward": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_i64, c_vp, c_int, c_int, c_vp, c_int, c_f32, c_vp, c_i64,
                                         c_vp, c_vp]),
     "b200seg_conv3x3_dgrad": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_i64, c_vp, c_int, c_int, c_vp, c_f32, c_vp, c_i64, c_vp,
@@ -664,11 +665,48 @@ def conv3x3_pack_weights(weights: Sequence[torch.Tensor]):
     Co = sum(parts)
     dev = weights[0].device
     Wf = torch.empty((9, Co, Ci), dtype=torch.bfloat16, device=dev)
-    Wb = torch.zeros((9, Ci, _round8(Co)), dtype=torch.bfloat16, device=dev)
+    Wb = torch.empty((9, Ci, _round8(Co)), dtype=torch.bfloat16, device=dev)       # padding columns are zero-filled by the kernel
     with _on_device(dev):
         _check(lib.b200seg_conv3x3_pack_weights(_ptr_array(weights), (c_int * len(parts))(*parts), len(parts), Ci, Wf.data_ptr(),
                                                 Wb.data_ptr(), Wb.shape[2], _stream()))
     return Wf, Wb
+
+
+def conv3x3_pack_weights_stack(layers: Sequence[Sequence[torch.Tensor]], bias_parts: Sequence[Optional[torch.Tensor]] = (),
+                               bias_lens: Sequence[int] = ()):
+    """Every layer of a conv stack in ONE launch: ``layers[l]`` = the [Co_i,Ci_l,3,3] fp32 tensors concatenated along Co for layer
+    l.  Returns ([(Wf_l, Wb_l)], bias) with bias = the concatenation of ``bias_parts`` (None = zeros of ``bias_lens[i]``)."""
+    lib = load()
+    flat, parts, ppl, cis, Wfs, Wbs, pitches = [], [], [], [], [], [], []
+    dev = layers[0][0].device
+    for ws in layers:
+        Ci = int(ws[0].shape[1])
+        for wt in ws:
+            _need(wt, torch.float32, "conv weight")
+            if wt.dim() != 4 or tuple(wt.shape[1:]) != (Ci, 3, 3) or wt.device != dev:
+                raise B200SegError(f"conv weight shape {tuple(wt.shape)}: expected [Co,{Ci},3,3] on {dev}")
+        if Ci % 8 != 0:
+            raise B200SegError(f"conv3x3: in_channels={Ci} must be a multiple of 8")
+        Co = sum(int(wt.shape[0]) for wt in ws)
+        flat += list(ws)
+        parts += [int(wt.shape[0]) for wt in ws]
+        ppl.append(len(ws))
+        cis.append(Ci)
+        Wfs.append(torch.empty((9, Co, Ci), dtype=torch.bfloat16, device=dev))
+        Wbs.append(torch.empty((9, Ci, _round8(Co)), dtype=torch.bfloat16, device=dev))
+        pitches.append(_round8(Co))
+    bias = None
+    if bias_lens:
+        for b_, n_ in zip(bias_parts, bias_lens):
+            if b_ is not None and (_need(b_, torch.float32, "bias").numel() != n_):
+                raise B200SegError("conv3x3_pack_weights_stack: bias length mismatch")
+        bias = torch.empty(int(sum(bias_lens)), dtype=torch.float32, device=dev)
+    ia = lambda v: (c_int * len(v))(*[int(x) for x in v])  # noqa: E731
+    with _on_device(dev):
+        _check(lib.b200seg_conv3x3_pack_weights_stack(len(layers), _ptr_array(flat), ia(parts), ia(ppl), ia(cis), _ptr_array(Wfs),
+                                                      _ptr_array(Wbs), ia(pitches), _ptr_array(list(bias_parts)) if bias_lens else None,
+                                                      ia(bias_lens) if bias_lens else None, len(bias_lens), _ptr(bias), _stream()))
+    return list(zip(Wfs, Wbs)), bias
 
 
 def _need_nhwc(t: torch.Tensor, name: str):

@@ -75,6 +75,8 @@ long long k5_workspace_bytes(int, int, int, int, int, int);
 int k5_forward(const float*, const float*, int, int, int, int, int, int, float, float, int, int, void*, long long, float*, cudaStream_t);
 int k5_backward(const void*, int, int, int, int, int, int, const float*, const float*, float*, cudaStream_t);
 int conv3x3_pack_weights(const float* const*, const int*, int, int, void*, void*, int, cudaStream_t);
+int conv3x3_pack_weights_stack(int, const float* const*, const int*, const int*, const int*, void* const*, void* const*, const int*,
+                               const float* const*, const int*, int, float*, cudaStream_t);
 int conv3x3_forward(const void*, int, int, int, int, long long, const void*, int, int, const float*, int, float, void*, long long, float*,
                     cudaStream_t);
 int conv3x3_dgrad(const void*, int, int, int, int, long long, const void*, int, int, const void*, float, void*, long long, float*,
@@ -295,6 +297,15 @@ int b200seg_conv3x3_pack_weights(const float* const* weights, const int* part_co
                                  int co_pitch, void* stream) {
   REQUIRE_DEVICE();
   return conv3x3_pack_weights(weights, part_co_host, n_parts, Ci, Wf, Wb, co_pitch, S(stream));
+}
+
+int b200seg_conv3x3_pack_weights_stack(int n_layers, const float* const* weights, const int* part_co_host, const int* parts_per_layer_host,
+                                       const int* Ci_host, void* const* Wf, void* const* Wb, const int* co_pitch_host,
+                                       const float* const* bias_parts, const int* bias_len_host, int n_bias, float* bias_out,
+                                       void* stream) {
+  REQUIRE_DEVICE();
+  return conv3x3_pack_weights_stack(n_layers, weights, part_co_host, parts_per_layer_host, Ci_host, Wf, Wb, co_pitch_host, bias_parts,
+                                    bias_len_host, n_bias, bias_out, S(stream));
 }
 
 int b200seg_conv3x3_forward(const void* act, int N, int h, int w, int Ci, int64_t act_pitch, const void* Wf, int Co, int dilation,

@@ -17,6 +17,7 @@
 //     wgrad  dWp[j, ci] = sum_p G'[p, j] * Xp[p, ci]             M=640  N=Cin   K=P     (MN-major x MN-major, split-K)
 // All three GEMMs run on the tcgen05 core in gemm_sm100.cuh with 98 % useful MMA work at C=19.
 // Operands are bf16 (features, packed weights, output gradient), accumulation is fp32 in TMEM.
+#include <limits.h>
 #include "common.cuh"
 #include "gemm_sm100.cuh"
 
@@ -62,22 +63,22 @@ struct MutPtrList {
 // segment of every Wp row -- no strided 2-byte scatter (the per-element version took ~30 us of every training step; the weights
 // change every step).  Element values and the centre-tap summation order ((w0+w1)+w2)+w3 are those of the per-element version.
 constexpr int PW_CI = 8;
-__device__ __forceinline__ float packed_weight(const float* __restrict__ w_s, int R, int C, int j, int ci_l) {
-  const int t = j / C, c = j - t * C;
-  if (t < 8 * R) {
-    const int r = t >> 3, q = t & 7;
-    const int k = q < 4 ? q : q + 1;                                       // skip the centre (k == 4)
-    return w_s[((r * C + c) * PW_CI + ci_l) * 9 + k];
-  }
+// tab[j] >= 0: offset of w_s[r][c][0][k] for an off-centre row; -1 - c: centre row of class c (sum over branches); INT_MIN: padding
+__device__ __forceinline__ float packed_weight(const float* __restrict__ w_s, const int* __restrict__ tab, int R, int C, int j, int ci_l) {
+  const int e = tab[j];
+  if (e >= 0) return w_s[e + ci_l * 9];
   float v = 0.f;
-  if (t == 8 * R)
+  if (e != INT_MIN) {
+    const int c = -1 - e;
     for (int r = 0; r < R; ++r) v += w_s[((r * C + c) * PW_CI + ci_l) * 9 + 4];
-  return v;                                                                // rows beyond (8R+1)*C are zero padding
+  }
+  return v;
 }
 __global__ void __launch_bounds__(256) pack_weights_kernel(PtrList w, PtrList b, int R, int C, int Cin, int NJ,
                                                            __nv_bfloat16* __restrict__ Wp, __nv_bfloat16* __restrict__ WpT,
                                                            float* __restrict__ bias_sum) {
-  extern __shared__ float pw_s[];                                          // [R][C][PW_CI][9]
+  extern __shared__ float pw_s[];                                          // [R][C][PW_CI][9] floats, then the row table [NJ]
+  int* tab = reinterpret_cast<int*>(pw_s + R * C * PW_CI * 9);
   const int ci0 = blockIdx.x * PW_CI;
   if (blockIdx.x == 0 && threadIdx.x < C) {
     const int idx = threadIdx.x;
@@ -85,25 +86,39 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(PtrList w, PtrList b,
     for (int r = 1; r < R; ++r) s += b.p[r] ? b.p[r][idx] : 0.f;          // ((b0+b1)+b2)+b3, the reference's order
     bias_sum[idx] = s;
   }
+  for (int j = threadIdx.x; j < NJ; j += 256) {                            // the only integer divisions of the kernel
+    const int t = j / C, c = j - t * C;
+    int e = INT_MIN;
+    if (t < 8 * R) {
+      const int r = t >> 3, q = t & 7;
+      e = ((r * C + c) * PW_CI) * 9 + (q < 4 ? q : q + 1);                 // skip the centre (k == 4)
+    } else if (t == 8 * R) {
+      e = -1 - c;
+    }
+    tab[j] = e;
+  }
   constexpr int SEG = PW_CI * 9;
-  for (int i = threadIdx.x; i < R * C * SEG; i += 256) {
-    const int rc = i / SEG, off = i - rc * SEG;
-    const int r = rc / C, c = rc - r * C;
-    pw_s[i] = __ldg(w.p[r] + ((long long)c * Cin + ci0) * 9 + off);
+  for (int rc = 0; rc < R * C; ++rc) {
+    const int r = rc / C, c = rc - r * C;                                  // block-uniform
+    const float* src = w.p[r] + ((long long)c * Cin + ci0) * 9;
+    if (threadIdx.x < SEG) pw_s[rc * SEG + threadIdx.x] = __ldg(src + threadIdx.x);
   }
   __syncthreads();
   // WpT[ci][j]: pairs of j (NJ is a multiple of 128), contiguous along j
-  for (int i = threadIdx.x; i < PW_CI * (NJ / 2); i += 256) {
-    const int ci_l = i / (NJ / 2), j = 2 * (i - ci_l * (NJ / 2));
-    const __nv_bfloat162 v = __floats2bfloat162_rn(packed_weight(pw_s, R, C, j, ci_l), packed_weight(pw_s, R, C, j + 1, ci_l));
-    *reinterpret_cast<__nv_bfloat162*>(WpT + (long long)(ci0 + ci_l) * NJ + j) = v;
+  const int half = NJ >> 1;
+  for (int ci_l = 0; ci_l < PW_CI; ++ci_l) {
+    for (int jp = threadIdx.x; jp < half; jp += 256) {
+      const int j = 2 * jp;
+      const __nv_bfloat162 v = __floats2bfloat162_rn(packed_weight(pw_s, tab, R, C, j, ci_l), packed_weight(pw_s, tab, R, C, j + 1, ci_l));
+      *reinterpret_cast<__nv_bfloat162*>(WpT + (long long)(ci0 + ci_l) * NJ + j) = v;
+    }
   }
   // Wp[j][ci0 .. ci0+8): one 16-byte store per row
   for (int j = threadIdx.x; j < NJ; j += 256) {
     uint32_t w4[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const __nv_bfloat162 v = __floats2bfloat162_rn(packed_weight(pw_s, R, C, j, 2 * e), packed_weight(pw_s, R, C, j, 2 * e + 1));
+      const __nv_bfloat162 v = __floats2bfloat162_rn(packed_weight(pw_s, tab, R, C, j, 2 * e), packed_weight(pw_s, tab, R, C, j, 2 * e + 1));
       w4[e] = *reinterpret_cast<const uint32_t*>(&v);
     }
     *reinterpret_cast<uint4*>(Wp + (long long)j * Cin + ci0) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
@@ -378,7 +393,7 @@ int aspp_pack_weights(const float* const* w, const float* const* b, int R, int C
   const int NJ = aspp_nj(C, R);
   B200SEG_CHECK_ARG(C <= 256 && (reinterpret_cast<uintptr_t>(Wp) & 15) == 0 && (reinterpret_cast<uintptr_t>(WpT) & 3) == 0,
                     "aspp_pack_weights: at most 256 classes, Wp 16-byte aligned");
-  const size_t smem = (size_t)R * C * PW_CI * 9 * sizeof(float);
+  const size_t smem = (size_t)R * C * PW_CI * 9 * sizeof(float) + (size_t)NJ * sizeof(int);
   B200SEG_CHECK_ARG(smem <= 200 * 1024, "aspp_pack_weights: %d branches x %d classes do not fit the staging buffer", R, C);
   if (smem > 48 * 1024)
     B200SEG_CUDA(cudaFuncSetAttribute(pack_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -615,33 +615,71 @@ int conv3x3_wgrad_run(const void* g, int Co, long long g_pitch, const void* x, i
 // helper kernels
 // ------------------------------------------------------------------------------------------
 // w fp32 [Co_part][Ci][3][3] -> Wf bf16 [9][Co_total][Ci] (rows co0 + co) and Wb bf16 [9][Ci][co_pitch] (columns co0 + co).
-// A block owns 16 output x 64 input channels: 16 contiguous runs of 576 floats in (coalesced), then Wf as 128-byte runs along ci
-// and Wb as 32-byte runs along co -- both full sectors (the earlier version scattered Wb as single 2-byte elements, ~70 us per
-// discriminator re-pack, which training pays every step).
+// ONE launch packs every weight tensor of a layer -- or of the whole discriminator stack -- from a job table in the kernel
+// parameters (training re-packs every step: four launches + three memsets + a concatenation cost ~70 us of device time, mostly
+// dependency latency between tiny nodes).  A block owns 16 output x 64 input channels of one job: 16 contiguous runs of 576 floats
+// in (coalesced), then Wf as 128-byte runs along ci and Wb as 32-byte runs along co -- full sectors, shift/mask indexing only.
+// The block of the first output tile of a layer's last part also zero-fills the padding columns [Co_total, co_pitch) of Wb, and
+// block 0 concatenates the bias vectors of the last layer's parts.
 constexpr int CPW_CO = 16, CPW_CI = 64, CPW_PITCH = CPW_CI * 9 + 1;      // odd pitch: the co-fastest reads are conflict-free
-__global__ void __launch_bounds__(256) conv_pack_weights_kernel(const float* __restrict__ wsrc, int Co_part, int Ci, int co0, int Co_total,
-                                                                int co_pitch, __nv_bfloat16* __restrict__ Wf,
-                                                                __nv_bfloat16* __restrict__ Wb) {
+constexpr int CPW_MAX_JOBS = 8, CPW_MAX_BIAS = 4;
+struct PackJob {
+  const float* w;
+  __nv_bfloat16* Wf;
+  __nv_bfloat16* Wb;
+  int Co_part, Ci, co0, Co_total, co_pitch, tiles_ci, tile0, zero_pad;
+};
+struct PackTable {
+  PackJob job[CPW_MAX_JOBS];
+  int n, total_tiles;
+  const float* bias_src[CPW_MAX_BIAS];
+  int bias_len[CPW_MAX_BIAS];
+  int n_bias;
+  float* bias_dst;
+};
+__global__ void __launch_bounds__(256) conv_pack_weights_kernel(const PackTable t) {
   __shared__ float sm[CPW_CO * CPW_PITCH];
-  const int ci0 = blockIdx.x * CPW_CI, cop0 = blockIdx.y * CPW_CO;
-  const int nci = min(CPW_CI, Ci - ci0), nco = min(CPW_CO, Co_part - cop0);
-  for (int i = threadIdx.x; i < nco * nci * 9; i += 256) {
-    const int co_l = i / (nci * 9), off = i - co_l * (nci * 9);
-    sm[co_l * CPW_PITCH + off] = __ldg(wsrc + ((long long)(cop0 + co_l) * Ci + ci0) * 9 + off);
-  }
-  __syncthreads();
-  if (Wf) {
-    for (int i = threadIdx.x; i < 9 * nco * CPW_CI; i += 256) {            // ci fastest
-      const int ci_l = i % CPW_CI, kc = i / CPW_CI, co_l = kc % nco, k = kc / nco;
-      if (ci_l < nci)
-        Wf[((long long)k * Co_total + co0 + cop0 + co_l) * Ci + ci0 + ci_l] = __float2bfloat16(sm[co_l * CPW_PITCH + ci_l * 9 + k]);
+  if (blockIdx.x == 0 && t.bias_dst) {
+    int off = 0;
+#pragma unroll
+    for (int i = 0; i < CPW_MAX_BIAS; ++i) {
+      if (i < t.n_bias) {
+        for (int e = threadIdx.x; e < t.bias_len[i]; e += 256) t.bias_dst[off + e] = t.bias_src[i] ? __ldg(t.bias_src[i] + e) : 0.f;
+        off += t.bias_len[i];
+      }
     }
   }
-  if (Wb) {
-    for (int i = threadIdx.x; i < 9 * nci * CPW_CO; i += 256) {            // co fastest
-      const int co_l = i % CPW_CO, kc = i / CPW_CO, ci_l = kc % nci, k = kc / nci;
-      if (co_l < nco)
-        Wb[((long long)k * Ci + ci0 + ci_l) * co_pitch + co0 + cop0 + co_l] = __float2bfloat16(sm[co_l * CPW_PITCH + ci_l * 9 + k]);
+  PackJob j = t.job[0];
+#pragma unroll
+  for (int k = 1; k < CPW_MAX_JOBS; ++k)
+    if (k < t.n && (int)blockIdx.x >= t.job[k].tile0) j = t.job[k];
+  const int local = (int)blockIdx.x - j.tile0;
+  const int ci0 = (local % j.tiles_ci) * CPW_CI, cop0 = (local / j.tiles_ci) * CPW_CO;
+  const int nci = min(CPW_CI, j.Ci - ci0), nco = min(CPW_CO, j.Co_part - cop0);
+  for (int co_l = 0; co_l < nco; ++co_l) {
+    const float* src = j.w + ((long long)(cop0 + co_l) * j.Ci + ci0) * 9;
+    for (int off = threadIdx.x; off < nci * 9; off += 256) sm[co_l * CPW_PITCH + off] = __ldg(src + off);
+  }
+  __syncthreads();
+  if (j.Wf) {
+    for (int i = threadIdx.x; i < 9 * CPW_CO * CPW_CI; i += 256) {         // ci fastest
+      const int ci_l = i & (CPW_CI - 1), co_l = (i >> 6) & (CPW_CO - 1), k = i >> 10;
+      if (ci_l < nci && co_l < nco)
+        j.Wf[((long long)k * j.Co_total + j.co0 + cop0 + co_l) * j.Ci + ci0 + ci_l] = __float2bfloat16(sm[co_l * CPW_PITCH + ci_l * 9 + k]);
+    }
+  }
+  if (j.Wb) {
+    for (int i = threadIdx.x; i < 9 * CPW_CI * CPW_CO; i += 256) {         // co fastest
+      const int co_l = i & (CPW_CO - 1), ci_l = (i >> 4) & (CPW_CI - 1), k = i >> 10;
+      if (ci_l < nci && co_l < nco)
+        j.Wb[((long long)k * j.Ci + ci0 + ci_l) * j.co_pitch + j.co0 + cop0 + co_l] = __float2bfloat16(sm[co_l * CPW_PITCH + ci_l * 9 + k]);
+    }
+    const int npad = j.co_pitch - j.Co_total;
+    if (j.zero_pad && cop0 == 0 && npad > 0) {
+      for (int i = threadIdx.x; i < 9 * nci * npad; i += 256) {
+        const int c = i % npad, kc = i / npad, ci_l = kc % nci, k = kc / nci;
+        j.Wb[((long long)k * j.Ci + ci0 + ci_l) * j.co_pitch + j.Co_total + c] = __float2bfloat16(0.f);
+      }
     }
   }
 }
@@ -744,21 +782,65 @@ __global__ void __launch_bounds__(256) conv_wgrad_reduce_flat_kernel(const float
 // ------------------------------------------------------------------------------------------
 // host entry points (wrapped 1:1 by api.cu)
 // ------------------------------------------------------------------------------------------
-int conv3x3_pack_weights(const float* const* weights, const int* part_co, int n_parts, int Ci, void* Wf, void* Wb, int co_pitch,
-                         cudaStream_t stream) {
-  B200SEG_CHECK_ARG(weights && part_co && n_parts >= 1 && (Wf || Wb), "conv3x3_pack_weights: bad arguments");
+static int pack_add_layer(PackTable& t, const float* const* weights, const int* part_co, int n_parts, int Ci, void* Wf, void* Wb,
+                          int co_pitch) {
+  B200SEG_CHECK_ARG(weights && part_co && n_parts >= 1 && (Wf || Wb) && Ci > 0, "conv3x3_pack_weights: bad arguments");
+  B200SEG_CHECK_ARG(t.n + n_parts <= CPW_MAX_JOBS, "conv3x3_pack_weights: more than %d weight tensors in one call", CPW_MAX_JOBS);
   int Co_total = 0;
-  for (int i = 0; i < n_parts; ++i) Co_total += part_co[i];
+  for (int i = 0; i < n_parts; ++i) {
+    B200SEG_CHECK_ARG(weights[i] && part_co[i] > 0, "conv3x3_pack_weights: part %d is null or empty", i);
+    Co_total += part_co[i];
+  }
   B200SEG_CHECK_ARG(!Wb || co_pitch >= Co_total, "conv3x3_pack_weights: co_pitch %d < total output channels %d", co_pitch, Co_total);
   int co0 = 0;
   for (int i = 0; i < n_parts; ++i) {
-    dim3 grid(ceil_div(Ci, CPW_CI), ceil_div(part_co[i], CPW_CO));
-    conv_pack_weights_kernel<<<grid, 256, 0, stream>>>(weights[i], part_co[i], Ci, co0, Co_total, co_pitch, (__nv_bfloat16*)Wf,
-                                                       (__nv_bfloat16*)Wb);
-    B200SEG_LAUNCH_CHECK();
+    PackJob& j = t.job[t.n++];
+    j.w = weights[i]; j.Wf = (__nv_bfloat16*)Wf; j.Wb = (__nv_bfloat16*)Wb;
+    j.Co_part = part_co[i]; j.Ci = Ci; j.co0 = co0; j.Co_total = Co_total; j.co_pitch = co_pitch;
+    j.tiles_ci = ceil_div(Ci, CPW_CI);
+    j.tile0 = t.total_tiles;
+    j.zero_pad = (i == n_parts - 1) ? 1 : 0;
+    t.total_tiles += j.tiles_ci * ceil_div(part_co[i], CPW_CO);
     co0 += part_co[i];
   }
   return B200SEG_OK;
+}
+
+static int pack_launch(const PackTable& t, cudaStream_t stream) {
+  conv_pack_weights_kernel<<<t.total_tiles, 256, 0, stream>>>(t);
+  B200SEG_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+// one layer; the padding columns [sum part_co, co_pitch) of Wb are zero-filled by the kernel
+int conv3x3_pack_weights(const float* const* weights, const int* part_co, int n_parts, int Ci, void* Wf, void* Wb, int co_pitch,
+                         cudaStream_t stream) {
+  PackTable t = {};
+  int rc = pack_add_layer(t, weights, part_co, n_parts, Ci, Wf, Wb, co_pitch);
+  if (rc) return rc;
+  return pack_launch(t, stream);
+}
+
+// a whole stack of layers in one launch: layer l owns parts [first, first + parts_per_layer[l]) of the flattened weights / part_co
+// arrays; bias_parts (optional, n_bias <= 4 device pointers, NULL = zeros) are concatenated into bias_out
+int conv3x3_pack_weights_stack(int n_layers, const float* const* weights, const int* part_co, const int* parts_per_layer,
+                               const int* Ci, void* const* Wf, void* const* Wb, const int* co_pitch, const float* const* bias_parts,
+                               const int* bias_len, int n_bias, float* bias_out, cudaStream_t stream) {
+  B200SEG_CHECK_ARG(n_layers >= 1 && weights && part_co && parts_per_layer && Ci && Wf && Wb && co_pitch,
+                    "conv3x3_pack_weights_stack: bad arguments");
+  B200SEG_CHECK_ARG(n_bias >= 0 && n_bias <= CPW_MAX_BIAS && (n_bias == 0 || (bias_parts && bias_len && bias_out)),
+                    "conv3x3_pack_weights_stack: 0..%d bias parts with an output buffer", CPW_MAX_BIAS);
+  PackTable t = {};
+  int first = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    int rc = pack_add_layer(t, weights + first, part_co + first, parts_per_layer[l], Ci[l], Wf[l], Wb[l], co_pitch[l]);
+    if (rc) return rc;
+    first += parts_per_layer[l];
+  }
+  t.n_bias = n_bias;
+  t.bias_dst = n_bias ? bias_out : nullptr;
+  for (int i = 0; i < n_bias; ++i) { t.bias_src[i] = bias_parts[i]; t.bias_len[i] = bias_len[i]; }
+  return pack_launch(t, stream);
 }
 
 int nchw_to_nhwc_bf16(const float* src, int N, int C, int hw, void* dst, int pitch, cudaStream_t stream) {

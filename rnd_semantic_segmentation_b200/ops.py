@@ -173,12 +173,10 @@ def aspp_head_loss(x, labels, weights, biases, rates, ignore_index=255, temperat
 def pack_discriminator_weights(w1, w2, wc1, wc2, bc1, bc2):
     """((Wf1, Wb1), (Wf2, Wb2), (Wf3, Wb3), bias3) -- cls1 | cls2 are packed as ONE layer with 2C output channels (the
     torch.cat of discriminator.py:47 costs nothing)."""
-    l1 = _lib.conv3x3_pack_weights([w1.detach()])
-    l2 = _lib.conv3x3_pack_weights([w2.detach()])
-    l3 = _lib.conv3x3_pack_weights([wc1.detach(), wc2.detach()])
     C = wc1.shape[0]
-    zero = wc1.new_zeros(C)
-    b3 = torch.cat((zero if bc1 is None else bc1.detach(), zero if bc2 is None else bc2.detach())).contiguous()
+    (l1, l2, l3), b3 = _lib.conv3x3_pack_weights_stack(
+        [[w1.detach()], [w2.detach()], [wc1.detach(), wc2.detach()]],
+        bias_parts=[None if bc1 is None else bc1.detach(), None if bc2 is None else bc2.detach()], bias_lens=[C, C])     # ONE launch
     return l1, l2, l3, b3
 
 
