@@ -98,10 +98,10 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(PtrList w, PtrList b,
     tab[j] = e;
   }
   constexpr int SEG = PW_CI * 9;
-  for (int rc = 0; rc < R * C; ++rc) {
-    const int r = rc / C, c = rc - r * C;                                  // block-uniform
-    const float* src = w.p[r] + ((long long)c * Cin + ci0) * 9;
-    if (threadIdx.x < SEG) pw_s[rc * SEG + threadIdx.x] = __ldg(src + threadIdx.x);
+  for (int i = threadIdx.x; i < R * C * SEG; i += 256) {                   // independent loads: ~21 in flight per thread
+    const int rc = i / SEG, off = i - rc * SEG;
+    const int r = rc / C, c = rc - r * C;
+    pw_s[i] = __ldg(w.p[r] + ((long long)c * Cin + ci0) * 9 + off);
   }
   __syncthreads();
   // WpT[ci][j]: pairs of j (NJ is a multiple of 128), contiguous along j
