@@ -89,9 +89,21 @@ class _PlanMixin:
         self._plans = {}
         return super().load_state_dict(state_dict)
 
-    def _plan(self, gi, params):
+    def __getstate__(self):
+        state = super().__getstate__()
+        state["grad_scale"] = getattr(self, "grad_scale", 1.0)
+        return state
+
+    def __setstate__(self, state):                      # unpickled / deep-copied optimizers carry no plans (and no raw pointers)
+        super().__setstate__(state)
+        self._plans = {}
+        if not hasattr(self, "grad_scale"):
+            self.grad_scale = 1.0
+
+    def _plan(self, gi, params, has_state=True):
         plan = self._plans.get(gi)
-        if plan is not None and len(plan["ids"]) == len(params) and all(a == id(b) for a, b in zip(plan["ids"], params)):
+        if (plan is not None and plan.get("has_state", True) == has_state and len(plan["ids"]) == len(params)
+                and all(a == id(b) for a, b in zip(plan["ids"], params))):
             return plan
         return None
 
@@ -125,7 +137,7 @@ class FusedSGD(_PlanMixin, torch.optim.SGD):
                 continue
             momentum = float(group["momentum"])
             hyper = (float(group["lr"]), momentum, float(group["dampening"]), float(group["weight_decay"]), 1 if group["nesterov"] else 0)
-            plan = self._plan(gi, params)
+            plan = self._plan(gi, params, has_state=momentum != 0)
             if plan is not None:
                 _launch(lib.b200seg_sgd_step, params[0].device, len(params), _ptrs(params), _ptrs(grads), plan["bufs"], plan["numels"],
                         *hyper, 0, self.grad_scale)
@@ -151,7 +163,7 @@ class FusedSGD(_PlanMixin, torch.optim.SGD):
                         *hyper, 1 if first else 0, self.grad_scale)
                 _touched(ps, bufs)
             bufs = [state[p]["momentum_buffer"] for p in params] if momentum != 0 else None
-            self._plans[gi] = dict(ids=[id(p) for p in params], keep=bufs, bufs=_ptrs(bufs) if bufs else None,
+            self._plans[gi] = dict(ids=[id(p) for p in params], has_state=momentum != 0, keep=bufs, bufs=_ptrs(bufs) if bufs else None,
                                    numels=(_lib.c_i64 * len(params))(*[p.numel() for p in params]))
         return loss
 

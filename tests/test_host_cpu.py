@@ -228,3 +228,25 @@ def test_color_palette_png_round_trip(tmp_path):
         ref_img = load_reference().get_color_palette(pred, palette)
         assert ref_img.mode == img.mode and ref_img.getpalette() == img.getpalette()
         np.testing.assert_array_equal(np.asarray(ref_img), np.asarray(img))
+
+
+def test_fused_optimizers_pickle_and_state_dict_contract():
+    """FusedSGD / FusedAdam are torch.optim.SGD / Adam for everything but step(): identical state_dict layout (the reference's
+    checkpoints hold optimizer_cls / optimizer_D state dicts, aspp_trainer.py:46-55), picklable / deep-copyable with the gradient
+    scale kept and no launch plan (raw pointers) carried over."""
+    import copy
+    import pickle
+    import rnd_semantic_segmentation_b200 as b200
+    ps = [torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.zeros(2, 2))]
+    pairs = ((b200.FusedSGD(ps, lr=0.1, momentum=0.9, weight_decay=5e-4, grad_scale=0.125), torch.optim.SGD(ps, lr=0.1, momentum=0.9, weight_decay=5e-4)),
+             (b200.FusedAdam(ps, lr=1e-4, betas=(0.9, 0.99)), torch.optim.Adam(ps, lr=1e-4, betas=(0.9, 0.99))))
+    for ours, stock in pairs:
+        assert isinstance(ours, type(stock))
+        a, b = ours.state_dict(), stock.state_dict()
+        assert a["param_groups"] == b["param_groups"] and a["state"] == b["state"]
+        stock.load_state_dict(a)
+        ours.load_state_dict(b)
+        ours._plans[0] = {"ids": []}
+        for clone in (copy.deepcopy(ours), pickle.loads(pickle.dumps(ours))):
+            assert type(clone) is type(ours) and clone._plans == {} and clone.grad_scale == ours.grad_scale
+            assert clone.state_dict()["param_groups"] == a["param_groups"]
