@@ -177,3 +177,23 @@ def allreduce_confusion_(cm: torch.Tensor, group=None) -> torch.Tensor:
     if is_distributed():
         dist.all_reduce(cm, op=dist.ReduceOp.SUM, group=group)
     return cm
+
+
+def allgather_frame_areas(local: torch.Tensor, n_frames: int, group=None) -> torch.Tensor:
+    """Per-frame (intersection, union, target, output) areas of ALL frames in frame order, for the macro metrics of
+    ``AverageMeter`` (utility.py:24-72: mean over frames of per-frame IoU / F1), when frames are sharded ``rank::world``
+    (``shard_indices``).  ``local``: integer tensor [n_local, 4, C], row k = this rank's k-th frame (frame ``rank + k * world``).
+    Returns [n_frames, 4, C] on every rank; integer areas, so the result is exact and order-independent."""
+    if not is_distributed():
+        return local[:n_frames]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    per_rank = (n_frames + world - 1) // world                      # the largest shard; shorter shards are zero-padded
+    padded = torch.zeros((per_rank,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    out = torch.empty((n_frames,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    for r, part in enumerate(parts):
+        idx = shard_indices(n_frames, r, world)
+        out[idx] = part[:len(idx)]
+    return out

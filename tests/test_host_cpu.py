@@ -194,6 +194,12 @@ def _dist_worker(rank, world, port, tmp):
     for f in range(7):
         want[f % 3, (f * 2) % 3] += 10 ** 12 + f
     assert torch.equal(cm, want)
+    # macro metrics: per-frame areas gathered in frame order (7 frames over 2 ranks: shards of 4 and 3)
+    local = torch.stack([torch.full((4, 3), f, dtype=torch.int64) + torch.arange(4).view(4, 1) for f in frames])
+    areas = D.allgather_frame_areas(local, 7)
+    assert tuple(areas.shape) == (7, 4, 3)
+    for f in range(7):
+        assert torch.equal(areas[f], torch.full((4, 3), f, dtype=torch.int64) + torch.arange(4).view(4, 1))
     torch.save(cm, os.path.join(tmp, f"cm{rank}.pt"))
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
