@@ -236,7 +236,7 @@ B200SEG_API int b200seg_tta_argmax_confusion(const float* const* logits_lr, cons
                                              int C, const int64_t* labels, int H, int W, int ignore_index, const float* divisors,
                                              int n_div, int div_exact, int64_t* cm, int64_t* pred, float* probs, void* stream);
 
-/* ensembles of one or two members: 1 (default) = the row-walking kernel (horizontal lerps of the two current source rows kept per
+/* ensembles of up to four members: 1 (default) = the row-walking kernel (horizontal lerps of the two current source rows kept per
  * thread in shared memory and re-used for every output row between them), 0 = the per-pixel kernel used for larger ensembles
  * (A/B experiments; the results are bit-identical) */
 B200SEG_API void b200seg_tta_set_row_walk(int on);

@@ -200,15 +200,17 @@ __global__ void __launch_bounds__(TTA_THREADS) tta_argmax_confusion_kernel(const
   }
 }
 
-// ---- row-walking variant for ensembles of one or two members (inference(flip=True), the reference's default) ----------------
+// ---- row-walking variant for ensembles of up to four members (inference(flip=True) has two) --------------------------------
 // The horizontal lerps of a source row do not depend on the output row: a thread (= one output column) keeps, per member and
 // class, the pair {t, u} = horizontal lerps on the two source rows of the current output row in SHARED memory, laid out
 // [member][class][thread] (8-byte accesses, conflict-free, private to the thread: no barriers), and refreshes it only when the
 // source-row pair changes (every (H-1)/(h-1) ~ 8 rows; moving down by one source row re-uses u as the new t).  Per pixel and member
 // that leaves one LDS.64 + the vertical lerp per class instead of four global loads and three lerps -- identical arithmetic,
-// ~2x fewer instructions.  A unit is TTA_RB consecutive rows of one 128-column strip.
+// ~2x fewer instructions.  A unit is TTA_RB consecutive rows of one 128-column strip.  The cache costs 19.5 KB of shared memory per
+// member and CTA, i.e. occupancy: measured at 1024 x 2048 against the per-pixel kernel 60 / 103 / 163 / 250 us vs 80 / 141 / 204 /
+// 266 us for 1 / 2 / 3 / 4 members, so larger ensembles stay on the per-pixel kernel.
 constexpr int TTA_RB = 8;
-constexpr int TTA_ROWS_MAX_MAPS = 2;
+constexpr int TTA_ROWS_MAX_MAPS = 4;
 
 template <int CT, bool EXACT>
 __device__ __forceinline__ void tta_hrow(const TtaMap& mp, int C, int row, const Tap& tx, float (&out)[CT]) {

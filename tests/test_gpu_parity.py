@@ -1062,9 +1062,11 @@ def test_k8_unaligned_views_and_two_launch_groups(lib):
     (7, [(9, 11), (9, 11)], [False, True], (2,), 5, 300),                 # fewer rows than a row block
     (30, [(8, 8), (12, 10)], [False, False], (2,), 64, 61),
     (19, [(8, 8)], [False], (), 8, 8),                                    # no upsampling at all: every row changes the source pair
+    (19, [(23, 45), (33, 65), (43, 84)], [False, True, False], (3,), 260, 517),       # three and four members (multi-scale)
+    (5, [(9, 9), (12, 14), (12, 14), (20, 17)], [False, False, True, True], (2, 2), 77, 130),
 ])
 def test_k7_row_walking_kernel_equals_per_pixel_kernel(lib, C, shapes, flips, divisors, H, W):
-    """Ensembles of <= 2 members run the row-walking kernel (source-row lerps cached per thread in shared memory); the per-pixel
+    """Ensembles of <= 4 members run the row-walking kernel (source-row lerps cached per thread in shared memory); the per-pixel
     kernel (larger ensembles) must give bit-identical probabilities, labels and counts, and both must equal torch."""
     members = _tta_members(C, shapes, 1.0, seed=400 + C + H)
     labels = make_labels(1, H, W, C, 0.1, 23).cuda()
