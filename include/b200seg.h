@@ -238,7 +238,9 @@ B200SEG_API int b200seg_tta_argmax_confusion(const float* const* logits_lr, cons
 
 /* ensembles of up to four members: 1 (default) = the row-walking kernel (horizontal lerps of the two current source rows kept per
  * thread in shared memory and re-used for every output row between them), 0 = the per-pixel kernel used for larger ensembles
- * (A/B experiments; the results are bit-identical) */
+ * (A/B experiments; the results are bit-identical).  Bit 1 set (on = 3): row walking without the labels-only fast path (when no
+ * probabilities are requested the kernel orders the classes with ex2.approx-based probabilities and re-runs ATen's exact
+ * sequence only for pixels whose best two sums are within 2e-5 per member; labels and matrix stay bit-exact) */
 B200SEG_API void b200seg_tta_set_row_walk(int on);
 
 /* ---------------------------------------------------------------------------------------------

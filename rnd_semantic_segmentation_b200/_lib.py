@@ -268,9 +268,10 @@ def tta_argmax_confusion(members: Sequence[torch.Tensor], flips: Sequence[bool],
     return cm, pred, probs
 
 
-def tta_set_row_walk(on):
-    """K7 A/B: row-walking kernel for <= 2 members (default) vs the per-pixel kernel."""
-    load().b200seg_tta_set_row_walk(1 if on else 0)
+def tta_set_row_walk(on, fast: bool = True):
+    """K7 A/B: row-walking kernel for <= 4 members (default) vs the per-pixel kernel; ``fast=False`` disables the labels-only
+    fast path of the row-walking kernel (approximate ordering + exact fallback on near ties)."""
+    load().b200seg_tta_set_row_walk((1 if on else 0) | (0 if fast else 2))
 
 
 def _optim_tables(params, grads, *states):

@@ -146,6 +146,122 @@ __device__ __forceinline__ void tta_finish(const TtaParams& p, float (&acc)[CT],
   }
 }
 
+// ---- labels-only fast path -----------------------------------------------------------------------------------------------
+// When only the labels / the confusion matrix are wanted, the probabilities need not be ATen's bit for bit -- only their ORDER.
+// acc[c] += e_c / s with e_c = ex2.approx((v_c - max) * log2 e) (one FFMA + one MUFU per class instead of expf's ~8 instructions)
+// and one reciprocal; every class whose sum lies within TTA_FAST_EPS * members of the largest is a candidate, and a pixel with more
+// than one candidate is recomputed by the exact sequence (tta_exact_pixel).  Error budget: |fast - exact| <= ~3.5e-6 per member and
+// class (ex2.approx 2^-22, the rounded exponent, the fp32 sum, one reciprocal; the common factor exp2(-max * log2 e) cancels in
+// e / s), so two classes whose fast sums differ by more than 7e-6 * members are ordered alike by the exact sequence; the scalar
+// divisions are monotone and cannot reorder them either.  Exactness of the labels against torch is what the tests check.
+constexpr float TTA_FAST_EPS = 2e-5f;
+__device__ __forceinline__ float tta_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <int CT, bool EXACT>
+__device__ __forceinline__ void tta_softmax_add_fast(const float (&v)[CT], int C, float (&acc)[CT]) {
+  float mx;
+  if (EXACT) {
+    mx = tree_max3<0, CT, CT>(v);
+  } else {
+    mx = v[0];
+#pragma unroll
+    for (int c = 1; c < CT; ++c)
+      if (c < C) mx = fmaxf(mx, v[c]);
+  }
+  const float k = 1.4426950408889634f, off = -mx * k;
+  float e[CT];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < CT; ++c) {
+    if (EXACT || c < C) {
+      e[c] = tta_ex2(fmaf(v[c], k, off));                   // one FFMA + one MUFU.EX2
+      s += e[c];
+    }
+  }
+  const float r = __frcp_rn(s);
+#pragma unroll
+  for (int c = 0; c < CT; ++c)
+    if (EXACT || c < C) acc[c] = fmaf(e[c], r, acc[c]);
+}
+
+// the exact sequence for ONE pixel, straight from the members' logits (the per-pixel kernel's body; rare path of the fast kernel)
+template <int CT, bool EXACT>
+__device__ __noinline__ int tta_exact_pixel(const TtaParams& p, int C, int x, int y) {
+  float acc[CT];
+#pragma unroll
+  for (int c = 0; c < CT; ++c) acc[c] = 0.f;
+#pragma unroll 1
+  for (int m = 0; m < p.n_maps; ++m) {
+    const TtaMap& mp = p.maps[m];
+    const int xs = mp.flip ? p.W - 1 - x : x;
+    const Tap ty = ac_tap(mp.scale_h, y, mp.h);
+    const Tap tx = ac_tap(mp.scale_w, xs, mp.w);
+    const unsigned hw = (unsigned)(mp.h * mp.w);
+    unsigned o00 = (unsigned)(ty.i0 * mp.w + tx.i0), o01 = (unsigned)(ty.i0 * mp.w + tx.i1);
+    unsigned o10 = (unsigned)(ty.i1 * mp.w + tx.i0), o11 = (unsigned)(ty.i1 * mp.w + tx.i1);
+    const float* __restrict__ lg = mp.logits;
+    float v[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+      if (EXACT || c < C) {
+        const float t = tta_lerp(tx.l0, __ldg(lg + o00), tx.l1, __ldg(lg + o01));
+        const float u = tta_lerp(tx.l0, __ldg(lg + o10), tx.l1, __ldg(lg + o11));
+        v[c] = tta_lerp(ty.l0, t, ty.l1, u);
+        o00 += hw; o01 += hw; o10 += hw; o11 += hw;
+      }
+    }
+    tta_softmax_add<CT, EXACT>(v, C, acc);
+  }
+#pragma unroll 1
+  for (int k = 0; k < p.n_div; ++k) {
+    const float d = p.div[k];
+    if (!p.div_exact) {
+      const float r = __fdiv_rn(1.0f, d);
+#pragma unroll
+      for (int c = 0; c < CT; ++c) acc[c] = __fmul_rn(acc[c], r);
+    } else {
+#pragma unroll
+      for (int c = 0; c < CT; ++c) acc[c] = __fdiv_rn(acc[c], d);
+    }
+  }
+  float best = acc[0];
+  int idx = 0;
+#pragma unroll
+  for (int c = 1; c < CT; ++c)
+    if ((EXACT || c < C) && acc[c] > best) { best = acc[c]; idx = c; }
+  return idx;
+}
+
+// labels-only epilogue: unique candidate -> it is the argmax; otherwise the exact sequence decides
+template <int CT, bool EXACT>
+__device__ __forceinline__ void tta_finish_fast(const TtaParams& p, const float (&acc)[CT], int C, int x, int y, int* hist) {
+  float best;
+  if (EXACT) {
+    best = tree_max3<0, CT, CT>(acc);
+  } else {
+    best = acc[0];
+#pragma unroll
+    for (int c = 1; c < CT; ++c)
+      if (c < C) best = fmaxf(best, acc[c]);
+  }
+  const float thr = best - TTA_FAST_EPS * (float)p.n_maps;
+  int cand = 0;
+#pragma unroll
+  for (int c = 0; c < CT; ++c)
+    if ((EXACT || c < C) && acc[c] >= thr) cand += 256 + c;       // exactly one candidate: cand - 256 is its index
+  int idx = cand - 256;
+  if (cand >= 512 || !(best == best)) idx = tta_exact_pixel<CT, EXACT>(p, C, x, y);       // near tie (or NaN): exact sequence
+  const long long pix = (long long)y * p.W + x;
+  if (p.pred) p.pred[pix] = idx;
+  if (p.cm) {
+    const long long lab = ld_stream_s64(p.labels + pix);
+    if (lab != p.ignore_index && lab >= 0 && lab < C) atomicAdd(&hist[(int)lab * C + idx], 1);
+  }
+}
+
 // EXACT: the class count is the compile-time CT (no per-class predicates)
 template <int CT, bool EXACT>
 __global__ void __launch_bounds__(TTA_THREADS) tta_argmax_confusion_kernel(const TtaParams p) {
@@ -226,8 +342,8 @@ __device__ __forceinline__ void tta_hrow(const TtaMap& mp, int C, int row, const
   }
 }
 
-template <int CT, bool EXACT>
-__global__ void __launch_bounds__(TTA_THREADS) tta_rows_kernel(const TtaParams p) {
+template <int CT, bool EXACT, bool FAST>
+__global__ void __launch_bounds__(TTA_THREADS, (FAST && EXACT) ? 5 : 1) tta_rows_kernel(const TtaParams p) {
   extern __shared__ __align__(16) unsigned char tta_smem_raw[];
   // [n_maps][CT][TTA_THREADS] float2 pairs, then the int32 histogram
   float2* pairs = reinterpret_cast<float2*>(tta_smem_raw);
@@ -284,10 +400,12 @@ __global__ void __launch_bounds__(TTA_THREADS) tta_rows_kernel(const TtaParams p
               v[c] = tta_lerp(ty.l0, tu.x, ty.l1, tu.y);
             }
           }
-          tta_softmax_add<CT, EXACT>(v, C, acc);
+          if (FAST) tta_softmax_add_fast<CT, EXACT>(v, C, acc);
+          else tta_softmax_add<CT, EXACT>(v, C, acc);
         }
       }
-      tta_finish<CT, EXACT>(p, acc, C, (long long)y * p.W + x, plane, hist);
+      if (FAST) tta_finish_fast<CT, EXACT>(p, acc, C, x, y, hist);
+      else tta_finish<CT, EXACT>(p, acc, C, (long long)y * p.W + x, plane, hist);
     }
   }
   if (p.cm) {
@@ -300,23 +418,30 @@ __global__ void __launch_bounds__(TTA_THREADS) tta_rows_kernel(const TtaParams p
 }
 
 static int g_tta_rows = 1;      // b200seg_tta_set_row_walk(): 0 = always the per-pixel kernel (A/B)
-void tta_set_row_walk(int on) { g_tta_rows = on; }
+static int g_tta_fast = 1;      // bit 1 of the same knob: 0 = never the labels-only fast path (A/B)
+void tta_set_row_walk(int on) { g_tta_rows = on & 1; g_tta_fast = (on & 2) ? 0 : 1; }
 
-template <int CT, bool EXACT>
-static int tta_rows_launch(const TtaParams& p, cudaStream_t stream) {
+template <int CT, bool EXACT, bool FAST>
+static int tta_rows_launch_t(const TtaParams& p, cudaStream_t stream) {
   const size_t smem = (size_t)p.n_maps * CT * TTA_THREADS * sizeof(float2) + (p.cm ? (size_t)p.C * p.C * 4 : 0);
   static size_t configured = 0;
   if (smem > configured) {
-    B200SEG_CUDA(cudaFuncSetAttribute(tta_rows_kernel<CT, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200SEG_CUDA(cudaFuncSetAttribute(tta_rows_kernel<CT, EXACT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   int per_sm = 1;
-  B200SEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tta_rows_kernel<CT, EXACT>, TTA_THREADS, smem));
+  B200SEG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tta_rows_kernel<CT, EXACT, FAST>, TTA_THREADS, smem));
   if (per_sm < 1) per_sm = 1;
   const int units = ceil_div(p.W, TTA_THREADS) * ceil_div(p.H, TTA_RB);
   const int cap = num_sms() * per_sm;
-  tta_rows_kernel<CT, EXACT><<<units < cap ? units : cap, TTA_THREADS, smem, stream>>>(p);
+  tta_rows_kernel<CT, EXACT, FAST><<<units < cap ? units : cap, TTA_THREADS, smem, stream>>>(p);
   return B200SEG_OK;
+}
+template <int CT, bool EXACT>
+static int tta_rows_launch(const TtaParams& p, cudaStream_t stream) {
+  // probabilities requested: every value must be ATen's; labels / matrix only: the order suffices (fast path + exact fallback)
+  if (g_tta_fast && p.probs == nullptr && CT <= 20) return tta_rows_launch_t<CT, EXACT, true>(p, stream);   // (CT = 32 x 4 members would spill)
+  return tta_rows_launch_t<CT, EXACT, false>(p, stream);
 }
 
 // logits[m]: fp32 [C, h[m], w[m]] (device pointers in a HOST array); flip[m] != 0: the member saw the mirrored image

@@ -1143,3 +1143,47 @@ def test_conv_weight_pack_layouts_exact(lib, parts, Ci):
     assert torch.equal(Wf, allw.permute(2, 0, 1).contiguous())
     Co = sum(parts)
     assert torch.equal(Wb[:, :, :Co], allw.permute(2, 1, 0).contiguous()) and float(Wb[:, :, Co:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("C,shapes,flips,divisors,H,W,sigma", [
+    (19, [(64, 128), (64, 128)], [False, True], (2,), 512, 1024, 1.0),
+    (19, [(64, 128), (64, 128)], [False, True], (2,), 512, 1024, 0.01),       # near-uniform probabilities: many near ties
+    (19, [(23, 45), (33, 65), (43, 84)], [False, True, False], (3,), 260, 517, 0.01),
+    (2, [(44, 44), (44, 44)], [False, True], (2,), 352, 352, 0.01),
+    (7, [(9, 11)], [True], (), 50, 70, 1e-4),
+    (20, [(8, 8), (12, 10)], [False, False], (2,), 64, 61, 0.01),
+])
+def test_k7_labels_only_fast_path_is_bit_exact(lib, C, shapes, flips, divisors, H, W, sigma):
+    """Without a probability output the row-walking kernel orders the classes with ex2.approx-based probabilities and re-runs the
+    exact sequence only on near ties: labels and confusion matrix must equal the exact kernel's and torch's, bit for bit."""
+    members = _tta_members(C, shapes, sigma, seed=500 + C + len(shapes))
+    labels = make_labels(1, H, W, C, 0.1, 29).cuda()
+    want_pred = to.tta_probabilities(members, flips, (H, W), divisors).max(1)[1]
+    got = {}
+    for fast in (True, False):
+        lib.tta_set_row_walk(True, fast=fast)
+        try:
+            got[fast] = lib.tta_argmax_confusion(members, flips, (H, W), labels=labels, divisors=divisors, want_pred=True)
+        finally:
+            lib.tta_set_row_walk(True)
+    assert torch.equal(got[True][1], got[False][1]) and torch.equal(got[True][0], got[False][0])
+    assert torch.equal(got[True][1].unsqueeze(0), want_pred)
+    cm_only, _, _ = lib.tta_argmax_confusion(members, flips, (H, W), labels=labels, divisors=divisors)
+    assert torch.equal(cm_only.cpu(), to.confusion_matrix_bincount(C, want_pred.flatten().cpu(), labels.flatten().cpu()))
+
+
+def test_k7_fast_path_exact_ties_and_one_ulp_pairs(lib):
+    """Adversarial members: identical classes (exact ties -> first index), pairs one ulp apart, and a member whose mirror image
+    cancels the other's preference -- the fast path has to hand every such pixel to the exact sequence."""
+    torch.manual_seed(5)
+    base = torch.randn(1, 1, 16, 32).repeat(1, 19, 1, 1)
+    base[:, 5] = torch.nextafter(base[:, 5], torch.full_like(base[:, 5], 10.0))
+    base[:, 11] = base[:, 5]
+    a = base.cuda()
+    b = base.flip(3).contiguous().cuda()                      # mirrored twin: un-mirrored it equals a (up to sampling rounding)
+    labels = make_labels(1, 128, 256, 19, 0.2, 9).cuda()
+    for members, flips, divs in (([a], [False], ()), ([a, b], [False, True], (2,)), ([a, a], [False, False], (2,))):
+        want = to.tta_probabilities(members, flips, (128, 256), divs).max(1)[1]
+        cm, pred, _ = lib.tta_argmax_confusion(members, flips, (128, 256), labels=labels, divisors=divs, want_pred=True)
+        assert torch.equal(pred.unsqueeze(0), want)
+        assert torch.equal(cm.cpu(), to.confusion_matrix_bincount(19, want.flatten().cpu(), labels.flatten().cpu()))
