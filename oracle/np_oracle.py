@@ -173,3 +173,75 @@ def aspp_head(x: np.ndarray, weights, biases, rates=(6, 12, 18, 24)) -> np.ndarr
                 patch = x[:, :, ys0 + dy:ys1 + dy, xs0 + dx:xs1 + dx]
                 out[:, :, ys0:ys1, xs0:xs1] += np.einsum("oc,nchw->nohw", wgt[:, :, ky, kx], patch)
     return out
+
+
+# --------------------------------------------------------------------------
+# 8f-3  test-time augmentation from the members' low-res logits
+#        (core/utils/utility.py:179-191 flip=True, :193-209 multi_scale_inference)
+# --------------------------------------------------------------------------
+def softmax_probabilities(x: np.ndarray) -> np.ndarray:
+    """float32 spatial softmax over axis 1, ATen's sequence (see softmax_first_max)."""
+    x = np.asarray(x, dtype=np.float32)
+    m = x.max(axis=1, keepdims=True)
+    e = np.exp((x - m).astype(F32)).astype(F32)
+    s = np.zeros(e.shape[:1] + e.shape[2:], dtype=F32)
+    for c in range(e.shape[1]):
+        s = (s + e[:, c]).astype(F32)
+    return (e / s[:, None]).astype(F32)
+
+
+def tta_probabilities(members, flips, size, divisors=()) -> np.ndarray:
+    """sum over members, in order, of the (un-mirrored) softmax of the upsampled logits [1,C,h_m,w_m]; then the scalar
+    divisions in order (float32 IEEE divisions, as ATen's CPU kernel performs ``tensor / python_scalar``)."""
+    total = None
+    for lg, fl in zip(members, flips):
+        pr = softmax_probabilities(upsample_bilinear_ac(np.asarray(lg, dtype=F32), size))
+        if fl:
+            pr = pr[..., ::-1]
+        total = pr.copy() if total is None else (total + pr).astype(F32)
+    for d in divisors:
+        total = (total / F32(d)).astype(F32)
+    return total
+
+
+# --------------------------------------------------------------------------
+# 8f-4  optimizer steps, the arithmetic of torch/optim/sgd.py::_single_tensor_sgd and torch/optim/adam.py::_single_tensor_adam
+#        as the reference configures them (aspp_trainer.py:25-26, fada_adapter.py:24).  ``a + alpha * b`` ops are single
+#        FMAs in ATen; numpy has no fma, so they are evaluated in float64 and rounded once to float32 (the float64 product of
+#        two float32 values is exact; the rare double rounding of the sum is below the 1e-6 parity bar).
+# --------------------------------------------------------------------------
+def _fma32(a, b, c):
+    return (np.asarray(a, dtype=np.float64) * np.asarray(b, dtype=np.float64) + np.asarray(c, dtype=np.float64)).astype(F32)
+
+
+def sgd_step(p, g, buf, lr, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False, grad_scale=1.0):
+    """One torch.optim.SGD update.  ``buf`` is None on the first step (torch's momentum_buffer is None).  Returns (p, buf)."""
+    p, g = np.asarray(p, dtype=F32), np.asarray(g, dtype=F32)
+    if grad_scale != 1.0:
+        g = (g * F32(grad_scale)).astype(F32)
+    if weight_decay != 0:
+        g = _fma32(F32(weight_decay), p, g)                       # grad.add(param, alpha=weight_decay)
+    d = g
+    if momentum != 0:
+        if buf is None:
+            buf = g.copy()                                       # torch.clone(grad)
+        else:
+            buf = _fma32(F32(1.0 - dampening), g, (np.asarray(buf, dtype=F32) * F32(momentum)).astype(F32))   # mul_().add_(grad, alpha)
+        d = _fma32(F32(momentum), buf, g) if nesterov else buf
+    return _fma32(F32(-lr), d, p), buf                           # param.add_(grad, alpha=-lr)
+
+
+def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+    """One torch.optim.Adam update (no amsgrad); ``step`` counts this update (>= 1); m, v start at zero.  Returns (p, m, v)."""
+    p, g, m, v = (np.asarray(t, dtype=F32) for t in (p, g, m, v))
+    if grad_scale != 1.0:
+        g = (g * F32(grad_scale)).astype(F32)
+    if weight_decay != 0:
+        g = _fma32(F32(weight_decay), p, g)
+    m = _fma32(F32(1.0 - beta1), (g - m).astype(F32), m)          # exp_avg.lerp_(grad, 1 - beta1)
+    v = _fma32((F32(1.0 - beta2) * g).astype(F32), g, (v * F32(beta2)).astype(F32))   # mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+    bc1 = 1.0 - beta1 ** step
+    bc2_sqrt = (1.0 - beta2 ** step) ** 0.5
+    denom = ((np.sqrt(v).astype(F32) / F32(bc2_sqrt)).astype(F32) + F32(eps)).astype(F32)
+    p = _fma32(F32(-(lr / bc1)), (m / denom).astype(F32), p)      # addcdiv_(exp_avg, denom, value=-step_size)
+    return p, m, v

@@ -267,3 +267,38 @@ def test_fada_iteration_oracle_equals_fada_step_losses_and_moves_parameters():
         assert torch.equal(a, b)
     assert all(not torch.equal(p, q) for p, q in zip(head.parameters(), head2.parameters()))
     assert all(not torch.equal(p, q) for p, q in zip(D.parameters(), D2.parameters()))
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def test_numpy_optimizer_restatement_matches_reference_golden(golden):
+    """np_oracle.sgd_step / adam_step (the formulas the CUDA kernels implement, term by term) against the parameters and states
+    torch.optim produced under the reference's setup: 1e-6 relative, the bar the GPU tests hold the kernels to."""
+    g = golden("optim")
+    n, steps = int(g["n"]), int(g["steps"])
+    lrs = [float(v) for v in g["lrs"]]
+    for i in range(n):
+        p, buf = g[f"p0.{i}"], None
+        for k in range(steps):
+            p, buf = npo.sgd_step(p, g[f"g{k}.{i}"], buf, lr=lrs[k] * 10, momentum=0.9, weight_decay=5e-4)
+        assert _rel(p, g[f"sgd.p.{i}"]) <= 1e-6 and _rel(buf, g[f"sgd.buf.{i}"]) <= 1e-6
+        p, m, v = g[f"p0.{i}"], np.zeros_like(g[f"p0.{i}"]), np.zeros_like(g[f"p0.{i}"])
+        for k in range(steps):
+            p, m, v = npo.adam_step(p, g[f"g{k}.{i}"], m, v, k + 1, lr=lrs[k] * 0.4, beta1=0.9, beta2=0.99)
+        assert _rel(p, g[f"adam.p.{i}"]) <= 1e-6 and _rel(m, g[f"adam.m.{i}"]) <= 1e-6 and _rel(v, g[f"adam.v.{i}"]) <= 4e-6
+
+
+def test_numpy_tta_restatement_matches_reference_golden(golden):
+    g = golden("tta")
+    size = g["label"].shape[-2:]
+    both = [g["flip.member0"], g["flip.member1"]]
+    np.testing.assert_allclose(npo.tta_probabilities(both, [False, True], size, (2,)), g["flip.probs"], rtol=2e-6, atol=2e-7)
+    members = [g[f"ms.member{k}"] for k in range(int(g["ms.n_members"]))]
+    got = npo.tta_probabilities(members, [bool(k % 2) for k in range(len(members))], size, (3, 2))
+    np.testing.assert_allclose(got, g["ms.probs"], rtol=2e-6, atol=2e-7)
+    top2 = np.sort(g["ms.probs"], axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-6
+    assert np.array_equal(got.argmax(1)[clear], g["ms.pred"][clear])
