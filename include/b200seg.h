@@ -50,11 +50,28 @@ B200SEG_API int b200seg_upsample_argmax_confusion(const float* logits, int N, in
                                       int W, int ignore_index, int64_t* cm, int64_t cm_frame_stride, int64_t* pred,
                                       int fma_mode, void* stream);
 
+/* The same kernel with label / prediction maps in either element width -- label_bytes / pred_bytes = 8 (int64, what the
+ * reference passes after `.long()`, core/testers/aspp_tester.py:58) or 1 (uint8, the tensor the dataloader already holds,
+ * core/datasets/transform.py:31-33): 8x fewer label bytes, no conversion pass. */
+B200SEG_API int b200seg_upsample_argmax_confusion_ex(const float* logits, int N, int C, int h, int w, const void* labels,
+                                         int label_bytes, int H, int W, int ignore_index, int64_t* cm, int64_t cm_frame_stride,
+                                         void* pred, int pred_bytes, int fma_mode, void* stream);
+/* Several frames of the tester loop (core/testers/aspp_tester.py:57-72, TEST.BATCH_SIZE = 1) in ONE launch: per-frame device
+ * pointers in HOST arrays (logits_host[f] -> f32 [C,h,w]; labels_host[f] -> [H,W]; pred_host[f] -> [H,W] or pred_host NULL).
+ * Any number of frames (16 per kernel launch).  cm as above (stride 0: one matrix for all frames). */
+B200SEG_API int b200seg_upsample_argmax_confusion_frames(const float* const* logits_host, int n_frames, int C, int h, int w,
+                                             const void* const* labels_host, int label_bytes, int H, int W, int ignore_index,
+                                             int64_t* cm, int64_t cm_frame_stride, void* const* pred_host, int pred_bytes,
+                                             void* stream);
+
 /* confusion matrix from a materialised prediction map (API-compat form of utility.py:347-359);
  * mutate_pd != 0 also writes pd[i] = ignore_index where gt[i] == ignore_index, as
  * intersectionAndUnionGPU does to its `output` argument (utility.py:154). */
 B200SEG_API int b200seg_confusion_from_pred(int64_t* pd, const int64_t* gt, int64_t n, int C, int ignore_index, int mutate_pd,
                                 int64_t* cm, void* stream);
+/* ... with int64 or uint8 maps (pd_bytes / gt_bytes = 8 or 1, any combination) */
+B200SEG_API int b200seg_confusion_from_pred_ex(void* pd, int pd_bytes, const void* gt, int gt_bytes, int64_t n, int C,
+                                   int ignore_index, int mutate_pd, int64_t* cm, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K2  upsample + softmax cross-entropy (ignore_index) forward, gradient w.r.t. low-res logits
@@ -70,6 +87,11 @@ B200SEG_API int64_t b200seg_upsample_ce_workspace_bytes(int N, int C, int h, int
 B200SEG_API int b200seg_upsample_ce_forward(const float* logits, int N, int C, int h, int w, const int64_t* labels, int H, int W,
                                 int ignore_index, float inv_temperature, int need_grad, void* workspace,
                                 int64_t workspace_bytes, float* loss_out2, void* stream);
+/* ... with int64 or uint8 labels (label_bytes = 8 or 1; the trainer's `.long()` at core/trainers/aspp_trainer.py:86 becomes
+ * unnecessary: the uint8 tensor of core/datasets/transform.py:31-33 is consumed as it is) */
+B200SEG_API int b200seg_upsample_ce_forward_ex(const float* logits, int N, int C, int h, int w, const void* labels, int label_bytes,
+                                   int H, int W, int ignore_index, float inv_temperature, int need_grad, void* workspace,
+                                   int64_t workspace_bytes, float* loss_out2, void* stream);
 B200SEG_API int b200seg_upsample_ce_backward(const void* workspace, int N, int C, int h, int w, int H, int W,
                                  float inv_temperature, const float* loss_out2, const float* grad_out,
                                  float* grad_logits, void* stream);
@@ -235,6 +257,12 @@ B200SEG_API int b200seg_nhwc_bf16_colsum(const void* g_nhwc_bf16, int64_t P, int
 B200SEG_API int b200seg_tta_argmax_confusion(const float* const* logits_lr, const int* h, const int* w, const int* flip, int n_members,
                                              int C, const int64_t* labels, int H, int W, int ignore_index, const float* divisors,
                                              int n_div, int div_exact, int64_t* cm, int64_t* pred, float* probs, void* stream);
+/* ... with int64 or uint8 label and prediction maps (label_bytes / pred_bytes = 8 or 1): uint8 labels as the dataloader holds them
+ * (core/datasets/transform.py:31-33), uint8 predictions as the pseudo-label writer stores them (core/testers/aspp_tester.py:40-45) */
+B200SEG_API int b200seg_tta_argmax_confusion_ex(const float* const* logits_lr, const int* h, const int* w, const int* flip,
+                                                int n_members, int C, const void* labels, int label_bytes, int H, int W,
+                                                int ignore_index, const float* divisors, int n_div, int div_exact, int64_t* cm,
+                                                void* pred, int pred_bytes, float* probs, void* stream);
 
 /* ensembles of up to four members: 1 (default) = the row-walking kernel (horizontal lerps of the two current source rows kept per
  * thread in shared memory and re-used for every output row between them), 0 = the per-pixel kernel used for larger ensembles

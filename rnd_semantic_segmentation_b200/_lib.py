@@ -27,7 +27,16 @@ SIGNATURES = {
     "b200seg_device_sms": (c_int, []),
     "b200seg_upsample_argmax_confusion": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_vp, c_i64,
                                                   c_vp, c_int, c_vp]),
+    "b200seg_upsample_argmax_confusion_ex": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_i64,
+                                                     c_vp, c_int, c_int, c_vp]),
+    "b200seg_upsample_argmax_confusion_frames": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp,
+                                                         c_i64, c_vp, c_int, c_vp]),
     "b200seg_confusion_from_pred": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_vp]),
+    "b200seg_confusion_from_pred_ex": (c_int, [c_vp, c_int, c_vp, c_int, c_i64, c_int, c_int, c_int, c_vp, c_vp]),
+    "b200seg_upsample_ce_forward_ex": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_f32, c_int, c_vp,
+                                               c_i64, c_vp, c_vp]),
+    "b200seg_tta_argmax_confusion_ex": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int,
+                                                c_int, c_vp, c_vp, c_int, c_vp, c_vp]),
     "b200seg_upsample_ce_workspace_bytes": (c_i64, [c_int] * 6),
     "b200seg_upsample_ce_forward": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_f32, c_int, c_vp,
                                             c_i64, c_vp, c_vp]),
@@ -189,21 +198,57 @@ def device_sms() -> int:
     return load().b200seg_device_sms()
 
 
+LABEL_DTYPES = (torch.int64, torch.uint8)
+
+
+def as_label_tensor(t: torch.Tensor) -> torch.Tensor:
+    """Label / prediction maps are consumed as int64 (what the reference passes after ``.long()``, aspp_trainer.py:86,
+    aspp_tester.py:58) or as uint8 (the tensor the dataloader holds, core/datasets/transform.py:31-33) without a conversion
+    pass; any other integer dtype is widened to int64 first."""
+    return t if t.dtype in LABEL_DTYPES else t.long()
+
+
+def _need_label(t: torch.Tensor, name: str) -> int:
+    """Checks a label / prediction map and returns its element width in bytes (8 or 1)."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise B200SegError(f"{name}: expected a CUDA tensor (b200seg has no CPU fallback), got device {t.device}")
+    if t.dtype not in LABEL_DTYPES:
+        raise B200SegError(f"{name}: expected dtype torch.int64 or torch.uint8, got {t.dtype}")
+    if not t.is_contiguous():
+        raise B200SegError(f"{name}: expected a contiguous tensor")
+    return 8 if t.dtype == torch.int64 else 1
+
+
+def _pred_dtype(want_pred):
+    """want_pred: False / True (int64, the reference's max(1)[1]) / torch.uint8 / torch.int64."""
+    if want_pred is True:
+        return torch.int64
+    if want_pred in LABEL_DTYPES:
+        return want_pred
+    if not want_pred:
+        return None
+    raise B200SegError(f"want_pred: expected a bool, torch.int64 or torch.uint8, got {want_pred!r}")
+
+
 # --------------------------------------------------------------------------------------------
 # K4
 # --------------------------------------------------------------------------------------------
 def upsample_argmax_confusion(logits_lr: torch.Tensor, labels: Optional[torch.Tensor], size, num_classes: Optional[int] = None,
                               ignore_index: int = 255, cm: Optional[torch.Tensor] = None, per_frame: bool = False,
-                              want_pred: bool = False, fma_mode: int = 0):
-    """Returns (cm, pred).  cm int64 [C,C] (or [N,C,C] if per_frame) accumulated in place when given."""
+                              want_pred=False, fma_mode: int = 0):
+    """Returns (cm, pred).  cm int64 [C,C] (or [N,C,C] if per_frame) accumulated in place when given.  ``labels``: int64 or
+    uint8 [N,H,W]; ``want_pred``: True (int64) or torch.uint8 / torch.int64."""
     lib = load()
     _need(logits_lr, torch.float32, "logits")
     N, C, h, w = logits_lr.shape
     H, W = int(size[0]), int(size[1])
     if num_classes is not None and num_classes != C:
         raise B200SegError(f"logits have {C} channels but num_classes={num_classes}")
+    lbytes = 8
     if labels is not None:
-        _need(labels, torch.int64, "labels")
+        lbytes = _need_label(labels, "labels")
         if labels.numel() != N * H * W:
             raise B200SegError(f"labels shape {tuple(labels.shape)} does not match N*H*W = {N}*{H}*{W}")
     stride = 0
@@ -212,17 +257,64 @@ def upsample_argmax_confusion(logits_lr: torch.Tensor, labels: Optional[torch.Te
             cm = torch.zeros((N, C, C) if per_frame else (C, C), dtype=torch.int64, device=logits_lr.device)
         _need(cm, torch.int64, "cm")
         stride = C * C if cm.dim() == 3 else 0
-    pred = torch.empty((N, H, W), dtype=torch.int64, device=logits_lr.device) if want_pred else None
+    pdt = _pred_dtype(want_pred)
+    pred = torch.empty((N, H, W), dtype=pdt, device=logits_lr.device) if pdt is not None else None
     with _on_device(logits_lr.device):
-        _check(lib.b200seg_upsample_argmax_confusion(logits_lr.data_ptr(), N, C, h, w, _ptr(labels), H, W, ignore_index,
-                                                     _ptr(cm) if labels is not None else None, stride, _ptr(pred), fma_mode,
-                                                     _stream()))
+        _check(lib.b200seg_upsample_argmax_confusion_ex(logits_lr.data_ptr(), N, C, h, w, _ptr(labels), lbytes, H, W, ignore_index,
+                                                        _ptr(cm) if labels is not None else None, stride, _ptr(pred),
+                                                        1 if pdt == torch.uint8 else 8, fma_mode, _stream()))
     return cm, pred
+
+
+def upsample_argmax_confusion_frames(logits: Sequence[torch.Tensor], labels: Optional[Sequence[torch.Tensor]], size,
+                                     ignore_index: int = 255, cm: Optional[torch.Tensor] = None, per_frame: bool = False,
+                                     want_pred=False):
+    """K4 over several frames of the tester loop in ONE launch (16 frames per kernel launch): ``logits[f]`` fp32 [C,h,w] (or
+    [1,C,h,w]) and ``labels[f]`` int64 / uint8 [H,W] are separate tensors (no concatenation pass).  Returns (cm, [pred_f] | None)
+    with cm int64 [C,C] accumulated over the frames, or [F,C,C] with ``per_frame``."""
+    lib = load()
+    F_ = len(logits)
+    if F_ == 0:
+        raise B200SegError("upsample_argmax_confusion_frames: no frames")
+    maps = []
+    for f, t in enumerate(logits):
+        _need(t, torch.float32, f"logits[{f}]")
+        if t.dim() == 4 and t.shape[0] == 1:
+            t = t[0]
+        if t.dim() != 3 or (maps and t.shape != maps[0].shape) or t.device != logits[0].device:
+            raise B200SegError(f"logits[{f}]: expected one [C,h,w] map per frame, all of one shape and device")
+        maps.append(t)
+    C, h, w = (int(v) for v in maps[0].shape)
+    H, W = int(size[0]), int(size[1])
+    dev = maps[0].device
+    lbytes = 8
+    if labels is not None:
+        if len(labels) != F_:
+            raise B200SegError("upsample_argmax_confusion_frames: one label map per frame")
+        lbytes = _need_label(labels[0], "labels[0]")
+        for f, t in enumerate(labels):
+            if _need_label(t, f"labels[{f}]") != lbytes or t.numel() != H * W or t.device != dev:
+                raise B200SegError(f"labels[{f}]: expected {H}x{W} maps of one dtype on {dev}")
+        if cm is None:
+            cm = torch.zeros((F_, C, C) if per_frame else (C, C), dtype=torch.int64, device=dev)
+        _need(cm, torch.int64, "cm")
+    elif cm is not None:
+        raise B200SegError("upsample_argmax_confusion_frames: a confusion matrix needs labels")
+    stride = C * C if (cm is not None and cm.dim() == 3) else 0
+    pdt = _pred_dtype(want_pred)
+    preds = [torch.empty((H, W), dtype=pdt, device=dev) for _ in range(F_)] if pdt is not None else None
+    with _on_device(dev):
+        _check(lib.b200seg_upsample_argmax_confusion_frames(_ptr_array(maps), F_, C, h, w,
+                                                            _ptr_array(list(labels)) if labels is not None else None, lbytes, H, W,
+                                                            ignore_index, _ptr(cm), stride,
+                                                            _ptr_array(preds) if preds is not None else None,
+                                                            1 if pdt == torch.uint8 else 8, _stream()))
+    return cm, preds
 
 
 def tta_argmax_confusion(members: Sequence[torch.Tensor], flips: Sequence[bool], size, labels: Optional[torch.Tensor] = None,
                          divisors: Sequence[float] = (), ignore_index: int = 255, cm: Optional[torch.Tensor] = None,
-                         want_pred: bool = False, want_probs: bool = False, div_exact: bool = False):
+                         want_pred=False, want_probs: bool = False, div_exact: bool = False):
     """K7: fused test-time augmentation for ONE frame.  ``members``: fp32 [C,h_m,w_m] (or [1,C,h_m,w_m]) low-res logit maps,
     ``flips[m]``: member m was computed on the mirrored image.  Returns (cm | None, pred int64 [H,W] | None, probs fp32 [C,H,W] | None)
     with probs = (sum_m unflip(softmax(upsample(member_m)))) / divisors[0] [/ divisors[1]] and pred its first argmax."""
@@ -244,8 +336,9 @@ def tta_argmax_confusion(members: Sequence[torch.Tensor], flips: Sequence[bool],
     C = int(maps[0].shape[0])
     H, W = int(size[0]), int(size[1])
     dev = maps[0].device
+    lbytes = 8
     if labels is not None:
-        _need(labels, torch.int64, "labels")
+        lbytes = _need_label(labels, "labels")
         if labels.numel() != H * W:
             raise B200SegError(f"labels shape {tuple(labels.shape)} does not match H*W = {H}*{W}")
         if cm is None:
@@ -255,7 +348,8 @@ def tta_argmax_confusion(members: Sequence[torch.Tensor], flips: Sequence[bool],
         raise B200SegError("tta_argmax_confusion: a confusion matrix needs labels")
     if len(divisors) > 2:
         raise B200SegError("tta_argmax_confusion: at most two divisors")
-    pred = torch.empty((H, W), dtype=torch.int64, device=dev) if want_pred else None
+    pdt = _pred_dtype(want_pred)
+    pred = torch.empty((H, W), dtype=pdt, device=dev) if pdt is not None else None
     probs = torch.empty((C, H, W), dtype=torch.float32, device=dev) if want_probs else None
     n = len(maps)
     hs = (c_int * n)(*[int(t.shape[1]) for t in maps])
@@ -263,8 +357,9 @@ def tta_argmax_confusion(members: Sequence[torch.Tensor], flips: Sequence[bool],
     fl = (c_int * n)(*[1 if f else 0 for f in flips])
     dv = (c_f32 * max(1, len(divisors)))(*[float(d) for d in divisors])
     with _on_device(dev):
-        _check(lib.b200seg_tta_argmax_confusion(_ptr_array(maps), hs, ws, fl, n, C, _ptr(labels), H, W, int(ignore_index), dv,
-                                                len(divisors), 1 if div_exact else 0, _ptr(cm), _ptr(pred), _ptr(probs), _stream()))
+        _check(lib.b200seg_tta_argmax_confusion_ex(_ptr_array(maps), hs, ws, fl, n, C, _ptr(labels), lbytes, H, W, int(ignore_index),
+                                                   dv, len(divisors), 1 if div_exact else 0, _ptr(cm), _ptr(pred),
+                                                   1 if pdt == torch.uint8 else 8, _ptr(probs), _stream()))
     return cm, pred, probs
 
 
@@ -325,16 +420,16 @@ def adam_step(params: Sequence[torch.Tensor], grads: Sequence[torch.Tensor], exp
 def confusion_from_pred(pd: torch.Tensor, gt: torch.Tensor, num_classes: int, ignore_index: int = 255,
                         mutate_pd: bool = False, cm: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = load()
-    _need(pd, torch.int64, "pd")
-    _need(gt, torch.int64, "gt")
+    pb = _need_label(pd, "pd")
+    gb = _need_label(gt, "gt")
     if pd.numel() != gt.numel():
         raise B200SegError("pd and gt must have the same number of elements")
     if cm is None:
         cm = torch.zeros(num_classes, num_classes, dtype=torch.int64, device=pd.device)
     _need(cm, torch.int64, "cm")
     with _on_device(pd.device):
-        _check(lib.b200seg_confusion_from_pred(pd.data_ptr(), gt.data_ptr(), pd.numel(), num_classes, ignore_index,
-                                               1 if mutate_pd else 0, cm.data_ptr(), _stream()))
+        _check(lib.b200seg_confusion_from_pred_ex(pd.data_ptr(), pb, gt.data_ptr(), gb, pd.numel(), num_classes, ignore_index,
+                                                  1 if mutate_pd else 0, cm.data_ptr(), _stream()))
     return cm
 
 
@@ -345,7 +440,7 @@ def upsample_ce_forward(logits_lr, labels, ignore_index=255, inv_temperature=1.0
     """Returns (loss_and_count float32[2], workspace) -- workspace feeds upsample_ce_backward."""
     lib = load()
     _need(logits_lr, torch.float32, "logits")
-    _need(labels, torch.int64, "labels")
+    lbytes = _need_label(labels, "labels")
     N, C, h, w = logits_lr.shape
     H, W = labels.shape[-2:]
     if labels.numel() != N * H * W:
@@ -354,9 +449,9 @@ def upsample_ce_forward(logits_lr, labels, ignore_index=255, inv_temperature=1.0
     ws = torch.empty(nbytes, dtype=torch.uint8, device=logits_lr.device)
     out2 = torch.empty(2, dtype=torch.float32, device=logits_lr.device)
     with _on_device(logits_lr.device):
-        _check(lib.b200seg_upsample_ce_forward(logits_lr.data_ptr(), N, C, h, w, labels.data_ptr(), H, W, ignore_index,
-                                               float(inv_temperature), 1 if need_grad else 0, ws.data_ptr(), nbytes,
-                                               out2.data_ptr(), _stream()))
+        _check(lib.b200seg_upsample_ce_forward_ex(logits_lr.data_ptr(), N, C, h, w, labels.data_ptr(), lbytes, H, W, ignore_index,
+                                                  float(inv_temperature), 1 if need_grad else 0, ws.data_ptr(), nbytes,
+                                                  out2.data_ptr(), _stream()))
     return out2, ws
 
 

@@ -38,11 +38,20 @@ class ASPP_Classifier_V2(nn.Module):
             rates.append(int(d[0]))
         return rates
 
+    def invalidate_packed(self):
+        """Drop the cached bf16 weight pack (call after writing the parameters through ``.data``, a raw pointer or a
+        CUDA-graph replay while the module is in eval mode)."""
+        self._packed = None
+        self._packed_key = None
+
     def _packed_weights(self):
-        """Packed bf16 weights, re-packed only when a parameter changed (eval loops reuse them)."""
+        """Packed bf16 weights.  In training mode they are re-packed on EVERY call (one ~6 us kernel): parameter version
+        counters miss in-place writes through ``.data`` -- the reference's own init idiom, classifier.py:23-24 -- and raw-pointer
+        / CUDA-graph writers, and a stale pack would silently train on old weights.  Only eval mode reuses the pack, keyed
+        on (data_ptr, _version); ``invalidate_packed()`` drops it explicitly."""
         params = [m.weight for m in self.conv2d_list] + [m.bias for m in self.conv2d_list]
         key = tuple((p.data_ptr(), p._version) for p in params)
-        if self._packed is None or key != self._packed_key:
+        if self.training or self._packed is None or key != self._packed_key:
             from . import _lib
             self._packed = _lib.aspp_pack_weights([m.weight.detach() for m in self.conv2d_list],
                                                   [m.bias.detach() for m in self.conv2d_list])

@@ -49,10 +49,12 @@ int num_sms() {
 }
 
 // kernels' host launchers (defined in the other translation units)
-int k4_launch(const float*, int, int, int, int, const long long*, int, int, int, long long*, long long, long long*, int, cudaStream_t);
-int confusion_pairs_launch(long long*, const long long*, long long, int, int, int, long long*, cudaStream_t);
+int k4_launch(const float*, int, int, int, int, const void*, int, int, int, int, long long*, long long, void*, int, int, cudaStream_t);
+int k4_launch_frames(const float* const*, int, int, int, int, const void* const*, int, int, int, int, long long*, long long, void* const*,
+                     int, int, cudaStream_t);
+int confusion_pairs_launch_ex(void*, int, const void*, int, long long, int, int, int, long long*, cudaStream_t);
 long long k2_workspace_bytes(int, int, int, int, int, int);
-int k2_forward(const float*, int, int, int, int, const long long*, int, int, int, float, int, void*, long long, float*, cudaStream_t);
+int k2_forward(const float*, int, int, int, int, const void*, int, int, int, int, float, int, void*, long long, float*, cudaStream_t);
 int k2_backward(const void*, int, int, int, int, int, int, float, const float*, const float*, float*, cudaStream_t);
 int k2_backward_packed(void*, int, int, int, int, int, int, float, const float*, const float*, void*, float*, cudaStream_t);
 int aspp_backward_packed(const void*, const void*, const void*, const int*, int, int, int, int, int, int, void*, long long, int, float*,
@@ -88,8 +90,8 @@ int conv3x3_wgrad(const void*, int, long long, const void*, int, long long, int,
 int nchw_to_nhwc_bf16(const float*, int, int, int, void*, int, cudaStream_t);
 long long nhwc_colsum_scratch_bytes(int);
 int nhwc_bf16_colsum(const void*, long long, int, int, void*, float*, cudaStream_t);
-int tta_launch(const float* const*, const int*, const int*, const int*, int, int, const long long*, int, int, int, const float*, int, int,
-               long long*, long long*, float*, cudaStream_t);
+int tta_launch(const float* const*, const int*, const int*, const int*, int, int, const void*, int, int, int, int, const float*, int, int,
+               long long*, void*, int, float*, cudaStream_t);
 void tta_set_row_walk(int);
 int sgd_step(int, float* const*, const float* const*, float* const*, const long long*, float, float, float, float, int, int, float,
              cudaStream_t);
@@ -138,15 +140,37 @@ int b200seg_upsample_argmax_confusion(const float* logits, int N, int C, int h, 
                                       int ignore_index, int64_t* cm, int64_t cm_frame_stride, int64_t* pred, int fma_mode,
                                       void* stream) {
   REQUIRE_DEVICE();
-  return k4_launch(logits, N, C, h, w, reinterpret_cast<const long long*>(labels), H, W, ignore_index,
-                   reinterpret_cast<long long*>(cm), cm_frame_stride, reinterpret_cast<long long*>(pred), fma_mode, S(stream));
+  return k4_launch(logits, N, C, h, w, labels, 8, H, W, ignore_index, reinterpret_cast<long long*>(cm), cm_frame_stride, pred, 8,
+                   fma_mode, S(stream));
+}
+
+int b200seg_upsample_argmax_confusion_ex(const float* logits, int N, int C, int h, int w, const void* labels, int label_bytes, int H,
+                                         int W, int ignore_index, int64_t* cm, int64_t cm_frame_stride, void* pred, int pred_bytes,
+                                         int fma_mode, void* stream) {
+  REQUIRE_DEVICE();
+  return k4_launch(logits, N, C, h, w, labels, label_bytes, H, W, ignore_index, reinterpret_cast<long long*>(cm), cm_frame_stride,
+                   pred, pred_bytes, fma_mode, S(stream));
+}
+
+int b200seg_upsample_argmax_confusion_frames(const float* const* logits_host, int n_frames, int C, int h, int w,
+                                             const void* const* labels_host, int label_bytes, int H, int W, int ignore_index,
+                                             int64_t* cm, int64_t cm_frame_stride, void* const* pred_host, int pred_bytes,
+                                             void* stream) {
+  REQUIRE_DEVICE();
+  return k4_launch_frames(logits_host, n_frames, C, h, w, labels_host, label_bytes, H, W, ignore_index,
+                          reinterpret_cast<long long*>(cm), cm_frame_stride, pred_host, pred_bytes, 0, S(stream));
 }
 
 int b200seg_confusion_from_pred(int64_t* pd, const int64_t* gt, int64_t n, int C, int ignore_index, int mutate_pd, int64_t* cm,
                                 void* stream) {
   REQUIRE_DEVICE();
-  return confusion_pairs_launch(reinterpret_cast<long long*>(pd), reinterpret_cast<const long long*>(gt), n, C, ignore_index,
-                                mutate_pd, reinterpret_cast<long long*>(cm), S(stream));
+  return confusion_pairs_launch_ex(pd, 8, gt, 8, n, C, ignore_index, mutate_pd, reinterpret_cast<long long*>(cm), S(stream));
+}
+
+int b200seg_confusion_from_pred_ex(void* pd, int pd_bytes, const void* gt, int gt_bytes, int64_t n, int C, int ignore_index,
+                                   int mutate_pd, int64_t* cm, void* stream) {
+  REQUIRE_DEVICE();
+  return confusion_pairs_launch_ex(pd, pd_bytes, gt, gt_bytes, n, C, ignore_index, mutate_pd, reinterpret_cast<long long*>(cm), S(stream));
 }
 
 int64_t b200seg_upsample_ce_workspace_bytes(int N, int C, int h, int w, int H, int W) {
@@ -158,8 +182,16 @@ int b200seg_upsample_ce_forward(const float* logits, int N, int C, int h, int w,
                                 int ignore_index, float inv_temperature, int need_grad, void* workspace, int64_t workspace_bytes,
                                 float* loss_out2, void* stream) {
   REQUIRE_DEVICE();
-  return k2_forward(logits, N, C, h, w, reinterpret_cast<const long long*>(labels), H, W, ignore_index, inv_temperature,
-                    need_grad, workspace, workspace_bytes, loss_out2, S(stream));
+  return k2_forward(logits, N, C, h, w, labels, 8, H, W, ignore_index, inv_temperature, need_grad, workspace, workspace_bytes,
+                    loss_out2, S(stream));
+}
+
+int b200seg_upsample_ce_forward_ex(const float* logits, int N, int C, int h, int w, const void* labels, int label_bytes, int H, int W,
+                                   int ignore_index, float inv_temperature, int need_grad, void* workspace, int64_t workspace_bytes,
+                                   float* loss_out2, void* stream) {
+  REQUIRE_DEVICE();
+  return k2_forward(logits, N, C, h, w, labels, label_bytes, H, W, ignore_index, inv_temperature, need_grad, workspace,
+                    workspace_bytes, loss_out2, S(stream));
 }
 
 int b200seg_upsample_ce_backward(const void* workspace, int N, int C, int h, int w, int H, int W, float inv_temperature,
@@ -359,8 +391,16 @@ int b200seg_tta_argmax_confusion(const float* const* logits_lr, const int* h, co
                                  const int64_t* labels, int H, int W, int ignore_index, const float* divisors, int n_div,
                                  int div_exact, int64_t* cm, int64_t* pred, float* probs, void* stream) {
   REQUIRE_DEVICE();
-  return tta_launch(logits_lr, h, w, flip, n_members, C, reinterpret_cast<const long long*>(labels), H, W, ignore_index, divisors,
-                    n_div, div_exact, reinterpret_cast<long long*>(cm), reinterpret_cast<long long*>(pred), probs, S(stream));
+  return tta_launch(logits_lr, h, w, flip, n_members, C, labels, 8, H, W, ignore_index, divisors, n_div, div_exact,
+                    reinterpret_cast<long long*>(cm), pred, 8, probs, S(stream));
+}
+
+int b200seg_tta_argmax_confusion_ex(const float* const* logits_lr, const int* h, const int* w, const int* flip, int n_members, int C,
+                                    const void* labels, int label_bytes, int H, int W, int ignore_index, const float* divisors,
+                                    int n_div, int div_exact, int64_t* cm, void* pred, int pred_bytes, float* probs, void* stream) {
+  REQUIRE_DEVICE();
+  return tta_launch(logits_lr, h, w, flip, n_members, C, labels, label_bytes, H, W, ignore_index, divisors, n_div, div_exact,
+                    reinterpret_cast<long long*>(cm), pred, pred_bytes, probs, S(stream));
 }
 
 void b200seg_tta_set_row_walk(int on) { tta_set_row_walk(on); }

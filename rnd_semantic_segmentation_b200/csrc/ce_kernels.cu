@@ -88,7 +88,8 @@ long long k2_workspace_bytes(int N, int C, int h, int w, int H, int W) {
 struct K2Params {
   K2Geom g;
   const float* logits;       // [N,C,h,w]
-  const long long* labels;   // [N,H,W]
+  const void* labels;        // [N,H,W] int64, or uint8 when label_u8
+  int label_u8;
   int ignore_index;
   float inv_T;
   float* loss_part;          // [tiles]
@@ -260,9 +261,21 @@ __global__ void __launch_bounds__(K2_THREADS * SPLIT, SPLIT == 1 ? 3 : K2_SPLIT_
   const int i_lo = (int)(g.scale_h * (float)y_begin);
   const int jspan = g.jspan_max;
 
-  // labels of the whole tile go in flight first: one commit group per K2_STRIP rows (issued by thread 0 of each column)
-  {
-    const char* src = reinterpret_cast<const char*>(p.labels + (long long)n * g.H * g.W + (long long)y_begin * g.W + (xvalid ? x : 0));
+  // labels of the whole tile go in flight first: one commit group per K2_STRIP rows (issued by thread 0 of each column).
+  // uint8 labels (the tensor the dataloader holds, core/datasets/transform.py:31-33): plain byte loads, all rows of the column
+  // in flight at once, parked in the same ring as zero-extended 64-bit entries so the row loop is unchanged.
+  if (p.label_u8) {
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.labels) + (long long)n * g.H * g.W + (long long)y_begin * g.W + (xvalid ? x : 0);
+    unsigned b[K2_TILE_H];
+#pragma unroll
+    for (int r = 0; r < K2_TILE_H; ++r) b[r] = (half == 0 && xvalid && y_begin + r < y_end) ? (unsigned)__ldg(src + (long long)r * g.W) : 0xffu;
+#pragma unroll
+    for (int r = 0; r < K2_TILE_H; ++r)
+      if (half == 0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ring_s + r * (K2_THREADS * 8)), "r"(b[r]), "r"(0u) : "memory");
+#pragma unroll
+    for (int st = 0; st < K2_TILE_H / K2_STRIP; ++st) cp_async_commit();       // keep the group accounting of the row loop
+  } else {
+    const char* src = reinterpret_cast<const char*>(reinterpret_cast<const long long*>(p.labels) + (long long)n * g.H * g.W + (long long)y_begin * g.W + (xvalid ? x : 0));
     const long long row_bytes = (long long)g.W * 8;
 #pragma unroll
     for (int st = 0; st < K2_TILE_H / K2_STRIP; ++st) {
@@ -628,8 +641,9 @@ static int k2_main_launch(const K2Params& p, bool grad, cudaStream_t stream) {
   return B200SEG_OK;
 }
 
-int k2_forward(const float* logits, int N, int C, int h, int w, const long long* labels, int H, int W, int ignore_index,
+int k2_forward(const float* logits, int N, int C, int h, int w, const void* labels, int label_bytes, int H, int W, int ignore_index,
                float inv_T, int need_grad, void* workspace, long long workspace_bytes, float* loss_out2, cudaStream_t stream) {
+  B200SEG_CHECK_ARG(label_bytes == 8 || label_bytes == 1, "upsample_ce_forward: labels must be int64 or uint8 (label_bytes=%d)", label_bytes);
   B200SEG_CHECK_ARG(logits && labels && workspace && loss_out2, "upsample_ce_forward: null pointer");
   B200SEG_CHECK_ARG(N > 0 && C > 0 && h > 0 && w > 0 && H > 0 && W > 0, "upsample_ce_forward: bad shape");
   B200SEG_CHECK_ARG(C <= 32, "upsample_ce_forward: num_classes=%d > 32 is not supported", C);
@@ -638,7 +652,7 @@ int k2_forward(const float* logits, int N, int C, int h, int w, const long long*
   K2Params p;
   k2_geometry(p.g, N, C, h, w, H, W);
   const long long tiles = k2_tiles(p.g);
-  p.logits = logits; p.labels = labels; p.ignore_index = ignore_index; p.inv_T = inv_T;
+  p.logits = logits; p.labels = labels; p.label_u8 = (label_bytes == 1); p.ignore_index = ignore_index; p.inv_T = inv_T;
   p.loss_part = reinterpret_cast<float*>(workspace);
   p.cnt_part = p.loss_part + tiles;
   p.blocks = p.cnt_part + tiles;

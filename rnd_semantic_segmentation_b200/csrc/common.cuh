@@ -158,6 +158,12 @@ __device__ __forceinline__ uint2 lds_v2u32(unsigned a) {
   asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
   return v;
 }
+__device__ __forceinline__ unsigned lds_u8(unsigned a) {
+  unsigned v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u8(unsigned a, unsigned v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_f32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ void smem_inc_u8(unsigned a) {      // thread-private byte counter += 1
   asm volatile("{ .reg .u32 t; ld.shared.u8 t, [%0]; add.u32 t, t, 1; st.shared.u8 [%0], t; }" ::"r"(a) : "memory");

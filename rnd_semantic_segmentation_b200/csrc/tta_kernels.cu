@@ -42,13 +42,24 @@ struct TtaParams {
   int n_div;               // 0, 1 or 2 scalar divisions after the sum
   int div_exact;           // 0: multiply by the fp32 reciprocal (ATen CUDA), 1: IEEE divide (ATen CPU)
   float div[2];
-  const long long* labels; // [H, W] or null
+  const void* labels;      // [H, W] int64 (or uint8 when label_u8) or null
   long long* cm;           // [C, C] or null (accumulated into)
-  long long* pred;         // [H, W] or null
+  void* pred;              // [H, W] int64 (or uint8 when pred_u8) or null
+  int label_u8, pred_u8;
   float* probs;            // [C, H, W] or null
 };
 
 __device__ __forceinline__ float tta_lerp(float wa, float a, float wb, float b) { return fmaf(wa, a, __fmul_rn(wb, b)); }
+
+// label / prediction maps in either element width (int64 as the reference passes them, or uint8 as the dataloader holds them)
+__device__ __forceinline__ long long tta_label(const TtaParams& p, long long pix) {
+  return p.label_u8 ? (long long)__ldg(reinterpret_cast<const unsigned char*>(p.labels) + pix)
+                    : ld_stream_s64(reinterpret_cast<const long long*>(p.labels) + pix);
+}
+__device__ __forceinline__ void tta_store_pred(const TtaParams& p, long long pix, int idx) {
+  if (p.pred_u8) reinterpret_cast<uint8_t*>(p.pred)[pix] = (uint8_t)idx;
+  else reinterpret_cast<long long*>(p.pred)[pix] = idx;
+}
 
 // v / s for every class with ONE reciprocal: r = rn(1/s); q = rn(v*r); q' = fma(fma(-q, s, v), r, q) is the correctly rounded
 // quotient (Markstein) as long as nothing is subnormal -- here s is in [1, 32] and v in (0, 1], so only a tiny v needs the generic
@@ -139,9 +150,9 @@ __device__ __forceinline__ void tta_finish(const TtaParams& p, float (&acc)[CT],
     for (int c = 0; c < CT; ++c)
       if (EXACT || c < C) __stcs(p.probs + c * plane + pix, acc[c]);
   }
-  if (p.pred) p.pred[pix] = idx;
+  if (p.pred) tta_store_pred(p, pix, idx);
   if (p.cm) {
-    const long long lab = ld_stream_s64(p.labels + pix);
+    const long long lab = tta_label(p, pix);
     if (lab != p.ignore_index && lab >= 0 && lab < C) atomicAdd(&hist[(int)lab * C + idx], 1);
   }
 }
@@ -255,9 +266,9 @@ __device__ __forceinline__ void tta_finish_fast(const TtaParams& p, const float 
   int idx = cand - 256;
   if (cand >= 512 || !(best == best)) idx = tta_exact_pixel<CT, EXACT>(p, C, x, y);       // near tie (or NaN): exact sequence
   const long long pix = (long long)y * p.W + x;
-  if (p.pred) p.pred[pix] = idx;
+  if (p.pred) tta_store_pred(p, pix, idx);
   if (p.cm) {
-    const long long lab = ld_stream_s64(p.labels + pix);
+    const long long lab = tta_label(p, pix);
     if (lab != p.ignore_index && lab >= 0 && lab < C) atomicAdd(&hist[(int)lab * C + idx], 1);
   }
 }
@@ -447,9 +458,11 @@ static int tta_rows_launch(const TtaParams& p, cudaStream_t stream) {
 }
 
 // logits[m]: fp32 [C, h[m], w[m]] (device pointers in a HOST array); flip[m] != 0: the member saw the mirrored image
-int tta_launch(const float* const* logits, const int* hs, const int* ws, const int* flips, int n_maps, int C, const long long* labels,
-               int H, int W, int ignore_index, const float* divisors, int n_div, int div_exact, long long* cm, long long* pred,
-               float* probs, cudaStream_t stream) {
+int tta_launch(const float* const* logits, const int* hs, const int* ws, const int* flips, int n_maps, int C, const void* labels,
+               int label_bytes, int H, int W, int ignore_index, const float* divisors, int n_div, int div_exact, long long* cm,
+               void* pred, int pred_bytes, float* probs, cudaStream_t stream) {
+  B200SEG_CHECK_ARG(labels == nullptr || label_bytes == 8 || label_bytes == 1, "tta_argmax_confusion: labels must be int64 or uint8");
+  B200SEG_CHECK_ARG(pred == nullptr || pred_bytes == 8 || pred_bytes == 1, "tta_argmax_confusion: pred must be int64 or uint8");
   B200SEG_CHECK_ARG(logits && hs && ws && flips, "tta_argmax_confusion: null member table");
   B200SEG_CHECK_ARG(n_maps >= 1 && n_maps <= TTA_MAX_MAPS, "tta_argmax_confusion: %d members (1..%d supported)", n_maps, TTA_MAX_MAPS);
   B200SEG_CHECK_ARG(C > 0 && C <= 32, "tta_argmax_confusion: num_classes=%d not in 1..32", C);
@@ -475,6 +488,7 @@ int tta_launch(const float* const* logits, const int* hs, const int* ws, const i
     p.div[k] = divisors[k];
   }
   p.labels = labels; p.cm = cm; p.pred = pred; p.probs = probs;
+  p.label_u8 = (label_bytes == 1); p.pred_u8 = (pred_bytes == 1);
   const long long units = (long long)ceil_div(W, TTA_THREADS) * H;
   const long long cap = (long long)num_sms() * 8;
   const int grid = (int)(units < cap ? units : cap);

@@ -33,11 +33,17 @@ class PixelDiscriminator(nn.Module):
         return [self.D[0].weight, self.D[0].bias, self.D[2].weight, self.D[2].bias,
                 self.cls1.weight, self.cls1.bias, self.cls2.weight, self.cls2.bias]
 
+    def invalidate_packed(self):
+        """Drop the cached bf16 weight pack (see ASPP_Classifier_V2.invalidate_packed)."""
+        self._packed = None
+        self._packed_key = None
+
     def _packed_weights(self):
-        """bf16 packed weights of the three layers, re-packed only when a parameter changed."""
+        """bf16 packed weights of the three layers: re-packed on every call in training mode (one launch; version counters
+        miss ``.data`` / raw-pointer / graph-replay writes), cached on (data_ptr, _version) in eval mode only."""
         params = self._params()
         key = tuple((p.data_ptr(), p._version) for p in params)
-        if self._packed is None or key != self._packed_key:
+        if self.training or self._packed is None or key != self._packed_key:
             w1, _, w2, _, wc1, bc1, wc2, bc2 = params
             self._packed = ops.pack_discriminator_weights(w1, w2, wc1, wc2, bc1, bc2)
             self._packed_key = key

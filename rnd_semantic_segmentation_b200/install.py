@@ -29,18 +29,34 @@ _stock_optimizers = {}
 
 
 def _optimizer_factory(stock, fused):
-    """``torch.optim.SGD(...)``-compatible callable: the fused subclass for all-CUDA fp32 parameter sets, the stock class otherwise
-    (the backbone's optimizer_fea is one of those calls too; it takes the fused path just the same when it is on the GPU)."""
+    """A CLASS that stands in for ``torch.optim.SGD`` / ``torch.optim.Adam``: constructing it builds the fused subclass for
+    all-CUDA fp32 parameter sets and the stock class otherwise (the backbone's optimizer_fea is one of those calls too; it takes
+    the fused path just the same when it is on the GPU).  It stays a type: ``isinstance(opt, torch.optim.SGD)`` and
+    ``issubclass`` answer as for the stock class, and ``class X(torch.optim.SGD)`` keeps working (a subclass constructs itself
+    normally, on the stock implementation)."""
 
-    def make(params, *args, **kwargs):
+    class _Meta(type(stock)):
+        def __instancecheck__(cls, obj):
+            return isinstance(obj, stock) if cls is dispatch_holder[0] else type.__instancecheck__(cls, obj)
+
+        def __subclasscheck__(cls, sub):
+            return issubclass(sub, stock) if cls is dispatch_holder[0] else type.__subclasscheck__(cls, sub)
+
+    dispatch_holder = [None]
+
+    def __new__(cls, params=None, *args, **kwargs):
+        if cls is not dispatch_holder[0]:                      # a user subclass: ordinary construction
+            return stock.__new__(cls)
         params = list(params)
         flat = [p for g in params for p in g["params"]] if params and isinstance(params[0], dict) else params
         if flat and all(isinstance(p, torch.Tensor) and p.is_cuda and p.dtype == torch.float32 for p in flat):
             return fused(params, *args, **kwargs)
-        return stock(params, *args, **kwargs)
+        return stock(params, *args, **kwargs)                  # neither result is an instance of `cls`: no second __init__
 
-    make.__wrapped__ = stock
-    return make
+    dispatch = _Meta(stock.__name__, (stock,), {"__new__": __new__, "__wrapped__": stock, "__module__": stock.__module__,
+                                                "__doc__": stock.__doc__})
+    dispatch_holder[0] = dispatch
+    return dispatch
 
 
 def install_optimizers():

@@ -13,10 +13,12 @@ from . import _lib
 # --------------------------------------------------------------------------------------------
 # The same feature tensor is consumed by several modules per iteration (FADA: classifier(tgt_fea) and model_D(tgt_fea),
 # classifier(src_fea) and model_D(src_fea.detach()), aspp_fada.py:91-123), and each would convert it to the bf16 pixel-major
-# GEMM operand again (an HBM pass of 12 B per element).  A small LRU keeps the last conversions.  An entry holds a reference
-# to the source storage (through a detached alias), so its address cannot be handed to another tensor while the entry lives,
-# and it is keyed on the version counter, so any in-place update through torch invalidates it.
-_PACK_CACHE_SLOTS = 2
+# GEMM operand again (an HBM pass of 12 B per element).  An OPT-IN LRU (``set_feature_pack_cache(n)``, default off) keeps the
+# last conversions.  An entry holds a reference to the source storage (through a detached alias), so its address cannot be
+# handed to another tensor while the entry lives, and it is keyed on the version counter, so any in-place update through
+# torch invalidates it -- but NOT writes through ``.data``, raw pointers or CUDA-graph replays into a static buffer, which is
+# why it is off unless the caller (who knows how the features are produced) turns it on; it also pins the fp32 sources.
+_PACK_CACHE_SLOTS = 0
 _pack_cache = []            # [(key, source alias, Xp)]
 
 
@@ -161,8 +163,7 @@ def aspp_head_loss(x, labels, weights, biases, rates, ignore_index=255, temperat
     """(loss, low-res logits [detached]) == CrossEntropyLoss(ignore_index)(interpolate(head(x), labels.shape[-2:]) / T, labels).
     ``grad_bucket`` (distributed.HeadGradBucket): write the parameter gradients into the bucket and overlap its all-reduce
     with the data-gradient GEMM instead of returning them through autograd."""
-    if labels.dtype != torch.int64:
-        labels = labels.long()
+    labels = _lib.as_label_tensor(labels)            # int64 or uint8 as they are; anything else widened to int64
     return _AsppHeadLossFn.apply(x, labels, int(ignore_index), float(temperature), tuple(int(r) for r in rates), packed,
                                  grad_bucket, *weights, *biases)
 
@@ -285,8 +286,7 @@ def upsample_cross_entropy(logits_lr: torch.Tensor, labels: torch.Tensor, ignore
                            temperature: float = 1.0) -> torch.Tensor:
     """CrossEntropyLoss(ignore_index)(interpolate(logits_lr, labels.shape[-2:]) / temperature, labels) without
     materialising the full-resolution logits (aspp_trainer.py:88-92, aspp_fada.py:91-96)."""
-    if labels.dtype != torch.int64:
-        labels = labels.long()
+    labels = _lib.as_label_tensor(labels)
     return _UpsampleCEFn.apply(logits_lr, labels, int(ignore_index), float(temperature))
 
 

@@ -81,12 +81,11 @@ def iutr_from_confusion(cm: torch.Tensor):
 
 
 def segmentation_eval_step(logits_lr: torch.Tensor, labels: torch.Tensor, ignore_index: int = 255,
-                           cm: Optional[torch.Tensor] = None, per_frame: bool = False, want_pred: bool = False):
+                           cm: Optional[torch.Tensor] = None, per_frame: bool = False, want_pred=False):
     """One launch for the whole post-head part of aspp_tester.py:60-72: align-corners upsample to
     ``labels.shape[-2:]``, softmax, argmax (first index on ties, bit-exact with the reference on CUDA)
     and the C x C int64 confusion matrix accumulated into ``cm``.  Returns (cm, pred or None)."""
-    if labels.dtype != torch.int64:
-        labels = labels.long()
+    labels = _lib.as_label_tensor(labels)              # int64 or uint8 consumed as they are
     return _lib.upsample_argmax_confusion(logits_lr.float().contiguous(), labels.contiguous(), labels.shape[-2:],
                                           ignore_index=ignore_index, cm=cm, per_frame=per_frame, want_pred=want_pred)
 
@@ -138,7 +137,11 @@ _pred_cache = weakref.WeakValueDictionary()
 
 
 class _PredRecord:
-    __slots__ = ("pred", "labels_ptr", "cm", "ignore_index", "__weakref__")
+    """What LazyProbabilities.max() remembers about the prediction it returned: identity (storage address, element count),
+    the version counters of the prediction and of the labels at that moment, and the matrix of the same launch.  The record
+    holds NO reference to the prediction tensor (the tensor holds the record, not the other way round: no reference cycle,
+    the frame's tensors are freed by refcount as soon as the tester drops them)."""
+    __slots__ = ("pred_numel", "pred_version", "labels_ptr", "labels_version", "labels_ref", "cm", "ignore_index", "__weakref__")
 
 
 class LazyProbabilities:
@@ -189,7 +192,7 @@ class LazyProbabilities:
     def max(self, dim=None, keepdim=False):
         if dim != 1 or keepdim:
             return self.materialize().max(dim, keepdim) if dim is not None else self.materialize().max()
-        labels = self.label if self.label.dtype == torch.int64 else self.label.long()
+        labels = _lib.as_label_tensor(self.label)
         labels = labels.reshape(self.logits_lr.shape[0], *labels.shape[-2:]).contiguous()
         if self.is_ensemble:
             cm, pred, _ = _lib.tta_argmax_confusion(self._members32(), self.flips, labels.shape[-2:], labels=labels,
@@ -199,7 +202,10 @@ class LazyProbabilities:
             cm, pred = _lib.upsample_argmax_confusion(self.logits_lr, labels, labels.shape[-2:],
                                                       ignore_index=self.ignore_index, per_frame=False, want_pred=True)
         rec = _PredRecord()
-        rec.pred, rec.labels_ptr, rec.cm, rec.ignore_index = pred, labels.data_ptr(), cm, self.ignore_index
+        rec.pred_numel, rec.pred_version = pred.numel(), pred._version
+        # (the reshaped ``labels`` is a temporary view; views share storage and version counter with the caller's tensor)
+        rec.labels_ptr, rec.labels_version, rec.labels_ref = labels.data_ptr(), labels._version, weakref.ref(self.label)
+        rec.cm, rec.ignore_index = cm, self.ignore_index
         _pred_cache[pred.data_ptr()] = rec
         pred._b200seg_record = rec          # keeps the record alive exactly as long as the prediction tensor
         return None, pred
@@ -208,6 +214,17 @@ class LazyProbabilities:
         if dim == 1 and not keepdim:
             return self.max(1)[1]
         return self.materialize().argmax(dim, keepdim)
+
+    def label_map(self, dtype=torch.uint8) -> torch.Tensor:
+        """[H,W] argmax labels written by the fused kernel directly in ``dtype`` (uint8: the pseudo-label format of
+        aspp_tester.py:40-45 -- 1 byte per pixel leaves the kernel instead of an int64 map that is narrowed afterwards).  No
+        confusion matrix, the ground truth is not read."""
+        size = self.label.shape[-2:]
+        if self.is_ensemble:
+            _, pred, _ = _lib.tta_argmax_confusion(self._members32(), self.flips, size, divisors=self.divisors, want_pred=dtype)
+            return pred
+        _, pred = _lib.upsample_argmax_confusion(self.logits_lr.detach().float().contiguous(), None, size, want_pred=dtype)
+        return pred[0]
 
     def cpu(self):
         return self.materialize().cpu()
@@ -258,7 +275,9 @@ def pseudo_label_map(output) -> np.ndarray:
     """H x W uint8 label map of a (lazy or real) [1,C,H,W] probability tensor: what ``save_distill`` (aspp_tester.py:40-42)
     derives with ``output.cpu().numpy().squeeze().argmax(0)`` -- but through the fused argmax, so 2 MB of labels cross PCIe
     instead of the 159 MB probability tensor (first index on ties in both)."""
-    pred = output.max(1)[1] if isinstance(output, LazyProbabilities) else torch.as_tensor(output).max(1)[1]
+    if isinstance(output, LazyProbabilities):
+        return output.label_map(torch.uint8).cpu().numpy()
+    pred = torch.as_tensor(output).max(1)[1]
     return pred.reshape(pred.shape[-2:]).to(torch.uint8).cpu().numpy()
 
 
@@ -278,10 +297,18 @@ def save_pseudo_label(output, path: str, palette):
 
 
 def _cached_record(pd: torch.Tensor, gt: torch.Tensor):
+    """The record of ``pd`` if it is still the untouched prediction of LazyProbabilities.max() against these very labels:
+    same storage, same element count, and NEITHER tensor edited in place since (version counters; views share them, so
+    ``pred.flatten()`` / ``y.flatten()`` as the tester passes them qualify).  The reference recounts from the tensors it is
+    given, so any in-place edit (id remapping, masking) must invalidate the memo.  intersectionAndUnionGPU's own raw-pointer
+    write of ignore_index does not bump the version and only touches pixels the matrix skips anyway."""
     rec = _pred_cache.get(pd.data_ptr())
-    if rec is None or rec.pred.numel() != pd.numel():
+    if rec is None or rec.pred_numel != pd.numel() or rec.pred_version != pd._version:
         return None
-    if gt.data_ptr() != rec.labels_ptr:
+    if gt.data_ptr() != rec.labels_ptr or gt.numel() != pd.numel():
+        return None
+    lab = rec.labels_ref()
+    if lab is None or lab._version != rec.labels_version or gt._version != rec.labels_version:
         return None
     return rec
 
@@ -299,7 +326,8 @@ def confusion_matrix(cfg, pd, gt):
     rec = _cached_record(pd, gt)
     if rec is not None and rec.ignore_index == 255 and rec.cm.shape[-1] == num_classes:
         return rec.cm.cpu()
-    cm = _lib.confusion_from_pred(pd.reshape(-1).long().contiguous(), gt.reshape(-1).long().contiguous(), num_classes, 255)
+    cm = _lib.confusion_from_pred(_lib.as_label_tensor(pd.reshape(-1)).contiguous(), _lib.as_label_tensor(gt.reshape(-1)).contiguous(),
+                                  num_classes, 255)
     return cm.cpu()
 
 
@@ -311,13 +339,13 @@ def intersectionAndUnionGPU(output, target, K, ignore_index=255):
     if not output.is_cuda:
         raise _lib.B200SegError("intersectionAndUnionGPU: expected CUDA tensors (b200seg has no CPU fallback)")
     out_flat = output.view(-1)
-    tgt_flat = target.reshape(-1)
-    if out_flat.dtype != torch.int64 or tgt_flat.dtype != torch.int64 or not tgt_flat.is_contiguous():
+    tgt_flat = _lib.as_label_tensor(target.reshape(-1)).contiguous()
+    if out_flat.dtype not in _lib.LABEL_DTYPES:
         work = out_flat.long().contiguous()
-        cm = _lib.confusion_from_pred(work, tgt_flat.long().contiguous(), K, ignore_index, mutate_pd=True)
+        cm = _lib.confusion_from_pred(work, tgt_flat, K, ignore_index, mutate_pd=True)
         out_flat.copy_(work.to(out_flat.dtype))
     else:
-        cm = _lib.confusion_from_pred(out_flat, tgt_flat, K, ignore_index, mutate_pd=True)
+        cm = _lib.confusion_from_pred(out_flat, tgt_flat, K, ignore_index, mutate_pd=True)       # int64 / uint8 maps, any mix
     i, u, t, o = iutr_from_confusion(cm)
     return i.float(), u.float(), t.float(), o.float()
 

@@ -493,30 +493,44 @@ def test_discriminator_stack_forward_backward(lib, n, cin, ndf, C, h, w):
     xc = x.cuda().requires_grad_(True)
     got = ours(xc)
     assert tuple(got.shape) == (n, 2 * C, h, w)
-    # the sign masks of the stored activations (recomputed through the same layer calls)
+    # INDEPENDENT oracle: its LeakyReLU branches follow its OWN fp64 pre-activations (no mask is taken from the CUDA path).
+    # The CUDA stack derives the backward slope from the sign of its stored bf16 activation; the two can only disagree where a
+    # pre-activation lies within fp32-accumulation distance (~1e-6 relative) of zero.  Count those disagreements against the
+    # activations the CUDA layers store, and bound them: none is expected at these sizes (P ~ 1e-6 per element).
+    refd = copy.deepcopy(ref).double()
+    xr = x.double().requires_grad_(True)
+    want = discriminator_bf16_oracle(refd, xr, None)
     with torch.no_grad():
         (Wf1, _), (Wf2, _), _, _ = ours._packed_weights()
         A1 = lib.conv3x3_forward(_nhwc_bf16(x), Wf1, ours.D[0].bias.detach(), 0.2)
         A2 = lib.conv3x3_forward(A1, Wf2, ours.D[2].bias.detach(), 0.2)
-    masks = (_nchw(A1) > 0, _nchw(A2) > 0)
-    refd = copy.deepcopy(ref).double()
-    xr = x.double().requires_grad_(True)
-    want = discriminator_bf16_oracle(refd, xr, masks)
+        r = lambda t: bf16_round(t.float()).double()  # noqa: E731
+        z1 = F.conv2d(r(x.double()), r(refd.D[0].weight), refd.D[0].bias, padding=1)
+        a1 = r(F.leaky_relu(z1, 0.2))
+        z2 = F.conv2d(a1, r(refd.D[2].weight), refd.D[2].bias, padding=1)
+        flips = int(((_nchw(A1) > 0) != (z1 > 0)).sum()) + int(((_nchw(A2) > 0) != (z2 > 0)).sum())
+        n_act = z1.numel() + z2.numel()
+    print(f"LeakyReLU sign disagreements CUDA vs independent fp64 oracle: {flips} of {n_act} pre-activations")
+    assert flips <= max(2, int(1e-5 * n_act)), (flips, n_act)
     assert rel_err(got, want) <= STACK_TOL
     print("D logits rel err vs same-rounding oracle:", rel_err(got, want), " vs fp32 reference module:", rel_err(got, ref(x)))
     assert rel_err(got, ref(x)) <= 2e-2
     want.backward(go.double())
     got.backward(go.cuda())
-    assert rel_err(xc.grad, xr.grad) <= STACK_TOL
+    # with no sign disagreement the un-masked comparison holds at the chain tolerance; each disagreement changes one element of
+    # an inter-layer gradient by the slope ratio, so then the bound is stated in L2
+    grad_ok = (lambda a, b: rel_err(a, b) <= STACK_TOL) if flips == 0 else \
+        (lambda a, b: ((a.detach().double().cpu() - b.double()).norm() / b.double().norm()).item() <= STACK_TOL)
+    assert grad_ok(xc.grad, xr.grad)
     for (name, p_ref), (_, p_ours) in zip(refd.named_parameters(), ours.named_parameters()):
-        assert rel_err(p_ours.grad, p_ref.grad) <= STACK_TOL, name
+        assert grad_ok(p_ours.grad, p_ref.grad), name
     # weights-only backward (the discriminator's own update on detached features, aspp_fada.py:119-125) and determinism
     ours.zero_grad()
     out2 = ours(x.cuda())
     out2.backward(go.cuda())
     g_first = [p.grad.clone() for p in ours.parameters()]
     for p_ours, (name, p_ref) in zip(ours.parameters(), refd.named_parameters()):
-        assert rel_err(p_ours.grad, p_ref.grad) <= STACK_TOL, name
+        assert grad_ok(p_ours.grad, p_ref.grad), name
     ours.zero_grad()
     ours(x.cuda()).backward(go.cuda())
     assert all(torch.equal(a, p.grad) for a, p in zip(g_first, ours.parameters()))
@@ -721,7 +735,7 @@ def test_cuda_graph_capture_train_eval_and_discriminator(lib):
             for a, b in zip(got, want):
                 assert torch.equal(a, b)
     finally:
-        b200.set_feature_pack_cache(2)
+        b200.set_feature_pack_cache(0)
 
 
 def test_overlapped_evaluator_bit_exact(lib):

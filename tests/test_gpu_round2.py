@@ -1,0 +1,375 @@
+"""-m gpu parity tests added in round 2:
+
+* the full-size BASELINE.json configs through the CUDA path against the CPU oracle (cfg1 incl. the survey's anchor
+  known-answer 4.04814, cfg2 kvasir, cfg3 the whole aspp_fada.py:91-125 iteration at 4 x 2048 x 64 x 128);
+* the two reference-generated fixtures no GPU test loaded before (soft_ce.npz, head_all_ignored.npz);
+* uint8 label / prediction maps bit-exact against the int64 path for K2 / K4 / K7 / confusion_from_pred,
+  and the several-frames-per-launch form of K4.
+
+Bars as in test_gpu_parity.py: bit-exact for integer results; <= 1e-3 (max-abs / max-abs) against the oracle fed the same
+bf16-rounded operands; 5e-3 (loss, logits) / 1e-2 (gradients) against the reference's un-rounded fp32 numbers."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import RATES, bf16_round, effective_bf16_head, make_labels, rel_err
+from oracle import torch_oracle as to
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from rnd_semantic_segmentation_b200 import _lib
+    _lib.load()
+    return _lib
+
+
+def _l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+
+# ------------------------------------------------------------------ full-size BASELINE configs against the CPU oracle
+def test_cfg1_full_size_anchor_known_answer_and_gradients(lib):
+    """BASELINE.json configs[0] (deeplabv2_r101_src, 2 x 2048 x 65 x 129 -> 512 x 1024, C = 19) with the survey's anchor inputs
+    (torch.manual_seed(0) ...) through ``forward_loss``: the loss must reproduce the reference's known answer
+    4.04814 to the bf16-operand bar (5e-3), and loss / low-res logits / every gradient must match the CPU oracle fed the same
+    bf16-rounded operands (fp32 math on the host cores, as aspp_trainer.py:88-92 computes them) to 1e-3."""
+    import rnd_semantic_segmentation_b200 as b200
+    torch.manual_seed(0)
+    ref = to.AsppHeadOracle(2048, RATES, RATES, 19)
+    x = torch.randn(2, 2048, 65, 129)
+    lab = torch.randint(0, 19, (2, 512, 1024))
+    lab[torch.rand(2, 512, 1024) < 0.1] = 255
+    head = b200.ASPP_Classifier_V2(2048, RATES, RATES, 19)
+    head.load_state_dict(ref.state_dict())
+    head.cuda()
+    xc = x.cuda().requires_grad_(True)
+    loss, logits_lr = head.forward_loss(xc, lab.cuda())
+    loss.backward()
+    assert abs(loss.item() - 4.04814) <= 5e-3 * 4.04814, loss.item()
+    # same-rounding oracle: bf16-rounded features and packed weights, fp32 arithmetic on the CPU
+    eff = effective_bf16_head(ref)
+    xr = bf16_round(x).requires_grad_(True)
+    want_lr = eff(xr)
+    want = to.hard_cross_entropy(to.upsample_bilinear_ac(want_lr, (512, 1024)), lab)
+    want.backward()
+    print("cfg1 loss", loss.item(), "same-rounding oracle", want.item(), "anchor 4.04814")
+    assert abs(loss.item() - want.item()) <= TOL * abs(want.item())
+    assert rel_err(logits_lr, want_lr) <= TOL
+    # the CUDA path rounds the low-res loss gradient to bf16 before its two GEMMs (the oracle does not): bf16 half-ulp = 2^-9
+    # on the operand, which averages out over the 16 770-pixel / 684-tap contractions
+    assert rel_err(xc.grad, xr.grad) <= 2e-3 and _l2(xc.grad, xr.grad) <= 2e-3
+    centre = eff.conv2d_list[0].weight.grad[:, :, 1, 1]
+    for i, (m_ref, m_ours) in enumerate(zip(eff.conv2d_list, head.conv2d_list)):
+        wg = m_ref.weight.grad.clone()
+        wg[:, :, 1, 1] = centre                                        # eff carries the shared centre tap on branch 0 only
+        assert rel_err(m_ours.weight.grad, wg) <= 2e-3 and _l2(m_ours.weight.grad, wg) <= 2e-3, f"branch {i}"
+        assert rel_err(m_ours.bias.grad, eff.conv2d_list[0].bias.grad) <= 1e-4
+    # and the API-compat path (materialised logits + the caller's own criterion) sees the same loss
+    out = head(x.cuda(), (512, 1024))
+    l2 = F.cross_entropy(out, lab.cuda(), ignore_index=255)
+    assert abs(l2.item() - loss.item()) <= 1e-4 * abs(loss.item())
+
+
+def test_cfg2_kvasir_full_size(lib):
+    """BASELINE.json configs[1] (deeplabv2_r101_src_kvasir: 16 x 2048 x 44 x 44 -> 352 x 352, C = 2, 5 % ignored) against the
+    same-rounding CPU oracle at 1e-3 and the un-rounded fp32 oracle at the bf16 bar."""
+    import rnd_semantic_segmentation_b200 as b200
+    from rnd_semantic_segmentation_b200 import synth
+    n, cin, h, w, H, W, C = synth.WORKLOADS["deeplabv2_r101_src_kvasir"]
+    torch.manual_seed(2)
+    ref = to.AsppHeadOracle(cin, RATES, RATES, C)
+    head = b200.ASPP_Classifier_V2(cin, RATES, RATES, C)
+    head.load_state_dict(ref.state_dict())
+    head.cuda()
+    x = synth.make_features(n, cin, h, w, seed=21)
+    lab = synth.make_labels(n, H, W, C, p_ignore=0.05, seed=22)
+    xc = x.cuda().requires_grad_(True)
+    loss, logits_lr = head.forward_loss(xc, lab.cuda())
+    loss.backward()
+    eff = effective_bf16_head(ref)
+    xr = bf16_round(x).requires_grad_(True)
+    want_lr = eff(xr)
+    want = to.hard_cross_entropy(to.upsample_bilinear_ac(want_lr, (H, W)), lab)
+    want.backward()
+    assert abs(loss.item() - want.item()) <= TOL * abs(want.item())
+    assert rel_err(logits_lr, want_lr) <= TOL
+    assert rel_err(xc.grad, xr.grad) <= 2e-3 and _l2(xc.grad, xr.grad) <= 2e-3
+    for i, (m_ref, m_ours) in enumerate(zip(eff.conv2d_list, head.conv2d_list)):
+        wg = m_ref.weight.grad.clone()
+        wg[:, :, 1, 1] = eff.conv2d_list[0].weight.grad[:, :, 1, 1]
+        assert rel_err(m_ours.weight.grad, wg) <= 2e-3, f"branch {i}"
+    want_fp32 = to.train_step_src(ref, x, lab)[0]
+    assert abs(loss.item() - want_fp32.item()) <= 5e-3 * abs(want_fp32.item())
+
+
+def test_cfg3_full_size_fada_iteration(lib):
+    """BASELINE.json configs[2] (deeplabv2_r101_adv) at FULL size: 4 + 4 feature maps 2048 x 64 x 128 -> 512 x 1024, C = 19,
+    PixelDiscriminator(2048, 256): everything after the backbone of aspp_fada.py:91-125 through the fused entry points against
+    ``oracle.fada_step`` on the host cores (un-rounded fp32): the four losses at the bf16 bar (5e-3) and every parameter
+    gradient in L2 (head 1e-2; discriminator 3e-2 -- bf16 operands AND bf16 stored activations through three layers)."""
+    import rnd_semantic_segmentation_b200 as b200
+    from rnd_semantic_segmentation_b200 import synth
+    n, cin, h, w, H, W, C = synth.WORKLOADS["deeplabv2_r101_adv"]
+    torch.manual_seed(4321)
+    ref_head = to.AsppHeadOracle(cin, RATES, RATES, C)
+    ref_D = to.PixelDiscriminatorOracle(cin, 256, num_classes=C)
+    head = b200.ASPP_Classifier_V2(cin, RATES, RATES, C)
+    head.load_state_dict(ref_head.state_dict())
+    D = b200.PixelDiscriminator(cin, 256, num_classes=C)
+    D.load_state_dict(ref_D.state_dict())
+    head.cuda(), D.cuda()
+    src = synth.make_features(n, cin, h, w, seed=555)
+    tgt = synth.make_features(n, cin, h, w, seed=777)
+    lab = synth.make_labels(n, H, W, C, seed=555)
+    want = to.fada_step(ref_head, ref_D, src, tgt, lab)
+    size = (H, W)
+    src_fea, tgt_fea = src.cuda().requires_grad_(True), tgt.cuda().requires_grad_(True)
+    loss_seg, src_lr = head.forward_loss(src_fea, lab.cuda(), temperature=1.8)
+    loss_seg.backward()
+    with torch.no_grad():
+        tgt_lr = head.logits(tgt_fea)
+    loss_adv = 0.001 * D.forward_soft_loss(tgt_fea, tgt_lr, size, slot=0)
+    loss_adv.backward()
+    D.zero_grad()
+    loss_d_src = 0.5 * D.forward_soft_loss(src_fea.detach(), src_lr, size, slot=0)
+    loss_d_src.backward()
+    loss_d_tgt = 0.5 * D.forward_soft_loss(tgt_fea.detach(), tgt_lr, size, slot=1)
+    loss_d_tgt.backward()
+    for name, got, exp in zip(("seg", "adv_tgt", "D_src", "D_tgt"), (loss_seg, loss_adv, loss_d_src, loss_d_tgt), want):
+        print("cfg3", name, got.item(), exp.item())
+        assert abs(got.item() - exp.item()) <= 5e-3 * abs(exp.item()), (name, got.item(), exp.item())
+    for (name, p), pr in zip(head.named_parameters(), ref_head.parameters()):
+        assert _l2(p.grad, pr.grad) <= 1e-2, (name, _l2(p.grad, pr.grad))
+    for (name, p), pr in zip(D.named_parameters(), ref_D.parameters()):
+        assert _l2(p.grad, pr.grad) <= 3e-2, (name, _l2(p.grad, pr.grad))
+
+
+# ------------------------------------------------------------------ reference-generated fixtures not loaded before
+def test_k3_soft_ce_against_reference_golden(lib, golden):
+    """soft_ce.npz: outputs of the reference's own soft_label_cross_entropy (utility.py:172-177), with and without pixel weights."""
+    import rnd_semantic_segmentation_b200 as b200
+    g = golden("soft_ce")
+    soft = torch.from_numpy(g["soft"]).cuda()
+    for wkey, lkey, gkey in ((None, "loss", "grad"), ("weights", "loss_w", "grad_w")):
+        pred = torch.from_numpy(g["pred"]).cuda().requires_grad_(True)
+        wts = None if wkey is None else torch.from_numpy(g[wkey]).cuda()
+        loss = b200.soft_label_cross_entropy(pred, soft, wts)
+        loss.backward()
+        assert abs(loss.item() - float(g[lkey])) <= TOL * abs(float(g[lkey]))
+        assert rel_err(pred.grad, torch.from_numpy(g[gkey])) <= TOL
+
+
+def test_head_all_ignored_against_reference_golden(lib, golden):
+    """head_all_ignored.npz: every label is 255 -> the reference's CrossEntropyLoss returns NaN (a4); so must both our paths."""
+    import rnd_semantic_segmentation_b200 as b200
+    g = golden("head_all_ignored")
+    assert np.isnan(g["loss"])
+    C = int(g["num_classes"])
+    x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    labels = torch.from_numpy(g["labels"]).cuda()
+    head = b200.ASPP_Classifier_V2(x.shape[1], RATES, RATES, C)
+    head.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd.")})
+    head.cuda()
+    loss, _ = head.forward_loss(x, labels)
+    assert torch.isnan(loss)
+    assert torch.isnan(F.cross_entropy(head(x.detach(), labels.shape[-2:]), labels, ignore_index=255))
+    assert torch.isnan(head.forward_loss(x, labels.to(torch.uint8))[0])
+
+
+# ------------------------------------------------------------------ uint8 labels (second half)
+@pytest.mark.parametrize("n,C,h,w,H,W", [(1, 19, 128, 256, 1024, 2048), (2, 19, 65, 129, 512, 1024), (3, 2, 44, 44, 352, 352),
+                                        (1, 7, 9, 11, 50, 70), (2, 19, 33, 17, 100, 131), (1, 30, 8, 8, 64, 64)])
+def test_k4_uint8_labels_and_predictions_bit_exact(lib, n, C, h, w, H, W):
+    """K4 fed the uint8 label tensor the dataloader holds (core/datasets/transform.py:31-33) instead of the tester's .long()
+    copy (aspp_tester.py:58): identical int64 matrix; uint8 prediction output == the int64 one; both == torch CUDA ops."""
+    g = torch.Generator().manual_seed(500 + C + h)
+    logits = torch.randn(n, C, h, w, generator=g).cuda()
+    lab64 = make_labels(n, H, W, C, 0.1, 501 + h).cuda()
+    lab8 = lab64.to(torch.uint8)
+    cm64, pred64 = lib.upsample_argmax_confusion(logits, lab64, (H, W), want_pred=True, per_frame=True)
+    cm8, pred8 = lib.upsample_argmax_confusion(logits, lab8, (H, W), want_pred=torch.uint8, per_frame=True)
+    assert pred8.dtype == torch.uint8 and torch.equal(pred8.long(), pred64)
+    assert torch.equal(cm8, cm64)
+    want_pred = to.eval_argmax(logits, (H, W))
+    assert torch.equal(pred64, want_pred)
+    for f in range(n):
+        assert torch.equal(cm8[f].cpu(), to.confusion_matrix_bincount(C, want_pred[f].flatten(), lab64[f].flatten()).cpu())
+    # prediction only (no labels), uint8
+    _, p_only = lib.upsample_argmax_confusion(logits, None, (H, W), want_pred=torch.uint8)
+    assert torch.equal(p_only, pred8)
+
+
+@pytest.mark.parametrize("F_,C,h,w,H,W", [(8, 19, 128, 256, 1024, 2048), (19, 19, 16, 32, 128, 256), (3, 2, 44, 44, 352, 352)])
+@pytest.mark.parametrize("ldtype", [torch.int64, torch.uint8])
+def test_k4_frames_per_launch_equals_single_frame_calls(lib, F_, C, h, w, H, W, ldtype):
+    """Several tester-loop frames (separate tensors, no concatenation) in one launch: same matrices / predictions as one call
+    per frame; more than 16 frames split into consecutive launches."""
+    g = torch.Generator().manual_seed(600 + F_)
+    logits = [torch.randn(1, C, h, w, generator=g).cuda() for _ in range(F_)]
+    labels = [make_labels(1, H, W, C, 0.1, 601 + f)[0].cuda().to(ldtype) for f in range(F_)]
+    cm_f, preds = lib.upsample_argmax_confusion_frames(logits, labels, (H, W), per_frame=True, want_pred=True)
+    cm_sum, _ = lib.upsample_argmax_confusion_frames(logits, labels, (H, W))
+    total = torch.zeros(C, C, dtype=torch.int64, device="cuda")
+    for f in range(F_):
+        cm1, p1 = lib.upsample_argmax_confusion(logits[f], labels[f].unsqueeze(0), (H, W), want_pred=True)
+        assert torch.equal(cm_f[f], cm1) and torch.equal(preds[f], p1[0])
+        total += cm1
+    assert torch.equal(cm_sum, total)
+    assert int(total.sum()) == sum(int((lb != 255).sum()) for lb in labels)
+
+
+@pytest.mark.parametrize("n,C,h,w,H,W,T", [(2, 19, 65, 129, 512, 1024, 1.0), (1, 19, 64, 128, 512, 1024, 1.8), (3, 2, 44, 44, 352, 352, 1.0),
+                                          (1, 7, 9, 11, 50, 70, 1.0), (2, 19, 33, 17, 100, 131, 1.8), (1, 19, 16, 16, 16, 16, 1.0)])
+def test_k2_uint8_labels_bit_identical_to_int64(lib, n, C, h, w, H, W, T):
+    """K2 with uint8 labels (no .long() at aspp_trainer.py:86): loss and low-res gradient bit-identical to the int64 path."""
+    from rnd_semantic_segmentation_b200 import ops
+    g = torch.Generator().manual_seed(700 + C + h)
+    logits = (2.0 * torch.randn(n, C, h, w, generator=g)).cuda()
+    lab64 = make_labels(n, H, W, C, 0.1, 701 + h).cuda()
+    outs = []
+    for lab in (lab64, lab64.to(torch.uint8)):
+        x = logits.clone().requires_grad_(True)
+        loss = ops.upsample_cross_entropy(x, lab, 255, T)
+        loss.backward()
+        outs.append((loss.detach(), x.grad))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    want = to.hard_cross_entropy(to.upsample_bilinear_ac(logits, (H, W)).div(T), lab64)
+    assert abs(outs[1][0].item() - want.item()) <= TOL * abs(want.item())
+
+
+def test_head_forward_loss_uint8_labels(lib):
+    """The fused train slice (head -> upsample + CE -> backward) with uint8 labels: bit-identical to int64 labels."""
+    import rnd_semantic_segmentation_b200 as b200
+    torch.manual_seed(8)
+    head = b200.ASPP_Classifier_V2(256, RATES, RATES, 19).cuda()
+    x = torch.relu(torch.randn(2, 256, 33, 65, generator=torch.Generator().manual_seed(9))).cuda()
+    lab64 = make_labels(2, 264, 520, 19, 0.1, 10).cuda()
+    res = []
+    for lab in (lab64, lab64.to(torch.uint8)):
+        head.zero_grad()
+        xg = x.clone().requires_grad_(True)
+        loss, lg = head.forward_loss(xg, lab)
+        loss.backward()
+        res.append([loss.detach(), lg, xg.grad] + [p.grad.clone() for p in head.parameters()])
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("C,shapes,flips,divisors,H,W", [
+    (19, [(128, 256), (128, 256)], [False, True], (2,), 1024, 2048),
+    (19, [(23, 45), (33, 65), (43, 84), (23, 45), (33, 65), (43, 84)], [False] * 3 + [True] * 3, (3, 2), 260, 517),
+    (2, [(44, 44), (44, 44)], [False, True], (2,), 352, 352),
+])
+def test_k7_uint8_labels_and_predictions(lib, C, shapes, flips, divisors, H, W):
+    g = torch.Generator().manual_seed(800 + C + len(shapes))
+    members = [torch.randn(1, C, a, b, generator=g).cuda() for a, b in shapes]
+    lab64 = make_labels(1, H, W, C, 0.1, 801).cuda()
+    cm64, p64, _ = lib.tta_argmax_confusion(members, flips, (H, W), labels=lab64, divisors=divisors, want_pred=True)
+    cm8, p8, _ = lib.tta_argmax_confusion(members, flips, (H, W), labels=lab64.to(torch.uint8), divisors=divisors, want_pred=torch.uint8)
+    assert p8.dtype == torch.uint8 and torch.equal(p8.long(), p64) and torch.equal(cm8, cm64)
+    want = to.tta_probabilities(members, flips, (H, W), divisors).max(1)[1]
+    assert torch.equal(p64.unsqueeze(0), want)
+
+
+@pytest.mark.parametrize("C", [2, 19, 30])
+@pytest.mark.parametrize("n", [77 * 91 * 3, 1024 * 2048, 13])
+def test_confusion_from_pred_mixed_widths(lib, C, n):
+    """confusion_matrix(cfg, pd, gt) / intersectionAndUnionGPU on int64 / uint8 maps in every combination (odd lengths and
+    unaligned views included): identical matrices, identical in-place ignore marking."""
+    g = torch.Generator().manual_seed(900 + C)
+    pd = torch.randint(0, C, (n + 3,), generator=g).cuda()
+    gt = make_labels(1, 1, n + 3, C, 0.2, 901)[0, 0].cuda()
+    want = to.confusion_matrix_bincount(C, pd[3:].flatten(), gt[3:].flatten()).cpu()
+    for off in (0, 3):                                                  # offset 3: not 16-byte aligned for the uint8 maps
+        for pdt in (torch.int64, torch.uint8):
+            for gdt in (torch.int64, torch.uint8):
+                p_, g_ = pd.to(pdt)[off:], gt.to(gdt)[off:]
+                exp = want if off == 3 else to.confusion_matrix_bincount(C, pd.flatten(), gt.flatten()).cpu()
+                p_work = p_.clone() if off == 0 else p_.clone()
+                cm = lib.confusion_from_pred(p_work, g_.contiguous(), C, 255, mutate_pd=True)
+                assert torch.equal(cm.cpu(), exp), (off, pdt, gdt)
+                assert bool((p_work[g_ == 255] == 255).all()) and torch.equal(p_work[g_ != 255], p_[g_ != 255])
+
+
+def test_eval_dropin_with_uint8_labels(lib, golden):
+    """The tester flow of aspp_tester.py:57-74 with the labels left as uint8 (no .long()): same predictions, matrices, areas."""
+    import types
+    import rnd_semantic_segmentation_b200 as b200
+    g = golden("eval")
+    C = int(g["num_classes"])
+    cfg = types.SimpleNamespace(MODEL=types.SimpleNamespace(NUM_CLASSES=C, NAME="deeplab_resnet101"))
+
+    class FixedHead(torch.nn.Module):
+        def forward(self, feats, size=None):
+            return feats
+
+    for f in range(3):
+        logits = torch.from_numpy(g[f"f{f}.logits_lr"]).cuda()
+        y = torch.from_numpy(g[f"f{f}.y"]).cuda().to(torch.uint8)
+        out = b200.inference(torch.nn.Identity(), FixedHead(), logits, y, flip=False)
+        pred = out.max(1)[1]
+        assert torch.equal(pred.cpu(), torch.from_numpy(g[f"f{f}.pred"]))
+        cm = b200.confusion_matrix(cfg, torch.flatten(pred), torch.flatten(y))
+        assert torch.equal(cm, torch.from_numpy(g[f"f{f}.cm"]))
+        i, u, t, r = b200.intersectionAndUnionGPU(pred, y, C, 255)
+        for got, key in ((i, "I"), (u, "U"), (t, "T"), (r, "R")):
+            np.testing.assert_array_equal(got.cpu().numpy(), g[f"f{f}.{key}"])
+        assert np.array_equal(b200.pseudo_label_map(out), g[f"f{f}.pred"].reshape(g[f"f{f}.pred"].shape[-2:]).astype(np.uint8))
+
+
+def test_confusion_matrix_memo_is_invalidated_by_in_place_edits(lib):
+    """confusion_matrix() may answer from the matrix computed together with the prediction only while neither the
+    prediction nor the labels were edited in place since; after an edit it recounts from the tensors it is given."""
+    import types
+    import rnd_semantic_segmentation_b200 as b200
+    C = 19
+    cfg = types.SimpleNamespace(MODEL=types.SimpleNamespace(NUM_CLASSES=C, NAME="deeplab_resnet101"))
+
+    class FixedHead(torch.nn.Module):
+        def forward(self, feats, size=None):
+            return feats
+
+    logits = torch.randn(1, C, 16, 32, generator=torch.Generator().manual_seed(3)).cuda()
+    y = make_labels(1, 128, 256, C, 0.1, 4).cuda()
+    pred = b200.inference(torch.nn.Identity(), FixedHead(), logits, y, flip=False).max(1)[1]
+    cm0 = b200.confusion_matrix(cfg, pred.flatten(), y.flatten())
+    assert torch.equal(cm0, to.confusion_matrix_bincount(C, pred.flatten(), y.flatten()).cpu())
+    pred[pred == 3] = 5                                                   # post-processing: remap a class id in place
+    cm1 = b200.confusion_matrix(cfg, pred.flatten(), y.flatten())
+    assert torch.equal(cm1, to.confusion_matrix_bincount(C, pred.flatten(), y.flatten()).cpu())
+    assert int(cm1[:, 3].sum()) == 0
+    y[y == 7] = 255                                                       # and mask a truth class
+    cm2 = b200.confusion_matrix(cfg, pred.flatten(), y.flatten())
+    assert torch.equal(cm2, to.confusion_matrix_bincount(C, pred.flatten(), y.flatten()).cpu())
+    assert int(cm2[7].sum()) == 0
+
+
+def test_training_mode_repacks_weights_written_through_data(lib):
+    """``p.data`` writes (the reference's own init idiom, classifier.py:23-24, and legacy optimizers) do not bump the
+    version counter.  In training mode the bf16 weight pack is rebuilt on every call, so the head must see them; in eval mode
+    the cached pack is documented to need ``invalidate_packed()``."""
+    import rnd_semantic_segmentation_b200 as b200
+    torch.manual_seed(1)
+    head = b200.ASPP_Classifier_V2(64, RATES, RATES, 7).cuda()
+    x = torch.relu(torch.randn(1, 64, 9, 11, generator=torch.Generator().manual_seed(2))).cuda()
+    with torch.no_grad():
+        y0 = head.logits(x).clone()
+        for m in head.conv2d_list:
+            m.weight.data.mul_(2.0)
+            m.bias.data.mul_(2.0)
+        y1 = head.logits(x)
+    assert rel_err(y1, 2 * y0) <= 1e-6
+    head.eval()
+    with torch.no_grad():
+        y2 = head.logits(x).clone()
+        for m in head.conv2d_list:
+            m.weight.data.mul_(0.5)
+            m.bias.data.mul_(0.5)
+        head.invalidate_packed()
+        y3 = head.logits(x)
+    assert rel_err(y2, y1) <= 1e-6 and rel_err(y3, y0) <= 1e-6
