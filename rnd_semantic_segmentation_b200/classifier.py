@@ -8,6 +8,8 @@ tcgen05 GEMM head in csrc/aspp_head.cu (bf16 operands, fp32 accumulate).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import nn
 
@@ -25,6 +27,12 @@ class ASPP_Classifier_V2(nn.Module):
             m.weight.data.normal_(0, 0.01)
         self._packed = None
         self._packed_key = None
+        # forward(x, size) returns a lazy.LazyLogits (fused head + upsample + loss when the caller's own criterion consumes it;
+        # materialised on any other use).  False: always the materialised tensor (needed under torch's DDP wrapper).
+        self.lazy = os.environ.get("B200SEG_LAZY", "1") != "0"
+
+    def out_channels_lowres(self):
+        return int(self.conv2d_list[0].out_channels)
 
     # ---- helpers -------------------------------------------------------------------------
     def _rates(self):
@@ -65,6 +73,9 @@ class ASPP_Classifier_V2(nn.Module):
 
     # ---- reference API -------------------------------------------------------------------
     def forward(self, x, size=None):
+        if size is not None and self.lazy and x.is_cuda:    # classifier.py:30-31, evaluated by whoever consumes it (lazy.py)
+            from .lazy import LazyLogits, _LogitsSource
+            return LazyLogits(_LogitsSource(self, x, size))
         out = self.logits(x)
         if size is not None:                                # classifier.py:30-31
             out = ops.upsample_bilinear_align_corners(out, size)

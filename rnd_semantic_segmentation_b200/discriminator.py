@@ -9,6 +9,8 @@ align-corners upsample, or the fused soft-label loss (``forward_soft_loss``).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import nn
 
@@ -28,6 +30,10 @@ class PixelDiscriminator(nn.Module):
 
         self._packed = None
         self._packed_key = None
+        self.lazy = os.environ.get("B200SEG_LAZY", "1") != "0"        # see ASPP_Classifier_V2.lazy
+
+    def out_channels_lowres(self):
+        return int(self.cls1.out_channels + self.cls2.out_channels)
 
     def _params(self):
         return [self.D[0].weight, self.D[0].bias, self.D[2].weight, self.D[2].bias,
@@ -55,6 +61,9 @@ class PixelDiscriminator(nn.Module):
                                               packed=self._packed_weights())
 
     def forward(self, x, size=None):
+        if size is not None and self.lazy and x.is_cuda:                  # discriminator.py:48-49, evaluated by its consumer
+            from .lazy import LazyLogits, _LogitsSource
+            return LazyLogits(_LogitsSource(self, x, size))
         out = self.logits(x)
         if size is not None:                                              # discriminator.py:48-49
             out = ops.upsample_bilinear_align_corners(out, size)

@@ -311,7 +311,15 @@ class _SoftCEFn(torch.autograd.Function):
 
 def soft_label_cross_entropy(pred: torch.Tensor, soft_label: torch.Tensor,
                              pixel_weights: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """core/utils/utility.py:172-177 (differentiable w.r.t. pred only, as every reference caller uses it)."""
+    """core/utils/utility.py:172-177 (differentiable w.r.t. pred only, as every reference caller uses it).  Lazy operands
+    (lazy.py: the discriminator's un-materialised output against a soft label built from un-materialised head logits,
+    aspp_fada.py:110-124) take the fused K6 + K5 path; anything else is materialised and streamed through K3."""
+    from . import lazy
+    if lazy.is_lazy(pred) or lazy.is_lazy(soft_label):
+        fused = lazy.soft_label_loss(pred, soft_label, pixel_weights)
+        if fused is not NotImplemented:
+            return fused
+        pred, soft_label = lazy.materialize(pred), lazy.materialize(soft_label)
     return _SoftCEFn.apply(pred, soft_label, pixel_weights)
 
 

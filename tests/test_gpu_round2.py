@@ -32,12 +32,33 @@ def _l2(a, b):
     return ((a - b).norm() / b.norm()).item()
 
 
+def _same_rounding_train_oracle(ref, x, lab, size, temperature=1.0):
+    """The train slice of aspp_trainer.py:88-92 on the host cores (fp32) with exactly the operand roundings of the CUDA path:
+    bf16 features, bf16 packed weights (centre taps pre-summed), and the low-res loss gradient rounded to bf16 before it enters
+    the data / weight gradient contractions (the bias gradient is summed from the fp32 gradient).  Returns (loss, low-res logits,
+    grad_x, [weight gradients with the shared centre tap filled in], bias gradient)."""
+    eff = effective_bf16_head(ref)
+    xr = bf16_round(x).requires_grad_(True)
+    lr = eff(xr)
+    leaf = lr.detach().requires_grad_(True)
+    loss = to.hard_cross_entropy(to.upsample_bilinear_ac(leaf, size).div(temperature), lab)
+    g, = torch.autograd.grad(loss, leaf)
+    lr.backward(bf16_round(g))
+    centre = eff.conv2d_list[0].weight.grad[:, :, 1, 1]
+    wgs = []
+    for m in eff.conv2d_list:
+        wg = m.weight.grad.clone()
+        wg[:, :, 1, 1] = centre                                        # eff carries the shared centre tap on branch 0 only
+        wgs.append(wg)
+    return loss.detach(), lr.detach(), xr.grad, wgs, g.sum((0, 2, 3))
+
+
 # ------------------------------------------------------------------ full-size BASELINE configs against the CPU oracle
 def test_cfg1_full_size_anchor_known_answer_and_gradients(lib):
     """BASELINE.json configs[0] (deeplabv2_r101_src, 2 x 2048 x 65 x 129 -> 512 x 1024, C = 19) with the survey's anchor inputs
     (torch.manual_seed(0) ...) through ``forward_loss``: the loss must reproduce the reference's known answer
     4.04814 to the bf16-operand bar (5e-3), and loss / low-res logits / every gradient must match the CPU oracle fed the same
-    bf16-rounded operands (fp32 math on the host cores, as aspp_trainer.py:88-92 computes them) to 1e-3."""
+    bf16-rounded operands (fp32 math on the host cores, as aspp_trainer.py:88-92 computes them) to 1e-3 (max-abs / max-abs)."""
     import rnd_semantic_segmentation_b200 as b200
     torch.manual_seed(0)
     ref = to.AsppHeadOracle(2048, RATES, RATES, 19)
@@ -51,24 +72,19 @@ def test_cfg1_full_size_anchor_known_answer_and_gradients(lib):
     loss, logits_lr = head.forward_loss(xc, lab.cuda())
     loss.backward()
     assert abs(loss.item() - 4.04814) <= 5e-3 * 4.04814, loss.item()
-    # same-rounding oracle: bf16-rounded features and packed weights, fp32 arithmetic on the CPU
-    eff = effective_bf16_head(ref)
-    xr = bf16_round(x).requires_grad_(True)
-    want_lr = eff(xr)
-    want = to.hard_cross_entropy(to.upsample_bilinear_ac(want_lr, (512, 1024)), lab)
-    want.backward()
+    # same-rounding oracle: bf16-rounded features / packed weights / low-res gradient operand, fp32 arithmetic on the CPU
+    want, want_lr, want_gx, want_gw, want_gb = _same_rounding_train_oracle(ref, x, lab, (512, 1024))
     print("cfg1 loss", loss.item(), "same-rounding oracle", want.item(), "anchor 4.04814")
     assert abs(loss.item() - want.item()) <= TOL * abs(want.item())
     assert rel_err(logits_lr, want_lr) <= TOL
-    # the CUDA path rounds the low-res loss gradient to bf16 before its two GEMMs (the oracle does not): bf16 half-ulp = 2^-9
-    # on the operand, which averages out over the 16 770-pixel / 684-tap contractions
-    assert rel_err(xc.grad, xr.grad) <= 2e-3 and _l2(xc.grad, xr.grad) <= 2e-3
-    centre = eff.conv2d_list[0].weight.grad[:, :, 1, 1]
-    for i, (m_ref, m_ours) in enumerate(zip(eff.conv2d_list, head.conv2d_list)):
-        wg = m_ref.weight.grad.clone()
-        wg[:, :, 1, 1] = centre                                        # eff carries the shared centre tap on branch 0 only
-        assert rel_err(m_ours.weight.grad, wg) <= 2e-3 and _l2(m_ours.weight.grad, wg) <= 2e-3, f"branch {i}"
-        assert rel_err(m_ours.bias.grad, eff.conv2d_list[0].bias.grad) <= 1e-4
+    # data gradient: the CUDA loss kernel's fp32 gradient differs from the oracle's by ~1e-6 (ex2.approx, summation order), which
+    # moves the bf16 rounding of the occasional gradient element by one ulp (2^-8 of that element); a feature-gradient element
+    # is a 684-term contraction, so single flips stay visible in the max-abs metric (measured 1.15e-3 at cfg1): 1e-3 in L2,
+    # 2e-3 max-abs.  The weight gradients average over all pixels and meet 1e-3 max-abs.
+    assert _l2(xc.grad, want_gx) <= TOL and rel_err(xc.grad, want_gx) <= 2e-3
+    for i, (wg, m_ours) in enumerate(zip(want_gw, head.conv2d_list)):
+        assert rel_err(m_ours.weight.grad, wg) <= TOL, f"branch {i}"
+        assert rel_err(m_ours.bias.grad, want_gb) <= 1e-4
     # and the API-compat path (materialised logits + the caller's own criterion) sees the same loss
     out = head(x.cuda(), (512, 1024))
     l2 = F.cross_entropy(out, lab.cuda(), ignore_index=255)
@@ -91,18 +107,17 @@ def test_cfg2_kvasir_full_size(lib):
     xc = x.cuda().requires_grad_(True)
     loss, logits_lr = head.forward_loss(xc, lab.cuda())
     loss.backward()
-    eff = effective_bf16_head(ref)
-    xr = bf16_round(x).requires_grad_(True)
-    want_lr = eff(xr)
-    want = to.hard_cross_entropy(to.upsample_bilinear_ac(want_lr, (H, W)), lab)
-    want.backward()
+    want, want_lr, want_gx, want_gw, want_gb = _same_rounding_train_oracle(ref, x, lab, (H, W))
     assert abs(loss.item() - want.item()) <= TOL * abs(want.item())
     assert rel_err(logits_lr, want_lr) <= TOL
-    assert rel_err(xc.grad, xr.grad) <= 2e-3 and _l2(xc.grad, xr.grad) <= 2e-3
-    for i, (m_ref, m_ours) in enumerate(zip(eff.conv2d_list, head.conv2d_list)):
-        wg = m_ref.weight.grad.clone()
-        wg[:, :, 1, 1] = eff.conv2d_list[0].weight.grad[:, :, 1, 1]
-        assert rel_err(m_ours.weight.grad, wg) <= 2e-3, f"branch {i}"
+    # data gradient: the CUDA loss kernel's fp32 gradient differs from the oracle's by ~1e-6 (ex2.approx, summation order), which
+    # moves the bf16 rounding of the occasional gradient element by one ulp (2^-8 of that element); a feature-gradient element
+    # is a 684-term contraction, so single flips stay visible in the max-abs metric (measured 1.15e-3 at cfg1): 1e-3 in L2,
+    # 2e-3 max-abs.  The weight gradients average over all pixels and meet 1e-3 max-abs.
+    assert _l2(xc.grad, want_gx) <= TOL and rel_err(xc.grad, want_gx) <= 2e-3
+    for i, (wg, m_ours) in enumerate(zip(want_gw, head.conv2d_list)):
+        assert rel_err(m_ours.weight.grad, wg) <= TOL, f"branch {i}"
+        assert rel_err(m_ours.bias.grad, want_gb) <= 1e-4
     want_fp32 = to.train_step_src(ref, x, lab)[0]
     assert abs(loss.item() - want_fp32.item()) <= 5e-3 * abs(want_fp32.item())
 
@@ -373,3 +388,165 @@ def test_training_mode_repacks_weights_written_through_data(lib):
         head.invalidate_packed()
         y3 = head.logits(x)
     assert rel_err(y2, y1) <= 1e-6 and rel_err(y3, y0) <= 1e-6
+
+
+# ------------------------------------------------------------------ lazy logits: unmodified trainer code reaches the fused path
+def _grads(mods, *tensors):
+    return [None if p.grad is None else p.grad.clone() for m in mods for p in m.parameters()] + [t.grad.clone() for t in tensors]
+
+
+def test_lazy_logits_unmodified_source_trainer_lines(lib):
+    """aspp_trainer.py:88-92 verbatim -- ``output = classifier(fea, size); loss = CrossEntropyLoss(ignore_index=255)(output, y);
+    loss.backward()`` -- takes the fused head + upsample + CE op (bit-identical to ``forward_loss``) and agrees with the same
+    lines run on the MATERIALISED [N,C,H,W] tensor (module.lazy = False: materialising upsample + ATen cross_entropy)."""
+    import rnd_semantic_segmentation_b200 as b200
+    from rnd_semantic_segmentation_b200 import _lib, lazy
+    torch.manual_seed(12)
+    classifier = b200.ASPP_Classifier_V2(256, RATES, RATES, 19).cuda()
+    fea = torch.relu(torch.randn(2, 256, 33, 65, generator=torch.Generator().manual_seed(13))).cuda()
+    src_label = make_labels(2, 264, 520, 19, 0.1, 14).cuda().long()
+    criterion = torch.nn.CrossEntropyLoss(ignore_index=255)
+
+    def trainer_lines(x):
+        classifier.zero_grad()
+        x = x.clone().requires_grad_(True)
+        size = src_label.shape[-2:]
+        output = classifier(x, size)
+        loss = criterion(output, src_label)
+        loss.backward()
+        return loss.detach(), _grads([classifier], x), output
+
+    l0 = _lib.launch_count()
+    loss_lazy, g_lazy, out = trainer_lines(fea)
+    n_lazy = _lib.launch_count() - l0
+    assert lazy.is_lazy(out) and tuple(out.shape) == (2, 19, 264, 520) and out._full is None      # never materialised
+    classifier.zero_grad()
+    xf = fea.clone().requires_grad_(True)
+    l0 = _lib.launch_count()
+    loss_f, _ = classifier.forward_loss(xf, src_label)
+    loss_f.backward()
+    assert _lib.launch_count() - l0 == n_lazy                                                     # the very same launches
+    assert torch.equal(loss_lazy, loss_f.detach())
+    for a, b in zip(g_lazy, _grads([classifier], xf)):
+        assert torch.equal(a, b)
+    classifier.lazy = False
+    try:
+        loss_mat, g_mat, out_mat = trainer_lines(fea)
+    finally:
+        classifier.lazy = True
+    assert isinstance(out_mat, torch.Tensor)
+    assert abs(loss_lazy.item() - loss_mat.item()) <= 1e-5 * abs(loss_mat.item())
+    for a, b in zip(g_lazy, g_mat):
+        assert rel_err(a, b) <= 5e-3          # the materialised path rounds the fp32 NCHW gradient to bf16 once more
+
+
+def test_lazy_logits_unmodified_fada_iteration_lines(lib):
+    """aspp_fada.py:91-125 verbatim (div(temperature), criterion, F.softmax(...).detach(), soft[soft > 0.9] = 0.9, model_D(fea,
+    size), soft_label_cross_entropy(pred, torch.cat((soft, zeros_like(soft)), 1)), ...) on the drop-in modules: every loss and
+    every gradient bit-identical to the explicit fused entry points, no full-resolution tensor materialised, and in agreement
+    with the same lines on materialised tensors (lazy = False)."""
+    import rnd_semantic_segmentation_b200 as b200
+    from rnd_semantic_segmentation_b200 import lazy
+    soft_label_cross_entropy = b200.soft_label_cross_entropy
+    n, cin, C, h, w, H, W = 2, 256, 19, 16, 32, 128, 256
+    torch.manual_seed(31)
+    classifier = b200.ASPP_Classifier_V2(cin, RATES, RATES, C).cuda()
+    model_D = b200.PixelDiscriminator(cin, 64, num_classes=C).cuda()
+    g = torch.Generator().manual_seed(32)
+    src, tgt = (torch.relu(torch.randn(n, cin, h, w, generator=g)).cuda() for _ in range(2))
+    src_label = make_labels(n, H, W, C, 0.1, 33).cuda()
+    criterion = torch.nn.CrossEntropyLoss(ignore_index=255)
+    src_size = tgt_size = (H, W)
+
+    def fada_lines():
+        classifier.zero_grad(), model_D.zero_grad()
+        src_fea, tgt_fea = src.clone().requires_grad_(True), tgt.clone().requires_grad_(True)
+        src_pred = classifier(src_fea, src_size)
+        temperature = 1.8
+        src_pred = src_pred.div(temperature)
+        loss_seg = criterion(src_pred, src_label)
+        loss_seg.backward()
+        src_soft_label = F.softmax(src_pred, dim=1).detach()
+        src_soft_label[src_soft_label > 0.9] = 0.9
+        tgt_pred = classifier(tgt_fea, tgt_size)
+        tgt_pred = tgt_pred.div(temperature)
+        tgt_soft_label = F.softmax(tgt_pred, dim=1)
+        tgt_soft_label = tgt_soft_label.detach()
+        tgt_soft_label[tgt_soft_label > 0.9] = 0.9
+        tgt_D_pred = model_D(tgt_fea, tgt_size)
+        loss_adv_tgt = 0.001 * soft_label_cross_entropy(tgt_D_pred, torch.cat((tgt_soft_label, torch.zeros_like(tgt_soft_label)), dim=1))
+        loss_adv_tgt.backward()
+        g_adv = _grads([classifier], src_fea, tgt_fea)
+        model_D.zero_grad()
+        src_D_pred = model_D(src_fea.detach(), src_size)
+        loss_D_src = 0.5 * soft_label_cross_entropy(src_D_pred, torch.cat((src_soft_label, torch.zeros_like(src_soft_label)), dim=1))
+        loss_D_src.backward()
+        tgt_D_pred = model_D(tgt_fea.detach(), tgt_size)
+        loss_D_tgt = 0.5 * soft_label_cross_entropy(tgt_D_pred, torch.cat((torch.zeros_like(tgt_soft_label), tgt_soft_label), dim=1))
+        loss_D_tgt.backward()
+        lazies = (src_pred, tgt_pred, src_soft_label, tgt_soft_label, tgt_D_pred, src_D_pred)
+        return [t.detach() for t in (loss_seg, loss_adv_tgt, loss_D_src, loss_D_tgt)], g_adv + _grads([model_D]), lazies
+
+    losses, grads, lazies = fada_lines()
+    assert all(lazy.is_lazy(t) and t._full is None for t in lazies)
+    # the explicit fused calls
+    classifier.zero_grad(), model_D.zero_grad()
+    src_fea, tgt_fea = src.clone().requires_grad_(True), tgt.clone().requires_grad_(True)
+    loss_seg, src_lr = classifier.forward_loss(src_fea, src_label, temperature=1.8)
+    loss_seg.backward()
+    with torch.no_grad():
+        tgt_lr = classifier.logits(tgt_fea)
+    loss_adv = 0.001 * model_D.forward_soft_loss(tgt_fea, tgt_lr, (H, W), slot=0)
+    loss_adv.backward()
+    g_adv = _grads([classifier], src_fea, tgt_fea)
+    model_D.zero_grad()
+    loss_d_src = 0.5 * model_D.forward_soft_loss(src_fea.detach(), src_lr, (H, W), slot=0)
+    loss_d_src.backward()
+    loss_d_tgt = 0.5 * model_D.forward_soft_loss(tgt_fea.detach(), tgt_lr, (H, W), slot=1)
+    loss_d_tgt.backward()
+    for a, b in zip(losses, (loss_seg, loss_adv, loss_d_src, loss_d_tgt)):
+        assert torch.equal(a, b.detach())
+    for a, b in zip(grads, g_adv + _grads([model_D])):
+        assert torch.equal(a, b)
+    # the same lines on materialised tensors
+    classifier.lazy = model_D.lazy = False
+    try:
+        losses_m, grads_m, reals = fada_lines()
+    finally:
+        classifier.lazy = model_D.lazy = True
+    assert all(isinstance(t, torch.Tensor) for t in reals)
+    for a, b in zip(losses, losses_m):
+        assert abs(a.item() - b.item()) <= 1e-4 * abs(b.item())
+    for a, b in zip(grads, grads_m):
+        assert ((a.double() - b.double()).norm() / b.double().norm()).item() <= 1e-2
+
+
+def test_lazy_logits_other_uses_materialise_with_reference_semantics(lib):
+    """Anything but the fused patterns computes the real tensor: arithmetic, indexing, torch functions, tensor methods, autograd."""
+    import rnd_semantic_segmentation_b200 as b200
+    from rnd_semantic_segmentation_b200 import lazy
+    torch.manual_seed(5)
+    head = b200.ASPP_Classifier_V2(64, RATES, RATES, 7).cuda()
+    x = torch.relu(torch.randn(2, 64, 9, 11, generator=torch.Generator().manual_seed(6))).cuda()
+    head.lazy = False
+    want = head(x, (50, 70)).detach()
+    head.lazy = True
+    out = head(x, (50, 70))
+    assert lazy.is_lazy(out) and out.shape == want.shape and out.size(1) == 7 and out.dim() == 4 and len(out) == 2
+    assert torch.equal((out * 2 + 1).detach(), want * 2 + 1)
+    assert torch.equal(out[:, 2:5].detach(), want[:, 2:5])
+    assert torch.equal(torch.sigmoid(out).detach(), torch.sigmoid(want))
+    assert torch.equal(out.max(1)[1], want.max(1)[1]) and torch.equal(out.argmax(1), want.argmax(1))
+    assert torch.equal(F.log_softmax(out, dim=1).detach(), F.log_softmax(want, dim=1))
+    assert torch.equal(F.softmax(head(x, (50, 70)).div(1.8), dim=1).materialize().detach(), F.softmax(want / 1.8, dim=1))
+    # class-weighted / sum-reduced criteria are not the fused pattern: still the reference's numbers
+    y = make_labels(2, 50, 70, 7, 0.1, 7).cuda()
+    wts = torch.rand(7, device="cuda")
+    assert torch.allclose(F.cross_entropy(head(x, (50, 70)), y, weight=wts, ignore_index=255), F.cross_entropy(want, y, weight=wts, ignore_index=255))
+    xg = x.clone().requires_grad_(True)
+    head(xg, (50, 70)).square().mean().backward()
+    head.lazy = False
+    xr = x.clone().requires_grad_(True)
+    head(xr, (50, 70)).square().mean().backward()
+    head.lazy = True
+    assert torch.equal(xg.grad, xr.grad)
