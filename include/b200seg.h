@@ -96,6 +96,11 @@ B200SEG_API int b200seg_upsample_ce_backward(const void* workspace, int N, int C
                                  float inv_temperature, const float* loss_out2, const float* grad_out,
                                  float* grad_logits, void* stream);
 
+/* K2 has two kernels with one contract: 1 (default) = the warp-tile kernel (csrc/ce_v2_kernels.cu) where it is eligible
+ * (upsampling by >= ~5.3x horizontally, not downsampling vertically) and measured faster (19 classes); 2 = the warp-tile kernel
+ * wherever it is eligible (19 or 2 classes); 0 = always the CTA-tile kernel (A/B experiments, cross-check in the tests). */
+B200SEG_API void b200seg_upsample_ce_set_variant(int variant);
+
 /* Packed backward for the fused head+loss path: writes the low-res gradient as bf16 class planes gOt [N][C][h*w]
  * (the NCHW layout at half the bytes; the buffer must hold N*h*w*32 elements) -- the operand layout
  * b200seg_aspp_backward_packed consumes -- and, if bias_grad != NULL, the per-class sum of the fp32 gradient

@@ -40,6 +40,7 @@ SIGNATURES = {
     "b200seg_upsample_ce_workspace_bytes": (c_i64, [c_int] * 6),
     "b200seg_upsample_ce_forward": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_f32, c_int, c_vp,
                                             c_i64, c_vp, c_vp]),
+    "b200seg_upsample_ce_set_variant": (None, [c_int]),
     "b200seg_upsample_ce_backward": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp, c_vp]),
     "b200seg_upsample_ce_backward_packed": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b200seg_upsample_bilinear_forward": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
@@ -453,6 +454,12 @@ def upsample_ce_forward(logits_lr, labels, ignore_index=255, inv_temperature=1.0
                                                   float(inv_temperature), 1 if need_grad else 0, ws.data_ptr(), nbytes,
                                                   out2.data_ptr(), _stream()))
     return out2, ws
+
+
+def upsample_ce_set_variant(v: int):
+    """K2 A/B: 1 (default) = warp-tile kernel where eligible and measured faster (19 classes), 2 = wherever eligible (also 2
+    classes), 0 = always the CTA-tile kernel."""
+    load().b200seg_upsample_ce_set_variant(int(v))
 
 
 def upsample_ce_backward(ws, out2, shape_lr, size, inv_temperature=1.0, grad_out: Optional[torch.Tensor] = None):

@@ -93,6 +93,7 @@ int nhwc_bf16_colsum(const void*, long long, int, int, void*, float*, cudaStream
 int tta_launch(const float* const*, const int*, const int*, const int*, int, int, const void*, int, int, int, int, const float*, int, int,
                long long*, void*, int, float*, cudaStream_t);
 void tta_set_row_walk(int);
+void k2_set_variant(int);
 int sgd_step(int, float* const*, const float* const*, float* const*, const long long*, float, float, float, float, int, int, float,
              cudaStream_t);
 int adam_step(int, float* const*, const float* const*, float* const*, float* const*, const long long*, float, float, float, float,
@@ -404,6 +405,7 @@ int b200seg_tta_argmax_confusion_ex(const float* const* logits_lr, const int* h,
 }
 
 void b200seg_tta_set_row_walk(int on) { tta_set_row_walk(on); }
+void b200seg_upsample_ce_set_variant(int v) { k2_set_variant(v); }
 
 int b200seg_sgd_step(int n_tensors, float* const* params, const float* const* grads, float* const* momentum_bufs,
                      const int64_t* numels, float lr, float momentum, float dampening, float weight_decay, int nesterov,

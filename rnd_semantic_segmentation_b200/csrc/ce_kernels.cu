@@ -19,7 +19,7 @@
 //
 // Also here: materialising align-corners upsample forward / backward (the API-compat path for
 // callers that want the full-resolution tensor, e.g. PixelDiscriminator.forward(x, size)).
-#include "common.cuh"
+#include "ce_geom.cuh"
 
 namespace b200seg {
 
@@ -31,71 +31,30 @@ constexpr int K2_TILE_W = 128;
 constexpr int K2_TILE_H = K2_TILE_H_DEF;        // <= 32 (four label strips in flight)
 constexpr int K2_STRIP = 8;
 
-struct K2Geom {
-  int N, C, h, w, H, W;
-  int tiles_x, tiles_y;
-  int ispan_max, jspan_max;     // max number of source rows / cols touched by one tile
-  int kmax;                     // max number of tile columns that interpolate from one source column
-  float scale_h, scale_w;
-};
+// CTA-tile geometry (128 x 32); the warp-tile kernel (ce_v2_kernels.cu) uses 32 x 32 tiles where the shape is eligible.  Forward
+// and backward pick the same one from the shape alone.
+static void k2_geometry(K2Geom& g, int N, int C, int h, int w, int H, int W) { k2_geometry_tiled(g, N, C, h, w, H, W, K2_TILE_W, K2_TILE_H); }
 
-__host__ __device__ __forceinline__ int host_i0(float scale, int dst) { return (int)(scale * (float)dst); }
-
-static void k2_geometry(K2Geom& g, int N, int C, int h, int w, int H, int W) {
-  g.N = N; g.C = C; g.h = h; g.w = w; g.H = H; g.W = W;
-  g.tiles_x = ceil_div(W, K2_TILE_W);
-  g.tiles_y = ceil_div(H, K2_TILE_H);
-  g.scale_h = ac_scale(h, H);
-  g.scale_w = ac_scale(w, W);
-  g.ispan_max = 1; g.jspan_max = 1;
-  for (int ty = 0; ty < g.tiles_y; ++ty) {
-    const int ya = ty * K2_TILE_H, yb = (ya + K2_TILE_H < H ? ya + K2_TILE_H : H) - 1;
-    const int lo = host_i0(g.scale_h, ya);
-    int hi = host_i0(g.scale_h, yb); hi += (hi < h - 1) ? 1 : 0;
-    if (hi - lo + 1 > g.ispan_max) g.ispan_max = hi - lo + 1;
-  }
-  for (int tx = 0; tx < g.tiles_x; ++tx) {
-    const int xa = tx * K2_TILE_W, xb = (xa + K2_TILE_W < W ? xa + K2_TILE_W : W) - 1;
-    const int lo = host_i0(g.scale_w, xa);
-    int hi = host_i0(g.scale_w, xb); hi += (hi < w - 1) ? 1 : 0;
-    if (hi - lo + 1 > g.jspan_max) g.jspan_max = hi - lo + 1;
-  }
-  // longest run of output columns sharing one x0, doubled (+2): columns with x0 in {j-1, j} feed source column j
-  int run = 0, best = 1, prev = -1;
-  for (int x = 0; x < W; ++x) {
-    const int i0 = host_i0(g.scale_w, x);
-    run = (i0 == prev) ? run + 1 : 1;
-    prev = i0;
-    if (run > best) best = run;
-  }
-  g.kmax = 2 * best + 2;
-  if (g.kmax > K2_TILE_W) g.kmax = K2_TILE_W;
+static int g_k2_variant = 1;
+void k2_set_variant(int v) { g_k2_variant = v; }
+// variant 0: always the CTA-tile kernel; 1 (default): the warp-tile kernel where it is eligible AND measured faster (19 classes);
+// 2: the warp-tile kernel wherever it is eligible (tests / A-B)
+static bool k2_pick_geometry(K2Geom& g, int N, int C, int h, int w, int H, int W) {
+  if (g_k2_variant != 0 && (C == 19 || g_k2_variant == 2) && k2v2_eligible(N, C, h, w, H, W)) { k2v2_geometry(g, N, C, h, w, H, W); return true; }
+  k2_geometry(g, N, C, h, w, H, W);
+  return false;
 }
-
-// Workspace layout (floats): [tiles] loss partial | [tiles] valid-count partial | [tiles][ispan][jspan][C] blocks
-static long long k2_block_floats(const K2Geom& g) { return (long long)g.ispan_max * g.jspan_max * g.C; }
-static long long k2_tiles(const K2Geom& g) { return (long long)g.N * g.tiles_x * g.tiles_y; }
-
-// per finalize-block partial sums of the low-res gradient (bias gradient), [N*h*ceil(w/128)][32]
-static long long k2_bias_part_floats(const K2Geom& g) { return (long long)g.N * g.h * ceil_div(g.w, 128) * 32; }
 
 long long k2_workspace_bytes(int N, int C, int h, int w, int H, int W) {
   K2Geom g;
   k2_geometry(g, N, C, h, w, H, W);
-  return (2 * k2_tiles(g) + k2_tiles(g) * k2_block_floats(g) + k2_bias_part_floats(g)) * 4 + 256;
+  long long b = k2_geom_bytes(g);
+  if (k2v2_eligible(N, C, h, w, H, W)) {
+    k2v2_geometry(g, N, C, h, w, H, W);
+    if (k2_geom_bytes(g) > b) b = k2_geom_bytes(g);
+  }
+  return b;
 }
-
-struct K2Params {
-  K2Geom g;
-  const float* logits;       // [N,C,h,w]
-  const void* labels;        // [N,H,W] int64, or uint8 when label_u8
-  int label_u8;
-  int ignore_index;
-  float inv_T;
-  float* loss_part;          // [tiles]
-  float* cnt_part;           // [tiles]
-  float* blocks;             // [tiles][ispan_max][jspan_max][C]
-};
 
 constexpr int K2_PITCH = K2_THREADS + 1;      // stage row pitch (floats): conflict-free for both access patterns
 
@@ -553,13 +512,13 @@ __global__ void __launch_bounds__(128) k2_finalize_grad(const K2Geom g, const fl
     const int ya = ac_first_dst(g.scale_h, i - 1, g.h, g.H), yb = ac_first_dst(g.scale_h, i + 1, g.h, g.H);
     const int xa = ac_first_dst(g.scale_w, j - 1, g.w, g.W), xb = ac_first_dst(g.scale_w, j + 1, g.w, g.W);
     if (ya < yb && xa < xb) {
-      const int ty0 = ya / K2_TILE_H, ty1 = (yb - 1) / K2_TILE_H;
-      const int tx0 = xa / K2_TILE_W, tx1 = (xb - 1) / K2_TILE_W;
+      const int ty0 = ya / g.tile_h, ty1 = (yb - 1) / g.tile_h;
+      const int tx0 = xa / g.tile_w, tx1 = (xb - 1) / g.tile_w;
       for (int ty = ty0; ty <= ty1; ++ty) {
-        const int li = i - (int)(g.scale_h * (float)(ty * K2_TILE_H));
+        const int li = i - (int)(g.scale_h * (float)(ty * g.tile_h));
         if (li < 0 || li >= g.ispan_max) continue;
         for (int tx = tx0; tx <= tx1; ++tx) {
-          const int lj = j - (int)(g.scale_w * (float)(tx * K2_TILE_W));
+          const int lj = j - (int)(g.scale_w * (float)(tx * g.tile_w));
           if (lj < 0 || lj >= g.jspan_max) continue;
           const long long tile = ((long long)n * g.tiles_y + ty) * g.tiles_x + tx;
           const float* src = blocks + tile * blk_floats + ((long long)li * g.jspan_max + lj) * g.C;
@@ -650,13 +609,21 @@ int k2_forward(const float* logits, int N, int C, int h, int w, const void* labe
   B200SEG_CHECK_ARG(workspace_bytes >= k2_workspace_bytes(N, C, h, w, H, W), "upsample_ce_forward: workspace too small (%lld < %lld)",
                     workspace_bytes, k2_workspace_bytes(N, C, h, w, H, W));
   K2Params p;
-  k2_geometry(p.g, N, C, h, w, H, W);
+  const bool v2 = k2_pick_geometry(p.g, N, C, h, w, H, W);
   const long long tiles = k2_tiles(p.g);
+  p.counter = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(workspace) + k2_geom_bytes(p.g) - 256);
   p.logits = logits; p.labels = labels; p.label_u8 = (label_bytes == 1); p.ignore_index = ignore_index; p.inv_T = inv_T;
   p.loss_part = reinterpret_cast<float*>(workspace);
   p.cnt_part = p.loss_part + tiles;
   p.blocks = p.cnt_part + tiles;
   int rc;
+  if (v2) {
+    rc = k2v2_main_launch(p, need_grad != 0, stream);
+    if (rc) return rc;
+    k2_finalize_loss<<<1, 256, 0, stream>>>(p.loss_part, p.cnt_part, (int)tiles, loss_out2);
+    B200SEG_LAUNCH_CHECK();
+    return B200SEG_OK;
+  }
 #ifndef K2_SPLIT_DEF
 #define K2_SPLIT_DEF 1   /* 2 = class dimension split over lane pairs: measured 135 us vs 108 us at C = 19 (profiles/README.md) */
 #endif
@@ -674,7 +641,7 @@ int k2_backward(const void* workspace, int N, int C, int h, int w, int H, int W,
                 const float* grad_out, float* grad_logits, cudaStream_t stream) {
   B200SEG_CHECK_ARG(workspace && loss_out2 && grad_logits, "upsample_ce_backward: null pointer");
   K2Geom g;
-  k2_geometry(g, N, C, h, w, H, W);
+  k2_pick_geometry(g, N, C, h, w, H, W);
   const long long tiles = k2_tiles(g);
   const float* blocks = reinterpret_cast<const float*>(workspace) + 2 * tiles;
   dim3 grid(ceil_div(w, 128), h, N);
@@ -689,7 +656,7 @@ int k2_backward_packed(void* workspace, int N, int C, int h, int w, int H, int W
   B200SEG_CHECK_ARG(workspace && loss_out2 && gOt, "upsample_ce_backward_packed: null pointer");
   B200SEG_CHECK_ARG(C <= 32, "upsample_ce_backward_packed: num_classes=%d > 32 is not supported", C);
   K2Geom g;
-  k2_geometry(g, N, C, h, w, H, W);
+  k2_pick_geometry(g, N, C, h, w, H, W);
   const long long tiles = k2_tiles(g);
   float* base = reinterpret_cast<float*>(workspace);
   const float* blocks = base + 2 * tiles;

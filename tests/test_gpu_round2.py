@@ -550,3 +550,44 @@ def test_lazy_logits_other_uses_materialise_with_reference_semantics(lib):
     head(xr, (50, 70)).square().mean().backward()
     head.lazy = True
     assert torch.equal(xg.grad, xr.grad)
+
+
+@pytest.mark.parametrize("n,C,h,w,H,W,T", [(8, 19, 64, 128, 512, 1024, 1.0), (2, 19, 65, 129, 512, 1024, 1.8), (3, 2, 44, 44, 352, 352, 1.0),
+                                          (2, 19, 33, 17, 100, 131, 1.8), (1, 19, 128, 256, 1024, 2048, 1.0), (2, 2, 9, 11, 77, 93, 1.0)])
+@pytest.mark.parametrize("ldtype", [torch.int64, torch.uint8])
+def test_k2_warp_tile_kernel_against_oracle_and_cta_tile_kernel(lib, n, C, h, w, H, W, T, ldtype):
+    """The warp-tile K2 kernel (csrc/ce_v2_kernels.cu: soft-max without a per-pixel maximum, labelled-class logit folded into the
+    row flushes, warp-local reductions, dynamic tile hand-out) forced on wherever it is eligible: against the oracle's
+    ``CrossEntropyLoss(ignore_index=255)(interpolate(x) / T, y)`` and its gradient at 1e-3, against the CTA-tile kernel at 1e-5,
+    run-to-run bit-identical, forward-only (no_grad) loss identical, extreme logit ranges (the exact-maximum path) included."""
+    from rnd_semantic_segmentation_b200 import ops
+    g = torch.Generator().manual_seed(40 + C + h)
+    logits = (2.0 * torch.randn(n, C, h, w, generator=g)).cuda()
+    labels64 = make_labels(n, H, W, C, 0.1, 41 + h).cuda()
+    labels = labels64.to(ldtype)
+
+    def run(variant, lg):
+        lib.upsample_ce_set_variant(variant)
+        try:
+            x = lg.clone().requires_grad_(True)
+            loss = ops.upsample_cross_entropy(x, labels, 255, T)
+            (0.5 * loss).backward()
+            with torch.no_grad():
+                loss_ng = ops.upsample_cross_entropy(lg, labels, 255, T)
+            return loss.detach(), x.grad, loss_ng
+        finally:
+            lib.upsample_ce_set_variant(1)
+
+    for scale in (1.0, 60.0):                       # 60: neighbouring source pixels ~ +-300 apart -> sums of exponentials underflow
+        lg = logits * scale
+        xr = lg.clone().requires_grad_(True)
+        want = to.hard_cross_entropy(to.upsample_bilinear_ac(xr, (H, W)).div(T), labels64)
+        want_g, = torch.autograd.grad(0.5 * want, xr)
+        l2, g2, l2_ng = run(2, lg)
+        l0, g0, _ = run(0, lg)
+        assert abs(l2.item() - want.item()) <= TOL * abs(want.item()), (scale, l2.item(), want.item())
+        assert rel_err(g2, want_g) <= TOL
+        assert abs(l2.item() - l0.item()) <= 1e-5 * abs(l0.item()) and rel_err(g2, g0) <= 1e-5
+        assert torch.equal(l2_ng, l2)
+        l2b, g2b, _ = run(2, lg)
+        assert torch.equal(l2b, l2) and torch.equal(g2b, g2)
