@@ -36,6 +36,19 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def workload_config(workload, world):
+    """The `config` object of the JSON line: the workload only, byte-identical from both arms (``--impl ours`` / ``--impl
+    reference``) so the driver's same_config check holds.  Everything measured lives in other keys."""
+    from rnd_semantic_segmentation_b200 import synth
+    n, cin, h, w, H, W, C = synth.WORKLOADS[workload]
+    return {"workload": workload, "features": [n, cin, h, w], "labels": [n, H, W], "num_classes": C,
+            "input": "fp32 NCHW layer4 features + int64 labels (the reference API contract), synthetic, seed 1234 + rank",
+            "step": "ASPP head fwd + align-corners upsample + CrossEntropyLoss(ignore_index=255) fwd + backward (dX, dW, db)"
+                    " [aspp_trainer.py:88-92 after the backbone]; N > 1: + mean all-reduce of the head gradients",
+            "l2": "inputs larger than L2 (features %d MB per step)" % (n * cin * h * w * 4 // 2 ** 20),
+            "parallelism": "dp%d (batch sharded by image, weak scaling)" % world}
+
+
 def load_traffic(kernel_key):
     """dram bytes per launch of the dominant kernel from the committed `ncu --set full` summary (profiles/), or None."""
     path = os.path.join(ROOT, "profiles", "ncu_summary.json")
@@ -198,9 +211,7 @@ def run_ours(args):
         xg = x_in.detach().requires_grad_(True)            # the backbone needs d loss / d features
         for p in head.parameters():
             p.grad = None
-        # in training the weights change every step, so the bf16 weight pack is part of every step: invalidate the module's
-        # packed-weight cache (keyed on the parameters' version counters) exactly as an optimizer step would
-        torch.autograd.graph.increment_version(head.conv2d_list[0].weight)
+        # (the module is in training mode: the bf16 weight pack is rebuilt on every call, as after every optimizer step)
         # N > 1: weight gradients land in the flat bucket and its NCCL mean all-reduce runs on a second stream underneath
         # the data-gradient GEMM; wait() joins the streams (the all-reduce is inside the timed step)
         loss, _ = head.forward_loss(xg, labels_in, grad_bucket=bucket)
@@ -231,16 +242,49 @@ def run_ours(args):
     gemm_n = sum(prof[k][1] for k in gemm_names if k in prof)
     avg_ms = gemm_ms / max(gemm_n, 1)
     achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
-    peak = peaks["bf16_tflops_sustained"]
+    # peak: the measured cuBLAS bf16 number for the clock regime this run was in -- BURST (1653 TFLOP/s, SMs at their maximum
+    # clock) when the sampled SM clock stayed within 10 % of the maximum (a 16 ms timed region does), else SUSTAINED.  Both
+    # fractions are printed.  FLOPs are the dense 36-tap convention of SURVEY 8d; the kernel executes 33 taps (the four centre taps
+    # are pre-summed), i.e. 33/36 of the credited FLOPs.
+    sm_mhz, sm_max = (clocks or {}).get("sm_mhz"), (clocks or {}).get("sm_max_mhz")
+    at_max_clock = bool(sm_mhz and sm_max and sm_mhz >= 0.9 * sm_max)
+    peak = peaks["bf16_tflops"] if at_max_clock else peaks["bf16_tflops_sustained"]
     kernels = {k: {"ms_per_launch": round(v[0] / v[1], 4), "launches_per_step": v[1] / args.steps} for k, v in prof.items()}
     for k in gemm_names:
         if k in kernels:
             kernels[k]["tflops"] = round(flops_per_launch / (kernels[k]["ms_per_launch"] * 1e-3) / 1e12, 1)
+    k2_ms = prof["upsample_ce_main"][0] / prof["upsample_ce_main"][1] if "upsample_ce_main" in prof else None
+    k2_bytes = 16 * n * H * W + 12 * n * C * h * w                  # int64 labels fwd + bwd, low-res logits r / r / w
     roofline = {"kernel": "gemm_bf16_kernel (tcgen05; head fwd / dgrad / wgrad launches)", "bound": "tensor",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                 "traffic": load_traffic("head_fwd_gemm") if args.workload == "train_b8_512x1024" else None,
-                "peak_source": peaks["source"] + ", sustained bf16",
-                "algorithmic_flops_per_launch": flops_per_launch, "kernels": kernels}
+                "peak_source": peaks["source"] + (", burst bf16 (SM clock at max during the timed region)" if at_max_clock else ", sustained bf16"),
+                "frac_of_burst": round(achieved / peaks["bf16_tflops"], 4), "frac_of_sustained": round(achieved / peaks["bf16_tflops_sustained"], 4),
+                "sm_mhz_during_timed_region": sm_mhz,
+                "algorithmic_flops_per_launch": flops_per_launch, "executed_flops_per_launch": flops_per_launch * 33 / 36,
+                "flops_convention": "credited: dense 36 taps (SURVEY 8d); executed: 33 taps (centre taps pre-summed)",
+                "head_fwd_bwd_incl_helpers_tflops": round(3 * flops_per_launch / (sum(prof[k][0] for k in prof if k.startswith(("head_", "pack_", "grad_im2col", "wgrad_reduce"))) / args.steps * 1e-3) / 1e12, 1),
+                "k2_upsample_ce_us": None if k2_ms is None else round(k2_ms * 1e3, 2),
+                "k2_hbm_frac": None if k2_ms is None else round(k2_bytes / (k2_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                "kernels": kernels}
+
+    # ---- the SAME step written as the reference's unmodified trainer lines (aspp_trainer.py:88-92): module call, the caller's
+    #      own nn.CrossEntropyLoss, backward -- reaches the fused kernels through lazy.LazyLogits
+    criterion = torch.nn.CrossEntropyLoss(ignore_index=255)
+
+    def unmodified_trainer_step():
+        xg = x.detach().requires_grad_(True)
+        for p in head.parameters():
+            p.grad = None
+        size = labels.shape[-2:]
+        output = head(xg, size)
+        loss = criterion(output, labels)
+        loss.backward()
+        return loss
+
+    ms_unmod, _ = timed(unmodified_trainer_step, args.steps, args.warmup)
+    roofline["unmodified_trainer_lines_ms_per_step"] = round(ms_unmod / args.steps, 4)
+    roofline["forward_loss_ms_per_step"] = round(ms_per_step, 4)
 
     # ---- the same step captured once in a CUDA graph and replayed (no Python / launch overhead at all): equal to the eager
     #      number when the step is GPU-bound.  Single-rank only (the bucket's NCCL all-reduce stays out of graphs here).
@@ -279,35 +323,55 @@ def run_ours(args):
            "note": "public API from pinned host buffers; every step's H2D and loss D2H are inside the timed region, the H2D of "
                    "step k+1 (copy stream, double-buffered) overlaps the compute of step k"}
     del xh, lh, e2e_step
+    # the same from host buffers in the seam formats of SURVEY 8f rank 2: bf16 channels_last features + uint8 labels (2.1x fewer bytes)
+    xh = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last).cpu().pin_memory()
+    lh = labels.to(torch.uint8).cpu().pin_memory()
+    e2e_seam_step = HostPipelinedStep(dev, (xh, lh), lambda xd, ld: train_step(xd, ld)[0])
+    ms_e2e_s, _ = timed(e2e_seam_step, e2e_steps, 1)
+    e2e["seam_bf16_uint8_value"] = round(world * label_px / (ms_e2e_s / e2e_steps * 1e-3) / 1e6, 2)
+    e2e["seam_h2d_bytes_per_step"] = xh.numel() * 2 + lh.numel()
+    del xh, lh, e2e_seam_step
 
-    # ---- eval img/s @1024x2048: head fwd (features 1x2048x128x256) + fused upsample/argmax/confusion
+    # ---- eval img/s @1024x2048 (the tester loop of aspp_tester.py:57-72 after the backbone): per frame the head forward on
+    #      1 x 2048 x 128 x 256 features; upsample + argmax + confusion matrix (K4) over 8 queued frames per launch
+    #      (utility.BatchedEvaluator -- a single 1024 x 2048 frame cannot fill 148 SMs with tall tiles).
     en, ecin, eh, ew, eH, eW, eC = synth.WORKLOADS["eval_1024x2048"]
     ehead = synth.scale_head_for_unit_logits(b200.ASPP_Classifier_V2(ecin, RATES, RATES, eC)).to(dev).eval()
-    nf = 4                                               # distinct frames cycled so inputs exceed L2 (4 x 268 MB)
+    nf, nl, kf = 4, 8, 8                                 # distinct feature maps (4 x 268 MB > L2) / label maps; frames per K4 launch
     ex = [synth.make_features(1, ecin, eh, ew, seed=99 + rank * 16 + i, device=dev) for i in range(nf)]
-    ey = [synth.make_labels(1, eH, eW, eC, seed=199 + rank * 16 + i, device=dev) for i in range(nf)]
-    cm = torch.zeros(eC, eC, dtype=torch.int64, device=dev)
-    fi = [0]
+    ey = [synth.make_labels(1, eH, eW, eC, seed=199 + rank * 16 + i, device=dev) for i in range(nl)]
+    ey8 = [t.to(torch.uint8) for t in ey]
+    esteps = max(args.steps * 4, 24) // kf * kf
+    k4_bytes = 8 * eH * eW + 4 * eC * eh * ew + 8 * eC * eC
+    k4_bytes_u8 = eH * eW + 4 * eC * eh * ew + 8 * eC * eC
 
-    def eval_step():
-        i = fi[0] % nf
-        fi[0] += 1
-        with torch.no_grad():
-            lg = ehead.logits(ex[i])
-        b200.segmentation_eval_step(lg, ey[i], cm=cm)
+    def eval_leg(features, labels, frames_per_launch):
+        ev = b200.BatchedEvaluator(ehead, eC, frames=frames_per_launch)
+        k = [0]
 
-    esteps = max(args.steps * 4, 20)
-    ems, _ = timed(eval_step, esteps, args.warmup)
+        def step():
+            i = k[0]
+            k[0] += 1
+            ev.step(features[i % nf], labels[i % nl])
+
+        ms_leg, _ = timed(step, esteps, (args.warmup + kf - 1) // kf * kf)
+        _lib.profile_enable(True)
+        for _ in range(2 * kf):
+            step()
+        torch.cuda.synchronize()
+        prof_leg = _lib.profile_read()
+        _lib.profile_enable(False)
+        k4 = prof_leg["eval_argmax_confusion"]
+        return ms_leg, ev.finish(), prof_leg, k4[0] / (2 * kf)             # K4 ms per FRAME
+
+    ems, cm, eprof, k4_ms = eval_leg(ex, ey, kf)
     if world > 1:
         D.allreduce_confusion_(cm)
-    _lib.profile_enable(True)
-    for _ in range(8):
-        eval_step()
-    torch.cuda.synchronize()
-    eprof = _lib.profile_read()
-    _lib.profile_enable(False)
-    k4_ms = eprof["eval_argmax_confusion"][0] / eprof["eval_argmax_confusion"][1]
-    k4_bytes = 8 * eH * eW + 4 * eC * eh * ew + 8 * eC * eC
+    ems_u8, _, _, k4_ms_u8 = eval_leg(ex, ey8, kf)
+    ems_1, _, _, k4_ms_1 = eval_leg(ex, ey, 1)                             # one K4 launch per frame (the round-1 loop)
+    exs = [t.to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for t in ex]
+    ems_seam, _, _, _ = eval_leg(exs, ey8, kf)                             # seam formats: bf16 channels_last features + uint8 labels
+    del exs
     exh = ex[0].cpu().pin_memory()
     eyh = ey[0].cpu().pin_memory()
 
@@ -319,28 +383,27 @@ def run_ours(args):
 
     eval_e2e_step = HostPipelinedStep(dev, (exh, eyh), eval_from_device)
     ems_e2e, _ = timed(eval_e2e_step, 10, 1)
-    # seam format for eval: bf16 channels_last features straight into the head GEMM (no pack pass)
-    exs = [t.to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for t in ex]
-    fs = [0]
-
-    def eval_seam_step():
-        i = fs[0] % nf
-        fs[0] += 1
-        with torch.no_grad():
-            lg = ehead.logits(exs[i])
-        b200.segmentation_eval_step(lg, ey[i], cm=cm)
-
-    ems_seam, _ = timed(eval_seam_step, esteps, args.warmup)
     eval_obj = {"metric": "eval_img_per_s_1024x2048", "value": round(world * esteps / (ems * 1e-3), 1), "unit": "img/s",
-                "ms_per_frame": round(ems / esteps, 4), "frames": esteps * world, "confusion_total": int(cm.sum().item()),
+                "ms_per_frame": round(ems / esteps, 4), "frames": esteps * world, "frames_per_k4_launch": kf,
+                "confusion_total": int(cm.sum().item()),
                 "e2e": {"value": round(world * 10 / (ems_e2e * 1e-3), 1), "unit": "img/s",
                         "h2d_bytes_per_step": exh.numel() * 4 + eyh.numel() * 8, "d2h_bytes_per_step": 8 * eC * eC},
                 "roofline": {"kernel": "k4_upsample_argmax_confusion", "bound": "hbm", "achieved": round(k4_bytes / (k4_ms * 1e-3) / 1e9, 1),
                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(k4_bytes / (k4_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
-                             "traffic": load_traffic("eval_argmax_confusion"), "algorithmic_bytes_per_launch": k4_bytes},
+                             "traffic": load_traffic("eval_argmax_confusion"), "algorithmic_bytes_per_frame": k4_bytes,
+                             "us_per_frame": round(k4_ms * 1e3, 2),
+                             "uint8_labels": {"us_per_frame": round(k4_ms_u8 * 1e3, 2), "algorithmic_bytes_per_frame": k4_bytes_u8,
+                                              "frac": round(k4_bytes_u8 / (k4_ms_u8 * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)},
+                             "one_frame_per_launch_us": round(k4_ms_1 * 1e3, 2)},
                 "kernels": {k: round(v[0] / v[1], 4) for k, v in eprof.items()},
-                "seam_bf16_nhwc": {"value": round(world * esteps / (ems_seam * 1e-3), 1), "unit": "img/s",
-                                   "ms_per_frame": round(ems_seam / esteps, 4)}}
+                "uint8_labels": {"value": round(world * esteps / (ems_u8 * 1e-3), 1), "unit": "img/s"},
+                "one_k4_launch_per_frame": {"value": round(world * esteps / (ems_1 * 1e-3), 1), "unit": "img/s"},
+                "seam_bf16_nhwc_uint8": {"value": round(world * esteps / (ems_seam * 1e-3), 1), "unit": "img/s",
+                                         "ms_per_frame": round(ems_seam / esteps, 4)}}
+    roofline.update({"eval_img_per_s": eval_obj["value"], "eval_ms_per_frame": eval_obj["ms_per_frame"],
+                     "k4_us_per_frame": round(k4_ms * 1e3, 2), "k4_hbm_frac": eval_obj["roofline"]["frac"],
+                     "k4_uint8_us_per_frame": round(k4_ms_u8 * 1e3, 2), "eval_uint8_img_per_s": eval_obj["uint8_labels"]["value"]})
+    del ex, ey, ey8
 
     # ---- the other loss kernels of the scope table at the adversarial config: N=4, 2C=38, 512x1024
     from rnd_semantic_segmentation_b200 import ops as bops
@@ -383,6 +446,8 @@ def run_ours(args):
     del d_lr, s_lr
     aux.update(run_tta_and_optim(b200, _lib, dev, rank, peaks))
     adv = run_adv_step(b200, _lib, synth, dev, rank, world, peaks, args)
+    cfgs = run_baseline_configs(b200, _lib, synth, dev, rank, peaks, args) if world == 1 else {}
+    dp_check = run_dp_check(b200, D, synth, dev, rank, world, head, bucket, x, labels) if world > 1 else "n/a (single rank)"
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -391,22 +456,142 @@ def run_ours(args):
         adv["cpu_baseline"] = run_cpu_adv_reference()
 
     if rank == 0:
+        # scalars the driver keeps (it drops nested objects outside the contract keys): everything a reader needs to judge the
+        # other legs rides in `roofline`
+        roofline.update({"dp_check": dp_check, "adv_step_Mpx_per_s": adv["value"], "adv_step_ms": adv["ms_per_step"],
+                         "adv_conv_frac_of_sustained": adv["roofline"]["frac"], "seam_bf16_nhwc_ms_per_step": seam["ms_per_step"]})
+        for key, c in cfgs.items():
+            roofline.update({f"{key}_Mpx_per_s": c["Mpx_per_s"], f"{key}_ms_per_step": c["ms_per_step"],
+                             f"{key}_graph_replay_ms_per_step": c["graph_replay_ms_per_step"],
+                             f"{key}_gemm_frac_of_burst": c["gemm_frac_of_burst"], f"{key}_step_hbm_frac": c["step_hbm_frac"]})
         line = {"metric": "aspp_ce_train_Mpx_per_s", "value": round(value, 2), "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": args.workload, "features": [n, cin, h, w], "labels": [n, H, W], "num_classes": C,
-                           "input": "fp32 NCHW features resident in HBM (reference API contract); bf16 operands, fp32 accumulate",
-                           "step": "bf16 weight pack + head fwd + upsample/CE fwd + bwd (dX, dW, db)" + (" + NCCL mean all-reduce of head grads (overlapped with the dgrad GEMM)" if world > 1 else ""),
-                           "l2": "inputs larger than L2 (features %d MB per step)" % (x.numel() * 4 // 2 ** 20),
-                           "parallelism": "dp%d (batch sharded by image)" % world},
+                "config": workload_config(args.workload, world),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_timed), "roofline": roofline, "eval": eval_obj,
-                "seam_bf16_nhwc": seam, "aux_kernels": aux, "adv_step": adv,
+                "seam_bf16_nhwc": seam, "aux_kernels": aux, "adv_step": adv, "baseline_configs": cfgs, "dp_check": dp_check,
                 "cuda_graph_replay_ms_per_step": graph_ms}
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         emit(line)
     if dist.is_initialized():
         dist.destroy_process_group()
+
+
+def run_baseline_configs(b200, _lib, synth, dev, rank, peaks, args):
+    """BASELINE.json's literal train configs on one GPU (each is a parity-test case at full size in tests/test_gpu_round2.py; here
+    their throughput): cfg1 deeplabv2_r101_src (2 x 2048 x 65 x 129, C = 19), cfg2 deeplabv2_r101_src_kvasir (16 x 2048 x 44 x 44,
+    C = 2 -- arithmetic intensity 72 FLOP/B, so judged against HBM) and cfg4 deeplabv2_r101_tgt_self_distill (1 image
+    per GPU).  Eager public-API step and the same step replayed from a CUDA graph (what the ~10 stream launches cost on the host:
+    the small configs are host-bound in eager mode)."""
+    out = {}
+    for key, name, p_ign in (("cfg1", "deeplabv2_r101_src", 0.10), ("cfg2", "deeplabv2_r101_src_kvasir", 0.05),
+                             ("cfg4", "deeplabv2_r101_tgt_self_distill", 0.10)):
+        n, cin, h, w, H, W, C = synth.WORKLOADS[name]
+        torch.manual_seed(1234)
+        head = b200.ASPP_Classifier_V2(cin, RATES, RATES, C).to(dev)
+        xs = [synth.make_features(n, cin, h, w, seed=31 + rank + 7 * i, device=dev) for i in range(2)]    # 2 x >= 137 MB: > L2 for cfg1 / cfg2
+        labels = synth.make_labels(n, H, W, C, p_ignore=p_ign, seed=32 + rank, device=dev)
+        k = [0]
+
+        def step(x_in=None):
+            x_in = xs[k[0] & 1] if x_in is None else x_in
+            k[0] += 1
+            xg = x_in.detach().requires_grad_(True)
+            for p in head.parameters():
+                p.grad = None
+            loss, _ = head.forward_loss(xg, labels)
+            loss.backward()
+            return loss
+
+        ms, _ = timed(step, args.steps, args.warmup)
+        _lib.profile_enable(True)
+        for _ in range(4):
+            step()
+        torch.cuda.synchronize()
+        prof = _lib.profile_read()
+        _lib.profile_enable(False)
+        graph_ms = None
+        try:
+            for p in head.parameters():
+                p.grad = None
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step(xs[0])
+            ms_g, _ = timed(g.replay, args.steps, args.warmup)
+            graph_ms = ms_g / args.steps
+            del g
+        except Exception as e:
+            log(f"{key}: graph replay leg skipped:", repr(e))
+            torch.cuda.synchronize()
+        flops = 2.0 * 36 * cin * C * n * h * w
+        gms = sum(prof[q][0] for q in ("head_fwd_gemm", "head_dgrad_gemm", "head_wgrad_gemm") if q in prof) / 4
+        gemm_tf = 3 * flops / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
+        step_bytes = 8.0 * n * cin * h * w + 16.0 * n * H * W            # fp32 features read + feature gradient written, int64 labels twice
+        best_ms = min(ms / args.steps, graph_ms) if graph_ms else ms / args.steps
+        out[key] = {"workload": name, "Mpx_per_s": round(n * H * W / (ms / args.steps * 1e-3) / 1e6, 1), "ms_per_step": round(ms / args.steps, 4),
+                    "graph_replay_ms_per_step": None if graph_ms is None else round(graph_ms, 4),
+                    "gemm_tflops": round(gemm_tf, 1), "gemm_frac_of_burst": round(gemm_tf / peaks["bf16_tflops"], 4),
+                    "step_hbm_gbs": round(step_bytes / (best_ms * 1e-3) / 1e9, 1), "step_hbm_frac": round(step_bytes / (best_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                    "bound": "hbm" if C == 2 else "tensor"}
+        del head, xs, labels
+    return out
+
+
+def run_dp_check(b200, D, synth, dev, rank, world, head, bucket, x, labels):
+    """Data-parallel correctness inside the driver-run path ("distributed" tier), after the timed region:
+    (1) the gradients the overlapped bucket leaves in .grad are bit-identical on every rank and equal the mean of the per-rank
+    gradients computed WITHOUT the bucket (plain autograd path); (2) the all-reduced int64 confusion matrix equals the matrix one
+    rank computes over the union of all ranks' frames.  Returns "ok" or raises."""
+    import torch.distributed as dist
+    for p in head.parameters():
+        p.grad = None
+    xg = x.detach().requires_grad_(True)
+    loss, _ = head.forward_loss(xg, labels, grad_bucket=bucket)
+    loss.backward()
+    bucket.wait()
+    reduced = torch.cat([p.grad.reshape(-1) for p in head.parameters()]).clone()
+    for p in head.parameters():
+        p.grad = None
+    xg = x.detach().requires_grad_(True)
+    loss, _ = head.forward_loss(xg, labels)
+    loss.backward()
+    local = torch.cat([p.grad.reshape(-1) for p in head.parameters()]).clone()
+    for p in head.parameters():
+        p.grad = None
+    all_reduced = [torch.empty_like(reduced) for _ in range(world)]
+    all_local = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(all_reduced, reduced)
+    dist.all_gather(all_local, local)
+    for r in range(1, world):
+        if not torch.equal(all_reduced[r], all_reduced[0]):
+            raise RuntimeError(f"dp_check: bucket gradients differ between rank 0 and rank {r}")
+    mean = torch.stack([t.double() for t in all_local]).mean(0)
+    err = ((reduced.double() - mean).abs().max() / mean.abs().max()).item()
+    if not err <= 1e-6:
+        raise RuntimeError(f"dp_check: all-reduced gradients != mean of per-rank gradients (rel err {err:.3e})")
+    # eval: frames rank::world of a common list; every rank can regenerate any frame (seeded CUDA generators)
+    C, frames_total = 19, 2 * world
+
+    def frame(i):
+        g = torch.Generator(device=dev).manual_seed(9000 + i)
+        lg = torch.randn(1, C, 64, 128, device=dev, generator=g)
+        y = torch.randint(0, C, (1, 512, 1024), device=dev, generator=g)
+        y[:, : 64 * (i % 3)] = 255
+        return lg, y
+
+    cm = torch.zeros(C, C, dtype=torch.int64, device=dev)
+    for i in D.shard_indices(frames_total, rank, world):
+        lg, y = frame(i)
+        b200.segmentation_eval_step(lg, y, cm=cm)
+    D.allreduce_confusion_(cm)
+    union = torch.zeros_like(cm)
+    for i in range(frames_total):
+        lg, y = frame(i)
+        b200.segmentation_eval_step(lg, y, cm=union)
+    if not torch.equal(cm, union):
+        raise RuntimeError("dp_check: all-reduced confusion matrix != single-rank matrix over the union of the shards")
+    return "ok"
 
 
 def run_tta_and_optim(b200, _lib, dev, rank, peaks):
@@ -484,39 +669,71 @@ def run_adv_step(b200, _lib, synth, dev, rank, world, peaks, args):
     with_opt = [False]
     opt_cls = b200.FusedSGD(head.parameters(), lr=2.5e-3, momentum=0.9, weight_decay=5e-4)     # aspp_trainer.py:26
     opt_d = b200.FusedAdam(model_D.parameters(), lr=1e-4, betas=(0.9, 0.99))                   # fada_adapter.py:24
+    # N > 1: DDP semantics for both modules (train_adv.py shards the data but never synchronises).  Head gradients:
+    # flat bucket, mean all-reduce underneath the head's data-gradient GEMM.  Discriminator gradients (20.2 MB): flat bucket the
+    # two discriminator backward passes accumulate into, mean all-reduce started after the second one on the bucket's stream and
+    # joined only before the discriminator is used again -- i.e. it overlaps the NEXT iteration's source-domain head step.
+    from rnd_semantic_segmentation_b200 import distributed as D
+    hb = D.HeadGradBucket(head) if world > 1 else None
+    db = D.OverlappedGradBucket(model_D.parameters()) if world > 1 else None
 
     def adv_step():
         b200.clear_feature_pack_cache()                       # new features every iteration: 2 conversions per step, not 0
-        for p in list(head.parameters()) + list(model_D.parameters()):
+        if hb is not None:
+            hb.wait()                                         # (last iteration's head all-reduce / optimizer step)
+        for p in head.parameters():
             p.grad = None
-        # weights change every iteration in training: both modules re-pack their bf16 weights once per step
-        torch.autograd.graph.increment_version([head.conv2d_list[0].weight, model_D.cls1.weight])
+        if db is None:
+            for p in model_D.parameters():
+                p.grad = None
+        # (both modules are in training mode: their bf16 weight packs are rebuilt on every call)
         src_fea = src.detach().requires_grad_(True)
         tgt_fea = tgt.detach().requires_grad_(True)
-        loss_seg, src_lr = head.forward_loss(src_fea, lab, temperature=1.8)              # aspp_fada.py:91-96
+        loss_seg, src_lr = head.forward_loss(src_fea, lab, temperature=1.8, grad_bucket=hb)   # aspp_fada.py:91-96
         loss_seg.backward()
         with torch.no_grad():
             tgt_lr = head.logits(tgt_fea)                                                # :101-104 (soft labels are detached)
+        if db is not None:
+            db.wait()                                         # last iteration's discriminator all-reduce (+ Adam step) is done
         if freeze[0]:                                         # variant: D's own gradients of this pass are discarded at :117 anyway
             for p in model_D.parameters():
                 p.requires_grad_(False)
         loss_adv = 0.001 * model_D.forward_soft_loss(tgt_fea, tgt_lr, size, slot=0)      # :110-112
         loss_adv.backward()
         if with_opt[0]:
-            opt_cls.step()                                                               # :115 (K8)
+            if hb is not None:
+                hb.step(opt_cls)                                                         # :115 behind the head all-reduce
+            else:
+                opt_cls.step()                                                           # :115 (K8)
         for p in model_D.parameters():                                                   # optimizer_D.zero_grad(), :117
-            p.grad = None
             p.requires_grad_(True)
+        if db is not None:
+            db.zero_grads_()
+        else:
+            for p in model_D.parameters():
+                p.grad = None
         loss_d_src = 0.5 * model_D.forward_soft_loss(src_fea.detach(), src_lr, size, slot=0)   # :119-121
         loss_d_src.backward()
         loss_d_tgt = 0.5 * model_D.forward_soft_loss(tgt_fea.detach(), tgt_lr, size, slot=1)   # :123-125
         loss_d_tgt.backward()
-        if with_opt[0]:
+        if db is not None:
+            db.begin_allreduce_()
+            if with_opt[0]:
+                db.step(opt_d)                                                           # :127 behind the all-reduce
+        elif with_opt[0]:
             opt_d.step()                                                                 # :127 (K8)
         return loss_seg, loss_adv, loss_d_src, loss_d_tgt
 
+    def adv_step_sync():                                      # the timed unit: the iteration AND the collectives it started
+        out = adv_step()
+        return out
+
     l0 = _lib.launch_count()
     ms, _ = timed(adv_step, args.steps, args.warmup)
+    if db is not None:
+        db.wait()
+    if hb is not None:
+        hb.wait()
     launches = (_lib.launch_count() - l0) * args.steps // (args.steps + args.warmup)
     ms_step = ms / args.steps
     _lib.profile_enable(True)
@@ -534,6 +751,8 @@ def run_adv_step(b200, _lib, synth, dev, rank, world, peaks, args):
     # the whole iteration (~100 launches) captured once in a CUDA graph and replayed: what the launch gaps cost
     graph_ms = None
     try:
+        if world > 1:
+            raise RuntimeError("single-rank leg (the NCCL collectives stay out of the graph)")
         for p in list(head.parameters()) + list(model_D.parameters()):
             p.grad = None
         b200.clear_feature_pack_cache()
@@ -560,7 +779,9 @@ def run_adv_step(b200, _lib, synth, dev, rank, world, peaks, args):
             "ms_per_step": round(ms_step, 4), "gpu_launches": int(launches),
             "config": {"workload": "deeplabv2_r101_adv", "features_per_domain": [an, cin, ah, aw], "labels": [an, aH, aW],
                        "num_classes": aC, "discriminator": "PixelDiscriminator(2048, ndf=256) -> 2 x 19",
-                       "step": "aspp_fada.py:91-125 after the backbone, optimizer steps excluded; source + target label pixels counted"},
+                       "step": "aspp_fada.py:91-125 after the backbone, optimizer steps excluded; source + target label pixels counted"
+                               + ("; mean all-reduce of the head gradients (5.6 MB, under the head dgrad GEMM) and of the discriminator"
+                                  " gradients (20.2 MB, overlapping the next iteration's head step) inside the timed region" if world > 1 else "")},
             "roofline": {"kernel": "conv_gemm_kernel (tcgen05 implicit GEMM; discriminator fwd / dgrad / wgrad launches)", "bound": "tensor",
                          "achieved": round(tf, 1), "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": round(tf / peaks["bf16_tflops_sustained"], 4), "traffic": load_traffic("conv3x3_fwd"),
@@ -661,9 +882,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "aspp_ce_train_Mpx_per_s", "value": round(r["value"], 4), "unit": "Mpx/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["ms_per_step"], 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "features": [n, cin, h, w], "labels": [n, H, W], "num_classes": C,
-                       "note": "reference's CPU path (oracle port of classifier.py:26-32 + CrossEntropyLoss + backward) on the host cores; "
-                               "each step is a bounded one-image sample of the workload"},
+            "config": workload_config(args.workload, args.gpus),
+            "note": "reference's CPU path (oracle port of classifier.py:26-32 + CrossEntropyLoss + backward) on the host cores; "
+                    "each step is a bounded one-image sample of the workload (per-pixel normalised)",
             "cpu_baseline": r["cpu_baseline"],
             "e2e": {"value": round(r["value"], 4), "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)

@@ -19,7 +19,7 @@ from . import _lib, ops
 from .ops import soft_label_cross_entropy  # noqa: F401  (re-exported under the reference's name)
 
 __all__ = ["soft_label_cross_entropy", "inference", "multi_scale_inference", "intersectionAndUnion", "intersectionAndUnionGPU",
-           "confusion_matrix", "AverageMeter", "segmentation_eval_step", "iutr_from_confusion", "LazyProbabilities",
+           "confusion_matrix", "AverageMeter", "segmentation_eval_step", "iutr_from_confusion", "LazyProbabilities", "BatchedEvaluator",
            "pseudo_label_map", "get_color_palette", "save_pseudo_label"]
 
 
@@ -88,6 +88,55 @@ def segmentation_eval_step(logits_lr: torch.Tensor, labels: torch.Tensor, ignore
     labels = _lib.as_label_tensor(labels)              # int64 or uint8 consumed as they are
     return _lib.upsample_argmax_confusion(logits_lr.float().contiguous(), labels.contiguous(), labels.shape[-2:],
                                           ignore_index=ignore_index, cm=cm, per_frame=per_frame, want_pred=want_pred)
+
+
+class BatchedEvaluator:
+    """The tester loop of aspp_tester.py:57-72 after the backbone, with the upsample + argmax + confusion-matrix kernel (K4) run
+    over SEVERAL frames per launch: ``step(features, labels)`` runs the head for the frame (TEST.BATCH_SIZE = 1, as the reference)
+    and queues its low-res logits (2.5 MB) with the frame's labels (int64 or uint8, used in place -- no copy); every ``frames``
+    steps one launch processes the queued frames.  A single 1024 x 2048 frame is too little work to fill 148 SMs with tall tiles
+    (34 us per frame launched alone, 19 us per frame at 8 per launch), so batching the launches is what the eval img/s needs.
+    ``finish()`` flushes the queue and returns the int64 [C,C] matrix (with ``per_frame=True`` also the list of per-frame
+    matrices, for the macro metrics of AverageMeter).  Bit-identical to one ``segmentation_eval_step`` per frame."""
+
+    def __init__(self, classifier, num_classes: int, ignore_index: int = 255, frames: int = 8, per_frame: bool = False, device=None):
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.classifier, self.ignore_index, self.frames, self.per_frame = classifier, ignore_index, max(1, int(frames)), per_frame
+        self.cm = torch.zeros(num_classes, num_classes, dtype=torch.int64, device=dev)
+        self.frame_cms = []
+        self._logits, self._labels = [], []
+
+    def step(self, features: torch.Tensor, labels: torch.Tensor):
+        with torch.no_grad():
+            lg = self.classifier.logits(features)
+        return self.step_logits(lg, labels)
+
+    def step_logits(self, logits_lr: torch.Tensor, labels: torch.Tensor):
+        n = logits_lr.shape[0]
+        labels = _lib.as_label_tensor(labels).reshape(n, *labels.shape[-2:])
+        for f in range(n):
+            self._logits.append(logits_lr[f].detach().float().contiguous())
+            self._labels.append(labels[f].contiguous())
+        if len(self._logits) >= self.frames:
+            self.flush()
+        return self.cm
+
+    def flush(self):
+        if not self._logits:
+            return
+        if self.per_frame:
+            cms, _ = _lib.upsample_argmax_confusion_frames(self._logits, self._labels, self._labels[0].shape[-2:],
+                                                           ignore_index=self.ignore_index, per_frame=True)
+            self.frame_cms.extend(cms.unbind(0))
+            self.cm += cms.sum(0)
+        else:
+            _lib.upsample_argmax_confusion_frames(self._logits, self._labels, self._labels[0].shape[-2:],
+                                                  ignore_index=self.ignore_index, cm=self.cm)
+        self._logits, self._labels = [], []
+
+    def finish(self):
+        self.flush()
+        return (self.cm, self.frame_cms) if self.per_frame else self.cm
 
 
 class OverlappedEvaluator:

@@ -591,3 +591,32 @@ def test_k2_warp_tile_kernel_against_oracle_and_cta_tile_kernel(lib, n, C, h, w,
         assert torch.equal(l2_ng, l2)
         l2b, g2b, _ = run(2, lg)
         assert torch.equal(l2b, l2) and torch.equal(g2b, g2)
+
+
+@pytest.mark.parametrize("ldtype", [torch.int64, torch.uint8])
+def test_batched_evaluator_equals_per_frame_loop(lib, ldtype):
+    """BatchedEvaluator (K4 over several queued frames per launch): the same int64 matrix and per-frame matrices as one
+    segmentation_eval_step per frame, for a frame count that is not a multiple of the batch."""
+    import rnd_semantic_segmentation_b200 as b200
+    from rnd_semantic_segmentation_b200 import synth
+    C = 19
+    torch.manual_seed(3)
+    head = synth.scale_head_for_unit_logits(b200.ASPP_Classifier_V2(256, RATES, RATES, C)).cuda().eval()
+    frames = [(torch.relu(torch.randn(1, 256, 32, 64, generator=torch.Generator().manual_seed(10 + i))).cuda(),
+               make_labels(1, 256, 512, C, 0.1, 20 + i).cuda().to(ldtype)) for i in range(11)]
+    cm_seq = torch.zeros(C, C, dtype=torch.int64, device="cuda")
+    per = []
+    for x, y in frames:
+        with torch.no_grad():
+            c1, _ = b200.segmentation_eval_step(head.logits(x), y)
+        per.append(c1)
+        cm_seq += c1
+    ev = b200.BatchedEvaluator(head, C, frames=4, per_frame=True)
+    for x, y in frames:
+        ev.step(x, y)
+    cm, cms = ev.finish()
+    assert torch.equal(cm, cm_seq) and len(cms) == len(per) and all(torch.equal(a, b) for a, b in zip(cms, per))
+    ev2 = b200.BatchedEvaluator(head, C, frames=8)
+    for x, y in frames:
+        ev2.step(x, y)
+    assert torch.equal(ev2.finish(), cm_seq)

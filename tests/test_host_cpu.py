@@ -184,6 +184,32 @@ def _dist_worker(rank, world, port, tmp):
     for i, p in enumerate(head.parameters()):
         assert torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1)))       # mean of ranks (1, 2)
         assert p.grad.data_ptr() >= bucket.flat.data_ptr()
+    # the discriminator's overlapped bucket (DDP semantics for the module train_adv.py never synchronises): .grad stays aliased to
+    # the flat buffer across zero_grads_(), two backward passes accumulate in place, the mean lands in every rank's .grad, and the
+    # optimizer step behind it leaves bit-identical parameters on all ranks
+    torch.manual_seed(1)
+    model_D = b200.PixelDiscriminator(8, 8, num_classes=3)
+    dbucket = D.OverlappedGradBucket(model_D.parameters())
+    opt = torch.optim.Adam(model_D.parameters(), lr=1e-2, betas=(0.9, 0.99))
+    for it in range(2):
+        dbucket.zero_grads_()
+        for k in range(2):                                  # two backward passes into the same gradients (aspp_fada.py:119-125)
+            loss = sum(((p * float(rank + 1 + k + it)) ** 2).sum() for p in model_D.parameters())
+            loss.backward()
+        local = [p.grad.clone() for p in model_D.parameters()]
+        assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(dbucket.params, dbucket.views))
+        dbucket.begin_allreduce_()
+        dbucket.step(opt)
+        dbucket.wait()
+        gathered = [[torch.empty_like(g) for _ in range(world)] for g in local]
+        for g, out in zip(local, gathered):
+            torch.distributed.all_gather(out, g)
+        for p, out in zip(model_D.parameters(), gathered):
+            assert torch.allclose(p.grad, sum(out) / world, rtol=1e-6, atol=0)
+    flat_params = torch.cat([p.detach().reshape(-1) for p in model_D.parameters()])
+    both = [torch.empty_like(flat_params) for _ in range(world)]
+    torch.distributed.all_gather(both, flat_params)
+    assert torch.equal(both[0], both[1])
     # eval sharding: frames rank::world, int64 confusion matrix summed exactly
     frames = D.shard_indices(7, rank, world)
     cm = torch.zeros(3, 3, dtype=torch.int64)
