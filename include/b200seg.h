@@ -269,6 +269,18 @@ B200SEG_API int b200seg_tta_argmax_confusion_ex(const float* const* logits_lr, c
                                                 int ignore_index, const float* divisors, int n_div, int div_exact, int64_t* cm,
                                                 void* pred, int pred_bytes, float* probs, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Mean all-reduce of a flat fp32 gradient bucket over NVLink / NVSwitch peer memory (one kernel per rank)
+ *   replaces  the gradient all-reduce of DistributedDataParallel      train_distill.py:54-62 (mean over ranks)
+ *   The bucket lives in symmetric memory: peer_bufs_host[q] = rank q's bucket as mapped into THIS process, signal_pads_host[q] =
+ *   rank q's signal pad (uint32 flags, all zero between calls), multicast_ptr = the bucket's NVSwitch multicast address or NULL
+ *   (then plain peer loads / stores are used).  numel: bucket length in floats, a multiple of 4.  Every rank must enqueue the call
+ *   (the kernels meet at two cross-rank barriers); `blocks` CTAs of 512 threads, using pad slots [pad_slot0, pad_slot0 + blocks).
+ *   On return of the kernel every rank's bucket holds sum over ranks / world, bit-identical on all ranks.
+ * ------------------------------------------------------------------------------------------- */
+B200SEG_API int b200seg_p2p_allreduce_mean(void* const* peer_bufs_host, void* multicast_ptr, void* const* signal_pads_host, int rank,
+                                           int world, int64_t numel, int blocks, int pad_slot0, void* stream);
+
 /* ensembles of up to four members: 1 (default) = the row-walking kernel (horizontal lerps of the two current source rows kept per
  * thread in shared memory and re-used for every output row between them), 0 = the per-pixel kernel used for larger ensembles
  * (A/B experiments; the results are bit-identical).  Bit 1 set (on = 3): row walking without the labels-only fast path (when no

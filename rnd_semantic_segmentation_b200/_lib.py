@@ -41,6 +41,7 @@ SIGNATURES = {
     "b200seg_upsample_ce_forward": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_int, c_f32, c_int, c_vp,
                                             c_i64, c_vp, c_vp]),
     "b200seg_upsample_ce_set_variant": (None, [c_int]),
+    "b200seg_p2p_allreduce_mean": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_int, c_vp]),
     "b200seg_upsample_ce_backward": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp, c_vp]),
     "b200seg_upsample_ce_backward_packed": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b200seg_upsample_bilinear_forward": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
@@ -454,6 +455,17 @@ def upsample_ce_forward(logits_lr, labels, ignore_index=255, inv_temperature=1.0
                                                   float(inv_temperature), 1 if need_grad else 0, ws.data_ptr(), nbytes,
                                                   out2.data_ptr(), _stream()))
     return out2, ws
+
+
+def p2p_allreduce_mean(peer_ptrs: Sequence[int], multicast_ptr: int, signal_pad_ptrs: Sequence[int], rank: int, world: int, numel: int,
+                       blocks: int = 8, pad_slot0: int = 0, device=None):
+    """Enqueue the peer-memory mean all-reduce kernel on the current stream of ``device`` (every rank must)."""
+    lib = load()
+    n = len(peer_ptrs)
+    bufs = (c_vp * n)(*[int(v) for v in peer_ptrs])
+    pads = (c_vp * n)(*[int(v) for v in signal_pad_ptrs])
+    _check(lib.b200seg_p2p_allreduce_mean(bufs, int(multicast_ptr) if multicast_ptr else None, pads, int(rank), int(world), int(numel),
+                                          int(blocks), int(pad_slot0), _stream(device)))
 
 
 def upsample_ce_set_variant(v: int):

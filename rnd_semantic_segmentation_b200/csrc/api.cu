@@ -94,6 +94,7 @@ int tta_launch(const float* const*, const int*, const int*, const int*, int, int
                long long*, void*, int, float*, cudaStream_t);
 void tta_set_row_walk(int);
 void k2_set_variant(int);
+int p2p_allreduce_mean(void* const*, void*, void* const*, int, int, long long, int, int, cudaStream_t);
 int sgd_step(int, float* const*, const float* const*, float* const*, const long long*, float, float, float, float, int, int, float,
              cudaStream_t);
 int adam_step(int, float* const*, const float* const*, float* const*, float* const*, const long long*, float, float, float, float,
@@ -406,6 +407,12 @@ int b200seg_tta_argmax_confusion_ex(const float* const* logits_lr, const int* h,
 
 void b200seg_tta_set_row_walk(int on) { tta_set_row_walk(on); }
 void b200seg_upsample_ce_set_variant(int v) { k2_set_variant(v); }
+
+int b200seg_p2p_allreduce_mean(void* const* peer_bufs_host, void* multicast_ptr, void* const* signal_pads_host, int rank, int world,
+                               int64_t numel, int blocks, int pad_slot0, void* stream) {
+  REQUIRE_DEVICE();
+  return p2p_allreduce_mean(peer_bufs_host, multicast_ptr, signal_pads_host, rank, world, numel, blocks, pad_slot0, S(stream));
+}
 
 int b200seg_sgd_step(int n_tensors, float* const* params, const float* const* grads, float* const* momentum_bufs,
                      const int64_t* numels, float lr, float momentum, float dampening, float weight_decay, int nesterov,

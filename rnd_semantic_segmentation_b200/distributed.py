@@ -44,15 +44,47 @@ def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_items, world))
 
 
+_symm_warned = [False]
+
+
+def symmetric_flat_buffer(numel: int, device, group=None):
+    """(buffer, handle) -- ``numel`` fp32 (rounded up to a multiple of 4) in NVLink symmetric memory, mapped by every rank of
+    ``group`` (torch's symmetric-memory rendezvous: plumbing for the peer / multicast / signal-pad addresses our own all-reduce
+    kernel works on, csrc/p2p_allreduce.cu) -- or None when that is not available (CPU / gloo, single rank, B200SEG_P2P_ALLREDUCE=0,
+    no peer access).  A collective call: every rank must make it, in the same order."""
+    if os.environ.get("B200SEG_P2P_ALLREDUCE", "1") == "0" or not is_distributed():
+        return None
+    if torch.device(device).type != "cuda" or dist.get_backend(group) != "nccl":
+        return None
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        n4 = (int(numel) + 3) // 4 * 4
+        buf = symm_mem.empty(n4, dtype=torch.float32, device=torch.device(device))
+        hdl = symm_mem.rendezvous(buf, group=group if group is not None else dist.group.WORLD)
+        buf.zero_()
+        return buf, hdl
+    except Exception as e:                                  # pragma: no cover  (depends on the box)
+        if not _symm_warned[0]:
+            _symm_warned[0] = True
+            print(f"b200seg: symmetric memory unavailable ({e!r}); gradient buckets fall back to NCCL", flush=True)
+        return None
+
+
 class FlatGradBucket:
     """One flat fp32 buffer holding all gradients of a module; parameters' .grad are views into it, so the
-    step's all-reduce is ONE collective (head: 1 400 908 fp32 = 5.6 MB; discriminator: 20.2 MB)."""
+    step's all-reduce is ONE collective (head: 1 400 908 fp32 = 5.6 MB; discriminator: 20.2 MB).  ``symmetric``: place the buffer
+    in NVLink symmetric memory so that the all-reduce can be our own peer-memory kernel instead of NCCL."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    def __init__(self, params: Iterable[torch.nn.Parameter], symmetric: bool = False, group=None):
         self.params = [p for p in params if p.requires_grad]
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._symm = symmetric_flat_buffer(total, dev, group) if symmetric else None
+        if self._symm is not None:
+            self._flat_full = self._symm[0]                  # padded to 4 floats; the tail stays zero
+            self.flat = self._flat_full[:total]
+        else:
+            self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         off = 0
         self.views = []
         for p in self.params:
@@ -69,8 +101,18 @@ class FlatGradBucket:
         for p, v in zip(self.params, self.views):
             p.grad = v
 
+    def p2p_allreduce_mean_(self, blocks: int = 8):
+        """Our own mean all-reduce over peer memory (csrc/p2p_allreduce.cu), enqueued on the CURRENT stream; every rank must call it."""
+        from . import _lib
+        buf, hdl = self._symm
+        _lib.p2p_allreduce_mean(hdl.buffer_ptrs, getattr(hdl, "multicast_ptr", 0) or 0, hdl.signal_pad_ptrs, hdl.rank, hdl.world_size,
+                                buf.numel(), blocks=blocks, device=buf.device)
+
     def allreduce_mean_(self, group=None):
         self.gather_grads()
+        if self._symm is not None:
+            self.p2p_allreduce_mean_()
+            return self.flat
         if is_distributed():
             if dist.get_backend(group) == "nccl":
                 dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)      # mean inside the collective
@@ -92,16 +134,20 @@ class OverlappedGradBucket(FlatGradBucket):
     NEXT iteration's head forward / backward -- joins.  The collective and the update therefore overlap the next iteration's
     source-domain head step instead of sitting between iterations."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], group=None):
-        super().__init__(params)
+    def __init__(self, params: Iterable[torch.nn.Parameter], group=None, p2p_blocks: int = 16):
+        super().__init__(params, symmetric=True, group=group)
         self.group = group
+        self.p2p_blocks = int(p2p_blocks)
         self._pending = False
         self.stream = torch.cuda.Stream(device=self.flat.device) if self.flat.is_cuda else None
         self.ready_event = torch.cuda.Event() if self.flat.is_cuda else None
-        if is_distributed() and self.flat.is_cuda:           # build the communicator's channels now, not in the first steps
+        if is_distributed() and self.flat.is_cuda:           # first launches / communicator channels now, not in the first steps
             with torch.cuda.stream(self.stream):
                 for _ in range(2):
-                    dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+                    if self._symm is not None:
+                        self.p2p_allreduce_mean_(self.p2p_blocks)
+                    else:
+                        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             torch.cuda.current_stream().wait_stream(self.stream)
             self.flat.zero_()
 
@@ -122,7 +168,9 @@ class OverlappedGradBucket(FlatGradBucket):
         self.ready_event.record()
         self.stream.wait_event(self.ready_event)
         with torch.cuda.stream(self.stream):
-            if dist.get_backend(self.group) == "nccl":
+            if self._symm is not None:
+                self.p2p_allreduce_mean_(self.p2p_blocks)
+            elif dist.get_backend(self.group) == "nccl":
                 dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
             else:
                 dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
@@ -156,16 +204,19 @@ class HeadGradBucket(FlatGradBucket):
         #   2 ranks:  4 -> 0.928   8 -> 0.842   16 -> 0.846   32 -> 0.890   (no all-reduce 0.851, all-reduce afterwards 0.885)
         #   4 ranks:  4 -> 0.989   8 -> 0.885   16 -> 0.857   32 -> 0.868   (no all-reduce 0.852, all-reduce afterwards 0.892)
         #   8 ranks:  4 -> 1.277   8 -> 1.068   16 -> 0.971   32 -> 0.867   (no all-reduce 0.854, all-reduce afterwards 0.944)
+        convs = list(head.conv2d_list)
+        # bucket order: the R weights, then the R biases as one [R, C] block.  In symmetric memory when the box allows it: the
+        # all-reduce is then our own peer-memory kernel (NVSwitch multimem reduce + broadcast, csrc/p2p_allreduce.cu) on 8 CTAs,
+        # so the data-gradient GEMM cedes 8 SMs at any world size instead of the 8 / 16 / 32 an NCCL ring needs to finish in time.
+        super().__init__([m.weight for m in convs] + [m.bias for m in convs], symmetric=True, group=group)
         if overlap_ctas is None:
             world = dist.get_world_size() if is_distributed() else 1
-            overlap_ctas = 8 if world <= 2 else (16 if world <= 4 else 32)
-        convs = list(head.conv2d_list)
-        # bucket order: the R weights, then the R biases as one [R, C] block
-        super().__init__([m.weight for m in convs] + [m.bias for m in convs])
+            overlap_ctas = 8 if (self._symm is not None or world <= 2) else (16 if world <= 4 else 32)
+        self.p2p_blocks = int(overlap_ctas) if overlap_ctas > 0 else 8
         self.R = len(convs)
         # The persistent dgrad GEMM fills every SM's shared memory, so nothing else can be resident beside it: it leaves
         # `overlap_ctas` SMs free, and the all-reduce runs on a dedicated NCCL communicator capped at that many CTAs.
-        if group is None and is_distributed() and dist.get_backend() == "nccl" and overlap_ctas > 0:
+        if self._symm is None and group is None and is_distributed() and dist.get_backend() == "nccl" and overlap_ctas > 0:
             try:
                 opts = dist.ProcessGroupNCCL.Options()
                 opts.config.max_ctas = int(overlap_ctas)
@@ -188,7 +239,10 @@ class HeadGradBucket(FlatGradBucket):
         if is_distributed() and self.flat.is_cuda:
             with torch.cuda.stream(self.stream):
                 for _ in range(3):
-                    dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+                    if self._symm is not None:
+                        self.p2p_allreduce_mean_(self.p2p_blocks)
+                    else:
+                        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             torch.cuda.current_stream().wait_stream(self.stream)
 
     def weight_buffers(self):
@@ -204,7 +258,9 @@ class HeadGradBucket(FlatGradBucket):
             return
         self.stream.wait_event(self.ready_event)     # weight gradients (and the bias block enqueued before them) are complete
         with torch.cuda.stream(self.stream):
-            if dist.get_backend(self.group) == "nccl":
+            if self._symm is not None:
+                self.p2p_allreduce_mean_(self.p2p_blocks)
+            elif dist.get_backend(self.group) == "nccl":
                 dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
             else:
                 dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
