@@ -167,6 +167,14 @@ B200SEG_API int b200seg_aspp_pack_features(const float* x_nchw, int N, int Cin, 
 B200SEG_API int64_t b200seg_aspp_forward_scratch_bytes(int N, int C, int h, int w, int R);
 B200SEG_API int b200seg_aspp_forward(const void* Xp, const void* Wp, const float* bias_sum, const int* rates_host, int R, int N,
                          int Cin, int C, int h, int w, void* scratch, float* logits, void* stream);
+/* The same forward straight from the reference's fp32 NCHW features x [N,Cin,h,w] (classifier.py:26-29): the fp32 -> bf16
+ * conversion of the pixel operand happens inside the GEMM's producer warps -- no b200seg_aspp_pack_features pass, no packed copy.
+ * xn_bf16_nchw (optional, [N,Cin,h,w] bf16): a copy of the rounded features for the backward pass's weight-gradient GEMM.
+ * Eligible shapes (b200seg_aspp_forward_f32_supported != 0): h*w % 4 == 0, Cin % 64 == 0, at least two 128-row tiles of packed
+ * weights (e.g. 19 classes), x 16-byte aligned; otherwise returns an error and the caller packs. */
+B200SEG_API int b200seg_aspp_forward_f32_supported(const float* x, int Cin, int C, int h, int w, int R);
+B200SEG_API int b200seg_aspp_forward_f32(const float* x, const void* Wp, const float* bias_sum, const int* rates_host, int R, int N,
+                                         int Cin, int C, int h, int w, void* scratch, float* logits, void* xn_bf16_nchw, void* stream);
 B200SEG_API int64_t b200seg_aspp_backward_scratch_bytes(int N, int Cin, int C, int h, int w, int R, int splits);
 /* grad_x (f32 NCHW, may be NULL), grad_w[r] / grad_b[r] (may be NULL) are overwritten, not accumulated */
 B200SEG_API int b200seg_aspp_backward(const float* grad_logits, const void* Xp, const void* WpT, const int* rates_host, int R, int N,
@@ -328,6 +336,12 @@ B200SEG_API void b200seg_gemm_set_narrow_tiles(int on);
  * 0 (default) = shared-memory transpose + 16-byte LSU stores.  Measured equal (180.8 vs 179.4 us): the 537 MB of writes
  * themselves, not the store instructions, are what the kernel waits for */
 B200SEG_API void b200seg_gemm_set_tma_store(int on);
+/* 1: the head's forward takes fp32 NCHW features through the GEMM with in-kernel conversion (below) where the shape is eligible;
+ * 0 (default): pack + plain GEMM.  Measured equal at the eval shape (158.8 vs 158.3 us); kept as a tested option. */
+B200SEG_API void b200seg_gemm_set_fwd_convert(int on);
+/* on-device self-test of that kernel against a CUDA-core reference on bf16-rounded x; xn_err: max |bf16 copy - bf16(x)| */
+B200SEG_API int b200seg_gemm_fwd_convert_selftest(int M, int n_img, int hw, int K, int write_xn, double* max_err, double* max_ref,
+                                      double* xn_err);
 /* fp32 NCHW data-gradient GEMM tile order: 1 = consecutive tiles walk along the pixel axis (each channel row of dX is written as
  * long sequential runs), 0 = along the channel axis (tiles sharing the gradient operand adjacent in time) */
 B200SEG_API void b200seg_gemm_set_dgrad_n_fastest(int on);

@@ -61,6 +61,10 @@ SIGNATURES = {
     "b200seg_aspp_pack_features": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "b200seg_aspp_forward_scratch_bytes": (c_i64, [c_int] * 5),
     "b200seg_aspp_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "b200seg_aspp_forward_f32_supported": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int]),
+    "b200seg_aspp_forward_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "b200seg_gemm_set_fwd_convert": (None, [c_int]),
+    "b200seg_gemm_fwd_convert_selftest": (c_int, [c_int] * 5 + [ctypes.POINTER(ctypes.c_double)] * 3),
     "b200seg_aspp_backward_scratch_bytes": (c_i64, [c_int] * 7),
     "b200seg_aspp_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64, c_int,
                                       c_vp, c_vp, c_vp, c_vp]),
@@ -136,6 +140,8 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
         lib.b200seg_gemm_set_tma_store(int(os.environ["B200SEG_TMA_STORE"]))
     if os.environ.get("B200SEG_GEMM_NARROW"):
         lib.b200seg_gemm_set_narrow_tiles(int(os.environ["B200SEG_GEMM_NARROW"]))
+    if os.environ.get("B200SEG_FWD_CONVERT"):
+        lib.b200seg_gemm_set_fwd_convert(int(os.environ["B200SEG_FWD_CONVERT"]))
     if os.environ.get("B200SEG_CONV_PAIR"):
         lib.b200seg_conv_set_pair(int(os.environ["B200SEG_CONV_PAIR"]))
     return lib
@@ -695,14 +701,56 @@ def aspp_forward(Xp: torch.Tensor, Wp: torch.Tensor, bias_sum: torch.Tensor, rat
     return logits
 
 
+def aspp_forward_f32_supported(x: torch.Tensor, C: int, R: int) -> bool:
+    """True when the head's forward can take these fp32 NCHW features through the GEMM with in-kernel conversion."""
+    if x.dtype != torch.float32 or not x.is_cuda or not x.is_contiguous() or x.dim() != 4:
+        return False
+    N, Cin, h, w = x.shape
+    return bool(load().b200seg_aspp_forward_f32_supported(x.data_ptr(), Cin, C, h, w, R))
+
+
+def aspp_forward_f32(x: torch.Tensor, Wp: torch.Tensor, bias_sum: torch.Tensor, rates: Sequence[int], C: int, want_xn: bool = False):
+    """Head forward straight from fp32 NCHW features (no pack pass).  Returns (logits fp32 [N,C,h,w], xn bf16 [N,Cin,h,w] | None)."""
+    lib = load()
+    _need(x, torch.float32, "features")
+    _need(Wp, torch.bfloat16, "Wp")
+    _need(bias_sum, torch.float32, "bias_sum")
+    N, Cin, h, w = x.shape
+    R = len(rates)
+    nbytes = lib.b200seg_aspp_forward_scratch_bytes(N, C, h, w, R)
+    scratch = _scratch("aspp_fwd", nbytes, x.device)
+    logits = torch.empty((N, C, h, w), dtype=torch.float32, device=x.device)
+    xn = torch.empty((N, Cin, h, w), dtype=torch.bfloat16, device=x.device) if want_xn else None
+    rates_arr = (c_int * R)(*[int(r) for r in rates])
+    with _on_device(x.device):
+        _check(lib.b200seg_aspp_forward_f32(x.data_ptr(), Wp.data_ptr(), bias_sum.data_ptr(), rates_arr, R, N, Cin, C, h, w,
+                                            scratch.data_ptr(), logits.data_ptr(), _ptr(xn), _stream()))
+    return logits, xn
+
+
+def gemm_fwd_convert_selftest(M, n_img, hw, K, write_xn=True):
+    lib = load()
+    err, ref, xe = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_double(0)
+    _check(lib.b200seg_gemm_fwd_convert_selftest(M, n_img, hw, K, int(write_xn), ctypes.byref(err), ctypes.byref(ref), ctypes.byref(xe)))
+    return err.value, ref.value, xe.value
+
+
+def gemm_set_fwd_convert(on):
+    """True: fp32 NCHW features go through the forward GEMM with in-kernel conversion where eligible; False (default): pack + GEMM
+    (measured equal; env B200SEG_FWD_CONVERT=1 turns it on at load time)."""
+    load().b200seg_gemm_set_fwd_convert(1 if on else 0)
+
+
 def aspp_backward(grad_logits: torch.Tensor, Xp: torch.Tensor, WpT: torch.Tensor, rates: Sequence[int], N: int, h: int, w: int,
                   C: int, need_grad_x: bool = True, need_grad_w: bool = True, need_grad_b: bool = True, splits: int = 0):
     """Returns (grad_x fp32 NCHW | None, [grad_w]*R | None, [grad_b]*R | None)."""
     lib = load()
     grad_logits = _need(grad_logits.contiguous(), torch.float32, "grad_logits")
-    Cin = Xp.shape[1]
+    Cin = WpT.shape[0]
     R = len(rates)
-    dev = Xp.device
+    dev = WpT.device
+    if Xp is None and need_grad_w:
+        raise B200SegError("aspp_backward: the weight gradient needs the packed features")
     if splits <= 0:
         splits = default_wgrad_splits(N * h * w, C, Cin, R)
     nbytes = lib.b200seg_aspp_backward_scratch_bytes(N, Cin, C, h, w, R, splits)
@@ -712,7 +760,7 @@ def aspp_backward(grad_logits: torch.Tensor, Xp: torch.Tensor, WpT: torch.Tensor
     gbs = [torch.empty(C, dtype=torch.float32, device=dev) for _ in range(R)] if need_grad_b else None
     rates_arr = (c_int * R)(*[int(r) for r in rates])
     with _on_device(dev):
-        _check(lib.b200seg_aspp_backward(grad_logits.data_ptr(), Xp.data_ptr(), WpT.data_ptr(), rates_arr, R, N, Cin, C, h, w,
+        _check(lib.b200seg_aspp_backward(grad_logits.data_ptr(), _ptr(Xp), WpT.data_ptr(), rates_arr, R, N, Cin, C, h, w,
                                          scratch.data_ptr(), nbytes, splits, _ptr(gx),
                                          _ptr_array(gws) if gws else None, _ptr_array(gbs) if gbs else None, _stream()))
     return gx, gws, gbs
@@ -727,9 +775,11 @@ def aspp_backward_packed(gOt: torch.Tensor, Xp: torch.Tensor, WpT: torch.Tensor,
     ``weights_ready_event`` is recorded on the current stream once they are complete, before the data-gradient GEMM."""
     lib = load()
     _need(gOt, torch.bfloat16, "gOt")
-    Cin = Xp.shape[1]
+    Cin = WpT.shape[0]
     R = len(rates)
-    dev = Xp.device
+    dev = WpT.device
+    if Xp is None and need_grad_w:
+        raise B200SegError("aspp_backward_packed: the weight gradient needs the packed features")
     if splits <= 0:
         splits = default_wgrad_splits(N * h * w, C, Cin, R)
     nbytes = lib.b200seg_aspp_backward_scratch_bytes(N, Cin, C, h, w, R, splits)
@@ -751,7 +801,7 @@ def aspp_backward_packed(gOt: torch.Tensor, Xp: torch.Tensor, WpT: torch.Tensor,
             gx = torch.empty((N, Cin, h, w), dtype=torch.float32, device=dev)
     ev = None if weights_ready_event is None else weights_ready_event.cuda_event
     with _on_device(dev):
-        _check(lib.b200seg_aspp_backward_packed_ex(gOt.data_ptr(), Xp.data_ptr(), WpT.data_ptr(), rates_arr, R, N, Cin, C, h, w,
+        _check(lib.b200seg_aspp_backward_packed_ex(gOt.data_ptr(), _ptr(Xp), WpT.data_ptr(), rates_arr, R, N, Cin, C, h, w,
                                                    scratch.data_ptr(), nbytes, splits, _ptr(gx), _ptr(gx_nhwc),
                                                    _ptr_array(gws) if gws else None, ev, _stream()))
     if gx_nhwc is not None:

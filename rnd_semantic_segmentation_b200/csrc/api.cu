@@ -70,6 +70,8 @@ int aspp_pack_weights(const float* const*, const float* const*, int, int, int, v
 int aspp_pack_features(const float*, int, int, int, int, void*, cudaStream_t);
 long long aspp_yt_bytes(int, int, int, int, int);
 int aspp_forward(const void*, const void*, const float*, const int*, int, int, int, int, int, int, float*, float*, cudaStream_t);
+int aspp_forward_f32(const float*, const void*, const float*, const int*, int, int, int, int, int, int, float*, float*, void*, cudaStream_t);
+int aspp_forward_f32_supported(const float*, int, int, int, int, int);
 long long aspp_bwd_scratch_bytes(int, int, int, int, int, int, int);
 int aspp_backward(const float*, const void*, const void*, const int*, int, int, int, int, int, int, void*, long long, int, float*,
                   float* const*, float* const*, cudaStream_t);
@@ -107,6 +109,8 @@ void set_overlap_sms(int);
 void set_narrow_tiles(int);
 void set_n_fastest(int);
 void set_tma_store(int);
+void set_fwd_convert(int);
+int selftest_fwd_convert(int, int, int, int, int, double*, double*, double*);
 }
 
 static int require_device() {
@@ -314,6 +318,16 @@ int b200seg_aspp_forward(const void* Xp, const void* Wp, const float* bias_sum, 
   return aspp_forward(Xp, Wp, bias_sum, rates_host, R, N, Cin, C, h, w, reinterpret_cast<float*>(scratch), logits, S(stream));
 }
 
+int b200seg_aspp_forward_f32_supported(const float* x, int Cin, int C, int h, int w, int R) {
+  return aspp_forward_f32_supported(x, Cin, C, h, w, R);
+}
+
+int b200seg_aspp_forward_f32(const float* x, const void* Wp, const float* bias_sum, const int* rates_host, int R, int N, int Cin, int C,
+                             int h, int w, void* scratch, float* logits, void* xn_bf16_nchw, void* stream) {
+  REQUIRE_DEVICE();
+  return aspp_forward_f32(x, Wp, bias_sum, rates_host, R, N, Cin, C, h, w, reinterpret_cast<float*>(scratch), logits, xn_bf16_nchw, S(stream));
+}
+
 int64_t b200seg_aspp_backward_scratch_bytes(int N, int Cin, int C, int h, int w, int R, int splits) {
   if (N <= 0 || C <= 0 || h <= 0 || w <= 0 || R <= 0) return 0;
   return aspp_bwd_scratch_bytes(N, Cin, C, h, w, R, splits < 1 ? 1 : splits);
@@ -465,6 +479,11 @@ void b200seg_gemm_set_sharing(int on) { gemm::set_sharing(on); }
 void b200seg_gemm_set_narrow_tiles(int on) { gemm::set_narrow_tiles(on); }
 void b200seg_gemm_set_dgrad_n_fastest(int on) { gemm::set_n_fastest(on); }
 void b200seg_gemm_set_tma_store(int on) { gemm::set_tma_store(on); }
+void b200seg_gemm_set_fwd_convert(int on) { gemm::set_fwd_convert(on); }
+int b200seg_gemm_fwd_convert_selftest(int M, int n_img, int hw, int K, int write_xn, double* max_err, double* max_ref, double* xn_err) {
+  REQUIRE_DEVICE();
+  return gemm::selftest_fwd_convert(M, n_img, hw, K, write_xn, max_err, max_ref, xn_err);
+}
 void b200seg_gemm_set_overlap_sms(int n) { gemm::set_overlap_sms(n); }
 
 int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b_mn_major, int splits, int col_hw, int share, double* max_err,

@@ -447,6 +447,43 @@ int aspp_forward(const void* Xp, const void* Wp, const float* bias_sum, const in
   return B200SEG_OK;
 }
 
+// The same forward straight from the fp32 NCHW features the reference hands over (classifier.py:26-29): the fp32 -> bf16
+// conversion of the pixel operand happens inside the GEMM's producer warps (gemm_fwd_convert_kernel), so there is no separate
+// pack pass (146 us at the bench workload, 77 us per eval frame) and no packed copy to read back.  `xn` (optional): the bf16
+// NCHW copy of x the weight-gradient GEMM of the backward pass consumes.  Returns B200SEG_ERR_UNSUPPORTED for shapes the fused
+// kernel does not take (h*w % 4 != 0, Cin % 64 != 0, fewer than two M-tiles); aspp_forward_f32_supported() tells beforehand.
+int aspp_forward_f32_supported(const float* x, int Cin, int C, int h, int w, int R) {
+  return gemm::fwd_convert_eligible(x, Cin, h * w, aspp_nj(C, R)) ? 1 : 0;
+}
+
+int aspp_forward_f32(const float* x, const void* Wp, const float* bias_sum, const int* rates, int R, int N, int Cin, int C, int h,
+                     int w, float* Yt, float* logits, void* xn, cudaStream_t stream) {
+  B200SEG_CHECK_ARG(x && Wp && bias_sum && rates && Yt && logits, "aspp_forward_f32: null pointer");
+  B200SEG_CHECK_ARG(R >= 1 && R <= MAX_RATES, "aspp: %d dilation branches unsupported", R);
+  const long long P = (long long)N * h * w;
+  B200SEG_CHECK_ARG(P < (1LL << 31), "aspp_forward: too many pixels");
+  const int NJ = aspp_nj(C, R);
+  if (!gemm::fwd_convert_eligible(x, Cin, h * w, NJ)) {
+    set_error("aspp_forward_f32: shape not supported by the fused-conversion GEMM (h*w=%d, Cin=%d)", h * w, Cin);
+    return B200SEG_ERR_UNSUPPORTED;
+  }
+  const long long ypitch = ceil_div_ll(P, 4) * 4;
+  int rc = gemm::launch_fwd_convert((const __nv_bfloat16*)Wp, Cin, x, N, h * w, NJ, Cin, Yt, ypitch, (__nv_bfloat16*)xn, stream, 0);
+  if (rc) return rc;
+  TapTable tt;
+  make_taps(tt, rates, R);
+  const int CT = (C == 19) ? 5 : (C <= 4 ? 4 : 8);
+  const int nchunk = ceil_div(C, CT);
+  dim3 grid(ceil_div(w, GATHER_THREADS), h, N * nchunk);
+  profile_begin(4, stream);
+  if (CT == 5) head_gather_kernel<5><<<grid, GATHER_THREADS, 0, stream>>>(Yt, ypitch, tt, bias_sum, C, nchunk, h, w, logits);
+  else if (CT == 4) head_gather_kernel<4><<<grid, GATHER_THREADS, 0, stream>>>(Yt, ypitch, tt, bias_sum, C, nchunk, h, w, logits);
+  else head_gather_kernel<8><<<grid, GATHER_THREADS, 0, stream>>>(Yt, ypitch, tt, bias_sum, C, nchunk, h, w, logits);
+  profile_end(4, stream);
+  B200SEG_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
 // scratch: gOc bf16 [N][C][hw] (P*32 elements reserved) | G't [NJ][Ppitch] bf16 | wpart [S][NJ][Cin] fp32
 long long aspp_bwd_scratch_bytes(int N, int Cin, int C, int h, int w, int R, int splits) {
   const long long P = (long long)N * h * w;
@@ -470,7 +507,8 @@ void* aspp_bwd_gOt_ptr(void* scratch) { return scratch; }
 int aspp_backward_packed(const void* gOt_in, const void* Xp, const void* WpT, const int* rates, int R, int N, int Cin, int C,
                          int h, int w, void* scratch, long long scratch_bytes, int splits, float* grad_x, float* const* grad_w,
                          cudaStream_t stream, void* grad_x_nhwc_bf16, cudaEvent_t weights_ready) {
-  B200SEG_CHECK_ARG(gOt_in && Xp && WpT && rates && scratch, "aspp_backward: null pointer");
+  B200SEG_CHECK_ARG(gOt_in && WpT && rates && scratch, "aspp_backward: null pointer");
+  B200SEG_CHECK_ARG(Xp != nullptr || grad_w == nullptr, "aspp_backward: the weight gradient needs the packed features");
   B200SEG_CHECK_ARG(R >= 1 && R <= MAX_RATES, "aspp: %d dilation branches unsupported", R);
   B200SEG_CHECK_ARG(C <= 32, "aspp_backward: num_classes=%d > 32 is not supported", C);
   if (splits < 1) splits = 1;

@@ -224,6 +224,83 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
 }
 
 // ------------------------------------------------------------------------------------------
+// forward GEMM with the fp32 NCHW -> bf16 conversion of the pixel operand inside the kernel
+// ------------------------------------------------------------------------------------------
+// b200seg_gemm_set_fwd_convert(): 1 = the head's forward takes fp32 NCHW features through gemm_fwd_convert_kernel where eligible.
+// Default 0: measured EQUAL to pack + plain GEMM at the eval shape (158.8 vs 158.3 us per 1 x 2048 x 128 x 256 frame) -- a ring
+// stage is converted only after it has been released, so convert + proxy fence + cluster-scope publish (~2.5 us, most of it the
+// fence waiting for the remote stores) sits in every stage's critical path; see DESIGN.md for what would remove it.
+static int g_fwd_convert = 0;
+void set_fwd_convert(int on) { g_fwd_convert = on; }
+
+bool fwd_convert_eligible(const float* x, int K, int hw, int M) {
+  const int m_pairs = (ceil_div(M, BLOCK_M) + 1) / 2;
+  return g_fwd_convert && g_share_enabled != 0 && x != nullptr && hw > 0 && hw % 4 == 0 && K % BLOCK_K == 0 && M > BLOCK_M &&
+         m_pairs <= FWDX_MAX_MP && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+}
+
+template <int MP>
+static int launch_fwd_convert_t(const CUtensorMap& ta, const FwdXParams& p, cudaStream_t stream, int prof_tag) {
+  static bool configured = false;
+  static int max_clusters = 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(FWDX_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2 * MP;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (!configured) {
+    B200SEG_CUDA(cudaFuncSetAttribute(gemm_fwd_convert_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    // how many clusters of this size the device can hold at once (GPC granularity): the grid is sized to it
+    cfg.gridDim = dim3(2 * MP * (num_sms() / (2 * MP)));
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_fwd_convert_kernel<MP>, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = num_sms() / (2 * MP);
+    }
+    max_clusters = n;
+    configured = true;
+  }
+  const int clusters = p.n_tiles < max_clusters ? p.n_tiles : max_clusters;
+  cfg.gridDim = dim3(2 * MP * clusters);
+  profile_begin(prof_tag, stream);
+  B200SEG_CUDA(cudaLaunchKernelEx(&cfg, gemm_fwd_convert_kernel<MP>, ta, p));
+  profile_end(prof_tag, stream);
+  B200SEG_LAUNCH_CHECK();
+  return B200SEG_OK;
+}
+
+int launch_fwd_convert(const __nv_bfloat16* a, long long a_pitch, const float* x, int n_img, int hw, int M, int K, float* out,
+                       long long row_stride, __nv_bfloat16* xn, cudaStream_t stream, int prof_tag) {
+  B200SEG_CHECK_ARG(fwd_convert_eligible(x, K, hw, M), "gemm: forward-with-conversion called on an ineligible shape");
+  B200SEG_CHECK_ARG(xn == nullptr || (reinterpret_cast<uintptr_t>(xn) & 15) == 0, "gemm: the bf16 feature copy must be 16-byte aligned");
+  const long long P = (long long)n_img * hw;
+  B200SEG_CHECK_ARG(P < (1LL << 31), "gemm: too many pixels");
+  FwdXParams p;
+  p.M = M; p.P = (int)P; p.K = K;
+  p.m_tiles = ceil_div(M, BLOCK_M);
+  p.n_tiles = ceil_div((int)P, BLOCK_N);
+  p.kb_total = K / BLOCK_K;
+  p.out = out; p.row_stride = row_stride;
+  p.x = x; p.hw = hw; p.xn = xn;
+  CUtensorMap ta;
+  int rc = make_tmap(&ta, a, K, M, a_pitch, BLOCK_K, BLOCK_M);
+  if (rc) return rc;
+  switch ((p.m_tiles + 1) / 2) {
+    case 1: return launch_fwd_convert_t<1>(ta, p, stream, prof_tag);
+    case 2: return launch_fwd_convert_t<2>(ta, p, stream, prof_tag);
+    default: return launch_fwd_convert_t<3>(ta, p, stream, prof_tag);
+  }
+}
+
+int fwd_convert_max_clusters(int mp) { (void)mp; return 0; }
+
+// ------------------------------------------------------------------------------------------
 // Self-test helpers
 // ------------------------------------------------------------------------------------------
 __global__ void fill_bf16_kernel(__nv_bfloat16* p, long long n, uint32_t seed) {
@@ -311,6 +388,71 @@ int selftest(int M, int N, int K, int a_mn, int b_mn, int splits, int col_hw, in
     }
   }
   cudaFree(A); cudaFree(B); cudaFree(D); cudaFree(ref); cudaFree(res);
+  return rc;
+}
+
+// ---- self-test of the forward-with-conversion kernel: fp32 NCHW x, reference on bf16-rounded x; also checks the bf16 copy ----
+__global__ void fill_f32_kernel(float* p, long long n, uint32_t seed) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t x = (uint32_t)i * 2654435761u + seed;
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  p[i] = ((float)(x & 0xFFFFFF) / 16777216.0f - 0.5f) * 2.0f;
+}
+__global__ void naive_fwdx_kernel(const __nv_bfloat16* A, const float* x, float* C, int M, int P, int K, int hw, long long a_pitch) {
+  int pcol = blockIdx.x * blockDim.x + threadIdx.x;
+  int m = blockIdx.y;
+  if (pcol >= P || m >= M) return;
+  const int img = pcol / hw, off = pcol - img * hw;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k)
+    acc = fmaf(__bfloat162float(A[(long long)m * a_pitch + k]), __bfloat162float(__float2bfloat16(x[((long long)img * K + k) * hw + off])), acc);
+  C[(long long)m * P + pcol] = acc;
+}
+__global__ void compare_xn_kernel(const float* x, const __nv_bfloat16* xn, long long n, float* out1) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float d = fabsf(__bfloat162float(xn[i]) - __bfloat162float(__float2bfloat16(x[i])));
+  if (!(d == 0.f)) atomicMax(reinterpret_cast<int*>(out1), __float_as_int(d != d ? 1e30f : d));
+}
+
+int selftest_fwd_convert(int M, int n_img, int hw, int K, int write_xn, double* max_err, double* max_ref, double* xn_err) {
+  const long long P = (long long)n_img * hw;
+  const long long a_pitch = K, xe = (long long)n_img * K * hw;
+  const long long row_stride = ((P + 3) / 4) * 4;
+  __nv_bfloat16 *A = nullptr, *xn = nullptr;
+  float *x = nullptr, *D = nullptr, *ref = nullptr, *res = nullptr;
+  B200SEG_CUDA(cudaMalloc(&A, (long long)M * a_pitch * 2));
+  B200SEG_CUDA(cudaMalloc(&x, xe * 4));
+  B200SEG_CUDA(cudaMalloc(&xn, xe * 2));
+  B200SEG_CUDA(cudaMalloc(&D, (long long)M * row_stride * 4));
+  B200SEG_CUDA(cudaMalloc(&ref, (long long)M * P * 4));
+  B200SEG_CUDA(cudaMalloc(&res, 16));
+  B200SEG_CUDA(cudaMemset(res, 0, 16));
+  B200SEG_CUDA(cudaMemset(D, 0xFF, (long long)M * row_stride * 4));
+  B200SEG_CUDA(cudaMemset(xn, 0xFF, xe * 2));
+  fill_bf16_kernel<<<(unsigned)ceil_div_ll((long long)M * a_pitch, 256), 256>>>(A, (long long)M * a_pitch, 4321u);
+  fill_f32_kernel<<<(unsigned)ceil_div_ll(xe, 256), 256>>>(x, xe, 99u);
+  dim3 g(ceil_div((int)P, 128), M);
+  naive_fwdx_kernel<<<g, 128>>>(A, x, ref, M, (int)P, K, hw, a_pitch);
+  B200SEG_LAUNCH_CHECK();
+  int rc = launch_fwd_convert(A, a_pitch, x, n_img, hw, M, K, D, row_stride, write_xn ? xn : nullptr, 0, -1);
+  if (rc == B200SEG_OK) {
+    compare_kernel<<<g, 128>>>(D, ref, M, (int)P, 1, 0, row_stride, INT_MAX, 0, res);
+    if (write_xn) compare_xn_kernel<<<(unsigned)ceil_div_ll(xe, 256), 256>>>(x, xn, xe, res + 2);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      set_error("gemm fwd-convert selftest: kernel failed: %s", cudaGetErrorString(e));
+      rc = B200SEG_ERR_CUDA;
+    } else {
+      float h[3];
+      cudaMemcpy(h, res, 12, cudaMemcpyDeviceToHost);
+      *max_err = (h[0] != h[0]) ? 1e30 : (double)h[0];
+      *max_ref = (double)h[1];
+      *xn_err = (double)h[2];
+    }
+  }
+  cudaFree(A); cudaFree(x); cudaFree(xn); cudaFree(D); cudaFree(ref); cudaFree(res);
   return rc;
 }
 

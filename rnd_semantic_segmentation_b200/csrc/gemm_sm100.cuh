@@ -612,6 +612,302 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Forward GEMM of the ASPP head that reads the features as the reference hands them over -- fp32 NCHW -- and converts them to
+// the bf16 MMA operand INSIDE the kernel (no separate fp32 -> bf16 pack pass, no packed copy read back):
+//
+//   D[M x P] (fp32, row-major) = A[M x K] (bf16 K-major, TMA) * X[K x P]     X = fp32 NCHW features, K = channel, P = n*hw + pixel
+//
+// A cluster of 2 * MP CTAs owns ONE 256-pixel tile and ALL MP pairs of 128-row M-tiles (MP = 3 for the 19-class head: 640 packed
+// weight rows).  CTAs (2q, 2q+1) form pair q and drive one tcgen05.mma.cta_group::2 exactly as SHARE_PAIR above: each CTA stages
+// its own A tile by TMA and holds HALF r = rank & 1 of the B tile.  The B halves are PRODUCED by converter warps, once per cluster:
+// k-block kb of half r is converted by CTA (2 (kb % MP) + r) -- lane l of a warp loads 16 bytes = 4 consecutive pixels of one
+// channel row (a warp instruction = 512 contiguous bytes of x), rounds to bf16 (RN, as the pack kernel does) and stores 8 bytes
+// into the MN-major, 128-byte-swizzled operand box of EVERY CTA holding half r (its own shared memory and the peers' through
+// distributed shared memory) -- the NCHW layout IS the MN-major layout, so no transposition is involved.  x therefore crosses
+// L2 -> SM once per pixel tile (fp32 in, 10.7 KB per k-block per SM) instead of three times, and each converter has MP k-blocks of
+// lead.  A stage's full barrier (on each pair's leader) counts the leader's TMA arrive + one arrive per half from the converting
+// CTA's signaller warp (the converter threads fence their generic-proxy writes to the async proxy and meet the signaller at a
+// named barrier; the signaller's arrive carries the cluster-scope release); a stage is released to the cluster only when all MP
+// pairs have consumed it (empty barriers count MP, commits multicast to the whole cluster).
+// Optionally the bf16 values are also written out as NCHW (`xn`) for the weight-gradient GEMM of the backward pass.
+// ------------------------------------------------------------------------------------------
+constexpr int CONV_WARPS = 8;
+constexpr int FWDX_EPI_WARPS = 4;              // one per TMEM lane quarter, all 256 columns each (the epilogue hides behind a 32-k-block main loop)
+constexpr int FWDX_THREADS = (4 + FWDX_EPI_WARPS + CONV_WARPS) * 32;   // 512: warps 0-3 control, 4-7 epilogue, 8-15 convert -> 128 registers per thread,
+                                                                        // so the converters' 16 loads in flight per lane stay in registers
+constexpr int FWDX_MAX_MP = 3;               // 2 * MP <= ring stages (see the converters); 3 M-pairs = 768 packed weight rows = 23 classes
+
+struct FwdXParams {
+  int M, P, K;                       // rows of A / D, pixels (columns of D), channels
+  int m_tiles, n_tiles, kb_total;
+  float* out;                        // D [M][row_stride] fp32
+  long long row_stride;
+  const float* x;                    // fp32 NCHW [N][K][hw]
+  int hw;
+  __nv_bfloat16* xn;                 // optional bf16 NCHW copy of x (null: not written)
+};
+
+__device__ __forceinline__ void st_cluster_v2(uint32_t cluster_addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(cluster_addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+template <int MP>
+__global__ void __launch_bounds__(FWDX_THREADS, 1)
+gemm_fwd_convert_kernel(const __grid_constant__ CUtensorMap tmap_a, const FwdXParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  constexpr int STAGES = PAIR_STAGES;
+  constexpr int STAGE_BYTES = PAIR_STAGE_BYTES;                     // 16 KB A + 16 KB B half
+  constexpr int CS = 2 * MP;                                        // CTAs per cluster
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_FLOATS * 4);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)cluster_cta_rank();
+  const int q = rank >> 1, r = rank & 1;                            // pair (= M-pair) and pixel half of this CTA
+  const uint32_t leader = (uint32_t)(rank & ~1);
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_a);
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1 + 2);                               // leader's TMA arrive + the signaller of each half's converting CTA
+      mbar_init(&empty_bar[s], MP);                                 // every pair of the cluster has consumed the stage
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 2 * FWDX_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work unit = one 256-pixel tile; cluster c takes tiles c, c + nclusters, ...
+  const int units = p.n_tiles;
+  const int worker = (int)blockIdx.x / CS, nworkers = (int)gridDim.x / CS;
+  const int my_units = worker < units ? (units - worker + nworkers - 1) / nworkers : 0;
+
+  if (warp == 0) {
+    // ================= TMA producer: the A tile of this CTA =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int m0 = (q * 2 + r) * BLOCK_M;
+      const uint32_t fb0 = mapa_u32(smem_u32(&full_bar[0]), leader);
+      for (int u = 0; u < my_units; ++u) {
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (r == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * A_BYTES);
+          tma_load_2d_2sm(smem_u32(smem + stage * STAGE_BYTES), &tmap_a, fb0 + (uint32_t)stage * 8u, kb * BLOCK_K, m0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (the pair's leader CTA, one thread) =================
+    if (lane == 0 && r == 0) {
+      constexpr uint32_t idesc = make_idesc(false, true, 2 * BLOCK_M, BLOCK_N);
+      constexpr uint16_t all_mask = (uint16_t)((1u << CS) - 1u);
+      const uint16_t pair_mask = (uint16_t)(0x3u << (2 * q));
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = 0; u < my_units; ++u) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = make_smem_desc(sa + k * 32, 16, 1024);                    // K-major A
+            const uint64_t bdesc = make_smem_desc(sb + k * 2048, MN_BOX_BYTES, 1024);        // MN-major B (two 64-pixel boxes)
+            umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage], all_mask);             // this pair is done with the stage, in every CTA of the cluster
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(&tfull_bar[acc], pair_mask);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + FWDX_EPI_WARPS) {
+    // ================= epilogue: fp32 row-major D, 16-byte coalesced stores (as gemm_bf16_kernel's plain path) =================
+    const int wq = warp & 3;
+    float* stg = epi_stage + (warp - 4) * EPI_STAGE_FLOATS;
+    const bool vec_ok = (p.row_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    const uint32_t te0 = mapa_u32(smem_u32(&tempty_bar[0]), leader);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = 0; u < my_units; ++u) {
+      const int nt = worker + u * nworkers;
+      const int row_base = (q * 2 + r) * BLOCK_M + wq * 32;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int rows = min(32, p.M - row_base);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+      const int col_base = nt * BLOCK_N + half * (BLOCK_N / 2);
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BLOCK_N + half * (BLOCK_N / 2));
+      if (rows > 0 && col_base < p.P) {
+        constexpr int NCH = BLOCK_N / 2 / 16;
+        const int lane_col = vec_ok ? (lane & 3) * 4 : (lane & 15);
+        uint32_t rbuf[2][16];
+        tmem_ld16(taddr, rbuf[0]);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          tmem_ld_wait();
+          const uint32_t* rr_ = rbuf[c & 1];
+          if (c + 1 < NCH) tmem_ld16(taddr + (uint32_t)((c + 1) * 16), rbuf[(c + 1) & 1]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<float4*>(stg + lane * EPI_PITCH + 4 * k) =
+                make_float4(__uint_as_float(rr_[4 * k]), __uint_as_float(rr_[4 * k + 1]), __uint_as_float(rr_[4 * k + 2]),
+                            __uint_as_float(rr_[4 * k + 3]));
+          __syncwarp();
+          const int col0 = col_base + c * 16;
+          float* dst = p.out + (long long)row_base * p.row_stride + col0 + lane_col;
+          if (vec_ok) {
+            if (col0 + lane_col + 3 < p.P) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rr = (lane >> 2) + 8 * i;
+                if (rr < rows)
+                  *reinterpret_cast<float4*>(dst + (long long)rr * p.row_stride) = *reinterpret_cast<const float4*>(stg + rr * EPI_PITCH + lane_col);
+              }
+            } else {
+              for (int e = 0; e < 4; ++e)
+                if (col0 + lane_col + e < p.P)
+                  for (int i = 0; i < 4; ++i) {
+                    const int rr = (lane >> 2) + 8 * i;
+                    if (rr < rows) dst[(long long)rr * p.row_stride + e] = stg[rr * EPI_PITCH + lane_col + e];
+                  }
+            }
+          } else if (col0 + lane_col < p.P) {
+            for (int rr = (lane >> 4); rr < rows; rr += 2) dst[(long long)rr * p.row_stride] = stg[rr * EPI_PITCH + lane_col];
+          }
+          __syncwarp();
+        }
+      }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(te0 + (uint32_t)acc * 8u);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else if (warp >= 4 + FWDX_EPI_WARPS) {
+    // ================= converters: fp32 NCHW -> the bf16 MN-major half r of every pair, k-blocks kb % MP == q =================
+    // Two groups of four warps take the CTA's owned k-blocks alternately (group g: owned blocks g, g + 2, ...).  Inside a group
+    // warp cw owns channel rows [16 cw, 16 cw + 16) of the k-block and lane l pixels [4 l, 4 l + 4) of the 128-pixel half.  A
+    // group's loads for its NEXT block are issued right after it has published the current one (the proxy fence before the
+    // barrier arrive would otherwise wait for them), so every lane has 16 loads in flight for two owned blocks = 2 MP k-block
+    // periods: 64 KB per SM, enough to cover the HBM latency at the rate the tensor core consumes.
+    const int cwarp = warp - (4 + FWDX_EPI_WARPS);
+    const int grp = cwarp >> 2, cw = cwarp & 3;
+    // ownership by the cluster-wide k-block counter c = unit * kb_total + kb: CTA q converts c % MP == q, group (c / MP) % 2.
+    // A group's consecutive blocks are therefore exactly 2 MP <= STAGES counters apart, so when it comes back to a stage the
+    // use before the previous one has certainly been consumed and the parity wait below cannot be fooled (see static_assert).
+    static_assert(2 * MP <= STAGES, "a converter group must revisit the ring within one lap (parity waits)");
+    const int total_c = my_units * p.kb_total;
+    const uint32_t box_off = (uint32_t)(lane >> 4) * MN_BOX_BYTES + (uint32_t)(lane & 1) * 8;   // 64-pixel box + half of the 16-byte chunk
+    const uint32_t chunk = (uint32_t)((lane & 15) >> 1);
+    const uint32_t smem_s = smem_u32(smem);
+    uint32_t dst_base[MP];                                                     // the MP CTAs holding half r
+#pragma unroll
+    for (int d = 0; d < MP; ++d) dst_base[d] = mapa_u32(smem_s, (uint32_t)(2 * d + r));
+    float4 buf[16];
+    const float* src = nullptr;
+    __nv_bfloat16* dstn = nullptr;
+    // loads of the block with counter c (source address, by-product address)
+    auto fetch_block = [&](int c) {
+      const int u = c / p.kb_total;
+      const int kb = c - u * p.kb_total;
+      const int nt = worker + u * nworkers;
+      const long long px = (long long)nt * BLOCK_N + r * (BLOCK_N / 2) + 4 * lane;
+      src = nullptr; dstn = nullptr;
+      if (px < p.P) {
+        const int img = (int)(px / p.hw);
+        const long long off = ((long long)img * p.K + kb * BLOCK_K + 16 * cw) * p.hw + (px - (long long)img * p.hw);
+        src = p.x + off;
+        if (p.xn != nullptr) dstn = p.xn + off;
+      }
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) buf[rr] = src ? ld_stream_f4(src + (long long)rr * p.hw) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    const int c_first = q + MP * grp;
+    if (c_first < total_c) fetch_block(c_first);
+#pragma unroll 1
+    for (int c = c_first; c < total_c; c += 2 * MP) {
+      const int stage = c % STAGES;
+      const uint32_t phase = (uint32_t)(c / STAGES) & 1u;
+      mbar_wait(&empty_bar[stage], phase ^ 1u);                     // all MP pairs have released this stage (in every CTA)
+      const uint32_t so = (uint32_t)(stage * STAGE_BYTES + A_BYTES) + box_off;
+#pragma unroll
+      for (int rr = 0; rr < 16; ++rr) {
+        const int row = 16 * cw + rr;
+        const float4 v = buf[rr];
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(&lo), w1 = *reinterpret_cast<const uint32_t*>(&hi);
+        const uint32_t o = so + (uint32_t)row * 128u + ((chunk ^ (uint32_t)(row & 7)) << 4);
+#pragma unroll
+        for (int d = 0; d < MP; ++d) st_cluster_v2(dst_base[d] + o, w0, w1);
+        if (dstn != nullptr) *reinterpret_cast<uint2*>(dstn + (long long)rr * p.hw) = make_uint2(w0, w1);
+      }
+      fence_proxy_async_all();                                      // this thread's generic-proxy writes -> visible to the async proxy
+      named_bar_sync(1 + grp, 4 * 32 + 32);                         // the group's block is complete: hand it to the signaller warp
+      if (c + 2 * MP < total_c) fetch_block(c + 2 * MP);            // in flight while the other group converts and the cluster advances
+    }
+  } else if (warp == 3) {
+    // ================= signaller: publishes the converted blocks (release at cluster scope) =================
+    // The barrier arrives carry release semantics over the whole cluster (a memory barrier each); keeping them off the converter
+    // threads means those can put their next loads in flight immediately instead of draining them behind the barrier.
+    const int total_c = my_units * p.kb_total;
+    uint32_t dst_full[MP];
+#pragma unroll
+    for (int d = 0; d < MP; ++d) dst_full[d] = mapa_u32(smem_u32(&full_bar[0]), (uint32_t)(2 * d));
+#pragma unroll 1
+    for (int c = q; c < total_c; c += MP) {
+      const int grp = (c / MP) & 1;
+      named_bar_sync(1 + grp, 4 * 32 + 32);
+      if (lane == 0) {
+        const uint32_t stage = (uint32_t)(c % STAGES);
+        asm volatile("fence.acq_rel.cluster;" ::: "memory");
+#pragma unroll
+        for (int d = 0; d < MP; ++d)
+          asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(dst_full[d] + stage * 8u) : "memory");
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
 // Host side (gemm_sm100.cu)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -623,6 +919,11 @@ struct Operand {
   bool mn_major;        // false: [rows][K] K contiguous; true: [K][rows] rows contiguous
   long long pitch;      // elements between consecutive outer-dimension entries
 };
+// forward GEMM with in-kernel fp32 NCHW -> bf16 conversion of the pixel operand (see gemm_fwd_convert_kernel); returns
+// B200SEG_ERR_UNSUPPORTED when the shape is not eligible (hw % 4, K % 64, alignment) -- the caller then packs and uses launch()
+bool fwd_convert_eligible(const float* x, int K, int hw, int M);
+int launch_fwd_convert(const __nv_bfloat16* a, long long a_pitch, const float* x, int n_img, int hw, int M, int K, float* out,
+                       long long row_stride, __nv_bfloat16* xn, cudaStream_t stream, int prof_tag);
 int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, float* out, long long row_stride,
            int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used, int prof_tag = -1,
            int share = SHARE_NONE, bool out_bf16 = false, int sm_reserve = 0, int pair_fallback = SHARE_B);

@@ -59,11 +59,17 @@ def _pixel_major_bf16(x: torch.Tensor) -> torch.Tensor:
     return Xp
 
 
+def _fused_convert_ok(x: torch.Tensor, C: int, R: int) -> bool:
+    """fp32 NCHW features can go straight into the forward GEMM (conversion in its producer warps, no pack pass) -- unless the
+    caller turned the cross-module conversion cache on, in which case the packed copy is wanted for the other consumers."""
+    return _PACK_CACHE_SLOTS <= 0 and x.is_cuda and x.dtype == torch.float32 and _lib.aspp_forward_f32_supported(x.contiguous(), C, R)
+
+
 class _AsppHeadFn(torch.autograd.Function):
     """out[N,C,h,w] = sum_r conv3x3(x; W_r, b_r, dilation=padding=rates[r])  (classifier.py:26-29)."""
 
     @staticmethod
-    def forward(ctx, x, rates, packed, *params):
+    def forward(ctx, x, rates, packed, need_w, *params):
         R = len(rates)
         weights, biases = params[:R], params[R:]
         N, Cin, h, w = x.shape
@@ -71,9 +77,14 @@ class _AsppHeadFn(torch.autograd.Function):
         if packed is None:
             packed = _lib.aspp_pack_weights([p.detach() for p in weights], [None if b is None else b.detach() for b in biases])
         Wp, WpT, bias_sum = packed
+        ctx.rates, ctx.shape, ctx.x_dtype = tuple(rates), (N, Cin, h, w, C), x.dtype
+        if not need_w and _fused_convert_ok(x, C, R):
+            # eval / frozen head: straight from the fp32 NCHW features, no pack pass and nothing of x kept for backward
+            logits, _ = _lib.aspp_forward_f32(x.detach().contiguous(), Wp, bias_sum, rates, C)
+            ctx.save_for_backward(None, WpT)
+            return logits
         Xp = _pixel_major_bf16(x.detach())
         logits = _lib.aspp_forward(Xp, Wp, bias_sum, rates, N, h, w, C)
-        ctx.rates, ctx.shape, ctx.x_dtype = tuple(rates), (N, Cin, h, w, C), x.dtype
         ctx.save_for_backward(Xp, WpT)
         return logits
 
@@ -82,21 +93,22 @@ class _AsppHeadFn(torch.autograd.Function):
         Xp, WpT = ctx.saved_tensors
         N, Cin, h, w, C = ctx.shape
         R = len(ctx.rates)
-        need = ctx.needs_input_grad
+        need = ctx.needs_input_grad          # x, rates, packed, need_w, R weights, R biases
         need_x = need[0]
-        need_w = any(need[3:3 + R])
-        need_b = any(need[3 + R:3 + 2 * R])
+        need_w = any(need[4:4 + R])
+        need_b = any(need[4 + R:4 + 2 * R])
         gx, gws, gbs = _lib.aspp_backward(grad_logits.float(), Xp, WpT, ctx.rates, N, h, w, C, need_x, need_w, need_b)
         if gx is not None and ctx.x_dtype != torch.float32:
             gx = gx.to(ctx.x_dtype)
-        out_w = [gws[r] if (gws is not None and need[3 + r]) else None for r in range(R)]
-        out_b = [gbs[r] if (gbs is not None and need[3 + R + r]) else None for r in range(R)]
-        return (gx, None, None, *out_w, *out_b)
+        out_w = [gws[r] if (gws is not None and need[4 + r]) else None for r in range(R)]
+        out_b = [gbs[r] if (gbs is not None and need[4 + R + r]) else None for r in range(R)]
+        return (gx, None, None, None, *out_w, *out_b)
 
 
 def aspp_head(x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]],
               rates: Sequence[int], packed=None) -> torch.Tensor:
-    return _AsppHeadFn.apply(x, tuple(int(r) for r in rates), packed, *weights, *biases)
+    need_w = torch.is_grad_enabled() and any(p.requires_grad for p in weights)
+    return _AsppHeadFn.apply(x, tuple(int(r) for r in rates), packed, need_w, *weights, *biases)
 
 
 class _AsppHeadLossFn(torch.autograd.Function):

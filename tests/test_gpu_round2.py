@@ -620,3 +620,54 @@ def test_batched_evaluator_equals_per_frame_loop(lib, ldtype):
     for x, y in frames:
         ev2.step(x, y)
     assert torch.equal(ev2.finish(), cm_seq)
+
+
+# ------------------------------------------------------------------ forward GEMM with in-kernel fp32 NCHW -> bf16 conversion
+@pytest.mark.parametrize("M,n_img,hw,K,write_xn", [(256, 1, 256, 64, 1), (640, 1, 8192, 2048, 1), (640, 2, 1936, 256, 0), (640, 3, 1000, 128, 1),
+                                                   (300, 1, 516, 192, 1), (640, 8, 8192, 2048, 1), (768, 1, 512, 128, 1), (700, 2, 2048, 256, 0),
+                                                   (640, 1, 32768, 2048, 0)])
+def test_gemm_forward_with_in_kernel_conversion_selftest(lib, M, n_img, hw, K, write_xn):
+    """gemm_fwd_convert_kernel (tcgen05 cta_group::2 pairs; the pixel operand is read as fp32 NCHW and converted to the bf16
+    MN-major operand by the kernel's producer warps) against a CUDA-core reference on bf16-rounded x: ragged pixel counts, pixel
+    tiles straddling images, odd numbers of M-tiles; the optional bf16 NCHW copy must equal bf16(x) exactly."""
+    lib.gemm_set_fwd_convert(True)
+    try:
+        err, ref, xn_err = lib.gemm_fwd_convert_selftest(M, n_img, hw, K, bool(write_xn))
+    finally:
+        lib.gemm_set_fwd_convert(False)
+    assert ref > 0 and err <= 2e-4 * ref * max(1.0, (K / 2048) ** 0.5), (err, ref)
+    assert xn_err == 0.0
+
+
+@pytest.mark.parametrize("n,cin,C,h,w", [(1, 2048, 19, 128, 256), (2, 256, 19, 16, 32), (3, 128, 19, 44, 44), (2, 192, 19, 20, 27)])
+def test_head_forward_straight_from_fp32_nchw_equals_packed_path(lib, n, cin, C, h, w):
+    """The eval / frozen-head forward (no weight gradient wanted) takes the fused-conversion GEMM; logits bit-identical to the
+    pack + GEMM path, and the feature gradient of a frozen head is unchanged."""
+    import rnd_semantic_segmentation_b200 as b200
+    torch.manual_seed(7)
+    head = b200.ASPP_Classifier_V2(cin, RATES, RATES, C).cuda().eval()
+    x = torch.relu(torch.randn(n, cin, h, w, generator=torch.Generator().manual_seed(8))).cuda()
+    with torch.no_grad():
+        head.logits(x)                                                         # (eval mode: the weight pack is cached from here on)
+        l0 = lib.launch_count()
+        packed = head.logits(x)
+        n_packed = lib.launch_count() - l0
+    lib.gemm_set_fwd_convert(True)                                             # (an option, off by default: measured equal in speed)
+    try:
+        eligible = lib.aspp_forward_f32_supported(x, C, 4)
+        assert eligible == ((h * w) % 4 == 0 and cin % 64 == 0)
+        l0 = lib.launch_count()
+        with torch.no_grad():
+            fused = head.logits(x)
+        n_fused = lib.launch_count() - l0
+        assert torch.equal(fused, packed)
+        assert n_fused == n_packed - (1 if eligible else 0)                    # the pack launch is gone
+        for p in head.parameters():
+            p.requires_grad_(False)
+        xg = x.clone().requires_grad_(True)
+        head.logits(xg).square().sum().backward()
+    finally:
+        lib.gemm_set_fwd_convert(False)
+    xr = x.clone().requires_grad_(True)
+    head.logits(xr).square().sum().backward()
+    assert torch.equal(xg.grad, xr.grad)
