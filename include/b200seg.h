@@ -143,7 +143,7 @@ B200SEG_API int b200seg_soft_ce_backward_stats(const float* pred, const float* s
  *             soft_label_cross_entropy(D_pred, soft_label) + backward       core/utils/utility.py:172-177
  *   d_logits [N,2C,h,w] f32 (low-res discriminator output), seg_logits [N,C,h,w] f32 (low-res head output, treated
  *   as constant like the reference's .detach()).  loss_out2 = { loss, N*H*W }.  grad_d_logits [N,2C,h,w] f32.
- *   Fused instantiations: C == 19 (Cityscapes/GTA5) and C == 2 (Kvasir/BLI); other class counts use the materialised K3 path.
+ *   Any C <= 32: compile-time instantiations for C == 19 (Cityscapes/GTA5) and C == 2 (Kvasir/BLI), padded ones (8 / 16 / 24 / 32) otherwise.
  * ------------------------------------------------------------------------------------------- */
 B200SEG_API int64_t b200seg_fada_softce_workspace_bytes(int N, int C, int h, int w, int H, int W);
 B200SEG_API int b200seg_fada_softce_forward(const float* d_logits, const float* seg_logits, int N, int C, int h, int w, int H, int W,

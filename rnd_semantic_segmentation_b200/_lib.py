@@ -583,7 +583,8 @@ def soft_ce_backward(pred, soft, weights, grad_out, stats=None) -> torch.Tensor:
 # K5  fused FADA discriminator loss tail
 # --------------------------------------------------------------------------------------------
 def fada_softce_supported(num_classes: int) -> bool:
-    return num_classes in (2, 19)
+    """The fused K5 kernel takes any class count up to 32 (compile-time instantiations for 19 and 2, padded ones otherwise)."""
+    return 1 <= num_classes <= 32
 
 
 def fada_softce_forward(d_logits, seg_logits, size, slot: int, inv_temperature: float, clamp: float, need_grad: bool = True):

@@ -869,9 +869,10 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k5_fada_softce_main(const K5Par
         if (EXACT || k < K) {
           const float v = w0 * d0[k] + w1 * d1[k];
           sd += fast_exp2(v - md);
-          if (k >= SLOT * CT && k < SLOT * CT + CT) {
-            if (EXACT || (k - SLOT * CT) < C) sqv = fmaf(q[(k - SLOT * CT) < CT ? (k - SLOT * CT) : 0], v, sqv);
-          }
+          // the soft label sits in channels [SLOT * C, SLOT * C + C) (a runtime offset for the padded instantiations: their q[]
+          // is then indexed dynamically, i.e. lives in local memory -- the two class counts the reference trains are compile-time)
+          const int cc = k - SLOT * C;
+          if (cc >= 0 && cc < C) sqv = fmaf(q[cc], v, sqv);
         }
       loss_acc += LN2 * ((md + __log2f(sd)) * sq - sqv);
       if constexpr (GRAD) {
@@ -880,7 +881,8 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k5_fada_softce_main(const K5Par
         for (int k = 0; k < KT; ++k)
           if (EXACT || k < K) {
             float gk = fast_exp2((w0 * d0[k] + w1 * d1[k]) - md) * scale;
-            if (k >= SLOT * CT && k < SLOT * CT + CT) gk -= q[(k - SLOT * CT) < CT ? (k - SLOT * CT) : 0];
+            const int cc = k - SLOT * C;
+            if (cc >= 0 && cc < C) gk -= q[cc];
             acc0[k] = fmaf(w0, gk, acc0[k]);
             acc1[k] = fmaf(w1, gk, acc1[k]);
           }
@@ -994,8 +996,8 @@ int k5_forward(const float* dlogits, const float* slogits, int N, int C, int h, 
   B200SEG_CHECK_ARG(dlogits && slogits && workspace && loss_out2, "fada_softce_forward: null pointer");
   B200SEG_CHECK_ARG(N > 0 && C > 0 && h > 0 && w > 0 && H > 0 && W > 0, "fada_softce_forward: bad shape");
   B200SEG_CHECK_ARG(slot == 0 || slot == 1, "fada_softce_forward: slot must be 0 (source) or 1 (target)");
-  B200SEG_CHECK_ARG(C == 19 || C == 2, "fada_softce_forward: fused path is instantiated for num_classes 19 and 2 (got %d); use "
-                    "the materialised soft_ce path", C);
+  B200SEG_CHECK_ARG(C <= 32, "fada_softce_forward: num_classes=%d > 32 is not supported by the fused kernel (like K2 / K4); use the "
+                    "materialised soft_ce path", C);
   B200SEG_CHECK_ARG(workspace_bytes >= k5_workspace_bytes(N, C, h, w, H, W), "fada_softce_forward: workspace too small");
   K5Params p;
   k2_geometry(p.g, N, 2 * C, h, w, H, W);
@@ -1004,8 +1006,14 @@ int k5_forward(const float* dlogits, const float* slogits, int N, int C, int h, 
   p.loss_part = reinterpret_cast<float*>(workspace);
   p.blocks = p.loss_part + tiles;
   int rc;
+  // compile-time class counts for the two the reference trains (19: Cityscapes / GTA5, 2: Kvasir / BLI); any other count up to 32
+  // runs a padded instantiation with the count as a runtime bound (the widest ones trade registers for generality)
   if (C == 19) rc = k5_main_launch<19, true>(p, need_grad != 0, slot, stream);
-  else rc = k5_main_launch<2, true>(p, need_grad != 0, slot, stream);
+  else if (C == 2) rc = k5_main_launch<2, true>(p, need_grad != 0, slot, stream);
+  else if (C <= 8) rc = k5_main_launch<8, false>(p, need_grad != 0, slot, stream);
+  else if (C <= 16) rc = k5_main_launch<16, false>(p, need_grad != 0, slot, stream);
+  else if (C <= 24) rc = k5_main_launch<24, false>(p, need_grad != 0, slot, stream);
+  else rc = k5_main_launch<32, false>(p, need_grad != 0, slot, stream);
   if (rc) return rc;
   k5_finalize_loss<<<1, 256, 0, stream>>>(p.loss_part, (int)tiles, (double)N * H * W, loss_out2);
   B200SEG_LAUNCH_CHECK();

@@ -85,7 +85,8 @@ class _Lazy:
             raise AttributeError(name)
         return getattr(self.materialize(), name)
 
-    def __torch_function__(self, func, types, args=(), kwargs=None):
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
         kwargs = kwargs or {}
         handler = _HANDLERS.get(func)
         if handler is not None:

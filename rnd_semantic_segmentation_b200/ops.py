@@ -364,7 +364,7 @@ def fada_soft_label_loss(d_logits_lr: torch.Tensor, seg_logits_lr: torch.Tensor,
     aspp_fada.py:110-125 -- computed on the low-resolution tensors only.  seg_logits_lr is treated as a constant
     (the reference detaches the soft labels); the gradient flows to d_logits_lr."""
     C = seg_logits_lr.shape[1]
-    if not _lib.fada_softce_supported(C):
+    if not _lib.fada_softce_supported(C):        # more than 32 classes (K2 / K4 do not take those either): materialised operands + K3
         up_d = upsample_bilinear_align_corners(d_logits_lr, size)
         with torch.no_grad():
             soft = torch.softmax(upsample_bilinear_align_corners(seg_logits_lr, size) / temperature, dim=1)

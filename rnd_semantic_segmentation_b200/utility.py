@@ -281,7 +281,8 @@ class LazyProbabilities:
     def __getitem__(self, idx):
         return self.materialize()[idx]
 
-    def __torch_function__(self, func, types, args=(), kwargs=None):   # any torch.* call on the lazy object
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):   # any torch.* call on the lazy object
         kwargs = kwargs or {}
         args = tuple(a.materialize() if isinstance(a, LazyProbabilities) else a for a in args)
         return func(*args, **kwargs)

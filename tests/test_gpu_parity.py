@@ -179,7 +179,8 @@ def test_k3_soft_label_ce(lib, n, K, H, W, weighted):
 
 # ------------------------------------------------------------------ K5 (fused FADA discriminator loss tail)
 @pytest.mark.parametrize("n,C,h,w,H,W,slot", [(2, 19, 33, 65, 264, 520, 0), (1, 19, 64, 128, 512, 1024, 1), (2, 2, 44, 44, 352, 352, 1),
-                                             (1, 7, 9, 11, 50, 70, 0), (1, 19, 17, 23, 100, 131, 1), (1, 24, 8, 8, 40, 40, 0)])
+                                             (1, 7, 9, 11, 50, 70, 0), (1, 19, 17, 23, 100, 131, 1), (1, 24, 8, 8, 40, 40, 0), (1, 30, 8, 8, 40, 40, 1),
+                                             (2, 11, 16, 32, 128, 256, 1)])
 def test_k5_fada_soft_label_loss(lib, n, C, h, w, H, W, slot):
     import rnd_semantic_segmentation_b200 as b200
     g = torch.Generator().manual_seed(31 + C + h)
