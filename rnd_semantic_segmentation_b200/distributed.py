@@ -134,7 +134,7 @@ class OverlappedGradBucket(FlatGradBucket):
     NEXT iteration's head forward / backward -- joins.  The collective and the update therefore overlap the next iteration's
     source-domain head step instead of sitting between iterations."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], group=None, p2p_blocks: int = 16):
+    def __init__(self, params: Iterable[torch.nn.Parameter], group=None, p2p_blocks: int = 8):
         super().__init__(params, symmetric=True, group=group)
         self.group = group
         self.p2p_blocks = int(p2p_blocks)
@@ -206,12 +206,16 @@ class HeadGradBucket(FlatGradBucket):
         #   8 ranks:  4 -> 1.277   8 -> 1.068   16 -> 0.971   32 -> 0.867   (no all-reduce 0.854, all-reduce afterwards 0.944)
         convs = list(head.conv2d_list)
         # bucket order: the R weights, then the R biases as one [R, C] block.  In symmetric memory when the box allows it: the
-        # all-reduce is then our own peer-memory kernel (NVSwitch multimem reduce + broadcast, csrc/p2p_allreduce.cu) on 8 CTAs,
-        # so the data-gradient GEMM cedes 8 SMs at any world size instead of the 8 / 16 / 32 an NCCL ring needs to finish in time.
+        # all-reduce is then our own peer-memory kernel (NVSwitch multimem reduce + broadcast, csrc/p2p_allreduce.cu).  Measured
+        # (profiles/p2p_probe.py, 5.6 MB): 8 ranks 38 us on FOUR CTAs (NCCL: 178 / 104 / 57 us at 8 / 16 / 32 CTAs), 2 ranks 52 / 42 us
+        # on 4 / 8 CTAs -- so the data-gradient GEMM cedes 4 SMs (8 at two ranks) instead of the 8 / 16 / 32 an NCCL ring needs.
         super().__init__([m.weight for m in convs] + [m.bias for m in convs], symmetric=True, group=group)
         if overlap_ctas is None:
             world = dist.get_world_size() if is_distributed() else 1
-            overlap_ctas = 8 if (self._symm is not None or world <= 2) else (16 if world <= 4 else 32)
+            if self._symm is not None:
+                overlap_ctas = 8 if world <= 2 else 4
+            else:
+                overlap_ctas = 8 if world <= 2 else (16 if world <= 4 else 32)
         self.p2p_blocks = int(overlap_ctas) if overlap_ctas > 0 else 8
         self.R = len(convs)
         # The persistent dgrad GEMM fills every SM's shared memory, so nothing else can be resident beside it: it leaves
