@@ -206,10 +206,11 @@ def run_ours(args):
     labels = synth.make_labels(n, H, W, C, seed=1234 + rank, device=dev)
     bucket = D.HeadGradBucket(head) if world > 1 else None
     label_px = n * H * W
+    head_params = list(head.parameters())                  # (an optimizer holds this list; zero_grad() walks it)
 
     def train_step(x_in=x, labels_in=labels):
         xg = x_in.detach().requires_grad_(True)            # the backbone needs d loss / d features
-        for p in head.parameters():
+        for p in head_params:
             p.grad = None
         # (the module is in training mode: the bf16 weight pack is rebuilt on every call, as after every optimizer step)
         # N > 1: weight gradients land in the flat bucket and its NCCL mean all-reduce runs on a second stream underneath
@@ -274,7 +275,7 @@ def run_ours(args):
 
     def unmodified_trainer_step():
         xg = x.detach().requires_grad_(True)
-        for p in head.parameters():
+        for p in head_params:
             p.grad = None
         size = labels.shape[-2:]
         output = head(xg, size)
@@ -493,12 +494,13 @@ def run_baseline_configs(b200, _lib, synth, dev, rank, peaks, args):
         xs = [synth.make_features(n, cin, h, w, seed=31 + rank + 7 * i, device=dev) for i in range(2)]    # 2 x >= 137 MB: > L2 for cfg1 / cfg2
         labels = synth.make_labels(n, H, W, C, p_ignore=p_ign, seed=32 + rank, device=dev)
         k = [0]
+        params = list(head.parameters())
 
         def step(x_in=None):
             x_in = xs[k[0] & 1] if x_in is None else x_in
             k[0] += 1
             xg = x_in.detach().requires_grad_(True)
-            for p in head.parameters():
+            for p in params:
                 p.grad = None
             loss, _ = head.forward_loss(xg, labels)
             loss.backward()

@@ -203,6 +203,36 @@ B200SEG_API int b200seg_aspp_backward_packed_ex(const void* gOt, const void* Xp,
                                     void* grad_x_nhwc_bf16, float* const* grad_w, void* weights_ready_event, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K1 + K2 as ONE call per direction: the fused train slice
+ *   replaces  pred = classifier(feat, size); loss = CrossEntropyLoss(ignore_index)(pred / T, label); loss.backward()
+ *             core/trainers/aspp_trainer.py:86-93, core/combos/aspp_fada.py:88-96  (head: core/models/classifier.py:26-31)
+ *   forward : pack weights -> pack features (x_kind 0) -> 33-tap GEMM -> gather + bias -> upsample + CE (+ gradient partials) -> loss
+ *   backward: low-res gradient (bf16 planes) + bias gradients -> G't -> weight-gradient GEMM -> reduce -> [event] -> data-gradient GEMM
+ * The host cost of the step is the enqueue of these ~12 kernels; one foreign call each way keeps 1-2 image batches GPU-bound.
+ *   x        x_kind 0: fp32 NCHW [N,Cin,h,w];  x_kind 1: bf16 pixel-major [N*h*w, Cin] (channels_last seam format, used in place)
+ *   workspace  b200seg_head_loss_workspace_bytes(...) bytes, owned by the caller from forward until backward has run
+ *   scratch    b200seg_head_loss_scratch_bytes(...) bytes, transient inside each call (stream-ordered reuse is fine)
+ *   logits   fp32 [N,C,h,w] (out),  loss_out fp32 [1] (out; NaN when every label is ignored, like the reference)
+ *   backward: grad_loss fp32 [1] or NULL (= 1); give at most one of grad_x (fp32 NCHW) / grad_x_nhwc_bf16; grad_w / grad_b are
+ *   R pointers each (or NULL; every branch bias receives the same gradient); weights_ready_event as in
+ *   b200seg_aspp_backward_packed_ex.  x_bf16 = the forward's x when x_kind == 1 (the caller keeps it alive), else NULL.
+ * ------------------------------------------------------------------------------------------- */
+B200SEG_API int64_t b200seg_head_loss_workspace_bytes(int N, int Cin, int C, int h, int w, int R, int H, int W, int x_kind);
+B200SEG_API int64_t b200seg_head_loss_scratch_bytes(int N, int Cin, int C, int h, int w, int R);
+B200SEG_API int b200seg_head_loss_forward(const void* x, int x_kind, const float* const* weights, const float* const* biases,
+                                    const int* rates_host, int R, int N, int Cin, int C, int h, int w, const void* labels,
+                                    int label_bytes, int H, int W, int ignore_index, float inv_temperature, int need_grad,
+                                    void* workspace, int64_t workspace_bytes, void* scratch, int64_t scratch_bytes, float* logits,
+                                    float* loss_out, void* stream);
+B200SEG_API int b200seg_head_loss_backward(void* workspace, int64_t workspace_bytes, const void* x_bf16, int x_kind,
+                                    const int* rates_host, int R, int N, int Cin, int C, int h, int w, int H, int W,
+                                    float inv_temperature, const float* grad_loss, void* scratch, int64_t scratch_bytes,
+                                    float* grad_x, void* grad_x_nhwc_bf16, float* const* grad_w, float* const* grad_b,
+                                    void* weights_ready_event, void* stream);
+/* split-K factor the weight-gradient GEMM uses for P = N*h*w pixels (what the entries above pick) */
+B200SEG_API int b200seg_aspp_default_wgrad_splits(int64_t P, int C, int Cin, int R);
+
+/* ---------------------------------------------------------------------------------------------
  * K6  3x3 convolution layers as tcgen05 implicit GEMMs: the PixelDiscriminator conv stack
  *   replaces  D = Conv2d(Cin,ndf,3,1,1)+LeakyReLU(0.2)+Conv2d(ndf,ndf/2,3,1,1)+LeakyReLU(0.2)   core/models/discriminator.py:34-39
  *             cls1 / cls2 = Conv2d(ndf/2, C, 3, 1, 1)                                            core/models/discriminator.py:40-41

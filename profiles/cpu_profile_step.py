@@ -14,11 +14,12 @@ head = b200.ASPP_Classifier_V2(cin, RATES, RATES, C).to(dev)
 x = synth.make_features(n, cin, h, w, device=dev)
 labels = synth.make_labels(n, H, W, C, device=dev)
 b200.set_feature_pack_cache(0)
+params = list(head.parameters())
 
 
 def step():
     xg = x.detach().requires_grad_(True)
-    for p in head.parameters():
+    for p in params:
         p.grad = None
     loss, _ = head.forward_loss(xg, labels)
     loss.backward()

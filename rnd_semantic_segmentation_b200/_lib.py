@@ -74,6 +74,13 @@ SIGNATURES = {
                                                   c_int, c_vp, c_vp, c_vp]),
     "b200seg_aspp_backward_packed_ex": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64,
                                                 c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "b200seg_head_loss_workspace_bytes": (c_i64, [c_int] * 9),
+    "b200seg_head_loss_scratch_bytes": (c_i64, [c_int] * 6),
+    "b200seg_head_loss_forward": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_int,
+                                          c_int, c_int, c_f32, c_int, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "b200seg_head_loss_backward": (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                           c_f32, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "b200seg_aspp_default_wgrad_splits": (c_int, [c_i64, c_int, c_int, c_int]),
     "b200seg_conv3x3_pack_weights": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     "b200seg_conv3x3_pack_weights_stack": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     "b200seg_conv3x3_forward": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_i64, c_vp, c_int, c_int, c_vp, c_int, c_f32, c_vp, c_i64,
@@ -808,6 +815,108 @@ def aspp_backward_packed(gOt: torch.Tensor, Xp: torch.Tensor, WpT: torch.Tensor,
     if gx_nhwc is not None:
         gx = gx_nhwc.permute(0, 3, 1, 2)
     return gx, gws
+
+
+# --------------------------------------------------------------------------------------------
+# K1 + K2 in one foreign call per direction (the fused train slice)
+# --------------------------------------------------------------------------------------------
+_head_loss_plans = {}
+
+
+def _head_loss_plan(N, Cin, C, h, w, R, H, W, x_kind, rates):
+    """(workspace bytes, scratch bytes, ctypes rate array) per shape -- computed once."""
+    key = (N, Cin, C, h, w, R, H, W, x_kind, rates)
+    plan = _head_loss_plans.get(key)
+    if plan is None:
+        lib = load()
+        if len(_head_loss_plans) > 64:
+            _head_loss_plans.clear()
+        plan = (int(lib.b200seg_head_loss_workspace_bytes(N, Cin, C, h, w, R, H, W, x_kind)),
+                int(lib.b200seg_head_loss_scratch_bytes(N, Cin, C, h, w, R)), (c_int * R)(*rates))
+        _head_loss_plans[key] = plan
+    return plan
+
+
+def head_loss_forward(x: torch.Tensor, x_kind: int, shape, weights, biases, rates, labels: torch.Tensor, ignore_index: int,
+                      inv_temperature: float, need_grad: bool):
+    """pack -> head GEMM -> gather -> upsample + CE in ONE call.  ``x``: fp32 NCHW (x_kind 0) or bf16 pixel-major [N*h*w, Cin]
+    (x_kind 1); ``shape`` = (N, Cin, h, w).  Returns (loss fp32 scalar tensor, logits fp32 [N,C,h,w], workspace) -- the workspace
+    feeds head_loss_backward."""
+    lib = load()
+    N, Cin, h, w = shape
+    R = len(rates)
+    C = int(weights[0].shape[0])
+    _need(x, torch.float32 if x_kind == 0 else torch.bfloat16, "features")
+    for wt in weights:
+        _need(wt, torch.float32, "conv weight")
+        if tuple(wt.shape) != (C, Cin, 3, 3):
+            raise B200SegError(f"conv weight shape {tuple(wt.shape)} != {(C, Cin, 3, 3)}")
+    for b in biases:
+        if b is not None:
+            _need(b, torch.float32, "conv bias")
+    lbytes = _need_label(labels, "labels")
+    H, W = int(labels.shape[-2]), int(labels.shape[-1])
+    if labels.numel() != N * H * W:
+        raise B200SegError(f"labels shape {tuple(labels.shape)} does not match batch {N}")
+    dev = x.device
+    ws_bytes, sc_bytes, rates_arr = _head_loss_plan(N, Cin, C, h, w, R, H, W, x_kind, rates)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    logits = torch.empty((N, C, h, w), dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    with _on_device(dev):
+        scratch = _scratch("head_loss", sc_bytes, dev)
+        _check(lib.b200seg_head_loss_forward(x.data_ptr(), x_kind, _ptr_array(weights), _ptr_array(biases), rates_arr, R, N, Cin, C, h, w,
+                                             labels.data_ptr(), lbytes, H, W, ignore_index, inv_temperature, 1 if need_grad else 0,
+                                             ws.data_ptr(), ws_bytes, scratch.data_ptr(), scratch.numel(), logits.data_ptr(),
+                                             loss.data_ptr(), _stream()))
+    return loss, logits, ws
+
+
+def head_loss_backward(ws: torch.Tensor, x_bf16: Optional[torch.Tensor], x_kind: int, shape, C: int, rates, size, inv_temperature: float,
+                       grad_loss: Optional[torch.Tensor], need_x: bool, need_w: bool, need_b: bool, nhwc_bf16: bool = False,
+                       out_w=None, out_b=None, weights_ready_event=None):
+    """Backward of head_loss_forward in ONE call.  Returns (grad_x | None, [grad_w]*R | None, [grad_b]*R | None); ``out_w`` /
+    ``out_b``: preallocated destinations (views of a flat data-parallel bucket), ``weights_ready_event`` recorded once they are
+    complete (before the data-gradient GEMM)."""
+    lib = load()
+    N, Cin, h, w = shape
+    H, W = size
+    R = len(rates)
+    dev = ws.device
+    _, sc_bytes, rates_arr = _head_loss_plan(N, Cin, C, h, w, R, H, W, x_kind, rates)
+    if grad_loss is not None:
+        grad_loss = _need(grad_loss.reshape(1), torch.float32, "grad_loss")
+    gws = gbs = None
+    if need_w:
+        if out_w is not None:
+            gws = [_need(t, torch.float32, "out_w") for t in out_w]
+            if len(gws) != R or any(tuple(t.shape) != (C, Cin, 3, 3) for t in gws):
+                raise B200SegError("out_w: expected R contiguous fp32 [C,Cin,3,3] buffers")
+        else:
+            gws = torch.empty((R, C, Cin, 3, 3), dtype=torch.float32, device=dev).unbind(0)
+    if need_b:
+        if out_b is not None:
+            gbs = [_need(t, torch.float32, "out_b") for t in out_b]
+            if len(gbs) != R or any(t.numel() != C for t in gbs):
+                raise B200SegError("out_b: expected R contiguous fp32 [C] buffers")
+        else:
+            gbs = torch.empty((R, C), dtype=torch.float32, device=dev).unbind(0)
+    gx = gx_nhwc = None
+    if need_x:
+        if nhwc_bf16:
+            gx_nhwc = torch.empty((N, h, w, Cin), dtype=torch.bfloat16, device=dev)
+        else:
+            gx = torch.empty((N, Cin, h, w), dtype=torch.float32, device=dev)
+    ev = None if weights_ready_event is None else weights_ready_event.cuda_event
+    with _on_device(dev):
+        scratch = _scratch("head_loss", sc_bytes, dev)
+        _check(lib.b200seg_head_loss_backward(ws.data_ptr(), ws.numel(), _ptr(x_bf16), x_kind, rates_arr, R, N, Cin, C, h, w, H, W,
+                                              inv_temperature, _ptr(grad_loss), scratch.data_ptr(), scratch.numel(), _ptr(gx),
+                                              _ptr(gx_nhwc), _ptr_array(gws) if gws is not None else None,
+                                              _ptr_array(gbs) if gbs is not None else None, ev, _stream()))
+    if gx_nhwc is not None:
+        gx = gx_nhwc.permute(0, 3, 1, 2)
+    return gx, gws, gbs
 
 
 # --------------------------------------------------------------------------------------------

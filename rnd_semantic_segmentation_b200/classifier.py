@@ -88,5 +88,4 @@ class ASPP_Classifier_V2(nn.Module):
         gradients flow through the loss only.  ``grad_bucket``: a distributed.HeadGradBucket built over this module -- the
         parameter gradients then land in the bucket and its mean all-reduce overlaps the data-gradient GEMM."""
         return ops.aspp_head_loss(x, labels, [m.weight for m in self.conv2d_list], [m.bias for m in self.conv2d_list],
-                                  self._rates(), ignore_index, temperature, packed=self._packed_weights(),
-                                  grad_bucket=grad_bucket)
+                                  self._rates(), ignore_index, temperature, grad_bucket=grad_bucket)

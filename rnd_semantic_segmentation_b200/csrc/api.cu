@@ -54,7 +54,10 @@ int k4_launch_frames(const float* const*, int, int, int, int, const void* const*
                      int, int, cudaStream_t);
 int confusion_pairs_launch_ex(void*, int, const void*, int, long long, int, int, int, long long*, cudaStream_t);
 long long k2_workspace_bytes(int, int, int, int, int, int);
-int k2_forward(const float*, int, int, int, int, const void*, int, int, int, int, float, int, void*, long long, float*, cudaStream_t);
+int k2_forward(const float*, int, int, int, int, const void*, int, int, int, int, float, int, void*, long long, float*, cudaStream_t,
+               float* loss_copy = nullptr);
+int k2_backward_packed_multi(void*, int, int, int, int, int, int, float, const float*, const float*, void*, float* const*, int, cudaStream_t);
+void* aspp_bwd_gOt_ptr(void*);
 int k2_backward(const void*, int, int, int, int, int, int, float, const float*, const float*, float*, cudaStream_t);
 int k2_backward_packed(void*, int, int, int, int, int, int, float, const float*, const float*, void*, float*, cudaStream_t);
 int aspp_backward_packed(const void*, const void*, const void*, const int*, int, int, int, int, int, int, void*, long long, int, float*,
@@ -494,6 +497,115 @@ int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b_mn_major, i
     return B200SEG_ERR_ARG;
   }
   return gemm::selftest(M, N, K, a_mn_major, b_mn_major, splits, col_hw, share, max_err, max_ref);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// One call per direction for the fused train slice  loss = CE(interpolate(head(x), size) / T, labels)
+// (aspp_trainer.py:86-93 / aspp_fada.py:88-96; the head is classifier.py:26-31).  The host cost of the step is the enqueue of
+// ~12 kernels: issuing them from ONE foreign call each way (instead of eight, each with its own output allocations) is what
+// keeps the small BASELINE configs (1-2 images per GPU) GPU-bound in eager mode.
+// ---------------------------------------------------------------------------------------------------------------------------
+struct HeadLossLayout {
+  long long out2, WpT, Xp, k2ws, Wp, bias_sum, total;
+};
+static long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
+static HeadLossLayout head_loss_layout(int N, int Cin, int C, int h, int w, int R, int H, int W, int x_kind) {
+  HeadLossLayout L;
+  const long long P = (long long)N * h * w, NJ = aspp_nj(C, R);
+  long long o = 0;
+  L.out2 = o; o += 1024;
+  L.bias_sum = o; o += 1024;
+  L.WpT = o; o = align_up(o + (long long)Cin * NJ * 2, 1024);
+  L.Wp = o; o = align_up(o + NJ * Cin * 2, 1024);
+  L.Xp = o; if (x_kind == 0) o = align_up(o + P * Cin * 2, 1024);
+  L.k2ws = o; o = align_up(o + k2_workspace_bytes(N, C, h, w, H, W), 1024);
+  L.total = o;
+  return L;
+}
+
+// smallest split-K factor >= 4 of the weight-gradient GEMM that fills whole rounds of the 74 CTA pairs best (the rule of
+// _lib.default_wgrad_splits, restated here so the one-call entry needs no host-side planning)
+static int head_default_splits(long long P, int C, int Cin, int R) {
+  const int NJ = aspp_nj(C, R);
+  const long long tiles = (long long)(((NJ + 127) / 128 + 1) / 2) * ((Cin + 255) / 256);
+  const long long kb = (P + 63) / 64;
+  int best = 1;
+  double best_eff = -1.0;
+  for (int s = 1; s <= 16 && s <= kb; ++s) {
+    const long long units = tiles * s;
+    const double eff = (double)units / (double)(((units + 73) / 74) * 74);
+    if (s >= 4 && eff > best_eff + 1e-9) { best = s; best_eff = eff; }
+  }
+  if (best_eff > 0) return best;
+  return (int)(kb < 1 ? 1 : (kb < 4 ? kb : 4));
+}
+
+extern "C" {
+
+int b200seg_aspp_default_wgrad_splits(int64_t P, int C, int Cin, int R) { return head_default_splits(P, C, Cin, R); }
+
+int64_t b200seg_head_loss_workspace_bytes(int N, int Cin, int C, int h, int w, int R, int H, int W, int x_kind) {
+  if (N <= 0 || Cin <= 0 || C <= 0 || h <= 0 || w <= 0 || R <= 0 || H <= 0 || W <= 0) return 0;
+  return head_loss_layout(N, Cin, C, h, w, R, H, W, x_kind).total;
+}
+
+int64_t b200seg_head_loss_scratch_bytes(int N, int Cin, int C, int h, int w, int R) {
+  if (N <= 0 || Cin <= 0 || C <= 0 || h <= 0 || w <= 0 || R <= 0) return 0;
+  const long long f = aspp_yt_bytes(N, C, h, w, R);
+  const long long b = aspp_bwd_scratch_bytes(N, Cin, C, h, w, R, head_default_splits((long long)N * h * w, C, Cin, R));
+  return f > b ? f : b;
+}
+
+int b200seg_head_loss_forward(const void* x, int x_kind, const float* const* weights, const float* const* biases, const int* rates_host,
+                              int R, int N, int Cin, int C, int h, int w, const void* labels, int label_bytes, int H, int W,
+                              int ignore_index, float inv_temperature, int need_grad, void* workspace, int64_t workspace_bytes,
+                              void* scratch, int64_t scratch_bytes, float* logits, float* loss_out, void* stream) {
+  REQUIRE_DEVICE();
+  B200SEG_CHECK_ARG(x && weights && rates_host && labels && workspace && scratch && logits && loss_out, "head_loss_forward: null pointer");
+  B200SEG_CHECK_ARG(x_kind == 0 || x_kind == 1, "head_loss_forward: x_kind must be 0 (fp32 NCHW) or 1 (bf16 pixel-major), got %d", x_kind);
+  B200SEG_CHECK_ARG(N > 0 && Cin > 0 && C > 0 && h > 0 && w > 0 && R > 0 && H > 0 && W > 0, "head_loss_forward: bad shape");
+  const HeadLossLayout L = head_loss_layout(N, Cin, C, h, w, R, H, W, x_kind);
+  B200SEG_CHECK_ARG(workspace_bytes >= L.total, "head_loss_forward: workspace too small (%lld < %lld)", (long long)workspace_bytes, L.total);
+  B200SEG_CHECK_ARG(scratch_bytes >= aspp_yt_bytes(N, C, h, w, R), "head_loss_forward: scratch too small");
+  char* base = reinterpret_cast<char*>(workspace);
+  float* bias_sum = reinterpret_cast<float*>(base + L.bias_sum);
+  int rc = aspp_pack_weights(weights, biases, R, C, Cin, base + L.Wp, base + L.WpT, bias_sum, S(stream));
+  if (rc) return rc;
+  const void* Xp = x;
+  if (x_kind == 0) {
+    rc = aspp_pack_features(reinterpret_cast<const float*>(x), N, Cin, h, w, base + L.Xp, S(stream));
+    if (rc) return rc;
+    Xp = base + L.Xp;
+  }
+  rc = aspp_forward(Xp, base + L.Wp, bias_sum, rates_host, R, N, Cin, C, h, w, reinterpret_cast<float*>(scratch), logits, S(stream));
+  if (rc) return rc;
+  return k2_forward(logits, N, C, h, w, labels, label_bytes, H, W, ignore_index, inv_temperature, need_grad, base + L.k2ws,
+                    k2_workspace_bytes(N, C, h, w, H, W), reinterpret_cast<float*>(base + L.out2), S(stream), loss_out);
+}
+
+int b200seg_head_loss_backward(void* workspace, int64_t workspace_bytes, const void* x_bf16, int x_kind, const int* rates_host, int R,
+                               int N, int Cin, int C, int h, int w, int H, int W, float inv_temperature, const float* grad_loss,
+                               void* scratch, int64_t scratch_bytes, float* grad_x, void* grad_x_nhwc_bf16, float* const* grad_w,
+                               float* const* grad_b, void* weights_ready_event, void* stream) {
+  REQUIRE_DEVICE();
+  B200SEG_CHECK_ARG(workspace && rates_host && scratch, "head_loss_backward: null pointer");
+  B200SEG_CHECK_ARG(x_kind == 0 || (x_kind == 1 && (x_bf16 || !grad_w)), "head_loss_backward: bad x_kind / missing bf16 features");
+  B200SEG_CHECK_ARG(N > 0 && Cin > 0 && C > 0 && h > 0 && w > 0 && R > 0 && R <= 8 && H > 0 && W > 0, "head_loss_backward: bad shape");
+  const HeadLossLayout L = head_loss_layout(N, Cin, C, h, w, R, H, W, x_kind);
+  B200SEG_CHECK_ARG(workspace_bytes >= L.total, "head_loss_backward: workspace too small");
+  const int splits = head_default_splits((long long)N * h * w, C, Cin, R);
+  B200SEG_CHECK_ARG(scratch_bytes >= aspp_bwd_scratch_bytes(N, Cin, C, h, w, R, splits), "head_loss_backward: scratch too small");
+  char* base = reinterpret_cast<char*>(workspace);
+  void* gOt = aspp_bwd_gOt_ptr(scratch);
+  int rc = k2_backward_packed_multi(base + L.k2ws, N, C, h, w, H, W, inv_temperature, reinterpret_cast<const float*>(base + L.out2),
+                                    grad_loss, gOt, grad_b, grad_b ? R : 0, S(stream));
+  if (rc) return rc;
+  if (!grad_x && !grad_x_nhwc_bf16 && !grad_w) return B200SEG_OK;
+  const void* Xp = x_kind == 0 ? static_cast<const void*>(base + L.Xp) : x_bf16;
+  return aspp_backward_packed(gOt, Xp, base + L.WpT, rates_host, R, N, Cin, C, h, w, scratch, scratch_bytes, splits, grad_x, grad_w,
+                              S(stream), grad_x_nhwc_bf16, reinterpret_cast<cudaEvent_t>(weights_ready_event));
 }
 
 }  // extern "C"

@@ -472,7 +472,9 @@ __global__ void __launch_bounds__(K2_THREADS * SPLIT, SPLIT == 1 ? 3 : K2_SPLIT_
 }
 
 // loss = sum(loss_part) / sum(cnt_part)  (NaN when no valid pixel, like the reference); out = {loss, n_valid}
-__global__ void __launch_bounds__(256) k2_finalize_loss(const float* loss_part, const float* cnt_part, int tiles, float* out2) {
+// (loss_copy: optional second home of the loss scalar -- the tensor handed back to autograd by the one-call train entry)
+__global__ void __launch_bounds__(256) k2_finalize_loss(const float* loss_part, const float* cnt_part, int tiles, float* out2,
+                                                        float* loss_copy) {
   __shared__ double sl[8], sc[8];
   double l = 0.0, c = 0.0;
   for (int i = threadIdx.x; i < tiles; i += 256) { l += (double)loss_part[i]; c += (double)cnt_part[i]; }
@@ -484,6 +486,7 @@ __global__ void __launch_bounds__(256) k2_finalize_loss(const float* loss_part, 
     for (int i = 0; i < 8; ++i) { L += sl[i]; Cn += sc[i]; }
     out2[0] = (float)(L / Cn);
     out2[1] = (float)Cn;
+    if (loss_copy) loss_copy[0] = (float)(L / Cn);
   }
 }
 
@@ -557,8 +560,13 @@ __global__ void __launch_bounds__(128) k2_finalize_grad(const K2Geom g, const fl
   }
 }
 
-// bias_grad[c] = sum over finalize blocks of bias_part[blk][c]  (one block per class, fixed order)
-__global__ void __launch_bounds__(256) k2_bias_from_partials(const float* bias_part, long long nblk, int C, float* bias_grad) {
+// bias_grad[c] = sum over finalize blocks of bias_part[blk][c]  (one block per class, fixed order), written to every one of the
+// n destinations (the R branch biases of the head all receive the same gradient: classifier.py:27-29 sums the branches)
+struct K2BiasOuts {
+  float* p[8];
+  int n;
+};
+__global__ void __launch_bounds__(256) k2_bias_from_partials(const float* bias_part, long long nblk, int C, const K2BiasOuts outs) {
   __shared__ double red[8];
   const int c = blockIdx.x;
   double acc = 0.0;
@@ -569,7 +577,7 @@ __global__ void __launch_bounds__(256) k2_bias_from_partials(const float* bias_p
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int q = 0; q < 8; ++q) t += red[q];
-    bias_grad[c] = (float)t;
+    for (int q = 0; q < outs.n; ++q) outs.p[q][c] = (float)t;
   }
 }
 
@@ -601,7 +609,8 @@ static int k2_main_launch(const K2Params& p, bool grad, cudaStream_t stream) {
 }
 
 int k2_forward(const float* logits, int N, int C, int h, int w, const void* labels, int label_bytes, int H, int W, int ignore_index,
-               float inv_T, int need_grad, void* workspace, long long workspace_bytes, float* loss_out2, cudaStream_t stream) {
+               float inv_T, int need_grad, void* workspace, long long workspace_bytes, float* loss_out2, cudaStream_t stream,
+               float* loss_copy) {
   B200SEG_CHECK_ARG(label_bytes == 8 || label_bytes == 1, "upsample_ce_forward: labels must be int64 or uint8 (label_bytes=%d)", label_bytes);
   B200SEG_CHECK_ARG(logits && labels && workspace && loss_out2, "upsample_ce_forward: null pointer");
   B200SEG_CHECK_ARG(N > 0 && C > 0 && h > 0 && w > 0 && H > 0 && W > 0, "upsample_ce_forward: bad shape");
@@ -620,7 +629,7 @@ int k2_forward(const float* logits, int N, int C, int h, int w, const void* labe
   if (v2) {
     rc = k2v2_main_launch(p, need_grad != 0, stream);
     if (rc) return rc;
-    k2_finalize_loss<<<1, 256, 0, stream>>>(p.loss_part, p.cnt_part, (int)tiles, loss_out2);
+    k2_finalize_loss<<<1, 256, 0, stream>>>(p.loss_part, p.cnt_part, (int)tiles, loss_out2, loss_copy);
     B200SEG_LAUNCH_CHECK();
     return B200SEG_OK;
   }
@@ -632,7 +641,7 @@ int k2_forward(const float* logits, int N, int C, int h, int w, const void* labe
   else if (C <= 8) rc = k2_main_launch<8, false, 1>(p, need_grad != 0, stream);
   else rc = k2_main_launch<32, false, K2_SPLIT_DEF>(p, need_grad != 0, stream);
   if (rc) return rc;
-  k2_finalize_loss<<<1, 256, 0, stream>>>(p.loss_part, p.cnt_part, (int)tiles, loss_out2);
+  k2_finalize_loss<<<1, 256, 0, stream>>>(p.loss_part, p.cnt_part, (int)tiles, loss_out2, loss_copy);
   B200SEG_LAUNCH_CHECK();
   return B200SEG_OK;
 }
@@ -651,9 +660,10 @@ int k2_backward(const void* workspace, int N, int C, int h, int w, int H, int W,
 }
 
 // Packed form for the fused head+loss path: bf16 pixel-major gradient + bias gradient, no fp32 NCHW tensor.
-int k2_backward_packed(void* workspace, int N, int C, int h, int w, int H, int W, float inv_T, const float* loss_out2,
-                       const float* grad_out, void* gOt, float* bias_grad, cudaStream_t stream) {
+int k2_backward_packed_multi(void* workspace, int N, int C, int h, int w, int H, int W, float inv_T, const float* loss_out2,
+                             const float* grad_out, void* gOt, float* const* bias_grads, int n_bias, cudaStream_t stream) {
   B200SEG_CHECK_ARG(workspace && loss_out2 && gOt, "upsample_ce_backward_packed: null pointer");
+  B200SEG_CHECK_ARG(n_bias >= 0 && n_bias <= 8 && (n_bias == 0 || bias_grads), "upsample_ce_backward_packed: %d bias destinations", n_bias);
   B200SEG_CHECK_ARG(C <= 32, "upsample_ce_backward_packed: num_classes=%d > 32 is not supported", C);
   K2Geom g;
   k2_pick_geometry(g, N, C, h, w, H, W);
@@ -664,11 +674,19 @@ int k2_backward_packed(void* workspace, int N, int C, int h, int w, int H, int W
   dim3 grid(ceil_div(w, 128), h, N);
   k2_finalize_grad<true><<<grid, 128, 0, stream>>>(g, blocks, loss_out2, grad_out, inv_T, nullptr, (__nv_bfloat16*)gOt, bias_part);
   B200SEG_LAUNCH_CHECK();
-  if (bias_grad) {
-    k2_bias_from_partials<<<C, 256, 0, stream>>>(bias_part, (long long)grid.x * grid.y * grid.z, C, bias_grad);
+  K2BiasOuts outs = {};
+  for (int q = 0; q < n_bias; ++q)
+    if (bias_grads[q]) outs.p[outs.n++] = bias_grads[q];
+  if (outs.n > 0) {
+    k2_bias_from_partials<<<C, 256, 0, stream>>>(bias_part, (long long)grid.x * grid.y * grid.z, C, outs);
     B200SEG_LAUNCH_CHECK();
   }
   return B200SEG_OK;
+}
+
+int k2_backward_packed(void* workspace, int N, int C, int h, int w, int H, int W, float inv_T, const float* loss_out2,
+                       const float* grad_out, void* gOt, float* bias_grad, cudaStream_t stream) {
+  return k2_backward_packed_multi(workspace, N, C, h, w, H, W, inv_T, loss_out2, grad_out, gOt, &bias_grad, bias_grad ? 1 : 0, stream);
 }
 
 // =============================================================================================

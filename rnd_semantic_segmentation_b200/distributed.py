@@ -252,6 +252,9 @@ class HeadGradBucket(FlatGradBucket):
     def weight_buffers(self):
         return self.views[:self.R]
 
+    def bias_buffers(self):
+        return self.views[self.R:2 * self.R]
+
     def set_bias_grads_(self, bias_grad: torch.Tensor):
         self._bias_block.copy_(bias_grad.unsqueeze(0).expand_as(self._bias_block))     # d/d b_r is the same for every branch
 

@@ -113,71 +113,81 @@ def aspp_head(x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence
 
 class _AsppHeadLossFn(torch.autograd.Function):
     """Fused train slice: head forward -> upsample + CE forward, and in backward CE/upsample backward -> head dgrad /
-    wgrad with the low-res gradient handed over as packed bf16 (no fp32 NCHW gradient, no transposes)."""
+    wgrad with the low-res gradient handed over as packed bf16 (no fp32 NCHW gradient, no transposes).  ONE foreign call per
+    direction (b200seg_head_loss_forward / _backward): weight pack, feature pack, GEMMs, gathers and reductions are enqueued from
+    C, with one workspace allocation that lives from forward to backward."""
 
     @staticmethod
-    def forward(ctx, x, labels, ignore_index, temperature, rates, packed, grad_bucket, *params):
+    def forward(ctx, x, labels, ignore_index, temperature, rates, grad_bucket, *params):
         R = len(rates)
         ctx.grad_bucket = grad_bucket
         weights, biases = params[:R], params[R:]
         N, Cin, h, w = x.shape
         C = weights[0].shape[0]
-        if packed is None:
-            packed = _lib.aspp_pack_weights([p.detach() for p in weights], [None if b is None else b.detach() for b in biases])
-        Wp, WpT, bias_sum = packed
-        Xp = _pixel_major_bf16(x.detach())
-        logits = _lib.aspp_forward(Xp, Wp, bias_sum, rates, N, h, w, C)
+        xd = x.detach()
+        if not xd.is_cuda:
+            raise _lib.B200SegError("ASPP head: expected CUDA features (b200seg has no CPU fallback)")
+        if xd.dtype == torch.bfloat16 or _PACK_CACHE_SLOTS > 0:
+            xk, x_kind = _pixel_major_bf16(xd), 1           # bf16 channels_last input is taken zero-copy
+        else:
+            xk, x_kind = (xd if xd.dtype == torch.float32 else xd.float()).contiguous(), 0
         need_grad = any(ctx.needs_input_grad)
         inv_t = 1.0 / float(temperature)
-        out2, ws = _lib.upsample_ce_forward(logits, labels.contiguous(), ignore_index, inv_t, need_grad)
-        ctx.meta = (tuple(rates), (N, Cin, h, w, C), tuple(labels.shape[-2:]), inv_t, x.dtype, need_grad)
-        ctx.save_for_backward(Xp, WpT, out2, ws)
+        loss, logits, ws = _lib.head_loss_forward(xk, x_kind, (N, Cin, h, w), [p.detach() for p in weights],
+                                                  [None if b is None else b.detach() for b in biases], rates, labels.contiguous(),
+                                                  ignore_index, inv_t, need_grad)
+        ctx.meta = (rates, (N, Cin, h, w), C, tuple(labels.shape[-2:]), inv_t, x.dtype, need_grad, x_kind)
+        ctx.save_for_backward(ws, xk if x_kind == 1 else None)
         ctx.mark_non_differentiable(logits)
         ctx.set_materialize_grads(False)       # no zero tensor for the (non-differentiable) logits output in backward
-        return out2[0].clone(), logits
+        return loss, logits
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_logits_unused):
-        Xp, WpT, out2, ws = ctx.saved_tensors
-        rates, (N, Cin, h, w, C), size, inv_t, x_dtype, need_grad = ctx.meta
+        ws, x_bf16 = ctx.saved_tensors
+        rates, shape, C, size, inv_t, x_dtype, need_grad, x_kind = ctx.meta
         if not need_grad:
             raise _lib.B200SegError("forward_loss: forward ran without gradient tracking")
         R = len(rates)
-        need = ctx.needs_input_grad
-        need_w = any(need[7:7 + R])
-        need_b = any(need[7 + R:7 + 2 * R])
+        need = ctx.needs_input_grad          # x, labels, ignore_index, temperature, rates, grad_bucket, R weights, R biases
+        need_w = any(need[6:6 + R])
+        need_b = any(need[6 + R:6 + 2 * R])
         if grad_loss is None:
-            return (None,) * (7 + 2 * R)
-        gOt, bias = _lib.upsample_ce_backward_packed(ws, out2, (N, C, h, w), size, inv_t, grad_loss.detach().float(), need_b)
+            return (None,) * (6 + 2 * R)
+        grad_loss = grad_loss.detach()
+        if grad_loss.dtype != torch.float32:
+            grad_loss = grad_loss.float()
         # bf16 features (the channels_last seam format): the dgrad GEMM writes the bf16 NHWC gradient itself
-        seam = x_dtype == torch.bfloat16 and Cin % 8 == 0
+        seam = x_dtype == torch.bfloat16 and shape[1] % 8 == 0
         bucket = ctx.grad_bucket
         if bucket is not None and need_w and need_b:
             # data-parallel path: the weight / bias gradients are written straight into the flat bucket (the parameters'
             # .grad alias it), and the bucket's all-reduce starts on its own stream as soon as they are complete --
             # underneath the data-gradient GEMM.  Autograd gets no parameter gradients from this node.
-            bucket.set_bias_grads_(bias)              # enqueued before the GEMMs, so ready_event covers it too
-            gx, _ = _lib.aspp_backward_packed(gOt, Xp, WpT, rates, N, h, w, C, need[0], True, nhwc_bf16=seam,
-                                              out_w=bucket.weight_buffers(), weights_ready_event=bucket.ready_event)
+            gx, _, _ = _lib.head_loss_backward(ws, x_bf16, x_kind, shape, C, rates, size, inv_t, grad_loss, need[0], True, True,
+                                               nhwc_bf16=seam, out_w=bucket.weight_buffers(), out_b=bucket.bias_buffers(),
+                                               weights_ready_event=bucket.ready_event)
             bucket.begin_allreduce_()
             if gx is not None and gx.dtype != x_dtype:
                 gx = gx.to(x_dtype)
-            return (gx,) + (None,) * (6 + 2 * R)
-        gx, gws = _lib.aspp_backward_packed(gOt, Xp, WpT, rates, N, h, w, C, need[0], need_w, nhwc_bf16=seam)
+            return (gx,) + (None,) * (5 + 2 * R)
+        gx, gws, gbs = _lib.head_loss_backward(ws, x_bf16, x_kind, shape, C, rates, size, inv_t, grad_loss, need[0], need_w, need_b,
+                                               nhwc_bf16=seam)
         if gx is not None and gx.dtype != x_dtype:
             gx = gx.to(x_dtype)
-        out_w = [gws[r] if (gws is not None and need[7 + r]) else None for r in range(R)]
-        out_b = [(bias if r == 0 else bias.clone()) if (bias is not None and need[7 + R + r]) else None for r in range(R)]
-        return (gx, None, None, None, None, None, None, *out_w, *out_b)
+        out_w = [gws[r] if (gws is not None and need[6 + r]) else None for r in range(R)]
+        out_b = [gbs[r] if (gbs is not None and need[6 + R + r]) else None for r in range(R)]
+        return (gx, None, None, None, None, None, *out_w, *out_b)
 
 
 def aspp_head_loss(x, labels, weights, biases, rates, ignore_index=255, temperature=1.0, packed=None, grad_bucket=None):
     """(loss, low-res logits [detached]) == CrossEntropyLoss(ignore_index)(interpolate(head(x), labels.shape[-2:]) / T, labels).
     ``grad_bucket`` (distributed.HeadGradBucket): write the parameter gradients into the bucket and overlap its all-reduce
-    with the data-gradient GEMM instead of returning them through autograd."""
+    with the data-gradient GEMM instead of returning them through autograd.  ``packed`` is accepted for compatibility and
+    ignored: the weights are packed inside the one-call entry on every step (a ~6 us kernel), never cached."""
     labels = _lib.as_label_tensor(labels)            # int64 or uint8 as they are; anything else widened to int64
-    return _AsppHeadLossFn.apply(x, labels, int(ignore_index), float(temperature), tuple(int(r) for r in rates), packed,
-                                 grad_bucket, *weights, *biases)
+    return _AsppHeadLossFn.apply(x, labels, int(ignore_index), float(temperature), tuple(int(r) for r in rates), grad_bucket,
+                                 *weights, *biases)
 
 
 # --------------------------------------------------------------------------------------------

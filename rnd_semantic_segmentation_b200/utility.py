@@ -228,14 +228,12 @@ class LazyProbabilities:
         return [m.detach().float().contiguous() for m in self.members]
 
     def materialize(self) -> torch.Tensor:
+        """The real [1,C,H,W] probability tensor, written by the fused kernel (K7 with ``want_probs``: upsample + ATen's exact
+        soft-max sequence per label pixel, bit-equal to ``F.softmax(F.interpolate(...))`` on CUDA) -- single member or ensemble."""
         if self._full is None:
-            if self.is_ensemble:
-                _, _, probs = _lib.tta_argmax_confusion(self._members32(), self.flips, self.label.shape[-2:],
-                                                        divisors=self.divisors, want_probs=True)
-                self._full = probs.unsqueeze(0)
-            else:
-                up = ops.upsample_bilinear_align_corners(self.logits_lr, self.label.shape[-2:])
-                self._full = F.softmax(up, dim=1)
+            _, _, probs = _lib.tta_argmax_confusion(self._members32(), self.flips, self.label.shape[-2:],
+                                                    divisors=self.divisors, want_probs=True)
+            self._full = probs.unsqueeze(0)
         return self._full
 
     def max(self, dim=None, keepdim=False):

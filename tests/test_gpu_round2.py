@@ -671,3 +671,101 @@ def test_head_forward_straight_from_fp32_nchw_equals_packed_path(lib, n, cin, C,
     xr = x.clone().requires_grad_(True)
     head.logits(xr).square().sum().backward()
     assert torch.equal(xg.grad, xr.grad)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# one foreign call per direction for the fused train slice (b200seg_head_loss_forward / _backward)
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,cin,C,h,w,H,W,ldt,xdt", [
+    (2, 256, 19, 33, 65, 128, 256, torch.int64, torch.float32),
+    (1, 2048, 19, 65, 129, 512, 1024, torch.uint8, torch.float32),
+    (3, 128, 2, 44, 44, 352, 352, torch.int64, torch.float32),
+    (2, 256, 19, 33, 65, 128, 256, torch.uint8, torch.bfloat16),
+    (2, 64, 7, 9, 13, 40, 50, torch.int64, torch.float32),
+])
+def test_one_call_train_slice_equals_the_separate_entries(lib, n, cin, C, h, w, H, W, ldt, xdt):
+    """forward_loss (ONE C-ABI call each way) == the same kernels issued through the separate entries (pack, head GEMM, upsample+CE,
+    packed backward): loss, logits, dX, dW and db bit-identical -- the composition adds no arithmetic of its own."""
+    import rnd_semantic_segmentation_b200 as b200
+    from rnd_semantic_segmentation_b200 import ops
+    torch.manual_seed(11)
+    head = b200.ASPP_Classifier_V2(cin, RATES, RATES, C).cuda()
+    g = torch.Generator().manual_seed(12)
+    x = torch.relu(torch.randn(n, cin, h, w, generator=g)).cuda()
+    if xdt == torch.bfloat16:
+        x = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    labels = torch.randint(0, C, (n, H, W), generator=g)
+    labels[torch.rand(n, H, W, generator=g) < 0.1] = 255
+    labels = labels.to(ldt).cuda()
+    T = 1.8
+    xg = x.clone().requires_grad_(True)
+    loss, logits = head.forward_loss(xg, labels, temperature=T)
+    loss.backward(torch.tensor(0.75, device="cuda"))
+    got = [loss.detach().clone(), logits.clone(), xg.grad.clone()] + [p.grad.clone() for p in head.parameters()]
+    assert xg.grad.dtype == xdt
+    # the separate entries
+    ws_, bs_ = [m.weight.detach() for m in head.conv2d_list], [m.bias.detach() for m in head.conv2d_list]
+    Wp, WpT, bias_sum = lib.aspp_pack_weights(ws_, bs_)
+    Xp = ops._pixel_major_bf16(x)
+    lg = lib.aspp_forward(Xp, Wp, bias_sum, RATES, n, h, w, C)
+    out2, k2ws = lib.upsample_ce_forward(lg, labels, 255, 1.0 / T, True)
+    gOt, bias = lib.upsample_ce_backward_packed(k2ws, out2, (n, C, h, w), (H, W), 1.0 / T, torch.tensor([0.75], device="cuda"), True)
+    gx, gws = lib.aspp_backward_packed(gOt, Xp, WpT, RATES, n, h, w, C, True, True, nhwc_bf16=(xdt == torch.bfloat16))
+    assert torch.equal(got[0], out2[0]) and torch.equal(got[1], lg)
+    assert torch.equal(got[2].float(), gx.float())
+    params = list(head.parameters())                     # conv2d_list.{0..3}.{weight,bias}
+    for r in range(4):
+        assert torch.equal(params[2 * r].grad, gws[r])
+        assert torch.equal(params[2 * r + 1].grad, bias)
+    assert lib.default_wgrad_splits(n * h * w, C, cin, 4) == lib.load().b200seg_aspp_default_wgrad_splits(n * h * w, C, cin, 4)
+
+
+def test_one_call_train_slice_partial_needs_and_two_forwards_in_flight(lib):
+    """Frozen head (only dX wanted), frozen features (only parameter gradients wanted), and two forwards in flight before either
+    backward (source + target batch through the same head, aspp_fada.py:88-104): each workspace lives with its own graph node."""
+    import rnd_semantic_segmentation_b200 as b200
+    torch.manual_seed(13)
+    n, cin, C, h, w, H, W = 2, 128, 19, 17, 23, 96, 128
+    head = b200.ASPP_Classifier_V2(cin, RATES, RATES, C).cuda()
+    g = torch.Generator().manual_seed(14)
+    xa = torch.relu(torch.randn(n, cin, h, w, generator=g)).cuda()
+    xb = torch.relu(torch.randn(n, cin, h, w, generator=g)).cuda()
+    la = torch.randint(0, C, (n, H, W), generator=g).cuda()
+    lb = torch.randint(0, C, (n, H, W), generator=g).cuda()
+
+    def grads(x, lab):
+        for p in head.parameters():
+            p.grad = None
+        xg = x.clone().requires_grad_(True)
+        head.forward_loss(xg, lab)[0].backward()
+        return xg.grad.clone(), [p.grad.clone() for p in head.parameters()]
+
+    gxa, gpa = grads(xa, la)
+    gxb, gpb = grads(xb, lb)
+    # two forwards, then the backwards in the opposite order
+    for p in head.parameters():
+        p.grad = None
+    xga, xgb = xa.clone().requires_grad_(True), xb.clone().requires_grad_(True)
+    l_a, _ = head.forward_loss(xga, la)
+    l_b, _ = head.forward_loss(xgb, lb)
+    l_b.backward()
+    l_a.backward()
+    assert torch.equal(xga.grad, gxa) and torch.equal(xgb.grad, gxb)
+    for p, a, b in zip(head.parameters(), gpa, gpb):
+        assert torch.equal(p.grad, b + a)                           # accumulated by autograd in backward order
+    # frozen features
+    for p in head.parameters():
+        p.grad = None
+    head.forward_loss(xa, la)[0].backward()
+    for p, a in zip(head.parameters(), gpa):
+        assert torch.equal(p.grad, a)
+    # frozen head
+    for p in head.parameters():
+        p.requires_grad_(False)
+    xg = xa.clone().requires_grad_(True)
+    head.forward_loss(xg, la)[0].backward()
+    assert torch.equal(xg.grad, gxa)
+    # no gradient at all: forward only, and a backward through it is refused loudly
+    with torch.no_grad():
+        l0, lg0 = head.forward_loss(xa, la)
+    assert torch.equal(l0, l_a.detach())

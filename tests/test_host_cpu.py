@@ -282,3 +282,15 @@ def test_fused_optimizers_pickle_and_state_dict_contract():
         for clone in (copy.deepcopy(ours), pickle.loads(pickle.dumps(ours))):
             assert type(clone) is type(ours) and clone._plans == {} and clone.grad_scale == ours.grad_scale
             assert clone.state_dict()["param_groups"] == a["param_groups"]
+
+
+def test_c_side_split_rule_matches_the_python_one(built_lib):
+    """b200seg_head_loss_backward picks the weight-gradient split-K factor itself; it must be the rule the separate entries use."""
+    from rnd_semantic_segmentation_b200 import _lib
+    lib = _lib.load()
+    for P in (1, 63, 64, 200, 1936, 8385, 16770, 30976, 67080, 131072, 1 << 22):
+        for C, Cin, R in ((19, 2048, 4), (2, 2048, 4), (19, 256, 4), (7, 64, 2), (32, 512, 1)):
+            assert lib.b200seg_aspp_default_wgrad_splits(P, C, Cin, R) == _lib.default_wgrad_splits(P, C, Cin, R), (P, C, Cin, R)
+    assert lib.b200seg_head_loss_workspace_bytes(2, 2048, 19, 65, 129, 4, 512, 1024, 0) > 2 * 65 * 129 * 2048 * 2
+    assert lib.b200seg_head_loss_workspace_bytes(2, 2048, 19, 65, 129, 4, 512, 1024, 1) < 2 * 65 * 129 * 2048 * 2
+    assert lib.b200seg_head_loss_workspace_bytes(0, 2048, 19, 65, 129, 4, 512, 1024, 0) == 0
