@@ -318,7 +318,7 @@ def run_ours(args):
     lh = labels.cpu().pin_memory()
     e2e_step = HostPipelinedStep(dev, (xh, lh), lambda xd, ld: train_step(xd, ld)[0])
     e2e_steps = max(2, min(args.steps, 10))
-    ms_e2e, _ = timed(e2e_step, e2e_steps, 1)
+    ms_e2e, _ = timed(e2e_step, e2e_steps, 4)
     e2e = {"value": round(world * label_px / (ms_e2e / e2e_steps * 1e-3) / 1e6, 2), "unit": "Mpx/s",
            "h2d_bytes_per_step": xh.numel() * 4 + lh.numel() * 8, "d2h_bytes_per_step": 4,
            "note": "public API from pinned host buffers; every step's H2D and loss D2H are inside the timed region, the H2D of "
@@ -328,7 +328,7 @@ def run_ours(args):
     xh = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last).cpu().pin_memory()
     lh = labels.to(torch.uint8).cpu().pin_memory()
     e2e_seam_step = HostPipelinedStep(dev, (xh, lh), lambda xd, ld: train_step(xd, ld)[0])
-    ms_e2e_s, _ = timed(e2e_seam_step, e2e_steps, 1)
+    ms_e2e_s, _ = timed(e2e_seam_step, e2e_steps, 4)
     e2e["seam_bf16_uint8_value"] = round(world * label_px / (ms_e2e_s / e2e_steps * 1e-3) / 1e6, 2)
     e2e["seam_h2d_bytes_per_step"] = xh.numel() * 2 + lh.numel()
     del xh, lh, e2e_seam_step
@@ -506,7 +506,9 @@ def run_baseline_configs(b200, _lib, synth, dev, rank, peaks, args):
             loss.backward()
             return loss
 
-        ms, _ = timed(step, args.steps, args.warmup)
+        # (two alternating inputs = two address sets: each is seen once, then captured by the one-call entries' graph cache,
+        #  so six warm-up steps put the timed region in the steady state a training loop runs in)
+        ms, _ = timed(step, args.steps, max(args.warmup, 6))
         _lib.profile_enable(True)
         for _ in range(4):
             step()

@@ -229,6 +229,14 @@ B200SEG_API int b200seg_head_loss_backward(void* workspace, int64_t workspace_by
                                     float inv_temperature, const float* grad_loss, void* scratch, int64_t scratch_bytes,
                                     float* grad_x, void* grad_x_nhwc_bf16, float* const* grad_w, float* const* grad_b,
                                     void* weights_ready_event, void* stream);
+/* The two entries above replay their kernel sequence from a CUDA graph once the same arguments (addresses, shapes, scalars) have
+ * been seen twice -- a training loop in steady state gets the same addresses back from its allocator every iteration, and ~7
+ * launches per direction become one cudaGraphLaunch on the caller's stream (weights_ready_event is recorded from inside the
+ * graph as an external event node).  Direct launches whenever the caller is itself capturing, per-kernel profiling is on, or the
+ * addresses keep changing (the cache then turns itself off).  on = 0 disables (also env B200SEG_STEP_GRAPHS=0); stats: replays
+ * and captures so far. */
+B200SEG_API void b200seg_set_step_graphs(int on);
+B200SEG_API void b200seg_step_graph_stats(long long* replays, long long* captures);
 /* split-K factor the weight-gradient GEMM uses for P = N*h*w pixels (what the entries above pick) */
 B200SEG_API int b200seg_aspp_default_wgrad_splits(int64_t P, int C, int Cin, int R);
 

@@ -14,6 +14,8 @@ head = b200.ASPP_Classifier_V2(cin, RATES, RATES, C).to(dev)
 x = synth.make_features(n, cin, h, w, device=dev)
 labels = synth.make_labels(n, H, W, C, device=dev)
 b200.set_feature_pack_cache(0)
+from rnd_semantic_segmentation_b200 import _lib
+_lib.set_step_graphs(os.environ.get("GRAPHS", "1") != "0")
 params = list(head.parameters())
 
 
@@ -43,3 +45,4 @@ pr.disable()
 torch.cuda.synchronize()
 st = pstats.Stats(pr)
 st.sort_stats("cumulative").print_stats(28)
+print("step graphs (replays, captures):", _lib.step_graph_stats())

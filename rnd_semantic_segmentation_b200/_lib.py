@@ -81,6 +81,8 @@ SIGNATURES = {
     "b200seg_head_loss_backward": (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                            c_f32, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b200seg_aspp_default_wgrad_splits": (c_int, [c_i64, c_int, c_int, c_int]),
+    "b200seg_set_step_graphs": (None, [c_int]),
+    "b200seg_step_graph_stats": (None, [c_vp, c_vp]),
     "b200seg_conv3x3_pack_weights": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     "b200seg_conv3x3_pack_weights_stack": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
     "b200seg_conv3x3_forward": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_i64, c_vp, c_int, c_int, c_vp, c_int, c_f32, c_vp, c_i64,
@@ -835,6 +837,18 @@ def _head_loss_plan(N, Cin, C, h, w, R, H, W, x_kind, rates):
                 int(lib.b200seg_head_loss_scratch_bytes(N, Cin, C, h, w, R)), (c_int * R)(*rates))
         _head_loss_plans[key] = plan
     return plan
+
+
+def set_step_graphs(on: bool):
+    """Graph replay of the one-call train entries (default on; env B200SEG_STEP_GRAPHS=0 turns it off at load time)."""
+    load().b200seg_set_step_graphs(1 if on else 0)
+
+
+def step_graph_stats():
+    """(replays, captures) of the one-call train entries since the last set_step_graphs()."""
+    a, b = ctypes.c_longlong(0), ctypes.c_longlong(0)
+    load().b200seg_step_graph_stats(ctypes.byref(a), ctypes.byref(b))
+    return a.value, b.value
 
 
 def head_loss_forward(x: torch.Tensor, x_kind: int, shape, weights, biases, rates, labels: torch.Tensor, ignore_index: int,

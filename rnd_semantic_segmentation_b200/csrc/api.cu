@@ -1,5 +1,6 @@
 // extern "C" boundary of libb200seg.so (declarations + reference citations: include/b200seg.h)
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "../../include/b200seg.h"
 #include "common.cuh"
@@ -130,6 +131,127 @@ static int require_device() {
 
 using namespace b200seg;
 #define S(stream) reinterpret_cast<cudaStream_t>(stream)
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Replay of the one-call train entries from CUDA graphs.  The sequence a call enqueues is a pure function of its arguments
+// (pointers, shapes, scalars) and of the library's global switches, so the second time the SAME arguments are seen the sequence
+// is captured on a private stream and from then on replayed with one cudaGraphLaunch on the caller's stream -- a training loop
+// in steady state hands the same addresses back every iteration (caching allocator), and ~7 launches per direction become one.
+// Anything that makes the replay unsafe or pointless takes the direct path: caller already capturing, per-kernel profiling on,
+// a switch flipped (all graphs dropped), addresses that keep changing (cache turns itself off).
+// ---------------------------------------------------------------------------------------------------------------------------
+struct StepKey {
+  const void* p[28];
+  long long i[24];
+  float f[4];
+};
+struct StepGraph {
+  StepKey key;
+  cudaGraphExec_t exec;
+  long long launches;
+  unsigned long long stamp;
+  bool used;
+};
+constexpr int STEP_GRAPHS = 16;
+static StepGraph g_step_graphs[STEP_GRAPHS];
+static cudaStream_t g_step_capture_stream[64];
+static int g_step_graphs_on = -1;                 // -1: read B200SEG_STEP_GRAPHS on first use
+static long long g_step_hits = 0, g_step_captures = 0;
+static unsigned long long g_step_stamp = 0;
+static int g_step_lock = 0;
+struct StepLock {
+  StepLock() { while (__atomic_exchange_n(&g_step_lock, 1, __ATOMIC_ACQUIRE)) {} }
+  ~StepLock() { __atomic_store_n(&g_step_lock, 0, __ATOMIC_RELEASE); }
+};
+
+static void step_graphs_drop_locked() {
+  for (int q = 0; q < STEP_GRAPHS; ++q) {
+    if (g_step_graphs[q].exec) cudaGraphExecDestroy(g_step_graphs[q].exec);
+    g_step_graphs[q] = StepGraph{};
+  }
+}
+static void step_graphs_drop() {
+  StepLock lock;
+  step_graphs_drop_locked();
+}
+
+template <class Body>
+static int run_step(const StepKey& key, cudaStream_t stream, bool allow_graph, Body&& body) {
+  if (g_step_graphs_on < 0) {
+    const char* e = getenv("B200SEG_STEP_GRAPHS");
+    g_step_graphs_on = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!allow_graph || !g_step_graphs_on || g_prof_on) return body(stream);
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return body(stream);
+  }
+  StepLock lock;
+  int slot = -1, lru = 0;                                                        // lru: a free slot, else the least recently used
+  for (int q = 0; q < STEP_GRAPHS; ++q) {
+    const StepGraph& c = g_step_graphs[q];
+    if (c.used && memcmp(&c.key, &key, sizeof(StepKey)) == 0) { slot = q; break; }
+    const StepGraph& b = g_step_graphs[lru];
+    if ((!c.used && b.used) || (c.used == b.used && c.stamp < b.stamp)) lru = q;
+  }
+  if (slot >= 0 && g_step_graphs[slot].exec) {                                   // replay
+    StepGraph& g = g_step_graphs[slot];
+    g.stamp = ++g_step_stamp;
+    ++g_step_hits;
+    __atomic_add_fetch(&g_launches, g.launches, __ATOMIC_RELAXED);
+    B200SEG_CUDA(cudaGraphLaunch(g.exec, stream));
+    return B200SEG_OK;
+  }
+  if (slot < 0) {                                                                // first sight: remember, run directly
+    StepGraph& g = g_step_graphs[lru];
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g = StepGraph{};
+    g.key = key; g.used = true; g.stamp = ++g_step_stamp;
+    return body(stream);
+  }
+  // second sight: capture on the private stream, instantiate, launch on the caller's stream
+  if (g_step_captures >= 48 && g_step_hits < 2 * g_step_captures) {             // addresses keep changing: stop trying
+    g_step_graphs_on = 0;
+    step_graphs_drop_locked();
+    return body(stream);
+  }
+  int dev = 0;
+  B200SEG_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return body(stream);
+  if (!g_step_capture_stream[dev]) B200SEG_CUDA(cudaStreamCreateWithFlags(&g_step_capture_stream[dev], cudaStreamNonBlocking));
+  cudaStream_t cs = g_step_capture_stream[dev];
+  if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    return body(stream);
+  }
+  const long long l0 = g_launches;
+  const int rc = body(cs);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(cs, &graph);
+  const long long captured = g_launches - l0;
+  __atomic_sub_fetch(&g_launches, captured, __ATOMIC_RELAXED);                   // nothing has run yet
+  if (rc != B200SEG_OK || e != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    g_step_graphs[slot] = StepGraph{};
+    return rc != B200SEG_OK ? rc : body(stream);
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e2 != cudaSuccess || !exec) {
+    cudaGetLastError();
+    g_step_graphs[slot] = StepGraph{};
+    return body(stream);
+  }
+  StepGraph& g = g_step_graphs[slot];
+  g.exec = exec; g.launches = captured; g.stamp = ++g_step_stamp;
+  ++g_step_captures;
+  __atomic_add_fetch(&g_launches, captured, __ATOMIC_RELAXED);
+  B200SEG_CUDA(cudaGraphLaunch(exec, stream));
+  return B200SEG_OK;
+}
 #define REQUIRE_DEVICE()                 \
   do {                                   \
     int rc__ = require_device();         \
@@ -423,7 +545,7 @@ int b200seg_tta_argmax_confusion_ex(const float* const* logits_lr, const int* h,
 }
 
 void b200seg_tta_set_row_walk(int on) { tta_set_row_walk(on); }
-void b200seg_upsample_ce_set_variant(int v) { k2_set_variant(v); }
+void b200seg_upsample_ce_set_variant(int v) { step_graphs_drop(); k2_set_variant(v); }
 
 int b200seg_p2p_allreduce_mean(void* const* peer_bufs_host, void* multicast_ptr, void* const* signal_pads_host, int rank, int world,
                                int64_t numel, int blocks, int pad_slot0, void* stream) {
@@ -457,6 +579,7 @@ int b200seg_nhwc_bf16_colsum(const void* g, int64_t P, int C, int pitch, void* s
 long long b200seg_launch_count(void) { return g_launches; }
 
 void b200seg_profile_enable(int on) {
+  step_graphs_drop();
   for (int t = 0; t < PROF_TAGS; ++t) {
     for (int i = 0; i < g_prof_n[t]; ++i) { cudaEventDestroy(g_prof_ev[t][i][0]); cudaEventDestroy(g_prof_ev[t][i][1]); }
     g_prof_n[t] = 0;
@@ -477,17 +600,17 @@ int b200seg_profile_read(int tag, double* total_ms, int* count) {
   return B200SEG_OK;
 }
 
-void b200seg_conv_set_pair(int on) { gemm::conv::set_pair(on); }
-void b200seg_gemm_set_sharing(int on) { gemm::set_sharing(on); }
-void b200seg_gemm_set_narrow_tiles(int on) { gemm::set_narrow_tiles(on); }
-void b200seg_gemm_set_dgrad_n_fastest(int on) { gemm::set_n_fastest(on); }
-void b200seg_gemm_set_tma_store(int on) { gemm::set_tma_store(on); }
-void b200seg_gemm_set_fwd_convert(int on) { gemm::set_fwd_convert(on); }
+void b200seg_conv_set_pair(int on) { step_graphs_drop(); gemm::conv::set_pair(on); }
+void b200seg_gemm_set_sharing(int on) { step_graphs_drop(); gemm::set_sharing(on); }
+void b200seg_gemm_set_narrow_tiles(int on) { step_graphs_drop(); gemm::set_narrow_tiles(on); }
+void b200seg_gemm_set_dgrad_n_fastest(int on) { step_graphs_drop(); gemm::set_n_fastest(on); }
+void b200seg_gemm_set_tma_store(int on) { step_graphs_drop(); gemm::set_tma_store(on); }
+void b200seg_gemm_set_fwd_convert(int on) { step_graphs_drop(); gemm::set_fwd_convert(on); }
 int b200seg_gemm_fwd_convert_selftest(int M, int n_img, int hw, int K, int write_xn, double* max_err, double* max_ref, double* xn_err) {
   REQUIRE_DEVICE();
   return gemm::selftest_fwd_convert(M, n_img, hw, K, write_xn, max_err, max_ref, xn_err);
 }
-void b200seg_gemm_set_overlap_sms(int n) { gemm::set_overlap_sms(n); }
+void b200seg_gemm_set_overlap_sms(int n) { step_graphs_drop(); gemm::set_overlap_sms(n); }
 
 int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b_mn_major, int splits, int col_hw, int share, double* max_err,
                           double* max_ref) {
@@ -569,20 +692,33 @@ int b200seg_head_loss_forward(const void* x, int x_kind, const float* const* wei
   const HeadLossLayout L = head_loss_layout(N, Cin, C, h, w, R, H, W, x_kind);
   B200SEG_CHECK_ARG(workspace_bytes >= L.total, "head_loss_forward: workspace too small (%lld < %lld)", (long long)workspace_bytes, L.total);
   B200SEG_CHECK_ARG(scratch_bytes >= aspp_yt_bytes(N, C, h, w, R), "head_loss_forward: scratch too small");
-  char* base = reinterpret_cast<char*>(workspace);
-  float* bias_sum = reinterpret_cast<float*>(base + L.bias_sum);
-  int rc = aspp_pack_weights(weights, biases, R, C, Cin, base + L.Wp, base + L.WpT, bias_sum, S(stream));
-  if (rc) return rc;
-  const void* Xp = x;
-  if (x_kind == 0) {
-    rc = aspp_pack_features(reinterpret_cast<const float*>(x), N, Cin, h, w, base + L.Xp, S(stream));
+  StepKey key = {};
+  int np = 0, ni = 0;
+  key.p[np++] = x; key.p[np++] = labels; key.p[np++] = workspace; key.p[np++] = scratch; key.p[np++] = logits; key.p[np++] = loss_out;
+  B200SEG_CHECK_ARG(R <= 8, "head_loss_forward: %d dilation branches unsupported", R);
+  for (int r = 0; r < R; ++r) { key.p[np++] = weights[r]; key.p[np++] = biases ? biases[r] : nullptr; key.i[ni++] = rates_host[r]; }
+  const long long ints[] = {1, x_kind, R, N, Cin, C, h, w, label_bytes, H, W, ignore_index, need_grad, workspace_bytes, scratch_bytes};
+  for (long long v : ints) key.i[ni++] = v;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  key.i[ni++] = dev;
+  key.f[0] = inv_temperature;
+  return run_step(key, S(stream), true, [&](cudaStream_t st) -> int {
+    char* base = reinterpret_cast<char*>(workspace);
+    float* bias_sum = reinterpret_cast<float*>(base + L.bias_sum);
+    int rc = aspp_pack_weights(weights, biases, R, C, Cin, base + L.Wp, base + L.WpT, bias_sum, st);
     if (rc) return rc;
-    Xp = base + L.Xp;
-  }
-  rc = aspp_forward(Xp, base + L.Wp, bias_sum, rates_host, R, N, Cin, C, h, w, reinterpret_cast<float*>(scratch), logits, S(stream));
-  if (rc) return rc;
-  return k2_forward(logits, N, C, h, w, labels, label_bytes, H, W, ignore_index, inv_temperature, need_grad, base + L.k2ws,
-                    k2_workspace_bytes(N, C, h, w, H, W), reinterpret_cast<float*>(base + L.out2), S(stream), loss_out);
+    const void* Xp = x;
+    if (x_kind == 0) {
+      rc = aspp_pack_features(reinterpret_cast<const float*>(x), N, Cin, h, w, base + L.Xp, st);
+      if (rc) return rc;
+      Xp = base + L.Xp;
+    }
+    rc = aspp_forward(Xp, base + L.Wp, bias_sum, rates_host, R, N, Cin, C, h, w, reinterpret_cast<float*>(scratch), logits, st);
+    if (rc) return rc;
+    return k2_forward(logits, N, C, h, w, labels, label_bytes, H, W, ignore_index, inv_temperature, need_grad, base + L.k2ws,
+                      k2_workspace_bytes(N, C, h, w, H, W), reinterpret_cast<float*>(base + L.out2), st, loss_out);
+  });
 }
 
 int b200seg_head_loss_backward(void* workspace, int64_t workspace_bytes, const void* x_bf16, int x_kind, const int* rates_host, int R,
@@ -597,15 +733,40 @@ int b200seg_head_loss_backward(void* workspace, int64_t workspace_bytes, const v
   B200SEG_CHECK_ARG(workspace_bytes >= L.total, "head_loss_backward: workspace too small");
   const int splits = head_default_splits((long long)N * h * w, C, Cin, R);
   B200SEG_CHECK_ARG(scratch_bytes >= aspp_bwd_scratch_bytes(N, Cin, C, h, w, R, splits), "head_loss_backward: scratch too small");
-  char* base = reinterpret_cast<char*>(workspace);
-  void* gOt = aspp_bwd_gOt_ptr(scratch);
-  int rc = k2_backward_packed_multi(base + L.k2ws, N, C, h, w, H, W, inv_temperature, reinterpret_cast<const float*>(base + L.out2),
-                                    grad_loss, gOt, grad_b, grad_b ? R : 0, S(stream));
-  if (rc) return rc;
-  if (!grad_x && !grad_x_nhwc_bf16 && !grad_w) return B200SEG_OK;
-  const void* Xp = x_kind == 0 ? static_cast<const void*>(base + L.Xp) : x_bf16;
-  return aspp_backward_packed(gOt, Xp, base + L.WpT, rates_host, R, N, Cin, C, h, w, scratch, scratch_bytes, splits, grad_x, grad_w,
-                              S(stream), grad_x_nhwc_bf16, reinterpret_cast<cudaEvent_t>(weights_ready_event));
+  StepKey key = {};
+  int np = 0, ni = 0;
+  key.p[np++] = workspace; key.p[np++] = x_bf16; key.p[np++] = grad_loss; key.p[np++] = scratch; key.p[np++] = grad_x;
+  key.p[np++] = grad_x_nhwc_bf16;
+  for (int r = 0; r < R; ++r) { key.p[np++] = grad_w ? grad_w[r] : nullptr; key.p[np++] = grad_b ? grad_b[r] : nullptr; key.i[ni++] = rates_host[r]; }
+  const long long ints[] = {2, x_kind, R, N, Cin, C, h, w, H, W, grad_w != nullptr, grad_b != nullptr, workspace_bytes, scratch_bytes};
+  for (long long v : ints) key.i[ni++] = v;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  key.i[ni++] = dev;
+  key.f[0] = inv_temperature;
+  key.p[np++] = weights_ready_event;       // recorded as an external event node inside the graph (aspp_backward_packed)
+  return run_step(key, S(stream), true, [&](cudaStream_t st) -> int {
+    char* base = reinterpret_cast<char*>(workspace);
+    void* gOt = aspp_bwd_gOt_ptr(scratch);
+    int rc = k2_backward_packed_multi(base + L.k2ws, N, C, h, w, H, W, inv_temperature, reinterpret_cast<const float*>(base + L.out2),
+                                      grad_loss, gOt, grad_b, grad_b ? R : 0, st);
+    if (rc) return rc;
+    if (!grad_x && !grad_x_nhwc_bf16 && !grad_w) return B200SEG_OK;
+    const void* Xp = x_kind == 0 ? static_cast<const void*>(base + L.Xp) : x_bf16;
+    return aspp_backward_packed(gOt, Xp, base + L.WpT, rates_host, R, N, Cin, C, h, w, scratch, scratch_bytes, splits, grad_x, grad_w,
+                                st, grad_x_nhwc_bf16, reinterpret_cast<cudaEvent_t>(weights_ready_event));
+  });
+}
+
+void b200seg_set_step_graphs(int on) {
+  step_graphs_drop();
+  g_step_graphs_on = on ? 1 : 0;
+  g_step_hits = g_step_captures = 0;
+}
+
+void b200seg_step_graph_stats(long long* replays, long long* captures) {
+  if (replays) *replays = g_step_hits;
+  if (captures) *captures = g_step_captures;
 }
 
 }  // extern "C"

@@ -560,7 +560,15 @@ int aspp_backward_packed(const void* gOt_in, const void* Xp, const void* WpT, co
   }
   // the weight gradients are complete here: a caller that all-reduces them on another stream can start while the
   // data-gradient GEMM below is still running
-  if (weights_ready) B200SEG_CUDA(cudaEventRecord(weights_ready, stream));
+  if (weights_ready) {
+    // inside a stream capture (the one-call entry's graph cache, or the caller's own graph) the record becomes an EXTERNAL event
+    // node: every launch of the graph records the event when the weight gradients are complete, and a cudaStreamWaitEvent
+    // issued on another stream after the graph launch orders behind it
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    B200SEG_CUDA(cudaStreamIsCapturing(stream, &cap));
+    if (cap == cudaStreamCaptureStatusActive) B200SEG_CUDA(cudaEventRecordWithFlags(weights_ready, stream, cudaEventRecordExternal));
+    else B200SEG_CUDA(cudaEventRecord(weights_ready, stream));
+  }
   if (grad_x) {
     // dX[ci, p] = WpT[ci, :] . G't[:, p]   -> fp32 NCHW: column p = (image, pixel), row = channel
     gemm::Operand a{(const __nv_bfloat16*)WpT, false, NJ};

@@ -133,8 +133,8 @@ class _AsppHeadLossFn(torch.autograd.Function):
             xk, x_kind = (xd if xd.dtype == torch.float32 else xd.float()).contiguous(), 0
         need_grad = any(ctx.needs_input_grad)
         inv_t = 1.0 / float(temperature)
-        loss, logits, ws = _lib.head_loss_forward(xk, x_kind, (N, Cin, h, w), [p.detach() for p in weights],
-                                                  [None if b is None else b.detach() for b in biases], rates, labels.contiguous(),
+        # (only the parameters' addresses cross the boundary: no detached views needed)
+        loss, logits, ws = _lib.head_loss_forward(xk, x_kind, (N, Cin, h, w), weights, biases, rates, labels.contiguous(),
                                                   ignore_index, inv_t, need_grad)
         ctx.meta = (rates, (N, Cin, h, w), C, tuple(labels.shape[-2:]), inv_t, x.dtype, need_grad, x_kind)
         ctx.save_for_backward(ws, xk if x_kind == 1 else None)

@@ -769,3 +769,105 @@ def test_one_call_train_slice_partial_needs_and_two_forwards_in_flight(lib):
     with torch.no_grad():
         l0, lg0 = head.forward_loss(xa, la)
     assert torch.equal(l0, l_a.detach())
+
+
+def test_one_call_train_slice_graph_replay_equals_direct_launches(lib):
+    """Steady-state loop (same addresses every iteration): the one-call entries replay a captured graph from the third iteration
+    on.  Same results as direct launches, bit for bit, INCLUDING after the weights / features / labels changed in place between
+    iterations (the graph re-packs and re-reads everything; only addresses are baked in)."""
+    import rnd_semantic_segmentation_b200 as b200
+    n, cin, C, h, w, H, W = 2, 256, 19, 33, 65, 128, 256
+    torch.manual_seed(21)
+    head = b200.ASPP_Classifier_V2(cin, RATES, RATES, C).cuda()
+    g = torch.Generator().manual_seed(22)
+    x = torch.relu(torch.randn(n, cin, h, w, generator=g)).cuda()
+    labels = torch.randint(0, C, (n, H, W), generator=g).cuda()
+    w0 = [p.detach().clone() for p in head.parameters()]
+
+    def run(graphs):
+        lib.set_step_graphs(graphs)
+        with torch.no_grad():
+            for p, v in zip(head.parameters(), w0):
+                p.copy_(v)
+        xi, li = x.clone(), labels.clone()
+        # result holders allocated up front: nothing but the step itself allocates inside the loop, as in a steady training loop
+        outs = [[torch.empty((), device="cuda"), torch.empty(n, C, h, w, device="cuda"), torch.empty_like(x)]
+                + [torch.empty_like(p) for p in head.parameters()] for _ in range(6)]
+        torch.cuda.synchronize()
+        for it in range(6):
+            for p in head.parameters():
+                p.grad = None
+            xg = xi.detach().requires_grad_(True)
+            loss, logits = head.forward_loss(xg, li)
+            loss.backward()
+            for dst, src in zip(outs[it], [loss.detach(), logits, xg.grad] + [p.grad for p in head.parameters()]):
+                dst.copy_(src)
+            del loss, logits, xg
+            with torch.no_grad():                                   # in-place updates: same addresses, new contents
+                for p in head.parameters():
+                    p.add_(p.grad, alpha=-0.05)
+                xi.mul_(0.9).add_(0.01)
+                li.copy_((li + 1) % C)
+        return outs, lib.step_graph_stats()
+
+    try:
+        direct, (r0, c0) = run(False)
+        replayed, (r1, c1) = run(True)
+    finally:
+        lib.set_step_graphs(True)
+    assert (r0, c0) == (0, 0)
+    assert c1 >= 2 and r1 >= 4, (r1, c1)           # forward + backward captured once each, then replayed
+    for a, b in zip(direct, replayed):
+        for u, v in zip(a, b):
+            assert torch.equal(u, v)
+    assert not torch.equal(direct[0][0], direct[5][0])
+
+
+def test_graph_replayed_backward_records_the_weights_ready_event(lib):
+    """Data-parallel path under graph replay: the bucket's ready_event is recorded from INSIDE the replayed graph (external event
+    node) once the weight gradients are complete.  A side stream that waits on it right after the launch must see this iteration's
+    weight and bias gradients in the bucket (zeroed before every step, inputs changed every step) -- the ordering the overlapped
+    all-reduce relies on."""
+    import rnd_semantic_segmentation_b200 as b200
+    from rnd_semantic_segmentation_b200 import distributed as D
+    n, cin, C, h, w, H, W = 4, 512, 19, 33, 65, 256, 512
+    torch.manual_seed(31)
+    head = b200.ASPP_Classifier_V2(cin, RATES, RATES, C).cuda()
+    g = torch.Generator().manual_seed(32)
+    x = torch.relu(torch.randn(n, cin, h, w, generator=g)).cuda()
+    labels = torch.randint(0, C, (n, H, W), generator=g).cuda()
+    # per-iteration references through the plain autograd path, direct launches
+    lib.set_step_graphs(False)
+    want = []
+    xi = x.clone()
+    for it in range(6):
+        for p in head.parameters():
+            p.grad = None
+        head.forward_loss(xi, labels)[0].backward()
+        want.append(torch.cat([p.grad.reshape(-1) for p in [m.weight for m in head.conv2d_list] + [m.bias for m in head.conv2d_list]]))
+        xi.mul_(0.9).add_(0.02)
+    lib.set_step_graphs(True)
+    try:
+        bucket = D.HeadGradBucket(head)
+        side = torch.cuda.Stream()
+        snaps = [torch.empty_like(bucket.flat) for _ in range(6)]
+        xi = x.clone()
+        torch.cuda.synchronize()
+        for it in range(6):
+            bucket.flat.zero_()
+            loss, _ = head.forward_loss(xi, labels, grad_bucket=bucket)
+            loss.backward()
+            side.wait_event(bucket.ready_event)
+            with torch.cuda.stream(side):
+                snaps[it].copy_(bucket.flat)
+            bucket.wait()
+            torch.cuda.current_stream().wait_stream(side)
+            xi.mul_(0.9).add_(0.02)
+            del loss
+        torch.cuda.synchronize()
+        replays, captures = lib.step_graph_stats()
+    finally:
+        lib.set_step_graphs(True)
+    assert captures >= 2 and replays >= 4, (replays, captures)
+    for it in range(6):
+        assert torch.equal(snaps[it], want[it]), it
