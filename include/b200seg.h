@@ -374,6 +374,11 @@ B200SEG_API void b200seg_gemm_set_narrow_tiles(int on);
  * 0 (default) = shared-memory transpose + 16-byte LSU stores.  Measured equal (180.8 vs 179.4 us): the 537 MB of writes
  * themselves, not the store instructions, are what the kernel waits for */
 B200SEG_API void b200seg_gemm_set_tma_store(int on);
+/* fp32 NCHW data gradient of the head (the dX of classifier.py:26-29's convolutions): 0 = channels along the GEMM's M dimension
+ * (shared-memory transpose epilogue), 1 (default) = pixels along M as CTA pairs, stored straight from the accumulator registers
+ * (lane = pixel: one store instruction = 32 consecutive pixels of a channel plane), 2 = the same with streaming stores, 3 = the same
+ * on multicast pairs instead of cta_group::2 pairs */
+B200SEG_API void b200seg_gemm_set_dgrad_mode(int mode);
 /* 1: the head's forward takes fp32 NCHW features through the GEMM with in-kernel conversion (below) where the shape is eligible;
  * 0 (default): pack + plain GEMM.  Measured equal at the eval shape (158.8 vs 158.3 us); kept as a tested option. */
 B200SEG_API void b200seg_gemm_set_fwd_convert(int on);

@@ -23,6 +23,10 @@ ey = synth.make_labels(1, eH, eW, eC, seed=6, device=dev)
 ehead = synth.scale_head_for_unit_logits(b200.ASPP_Classifier_V2(ecin, RATES, RATES, eC)).to(dev).eval()
 cm = torch.zeros(eC, eC, dtype=torch.int64, device=dev)
 b200.set_feature_pack_cache(0)          # the same x every iteration: keep the fp32 -> bf16 pack in the capture
+from rnd_semantic_segmentation_b200 import _lib
+_lib.set_step_graphs(False)             # direct launches: every kernel is its own profiled launch
+if os.environ.get("DGRAD_MODE"):
+    _lib.gemm_set_dgrad_mode(int(os.environ["DGRAD_MODE"]))
 for it in range(3):
     if it == 2:
         torch.cuda.synchronize()

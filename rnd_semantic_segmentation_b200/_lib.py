@@ -64,6 +64,7 @@ SIGNATURES = {
     "b200seg_aspp_forward_f32_supported": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int]),
     "b200seg_aspp_forward_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "b200seg_gemm_set_fwd_convert": (None, [c_int]),
+    "b200seg_gemm_set_dgrad_mode": (None, [c_int]),
     "b200seg_gemm_fwd_convert_selftest": (c_int, [c_int] * 5 + [ctypes.POINTER(ctypes.c_double)] * 3),
     "b200seg_aspp_backward_scratch_bytes": (c_i64, [c_int] * 7),
     "b200seg_aspp_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64, c_int,
@@ -1146,6 +1147,12 @@ def gemm_selftest(M, N, K, a_mn=False, b_mn=False, splits=1, col_hw=0, share=0):
     err, ref = ctypes.c_double(0), ctypes.c_double(0)
     _check(lib.b200seg_gemm_selftest(M, N, K, int(a_mn), int(b_mn), splits, col_hw, int(share), ctypes.byref(err), ctypes.byref(ref)))
     return err.value, ref.value
+
+
+def gemm_set_dgrad_mode(mode: int):
+    """fp32 NCHW data gradient of the head: 0 = channel-major GEMM with the shared-memory transpose epilogue, 1 (default) = pixel-major
+    CTA pairs storing straight from registers, 2 = + streaming stores, 3 = pixel-major on multicast pairs."""
+    load().b200seg_gemm_set_dgrad_mode(int(mode))
 
 
 def gemm_set_tma_store(on):

@@ -569,12 +569,21 @@ int aspp_backward_packed(const void* gOt_in, const void* Xp, const void* WpT, co
     if (cap == cudaStreamCaptureStatusActive) B200SEG_CUDA(cudaEventRecordWithFlags(weights_ready, stream, cudaEventRecordExternal));
     else B200SEG_CUDA(cudaEventRecord(weights_ready, stream));
   }
-  if (grad_x) {
+  if (grad_x && gemm::dgrad_mode() == 0) {
     // dX[ci, p] = WpT[ci, :] . G't[:, p]   -> fp32 NCHW: column p = (image, pixel), row = channel
     gemm::Operand a{(const __nv_bfloat16*)WpT, false, NJ};
     gemm::Operand b{Gp, true, Ppitch};
     int rc = gemm::launch(a, b, Cin, (int)P, NJ, 1, grad_x, hw, hw, (long long)Cin * hw, 0, stream, nullptr, 1, gemm::SHARE_B, false,
                           weights_ready ? gemm::overlap_sms() : 0);
+    if (rc) return rc;
+  } else if (grad_x) {
+    // dXt[p, ci] = G't[:, p] . WpT[ci, :] with the PIXELS along M, written as fp32 NCHW straight from the accumulator registers:
+    // a TMEM lane is a pixel, so one store instruction covers 32 consecutive pixels of a channel plane (no smem transpose)
+    gemm::Operand a{Gp, true, Ppitch};
+    gemm::Operand b{(const __nv_bfloat16*)WpT, false, NJ};
+    int rc = gemm::launch(a, b, (int)P, Cin, NJ, 1, grad_x, 0, 0, (long long)Cin * hw, 0, stream, nullptr, 1,
+                          gemm::dgrad_mode() == 3 ? gemm::SHARE_B : gemm::SHARE_PAIR, false, weights_ready ? gemm::overlap_sms() : 0,
+                          gemm::SHARE_B, hw);
     if (rc) return rc;
   }
   if (grad_x_nhwc_bf16) {

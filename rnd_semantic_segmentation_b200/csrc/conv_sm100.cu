@@ -381,8 +381,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
-        else mbar_arrive(&tempty_bar[acc]);
+        if (PAIR) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        else mbar_arrive_relaxed(&tempty_bar[acc]);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }

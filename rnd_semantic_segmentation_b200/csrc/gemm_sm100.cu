@@ -85,6 +85,9 @@ static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensor
 
 static int g_tma_store = 0;          // b200seg_gemm_set_tma_store(): 1 = fp32 NCHW epilogue through TMA bulk stores (measured equal to the LSU stores: 180.8 vs 179.4 us)
 void set_tma_store(int on) { g_tma_store = on; }
+static int g_dgrad_mode = 1;         // b200seg_gemm_set_dgrad_mode(): see gemm_sm100.cuh
+void set_dgrad_mode(int mode) { g_dgrad_mode = mode; }
+int dgrad_mode() { return g_dgrad_mode; }
 static int g_n_fastest = 0;
 void set_n_fastest(int on) { g_n_fastest = on; }
 static int g_narrow_tiles = 1;        // b200seg_gemm_set_narrow_tiles(): 0 = always 256-column tiles
@@ -115,8 +118,10 @@ static int launch_s(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensor
 
 int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, float* out, long long row_stride,
            int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used, int prof_tag,
-           int share, bool out_bf16, int sm_reserve, int pair_fallback) {
+           int share, bool out_bf16, int sm_reserve, int pair_fallback, int row_hw) {
   B200SEG_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem %dx%dx%d", M, N, K);
+  B200SEG_CHECK_ARG(row_hw <= 0 || (!out_bf16 && col_hw <= 0 && splits <= 1 && M % row_hw == 0),
+                    "gemm: the pixel-major NCHW epilogue needs fp32 output, no split-K and whole images along M");
   B200SEG_CHECK_ARG(!out_bf16 || (col_hw <= 0 && N % 8 == 0 && row_stride % 8 == 0 && split_stride % 8 == 0 &&
                                   (reinterpret_cast<uintptr_t>(out) & 15) == 0),
                     "gemm: bf16 output needs plain row-major D with N, row pitch multiples of 8 and a 16-byte aligned base");
@@ -142,7 +147,13 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
   p.img_stride = img_stride;
   p.split_stride = split_stride;
   p.out_bf16 = out_bf16 ? 1 : 0;
-  p.n_fastest = g_n_fastest && col_hw > 0 ? 1 : 0;          // the fp32 NCHW data gradient (store-bound)          // the fp32 NCHW data gradient (store-bound)
+  p.row_hw_px = row_hw > 0 ? row_hw : 0;
+  p.row_hw = row_hw > 0 ? (g_dgrad_mode == 2 ? 2 : 1) : 0;
+  // tile order: the units running together should share the LARGER operand, so that it streams from HBM once and the small
+  // one lives in L2.  Channel-major problems (M = channels / packed weight rows <= N = pixels) walk along M; pixel-major ones
+  // (M = pixels: the seam-format and the register-store data gradients) walk along N -- M-fastest made them re-read the
+  // 86 MB pixel operand once per N-tile (653 MB of DRAM reads per launch at the bench shape, ncu profiles/r2_dgrad_*).
+  p.n_fastest = ((g_n_fastest && col_hw > 0) || M > N) ? 1 : 0;
   if (splits_used) *splits_used = p.splits;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && row_stride % 4 == 0 && split_stride % 4 == 0 &&
               (col_hw <= 0 || (col_hw % 4 == 0 && img_stride % 4 == 0)))

@@ -49,6 +49,10 @@ struct Params {
   int out_bf16;             // D is written as bf16 (plain row-major [M][row_stride], 16-byte aligned rows) instead of fp32
   int n_fastest;            // tile order: consecutive work units walk along N (rows of D are written as long sequential runs)
   int tma_store;            // fp32 image-mapped D (NCHW) written by TMA bulk stores from swizzled shared-memory boxes
+  int row_hw_px;            // pixels per image for the row_hw mode
+  int row_hw;               // > 0: ROWS of D are pixels of images with row_hw pixels each and D is fp32 NCHW: element (m, n)
+                            // lives at out[(m / row_hw) * img_stride + n * row_hw + m % row_hw]; stored straight from registers
+                            // (lane = pixel: a warp-level store is 32 consecutive pixels of one channel plane); 2: streaming stores
 };
 
 // ------------------------------------------------------------------------------------------
@@ -192,6 +196,17 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// "accumulator drained" arrives of the epilogue warps.  RELAXED on purpose: what they order -- the tcgen05.ld reads of the
+// accumulator before the next tcgen05.mma into it -- is already guaranteed by tcgen05.wait::ld + tcgen05.fence::before_thread_sync.
+// A release arrive additionally waits (MEMBAR + ERRBAR in SASS) until every global store the warp has in flight is performed,
+// i.e. it puts the drain of the epilogue's stores on the MMA's critical path once per tile (ncu: 11 % of the dgrad GEMM's warp
+// samples sat on exactly that; profiles/README.md round-2 table).
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // 2-SM TMA load: the completion barrier is a shared::cluster address and may live in the peer (leader) CTA
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {
@@ -501,6 +516,40 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             __syncwarp();
           }
         }
+      } else if (p.row_hw > 0) {
+        // fp32 NCHW D with the pixels along M: a TMEM lane is a pixel and a register column is a channel, so the 32 lanes of a
+        // store instruction write 32 consecutive pixels of ONE channel plane = 128 contiguous bytes, straight from the registers
+        // tcgen05.ld filled.  No shared-memory transpose (its STS + LDS traffic through L1 was what held the channel-major form
+        // of this epilogue back: L1/TEX 76 % busy) and no dependence on the plane pitch being a multiple of 4 pixels.
+        if (rows > 0 && col_base < p.N) {
+          const int hw = p.row_hw_px;
+          const bool ok = lane < rows;
+          const int m = ok ? row_base + lane : row_base;
+          const int img = m / hw;
+          float* dst = out + (long long)img * p.img_stride + (m - img * hw) + (long long)col_base * hw;
+          constexpr int NCH = BLOCK_N / 2 / 16;
+          uint32_t rbuf[2][16];
+          tmem_ld16(taddr, rbuf[0]);
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            tmem_ld_wait();
+            const uint32_t* r = rbuf[c & 1];
+            if (c + 1 < NCH) tmem_ld16(taddr + (uint32_t)((c + 1) * 16), rbuf[(c + 1) & 1]);
+            const int ncols = p.N - (col_base + c * 16);
+            if (ok) {
+              float* d = dst + (long long)(c * 16) * hw;
+              if (p.row_hw == 2) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                  if (k < ncols) __stcs(d + (long long)k * hw, __uint_as_float(r[k]));
+              } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                  if (k < ncols) d[(long long)k * hw] = __uint_as_float(r[k]);
+              }
+            }
+          }
+        }
       } else if (p.tma_store) {
         // fp32 NCHW D through the TMA unit: each 32 x 16 chunk goes TMEM -> registers -> a dense, 64-byte-swizzled
         // shared-memory box (conflict-free 16-byte stores) -> one cp.async.bulk.tensor store that clips rows >= M and
@@ -594,8 +643,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
-        else mbar_arrive(&tempty_bar[acc]);
+        if (PAIR) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+        else mbar_arrive_relaxed(&tempty_bar[acc]);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -811,7 +860,7 @@ gemm_fwd_convert_kernel(const __grid_constant__ CUtensorMap tmap_a, const FwdXPa
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(te0 + (uint32_t)acc * 8u);
+      if (lane == 0) mbar_arrive_cluster_relaxed(te0 + (uint32_t)acc * 8u);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   } else if (warp >= 4 + FWDX_EPI_WARPS) {
@@ -926,7 +975,11 @@ int launch_fwd_convert(const __nv_bfloat16* a, long long a_pitch, const float* x
                        long long row_stride, __nv_bfloat16* xn, cudaStream_t stream, int prof_tag);
 int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, float* out, long long row_stride,
            int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used, int prof_tag = -1,
-           int share = SHARE_NONE, bool out_bf16 = false, int sm_reserve = 0, int pair_fallback = SHARE_B);
+           int share = SHARE_NONE, bool out_bf16 = false, int sm_reserve = 0, int pair_fallback = SHARE_B, int row_hw = 0);
+// fp32 NCHW data gradient of the head: 0 = channels along M (shared-memory transpose epilogue), 1 = pixels along M (stores
+// straight from registers), 2 = the same with streaming (evict-first) stores
+void set_dgrad_mode(int mode);
+int dgrad_mode();
 
 }  // namespace gemm
 }  // namespace b200seg
