@@ -28,7 +28,7 @@ def step():
 
 ref = None
 for rep in range(2):
-    for mode in (0, 1, 2, 3):
+    for mode in [int(m) for m in os.environ.get("MODES", "0,1,2,3").split(",")]:
         _lib.gemm_set_dgrad_mode(mode)
         for _ in range(5):
             g = step()

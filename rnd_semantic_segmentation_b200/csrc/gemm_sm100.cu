@@ -1,5 +1,6 @@
 // Host side of the tcgen05 GEMM core: TMA tensor-map encoding, launch, and an on-device self-test
 // against a naive CUDA-core kernel (used by tests/ to pin descriptors on real hardware).
+#include <stdlib.h>
 #include "gemm_sm100.cuh"
 #include <limits.h>
 
@@ -55,15 +56,15 @@ int overlap_sms() { return g_overlap_sms; }
 static int g_share_enabled = 1;
 void set_sharing(int on) { g_share_enabled = on; }
 
-template <bool A_MN, bool B_MN, int SHARE, int BN = 256>
+template <bool A_MN, bool B_MN, int SHARE, int BN = 256, bool RS = false>
 static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const Params& p, int grid, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    B200SEG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, SHARE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    B200SEG_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<A_MN, B_MN, SHARE, BN, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
   if (SHARE == SHARE_NONE) {
-    gemm_bf16_kernel<A_MN, B_MN, SHARE, BN><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, to, p);
+    gemm_bf16_kernel<A_MN, B_MN, SHARE, BN, RS><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(ta, tb, to, p);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -77,7 +78,7 @@ static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensor
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    B200SEG_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, SHARE, BN>, ta, tb, to, p));
+    B200SEG_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<A_MN, B_MN, SHARE, BN, RS>, ta, tb, to, p));
   }
   B200SEG_LAUNCH_CHECK();
   return B200SEG_OK;
@@ -149,6 +150,15 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
   p.out_bf16 = out_bf16 ? 1 : 0;
   p.row_hw_px = row_hw > 0 ? row_hw : 0;
   p.row_hw = row_hw > 0 ? (g_dgrad_mode == 2 ? 2 : 1) : 0;
+  // pace the register-store epilogue: ~1/20 of a tile's MMA time after each of its 8 chunks (K = 640: 192 ns), so that the
+  // 128 KB a tile stores leave the SM spread over the tile time instead of as one burst in front of the operand requests
+  // (measured at the bench shape: 161 -> 150 us; B200SEG_EPI_SLEEP=<ns> overrides, 0 = off)
+  {
+    static int env_ns = -2;
+    if (env_ns == -2) { const char* e = getenv("B200SEG_EPI_SLEEP"); env_ns = e ? atoi(e) : -1; }
+    const int ns = K * 3 / 10;
+    p.epi_sleep_ns = row_hw > 0 ? (env_ns >= 0 ? env_ns : (ns > 200 ? 200 : ns)) : 0;
+  }
   // tile order: the units running together should share the LARGER operand, so that it streams from HBM once and the small
   // one lives in L2.  Channel-major problems (M = channels / packed weight rows <= N = pixels) walk along M; pixel-major ones
   // (M = pixels: the seam-format and the register-store data gradients) walk along N -- M-fastest made them re-read the
@@ -225,7 +235,8 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
     grid = cs * clusters;
   }
   profile_begin(prof_tag, stream);
-  if (!a.mn_major && !b.mn_major && bn != BLOCK_N) rc = launch_kk(ta, tb, to, p, grid, share, bn, stream);
+  if (p.row_hw == 1 && share == SHARE_PAIR && a.mn_major && !b.mn_major) rc = launch_t<true, false, SHARE_PAIR, 256, true>(ta, tb, to, p, grid, stream);
+  else if (!a.mn_major && !b.mn_major && bn != BLOCK_N) rc = launch_kk(ta, tb, to, p, grid, share, bn, stream);
   else if (!a.mn_major && !b.mn_major) rc = launch_s<false, false>(ta, tb, to, p, grid, share, stream);
   else if (a.mn_major && b.mn_major) rc = launch_s<true, true>(ta, tb, to, p, grid, share, stream);
   else if (a.mn_major && !b.mn_major) rc = launch_s<true, false>(ta, tb, to, p, grid, share, stream);

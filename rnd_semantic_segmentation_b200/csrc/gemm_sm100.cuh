@@ -50,6 +50,7 @@ struct Params {
   int n_fastest;            // tile order: consecutive work units walk along N (rows of D are written as long sequential runs)
   int tma_store;            // fp32 image-mapped D (NCHW) written by TMA bulk stores from swizzled shared-memory boxes
   int row_hw_px;            // pixels per image for the row_hw mode
+  int epi_sleep_ns;         // row_hw mode: pause after each 16-column chunk's stores (paces the epilogue's store bursts)
   int row_hw;               // > 0: ROWS of D are pixels of images with row_hw pixels each and D is fp32 NCHW: element (m, n)
                             // lives at out[(m / row_hw) * img_stride + n * row_hw + m % row_hw]; stored straight from registers
                             // (lane = pixel: a warp-level store is 32 consecutive pixels of one channel plane); 2: streaming stores
@@ -290,7 +291,10 @@ struct TileSched {
 // tile count a near-multiple of the SM count: 5 M-tiles x 128 N-tiles of 256 on 148 SMs are 4.3 waves = 5 rounds; the same
 // problem in 224-column tiles is 5 x 147 = 4.97 waves = 5 rounds of 12.5 % less work each.  K-major operands, fp32 output,
 // SHARE_NONE / SHARE_A only.
-template <bool A_MN, bool B_MN, int SHARE, int BN = 256>
+// RS ("register stores"): the fp32 NCHW pixel-major epilogue only (Params::row_hw), which needs no shared-memory staging -- the
+// 32 KB go to a seventh ring stage instead (PAIR mode): the operand loads of this store-heavy problem see their latency inflated
+// by the epilogue's store bursts, and bytes in flight are what hides it.
+template <bool A_MN, bool B_MN, int SHARE, int BN = 256, bool RS = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const Params p) {
@@ -303,12 +307,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   static_assert(BN % 32 == 0 && BN <= 256, "epilogue halves are BN / 2 columns in chunks of 16");
   constexpr int BLOCK_N = BN;                                       // shadows gemm::BLOCK_N below
   constexpr int B_BYTES = BN * BLOCK_K * 2;
-  constexpr int STAGES = PAIR ? PAIR_STAGES : gemm::STAGES;         // same total bytes either way
+  static_assert(!RS || (PAIR && BN == 256), "register-store variant: cta_group::2 pairs only");
+  constexpr int STAGES = PAIR ? (RS ? PAIR_STAGES + 1 : PAIR_STAGES) : gemm::STAGES;         // same total bytes either way
   constexpr int STAGE_BYTES = PAIR ? PAIR_STAGE_BYTES : gemm::STAGE_BYTES;     // ring stride (a narrow B tile leaves its tail unused)
   constexpr int STAGE_TX = PAIR ? PAIR_STAGE_BYTES : A_BYTES + B_BYTES;        // bytes that land in a stage per k-block
   static_assert(PAIR_STAGES * PAIR_STAGE_BYTES == gemm::STAGES * gemm::STAGE_BYTES, "epilogue staging / barriers sit behind the ring");
-  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_WARPS * EPI_STAGE_FLOATS * 4);
+  static_assert(!RS || PAIR_STAGE_BYTES == EPI_WARPS * EPI_STAGE_FLOATS * 4, "the extra stage takes exactly the staging area");
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);                   // (RS: not used)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + (RS ? 0 : EPI_WARPS * EPI_STAGE_FLOATS * 4));
   uint64_t* full_bar = bars;                  // [STAGES]
   uint64_t* empty_bar = bars + STAGES;        // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
@@ -480,7 +486,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * gemm::BLOCK_N + half * (BLOCK_N / 2));
       const int rows = min(32, p.M - row_base);
-      if (p.out_bf16) {
+      if (!RS && p.out_bf16) {
         // bf16 row-major D (the NHWC feature gradient): 32 columns per pass, converted before the smem transpose, every
         // store instruction writes 8 rows x 64 contiguous bytes
         if (rows > 0 && col_base < p.N) {
@@ -516,7 +522,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             __syncwarp();
           }
         }
-      } else if (p.row_hw > 0) {
+      } else if (RS || p.row_hw > 0) {
         // fp32 NCHW D with the pixels along M: a TMEM lane is a pixel and a register column is a channel, so the 32 lanes of a
         // store instruction write 32 consecutive pixels of ONE channel plane = 128 contiguous bytes, straight from the registers
         // tcgen05.ld filled.  No shared-memory transpose (its STS + LDS traffic through L1 was what held the channel-major form
@@ -548,6 +554,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                   if (k < ncols) d[(long long)k * hw] = __uint_as_float(r[k]);
               }
             }
+            if (p.epi_sleep_ns > 0) __nanosleep((unsigned)p.epi_sleep_ns);
           }
         }
       } else if (p.tma_store) {
@@ -976,8 +983,9 @@ int launch_fwd_convert(const __nv_bfloat16* a, long long a_pitch, const float* x
 int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, float* out, long long row_stride,
            int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used, int prof_tag = -1,
            int share = SHARE_NONE, bool out_bf16 = false, int sm_reserve = 0, int pair_fallback = SHARE_B, int row_hw = 0);
-// fp32 NCHW data gradient of the head: 0 = channels along M (shared-memory transpose epilogue), 1 = pixels along M (stores
-// straight from registers), 2 = the same with streaming (evict-first) stores
+// fp32 NCHW data gradient of the head: 0 = channels along M (shared-memory transpose epilogue), 1 = pixels along M as cta_group::2
+// pairs, stores straight from registers, seven ring stages; 2 = the same with streaming (evict-first) stores and six stages;
+// 3 = pixels along M on multicast pairs
 void set_dgrad_mode(int mode);
 int dgrad_mode();
 
