@@ -379,6 +379,9 @@ B200SEG_API void b200seg_gemm_set_tma_store(int on);
  * (lane = pixel: one store instruction = 32 consecutive pixels of a channel plane), 2 = the same with streaming stores, 3 = the same
  * on multicast pairs instead of cta_group::2 pairs */
 B200SEG_API void b200seg_gemm_set_dgrad_mode(int mode);
+/* forward GEMM of the head (classifier.py:26-29): 0 = channel-major (M = packed weight rows; 5 M-tiles on 3 CTA pairs), 1 (default)
+ * = pixel-major (M = pixels, the 2.5 N-tiles' ragged last one at half MMA width, register-store epilogue) */
+B200SEG_API void b200seg_gemm_set_fwd_mode(int mode);
 /* 1: the head's forward takes fp32 NCHW features through the GEMM with in-kernel conversion (below) where the shape is eligible;
  * 0 (default): pack + plain GEMM.  Measured equal at the eval shape (158.8 vs 158.3 us); kept as a tested option. */
 B200SEG_API void b200seg_gemm_set_fwd_convert(int on);

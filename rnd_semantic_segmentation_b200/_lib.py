@@ -65,6 +65,7 @@ SIGNATURES = {
     "b200seg_aspp_forward_f32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "b200seg_gemm_set_fwd_convert": (None, [c_int]),
     "b200seg_gemm_set_dgrad_mode": (None, [c_int]),
+    "b200seg_gemm_set_fwd_mode": (None, [c_int]),
     "b200seg_gemm_fwd_convert_selftest": (c_int, [c_int] * 5 + [ctypes.POINTER(ctypes.c_double)] * 3),
     "b200seg_aspp_backward_scratch_bytes": (c_i64, [c_int] * 7),
     "b200seg_aspp_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_i64, c_int,
@@ -1153,6 +1154,11 @@ def gemm_set_dgrad_mode(mode: int):
     """fp32 NCHW data gradient of the head: 0 = channel-major GEMM with the shared-memory transpose epilogue, 1 (default) = pixel-major
     CTA pairs storing straight from registers, 2 = + streaming stores, 3 = pixel-major on multicast pairs."""
     load().b200seg_gemm_set_dgrad_mode(int(mode))
+
+
+def gemm_set_fwd_mode(mode: int):
+    """Head forward GEMM: 0 = channel-major, 1 (default) = pixel-major with the ragged last N-tile at half MMA width."""
+    load().b200seg_gemm_set_fwd_mode(int(mode))
 
 
 def gemm_set_tma_store(on):

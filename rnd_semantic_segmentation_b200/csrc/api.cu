@@ -114,6 +114,7 @@ void set_narrow_tiles(int);
 void set_n_fastest(int);
 void set_tma_store(int);
 void set_dgrad_mode(int);
+void set_fwd_mode(int);
 void set_fwd_convert(int);
 int selftest_fwd_convert(int, int, int, int, int, double*, double*, double*);
 }
@@ -607,6 +608,7 @@ void b200seg_gemm_set_narrow_tiles(int on) { step_graphs_drop(); gemm::set_narro
 void b200seg_gemm_set_dgrad_n_fastest(int on) { step_graphs_drop(); gemm::set_n_fastest(on); }
 void b200seg_gemm_set_tma_store(int on) { step_graphs_drop(); gemm::set_tma_store(on); }
 void b200seg_gemm_set_dgrad_mode(int mode) { step_graphs_drop(); gemm::set_dgrad_mode(mode); }
+void b200seg_gemm_set_fwd_mode(int mode) { step_graphs_drop(); gemm::set_fwd_mode(mode); }
 void b200seg_gemm_set_fwd_convert(int on) { step_graphs_drop(); gemm::set_fwd_convert(on); }
 int b200seg_gemm_fwd_convert_selftest(int M, int n_img, int hw, int K, int write_xn, double* max_err, double* max_ref, double* xn_err) {
   REQUIRE_DEVICE();

@@ -430,7 +430,17 @@ int aspp_forward(const void* Xp, const void* Wp, const float* bias_sum, const in
   gemm::Operand b{(const __nv_bfloat16*)Xp, false, Cin};
   // CTA pairs on one tcgen05.mma.cta_group::2 along M (NJ = 640 = 5 M-tiles -> 3 pairs, the last one half empty): each SM
   // pulls 32 KB per k-block instead of 48 KB -- 143 vs 154 us at the bench workload although a sixth of the pair slots idles
-  int rc = gemm::launch(a, b, NJ, (int)P, Cin, 1, Yt, ypitch, 0, 0, 0, stream, nullptr, 0, gemm::SHARE_PAIR, false, 0, gemm::SHARE_A);
+  int rc;
+  if (gemm::fwd_mode() == 1 && P >= 2 * 128 && NJ > 256) {        // (one N-tile only, e.g. 2 classes: channel-major measured faster, 33 vs 37 us)
+    // pixel-major: Yt[j, p] computed as D[p, j] with the PIXELS along M.  NJ = 640 is 2.5 N-tiles of 256: the last one runs at
+    // MMA width 128 (half the cycles) instead of leaving half a CTA pair idle as the channel-major form does with its 5 M-tiles
+    // on 3 pairs; the accumulator goes to Yt straight from registers (a lane is a pixel: 32 consecutive pixels of one row j per
+    // store instruction)
+    rc = gemm::launch(b, a, (int)P, NJ, Cin, 1, Yt, 0, 0, 0, 0, stream, nullptr, 0, gemm::SHARE_PAIR, false, 0, gemm::SHARE_B,
+                      (int)ypitch);
+  } else {
+    rc = gemm::launch(a, b, NJ, (int)P, Cin, 1, Yt, ypitch, 0, 0, 0, stream, nullptr, 0, gemm::SHARE_PAIR, false, 0, gemm::SHARE_A);
+  }
   if (rc) return rc;
   TapTable tt;
   make_taps(tt, rates, R);

@@ -89,6 +89,9 @@ void set_tma_store(int on) { g_tma_store = on; }
 static int g_dgrad_mode = 1;         // b200seg_gemm_set_dgrad_mode(): see gemm_sm100.cuh
 void set_dgrad_mode(int mode) { g_dgrad_mode = mode; }
 int dgrad_mode() { return g_dgrad_mode; }
+static int g_fwd_mode = 1;           // b200seg_gemm_set_fwd_mode(): see gemm_sm100.cuh
+void set_fwd_mode(int mode) { g_fwd_mode = mode; }
+int fwd_mode() { return g_fwd_mode; }
 static int g_n_fastest = 0;
 void set_n_fastest(int on) { g_n_fastest = on; }
 static int g_narrow_tiles = 1;        // b200seg_gemm_set_narrow_tiles(): 0 = always 256-column tiles
@@ -121,8 +124,8 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
            int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used, int prof_tag,
            int share, bool out_bf16, int sm_reserve, int pair_fallback, int row_hw) {
   B200SEG_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem %dx%dx%d", M, N, K);
-  B200SEG_CHECK_ARG(row_hw <= 0 || (!out_bf16 && col_hw <= 0 && splits <= 1 && M % row_hw == 0),
-                    "gemm: the pixel-major NCHW epilogue needs fp32 output, no split-K and whole images along M");
+  B200SEG_CHECK_ARG(row_hw <= 0 || (!out_bf16 && col_hw <= 0 && splits <= 1 && (M % row_hw == 0 || M <= row_hw)),
+                    "gemm: the pixel-major epilogue needs fp32 output, no split-K and whole images (or one plane) along M");
   B200SEG_CHECK_ARG(!out_bf16 || (col_hw <= 0 && N % 8 == 0 && row_stride % 8 == 0 && split_stride % 8 == 0 &&
                                   (reinterpret_cast<uintptr_t>(out) & 15) == 0),
                     "gemm: bf16 output needs plain row-major D with N, row pitch multiples of 8 and a 16-byte aligned base");
@@ -157,7 +160,8 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
     static int env_ns = -2;
     if (env_ns == -2) { const char* e = getenv("B200SEG_EPI_SLEEP"); env_ns = e ? atoi(e) : -1; }
     const int ns = K * 3 / 10;
-    p.epi_sleep_ns = row_hw > 0 ? (env_ns >= 0 ? env_ns : (ns > 200 ? 200 : ns)) : 0;
+    // (long-K problems store little per unit of MMA time: no pacing)
+    p.epi_sleep_ns = row_hw > 0 ? (env_ns >= 0 ? env_ns : (K > 1024 ? 0 : (ns > 200 ? 200 : ns))) : 0;
   }
   // tile order: the units running together should share the LARGER operand, so that it streams from HBM once and the small
   // one lives in L2.  Channel-major problems (M = channels / packed weight rows <= N = pixels) walk along M; pixel-major ones
@@ -234,8 +238,14 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
     const int clusters = units < sms / cs ? units : sms / cs;
     grid = cs * clusters;
   }
+  const bool rs = p.row_hw == 1 && share == SHARE_PAIR && !b.mn_major;        // register-store variant (7 ring stages)
+  if (rs) {
+    rc = make_tmap(&to, b.ptr, K, N, b.pitch, BLOCK_K, BLOCK_N / 4);          // 64-row B boxes for a ragged last N-tile
+    if (rc) return rc;
+  }
   profile_begin(prof_tag, stream);
-  if (p.row_hw == 1 && share == SHARE_PAIR && a.mn_major && !b.mn_major) rc = launch_t<true, false, SHARE_PAIR, 256, true>(ta, tb, to, p, grid, stream);
+  if (rs && a.mn_major) rc = launch_t<true, false, SHARE_PAIR, 256, true>(ta, tb, to, p, grid, stream);
+  else if (rs) rc = launch_t<false, false, SHARE_PAIR, 256, true>(ta, tb, to, p, grid, stream);
   else if (!a.mn_major && !b.mn_major && bn != BLOCK_N) rc = launch_kk(ta, tb, to, p, grid, share, bn, stream);
   else if (!a.mn_major && !b.mn_major) rc = launch_s<false, false>(ta, tb, to, p, grid, share, stream);
   else if (a.mn_major && b.mn_major) rc = launch_s<true, true>(ta, tb, to, p, grid, share, stream);

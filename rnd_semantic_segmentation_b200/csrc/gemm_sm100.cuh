@@ -370,15 +370,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const int k0 = kb * BLOCK_K;
           if (PAIR) {
             // own A tile + own half of B; both CTAs' bytes complete on the leader's full barrier
-            if (sched.rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_TX);
+            // RS variant, last N-tile with <= 128 columns left: the MMA runs with N = 128 (half the cycles), of which each CTA
+            // supplies 64 rows of B, fetched through a 64-row box (the tensor map in the otherwise unused tmap_out slot)
+            const bool narrow = RS && !B_MN && (p.N - n0) <= BLOCK_N / 2;
+            if (sched.rank == 0) mbar_arrive_expect_tx(&full_bar[stage], narrow ? 2 * (A_BYTES + B_BYTES / 4) : 2 * STAGE_TX);
             const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
             if (!A_MN) tma_load_2d_2sm(sa, &tmap_a, fb, k0, m0);
             else {
 #pragma unroll
               for (int b = 0; b < BLOCK_M / 64; ++b) tma_load_2d_2sm(sa + b * MN_BOX_BYTES, &tmap_a, fb, m0 + b * 64, k0);
             }
-            const int nh = n0 + sched.rank * (BLOCK_N / 2);
-            if (!B_MN) tma_load_2d_2sm(sb, &tmap_b, fb, k0, nh);
+            const int nh = n0 + sched.rank * (narrow ? BLOCK_N / 4 : BLOCK_N / 2);
+            if (narrow) tma_load_2d_2sm(sb, &tmap_out, fb, k0, nh);
+            else if (!B_MN) tma_load_2d_2sm(sb, &tmap_b, fb, k0, nh);
             else {
 #pragma unroll
               for (int b = 0; b < BLOCK_N / 2 / 64; ++b) tma_load_2d_2sm(sb + b * MN_BOX_BYTES, &tmap_b, fb, nh + b * 64, k0);
@@ -428,6 +432,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ================= MMA issuer (one thread) =================
     if (lane == 0 && (!PAIR || sched.rank == 0)) {
       constexpr uint32_t idesc = make_idesc(A_MN, B_MN, PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
+      constexpr uint32_t idesc_narrow = make_idesc(A_MN, B_MN, PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N / 2);   // RS: ragged last N-tile
       // K-major: 8-row groups 1024 B apart (SBO), LBO unused (1); +32 B per UMMA_K step.
       // MN-major: 64-element chunks one TMA box (8 KB) apart (LBO), 8-k-row groups 1024 B apart (SBO);
       //           +16 k-rows = 2048 B per UMMA_K step.
@@ -454,7 +459,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc(sa + k * a_step, a_lbo, a_sbo);
             const uint64_t bdesc = make_smem_desc(sb + k * b_step, b_lbo, b_sbo);
-            if (PAIR) umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (PAIR) umma_bf16_2sm(tmem_d, adesc, bdesc, (RS && !B_MN && (p.N - nt * BLOCK_N) <= BLOCK_N / 2) ? idesc_narrow : idesc,
+                                    (kb > kb0 || k > 0) ? 1u : 0u);
             else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           // frees the slot in every CTA that multicasts into this one (itself included) when these MMAs retire
@@ -988,6 +994,10 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
 // 3 = pixels along M on multicast pairs
 void set_dgrad_mode(int mode);
 int dgrad_mode();
+// forward GEMM of the head: 0 = channel-major (M = packed weight rows, shared-memory transpose epilogue), 1 = pixel-major
+// (M = pixels, register stores, ragged last N-tile at half MMA width)
+void set_fwd_mode(int mode);
+int fwd_mode();
 
 }  // namespace gemm
 }  // namespace b200seg
