@@ -370,14 +370,11 @@ B200SEG_API int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b
 /* head forward GEMM: 1 (default) = the tile width (256 / 224 / 192 accumulator columns) is chosen per problem so that the tile
  * count is a near-multiple of the SM count (wave quantisation), 0 = always 256 */
 B200SEG_API void b200seg_gemm_set_narrow_tiles(int on);
-/* fp32 NCHW data-gradient epilogue: 1 = TMA bulk stores from swizzled shared-memory boxes (needs h*w % 16 == 0),
- * 0 (default) = shared-memory transpose + 16-byte LSU stores.  Measured equal (180.8 vs 179.4 us): the 537 MB of writes
- * themselves, not the store instructions, are what the kernel waits for */
-B200SEG_API void b200seg_gemm_set_tma_store(int on);
 /* fp32 NCHW data gradient of the head (the dX of classifier.py:26-29's convolutions): 0 = channels along the GEMM's M dimension
  * (shared-memory transpose epilogue), 1 (default) = pixels along M as CTA pairs, stored straight from the accumulator registers
- * (lane = pixel: one store instruction = 32 consecutive pixels of a channel plane), 2 = the same with streaming stores, 3 = the same
- * on multicast pairs instead of cta_group::2 pairs */
+ * (lane = pixel: one store instruction = 32 consecutive pixels of a channel plane; seven ring stages, paced stores), 2 = the same
+ * with streaming (evict-first) stores (measured no better).  The tile order of every GEMM follows the operand sizes (the larger
+ * operand streams from HBM once). */
 B200SEG_API void b200seg_gemm_set_dgrad_mode(int mode);
 /* forward GEMM of the head (classifier.py:26-29): 0 = channel-major (M = packed weight rows; 5 M-tiles on 3 CTA pairs), 1 (default)
  * = pixel-major (M = pixels, the 2.5 N-tiles' ragged last one at half MMA width, register-store epilogue) */
@@ -388,9 +385,6 @@ B200SEG_API void b200seg_gemm_set_fwd_convert(int on);
 /* on-device self-test of that kernel against a CUDA-core reference on bf16-rounded x; xn_err: max |bf16 copy - bf16(x)| */
 B200SEG_API int b200seg_gemm_fwd_convert_selftest(int M, int n_img, int hw, int K, int write_xn, double* max_err, double* max_ref,
                                       double* xn_err);
-/* fp32 NCHW data-gradient GEMM tile order: 1 = consecutive tiles walk along the pixel axis (each channel row of dX is written as
- * long sequential runs), 0 = along the channel axis (tiles sharing the gradient operand adjacent in time) */
-B200SEG_API void b200seg_gemm_set_dgrad_n_fastest(int on);
 /* K6 conv kernel: 1 (default) = CTA pairs driving one tcgen05.mma.cta_group::2 (M = 256) wherever a layer has two M-tiles,
  * 0 = one CTA per tile (A/B experiments) */
 B200SEG_API void b200seg_conv_set_pair(int on);

@@ -113,8 +113,6 @@ SIGNATURES = {
     "b200seg_tta_set_row_walk": (None, [c_int]),
     "b200seg_sgd_step": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_f32, c_f32, c_f32, c_f32, c_int, c_int, c_f32, c_vp]),
     "b200seg_adam_step": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_f32, c_f32, c_f32, c_f32, c_i64, c_f32, c_vp]),
-    "b200seg_gemm_set_dgrad_n_fastest": (None, [c_int]),
-    "b200seg_gemm_set_tma_store": (None, [c_int]),
 }
 
 
@@ -145,10 +143,6 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
     _lib = lib
     if os.environ.get("B200SEG_GEMM_SHARING"):        # A/B experiments (profiles/): operand-sharing mode of the head GEMMs
         lib.b200seg_gemm_set_sharing(int(os.environ["B200SEG_GEMM_SHARING"]))
-    if os.environ.get("B200SEG_DGRAD_N_FASTEST"):
-        lib.b200seg_gemm_set_dgrad_n_fastest(int(os.environ["B200SEG_DGRAD_N_FASTEST"]))
-    if os.environ.get("B200SEG_TMA_STORE"):
-        lib.b200seg_gemm_set_tma_store(int(os.environ["B200SEG_TMA_STORE"]))
     if os.environ.get("B200SEG_GEMM_NARROW"):
         lib.b200seg_gemm_set_narrow_tiles(int(os.environ["B200SEG_GEMM_NARROW"]))
     if os.environ.get("B200SEG_FWD_CONVERT"):
@@ -1152,18 +1146,13 @@ def gemm_selftest(M, N, K, a_mn=False, b_mn=False, splits=1, col_hw=0, share=0):
 
 def gemm_set_dgrad_mode(mode: int):
     """fp32 NCHW data gradient of the head: 0 = channel-major GEMM with the shared-memory transpose epilogue, 1 (default) = pixel-major
-    CTA pairs storing straight from registers, 2 = + streaming stores, 3 = pixel-major on multicast pairs."""
+    CTA pairs storing straight from registers (seven ring stages, paced stores)."""
     load().b200seg_gemm_set_dgrad_mode(int(mode))
 
 
 def gemm_set_fwd_mode(mode: int):
     """Head forward GEMM: 0 = channel-major, 1 (default) = pixel-major with the ragged last N-tile at half MMA width."""
     load().b200seg_gemm_set_fwd_mode(int(mode))
-
-
-def gemm_set_tma_store(on):
-    """fp32 NCHW data-gradient epilogue through TMA bulk stores instead of LSU stores (default off: measured equal)."""
-    load().b200seg_gemm_set_tma_store(1 if on else 0)
 
 
 def gemm_set_narrow_tiles(on):

@@ -111,8 +111,6 @@ int selftest(int, int, int, int, int, int, int, int, double*, double*);
 void set_sharing(int);
 void set_overlap_sms(int);
 void set_narrow_tiles(int);
-void set_n_fastest(int);
-void set_tma_store(int);
 void set_dgrad_mode(int);
 void set_fwd_mode(int);
 void set_fwd_convert(int);
@@ -605,8 +603,6 @@ int b200seg_profile_read(int tag, double* total_ms, int* count) {
 void b200seg_conv_set_pair(int on) { step_graphs_drop(); gemm::conv::set_pair(on); }
 void b200seg_gemm_set_sharing(int on) { step_graphs_drop(); gemm::set_sharing(on); }
 void b200seg_gemm_set_narrow_tiles(int on) { step_graphs_drop(); gemm::set_narrow_tiles(on); }
-void b200seg_gemm_set_dgrad_n_fastest(int on) { step_graphs_drop(); gemm::set_n_fastest(on); }
-void b200seg_gemm_set_tma_store(int on) { step_graphs_drop(); gemm::set_tma_store(on); }
 void b200seg_gemm_set_dgrad_mode(int mode) { step_graphs_drop(); gemm::set_dgrad_mode(mode); }
 void b200seg_gemm_set_fwd_mode(int mode) { step_graphs_drop(); gemm::set_fwd_mode(mode); }
 void b200seg_gemm_set_fwd_convert(int on) { step_graphs_drop(); gemm::set_fwd_convert(on); }

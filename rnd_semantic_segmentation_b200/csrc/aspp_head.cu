@@ -592,7 +592,7 @@ int aspp_backward_packed(const void* gOt_in, const void* Xp, const void* WpT, co
     gemm::Operand a{Gp, true, Ppitch};
     gemm::Operand b{(const __nv_bfloat16*)WpT, false, NJ};
     int rc = gemm::launch(a, b, (int)P, Cin, NJ, 1, grad_x, 0, 0, (long long)Cin * hw, 0, stream, nullptr, 1,
-                          gemm::dgrad_mode() == 3 ? gemm::SHARE_B : gemm::SHARE_PAIR, false, weights_ready ? gemm::overlap_sms() : 0,
+                          gemm::SHARE_PAIR, false, weights_ready ? gemm::overlap_sms() : 0,
                           gemm::SHARE_B, hw);
     if (rc) return rc;
   }

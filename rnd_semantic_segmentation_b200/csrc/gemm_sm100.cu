@@ -84,16 +84,12 @@ static int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensor
   return B200SEG_OK;
 }
 
-static int g_tma_store = 0;          // b200seg_gemm_set_tma_store(): 1 = fp32 NCHW epilogue through TMA bulk stores (measured equal to the LSU stores: 180.8 vs 179.4 us)
-void set_tma_store(int on) { g_tma_store = on; }
 static int g_dgrad_mode = 1;         // b200seg_gemm_set_dgrad_mode(): see gemm_sm100.cuh
 void set_dgrad_mode(int mode) { g_dgrad_mode = mode; }
 int dgrad_mode() { return g_dgrad_mode; }
 static int g_fwd_mode = 1;           // b200seg_gemm_set_fwd_mode(): see gemm_sm100.cuh
 void set_fwd_mode(int mode) { g_fwd_mode = mode; }
 int fwd_mode() { return g_fwd_mode; }
-static int g_n_fastest = 0;
-void set_n_fastest(int on) { g_n_fastest = on; }
 static int g_narrow_tiles = 1;        // b200seg_gemm_set_narrow_tiles(): 0 = always 256-column tiles
 void set_narrow_tiles(int on) { g_narrow_tiles = on; }
 
@@ -114,7 +110,6 @@ template <bool A_MN, bool B_MN>
 static int launch_s(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const Params& p, int grid, int share,
                     cudaStream_t stream) {
   if (share == SHARE_PAIR) return launch_t<A_MN, B_MN, SHARE_PAIR>(ta, tb, to, p, grid, stream);
-  if (share == SHARE_AB) return launch_t<A_MN, B_MN, SHARE_AB>(ta, tb, to, p, grid, stream);
   if (share == SHARE_B) return launch_t<A_MN, B_MN, SHARE_B>(ta, tb, to, p, grid, stream);
   if (share == SHARE_A) return launch_t<A_MN, B_MN, SHARE_A>(ta, tb, to, p, grid, stream);
   return launch_t<A_MN, B_MN, SHARE_NONE>(ta, tb, to, p, grid, stream);
@@ -131,8 +126,7 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
                     "gemm: bf16 output needs plain row-major D with N, row pitch multiples of 8 and a 16-byte aligned base");
   // callers name the sharing geometry they want; the global mode (A/B experiments) can veto or override it
   if (!g_share_enabled) share = SHARE_NONE;
-  if (g_share_enabled == 2 && share != SHARE_NONE) share = SHARE_AB;        // 2 x 2 clusters sharing both operands
-  if (g_share_enabled != 2 && share == SHARE_AB) share = SHARE_A;
+  if (share == SHARE_AB) share = SHARE_A;                                    // (the 2 x 2-cluster mode measured ~1.9x slower and was removed)
   if (g_share_enabled == 3 && share == SHARE_B) share = SHARE_PAIR;         // also the store-bound fp32 dgrad as 2-SM pairs
   if (g_share_enabled == 4 && (share == SHARE_A || share == SHARE_B)) share = SHARE_PAIR;
   if (g_share_enabled == 5 && share == SHARE_PAIR) share = pair_fallback;   // no cta_group::2: the multicast pairs used before
@@ -167,15 +161,13 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
   // one lives in L2.  Channel-major problems (M = channels / packed weight rows <= N = pixels) walk along M; pixel-major ones
   // (M = pixels: the seam-format and the register-store data gradients) walk along N -- M-fastest made them re-read the
   // 86 MB pixel operand once per N-tile (653 MB of DRAM reads per launch at the bench shape, ncu profiles/r2_dgrad_*).
-  p.n_fastest = ((g_n_fastest && col_hw > 0) || M > N) ? 1 : 0;
+  p.n_fastest = M > N ? 1 : 0;
   if (splits_used) *splits_used = p.splits;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && row_stride % 4 == 0 && split_stride % 4 == 0 &&
               (col_hw <= 0 || (col_hw % 4 == 0 && img_stride % 4 == 0)))
                  ? 1
                  : 0;
   // a pair needs two tiles along the paired dimension to be worth it
-  if (share == SHARE_AB && p.m_tiles < 2) share = SHARE_A;
-  if (share == SHARE_AB && p.n_tiles < 2) share = SHARE_B;
   if (share == SHARE_B && p.m_tiles < 2) share = SHARE_NONE;
   if (share == SHARE_PAIR && p.m_tiles < 2) share = SHARE_NONE;
   if (share == SHARE_A && p.n_tiles < 2) share = SHARE_NONE;
@@ -206,21 +198,7 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
   else rc = make_tmap(&tb, b.ptr, N, K, b.pitch, 64, BLOCK_K);
   if (rc) return rc;
 
-  // fp32 NCHW output (the data gradient): TMA bulk stores when every 16-column chunk stays inside one image
-  CUtensorMap to = ta;
-  p.tma_store = 0;
-  if (g_tma_store && !out_bf16 && col_hw > 0 && col_hw % 16 == 0 && p.vec_ok && N % col_hw == 0) {
-    EncodeTiledFn fn = encode_fn();
-    cuuint64_t gdim[3] = {(cuuint64_t)col_hw, (cuuint64_t)M, (cuuint64_t)(N / col_hw)};
-    cuuint64_t gstr[2] = {(cuuint64_t)row_stride * 4, (cuuint64_t)img_stride * 4};
-    cuuint32_t box[3] = {16, 32, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    if (fn && fn(&to, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                 CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
-      p.tma_store = 1;
-    else
-      to = ta;
-  }
+  CUtensorMap to = ta;            // third tensor-map slot: the 64-row B boxes of the register-store variant (below)
 
   // persistent CTAs, one per SM, minus the SMs the caller wants left free for a concurrent kernel (the NCCL all-reduce
   // of the weight gradients running underneath the data-gradient GEMM)

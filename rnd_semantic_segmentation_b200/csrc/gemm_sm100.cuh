@@ -48,12 +48,11 @@ struct Params {
   int vec_ok;               // output addressing allows 16-byte vector stores
   int out_bf16;             // D is written as bf16 (plain row-major [M][row_stride], 16-byte aligned rows) instead of fp32
   int n_fastest;            // tile order: consecutive work units walk along N (rows of D are written as long sequential runs)
-  int tma_store;            // fp32 image-mapped D (NCHW) written by TMA bulk stores from swizzled shared-memory boxes
   int row_hw_px;            // pixels per image for the row_hw mode
   int epi_sleep_ns;         // row_hw mode: pause after each 16-column chunk's stores (paces the epilogue's store bursts)
   int row_hw;               // > 0: ROWS of D are pixels of images with row_hw pixels each and D is fp32 NCHW: element (m, n)
                             // lives at out[(m / row_hw) * img_stride + n * row_hw + m % row_hw]; stored straight from registers
-                            // (lane = pixel: a warp-level store is 32 consecutive pixels of one channel plane); 2: streaming stores
+                            // (lane = pixel: a warp-level store is 32 consecutive pixels of one channel plane)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -138,16 +137,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 // TMA bulk store of a {16 cols, 32 rows, 1 image} fp32 box from shared memory (3-D map: column-in-image, row, image)
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(m), "r"(smem_src), "r"(c0),
-               "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (sm_100 format): start>>4 [0,14), LBO>>4 [16,30),
@@ -550,7 +539,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int ncols = p.N - (col_base + c * 16);
             if (ok) {
               float* d = dst + (long long)(c * 16) * hw;
-              if (p.row_hw == 2) {
+              // (Code-generation note: with this two-way branch nvcc 12.9 keeps both TMEM register sets live -- 80 registers,
+              //  147 us at the bench shape.  The same loop without the branch compiled to 71 registers and ran 248 us: check
+              //  `cuobjdump --dump-resource-usage` and profiles/dgrad_modes.py after touching this block.)
+              if (p.row_hw == 2) {                      // streaming (evict-first) stores: measured no better, kept as dgrad mode 2
 #pragma unroll
                 for (int k = 0; k < 16; ++k)
                   if (k < ncols) __stcs(d + (long long)k * hw, __uint_as_float(r[k]));
@@ -562,46 +554,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             if (p.epi_sleep_ns > 0) __nanosleep((unsigned)p.epi_sleep_ns);
           }
-        }
-      } else if (p.tma_store) {
-        // fp32 NCHW D through the TMA unit: each 32 x 16 chunk goes TMEM -> registers -> a dense, 64-byte-swizzled
-        // shared-memory box (conflict-free 16-byte stores) -> one cp.async.bulk.tensor store that clips rows >= M and
-        // images >= N/hw itself.  No shared-memory read-back and no global stores through the LSU / L1: the SM-local
-        // memory pipe was this epilogue's limiter.  Two boxes per warp, so chunk c is staged while c - 1 drains.
-        if (rows > 0 && col_base < p.N) {
-          constexpr int NCH = BLOCK_N / 2 / 16;
-          uint8_t* sbuf = reinterpret_cast<uint8_t*>(stg);
-          int img = col_base / p.col_hw;
-          int rem = col_base - img * p.col_hw;
-          const uint32_t sw = (uint32_t)((lane >> 1) & 3);          // 64-byte swizzle: 16-byte chunk ^= (row / 2) % 4
-          uint32_t rbuf[2][16];
-          tmem_ld16(taddr, rbuf[0]);
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            tmem_ld_wait();
-            const uint32_t* r = rbuf[c & 1];
-            if (c + 1 < NCH) tmem_ld16(taddr + (uint32_t)((c + 1) * 16), rbuf[(c + 1) & 1]);
-            uint8_t* buf = sbuf + (c & 1) * 2048;
-            if (c >= 2) {                                            // the store of chunk c - 2 has finished reading this box
-              if (lane == 0) bulk_wait_read<1>();
-              __syncwarp();
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              *reinterpret_cast<float4*>(buf + lane * 64 + (((uint32_t)k ^ sw) << 4)) =
-                  make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), __uint_as_float(r[4 * k + 2]),
-                              __uint_as_float(r[4 * k + 3]));
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_3d(&tmap_out, smem_u32(buf), rem, row_base, img);
-              bulk_commit();
-            }
-            rem += 16;
-            while (rem >= p.col_hw) { rem -= p.col_hw; ++img; }
-          }
-          if (lane == 0) bulk_wait_read<0>();                        // both boxes are free for the next tile
-          __syncwarp();
         }
       } else if (rows > 0 && col_base < p.N) {
         // per-lane (image, offset) of its first column, advanced by 16 columns per chunk (no division in the loop)
@@ -663,7 +615,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   }
 
-  if (warp >= 4 && lane == 0 && p.tma_store) bulk_wait_all();       // every bulk store of this warp has been written out
   tc_fence_before();
   __syncthreads();
   if (CLUSTER) cluster_sync_all();            // the peer may still multicast into / arrive on this CTA until it is done too
@@ -990,8 +941,7 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
            int col_hw, long long img_stride, long long split_stride, cudaStream_t stream, int* splits_used, int prof_tag = -1,
            int share = SHARE_NONE, bool out_bf16 = false, int sm_reserve = 0, int pair_fallback = SHARE_B, int row_hw = 0);
 // fp32 NCHW data gradient of the head: 0 = channels along M (shared-memory transpose epilogue), 1 = pixels along M as cta_group::2
-// pairs, stores straight from registers, seven ring stages; 2 = the same with streaming (evict-first) stores and six stages;
-// 3 = pixels along M on multicast pairs
+// pairs, stores straight from registers, seven ring stages
 void set_dgrad_mode(int mode);
 int dgrad_mode();
 // forward GEMM of the head: 0 = channel-major (M = packed weight rows, shared-memory transpose epilogue), 1 = pixel-major

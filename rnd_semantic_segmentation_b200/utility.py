@@ -139,46 +139,6 @@ class BatchedEvaluator:
         return (self.cm, self.frame_cms) if self.per_frame else self.cm
 
 
-class OverlappedEvaluator:
-    """Eval loop of aspp_tester.py:57-72 after the backbone with the two halves of a frame on two CUDA streams:
-
-        head stream : features -> ASPP head (feature pack, tcgen05 GEMM, gather) -> low-res logits        (tensor pipe / HBM)
-        tail stream : upsample + argmax + confusion matrix of the PREVIOUS frame (K4)                      (CUDA-core issue bound)
-
-    The persistent GEMM leaves ~30 KB of shared memory and half the registers of every SM free, enough for one K4 CTA per
-    SM, so the issue-bound tail of frame i runs underneath the head of frame i + 1.  The confusion matrix accumulates in one
-    device-resident int64 [C,C]; ``finish()`` joins the streams and returns it."""
-
-    def __init__(self, classifier, num_classes: int, ignore_index: int = 255, device=None):
-        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.classifier, self.ignore_index = classifier, ignore_index
-        self.cm = torch.zeros(num_classes, num_classes, dtype=torch.int64, device=dev)
-        self.tail = torch.cuda.Stream(device=dev)
-        self._inflight = []                  # (logits, labels) kept alive until the tail stream has consumed them
-
-    def step(self, features: torch.Tensor, labels: torch.Tensor):
-        head_stream = torch.cuda.current_stream(features.device)
-        with torch.no_grad():
-            lg = self.classifier.logits(features)
-        ready = torch.cuda.Event()
-        ready.record(head_stream)
-        self.tail.wait_event(ready)
-        with torch.cuda.stream(self.tail):
-            segmentation_eval_step(lg, labels, self.ignore_index, cm=self.cm)
-            done = torch.cuda.Event()
-            done.record(self.tail)
-        self._inflight.append((lg, labels, done))
-        while len(self._inflight) > 2:       # the oldest frame's tail has long finished when two newer ones are queued ...
-            old = self._inflight.pop(0)
-            head_stream.wait_event(old[2])   # ... but make the allocator's reuse of its buffers wait for it anyway
-        return self.cm
-
-    def finish(self) -> torch.Tensor:
-        torch.cuda.current_stream(self.cm.device).wait_stream(self.tail)
-        self._inflight.clear()
-        return self.cm
-
-
 # A prediction produced by LazyProbabilities.max remembers the confusion matrix computed in the same
 # launch, so the reference tester's follow-up calls confusion_matrix(...) / intersectionAndUnionGPU(...)
 # on that very tensor are answered without touching the pixels again.

@@ -217,18 +217,6 @@ def test_gemm_core_narrow_tiles(lib, M, N, K, share):
         assert ref > 0 and err <= 1e-3 * ref, (narrow, err, ref)
 
 
-@pytest.mark.parametrize("M,N,K,b_mn,col_hw,share", [(2048, 1024, 640, True, 256, 1), (300, 4096, 128, False, 512, 0), (2048, 2048, 640, True, 1024, 4)])
-def test_gemm_core_tma_store_epilogue(lib, M, N, K, b_mn, col_hw, share):
-    """fp32 image-mapped (NCHW) output through TMA bulk stores from 64-byte-swizzled shared-memory boxes (optional epilogue of the
-    data-gradient GEMM), ragged M included (the TMA unit clips rows >= M)."""
-    lib.gemm_set_tma_store(True)
-    try:
-        err, ref = lib.gemm_selftest(M, N, K, False, b_mn, 1, col_hw, share)
-    finally:
-        lib.gemm_set_tma_store(False)
-    assert ref > 0 and err <= 1e-3 * ref, (err, ref)
-
-
 # ------------------------------------------------------------------ K1
 def _head_pair(cin, C, seed):
     torch.manual_seed(seed)
@@ -739,27 +727,6 @@ def test_cuda_graph_capture_train_eval_and_discriminator(lib):
                 assert torch.equal(a, b)
     finally:
         b200.set_feature_pack_cache(0)
-
-
-def test_overlapped_evaluator_bit_exact(lib):
-    """Two-stream eval loop (K4 of frame i underneath the head of frame i+1): same int64 confusion matrix as the sequential loop."""
-    import rnd_semantic_segmentation_b200 as b200
-    from rnd_semantic_segmentation_b200 import synth
-    C = 19
-    torch.manual_seed(3)
-    head = synth.scale_head_for_unit_logits(b200.ASPP_Classifier_V2(256, RATES, RATES, C)).cuda().eval()
-    frames = [(torch.relu(torch.randn(1, 256, 32, 64, generator=torch.Generator().manual_seed(10 + i))).cuda(),
-               make_labels(1, 256, 512, C, 0.1, 20 + i).cuda()) for i in range(7)]
-    cm_seq = torch.zeros(C, C, dtype=torch.int64, device="cuda")
-    for x, y in frames:
-        with torch.no_grad():
-            b200.segmentation_eval_step(head.logits(x), y, cm=cm_seq)
-    for _ in range(3):                                   # repeated: a stream-ordering bug would show up as a flaky difference
-        ov = b200.OverlappedEvaluator(head, C)
-        for x, y in frames:
-            ov.step(x, y)
-        assert torch.equal(ov.finish(), cm_seq)
-    assert int(cm_seq.sum()) == sum(int((y != 255).sum()) for _, y in frames)
 
 
 def test_discriminator_tail_and_soft_ce_golden(lib, golden):
