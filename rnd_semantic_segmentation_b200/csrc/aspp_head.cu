@@ -360,14 +360,26 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   const int c = blockIdx.y, r = blockIdx.z;
   if (!gw.p[r]) return;
   if (ci < Cin) {
+    // nine independent loads per split in flight (two splits per trip): the kernel is latency-bound, not byte-bound (31 MB);
+    // summation order per tap is still split 0, 1, 2, ... (deterministic)
+    const float* src[9];
+    float acc[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
       const int t = (k == 4) ? 8 * R : r * 8 + (k < 4 ? k : k - 1);
-      const long long off = (long long)(t * C + c) * Cin + ci;
-      float acc = 0.f;
-      for (int s = 0; s < S; ++s) acc += __ldcs(part + s * slab + off);
-      sm[threadIdx.x * 9 + k] = acc;
+      src[k] = part + (long long)(t * C + c) * Cin + ci;
+      acc[k] = 0.f;
     }
+#pragma unroll 2
+    for (int s = 0; s < S; ++s) {
+      float v[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) v[k] = __ldcs(src[k] + s * slab);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) acc[k] += v[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) sm[threadIdx.x * 9 + k] = acc[k];
   }
   __syncthreads();
   const int nci = min(256, Cin - ci0);

@@ -548,14 +548,16 @@ __global__ void __launch_bounds__(128) k2_finalize_grad(const K2Geom g, const fl
   if (PACKED) {                       // fixed-order block reduction of the fp32 gradient per class
 #pragma unroll
     for (int c = 0; c < 32; ++c) {
-      const float v = warp_sum(acc[c]);
-      if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][c] = v;
+      if (c < g.C) {                    // (uniform: classes beyond C are all-zero accumulators, no need to reduce them)
+        const float v = warp_sum(acc[c]);
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5][c] = v;
+      }
     }
     __syncthreads();
     if (threadIdx.x < 32) {
       const int c = threadIdx.x;
       const long long blk_id = ((long long)n * g.h + i) * gridDim.x + blockIdx.x;
-      bias_part[blk_id * 32 + c] = (wsum[0][c] + wsum[1][c]) + (wsum[2][c] + wsum[3][c]);
+      bias_part[blk_id * 32 + c] = c < g.C ? (wsum[0][c] + wsum[1][c]) + (wsum[2][c] + wsum[3][c]) : 0.f;
     }
   }
 }
