@@ -208,15 +208,19 @@ class HeadGradBucket(FlatGradBucket):
         # bucket order: the R weights, then the R biases as one [R, C] block.  In symmetric memory when the box allows it: the
         # all-reduce is then our own peer-memory kernel (NVSwitch multimem reduce + broadcast, csrc/p2p_allreduce.cu).  Measured
         # (profiles/p2p_probe.py, 5.6 MB): 8 ranks 38 us on FOUR CTAs (NCCL: 178 / 104 / 57 us at 8 / 16 / 32 CTAs), 2 ranks 52 / 42 us
-        # on 4 / 8 CTAs -- so the data-gradient GEMM cedes 4 SMs (8 at two ranks) instead of the 8 / 16 / 32 an NCCL ring needs.
+        # on 4 / 8 CTAs -- so the data-gradient GEMM cedes 4 SMs instead of the 8 / 16 / 32 an NCCL ring needs.
         super().__init__([m.weight for m in convs] + [m.bias for m in convs], symmetric=True, group=group)
+        if overlap_ctas is None and os.environ.get("B200SEG_OVERLAP_CTAS"):
+            overlap_ctas = int(os.environ["B200SEG_OVERLAP_CTAS"])           # (experiments)
         if overlap_ctas is None:
             world = dist.get_world_size() if is_distributed() else 1
             if self._symm is not None:
                 # multimem path (> 2 ranks): 4 CTAs (38 us for the 5.6 MB bucket at 8 ranks).  Fewer looked as good in a long-running
                 # probe at sustained clocks (profiles/dp_overlap_probe.py) but lose in the bench regime: 8 ranks, 20 timed steps,
                 # 4 CTAs 0.767 ms per step, 2 CTAs 0.865 ms (the collective no longer fits under the data-gradient GEMM)
-                overlap_ctas = 8 if world <= 2 else 4
+                # (two ranks, bench regime: 4 CTAs 0.748 / 0.751 ms per step, 8 CTAs 0.766 / 0.756 -- the multicast address exists at
+                #  two ranks as well)
+                overlap_ctas = 4
             else:
                 overlap_ctas = 8 if world <= 2 else (16 if world <= 4 else 32)
         self.p2p_blocks = int(overlap_ctas) if overlap_ctas > 0 else 8
