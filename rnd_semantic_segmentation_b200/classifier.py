@@ -29,7 +29,7 @@ class ASPP_Classifier_V2(nn.Module):
         self._packed_key = None
         # forward(x, size) returns a lazy.LazyLogits (fused head + upsample + loss when the caller's own criterion consumes it;
         # materialised on any other use).  False: always the materialised tensor (needed under torch's DDP wrapper).
-        self.lazy = os.environ.get("B200SEG_LAZY", "1") != "0"
+        self.lazy = None        # None = automatic (lazy.lazy_enabled): lazy unless a multi-rank process group is initialised
 
     def out_channels_lowres(self):
         return int(self.conv2d_list[0].out_channels)
@@ -73,7 +73,8 @@ class ASPP_Classifier_V2(nn.Module):
 
     # ---- reference API -------------------------------------------------------------------
     def forward(self, x, size=None):
-        if size is not None and self.lazy and x.is_cuda:    # classifier.py:30-31, evaluated by whoever consumes it (lazy.py)
+        from . import lazy as _lazy
+        if size is not None and x.is_cuda and _lazy.lazy_enabled(self.lazy):    # classifier.py:30-31, evaluated by whoever consumes it (lazy.py)
             from .lazy import LazyLogits, _LogitsSource
             return LazyLogits(_LogitsSource(self, x, size))
         out = self.logits(x)

@@ -30,7 +30,7 @@ class PixelDiscriminator(nn.Module):
 
         self._packed = None
         self._packed_key = None
-        self.lazy = os.environ.get("B200SEG_LAZY", "1") != "0"        # see ASPP_Classifier_V2.lazy
+        self.lazy = None        # None = automatic (lazy.lazy_enabled): lazy unless a multi-rank process group is initialised
 
     def out_channels_lowres(self):
         return int(self.cls1.out_channels + self.cls2.out_channels)
@@ -61,7 +61,8 @@ class PixelDiscriminator(nn.Module):
                                               packed=self._packed_weights())
 
     def forward(self, x, size=None):
-        if size is not None and self.lazy and x.is_cuda:                  # discriminator.py:48-49, evaluated by its consumer
+        from . import lazy as _lazy
+        if size is not None and x.is_cuda and _lazy.lazy_enabled(self.lazy):                  # discriminator.py:48-49, evaluated by its consumer
             from .lazy import LazyLogits, _LogitsSource
             return LazyLogits(_LogitsSource(self, x, size))
         out = self.logits(x)

@@ -24,12 +24,31 @@ gradient buckets of ``distributed.py``.
 """
 from __future__ import annotations
 
+import os
+
 import torch
+import torch.distributed as dist
 import torch.nn.functional as F
 
 from . import ops
 
 __all__ = ["LazyLogits", "LazySoftLabel", "LazyZeros", "LazySlotLabel", "is_lazy", "materialize"]
+
+
+def lazy_enabled(flag) -> bool:
+    """Whether ``module(x, size)`` hands out a lazy object.  ``flag`` is the module's ``lazy`` attribute: True / False force it;
+    None (the default) = automatic: env B200SEG_LAZY=0/1 if set, else lazy UNLESS a multi-rank process group is initialised.
+    The reference wraps its modules in ``DistributedDataParallel(..., find_unused_parameters=True)`` (train_distill.py:54-62): DDP then
+    walks the module OUTPUT for tensors to discover the used parameters, finds none in a lazy stand-in, and would mark every
+    parameter unused.  Under a process group the default is therefore the materialised tensor (round-1 behaviour); the fused path
+    is reached there through ``forward_loss`` / the gradient buckets (distributed.py), or by setting ``module.lazy = True`` when
+    the module is not wrapped in DDP."""
+    if flag is not None:
+        return bool(flag)
+    env = os.environ.get("B200SEG_LAZY")
+    if env is not None:
+        return env != "0"
+    return not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
 
 
 def is_lazy(obj) -> bool:

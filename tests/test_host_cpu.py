@@ -176,8 +176,13 @@ def _dist_worker(rank, world, port, tmp):
     from rnd_semantic_segmentation_b200 import distributed as D
     import rnd_semantic_segmentation_b200 as b200
     assert D.init_from_env("gloo")
+    # under a multi-rank process group module(x, size) defaults to the materialised tensor: the reference's
+    # DistributedDataParallel(find_unused_parameters=True) wrapper (train_distill.py:54-62) looks for tensors in the output
+    from rnd_semantic_segmentation_b200 import lazy
+    assert lazy.lazy_enabled(None) is False and lazy.lazy_enabled(True) is True and lazy.lazy_enabled(False) is False
     torch.manual_seed(0)
     head = b200.ASPP_Classifier_V2(8, [6, 12, 18, 24], [6, 12, 18, 24], 3)
+    assert head.lazy is None
     for i, p in enumerate(head.parameters()):
         p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
     bucket = D.allreduce_mean_grads_(head)
@@ -294,3 +299,19 @@ def test_c_side_split_rule_matches_the_python_one(built_lib):
     assert lib.b200seg_head_loss_workspace_bytes(2, 2048, 19, 65, 129, 4, 512, 1024, 0) > 2 * 65 * 129 * 2048 * 2
     assert lib.b200seg_head_loss_workspace_bytes(2, 2048, 19, 65, 129, 4, 512, 1024, 1) < 2 * 65 * 129 * 2048 * 2
     assert lib.b200seg_head_loss_workspace_bytes(0, 2048, 19, 65, 129, 4, 512, 1024, 0) == 0
+
+
+def test_lazy_logits_default_is_automatic():
+    """Single process, no process group: lazy; B200SEG_LAZY overrides; an explicit module attribute overrides both."""
+    from rnd_semantic_segmentation_b200 import lazy
+    old = os.environ.pop("B200SEG_LAZY", None)
+    try:
+        assert lazy.lazy_enabled(None) is True
+        os.environ["B200SEG_LAZY"] = "0"
+        assert lazy.lazy_enabled(None) is False and lazy.lazy_enabled(True) is True
+        os.environ["B200SEG_LAZY"] = "1"
+        assert lazy.lazy_enabled(None) is True and lazy.lazy_enabled(False) is False
+    finally:
+        os.environ.pop("B200SEG_LAZY", None)
+        if old is not None:
+            os.environ["B200SEG_LAZY"] = old
