@@ -315,3 +315,26 @@ def test_lazy_logits_default_is_automatic():
         os.environ.pop("B200SEG_LAZY", None)
         if old is not None:
             os.environ["B200SEG_LAZY"] = old
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """include/b200seg.h is the drop-in boundary: it must compile as C99 and as C++ on its own (no torch / CUDA types), and a C
+    program that only includes it and calls a host-side query must link against libb200seg.so."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    hdr = os.path.join(ROOT, "include", "b200seg.h")
+    subprocess.run(["gcc", "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", hdr], check=True)
+    subprocess.run(["g++", "-fsyntax-only", "-x", "c++", "-Wall", "-Werror", hdr], check=True)
+    from rnd_semantic_segmentation_b200 import _build_ext
+    so = _build_ext.build()
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "b200seg.h"\nint main(void) {\n'
+                   '  printf("%d %d %d\\n", b200seg_abi_version(), b200seg_aspp_packed_rows(19, 4), b200seg_aspp_default_wgrad_splits(67080, 19, 2048, 4));\n'
+                   '  return 0;\n}\n')
+    exe = tmp_path / "t"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), so,
+                    "-Wl,-rpath," + os.path.dirname(so)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out == ["1", "640", "6"], out
