@@ -372,7 +372,7 @@ B200SEG_API int b200seg_gemm_selftest(int M, int N, int K, int a_mn_major, int b
 B200SEG_API void b200seg_gemm_set_narrow_tiles(int on);
 /* fp32 NCHW data gradient of the head (the dX of classifier.py:26-29's convolutions): 0 = channels along the GEMM's M dimension
  * (shared-memory transpose epilogue), 1 (default) = pixels along M as CTA pairs, stored straight from the accumulator registers
- * (lane = pixel: one store instruction = 32 consecutive pixels of a channel plane; seven ring stages, paced stores), 2 = the same
+ * (lane = pixel: one store instruction = 32 consecutive pixels of a channel plane; seven ring stages), 2 = the same
  * with streaming (evict-first) stores (measured no better).  The tile order of every GEMM follows the operand sizes (the larger
  * operand streams from HBM once). */
 B200SEG_API void b200seg_gemm_set_dgrad_mode(int mode);

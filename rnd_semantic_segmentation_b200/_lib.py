@@ -1146,7 +1146,7 @@ def gemm_selftest(M, N, K, a_mn=False, b_mn=False, splits=1, col_hw=0, share=0):
 
 def gemm_set_dgrad_mode(mode: int):
     """fp32 NCHW data gradient of the head: 0 = channel-major GEMM with the shared-memory transpose epilogue, 1 (default) = pixel-major
-    CTA pairs storing straight from registers (seven ring stages, paced stores)."""
+    CTA pairs storing straight from registers (seven ring stages)."""
     load().b200seg_gemm_set_dgrad_mode(int(mode))
 
 

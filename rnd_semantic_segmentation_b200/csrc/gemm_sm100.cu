@@ -147,15 +147,14 @@ int launch(const Operand& a, const Operand& b, int M, int N, int K, int splits, 
   p.out_bf16 = out_bf16 ? 1 : 0;
   p.row_hw_px = row_hw > 0 ? row_hw : 0;
   p.row_hw = row_hw > 0 ? (g_dgrad_mode == 2 ? 2 : 1) : 0;
-  // pace the register-store epilogue: ~1/20 of a tile's MMA time after each of its 8 chunks (K = 640: 192 ns), so that the
-  // 128 KB a tile stores leave the SM spread over the tile time instead of as one burst in front of the operand requests
-  // (measured at the bench shape: 161 -> 150 us; B200SEG_EPI_SLEEP=<ns> overrides, 0 = off)
+  // optional pacing of the register-store epilogue (B200SEG_EPI_SLEEP=<ns> after each 16-column chunk's stores, default off): with a
+  // six-stage ring, spreading a tile's 128 KB of stores over the tile time took the data gradient from 161 to 150 us (the
+  // store bursts delay the operand requests queued behind them); with the seventh stage it no longer changes anything (154-156 us
+  // with 0 or 192 ns), so it stays an experiment knob
   {
     static int env_ns = -2;
-    if (env_ns == -2) { const char* e = getenv("B200SEG_EPI_SLEEP"); env_ns = e ? atoi(e) : -1; }
-    const int ns = K * 3 / 10;
-    // (long-K problems store little per unit of MMA time: no pacing)
-    p.epi_sleep_ns = row_hw > 0 ? (env_ns >= 0 ? env_ns : (K > 1024 ? 0 : (ns > 200 ? 200 : ns))) : 0;
+    if (env_ns == -2) { const char* e = getenv("B200SEG_EPI_SLEEP"); env_ns = e ? atoi(e) : 0; }
+    p.epi_sleep_ns = row_hw > 0 && env_ns > 0 ? env_ns : 0;
   }
   // tile order: the units running together should share the LARGER operand, so that it streams from HBM once and the small
   // one lives in L2.  Channel-major problems (M = channels / packed weight rows <= N = pixels) walk along M; pixel-major ones
