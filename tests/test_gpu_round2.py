@@ -871,3 +871,53 @@ def test_graph_replayed_backward_records_the_weights_ready_event(lib):
     assert captures >= 2 and replays >= 4, (replays, captures)
     for it in range(6):
         assert torch.equal(snaps[it], want[it]), it
+
+
+def test_graph_cache_turns_itself_off_when_addresses_keep_changing(lib):
+    """A loop that keeps every output alive gets fresh addresses each iteration: nothing is ever seen twice, so nothing is captured
+    (direct launches, same results); a loop whose addresses change every few iterations captures a bounded number of graphs and
+    then stops trying.  Results are those of direct launches throughout."""
+    import rnd_semantic_segmentation_b200 as b200
+    n, cin, C, h, w, H, W = 1, 64, 19, 17, 33, 64, 128
+    torch.manual_seed(41)
+    head = b200.ASPP_Classifier_V2(cin, RATES, RATES, C).cuda()
+    g = torch.Generator().manual_seed(42)
+    labels = torch.randint(0, C, (n, H, W), generator=g).cuda()
+    xs = [torch.relu(torch.randn(n, cin, h, w, generator=g)).cuda() for _ in range(4)]
+    lib.set_step_graphs(False)
+    want = []
+    for x in xs:
+        xg = x.clone().requires_grad_(True)
+        loss, _ = head.forward_loss(xg, labels)
+        loss.backward()
+        want.append((loss.detach().clone(), xg.grad.clone()))
+    for p in head.parameters():
+        p.grad = None
+    lib.set_step_graphs(True)
+    try:
+        keep = []
+        for it in range(40):                                   # every output kept alive: fresh addresses every iteration
+            xg = xs[it % 4].clone().requires_grad_(True)
+            loss, logits = head.forward_loss(xg, labels)
+            loss.backward()
+            keep.append((xg, loss, logits))
+            assert torch.equal(loss.detach(), want[it % 4][0]) and torch.equal(xg.grad, want[it % 4][1])
+        replays, captures = lib.step_graph_stats()
+        assert captures == 0 and replays == 0, (replays, captures)
+        del keep
+        for p in head.parameters():
+            p.grad = None
+        held = []
+        for it in range(400):                                  # addresses shift every third iteration
+            xg = xs[it % 4].clone().requires_grad_(True)
+            loss, logits = head.forward_loss(xg, labels)
+            loss.backward()
+            assert torch.equal(loss.detach(), want[it % 4][0]) and torch.equal(xg.grad, want[it % 4][1])
+            if it % 3 == 0:
+                held.append(torch.empty(1 << 16, device="cuda"))
+            for p in head.parameters():
+                p.grad = None
+        replays, captures = lib.step_graph_stats()
+        assert captures <= 64, (replays, captures)
+    finally:
+        lib.set_step_graphs(True)
