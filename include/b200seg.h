@@ -249,6 +249,25 @@ B200SEG_API int b200seg_aspp_default_wgrad_splits(int64_t P, int C, int Cin, int
  *   Activations are bf16 NHWC [N,h,w,pitch] (pitch = channels rounded to a multiple of 8); weights are packed once per
  *   parameter update.  Stride 1, padding == dilation.  The zero padding is the TMA unit's out-of-bounds fill.
  * ------------------------------------------------------------------------------------------- */
+/* The whole stack in ONE call per direction (replayed from a CUDA graph once the same arguments have been seen twice, like
+ * b200seg_head_loss_forward / _backward; every buffer is caller-provided, results bit-identical to the separate entries below):
+ *   forward : [pack w1, w2, cls1 | cls2 (do_pack)] -> [pack x (x_kind 0: fp32 NCHW; 1: bf16 NHWC used in place)] -> conv + LReLU ->
+ *             conv + LReLU -> cls1 | cls2 -> out fp32 [N, 2C, h, w]                     discriminator.py:34-47
+ *   backward: grad_out fp32 [N, 2C, h, w] -> bf16 NHWC -> bias / weight / data gradients of the three layers (LeakyReLU' fused
+ *             into the data-gradient epilogues); NULL outputs are skipped together with everything only they need
+ *   Wf_l / Wb_l: bf16 [9][Co_l][Ci_l] / [9][Ci_l][round8(Co_l)]; b3 fp32 [2C]; Xp / A1 / A2 / G3 / dZ2 / dZ1: bf16 NHWC;
+ *   gb3 fp32 [2C] = the cls1 | cls2 bias gradients; scratch: b200seg_disc_backward_scratch_bytes(...) bytes */
+B200SEG_API int b200seg_disc_forward(const void* x, int x_kind, int N, int Cin, int h, int w, int ndf1, int ndf2, int C,
+                                    const float* w1, const float* b1, const float* w2, const float* b2, const float* wc1,
+                                    const float* bc1, const float* wc2, const float* bc2, float slope, int do_pack, void* Wf1,
+                                    void* Wb1, void* Wf2, void* Wb2, void* Wf3, void* Wb3, float* b3, void* Xp, void* A1, void* A2,
+                                    float* out, void* stream);
+B200SEG_API int64_t b200seg_disc_backward_scratch_bytes(int N, int Cin, int h, int w, int ndf1, int ndf2, int C);
+B200SEG_API int b200seg_disc_backward(const float* grad_out, const void* Xp, const void* A1, const void* A2, const void* Wb1,
+                                    const void* Wb2, const void* Wb3, int N, int Cin, int h, int w, int ndf1, int ndf2, int C,
+                                    float slope, void* G3, void* dZ2, void* dZ1, void* scratch, int64_t scratch_bytes, float* gw1,
+                                    float* gb1, float* gw2, float* gb2, float* gwc1, float* gwc2, float* gb3, float* gx_f32_nchw,
+                                    void* gx_bf16_nhwc, void* stream);
 /* n_parts weight tensors fp32 [part_co[i]][Ci][3][3], concatenated along the output-channel axis (cls1 | cls2 = torch.cat(dim=1)):
  *   Wf bf16 [9][Co][Ci]        forward operand (Co = sum part_co)           (may be NULL)
  *   Wb bf16 [9][Ci][co_pitch]  data-gradient operand, caller zero-fills the padding columns co_pitch > Co   (may be NULL) */

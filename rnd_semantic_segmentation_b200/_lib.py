@@ -83,6 +83,9 @@ SIGNATURES = {
     "b200seg_head_loss_backward": (c_int, [c_vp, c_i64, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                            c_f32, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b200seg_aspp_default_wgrad_splits": (c_int, [c_i64, c_int, c_int, c_int]),
+    "b200seg_disc_backward_scratch_bytes": (c_i64, [c_int] * 7),
+    "b200seg_disc_forward": (c_int, [c_vp, c_int] + [c_int] * 7 + [c_vp] * 8 + [c_f32, c_int] + [c_vp] * 11 + [c_vp]),
+    "b200seg_disc_backward": (c_int, [c_vp] * 7 + [c_int] * 7 + [c_f32] + [c_vp] * 4 + [c_i64] + [c_vp] * 9 + [c_vp]),
     "b200seg_set_step_graphs": (None, [c_int]),
     "b200seg_step_graph_stats": (None, [c_vp, c_vp]),
     "b200seg_conv3x3_pack_weights": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
@@ -927,6 +930,95 @@ def head_loss_backward(ws: torch.Tensor, x_bf16: Optional[torch.Tensor], x_kind:
     if gx_nhwc is not None:
         gx = gx_nhwc.permute(0, 3, 1, 2)
     return gx, gws, gbs
+
+
+# --------------------------------------------------------------------------------------------
+# K6 in one foreign call per direction (the PixelDiscriminator conv stack, graph-replayed like the head entries)
+# --------------------------------------------------------------------------------------------
+def disc_forward(x: torch.Tensor, x_kind: int, shape, weights, biases, slope: float, packed=None):
+    """cat(cls1, cls2)(LReLU(conv(LReLU(conv(x))))) in ONE call (weight pack, feature pack, three conv layers).  ``x``: fp32 NCHW
+    (x_kind 0) or bf16 NHWC [N,h,w,Cin] (x_kind 1); ``shape`` = (N, Cin, h, w); ``weights`` = (w1, w2, wc1, wc2), ``biases`` =
+    (b1, b2, bc1, bc2).  ``packed`` = ((Wf1,Wb1),(Wf2,Wb2),(Wf3,Wb3),b3) to reuse an existing pack (eval), None to pack inside the call.
+    Returns (out fp32 [N,2C,h,w], Xp, A1, A2, packed)."""
+    lib = load()
+    N, Cin, h, w = shape
+    w1, w2, wc1, wc2 = weights
+    b1, b2, bc1, bc2 = biases
+    ndf1, ndf2, C = int(w1.shape[0]), int(w2.shape[0]), int(wc1.shape[0])
+    dev = x.device
+    _need(x, torch.float32 if x_kind == 0 else torch.bfloat16, "features")
+    for wt, shp in ((w1, (ndf1, Cin, 3, 3)), (w2, (ndf2, ndf1, 3, 3)), (wc1, (C, ndf2, 3, 3)), (wc2, (C, ndf2, 3, 3))):
+        if tuple(_need(wt, torch.float32, "conv weight").shape) != shp:
+            raise B200SegError(f"conv weight shape {tuple(wt.shape)}: expected {shp}")
+    for b_ in biases:
+        if b_ is not None:
+            _need(b_, torch.float32, "conv bias")
+    if Cin % 8 or ndf1 % 8 or ndf2 % 8:
+        raise B200SegError("PixelDiscriminator: in_channels, ndf and ndf/2 must be multiples of 8")
+    do_pack = packed is None
+    if do_pack:
+        bf = torch.bfloat16
+        packed = ((torch.empty((9, ndf1, Cin), dtype=bf, device=dev), torch.empty((9, Cin, ndf1), dtype=bf, device=dev)),
+                  (torch.empty((9, ndf2, ndf1), dtype=bf, device=dev), torch.empty((9, ndf1, ndf2), dtype=bf, device=dev)),
+                  (torch.empty((9, 2 * C, ndf2), dtype=bf, device=dev), torch.empty((9, ndf2, _round8(2 * C)), dtype=bf, device=dev)),
+                  torch.empty(2 * C, dtype=torch.float32, device=dev))
+    (Wf1, Wb1), (Wf2, Wb2), (Wf3, Wb3), b3 = packed
+    Xp = x if x_kind == 1 else torch.empty((N, h, w, Cin), dtype=torch.bfloat16, device=dev)
+    A1 = torch.empty((N, h, w, ndf1), dtype=torch.bfloat16, device=dev)
+    A2 = torch.empty((N, h, w, ndf2), dtype=torch.bfloat16, device=dev)
+    out = torch.empty((N, 2 * C, h, w), dtype=torch.float32, device=dev)
+    with _on_device(dev):
+        _check(lib.b200seg_disc_forward(x.data_ptr(), x_kind, N, Cin, h, w, ndf1, ndf2, C, w1.data_ptr(), _ptr(b1), w2.data_ptr(), _ptr(b2),
+                                        wc1.data_ptr(), _ptr(bc1), wc2.data_ptr(), _ptr(bc2), float(slope), 1 if do_pack else 0,
+                                        Wf1.data_ptr(), Wb1.data_ptr(), Wf2.data_ptr(), Wb2.data_ptr(), Wf3.data_ptr(), Wb3.data_ptr(),
+                                        b3.data_ptr(), None if x_kind == 1 else Xp.data_ptr(), A1.data_ptr(), A2.data_ptr(),
+                                        out.data_ptr(), _stream()))
+    return out, Xp, A1, A2, packed
+
+
+def disc_backward(grad_out: torch.Tensor, Xp, A1, A2, Wb1, Wb2, Wb3, C: int, slope: float, need, x_bf16: bool):
+    """Backward of disc_forward in ONE call.  ``need`` = (x, w1, b1, w2, b2, wc1, bc1, wc2, bc2) booleans.  Returns
+    (gx | None, gw1, gb1, gw2, gb2, gwc1, gbc1, gwc2, gbc2) with None where not needed; gx is fp32 NCHW, or with ``x_bf16`` a bf16
+    channels_last tensor of logical shape [N,Cin,h,w]."""
+    lib = load()
+    N, h, w, Cin = (int(v) for v in Xp.shape)
+    ndf1, ndf2 = int(A1.shape[3]), int(A2.shape[3])
+    dev = Xp.device
+    grad_out = _need(grad_out, torch.float32, "grad_out")
+    if tuple(grad_out.shape) != (N, 2 * C, h, w):
+        raise B200SegError(f"disc_backward: grad_out shape {tuple(grad_out.shape)} != {(N, 2 * C, h, w)}")
+    nx, nw1, nb1, nw2, nb2, nwc1, nbc1, nwc2, nbc2 = (bool(v) for v in need)
+    f32, bf = torch.float32, torch.bfloat16
+    need_l1 = nx or nw1 or nb1
+    need_l2 = need_l1 or nw2 or nb2
+    G3 = torch.empty((N, h, w, _round8(2 * C)), dtype=bf, device=dev)
+    dZ2 = torch.empty((N, h, w, ndf2), dtype=bf, device=dev) if need_l2 else None
+    dZ1 = torch.empty((N, h, w, ndf1), dtype=bf, device=dev) if need_l1 else None
+    gw1 = torch.empty((ndf1, Cin, 3, 3), dtype=f32, device=dev) if nw1 else None
+    gb1 = torch.empty(ndf1, dtype=f32, device=dev) if nb1 else None
+    gw2 = torch.empty((ndf2, ndf1, 3, 3), dtype=f32, device=dev) if nw2 else None
+    gb2 = torch.empty(ndf2, dtype=f32, device=dev) if nb2 else None
+    gwc1 = torch.empty((C, ndf2, 3, 3), dtype=f32, device=dev) if nwc1 else None
+    gwc2 = torch.empty((C, ndf2, 3, 3), dtype=f32, device=dev) if nwc2 else None
+    gb3 = torch.empty(2 * C, dtype=f32, device=dev) if (nbc1 or nbc2) else None
+    gx = gx_nhwc = None
+    if nx:
+        if x_bf16:
+            gx_nhwc = torch.empty((N, h, w, Cin), dtype=bf, device=dev)
+        else:
+            gx = torch.empty((N, Cin, h, w), dtype=f32, device=dev)
+    with _on_device(dev):
+        nbytes = int(lib.b200seg_disc_backward_scratch_bytes(N, Cin, h, w, ndf1, ndf2, C))
+        scratch = _scratch("disc_bwd", nbytes, dev)
+        _check(lib.b200seg_disc_backward(grad_out.data_ptr(), Xp.data_ptr(), A1.data_ptr(), A2.data_ptr(), Wb1.data_ptr(), Wb2.data_ptr(),
+                                         Wb3.data_ptr(), N, Cin, h, w, ndf1, ndf2, C, float(slope), G3.data_ptr(), _ptr(dZ2), _ptr(dZ1),
+                                         scratch.data_ptr(), scratch.numel(), _ptr(gw1), _ptr(gb1), _ptr(gw2), _ptr(gb2), _ptr(gwc1),
+                                         _ptr(gwc2), _ptr(gb3), _ptr(gx), _ptr(gx_nhwc), _stream()))
+    if gx_nhwc is not None:
+        gx = gx_nhwc.permute(0, 3, 1, 2)
+    gbc1 = gb3[:C] if nbc1 else None
+    gbc2 = gb3[C:] if nbc2 else None
+    return gx, gw1, gb1, gw2, gb2, gwc1, gbc1, gwc2, gbc2
 
 
 # --------------------------------------------------------------------------------------------

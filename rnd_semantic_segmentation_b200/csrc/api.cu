@@ -758,6 +758,136 @@ int b200seg_head_loss_backward(void* workspace, int64_t workspace_bytes, const v
   });
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// PixelDiscriminator conv stack (discriminator.py:34-47) as ONE call per direction, with the same argument-keyed graph replay as
+// the head entries above: weight pack, feature pack and the three conv layers forward; the whole backward chain (gradient layout
+// conversion, bias sums, three weight-gradient and three data-gradient GEMMs with their reductions) in the other direction.
+// Every buffer is caller-provided (the Python side allocates exactly what the separate entries allocate), so the composition adds
+// no arithmetic and no layout of its own: results are bit-identical to the separate entries.
+// ---------------------------------------------------------------------------------------------------------------------------
+static int round8i(int v) { return (v + 7) / 8 * 8; }
+
+int64_t b200seg_disc_backward_scratch_bytes(int N, int Cin, int h, int w, int ndf1, int ndf2, int C) {
+  if (N <= 0 || Cin <= 0 || h <= 0 || w <= 0 || ndf1 <= 0 || ndf2 <= 0 || C <= 0) return 0;
+  long long m = nhwc_colsum_scratch_bytes(round8i(2 * C));
+  const long long cands[] = {conv3x3_wgrad_scratch_bytes(N, h, w, 2 * C, ndf2, 0), conv3x3_wgrad_scratch_bytes(N, h, w, ndf2, ndf1, 0),
+                             conv3x3_wgrad_scratch_bytes(N, h, w, ndf1, Cin, 0), conv3x3_dgrad_colsum_scratch_bytes(N, h, w, ndf2),
+                             conv3x3_dgrad_colsum_scratch_bytes(N, h, w, ndf1)};
+  for (long long v : cands) m = v > m ? v : m;
+  return m + 256;
+}
+
+int b200seg_disc_forward(const void* x, int x_kind, int N, int Cin, int h, int w, int ndf1, int ndf2, int C, const float* w1,
+                         const float* b1, const float* w2, const float* b2, const float* wc1, const float* bc1, const float* wc2,
+                         const float* bc2, float slope, int do_pack, void* Wf1, void* Wb1, void* Wf2, void* Wb2, void* Wf3, void* Wb3,
+                         float* b3, void* Xp, void* A1, void* A2, float* out, void* stream) {
+  REQUIRE_DEVICE();
+  B200SEG_CHECK_ARG(x && Wf1 && Wb1 && Wf2 && Wb2 && Wf3 && Wb3 && b3 && A1 && A2 && out, "disc_forward: null pointer");
+  B200SEG_CHECK_ARG(x_kind == 0 || x_kind == 1, "disc_forward: x_kind must be 0 (fp32 NCHW) or 1 (bf16 NHWC), got %d", x_kind);
+  B200SEG_CHECK_ARG(x_kind == 1 || Xp, "disc_forward: fp32 NCHW features need the Xp buffer");
+  B200SEG_CHECK_ARG(!do_pack || (w1 && w2 && wc1 && wc2), "disc_forward: null weight pointer");
+  B200SEG_CHECK_ARG(N > 0 && Cin > 0 && h > 0 && w > 0 && ndf1 > 0 && ndf2 > 0 && C > 0 && Cin % 8 == 0 && ndf1 % 8 == 0 && ndf2 % 8 == 0,
+                    "disc_forward: bad shape (channel counts must be multiples of 8)");
+  StepKey key = {};
+  int np = 0, ni = 0;
+  const void* ptrs[] = {x, w1, b1, w2, b2, wc1, bc1, wc2, bc2, Wf1, Wb1, Wf2, Wb2, Wf3, Wb3, b3, Xp, A1, A2, out};
+  for (const void* q : ptrs) key.p[np++] = q;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const long long ints[] = {3, x_kind, N, Cin, h, w, ndf1, ndf2, C, do_pack, dev};
+  for (long long v : ints) key.i[ni++] = v;
+  key.f[0] = slope;
+  return run_step(key, S(stream), true, [&](cudaStream_t st) -> int {
+    int rc;
+    if (do_pack) {
+      const float* weights[4] = {w1, w2, wc1, wc2};
+      const int part_co[4] = {ndf1, ndf2, C, C}, parts_per_layer[3] = {1, 1, 2}, cis[3] = {Cin, ndf1, ndf2};
+      void* Wfs[3] = {Wf1, Wf2, Wf3};
+      void* Wbs[3] = {Wb1, Wb2, Wb3};
+      const int pitches[3] = {round8i(ndf1), round8i(ndf2), round8i(2 * C)};
+      const float* bias_parts[2] = {bc1, bc2};
+      const int bias_lens[2] = {C, C};
+      rc = conv3x3_pack_weights_stack(3, weights, part_co, parts_per_layer, cis, Wfs, Wbs, pitches, bias_parts, bias_lens, 2, b3, st);
+      if (rc) return rc;
+    }
+    const void* act = x;
+    if (x_kind == 0) {
+      rc = aspp_pack_features(reinterpret_cast<const float*>(x), N, Cin, h, w, Xp, st);
+      if (rc) return rc;
+      act = Xp;
+    }
+    rc = conv3x3_forward(act, N, h, w, Cin, Cin, Wf1, ndf1, 1, b1, 1, slope, A1, ndf1, nullptr, st);
+    if (rc) return rc;
+    rc = conv3x3_forward(A1, N, h, w, ndf1, ndf1, Wf2, ndf2, 1, b2, 1, slope, A2, ndf2, nullptr, st);
+    if (rc) return rc;
+    return conv3x3_forward(A2, N, h, w, ndf2, ndf2, Wf3, 2 * C, 1, b3, 0, 0.f, nullptr, 2 * C, out, st);
+  });
+}
+
+int b200seg_disc_backward(const float* grad_out, const void* Xp, const void* A1, const void* A2, const void* Wb1, const void* Wb2,
+                          const void* Wb3, int N, int Cin, int h, int w, int ndf1, int ndf2, int C, float slope, void* G3, void* dZ2,
+                          void* dZ1, void* scratch, int64_t scratch_bytes, float* gw1, float* gb1, float* gw2, float* gb2, float* gwc1,
+                          float* gwc2, float* gb3, float* gx_f32_nchw, void* gx_bf16_nhwc, void* stream) {
+  REQUIRE_DEVICE();
+  B200SEG_CHECK_ARG(grad_out && Xp && A1 && A2 && Wb1 && Wb2 && Wb3 && G3 && scratch, "disc_backward: null pointer");
+  B200SEG_CHECK_ARG(N > 0 && Cin > 0 && h > 0 && w > 0 && ndf1 > 0 && ndf2 > 0 && C > 0, "disc_backward: bad shape");
+  B200SEG_CHECK_ARG(!(gx_f32_nchw && gx_bf16_nhwc), "disc_backward: give at most one feature-gradient destination");
+  const bool need_x = gx_f32_nchw || gx_bf16_nhwc;
+  const bool need_l1 = need_x || gw1 || gb1;                 // anything below layer 2's data gradient
+  const bool need_l2 = need_l1 || gw2 || gb2;                // anything below layer 3's data gradient
+  B200SEG_CHECK_ARG(!need_l2 || dZ2, "disc_backward: dZ2 buffer missing");
+  B200SEG_CHECK_ARG(!need_l1 || dZ1, "disc_backward: dZ1 buffer missing");
+  B200SEG_CHECK_ARG(scratch_bytes >= b200seg_disc_backward_scratch_bytes(N, Cin, h, w, ndf1, ndf2, C), "disc_backward: scratch too small");
+  StepKey key = {};
+  int np = 0, ni = 0;
+  const void* ptrs[] = {grad_out, Xp, A1, A2, Wb1, Wb2, Wb3, G3, dZ2, dZ1, scratch, gw1, gb1, gw2, gb2, gwc1, gwc2, gb3, gx_f32_nchw, gx_bf16_nhwc};
+  for (const void* q : ptrs) key.p[np++] = q;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const long long ints[] = {4, N, Cin, h, w, ndf1, ndf2, C, scratch_bytes, dev};
+  for (long long v : ints) key.i[ni++] = v;
+  key.f[0] = slope;
+  return run_step(key, S(stream), true, [&](cudaStream_t st) -> int {
+    const int p3 = round8i(2 * C);
+    int rc = nchw_to_nhwc_bf16(grad_out, N, 2 * C, h * w, G3, p3, st);
+    if (rc) return rc;
+    if (gb3) {                                                // bias gradient of cls1 | cls2: column sums of the loss gradient
+      rc = nhwc_bf16_colsum(G3, (long long)N * h * w, 2 * C, p3, scratch, gb3, st);
+      if (rc) return rc;
+    }
+    if (gwc1 || gwc2) {
+      float* outs[2] = {gwc1, gwc2};
+      const int parts[2] = {C, C};
+      rc = conv3x3_wgrad(G3, 2 * C, p3, A2, ndf2, ndf2, N, h, w, 1, 0, scratch, scratch_bytes, outs, parts, 2, st);
+      if (rc) return rc;
+    }
+    if (!need_l2) return B200SEG_OK;
+    // dZ2 = (G3 * Wb3) . LeakyReLU'(A2); the bias gradient of layer 2 comes out of the same epilogue
+    rc = conv3x3_dgrad(G3, N, h, w, p3, p3, Wb3, ndf2, 1, A2, slope, dZ2, ndf2, nullptr, st, gb2 ? scratch : nullptr,
+                       gb2 ? scratch_bytes : 0, gb2);
+    if (rc) return rc;
+    if (gw2) {
+      float* outs[1] = {gw2};
+      const int parts[1] = {ndf2};
+      rc = conv3x3_wgrad(dZ2, ndf2, ndf2, A1, ndf1, ndf1, N, h, w, 1, 0, scratch, scratch_bytes, outs, parts, 1, st);
+      if (rc) return rc;
+    }
+    if (!need_l1) return B200SEG_OK;
+    rc = conv3x3_dgrad(dZ2, N, h, w, ndf2, ndf2, Wb2, ndf1, 1, A1, slope, dZ1, ndf1, nullptr, st, gb1 ? scratch : nullptr,
+                       gb1 ? scratch_bytes : 0, gb1);
+    if (rc) return rc;
+    if (gw1) {
+      float* outs[1] = {gw1};
+      const int parts[1] = {ndf1};
+      rc = conv3x3_wgrad(dZ1, ndf1, ndf1, Xp, Cin, Cin, N, h, w, 1, 0, scratch, scratch_bytes, outs, parts, 1, st);
+      if (rc) return rc;
+    }
+    if (need_x)
+      rc = conv3x3_dgrad(dZ1, N, h, w, ndf1, ndf1, Wb1, Cin, 1, nullptr, slope, gx_bf16_nhwc, Cin, gx_f32_nchw, st, nullptr, 0, nullptr);
+    return rc;
+  });
+}
+
 void b200seg_set_step_graphs(int on) {
   step_graphs_drop();
   g_step_graphs_on = on ? 1 : 0;

@@ -57,8 +57,10 @@ class PixelDiscriminator(nn.Module):
 
     def logits(self, x):
         """Low-resolution logits [N,2C,h,w] = cat(cls1(D(x)), cls2(D(x)))  (discriminator.py:45-47)."""
+        # training mode: the weights are packed INSIDE the one-call forward on every call (version counters miss ``.data`` /
+        # raw-pointer / graph-replay writes); eval mode reuses the pack cached on (data_ptr, _version)
         return ops.pixel_discriminator_logits(x, *self._params(), slope=self.D[1].negative_slope,
-                                              packed=self._packed_weights())
+                                              packed=None if self.training else self._packed_weights())
 
     def forward(self, x, size=None):
         from . import lazy as _lazy

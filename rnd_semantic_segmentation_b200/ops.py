@@ -204,18 +204,21 @@ def pack_discriminator_weights(w1, w2, wc1, wc2, bc1, bc2):
 
 
 class _PixelDiscriminatorFn(torch.autograd.Function):
-    """cat(cls1(mid), cls2(mid)) with mid = LReLU(conv(LReLU(conv(x))))  (discriminator.py:34-47), fp32 NCHW [N,2C,h,w]."""
+    """cat(cls1(mid), cls2(mid)) with mid = LReLU(conv(LReLU(conv(x))))  (discriminator.py:34-47), fp32 NCHW [N,2C,h,w].
+    ONE foreign call per direction (b200seg_disc_forward / _backward, graph-replayed in a steady-state loop)."""
 
     @staticmethod
     def forward(ctx, x, slope, packed, w1, b1, w2, b2, wc1, bc1, wc2, bc2):
         N, Cin, h, w = x.shape
-        if packed is None:
-            packed = pack_discriminator_weights(w1, w2, wc1, wc2, bc1, bc2)
-        (Wf1, Wb1), (Wf2, Wb2), (Wf3, Wb3), b3 = packed
-        Xp = _pixel_major_bf16(x.detach()).view(N, h, w, Cin)
-        A1 = _lib.conv3x3_forward(Xp, Wf1, None if b1 is None else b1.detach(), slope)
-        A2 = _lib.conv3x3_forward(A1, Wf2, None if b2 is None else b2.detach(), slope)
-        out = _lib.conv3x3_forward(A2, Wf3, b3, None, out_f32_nchw=True)
+        xd = x.detach()
+        if not xd.is_cuda:
+            raise _lib.B200SegError("PixelDiscriminator: expected CUDA features (b200seg has no CPU fallback)")
+        if xd.dtype == torch.bfloat16 or _PACK_CACHE_SLOTS > 0:
+            xk, x_kind = _pixel_major_bf16(xd).view(N, h, w, Cin), 1          # bf16 channels_last input is taken zero-copy
+        else:
+            xk, x_kind = (xd if xd.dtype == torch.float32 else xd.float()).contiguous(), 0
+        out, Xp, A1, A2, packed = _lib.disc_forward(xk, x_kind, (N, Cin, h, w), (w1, w2, wc1, wc2), (b1, b2, bc1, bc2), slope, packed)
+        (_, Wb1), (_, Wb2), (_, Wb3), _ = packed
         ctx.meta = (float(slope), x.dtype, int(wc1.shape[0]))
         ctx.save_for_backward(Xp, A1, A2, Wb1, Wb2, Wb3)
         return out
@@ -225,35 +228,13 @@ class _PixelDiscriminatorFn(torch.autograd.Function):
         Xp, A1, A2, Wb1, Wb2, Wb3 = ctx.saved_tensors
         slope, x_dtype, C = ctx.meta
         need = ctx.needs_input_grad          # x, slope, packed, w1, b1, w2, b2, wc1, bc1, wc2, bc2
-        G3 = _lib.nchw_to_nhwc_bf16(grad_out.detach().float().contiguous(), Wb3.shape[2])
-        gwc1 = gwc2 = gbc1 = gbc2 = gw2 = gb2 = gw1 = gb1 = gx = None
-        if need[8] or need[10]:
-            b3 = _lib.nhwc_bf16_colsum(G3, 2 * C)
-            gbc1, gbc2 = (b3[:C] if need[8] else None), (b3[C:] if need[10] else None)
-        if need[7] or need[9]:
-            gwc1, gwc2 = _lib.conv3x3_wgrad(G3, A2, [C, C])
-            gwc1, gwc2 = (gwc1 if need[7] else None), (gwc2 if need[9] else None)
-        if any(need[i] for i in (0, 3, 4, 5, 6)):
-            if need[6]:        # bias gradient = column sums of dZ2, accumulated in the dgrad epilogue
-                dZ2, gb2 = _lib.conv3x3_dgrad(G3, Wb3, mask=A2, slope=slope, want_colsum=True)
-            else:
-                dZ2 = _lib.conv3x3_dgrad(G3, Wb3, mask=A2, slope=slope)
-            if need[5]:
-                gw2, = _lib.conv3x3_wgrad(dZ2, A1, [dZ2.shape[3]])
-            if any(need[i] for i in (0, 3, 4)):
-                if need[4]:
-                    dZ1, gb1 = _lib.conv3x3_dgrad(dZ2, Wb2, mask=A1, slope=slope, want_colsum=True)
-                else:
-                    dZ1 = _lib.conv3x3_dgrad(dZ2, Wb2, mask=A1, slope=slope)
-                if need[3]:
-                    gw1, = _lib.conv3x3_wgrad(dZ1, Xp, [dZ1.shape[3]])
-                if need[0]:
-                    if x_dtype == torch.bfloat16:          # seam format: bf16 channels_last gradient straight from the epilogue
-                        gx = _lib.conv3x3_dgrad(dZ1, Wb1).permute(0, 3, 1, 2)
-                    else:
-                        gx = _lib.conv3x3_dgrad(dZ1, Wb1, out_f32_nchw=True)
-                        if gx.dtype != x_dtype:
-                            gx = gx.to(x_dtype)
+        go = grad_out.detach()
+        if go.dtype != torch.float32:
+            go = go.float()
+        gx, gw1, gb1, gw2, gb2, gwc1, gbc1, gwc2, gbc2 = _lib.disc_backward(
+            go.contiguous(), Xp, A1, A2, Wb1, Wb2, Wb3, C, slope, (need[0],) + tuple(need[3:11]), x_bf16=(x_dtype == torch.bfloat16))
+        if gx is not None and gx.dtype != x_dtype:
+            gx = gx.to(x_dtype)
         return gx, None, None, gw1, gb1, gw2, gb2, gwc1, gbc1, gwc2, gbc2
 
 

@@ -921,3 +921,108 @@ def test_graph_cache_turns_itself_off_when_addresses_keep_changing(lib):
         assert captures <= 64, (replays, captures)
     finally:
         lib.set_step_graphs(True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# one foreign call per direction for the PixelDiscriminator conv stack (b200seg_disc_forward / _backward)
+# ---------------------------------------------------------------------------------------------------------------------------
+def _disc_separate_entries(lib, D, x, grad_out, slope=0.2):
+    """The same stack through the separate C-ABI entries (what ops._PixelDiscriminatorFn issued before the one-call entries)."""
+    from rnd_semantic_segmentation_b200 import ops
+    w1, b1, w2, b2, wc1, bc1, wc2, bc2 = [p.detach() for p in D._params()]
+    C = wc1.shape[0]
+    (l1, l2, l3), b3 = lib.conv3x3_pack_weights_stack([[w1], [w2], [wc1, wc2]], bias_parts=[bc1, bc2], bias_lens=[C, C])
+    (Wf1, Wb1), (Wf2, Wb2), (Wf3, Wb3) = l1, l2, l3
+    N, Cin, h, w = x.shape
+    Xp = ops._pixel_major_bf16(x.detach()).view(N, h, w, Cin)
+    A1 = lib.conv3x3_forward(Xp, Wf1, b1, slope)
+    A2 = lib.conv3x3_forward(A1, Wf2, b2, slope)
+    out = lib.conv3x3_forward(A2, Wf3, b3, None, out_f32_nchw=True)
+    G3 = lib.nchw_to_nhwc_bf16(grad_out.float().contiguous(), Wb3.shape[2])
+    gb3 = lib.nhwc_bf16_colsum(G3, 2 * C)
+    gwc1, gwc2 = lib.conv3x3_wgrad(G3, A2, [C, C])
+    dZ2, gb2 = lib.conv3x3_dgrad(G3, Wb3, mask=A2, slope=slope, want_colsum=True)
+    gw2, = lib.conv3x3_wgrad(dZ2, A1, [dZ2.shape[3]])
+    dZ1, gb1 = lib.conv3x3_dgrad(dZ2, Wb2, mask=A1, slope=slope, want_colsum=True)
+    gw1, = lib.conv3x3_wgrad(dZ1, Xp, [dZ1.shape[3]])
+    if x.dtype == torch.bfloat16:
+        gx = lib.conv3x3_dgrad(dZ1, Wb1).permute(0, 3, 1, 2)
+    else:
+        gx = lib.conv3x3_dgrad(dZ1, Wb1, out_f32_nchw=True)
+    return out, gx, [gw1, gb1, gw2, gb2, gwc1, gb3[:C], gwc2, gb3[C:]]
+
+
+@pytest.mark.parametrize("n,cin,ndf,C,h,w,xdt", [(2, 256, 64, 19, 33, 65, torch.float32), (1, 2048, 256, 19, 64, 128, torch.float32),
+                                                (3, 64, 32, 2, 44, 44, torch.float32), (2, 128, 64, 19, 20, 27, torch.bfloat16)])
+def test_one_call_discriminator_equals_the_separate_entries(lib, n, cin, ndf, C, h, w, xdt):
+    """PixelDiscriminator.logits + backward (ONE C-ABI call each way, graph-replayed from the third iteration on) == the same kernels
+    through the separate entries: logits, dX and all eight parameter gradients bit-identical, with graphs on and off."""
+    import rnd_semantic_segmentation_b200 as b200
+    torch.manual_seed(51)
+    D = b200.PixelDiscriminator(cin, ndf, num_classes=C).cuda()
+    g = torch.Generator().manual_seed(52)
+    x = torch.relu(torch.randn(n, cin, h, w, generator=g)).cuda()
+    if xdt == torch.bfloat16:
+        x = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    go = torch.randn(n, 2 * C, h, w, generator=g).cuda()
+    want_out, want_gx, want_gp = _disc_separate_entries(lib, D, x, go)
+    for graphs in (False, True):
+        lib.set_step_graphs(graphs)
+        try:
+            for it in range(4):
+                for p in D.parameters():
+                    p.grad = None
+                xg = x.detach().requires_grad_(True)
+                out = D.logits(xg)
+                out.backward(go)
+                assert torch.equal(out.detach(), want_out), (graphs, it)
+                assert xg.grad.dtype == xdt and torch.equal(xg.grad.float(), want_gx.float()), (graphs, it)
+                for p, wgt in zip(D._params(), want_gp):
+                    assert torch.equal(p.grad, wgt), (graphs, it)
+                del out, xg
+            if graphs:
+                replays, captures = lib.step_graph_stats()
+                assert captures >= 2 and replays >= 2, (replays, captures)
+        finally:
+            lib.set_step_graphs(True)
+
+
+def test_one_call_discriminator_partial_needs_and_eval_pack(lib):
+    """Frozen discriminator (only dX wanted: aspp_fada.py:110-113 with the tip of INTEGRATION.md), detached features (only parameter
+    gradients: :119-125), and eval mode (the cached weight pack is reused, invalidate_packed() after a .data write)."""
+    import rnd_semantic_segmentation_b200 as b200
+    torch.manual_seed(53)
+    n, cin, ndf, C, h, w = 2, 128, 64, 19, 17, 23
+    D = b200.PixelDiscriminator(cin, ndf, num_classes=C).cuda()
+    g = torch.Generator().manual_seed(54)
+    x = torch.relu(torch.randn(n, cin, h, w, generator=g)).cuda()
+    go = torch.randn(n, 2 * C, h, w, generator=g).cuda()
+    want_out, want_gx, want_gp = _disc_separate_entries(lib, D, x, go)
+    # detached features
+    D.logits(x).backward(go)
+    for p, wgt in zip(D._params(), want_gp):
+        assert torch.equal(p.grad, wgt)
+    # frozen discriminator
+    for p in D.parameters():
+        p.requires_grad_(False)
+        p.grad = None
+    xg = x.clone().requires_grad_(True)
+    D.logits(xg).backward(go)
+    assert torch.equal(xg.grad, want_gx) and all(p.grad is None for p in D.parameters())
+    # only the last layer trainable
+    D.cls1.weight.requires_grad_(True)
+    D.cls1.bias.requires_grad_(True)
+    D.logits(x).backward(go)
+    assert torch.equal(D.cls1.weight.grad, want_gp[4]) and torch.equal(D.cls1.bias.grad, want_gp[5])
+    assert D.D[0].weight.grad is None and D.cls2.weight.grad is None
+    # eval mode: cached pack; a .data write needs invalidate_packed()
+    D.eval()
+    with torch.no_grad():
+        assert torch.equal(D.logits(x), want_out)
+        D.cls1.bias.data.add_(1.0)
+        stale = D.logits(x)
+        assert torch.equal(stale, want_out)                        # documented: version counters miss .data writes in eval mode
+        D.invalidate_packed()
+        fresh = D.logits(x)
+        assert not torch.equal(fresh, want_out)
+        assert torch.allclose(fresh[:, :C] - want_out[:, :C], torch.ones_like(fresh[:, :C]), atol=1e-5)
