@@ -34,16 +34,38 @@ struct P2PParams {
 };
 
 // put: flip the flag the peer waits on from 0 to 1 (spin while a previous signal is still unconsumed); wait: consume own flag.
+// A peer that never arrives (crashed rank, mismatched call sequence) must not hang the GPU: after P2P_TIMEOUT_NS of spinning the
+// kernel traps, which surfaces as a CUDA error on the host instead of a stuck device.
+constexpr unsigned long long P2P_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+__device__ __forceinline__ unsigned long long p2p_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void p2p_put(unsigned* addr) {
   unsigned old;
+  unsigned long long t0 = 0;
+  unsigned spins = 0;
   do {
     asm volatile("atom.release.sys.global.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "l"(addr) : "memory");
+    if (old != 0u && (++spins & 1023u) == 0u) {
+      const unsigned long long t = p2p_now_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > P2P_TIMEOUT_NS) __trap();
+    }
   } while (old != 0u);
 }
 __device__ __forceinline__ void p2p_wait(unsigned* addr) {
   unsigned old;
+  unsigned long long t0 = 0;
+  unsigned spins = 0;
   do {
     asm volatile("atom.acquire.sys.global.cas.b32 %0, [%1], 1, 0;" : "=r"(old) : "l"(addr) : "memory");
+    if (old != 1u && (++spins & 1023u) == 0u) {
+      const unsigned long long t = p2p_now_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > P2P_TIMEOUT_NS) __trap();
+    }
   } while (old != 1u);
 }
 // every CTA b of every rank meets CTA b of every other rank
