@@ -307,15 +307,15 @@ __global__ void __launch_bounds__(256) build_gprime_t_kernel(const __nv_bfloat16
 
 // Same copy with 16-byte stores: one thread per 8 pixels (requires w % 8 == 0 so a vector never straddles an image row,
 // and even dx so the four shifted source words are 4-byte aligned).
-constexpr int GPT8_ITERS = 2;                // 16-byte vectors per thread; a block covers 256 * 8 * GPT8_ITERS pixels
+constexpr int GPT8_ITERS = 4;                // 16-byte vectors per thread; a block covers 256 * 8 * GPT8_ITERS pixels
 __global__ void __launch_bounds__(256) build_gprime_t8_kernel(const __nv_bfloat16* __restrict__ gOc, TapTable tt, int C, int h, int w,
                                                               int N, long long Ppitch, __nv_bfloat16* __restrict__ Gp) {
   const int j = blockIdx.y;
   const int t = j / C, c = j - t * C;
   const int hw = h * w;
-  const long long P = (long long)N * hw;
-  long long p0 = (long long)blockIdx.x * (2048 * GPT8_ITERS) + threadIdx.x * 8;
-  uint4* out = reinterpret_cast<uint4*>(Gp + (long long)j * Ppitch);
+  const int P = N * hw;                                  // (< 2^31: checked by the host)
+  int p0 = (int)blockIdx.x * (2048 * GPT8_ITERS) + (int)threadIdx.x * 8;      // 32-bit index math: the per-thread set-up (three
+  uint4* out = reinterpret_cast<uint4*>(Gp + (long long)j * Ppitch);          // divisions) was most of this kernel's instructions
   if (t >= tt.n_taps) {
 #pragma unroll
     for (int it = 0; it < GPT8_ITERS; ++it, p0 += 2048)
@@ -324,8 +324,8 @@ __global__ void __launch_bounds__(256) build_gprime_t8_kernel(const __nv_bfloat1
   }
   const int dy = tt.dy[t], dx = tt.dx[t];
   const unsigned short* planes = reinterpret_cast<const unsigned short*>(gOc);
-  int n = (int)(p0 / hw);
-  int sidx = (int)(p0 - (long long)n * hw);
+  int n = p0 / hw;
+  int sidx = p0 - n * hw;
   int y = sidx / w, x = sidx - y * w;
   const int step_y = 2048 / w, step_x = 2048 - step_y * w;
 #pragma unroll
@@ -579,6 +579,7 @@ int aspp_backward_packed(const void* gOt_in, const void* Xp, const void* WpT, co
   if (splits < 1) splits = 1;
   B200SEG_CHECK_ARG(scratch_bytes >= aspp_bwd_scratch_bytes(N, Cin, C, h, w, R, splits), "aspp_backward: scratch too small");
   const long long P = (long long)N * h * w;
+  B200SEG_CHECK_ARG(P + 2048 * 16 < (1LL << 31), "aspp_backward: too many pixels");
   const int NJ = aspp_nj(C, R);
   const int hw = h * w;
   __nv_bfloat16 *gOt_own, *Gp;
